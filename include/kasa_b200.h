@@ -1,0 +1,195 @@
+/*
+ * kasa_b200.h — C ABI of libkasa_b200.so: kASA's `identify` hot path and the `build`
+ * index-sort path as hand-written sm_100a CUDA kernels.
+ *
+ * kASA (the reference) has no plugin / FFI interface; it is a monolithic C++ CLI.
+ * The entry points below are what a kASA maintainer would bind in place of the
+ * reference's own call sites (cited per function; paths relative to
+ * /root/reference/source).  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success
+ * and a negative kasa_status otherwise; no exception crosses the boundary;
+ * kasa_last_error(ctx) returns the message of the last failure on that context
+ * (the reference throws runtime_error and main prints "ERROR: <what>", main.cpp:1717-1720).
+ * The caller owns all host buffers, the library owns all device memory.  Calls on
+ * one context are not re-entrant (the reference's driver thread is the only caller
+ * too: Compare.hpp:3100-3440).  The library never falls back to a CPU path: without
+ * a CUDA device every compute entry point fails with KASA_ERR_CUDA.
+ */
+#ifndef KASA_B200_H
+#define KASA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KASA_B200_ABI_VERSION 1
+
+typedef enum {
+    KASA_OK = 0,
+    KASA_ERR_ARG = -1,        /* invalid argument / unsupported parameter combination */
+    KASA_ERR_CUDA = -2,       /* CUDA runtime error (no device, launch failure, ...) */
+    KASA_ERR_NOMEM = -3,      /* device or host allocation failed / workspace too small */
+    KASA_ERR_STATE = -4,      /* call order violated (e.g. identify before index load) */
+    KASA_ERR_DATA = -5,       /* inconsistent input (taxid missing from content, unsorted index, ...) */
+    KASA_ERR_INTERNAL = -6    /* kernel watchdog tripped (would have hung) */
+} kasa_status;
+
+typedef struct kasa_ctx kasa_ctx;
+
+/* Where a buffer handed to the library lives. */
+#define KASA_MEM_HOST   0
+#define KASA_MEM_DEVICE 1
+
+/* Encoding of sequence data handed to the library. */
+#define KASA_SEQ_ASCII   0    /* one char per base, as read from FASTA/FASTQ                          */
+#define KASA_SEQ_PACKED2 1    /* 2 bits per base (A0 C1 T2 G3, kASA.hpp:70-75), 16 bases per uint32,
+                                 LSB first, plus a 1-bit-per-base non-ACGT plane (32 bases per uint32) */
+
+/* Per-read scoring mode (Compare.hpp:516-532 scoreMatchNonAVX is the spec). */
+#define KASA_SCORE_NONE  0    /* profile only: counts, no per-read scores (kASA without -q)            */
+#define KASA_SCORE_FAST  1    /* fp32, canonical order (k-mer position in read, k ascending);
+                                 deterministic and batch independent; <= 4e-6 rel. of the reference    */
+#define KASA_SCORE_EXACT 2    /* fp32 in the reference's own flush order (Compare.hpp:917-955,
+                                 1032-1041) — bit-exact with `kASA -n 1` when the batch is the same     */
+
+typedef struct {
+    int32_t device;           /* CUDA device ordinal                                                   */
+    int32_t highest_k;        /* index width: 12 (64-bit k-mers) or 25 (128-bit); kASA _iHighestK      */
+    int32_t k_high, k_low;    /* -k <high> <low> (main.cpp:372-385); k_low >= 1, k_high <= highest_k   */
+    int32_t frames;           /* 3 = forward frames (default), 6 = --six; 1 (--one) is not supported   */
+    int32_t score_mode;       /* KASA_SCORE_*                                                          */
+    uint64_t max_batch_kmers; /* workspace sizing: largest sum of kMerCount per batch                  */
+    uint32_t max_batch_seqs;  /* largest number of sequences (reads/mates or build pieces) per batch   */
+    uint64_t max_batch_bases; /* largest number of bases per batch                                     */
+    const uint8_t *codon_table; /* 512-byte table indexed c0<<6|c1<<3|c2 (kASA.hpp:621-667; `-a` file,
+                                 kASA.hpp:579-615) or NULL for the built-in standard code               */
+} kasa_params;
+
+/* --------------------------------------------------------------------------------------------------- */
+/* context                                                                                              */
+
+/* Replaces: Compare<...> kASAObj construction (main.cpp:1023/1070) resp. Read<...> (main.cpp:664).     */
+int kasa_ctx_create(const kasa_params *params, kasa_ctx **out);
+void kasa_ctx_destroy(kasa_ctx *ctx);
+const char *kasa_last_error(const kasa_ctx *ctx);   /* never NULL; ctx may be NULL (creation errors)   */
+int kasa_abi_version(void);
+
+/* Run all kernels of this context on an existing CUDA stream (cudaStream_t passed as void*), e.g.
+ * torch's current stream so that torch.cuda.Event timing sees them.  Default: a private stream.       */
+int kasa_ctx_set_stream(kasa_ctx *ctx, void *cuda_stream);
+int kasa_ctx_synchronize(kasa_ctx *ctx);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t kasa_ctx_launch_count(const kasa_ctx *ctx);
+
+/* --------------------------------------------------------------------------------------------------- */
+/* index                                                                                                */
+
+/* Replaces: Compare::index.loadIndex / loadTrie / loadContentAndFrequencyFiles (Compare.hpp:96-337,
+ * main.cpp:1050-1060).  `entries` = the index file bytes: n records of packedBigPair {u64 kmer, u32 taxid}
+ * (12 B, packedPairs.hpp:107-111) when bits == 64, or packedLargePair {u64 low, u64 high, u32 taxid}
+ * (20 B, :132-136) when bits == 128; must be sorted by (kmer, taxid) as `kASA build` writes it.
+ * taxid_of_idx[0] is the "non_unique" pseudo taxon (0); taxid_of_idx[i] the taxid of content line i
+ * (Compare.hpp:124-147).  n_taxa (incl. index 0) <= 65535.  The prefix-table file (`_trie`) is NOT an
+ * input: the lookup kernel searches the HBM-resident index directly.  The library copies
+ * what it needs; the caller may free its buffers after return.                                         */
+int kasa_index_load(kasa_ctx *ctx, const void *entries, uint64_t n, int bits,
+                    const uint32_t *taxid_of_idx, uint32_t n_taxa);
+
+/* Adopt the index just built on this context by kasa_build_finish (stays in HBM, no host round trip).  */
+int kasa_index_from_build(kasa_ctx *ctx, const uint32_t *taxid_of_idx, uint32_t n_taxa);
+
+uint64_t kasa_index_size(const kasa_ctx *ctx);
+
+/* --------------------------------------------------------------------------------------------------- */
+/* identify                                                                                             */
+
+typedef struct {
+    uint32_t n_reads;         /* read ids 0..n_reads-1 are batch local (Read.hpp:1107)                  */
+    uint32_t n_seqs;          /* sequences; paired-end mates are consecutive and share a read id        */
+    int32_t  format;          /* KASA_SEQ_ASCII | KASA_SEQ_PACKED2                                      */
+    int32_t  location;        /* KASA_MEM_HOST | KASA_MEM_DEVICE (applies to all pointers below)        */
+    const void *bases;        /* ASCII: chars, raw as in the file (cleaning Read.hpp:657-675 happens on
+                                 device). PACKED2: uint32 words                                         */
+    const uint32_t *nmask;    /* PACKED2 only: non-ACGT plane                                           */
+    const uint64_t *seq_start;/* [n_seqs] first base of each sequence (PACKED2: multiple of 32)         */
+    const uint32_t *seq_len;  /* [n_seqs] bases                                                         */
+    const uint32_t *read_first_seq; /* [n_reads+1] first sequence of each read, or NULL = one seq/read  */
+} kasa_read_batch;
+
+typedef struct {
+    uint64_t n_kmers;         /* out: sum of kMerCount = this batch's part of iNumberOfkMersInInput
+                                 (Compare.hpp:3109-3122)                                                */
+    float *scores;            /* in: caller buffer [n_reads][n_taxa] (row = Non_contiguousArray row,
+                                 Utilities.hpp:592-636) or NULL; filled unless score_mode == NONE       */
+    int32_t scores_location;  /* KASA_MEM_HOST | KASA_MEM_DEVICE                                        */
+    float gpu_ms;             /* out: device time of this batch's kernels (CUDA events)                 */
+} kasa_batch_result;
+
+/* Replaces, per batch: Read::convertAndSort (Read.hpp:763-827) + Compare::sortInputAndCheckInvalidkMers_sta
+ * (Compare.hpp:1074-1260) + Compare::compareWithDatabase (Compare.hpp:679-1069) + the score matrix
+ * (Compare.hpp:3192).  Counts are accumulated inside ctx across batches.                               */
+int kasa_identify_batch(kasa_ctx *ctx, const kasa_read_batch *in, kasa_batch_result *out);
+
+/* Replaces: the per-thread count reduction (Compare.hpp:3445-3454).  count_all / count_unique are
+ * [numK][n_taxa], level 0 = k_high (kASA _aOfK, kASA.hpp:299-302).  Resets the accumulators
+ * (Compare.hpp:3748-3752).                                                                             */
+int kasa_identify_finish(kasa_ctx *ctx, double *count_all, uint64_t *count_unique, uint64_t *n_kmers_total);
+
+/* --------------------------------------------------------------------------------------------------- */
+/* build                                                                                                */
+
+typedef struct {
+    uint32_t n_seqs;          /* prepared strings: cleaned ('Z'), marker 'X'*3*(K-1) already appended where
+                                 the reference appends it (Read.hpp:2323-2333, 2529-2538)               */
+    int32_t  location;
+    const char *bases;        /* ASCII incl. 'X' / 'Z'                                                  */
+    const uint64_t *seq_start;/* [n_seqs]                                                               */
+    const uint32_t *seq_len;  /* [n_seqs]                                                               */
+    const uint32_t *taxid;    /* [n_seqs]                                                               */
+} kasa_seq_batch;
+
+/* Replaces: Read::dnaTokMers + Build::addToInt (Read.hpp:1991-2139, Build.hpp:116-130).                */
+int kasa_build_push(kasa_ctx *ctx, const kasa_seq_batch *in);
+
+/* Replaces: Build::IntToExtPart + mergeTemporaries (Build.hpp:305-477), Trie::SaveToStxxlVec
+ * (Trie.hpp:366-394).  Sorts by (kmer, taxid), removes duplicates, run-length encodes the 6-letter
+ * prefixes.  Outputs the counts; fetch the data with kasa_build_fetch.                                  */
+int kasa_build_finish(kasa_ctx *ctx, uint64_t *n_entries, uint64_t *n_trie);
+
+/* Copy out the built index in file layout: entries = packedBigPair / packedLargePair records,
+ * trie = packedBigPairTrie {u64 count, u32 prefix30} records (packedPairs.hpp:157-166).  Either may be
+ * NULL.  Replaces the STXXL export (Build.hpp:457-470).                                                 */
+int kasa_build_fetch(kasa_ctx *ctx, void *entries, void *trie);
+
+/* Replaces: kASA::GetFrequencyK (kASA.hpp:449-575).  freq is [n_taxa][highest_k]; column j counts the
+ * entries of that taxon whose letter at position highest_k - j is not '^' (30).                        */
+int kasa_build_frequency(kasa_ctx *ctx, const uint32_t *taxid_of_idx, uint32_t n_taxa, uint64_t *freq);
+
+/* --------------------------------------------------------------------------------------------------- */
+/* stage-level entry points (parity tests drive each kernel against the oracle through these)           */
+
+/* k-mers of a read batch in emission order (Read.hpp:84-220): kmers_lo/hi [n_kmers], ids = read id.
+ * Buffers are host memory sized max_batch_kmers.                                                       */
+int kasa_dbg_extract(kasa_ctx *ctx, const kasa_read_batch *in, uint64_t *kmers_lo, uint64_t *kmers_hi,
+                     uint32_t *read_id, uint64_t *n_kmers);
+
+/* LSD radix sort of (key, value) pairs on bits [bit_lo, bit_hi) of the key; host buffers, in place.    */
+int kasa_dbg_sort_pairs(kasa_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t n, int bit_lo, int bit_hi);
+
+/* Synthetic workload generators (device side of kasa_b200/synth.py; used by bench.py to create the
+ * C2 workload in HBM).  kasa_synth_build_reference pushes `n_taxa` genomes of `genome_len` bases
+ * (taxid 1000+t) through the build path.  kasa_synth_reads writes n_reads x read_len ASCII bases.       */
+int kasa_synth_build_reference(kasa_ctx *ctx, uint64_t seed, uint32_t n_taxa, uint64_t genome_len);
+int kasa_synth_reads(kasa_ctx *ctx, uint64_t genome_seed, uint64_t read_seed, uint64_t first_read,
+                     uint32_t n_reads, uint32_t n_taxa, uint64_t genome_len, uint32_t read_len,
+                     uint32_t subst_ppm, uint32_t n_ppm, char *out, int out_location);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KASA_B200_H */

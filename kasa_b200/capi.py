@@ -1,0 +1,286 @@
+"""ctypes binding of include/kasa_b200.h plus a small host-side wrapper.
+
+The wrapper mirrors the reference's call sites for the path:
+  Context.load_index        <- Compare::index.loadIndex / loadContentAndFrequencyFiles (Compare.hpp:96-337)
+  Context.identify_batch    <- convertAndSort + sortInputAndCheckInvalidkMers_sta + compareWithDatabase per batch
+  Context.identify_finish   <- count reduction (Compare.hpp:3445-3454)
+  Context.build_push/finish <- dnaTokMers/addToInt, IntToExtPart/mergeTemporaries/SaveToStxxlVec, GetFrequencyK
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+MEM_HOST, MEM_DEVICE = 0, 1
+SEQ_ASCII, SEQ_PACKED2 = 0, 1
+SCORE_NONE, SCORE_FAST, SCORE_EXACT = 0, 1, 2
+
+REC64 = np.dtype([("lo", "<u8"), ("tax", "<u4")])                     # packedBigPair, packedPairs.hpp:107-111
+REC128 = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("tax", "<u4")])     # packedLargePair, packedPairs.hpp:132-136
+TRIE = np.dtype([("count", "<u8"), ("prefix", "<u4")])                # packedBigPairTrie, packedPairs.hpp:157-166
+
+EXPORTS = [
+    "kasa_abi_version", "kasa_ctx_create", "kasa_ctx_destroy", "kasa_last_error", "kasa_ctx_set_stream",
+    "kasa_ctx_synchronize", "kasa_ctx_launch_count", "kasa_index_load", "kasa_index_from_build", "kasa_index_size",
+    "kasa_identify_batch", "kasa_identify_finish", "kasa_build_push", "kasa_build_finish", "kasa_build_fetch",
+    "kasa_build_frequency", "kasa_dbg_extract", "kasa_dbg_sort_pairs", "kasa_synth_build_reference", "kasa_synth_reads",
+]
+
+
+class KasaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("kasa_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CParams(C.Structure):
+    _fields_ = [("device", C.c_int32), ("highest_k", C.c_int32), ("k_high", C.c_int32), ("k_low", C.c_int32),
+                ("frames", C.c_int32), ("score_mode", C.c_int32), ("max_batch_kmers", C.c_uint64),
+                ("max_batch_seqs", C.c_uint32), ("max_batch_bases", C.c_uint64), ("codon_table", C.c_void_p)]
+
+
+class CReadBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_seqs", C.c_uint32), ("format", C.c_int32), ("location", C.c_int32),
+                ("bases", C.c_void_p), ("nmask", C.c_void_p), ("seq_start", C.c_void_p), ("seq_len", C.c_void_p),
+                ("read_first_seq", C.c_void_p)]
+
+
+class CBatchResult(C.Structure):
+    _fields_ = [("n_kmers", C.c_uint64), ("scores", C.c_void_p), ("scores_location", C.c_int32), ("gpu_ms", C.c_float)]
+
+
+class CSeqBatch(C.Structure):
+    _fields_ = [("n_seqs", C.c_uint32), ("location", C.c_int32), ("bases", C.c_void_p), ("seq_start", C.c_void_p),
+                ("seq_len", C.c_void_p), ("taxid", C.c_void_p)]
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libkasa_b200.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """dlopen libkasa_b200.so; raises if it has not been built (python __graft_entry__.py / make -C kasa_b200/csrc)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise KasaError(-2, "libkasa_b200.so is not built (run `make -C kasa_b200/csrc`); there is no CPU fallback")
+    L = C.CDLL(path)
+    L.kasa_last_error.restype = C.c_char_p
+    L.kasa_last_error.argtypes = [C.c_void_p]
+    L.kasa_ctx_create.argtypes = [C.POINTER(CParams), C.POINTER(C.c_void_p)]
+    L.kasa_ctx_destroy.argtypes = [C.c_void_p]
+    L.kasa_ctx_destroy.restype = None
+    L.kasa_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.kasa_ctx_synchronize.argtypes = [C.c_void_p]
+    L.kasa_ctx_launch_count.argtypes = [C.c_void_p]
+    L.kasa_ctx_launch_count.restype = C.c_uint64
+    L.kasa_index_size.argtypes = [C.c_void_p]
+    L.kasa_index_size.restype = C.c_uint64
+    L.kasa_index_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32]
+    L.kasa_index_from_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.kasa_identify_batch.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.POINTER(CBatchResult)]
+    L.kasa_identify_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.kasa_build_push.argtypes = [C.c_void_p, C.POINTER(CSeqBatch)]
+    L.kasa_build_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.kasa_build_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.kasa_build_frequency.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.kasa_dbg_extract.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_uint64)]
+    L.kasa_dbg_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+    L.kasa_synth_build_reference.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64]
+    L.kasa_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64,
+                                   C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
+    _LIB = L
+    return L
+
+
+@dataclass
+class Params:
+    device: int = 0
+    highest_k: int = 12
+    k_high: int = 12
+    k_low: int = 7
+    frames: int = 3
+    score_mode: int = SCORE_FAST
+    max_batch_kmers: int = 1 << 22
+    max_batch_seqs: int = 1 << 16
+    max_batch_bases: int = 1 << 24
+    codon_table: np.ndarray | None = None
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One GPU context (one per process / rank)."""
+
+    def __init__(self, params: Params):
+        self.lib = load_library()
+        self.params = params
+        self._table = None
+        cp = CParams(params.device, params.highest_k, params.k_high, params.k_low, params.frames, params.score_mode,
+                     params.max_batch_kmers, params.max_batch_seqs, params.max_batch_bases, None)
+        if params.codon_table is not None:
+            self._table = np.ascontiguousarray(params.codon_table, dtype=np.uint8)
+            cp.codon_table = self._table.ctypes.data
+        h = C.c_void_p()
+        rc = self.lib.kasa_ctx_create(C.byref(cp), C.byref(h))
+        if rc != 0:
+            raise KasaError(rc, self.lib.kasa_last_error(None).decode())
+        self.h = h
+        self.n_taxa = 0
+        self.num_k = params.k_high - params.k_low + 1
+        self.wide = params.highest_k > 12
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kasa_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise KasaError(rc, self.lib.kasa_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.kasa_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.kasa_ctx_synchronize(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.kasa_ctx_launch_count(self.h))
+
+    @property
+    def index_size(self) -> int:
+        return int(self.lib.kasa_index_size(self.h))
+
+    # ---------------------------------------------------------------- index
+    def load_index(self, records: np.ndarray, taxid_of_idx: np.ndarray):
+        records = np.ascontiguousarray(records)
+        bits = 128 if records.dtype.itemsize == 20 else 64
+        tax = np.ascontiguousarray(taxid_of_idx, dtype=np.uint32)
+        self._check(self.lib.kasa_index_load(self.h, _ptr(records), len(records), bits, _ptr(tax), len(tax)))
+        self.n_taxa = len(tax)
+
+    def index_from_build(self, taxid_of_idx: np.ndarray):
+        tax = np.ascontiguousarray(taxid_of_idx, dtype=np.uint32)
+        self._check(self.lib.kasa_index_from_build(self.h, _ptr(tax), len(tax)))
+        self.n_taxa = len(tax)
+
+    # ---------------------------------------------------------------- identify
+    @staticmethod
+    def pack_reads(seqs: list[bytes]):
+        """Concatenate raw sequences -> (ascii u8 array, seq_start u64, seq_len u32)."""
+        lens = np.array([len(s) for s in seqs], dtype=np.uint32)
+        starts = np.zeros(len(seqs), dtype=np.uint64)
+        if len(seqs) > 1:
+            starts[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+        data = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if seqs else np.zeros(0, np.uint8)
+        return data, starts, lens
+
+    def _read_batch(self, seqs, read_first_seq):
+        data, starts, lens = self.pack_reads(seqs) if isinstance(seqs, list) else seqs
+        n_seqs = len(lens)
+        first = None
+        n_reads = n_seqs
+        if read_first_seq is not None:
+            first = np.ascontiguousarray(read_first_seq, dtype=np.uint32)
+            n_reads = len(first) - 1
+        rb = CReadBatch(n_reads, n_seqs, SEQ_ASCII, MEM_HOST, data.ctypes.data if len(data) else None, None,
+                        starts.ctypes.data if n_seqs else None, lens.ctypes.data if n_seqs else None,
+                        first.ctypes.data if first is not None else None)
+        return rb, (data, starts, lens, first), n_reads
+
+    def identify_batch(self, seqs, read_first_seq=None):
+        """seqs: list of raw sequences (bytes) or (ascii, seq_start, seq_len) arrays.  Returns (n_kmers, scores, gpu_ms)."""
+        rb, keep, n_reads = self._read_batch(seqs, read_first_seq)
+        want = self.params.score_mode != SCORE_NONE
+        scores = np.zeros((n_reads, self.n_taxa), dtype=np.float32) if want else None
+        res = CBatchResult(0, scores.ctypes.data if want and scores.size else None, MEM_HOST, 0.0)
+        self._check(self.lib.kasa_identify_batch(self.h, C.byref(rb), C.byref(res)))
+        return int(res.n_kmers), scores, float(res.gpu_ms)
+
+    def identify_batch_raw(self, rb: CReadBatch, res: CBatchResult):
+        self._check(self.lib.kasa_identify_batch(self.h, C.byref(rb), C.byref(res)))
+
+    def identify_finish(self):
+        ca = np.zeros((self.num_k, self.n_taxa), dtype=np.float64)
+        cu = np.zeros((self.num_k, self.n_taxa), dtype=np.uint64)
+        n = C.c_uint64(0)
+        self._check(self.lib.kasa_identify_finish(self.h, _ptr(ca), _ptr(cu), C.byref(n)))
+        return ca, cu, int(n.value)
+
+    # ---------------------------------------------------------------- build
+    def build_push(self, strings: list[bytes], taxids):
+        data, starts, lens = self.pack_reads(strings)
+        tax = np.ascontiguousarray(taxids, dtype=np.uint32)
+        sb = CSeqBatch(len(lens), MEM_HOST, data.ctypes.data if len(data) else None, starts.ctypes.data, lens.ctypes.data,
+                       tax.ctypes.data)
+        self._check(self.lib.kasa_build_push(self.h, C.byref(sb)))
+
+    def build_finish(self, fetch: bool = True):
+        n, nt = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.kasa_build_finish(self.h, C.byref(n), C.byref(nt)))
+        if not fetch:
+            return int(n.value), int(nt.value)
+        rec = np.zeros(n.value, dtype=REC128 if self.wide else REC64)
+        trie = np.zeros(nt.value, dtype=TRIE)
+        self._check(self.lib.kasa_build_fetch(self.h, _ptr(rec) if n.value else None, _ptr(trie) if nt.value else None))
+        return rec, trie
+
+    def build_frequency(self, taxid_of_idx: np.ndarray) -> np.ndarray:
+        tax = np.ascontiguousarray(taxid_of_idx, dtype=np.uint32)
+        f = np.zeros((len(tax), self.params.highest_k), dtype=np.uint64)
+        self._check(self.lib.kasa_build_frequency(self.h, _ptr(tax), len(tax), _ptr(f)))
+        return f
+
+    # ---------------------------------------------------------------- stage-level (tests)
+    def dbg_extract(self, seqs, read_first_seq=None):
+        rb, keep, n_reads = self._read_batch(seqs, read_first_seq)
+        cap = self.params.max_batch_kmers
+        lo = np.zeros(cap, dtype=np.uint64)
+        hi = np.zeros(cap if self.wide else 1, dtype=np.uint64)
+        rid = np.zeros(cap, dtype=np.uint32)
+        n = C.c_uint64(0)
+        self._check(self.lib.kasa_dbg_extract(self.h, C.byref(rb), _ptr(lo), _ptr(hi), _ptr(rid), C.byref(n)))
+        n = int(n.value)
+        return lo[:n], (hi[:n] if self.wide else np.zeros(n, np.uint64)), rid[:n]
+
+    def dbg_sort_pairs(self, keys: np.ndarray, vals: np.ndarray, bit_lo: int = 0, bit_hi: int = 64):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+        vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+        self._check(self.lib.kasa_dbg_sort_pairs(self.h, _ptr(keys), _ptr(vals), len(keys), bit_lo, bit_hi))
+        return keys, vals
+
+    def synth_build_reference(self, seed: int, n_taxa: int, genome_len: int):
+        self._check(self.lib.kasa_synth_build_reference(self.h, seed, n_taxa, genome_len))
+
+    def synth_reads(self, genome_seed, read_seed, first_read, n_reads, n_taxa, genome_len, read_len=150,
+                    subst_ppm=10000, n_ppm=1000, out=None, out_location=MEM_HOST):
+        if out is None:
+            out = np.zeros((n_reads, read_len), dtype=np.uint8)
+        self._check(self.lib.kasa_synth_reads(self.h, genome_seed, read_seed, first_read, n_reads, n_taxa, genome_len,
+                                              read_len, subst_ppm, n_ppm, _ptr(out), out_location))
+        return out

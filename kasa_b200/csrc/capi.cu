@@ -1,0 +1,746 @@
+// capi.cu — the C ABI of include/kasa_b200.h: context, HBM layout, kernel orchestration.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/kasa_b200.h"
+#include "build.cuh"
+#include "common.cuh"
+#include "extract.cuh"
+#include "lookup.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+#include "synth.cuh"
+
+using namespace kasa;
+
+struct kasa_ctx {
+    kasa_params p{};
+    std::string err;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    int K = 12, num_k = 6, hb = 3;
+    bool wide = false;
+    std::vector<void *> allocs;
+
+    // record arrays (sort ping-pong; shared by identify batches and the build brick)
+    bool ws_ready = false;
+    uint64_t cap_kmers = 0;
+    SortBuffers sb{};
+    void *sort_ws = nullptr;
+    uint32_t *d_err = nullptr;          // [4] device error flags
+    // sequence staging
+    char *d_ascii = nullptr;
+    uint32_t *d_bases2 = nullptr, *d_nmask = nullptr;
+    uint64_t *d_seq_start = nullptr, *d_pstart = nullptr, *d_koff = nullptr, *d_read_koff = nullptr, *d_scan_tmp = nullptr;
+    uint32_t *d_seq_len = nullptr, *d_read_first = nullptr, *d_taxid = nullptr;
+    // lookup / accumulation
+    uint64_t *d_part = nullptr, *d_rec = nullptr;
+    float *d_scores = nullptr;
+    unsigned long long *d_cnt_fx = nullptr, *d_cnt_un = nullptr, *d_tot_un = nullptr;
+    double *d_tot_all = nullptr;
+    uint64_t n_kmers_total = 0;
+    // index (HBM resident, structure of arrays)
+    uint64_t idx_n = 0;
+    uint64_t *idx_lo = nullptr, *idx_hi = nullptr;
+    uint16_t *idx_tax = nullptr;
+    uint32_t n_taxa = 0;
+    // build
+    int build_buf = 0;
+    uint64_t build_fill = 0;
+    bool build_done = false;
+    uint64_t n_trie = 0;
+    uint32_t *d_trie_words = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+T *dev_alloc(kasa_ctx *c, size_t n)
+{
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(n * sizeof(T), 256);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        throw Error{KASA_ERR_NOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e)};
+    }
+    c->allocs.push_back(p);
+    return static_cast<T *>(p);
+}
+
+void dev_free(kasa_ctx *c, void *p)
+{
+    if (!p) return;
+    auto it = std::find(c->allocs.begin(), c->allocs.end(), p);
+    if (it != c->allocs.end()) c->allocs.erase(it);
+    cudaFree(p);
+}
+
+// standard genetic code in kASA's letter alphabet (kASA.hpp:621-667): stop TAA/TAG '[', TGA ']',
+// codons holding 'Z' -> '_', otherwise codons holding 'X' -> '^'.
+void builtin_codon_table(uint8_t t[512])
+{
+    static const char *tcag = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    static const int code_of[4] = {2, 1, 0, 3};   // T C A G -> A0 C1 T2 G3
+    std::memset(t, ' ', 512);
+    for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b)
+            for (int c = 0; c < 6; ++c) {
+                int idx = a << 6 | b << 3 | c;
+                if (a == 5 || b == 5 || c == 5) t[idx] = '_';
+                else if (a == 4 || b == 4 || c == 4) t[idx] = '^';
+            }
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b)
+            for (int c = 0; c < 4; ++c) {
+                char aa = tcag[a * 16 + b * 4 + c];
+                if (aa == '*') aa = (a == 0 && b == 3 && c == 2) ? ']' : '[';
+                t[code_of[a] << 6 | code_of[b] << 3 | code_of[c]] = (uint8_t)aa;
+            }
+}
+
+LevelParams level_params(const kasa_ctx *c)
+{
+    return LevelParams{c->K, c->p.k_high, c->p.k_low, c->num_k, (int)c->n_taxa, c->hb};
+}
+
+void ensure_workspace(kasa_ctx *c)
+{
+    if (c->ws_ready) return;
+    const uint64_t cap = c->p.max_batch_kmers;
+    const uint32_t ns = c->p.max_batch_seqs;
+    const uint64_t nb = c->p.max_batch_bases;
+    for (int i = 0; i < 2; ++i) {
+        c->sb.w0[i] = dev_alloc<uint64_t>(c, cap);
+        c->sb.w1[i] = c->wide ? dev_alloc<uint64_t>(c, cap) : nullptr;
+        c->sb.v[i] = dev_alloc<uint32_t>(c, cap);
+    }
+    c->sort_ws = dev_alloc<char>(c, sort_workspace_bytes(cap));
+    c->d_err = dev_alloc<uint32_t>(c, 4);
+    KASA_CUDA_TRY(cudaMemset(c->d_err, 0, 16));
+    c->d_ascii = dev_alloc<char>(c, nb + 64);
+    const uint64_t packed_bases = nb + 32ull * ns + 64;
+    c->d_bases2 = dev_alloc<uint32_t>(c, packed_bases / 16 + 4);
+    c->d_nmask = dev_alloc<uint32_t>(c, packed_bases / 32 + 4);
+    c->d_seq_start = dev_alloc<uint64_t>(c, (size_t)ns + 1);
+    c->d_pstart = dev_alloc<uint64_t>(c, (size_t)ns + 1);
+    c->d_koff = dev_alloc<uint64_t>(c, (size_t)ns + 1);
+    c->d_read_koff = dev_alloc<uint64_t>(c, (size_t)ns + 1);
+    c->d_scan_tmp = dev_alloc<uint64_t>(c, scan_tmp_elems(std::max<uint64_t>(cap + 1, ns + 1)) + 1);
+    c->d_seq_len = dev_alloc<uint32_t>(c, (size_t)ns + 1);
+    c->d_read_first = dev_alloc<uint32_t>(c, (size_t)ns + 1);
+    c->d_taxid = dev_alloc<uint32_t>(c, (size_t)ns + 1);
+    c->d_part = dev_alloc<uint64_t>(c, 2 * (size_t)div_up<uint64_t>(cap, kLookupTile) + 2);
+    c->d_rec = dev_alloc<uint64_t>(c, (size_t)(cap + 2) * kRecWords);
+    c->ws_ready = true;
+}
+
+void check_device_flags(kasa_ctx *c)
+{
+    uint32_t h[4];
+    KASA_CUDA_TRY(cudaMemcpyAsync(h, c->d_err, 16, cudaMemcpyDeviceToHost, c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (h[0] | h[1] | h[2] | h[3]) {
+        KASA_CUDA_TRY(cudaMemsetAsync(c->d_err, 0, 16, c->stream));
+        uint32_t f = h[0] | h[1] | h[2] | h[3];
+        if (f == 1) throw Error{KASA_ERR_INTERNAL, "radix sort look-back watchdog tripped"};
+        if (f == 2) throw Error{KASA_ERR_DATA, "a taxid of the index is missing from the content table"};
+        if (f == 3) throw Error{KASA_ERR_DATA, "index records are not sorted by (kmer, taxid)"};
+        throw Error{KASA_ERR_INTERNAL, "device error flag " + std::to_string(f)};
+    }
+}
+
+uint64_t read_u64(kasa_ctx *c, const uint64_t *dptr)
+{
+    uint64_t v = 0;
+    KASA_CUDA_TRY(cudaMemcpyAsync(&v, dptr, 8, cudaMemcpyDeviceToHost, c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return v;
+}
+
+// taxid -> dense index table (sorted by taxid) on device
+struct TaxTable {
+    uint32_t *d_taxid = nullptr;
+    uint16_t *d_idx = nullptr;
+    uint32_t n = 0;
+};
+
+TaxTable upload_tax_table(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_taxa)
+{
+    std::vector<std::pair<uint32_t, uint16_t>> v;
+    for (uint32_t i = 1; i < n_taxa; ++i) v.emplace_back(taxid_of_idx[i], (uint16_t)i);   // idx 0 = "non_unique"
+    std::sort(v.begin(), v.end());
+    std::vector<uint32_t> t(v.size());
+    std::vector<uint16_t> x(v.size());
+    for (size_t i = 0; i < v.size(); ++i) { t[i] = v[i].first; x[i] = v[i].second; }
+    TaxTable tt;
+    tt.n = (uint32_t)v.size();
+    tt.d_taxid = dev_alloc<uint32_t>(c, tt.n + 1);
+    tt.d_idx = dev_alloc<uint16_t>(c, tt.n + 1);
+    KASA_CUDA_TRY(cudaMemcpyAsync(tt.d_taxid, t.data(), tt.n * 4, cudaMemcpyHostToDevice, c->stream));
+    KASA_CUDA_TRY(cudaMemcpyAsync(tt.d_idx, x.data(), tt.n * 2, cudaMemcpyHostToDevice, c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return tt;
+}
+
+void set_taxa(kasa_ctx *c, uint32_t n_taxa)
+{
+    KASA_REQUIRE(n_taxa >= 1 && n_taxa <= 65535, KASA_ERR_ARG, "n_taxa must be in [1, 65535]");
+    KASA_REQUIRE((int)n_taxa - 1 <= record_taxa_capacity(c->hb), KASA_ERR_ARG,
+                 "this build supports at most " + std::to_string(record_taxa_capacity(c->hb)) +
+                     " taxa for the requested number of k levels (dense match records)");
+    c->n_taxa = n_taxa;
+    const size_t cells = (size_t)c->num_k * n_taxa;
+    c->d_cnt_fx = dev_alloc<unsigned long long>(c, cells);
+    c->d_cnt_un = dev_alloc<unsigned long long>(c, cells);
+    c->d_tot_un = dev_alloc<unsigned long long>(c, cells);
+    c->d_tot_all = dev_alloc<double>(c, cells);
+    KASA_CUDA_TRY(cudaMemsetAsync(c->d_cnt_fx, 0, cells * 8, c->stream));
+    KASA_CUDA_TRY(cudaMemsetAsync(c->d_cnt_un, 0, cells * 8, c->stream));
+    KASA_CUDA_TRY(cudaMemsetAsync(c->d_tot_un, 0, cells * 8, c->stream));
+    KASA_CUDA_TRY(cudaMemsetAsync(c->d_tot_all, 0, cells * 8, c->stream));
+    c->d_scores = dev_alloc<float>(c, (size_t)c->p.max_batch_seqs * n_taxa + 1);
+    c->n_kmers_total = 0;
+}
+
+void drop_index(kasa_ctx *c)
+{
+    dev_free(c, c->idx_lo); dev_free(c, c->idx_hi); dev_free(c, c->idx_tax);
+    dev_free(c, c->d_cnt_fx); dev_free(c, c->d_cnt_un); dev_free(c, c->d_tot_un); dev_free(c, c->d_tot_all); dev_free(c, c->d_scores);
+    c->idx_lo = c->idx_hi = nullptr; c->idx_tax = nullptr;
+    c->d_cnt_fx = c->d_cnt_un = c->d_tot_un = nullptr; c->d_tot_all = nullptr; c->d_scores = nullptr;
+    c->idx_n = 0; c->n_taxa = 0;
+}
+
+// stage a batch of sequences: after this, d_seq_start/d_seq_len (and d_ascii for host ASCII input) are valid.
+// Returns device pointers for the sequence data.
+struct Staged {
+    const char *ascii = nullptr;
+    const uint32_t *bases2 = nullptr, *nmask = nullptr;
+    const uint64_t *seq_start = nullptr;
+    const uint32_t *seq_len = nullptr;
+};
+
+template <typename T>
+const T *stage_array(kasa_ctx *c, const T *src, size_t n, T *dst, int location)
+{
+    if (location == KASA_MEM_DEVICE) return src;
+    KASA_CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return dst;
+}
+
+uint64_t host_total_bases(const uint64_t *seq_start, const uint32_t *seq_len, uint32_t n)
+{
+    uint64_t m = 0;
+    for (uint32_t i = 0; i < n; ++i) m = std::max<uint64_t>(m, seq_start[i] + seq_len[i]);
+    return m;
+}
+
+// sorts the accumulated build records by (kmer, taxid), removes duplicates and sentinels; the result
+// is left in buffer set c->build_buf, c->build_fill = number of distinct records.
+void build_compact(kasa_ctx *c)
+{
+    const uint64_t n = c->build_fill;
+    if (n == 0) return;
+    SortPlan plan{};
+    for (int b = 0; b < 32; b += 8) plan.pass[plan.n_passes++] = SortPass{SRC_V, b, 0xffu};
+    SortPlan kp = plan_for_kmer_bits(c->wide ? 128 : 64);   // all bits: sentinels (~0) must sort last
+    for (int i = 0; i < kp.n_passes; ++i) plan.pass[plan.n_passes++] = kp.pass[i];
+    int cur = radix_sort(c->stream, c->sb, c->build_buf, n, plan, c->sort_ws, c->d_err, &c->launches);
+    uint64_t *flags = c->d_rec;
+    launch_unique_flags(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, flags, &c->launches);
+    exclusive_scan_u64(c->stream, flags, n, c->d_scan_tmp, &c->launches);
+    const uint64_t n_unique = read_u64(c, flags + n);
+    const int dst = cur ^ 1;
+    launch_compact(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, flags, c->sb.w0[dst], c->sb.w1[dst], c->sb.v[dst],
+                   &c->launches);
+    KASA_CUDA_TRY(cudaGetLastError());
+    check_device_flags(c);
+    c->build_buf = dst;
+    c->build_fill = n_unique;
+}
+
+int fail(kasa_ctx *c, const Error &e)
+{
+    if (c) c->err = e.msg; else g_create_error = e.msg;
+    return e.code;
+}
+
+#define KASA_API_BEGIN try {
+#define KASA_API_END(ctx)                                                                   \
+    }                                                                                       \
+    catch (const Error &e) { return fail((ctx), e); }                                       \
+    catch (const std::exception &e) { return fail((ctx), Error{KASA_ERR_INTERNAL, e.what()}); } \
+    return KASA_OK;
+
+}  // namespace
+
+extern "C" {
+
+int kasa_abi_version(void) { return KASA_B200_ABI_VERSION; }
+
+const char *kasa_last_error(const kasa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int kasa_ctx_create(const kasa_params *p, kasa_ctx **out)
+{
+    kasa_ctx *c = nullptr;
+    try {
+        KASA_REQUIRE(p && out, KASA_ERR_ARG, "null argument");
+        KASA_REQUIRE(p->highest_k == 12 || p->highest_k == 25, KASA_ERR_ARG, "highest_k must be 12 or 25");
+        KASA_REQUIRE(p->k_low >= 1 && p->k_low <= p->k_high && p->k_high <= p->highest_k, KASA_ERR_ARG,
+                     "need 1 <= k_low <= k_high <= highest_k");
+        KASA_REQUIRE(p->frames == 3 || p->frames == 6, KASA_ERR_ARG, "frames must be 3 or 6 (--one is not supported)");
+        KASA_REQUIRE(p->score_mode == KASA_SCORE_NONE || p->score_mode == KASA_SCORE_FAST, KASA_ERR_ARG,
+                     "score_mode must be KASA_SCORE_NONE or KASA_SCORE_FAST in this version");
+        KASA_REQUIRE(p->max_batch_kmers > 0 && p->max_batch_kmers < (1ull << 32) - 2 * kSortTile, KASA_ERR_ARG,
+                     "max_batch_kmers must be in (0, 2^32)");
+        KASA_REQUIRE(p->max_batch_seqs > 0 && p->max_batch_bases > 0, KASA_ERR_ARG, "max_batch_seqs / max_batch_bases must be > 0");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            throw Error{KASA_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                           " (libkasa_b200 has no CPU fallback)"};
+        }
+        KASA_REQUIRE(p->device >= 0 && p->device < ndev, KASA_ERR_ARG, "device ordinal out of range");
+        KASA_CUDA_TRY(cudaSetDevice(p->device));
+        c = new kasa_ctx();
+        c->p = *p;
+        c->p.codon_table = nullptr;
+        c->K = p->highest_k;
+        c->wide = p->highest_k > 12;
+        c->num_k = p->k_high - p->k_low + 1;
+        c->hb = record_level_bits(c->num_k);
+        KASA_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+        KASA_CUDA_TRY(cudaEventCreate(&c->ev0));
+        KASA_CUDA_TRY(cudaEventCreate(&c->ev1));
+        uint8_t table[512];
+        if (p->codon_table) std::memcpy(table, p->codon_table, 512); else builtin_codon_table(table);
+        upload_codon_table(table);
+        *out = c;
+    } catch (const Error &e) {
+        if (c) kasa_ctx_destroy(c);
+        return fail(nullptr, e);
+    }
+    return KASA_OK;
+}
+
+void kasa_ctx_destroy(kasa_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->p.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void *p : c->allocs) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int kasa_ctx_set_stream(kasa_ctx *c, void *cuda_stream)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    c->own_stream = false;
+    KASA_API_END(c)
+}
+
+int kasa_ctx_synchronize(kasa_ctx *c)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    KASA_API_END(c)
+}
+
+uint64_t kasa_ctx_launch_count(const kasa_ctx *c) { return c ? c->launches : 0; }
+uint64_t kasa_index_size(const kasa_ctx *c) { return c ? c->idx_n : 0; }
+
+int kasa_index_load(kasa_ctx *c, const void *entries, uint64_t n, int bits, const uint32_t *taxid_of_idx, uint32_t n_taxa)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && entries && taxid_of_idx, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(bits == (c->wide ? 128 : 64), KASA_ERR_ARG, "index width does not match highest_k of the context");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    ensure_workspace(c);
+    drop_index(c);
+    set_taxa(c, n_taxa);
+    const size_t words_per = c->wide ? 5 : 3;
+    uint32_t *d_words = dev_alloc<uint32_t>(c, n * words_per + 1);
+    uint32_t *d_tax32 = dev_alloc<uint32_t>(c, n + 1);
+    c->idx_lo = dev_alloc<uint64_t>(c, n + 1);
+    c->idx_hi = c->wide ? dev_alloc<uint64_t>(c, n + 1) : nullptr;
+    c->idx_tax = dev_alloc<uint16_t>(c, n + 1);
+    KASA_CUDA_TRY(cudaMemcpyAsync(d_words, entries, n * words_per * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_unpack_records(c->stream, d_words, n, c->wide, c->idx_lo, c->idx_hi, d_tax32, &c->launches);
+    launch_check_sorted(c->stream, c->idx_lo, c->idx_hi, d_tax32, n, c->d_err, &c->launches);
+    TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
+    launch_map_taxids(c->stream, d_tax32, n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
+    KASA_CUDA_TRY(cudaGetLastError());
+    check_device_flags(c);
+    dev_free(c, d_words); dev_free(c, d_tax32); dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
+    c->idx_n = n;
+    KASA_API_END(c)
+}
+
+int kasa_index_from_build(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_taxa)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && taxid_of_idx, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(c->build_done, KASA_ERR_STATE, "kasa_index_from_build needs a finished build (kasa_build_finish)");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    drop_index(c);
+    set_taxa(c, n_taxa);
+    const uint64_t n = c->build_fill;
+    const int b = c->build_buf;
+    c->idx_lo = dev_alloc<uint64_t>(c, n + 1);
+    c->idx_hi = c->wide ? dev_alloc<uint64_t>(c, n + 1) : nullptr;
+    c->idx_tax = dev_alloc<uint16_t>(c, n + 1);
+    KASA_CUDA_TRY(cudaMemcpyAsync(c->idx_lo, c->sb.w0[b], n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->wide) KASA_CUDA_TRY(cudaMemcpyAsync(c->idx_hi, c->sb.w1[b], n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
+    launch_map_taxids(c->stream, c->sb.v[b], n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
+    KASA_CUDA_TRY(cudaGetLastError());
+    check_device_flags(c);
+    dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
+    c->idx_n = n;
+    KASA_API_END(c)
+}
+
+// shared front half of identify: stage + pack + count + extract; returns number of k-mers
+static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in)
+{
+    KASA_REQUIRE(in->n_seqs <= c->p.max_batch_seqs, KASA_ERR_NOMEM, "batch has more sequences than max_batch_seqs");
+    KASA_REQUIRE(in->n_reads <= in->n_seqs, KASA_ERR_ARG, "n_reads > n_seqs");
+    KASA_REQUIRE(in->format == KASA_SEQ_ASCII || in->format == KASA_SEQ_PACKED2, KASA_ERR_ARG, "unknown sequence format");
+    KASA_REQUIRE(in->read_first_seq || in->n_reads == in->n_seqs, KASA_ERR_ARG, "read_first_seq is required when n_reads != n_seqs");
+    ensure_workspace(c);
+    const uint32_t ns = in->n_seqs;
+    if (ns == 0) return 0;
+    const uint64_t *seq_start = stage_array(c, in->seq_start, ns, c->d_seq_start, in->location);
+    const uint32_t *seq_len = stage_array(c, in->seq_len, ns, c->d_seq_len, in->location);
+    PackedSeqs ps{};
+    ps.n_seqs = ns;
+    ps.seq_len = seq_len;
+    if (in->format == KASA_SEQ_ASCII) {
+        const char *ascii = static_cast<const char *>(in->bases);
+        if (in->location == KASA_MEM_HOST) {
+            uint64_t total = host_total_bases(in->seq_start, in->seq_len, ns);
+            KASA_REQUIRE(total <= c->p.max_batch_bases, KASA_ERR_NOMEM, "batch has more bases than max_batch_bases");
+            KASA_CUDA_TRY(cudaMemcpyAsync(c->d_ascii, in->bases, total, cudaMemcpyHostToDevice, c->stream));
+            ascii = c->d_ascii;
+        }
+        launch_pack_sizes(c->stream, seq_len, ns, c->d_pstart, &c->launches);
+        exclusive_scan_u64(c->stream, c->d_pstart, ns, c->d_scan_tmp, &c->launches);
+        launch_pack_ascii(c->stream, ascii, seq_start, seq_len, ns, c->d_pstart, c->d_bases2, c->d_nmask, &c->launches);
+        ps.bases2 = c->d_bases2; ps.nmask = c->d_nmask; ps.seq_start = c->d_pstart;
+    } else {
+        KASA_REQUIRE(in->nmask, KASA_ERR_ARG, "PACKED2 input needs the non-ACGT plane");
+        if (in->location == KASA_MEM_HOST) {
+            uint64_t total = host_total_bases(in->seq_start, in->seq_len, ns);
+            KASA_REQUIRE(total <= c->p.max_batch_bases + 32ull * ns, KASA_ERR_NOMEM, "batch has more bases than max_batch_bases");
+            KASA_CUDA_TRY(cudaMemcpyAsync(c->d_bases2, in->bases, div_up<uint64_t>(total, 16) * 4, cudaMemcpyHostToDevice, c->stream));
+            KASA_CUDA_TRY(cudaMemcpyAsync(c->d_nmask, in->nmask, div_up<uint64_t>(total, 32) * 4, cudaMemcpyHostToDevice, c->stream));
+            ps.bases2 = c->d_bases2; ps.nmask = c->d_nmask;
+        } else {
+            ps.bases2 = static_cast<const uint32_t *>(in->bases); ps.nmask = in->nmask;
+        }
+        ps.seq_start = seq_start;
+    }
+    KmerParams kp{c->K, c->p.k_low, c->p.frames == 6 ? 2 : 1};
+    launch_kmer_counts(c->stream, seq_len, ns, kp, c->d_koff, &c->launches);
+    exclusive_scan_u64(c->stream, c->d_koff, ns, c->d_scan_tmp, &c->launches);
+    const uint64_t n = read_u64(c, c->d_koff + ns);
+    KASA_REQUIRE(n <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "batch yields more k-mers than max_batch_kmers");
+    launch_extract_identify(c->stream, ps, kp, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
+    KASA_CUDA_TRY(cudaGetLastError());
+    return n;
+}
+
+int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_result *out)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && in && out, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(c->idx_lo, KASA_ERR_STATE, "kasa_identify_batch before an index was loaded");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    KASA_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    const uint64_t n = extract_batch(c, in);
+    out->n_kmers = n;
+    const bool want_scores = c->p.score_mode != KASA_SCORE_NONE;
+    if (n) {
+        SortPlan plan = plan_for_kmer_bits(5 * c->K);
+        const int cur = radix_sort(c->stream, c->sb, 0, n, plan, c->sort_ws, c->d_err, &c->launches);
+        const uint32_t *first = in->read_first_seq
+                                    ? stage_array(c, in->read_first_seq, (size_t)in->n_reads + 1, c->d_read_first, in->location)
+                                    : nullptr;
+        launch_read_offsets(c->stream, c->d_koff, first, in->n_reads, c->d_read_koff, &c->launches);
+        IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n};
+        LevelParams lp = level_params(c);
+        launch_partition(c->stream, c->sb.w0[cur], c->sb.w1[cur], n, idx, lp, c->d_part, &c->launches);
+        launch_lookup(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, idx, lp, c->d_part, c->d_rec, &c->launches);
+        launch_per_read(c->stream, c->d_rec, c->d_read_koff, in->n_reads, lp, want_scores ? c->d_scores : nullptr, c->d_cnt_fx,
+                        c->d_cnt_un, &c->launches);
+        launch_fold_counts(c->stream, c->d_cnt_fx, c->d_cnt_un, lp, c->d_tot_all, c->d_tot_un, &c->launches);
+    } else if (want_scores && in->n_reads) {
+        KASA_CUDA_TRY(cudaMemsetAsync(c->d_scores, 0, (size_t)in->n_reads * c->n_taxa * 4, c->stream));
+    }
+    KASA_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    if (want_scores && out->scores && in->n_reads) {
+        KASA_CUDA_TRY(cudaMemcpyAsync(out->scores, c->d_scores, (size_t)in->n_reads * c->n_taxa * 4,
+                                      out->scores_location == KASA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                      c->stream));
+    }
+    check_device_flags(c);     // synchronises the stream
+    KASA_CUDA_TRY(cudaEventElapsedTime(&out->gpu_ms, c->ev0, c->ev1));
+    c->n_kmers_total += n;
+    KASA_API_END(c)
+}
+
+int kasa_identify_finish(kasa_ctx *c, double *count_all, uint64_t *count_unique, uint64_t *n_kmers_total)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
+    KASA_REQUIRE(c->idx_lo, KASA_ERR_STATE, "kasa_identify_finish before an index was loaded");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    const size_t cells = (size_t)c->num_k * c->n_taxa;
+    if (count_all) KASA_CUDA_TRY(cudaMemcpyAsync(count_all, c->d_tot_all, cells * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (count_unique) KASA_CUDA_TRY(cudaMemcpyAsync(count_unique, c->d_tot_un, cells * 8, cudaMemcpyDeviceToHost, c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (n_kmers_total) *n_kmers_total = c->n_kmers_total;
+    KASA_CUDA_TRY(cudaMemsetAsync(c->d_tot_all, 0, cells * 8, c->stream));
+    KASA_CUDA_TRY(cudaMemsetAsync(c->d_tot_un, 0, cells * 8, c->stream));
+    c->n_kmers_total = 0;
+    KASA_API_END(c)
+}
+
+int kasa_build_push(kasa_ctx *c, const kasa_seq_batch *in)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && in, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(in->n_seqs <= c->p.max_batch_seqs, KASA_ERR_NOMEM, "batch has more sequences than max_batch_seqs");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    ensure_workspace(c);
+    if (c->build_done) { c->build_done = false; c->build_fill = 0; c->build_buf = 0; }
+    const uint32_t ns = in->n_seqs;
+    if (ns == 0) return KASA_OK;
+    const char *ascii = in->bases;
+    if (in->location == KASA_MEM_HOST) {
+        uint64_t total = host_total_bases(in->seq_start, in->seq_len, ns);
+        KASA_REQUIRE(total <= c->p.max_batch_bases, KASA_ERR_NOMEM, "batch has more bases than max_batch_bases");
+        KASA_CUDA_TRY(cudaMemcpyAsync(c->d_ascii, in->bases, total, cudaMemcpyHostToDevice, c->stream));
+        ascii = c->d_ascii;
+    }
+    const uint64_t *seq_start = stage_array(c, in->seq_start, ns, c->d_seq_start, in->location);
+    const uint32_t *seq_len = stage_array(c, in->seq_len, ns, c->d_seq_len, in->location);
+    const uint32_t *taxid = stage_array(c, in->taxid, ns, c->d_taxid, in->location);
+    launch_build_counts(c->stream, seq_len, ns, c->K, c->d_koff, &c->launches);
+    exclusive_scan_u64(c->stream, c->d_koff, ns, c->d_scan_tmp, &c->launches);
+    const uint64_t nw = read_u64(c, c->d_koff + ns);
+    if (c->build_fill + nw > c->p.max_batch_kmers) build_compact(c);     // the brick is full: Build.hpp:116-122
+    KASA_REQUIRE(c->build_fill + nw <= c->p.max_batch_kmers, KASA_ERR_NOMEM,
+                 "index does not fit max_batch_kmers records (prefix-sharded multi-GPU build is not in this version)");
+    const int b = c->build_buf;
+    const uint64_t o = c->build_fill;
+    launch_extract_build(c->stream, ascii, seq_start, seq_len, taxid, ns, c->K, c->d_koff, nw, c->sb.w0[b] + o,
+                         c->wide ? c->sb.w1[b] + o : nullptr, c->sb.v[b] + o, &c->launches);
+    KASA_CUDA_TRY(cudaGetLastError());
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));    // staging buffers are reused by the next push
+    c->build_fill += nw;
+    KASA_API_END(c)
+}
+
+int kasa_build_finish(kasa_ctx *c, uint64_t *n_entries, uint64_t *n_trie)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    ensure_workspace(c);
+    build_compact(c);
+    const uint64_t n = c->build_fill;
+    const int b = c->build_buf;
+    c->n_trie = 0;
+    if (n) {
+        // Trie.hpp:366-394: run lengths of the first six letters.  Scratch lives in d_rec:
+        // [flags/pos: n+1 u64][run starts: n_runs+1 u64][trie words: 3 u32 per run]
+        uint64_t *flags = c->d_rec;
+        launch_prefix_flags(c->stream, c->sb.w0[b], c->sb.w1[b], n, c->K, flags, &c->launches);
+        exclusive_scan_u64(c->stream, flags, n, c->d_scan_tmp, &c->launches);
+        const uint64_t runs = read_u64(c, flags + n);
+        uint64_t *starts = flags + n + 1;
+        c->d_trie_words = reinterpret_cast<uint32_t *>(starts + runs + 1);
+        launch_trie_records(c->stream, c->sb.w0[b], c->sb.w1[b], n, c->K, flags, runs, starts, c->d_trie_words, &c->launches);
+        KASA_CUDA_TRY(cudaGetLastError());
+        KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->n_trie = runs;
+    }
+    c->build_done = true;
+    if (n_entries) *n_entries = n;
+    if (n_trie) *n_trie = c->n_trie;
+    KASA_API_END(c)
+}
+
+int kasa_build_fetch(kasa_ctx *c, void *entries, void *trie)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
+    KASA_REQUIRE(c->build_done, KASA_ERR_STATE, "kasa_build_fetch before kasa_build_finish");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    const uint64_t n = c->build_fill;
+    const int b = c->build_buf;
+    if (trie && c->n_trie) {
+        KASA_CUDA_TRY(cudaMemcpyAsync(trie, c->d_trie_words, c->n_trie * 12, cudaMemcpyDeviceToHost, c->stream));
+        KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    if (entries && n) {
+        // file records through the free half of the sort ping-pong (enough for a chunk of n/2 records)
+        const size_t wpr = c->wide ? 5 : 3;
+        uint32_t *stage = reinterpret_cast<uint32_t *>(c->sb.w0[b ^ 1]);
+        const uint64_t chunk = std::max<uint64_t>(1, c->p.max_batch_kmers * 8 / (wpr * 4));
+        for (uint64_t o = 0; o < n; o += chunk) {
+            const uint64_t m = std::min(chunk, n - o);
+            launch_pack_records(c->stream, c->sb.w0[b] + o, c->wide ? c->sb.w1[b] + o : nullptr, c->sb.v[b] + o, m, stage, &c->launches);
+            KASA_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(entries) + o * wpr * 4, stage, m * wpr * 4, cudaMemcpyDeviceToHost, c->stream));
+            KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+    }
+    KASA_API_END(c)
+}
+
+int kasa_build_frequency(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_taxa, uint64_t *freq)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && taxid_of_idx && freq, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(c->build_done, KASA_ERR_STATE, "kasa_build_frequency before kasa_build_finish");
+    KASA_REQUIRE(n_taxa >= 1 && n_taxa <= 65535, KASA_ERR_ARG, "n_taxa must be in [1, 65535]");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    const uint64_t n = c->build_fill;
+    const int b = c->build_buf;
+    const size_t cells = (size_t)n_taxa * c->K;
+    TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
+    uint16_t *dense = reinterpret_cast<uint16_t *>(c->sb.v[b ^ 1]);     // free half of the ping-pong
+    unsigned long long *d_freq = dev_alloc<unsigned long long>(c, cells);
+    KASA_CUDA_TRY(cudaMemsetAsync(d_freq, 0, cells * 8, c->stream));
+    launch_map_taxids(c->stream, c->sb.v[b], n, tt.d_taxid, tt.d_idx, tt.n, dense, c->d_err, &c->launches);
+    launch_frequency(c->stream, c->sb.w0[b], c->sb.w1[b], dense, n, c->K, n_taxa, d_freq, &c->launches);
+    KASA_CUDA_TRY(cudaGetLastError());
+    KASA_CUDA_TRY(cudaMemcpyAsync(freq, d_freq, cells * 8, cudaMemcpyDeviceToHost, c->stream));
+    check_device_flags(c);
+    dev_free(c, d_freq); dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
+    KASA_API_END(c)
+}
+
+int kasa_dbg_extract(kasa_ctx *c, const kasa_read_batch *in, uint64_t *kmers_lo, uint64_t *kmers_hi, uint32_t *read_id,
+                     uint64_t *n_kmers)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && in && kmers_lo && n_kmers, KASA_ERR_ARG, "null argument");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    const uint64_t n = extract_batch(c, in);
+    *n_kmers = n;
+    if (n) {
+        KASA_CUDA_TRY(cudaMemcpyAsync(kmers_lo, c->sb.w0[0], n * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (c->wide && kmers_hi) KASA_CUDA_TRY(cudaMemcpyAsync(kmers_hi, c->sb.w1[0], n * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (read_id && in->n_seqs) {
+        std::vector<uint64_t> koff((size_t)in->n_seqs + 1);
+        KASA_CUDA_TRY(cudaMemcpyAsync(koff.data(), c->d_koff, koff.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        std::vector<uint32_t> first;
+        if (in->read_first_seq) {
+            first.resize((size_t)in->n_reads + 1);
+            KASA_CUDA_TRY(cudaMemcpyAsync(first.data(), in->read_first_seq, first.size() * 4,
+                                          in->location == KASA_MEM_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost, c->stream));
+        }
+        KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (uint32_t r = 0; r < in->n_reads; ++r) {
+            uint32_t s0 = in->read_first_seq ? first[r] : r, s1 = in->read_first_seq ? first[r + 1] : r + 1;
+            for (uint64_t i = koff[s0]; i < koff[s1]; ++i) read_id[i] = r;
+        }
+    }
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    KASA_API_END(c)
+}
+
+int kasa_dbg_sort_pairs(kasa_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t n, int bit_lo, int bit_hi)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && keys && vals, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(n <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "more records than max_batch_kmers");
+    KASA_REQUIRE(0 <= bit_lo && bit_lo < bit_hi && bit_hi <= 64, KASA_ERR_ARG, "need 0 <= bit_lo < bit_hi <= 64");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    ensure_workspace(c);
+    if (n == 0) return KASA_OK;
+    SortBuffers sb = c->sb;
+    sb.w1[0] = sb.w1[1] = nullptr;
+    KASA_CUDA_TRY(cudaMemcpyAsync(sb.w0[0], keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+    KASA_CUDA_TRY(cudaMemcpyAsync(sb.v[0], vals, n * 4, cudaMemcpyHostToDevice, c->stream));
+    SortPlan plan{};
+    for (int b = bit_lo; b < bit_hi; b += 8) {
+        int bits = std::min(8, bit_hi - b);
+        plan.pass[plan.n_passes++] = SortPass{SRC_W0, b, (1u << bits) - 1u};
+    }
+    const int cur = radix_sort(c->stream, sb, 0, n, plan, c->sort_ws, c->d_err, &c->launches);
+    KASA_CUDA_TRY(cudaMemcpyAsync(keys, sb.w0[cur], n * 8, cudaMemcpyDeviceToHost, c->stream));
+    KASA_CUDA_TRY(cudaMemcpyAsync(vals, sb.v[cur], n * 4, cudaMemcpyDeviceToHost, c->stream));
+    check_device_flags(c);
+    KASA_API_END(c)
+}
+
+int kasa_synth_build_reference(kasa_ctx *c, uint64_t seed, uint32_t n_taxa, uint64_t genome_len)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    ensure_workspace(c);
+    const uint32_t marker = 3 * (c->K - 1);
+    KASA_REQUIRE(genome_len + marker <= c->p.max_batch_bases && genome_len < (1ull << 32) - 1024, KASA_ERR_NOMEM,
+                 "genome_len exceeds max_batch_bases");
+    for (uint32_t t = 0; t < n_taxa; ++t) {
+        launch_synth_genome(c->stream, seed, t, genome_len, marker, c->d_ascii, &c->launches);
+        uint64_t start = 0;
+        uint32_t len = (uint32_t)(genome_len + marker), tax = 1000 + t;
+        KASA_CUDA_TRY(cudaMemcpyAsync(c->d_seq_start, &start, 8, cudaMemcpyHostToDevice, c->stream));
+        KASA_CUDA_TRY(cudaMemcpyAsync(c->d_seq_len, &len, 4, cudaMemcpyHostToDevice, c->stream));
+        KASA_CUDA_TRY(cudaMemcpyAsync(c->d_taxid, &tax, 4, cudaMemcpyHostToDevice, c->stream));
+        KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        kasa_seq_batch sbatch{1, KASA_MEM_DEVICE, c->d_ascii, c->d_seq_start, c->d_seq_len, c->d_taxid};
+        int rc = kasa_build_push(c, &sbatch);
+        if (rc != KASA_OK) return rc;
+    }
+    KASA_API_END(c)
+}
+
+int kasa_synth_reads(kasa_ctx *c, uint64_t genome_seed, uint64_t read_seed, uint64_t first_read, uint32_t n_reads, uint32_t n_taxa,
+                     uint64_t genome_len, uint32_t read_len, uint32_t subst_ppm, uint32_t n_ppm, char *out, int out_location)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && out, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(genome_len >= read_len && n_taxa > 0, KASA_ERR_ARG, "genome shorter than a read");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    const uint64_t total = (uint64_t)n_reads * read_len;
+    if (out_location == KASA_MEM_DEVICE) {
+        launch_synth_reads(c->stream, genome_seed, read_seed, first_read, n_reads, n_taxa, genome_len, read_len, subst_ppm, n_ppm, out,
+                           &c->launches);
+    } else {
+        ensure_workspace(c);
+        KASA_REQUIRE(total <= c->p.max_batch_bases, KASA_ERR_NOMEM, "more bases than max_batch_bases");
+        launch_synth_reads(c->stream, genome_seed, read_seed, first_read, n_reads, n_taxa, genome_len, read_len, subst_ppm, n_ppm,
+                           c->d_ascii, &c->launches);
+        KASA_CUDA_TRY(cudaMemcpyAsync(out, c->d_ascii, total, cudaMemcpyDeviceToHost, c->stream));
+    }
+    KASA_CUDA_TRY(cudaGetLastError());
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    KASA_API_END(c)
+}
+
+}  // extern "C"

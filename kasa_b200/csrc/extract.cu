@@ -1,0 +1,227 @@
+// extract.cu — see extract.cuh.
+#include "extract.cuh"
+
+namespace kasa {
+
+// 5-bit letter codes of the codon table (kASA.hpp:621-667: letter & 31), index c0<<6|c1<<3|c2
+__constant__ uint8_t c_aa[512];
+
+void upload_codon_table(const uint8_t table512[512])
+{
+    uint8_t t[512];
+    for (int i = 0; i < 512; ++i) t[i] = table512[i] & 31u;
+    KASA_CUDA_TRY(cudaMemcpyToSymbol(c_aa, t, 512));
+}
+
+namespace {
+
+constexpr int kExtractWarps = 8;
+constexpr int kSeg = 256;              // output positions per shared-memory segment
+constexpr int kAaPad = 3 * 24 + 8;     // 3*(K-1) extra letters for K <= 25
+
+__global__ void pack_sizes_kernel(const uint32_t *__restrict__ seq_len, uint32_t n, uint64_t *__restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ((uint64_t)seq_len[i] + 31u) & ~31ull;
+}
+
+// one warp per sequence; lane l packs 32-base groups l, l+32, ...
+__global__ void __launch_bounds__(256) pack_ascii_kernel(const char *__restrict__ ascii, const uint64_t *__restrict__ astart,
+                                                         const uint32_t *__restrict__ seq_len, uint32_t n_seqs,
+                                                         const uint64_t *__restrict__ pstart, uint32_t *__restrict__ bases2,
+                                                         uint32_t *__restrict__ nmask)
+{
+    uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= n_seqs) return;
+    const uint32_t L = seq_len[s];
+    const char *src = ascii + astart[s];
+    const uint64_t g0 = pstart[s] >> 5;           // first 32-base group
+    const uint32_t groups = (L + 31) >> 5;
+    for (uint32_t g = lane_id(); g < groups; g += 32) {
+        uint32_t lo = 0, hi = 0, m = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            uint32_t pos = g * 32 + j;
+            uint32_t code = 0, bad = 0;
+            if (pos < L) {
+                char c = src[pos];
+                // Read.hpp:657-675: only ACGTacgt survive, everything else becomes 'Z'
+                bool ok = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T') | (c == 'a') | (c == 'c') | (c == 'g') | (c == 't');
+                code = ok ? ((uint32_t)(c & 14) >> 1) : 0u;     // kASA.hpp:70-75: A0 C1 T2 G3
+                bad = ok ? 0u : 1u;
+            }
+            if (j < 16) lo |= code << (2 * j); else hi |= code << (2 * (j - 16));
+            m |= bad << j;
+        }
+        bases2[(g0 + g) * 2] = lo;
+        bases2[(g0 + g) * 2 + 1] = hi;
+        nmask[g0 + g] = m;
+    }
+}
+
+__host__ __device__ __forceinline__ uint64_t kmer_count(uint64_t len, int K)
+{
+    return len > (uint64_t)(3 * K + 1) ? len - 3 * K + 1 : 0;   // Read.hpp:50-52
+}
+
+__global__ void kmer_counts_kernel(const uint32_t *__restrict__ seq_len, uint32_t n, KmerParams p, uint64_t *__restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint64_t)p.strands * kmer_count((uint64_t)seq_len[i] + 3u * (p.K - p.k_low), p.K);
+}
+
+// 3-bit base code of the prepared string (forward: read + marker; reverse: revcomp(read) + marker)
+__device__ __forceinline__ uint32_t code_at(const uint32_t *__restrict__ b2, const uint32_t *__restrict__ nm, uint64_t start,
+                                            uint32_t L, int strand, uint32_t pos)
+{
+    if (pos >= L) return 4u;                                  // marker / padding 'X'
+    uint64_t g = start + (strand ? (L - 1 - pos) : pos);
+    uint32_t two = (__ldg(b2 + (g >> 4)) >> (2 * (uint32_t)(g & 15))) & 3u;
+    uint32_t isn = (__ldg(nm + (g >> 5)) >> (uint32_t)(g & 31)) & 1u;
+    return isn ? 5u : (strand ? (two ^ 2u) : two);            // complement A0<->T2, C1<->G3 (kASA.hpp:54)
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(PackedSeqs seqs, KmerParams p,
+                                                                              const uint64_t *__restrict__ koff,
+                                                                              uint64_t *__restrict__ key_lo,
+                                                                              uint64_t *__restrict__ key_hi,
+                                                                              uint32_t *__restrict__ inst)
+{
+    __shared__ uint8_t s_aa[kExtractWarps][kSeg + kAaPad];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t s = blockIdx.x * kExtractWarps + w;
+    if (s >= seqs.n_seqs) return;
+    const uint32_t L = seqs.seq_len[s];
+    const uint64_t start = seqs.seq_start[s];
+    const int K = p.K;
+    const uint32_t n = (uint32_t)kmer_count((uint64_t)L + 3u * (K - p.k_low), K);
+    if (n == 0) return;
+    const uint64_t out0 = koff[s];
+    uint8_t *aa = s_aa[w];
+    for (int strand = 0; strand < p.strands; ++strand) {
+        const uint64_t obase = out0 + (uint64_t)strand * n;
+        for (uint32_t p0 = 0; p0 < n; p0 += kSeg) {
+            const uint32_t cnt = min((uint32_t)kSeg, n - p0);
+            const uint32_t naa = cnt + 3 * (K - 1);
+            for (uint32_t j = lane; j < naa; j += 32) {
+                uint32_t pos = p0 + j;
+                uint32_t c0 = code_at(seqs.bases2, seqs.nmask, start, L, strand, pos);
+                uint32_t c1 = code_at(seqs.bases2, seqs.nmask, start, L, strand, pos + 1);
+                uint32_t c2 = code_at(seqs.bases2, seqs.nmask, start, L, strand, pos + 2);
+                aa[j] = c_aa[c0 << 6 | c1 << 3 | c2];
+            }
+            __syncwarp();
+            for (uint32_t j = lane; j < cnt; j += 32) {
+                uint64_t lo = 0, hi = 0;
+                for (int i = 0; i < K; ++i) {
+                    if (WIDE) hi = (hi << 5) | (lo >> 59);
+                    lo = (lo << 5) | aa[j + 3 * i];
+                }
+                const uint64_t o = obase + p0 + j;
+                key_lo[o] = lo;
+                if (WIDE) key_hi[o] = hi;
+                inst[o] = (uint32_t)o;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void build_counts_kernel(const uint32_t *__restrict__ seq_len, uint32_t n, int K, uint64_t *__restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = seq_len[i] >= (uint32_t)(3 * K) ? (uint64_t)seq_len[i] - 3 * K + 1 : 0;   // Read.hpp:1995
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) extract_build_kernel(const char *__restrict__ ascii, const uint64_t *__restrict__ seq_start,
+                                                            const uint32_t *__restrict__ taxid, uint32_t n_seqs, int K,
+                                                            const uint64_t *__restrict__ woff, uint64_t n_windows,
+                                                            uint64_t *__restrict__ key_lo, uint64_t *__restrict__ key_hi,
+                                                            uint32_t *__restrict__ val)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_windows; f += stride) {
+        // sequence of this window: last s with woff[s] <= f
+        uint32_t lo_s = 0, hi_s = n_seqs;
+        while (hi_s - lo_s > 1) {
+            uint32_t mid = (lo_s + hi_s) >> 1;
+            if (__ldg(woff + mid) <= f) lo_s = mid; else hi_s = mid;
+        }
+        const char *ptr = ascii + seq_start[lo_s] + (f - __ldg(woff + lo_s));
+        uint64_t lo = 0, hi = 0;
+        bool bad = false;
+        for (int i = 0; i < K; ++i) {
+            uint32_t c0 = (uint8_t)ptr[3 * i], c1 = (uint8_t)ptr[3 * i + 1], c2 = (uint8_t)ptr[3 * i + 2];
+            uint32_t a = c_aa[((c0 & 14u) << 5) | ((c1 & 14u) << 2) | ((c2 & 14u) >> 1)];   // kASA.hpp:75
+            bad |= (a == kLetterUnder);
+            if (WIDE) hi = (hi << 5) | (lo >> 59);
+            lo = (lo << 5) | a;
+        }
+        if (bad || (lo == 0 && hi == 0)) { lo = ~0ull; hi = ~0ull; }
+        key_lo[f] = lo;
+        if (WIDE) key_hi[f] = hi;
+        val[f] = taxid[lo_s];
+    }
+}
+
+}  // namespace
+
+void launch_pack_sizes(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, uint64_t *pstart, uint64_t *launches)
+{
+    if (!n_seqs) return;
+    pack_sizes_kernel<<<div_up(n_seqs, 256u), 256, 0, s>>>(seq_len, n_seqs, pstart);
+    ++*launches;
+}
+
+void launch_pack_ascii(cudaStream_t s, const char *ascii, const uint64_t *ascii_start, const uint32_t *seq_len,
+                       uint32_t n_seqs, const uint64_t *pstart, uint32_t *bases2, uint32_t *nmask, uint64_t *launches)
+{
+    if (!n_seqs) return;
+    pack_ascii_kernel<<<div_up(n_seqs, 8u), 256, 0, s>>>(ascii, ascii_start, seq_len, n_seqs, pstart, bases2, nmask);
+    ++*launches;
+}
+
+void launch_kmer_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, KmerParams p, uint64_t *koff, uint64_t *launches)
+{
+    if (!n_seqs) return;
+    kmer_counts_kernel<<<div_up(n_seqs, 256u), 256, 0, s>>>(seq_len, n_seqs, p, koff);
+    ++*launches;
+}
+
+void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint64_t *koff, uint64_t *key_lo,
+                             uint64_t *key_hi, uint32_t *inst, uint64_t *launches)
+{
+    if (!seqs.n_seqs) return;
+    unsigned grid = div_up(seqs.n_seqs, (uint32_t)kExtractWarps);
+    if (p.K > 12)
+        extract_identify_kernel<true><<<grid, kExtractWarps * 32, 0, s>>>(seqs, p, koff, key_lo, key_hi, inst);
+    else
+        extract_identify_kernel<false><<<grid, kExtractWarps * 32, 0, s>>>(seqs, p, koff, key_lo, key_hi, inst);
+    ++*launches;
+}
+
+void launch_build_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, int K, uint64_t *woff, uint64_t *launches)
+{
+    if (!n_seqs) return;
+    build_counts_kernel<<<div_up(n_seqs, 256u), 256, 0, s>>>(seq_len, n_seqs, K, woff);
+    ++*launches;
+}
+
+void launch_extract_build(cudaStream_t s, const char *ascii, const uint64_t *seq_start, const uint32_t *seq_len,
+                          const uint32_t *taxid, uint32_t n_seqs, int K, const uint64_t *woff, uint64_t n_windows,
+                          uint64_t *key_lo, uint64_t *key_hi, uint32_t *val, uint64_t *launches)
+{
+    (void)seq_len;
+    if (!n_windows) return;
+    uint64_t want = div_up<uint64_t>(n_windows, 256);
+    unsigned grid = (unsigned)(want < (uint64_t)kSMs * 32 ? want : (uint64_t)kSMs * 32);
+    if (K > 12)
+        extract_build_kernel<true><<<grid, 256, 0, s>>>(ascii, seq_start, taxid, n_seqs, K, woff, n_windows, key_lo, key_hi, val);
+    else
+        extract_build_kernel<false><<<grid, 256, 0, s>>>(ascii, seq_start, taxid, n_seqs, K, woff, n_windows, key_lo, key_hi, val);
+    ++*launches;
+}
+
+}  // namespace kasa

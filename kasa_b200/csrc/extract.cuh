@@ -1,0 +1,48 @@
+// extract.cuh — codon translation + packed k-mer construction.
+//   identify: Read::convert_dnaTokMer (Read.hpp:84-220), kASA::dnaToAminoacid (kASA.hpp:69-87),
+//             kASA::aminoacidTokMer (kASA.hpp:333-379), reverseComplement (kASA.hpp:214-221),
+//             read preparation (Read.hpp:612-695) done analytically on device.
+//   build:    Read::dnaTokMers (Read.hpp:1991-2139).
+#pragma once
+#include "common.cuh"
+
+namespace kasa {
+
+// 2-bit packed sequences on device (KASA_SEQ_PACKED2 of include/kasa_b200.h)
+struct PackedSeqs {
+    const uint32_t *bases2;     // 16 bases per word, LSB first, codes A0 C1 T2 G3
+    const uint32_t *nmask;      // 32 bases per word, bit = non-ACGT ('Z')
+    const uint64_t *seq_start;  // [n_seqs] first base (multiple of 32)
+    const uint32_t *seq_len;    // [n_seqs]
+    uint32_t n_seqs;
+};
+
+struct KmerParams {
+    int K;          // highest_k: 12 or 25
+    int k_low;      // marker = 3*(K - k_low) 'X' (Read.hpp:1068-1078)
+    int strands;    // 1 (three forward frames) or 2 (--six)
+};
+
+void upload_codon_table(const uint8_t table512[512]);   // -> __constant__ 5-bit letter codes
+
+// packed start of each sequence = exclusive scan of roundup32(len); writes pstart[n+1] inputs for the scan
+void launch_pack_sizes(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, uint64_t *pstart, uint64_t *launches);
+// ASCII -> 2-bit + mask (cleaning of Read.hpp:657-675: anything but ACGTacgt is 'Z')
+void launch_pack_ascii(cudaStream_t s, const char *ascii, const uint64_t *ascii_start, const uint32_t *seq_len,
+                       uint32_t n_seqs, const uint64_t *pstart, uint32_t *bases2, uint32_t *nmask, uint64_t *launches);
+
+// per-sequence k-mer counts (Read.hpp:36-57) into koff[0..n_seqs); scan afterwards
+void launch_kmer_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, KmerParams p, uint64_t *koff, uint64_t *launches);
+// k-mers in the reference's emission order (forward strand, then reverse strand, per sequence);
+// key_hi may be nullptr for K <= 12; inst[i] = i (sort payload = instance id)
+void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint64_t *koff, uint64_t *key_lo,
+                             uint64_t *key_hi, uint32_t *inst, uint64_t *launches);
+
+// build: one slot per window of each prepared ASCII string; windows holding '_' (31) or giving k-mer 0
+// get the sentinel key ~0 (dropped after the sort): Read.hpp:2016-2024, 2048-2059, 2097, 2122
+void launch_build_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, int K, uint64_t *woff, uint64_t *launches);
+void launch_extract_build(cudaStream_t s, const char *ascii, const uint64_t *seq_start, const uint32_t *seq_len,
+                          const uint32_t *taxid, uint32_t n_seqs, int K, const uint64_t *woff, uint64_t n_windows,
+                          uint64_t *key_lo, uint64_t *key_hi, uint32_t *val, uint64_t *launches);
+
+}  // namespace kasa

@@ -1,0 +1,396 @@
+// lookup.cu — see lookup.cuh.
+//
+// Data flow per batch (all arrays in HBM):
+//   sorted (q, inst)  --partition-->  per-tile index span  --lookup-->  rec[inst] (32 B, scattered
+//   back to emission order)  --per_read-->  scores[read][taxon], counts[level][taxon]
+//
+// The reference walks sorted queries and the sorted index with a sequential state machine and scores
+// "groups" (all query instances sharing a k-prefix) when the next group appears.  Every quantity it
+// accumulates is linear in the hit instances, so here each instance independently
+// finds the index entries sharing >= k_low leading letters with it (one binary search + a short scan of
+// a shared-memory copy of the tile's index span) and records, per taxon, up to which level it matches.
+#include "lookup.cuh"
+
+namespace kasa {
+namespace {
+
+struct Key {
+    uint64_t lo, hi;
+};
+
+template <bool W>
+__device__ __forceinline__ bool key_lt(const Key &a, const Key &b)
+{
+    if (W && a.hi != b.hi) return a.hi < b.hi;
+    return a.lo < b.lo;
+}
+
+// number of equal leading letters of two K-letter k-mers (5 bits per letter, first letter in the MSBs)
+template <bool W>
+__device__ __forceinline__ int common_letters(const Key &a, const Key &b, int K)
+{
+    int lead;
+    if (W) {
+        uint64_t xh = a.hi ^ b.hi;
+        if (xh) lead = __clzll((long long)xh) - (128 - 5 * K);
+        else {
+            uint64_t xl = a.lo ^ b.lo;
+            if (!xl) return K;
+            lead = (5 * K - 64) + __clzll((long long)xl);
+        }
+    } else {
+        uint64_t x = a.lo ^ b.lo;
+        if (!x) return K;
+        lead = __clzll((long long)x) - (64 - 5 * K);
+    }
+    return lead / 5;
+}
+
+// letter at 1-based position k
+template <bool W>
+__device__ __forceinline__ uint32_t letter_at(const Key &q, int k, int K)
+{
+    int sh = 5 * (K - k);
+    if (!W) return (uint32_t)(q.lo >> sh) & 31u;
+    if (sh >= 64) return (uint32_t)(q.hi >> (sh - 64)) & 31u;
+    if (sh + 5 <= 64) return (uint32_t)(q.lo >> sh) & 31u;
+    return (uint32_t)((q.hi << (64 - sh)) | (q.lo >> sh)) & 31u;
+}
+
+// smallest / one-past-largest k-mer sharing the first k letters of q
+template <bool W>
+__device__ __forceinline__ Key prefix_floor(const Key &q, int k, int K)
+{
+    int sh = 5 * (K - k);
+    Key r = q;
+    if (!W) { r.lo = sh >= 64 ? 0 : (q.lo >> sh) << sh; return r; }
+    if (sh >= 64) { r.lo = 0; r.hi = (sh - 64) >= 64 ? 0 : (q.hi >> (sh - 64)) << (sh - 64); }
+    else r.lo = (q.lo >> sh) << sh;
+    return r;
+}
+template <bool W>
+__device__ __forceinline__ Key prefix_ceil(const Key &q, int k, int K)
+{
+    int sh = 5 * (K - k);
+    Key r = prefix_floor<W>(q, k, K);
+    if (!W) { r.lo += 1ull << sh; return r; }
+    if (sh >= 64) r.hi += 1ull << (sh - 64);
+    else {
+        uint64_t old = r.lo;
+        r.lo += 1ull << sh;
+        if (r.lo < old) r.hi += 1;
+    }
+    return r;
+}
+
+struct GmemAcc {
+    const uint64_t *klo, *khi;
+    const uint16_t *tax;
+    template <bool W>
+    __device__ __forceinline__ Key key(int64_t i) const { return Key{__ldg(klo + i), W ? __ldg(khi + i) : 0ull}; }
+    __device__ __forceinline__ uint32_t taxon(int64_t i) const { return __ldg(tax + i); }
+};
+
+struct SmemAcc {
+    const uint64_t *klo, *khi;
+    const uint16_t *tax;
+    int64_t a;     // global index of element 0
+    template <bool W>
+    __device__ __forceinline__ Key key(int64_t i) const { return Key{klo[i - a], W ? khi[i - a] : 0ull}; }
+    __device__ __forceinline__ uint32_t taxon(int64_t i) const { return tax[i - a]; }
+};
+
+template <bool W, class Acc>
+__device__ __forceinline__ int64_t lower_bound(const Acc &acc, int64_t lo, int64_t hi, const Key &q)
+{
+    while (lo < hi) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if (key_lt<W>(acc.template key<W>(mid), q)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int HB>
+__device__ __forceinline__ void rec_update(uint64_t (&R)[kRecWords], int slot, uint32_t h)
+{
+    constexpr int FPW = 64 / HB;
+    constexpr uint64_t HM = (1ull << HB) - 1;
+    const int wi = slot / FPW, sh = (slot % FPW) * HB;
+    uint64_t w = wi == 0 ? R[0] : (wi == 1 ? R[1] : (wi == 2 ? R[2] : R[3]));
+    uint32_t cur = (uint32_t)(w >> sh) & (uint32_t)HM;
+    if (h > cur) {
+        uint64_t add = (uint64_t)(h - cur) << sh;
+        if (wi == 0) R[0] += add; else if (wi == 1) R[1] += add; else if (wi == 2) R[2] += add; else R[3] += add;
+    }
+}
+
+// Set semantics of Compare.hpp:785-1041 for one query instance: every index entry whose first c >= k_low
+// letters equal the query's belongs to taxa_k(prefix_k(q)) for k = k_low .. min(c, kv), where kv is the last
+// level not killed by a '^' letter (Compare.hpp:836, 897).
+template <bool W, int HB, class Acc>
+__device__ __forceinline__ void match_query(const Acc &acc, int64_t a, int64_t b, const Key &q, const LevelParams &lp,
+                                            uint64_t (&R)[kRecWords])
+{
+    int kv = lp.k_low - 1;
+    for (int k = lp.k_low; k <= lp.k_high; ++k) {
+        if (letter_at<W>(q, k, lp.K) == kLetterCaret) break;
+        kv = k;
+    }
+    if (kv < lp.k_low) return;
+    const int64_t pos = lower_bound<W>(acc, a, b, q);
+    for (int64_t e = pos; e < b; ++e) {
+        int c = common_letters<W>(acc.template key<W>(e), q, lp.K);
+        if (c < lp.k_low) break;
+        rec_update<HB>(R, (int)acc.taxon(e) - 1, (uint32_t)(min(c, kv) - lp.k_low + 1));
+    }
+    for (int64_t e = pos - 1; e >= a; --e) {
+        int c = common_letters<W>(acc.template key<W>(e), q, lp.K);
+        if (c < lp.k_low) break;
+        rec_update<HB>(R, (int)acc.taxon(e) - 1, (uint32_t)(min(c, kv) - lp.k_low + 1));
+    }
+}
+
+template <bool W>
+__global__ void __launch_bounds__(256) partition_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
+                                                        uint64_t n, IndexDev idx, LevelParams lp, uint64_t *__restrict__ part,
+                                                        uint64_t n_tiles)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    uint64_t i0 = t * kLookupTile, i1 = min(n, i0 + kLookupTile) - 1;
+    Key first{q_lo[i0], W ? q_hi[i0] : 0ull}, last{q_lo[i1], W ? q_hi[i1] : 0ull};
+    GmemAcc acc{idx.key_lo, idx.key_hi, idx.tax};
+    Key f = prefix_floor<W>(first, lp.k_low, lp.K), c = prefix_ceil<W>(last, lp.k_low, lp.K);
+    int64_t a = lower_bound<W>(acc, 0, (int64_t)idx.n, f);
+    int64_t b = lower_bound<W>(acc, a, (int64_t)idx.n, c);
+    part[2 * t] = (uint64_t)a;
+    part[2 * t + 1] = (uint64_t)b;
+}
+
+constexpr int kSpanCap = 4608;   // index entries staged per tile (avg span = tile * index/queries)
+
+template <bool W, int HB>
+__global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
+                                                              const uint32_t *__restrict__ inst, uint64_t n, IndexDev idx,
+                                                              LevelParams lp, const uint64_t *__restrict__ part,
+                                                              uint64_t *__restrict__ rec)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *s_klo = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *s_khi = s_klo + (W ? kSpanCap : 0);
+    uint16_t *s_tax = reinterpret_cast<uint16_t *>(s_khi + kSpanCap);
+
+    const uint64_t tile = blockIdx.x;
+    const uint64_t q0 = tile * kLookupTile;
+    const int64_t a = (int64_t)part[2 * tile], b = (int64_t)part[2 * tile + 1];
+    const int64_t span = b - a;
+    const bool staged = span <= kSpanCap;
+    if (staged) {
+        for (int64_t j = threadIdx.x; j < span; j += kLookupBlock) {
+            s_klo[j] = ldg_stream(idx.key_lo + a + j);
+            if (W) s_khi[j] = ldg_stream(idx.key_hi + a + j);
+            s_tax[j] = idx.tax[a + j];
+        }
+    }
+    __syncthreads();
+    SmemAcc sacc{s_klo, s_khi, s_tax, a};
+    GmemAcc gacc{idx.key_lo, idx.key_hi, idx.tax};
+#pragma unroll 1
+    for (int r = 0; r < kLookupTile / kLookupBlock; ++r) {
+        uint64_t i = q0 + (uint64_t)r * kLookupBlock + threadIdx.x;
+        if (i >= n) break;
+        Key q{ldg_stream(q_lo + i), W ? ldg_stream(q_hi + i) : 0ull};
+        uint64_t R[kRecWords] = {0, 0, 0, 0};
+        if (span > 0) {
+            if (staged) match_query<W, HB>(sacc, a, b, q, lp, R);
+            else match_query<W, HB>(gacc, a, b, q, lp, R);
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)ldg_stream(inst + i) * kRecWords);
+        dst[0] = make_uint4((uint32_t)R[0], (uint32_t)(R[0] >> 32), (uint32_t)R[1], (uint32_t)(R[1] >> 32));
+        dst[1] = make_uint4((uint32_t)R[2], (uint32_t)(R[2] >> 32), (uint32_t)R[3], (uint32_t)(R[3] >> 32));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kReadBlock = 128;
+
+template <int HB, int LW>
+__global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__restrict__ rec, const uint64_t *__restrict__ read_koff,
+                                                              uint32_t n_reads, LevelParams lp, float *__restrict__ scores,
+                                                              unsigned long long *__restrict__ cnt_fx,
+                                                              unsigned long long *__restrict__ cnt_unique)
+{
+    constexpr int FPW = 64 / HB;
+    constexpr uint64_t HM = (1ull << HB) - 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = lp.n_taxa, NK = lp.num_k;
+    unsigned long long *s_fx = reinterpret_cast<unsigned long long *>(smem_raw);   // [NK][T]
+    unsigned long long *s_un = s_fx + NK * T;                                      // [NK][T]
+    unsigned long long *s_invfx = s_un + NK * T;                                   // [256]
+    float *s_w = reinterpret_cast<float *>(s_invfx + 256);                         // [32]
+    float *s_score = s_w + 32;                                                     // [T][kReadBlock]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 2 * NK * T; i += kReadBlock) s_fx[i] = 0;
+    for (int i = tid; i < 256; i += kReadBlock) s_invfx[i] = i ? (unsigned long long)(4294967296.0 / i + 0.5) : 0ull;
+    if (tid < 32) {
+        int k = lp.k_low + tid;
+        s_w[tid] = (float)(k * k) / 625.f;        // Compare.hpp:392 arrWeightingFactors[25 - k]
+    }
+    __syncthreads();
+
+    for (uint64_t r0 = (uint64_t)blockIdx.x * kReadBlock; r0 < n_reads; r0 += (uint64_t)gridDim.x * kReadBlock) {
+        const uint64_t r = r0 + tid;
+        if (scores)
+            for (int t = 0; t < T; ++t) s_score[t * kReadBlock + tid] = 0.f;
+        if (r < n_reads) {
+            const uint64_t s_end = read_koff[r + 1];
+            for (uint64_t s = read_koff[r]; s < s_end; ++s) {
+                const uint4 x0 = __ldg(rec + 2 * s), x1 = __ldg(rec + 2 * s + 1);
+                uint64_t R[kRecWords] = {(uint64_t)x0.x | ((uint64_t)x0.y << 32), (uint64_t)x0.z | ((uint64_t)x0.w << 32),
+                                         (uint64_t)x1.x | ((uint64_t)x1.y << 32), (uint64_t)x1.z | ((uint64_t)x1.w << 32)};
+                if ((R[0] | R[1] | R[2] | R[3]) == 0) continue;
+                // pass 1: n_j = |taxa at level j| (byte counters)
+                uint64_t nl[LW];
+#pragma unroll
+                for (int i = 0; i < LW; ++i) nl[i] = 0;
+#pragma unroll
+                for (int wi = 0; wi < kRecWords; ++wi) {
+                    uint64_t w = R[wi];
+                    while (w) {
+                        int f = (__ffsll((long long)w) - 1) / HB;
+                        uint32_t h = (uint32_t)(R[wi] >> (f * HB)) & (uint32_t)HM;
+                        w &= ~(HM << (f * HB));
+                        if (LW == 1) nl[0] += 0x0101010101010101ull >> (8 * (8 - h));
+                        else
+                            for (uint32_t j = 0; j < h; ++j) nl[j >> 3] += 1ull << (8 * (j & 7));
+                    }
+                }
+                // pass 2: contributions, k ascending (Compare.hpp:924-925: score = w(k) * (1.f / n), counts 1/n)
+#pragma unroll
+                for (int wi = 0; wi < kRecWords; ++wi) {
+                    uint64_t w = R[wi];
+                    while (w) {
+                        int f = (__ffsll((long long)w) - 1) / HB;
+                        uint32_t h = (uint32_t)(R[wi] >> (f * HB)) & (uint32_t)HM;
+                        w &= ~(HM << (f * HB));
+                        const int t = wi * FPW + f + 1;
+                        for (uint32_t j = 0; j < h; ++j) {
+                            uint32_t nj = (uint32_t)(nl[LW == 1 ? 0 : (j >> 3)] >> (8 * (j & 7))) & 255u;
+                            if (scores) s_score[t * kReadBlock + tid] += s_w[j] * (1.f / (float)nj);
+                            atomicAdd(&s_fx[j * T + t], s_invfx[nj]);
+                            if (nj == 1) atomicAdd(&s_un[j * T + t], 1ull);
+                        }
+                    }
+                }
+            }
+        }
+        if (scores) {
+            __syncthreads();
+            const uint64_t rows = min((uint64_t)kReadBlock, n_reads - r0);
+            for (uint64_t i = tid; i < rows * T; i += kReadBlock) {
+                uint32_t rr = (uint32_t)(i / T), t = (uint32_t)(i % T);
+                scores[r0 * T + i] = s_score[t * kReadBlock + rr];
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < NK * T; i += kReadBlock) {
+        if (s_fx[i]) atomicAdd(cnt_fx + i, s_fx[i]);
+        if (s_un[i]) atomicAdd(cnt_unique + i, s_un[i]);
+    }
+}
+
+__global__ void read_offsets_kernel(const uint64_t *__restrict__ koff, const uint32_t *__restrict__ first_seq, uint32_t n_reads,
+                                    uint64_t *__restrict__ out)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= n_reads) out[r] = koff[first_seq ? first_seq[r] : r];
+}
+
+__global__ void fold_counts_kernel(unsigned long long *cnt_fx, unsigned long long *cnt_unique, LevelParams lp, double *total_all,
+                                   unsigned long long *total_unique)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = lp.num_k * lp.n_taxa;
+    if (i >= n) return;
+    int j = i / lp.n_taxa, t = i % lp.n_taxa;
+    int o = (lp.num_k - 1 - j) * lp.n_taxa + t;        // ik = 0 <-> k_high (kASA.hpp:299-302)
+    total_all[o] += (double)cnt_fx[i] * (1.0 / 4294967296.0);
+    total_unique[o] += cnt_unique[i];
+    cnt_fx[i] = 0;
+    cnt_unique[i] = 0;
+}
+
+template <bool W>
+void launch_lookup_hb(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n, IndexDev idx,
+                      LevelParams lp, const uint64_t *part, uint64_t *rec)
+{
+    const unsigned tiles = (unsigned)div_up<uint64_t>(n, kLookupTile);
+    const size_t sm = (size_t)kSpanCap * (W ? 16 : 8) + (size_t)kSpanCap * 2;
+    auto go = [&](auto kern) {
+        KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        kern<<<tiles, kLookupBlock, sm, s>>>(q_lo, q_hi, inst, n, idx, lp, part, rec);
+    };
+    if (lp.hb == 3) go(lookup_kernel<W, 3>);
+    else if (lp.hb == 4) go(lookup_kernel<W, 4>);
+    else go(lookup_kernel<W, 5>);
+}
+
+}  // namespace
+
+void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, uint64_t n, IndexDev idx, LevelParams lp,
+                      uint64_t *part, uint64_t *launches)
+{
+    if (!n) return;
+    const uint64_t tiles = div_up<uint64_t>(n, kLookupTile);
+    if (idx.key_hi) partition_kernel<true><<<(unsigned)div_up<uint64_t>(tiles, 256), 256, 0, s>>>(q_lo, q_hi, n, idx, lp, part, tiles);
+    else partition_kernel<false><<<(unsigned)div_up<uint64_t>(tiles, 256), 256, 0, s>>>(q_lo, q_hi, n, idx, lp, part, tiles);
+    ++*launches;
+}
+
+void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n, IndexDev idx,
+                   LevelParams lp, const uint64_t *part, uint64_t *rec, uint64_t *launches)
+{
+    if (!n) return;
+    if (idx.key_hi) launch_lookup_hb<true>(s, q_lo, q_hi, inst, n, idx, lp, part, rec);
+    else launch_lookup_hb<false>(s, q_lo, q_hi, inst, n, idx, lp, part, rec);
+    ++*launches;
+    KASA_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_per_read(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp,
+                     float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, uint64_t *launches)
+{
+    if (!n_reads) return;
+    const size_t sm = (size_t)2 * lp.num_k * lp.n_taxa * 8 + 256 * 8 + 32 * 4 + (scores ? (size_t)lp.n_taxa * kReadBlock * 4 : 0);
+    unsigned grid = (unsigned)div_up<uint64_t>(n_reads, kReadBlock);
+    if (grid > (unsigned)kSMs * 8) grid = kSMs * 8;
+    auto go = [&](auto kern) {
+        KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        kern<<<grid, kReadBlock, sm, s>>>(reinterpret_cast<const uint4 *>(rec), read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
+    };
+    const bool small = lp.num_k <= 8;
+    if (lp.hb == 3) go(per_read_kernel<3, 1>);
+    else if (lp.hb == 4) { if (small) go(per_read_kernel<4, 1>); else go(per_read_kernel<4, 4>); }
+    else go(per_read_kernel<5, 4>);
+    ++*launches;
+    KASA_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_read_offsets(cudaStream_t s, const uint64_t *koff, const uint32_t *read_first_seq, uint32_t n_reads,
+                         uint64_t *read_koff, uint64_t *launches)
+{
+    read_offsets_kernel<<<div_up(n_reads + 1, 256u), 256, 0, s>>>(koff, read_first_seq, n_reads, read_koff);
+    ++*launches;
+}
+
+void launch_fold_counts(cudaStream_t s, unsigned long long *cnt_fx, unsigned long long *cnt_unique, LevelParams lp,
+                        double *total_all, unsigned long long *total_unique, uint64_t *launches)
+{
+    int n = lp.num_k * lp.n_taxa;
+    fold_counts_kernel<<<div_up(n, 256), 256, 0, s>>>(cnt_fx, cnt_unique, lp, total_all, total_unique);
+    ++*launches;
+}
+
+}  // namespace kasa

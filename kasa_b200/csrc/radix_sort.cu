@@ -1,0 +1,339 @@
+// radix_sort.cu — see radix_sort.cuh.
+#include "radix_sort.cuh"
+
+namespace kasa {
+
+namespace {
+
+constexpr uint64_t kFlagAgg = 1ull << 62;    // tile aggregate published
+constexpr uint64_t kFlagIncl = 2ull << 62;   // inclusive prefix published
+constexpr uint64_t kValMask = (1ull << 62) - 1;
+constexpr uint32_t kSpinLimit = 1u << 22;    // watchdog: ~seconds, never reached when healthy
+
+struct PlanDev {
+    int n_passes;
+    int src[kMaxPasses];
+    int shift[kMaxPasses];
+    uint32_t mask[kMaxPasses];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Up-front histograms of every pass digit: one read of the record arrays that feed a digit.
+// grid = multiple of 148 SMs; shared-memory counters, one global atomic per (block, pass, bin).
+template <bool HAS_W1>
+__global__ void __launch_bounds__(512) hist_kernel(const uint64_t *__restrict__ w0, const uint64_t *__restrict__ w1,
+                                                   const uint32_t *__restrict__ v, uint64_t n, PlanDev plan,
+                                                   bool need_w0, bool need_w1, bool need_v,
+                                                   unsigned long long *__restrict__ ghist)
+{
+    extern __shared__ uint32_t sh[];   // [n_passes][256]
+    const int P = plan.n_passes;
+    for (int i = threadIdx.x; i < P * kRadix; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t a = need_w0 ? ldg_stream(w0 + i) : 0;
+        uint64_t b = (HAS_W1 && need_w1) ? ldg_stream(w1 + i) : 0;
+        uint64_t c = need_v ? (uint64_t)ldg_stream(v + i) : 0;
+#pragma unroll 4
+        for (int p = 0; p < P; ++p) {
+            uint64_t word = plan.src[p] == SRC_W0 ? a : (plan.src[p] == SRC_W1 ? b : c);
+            uint32_t d = (uint32_t)(word >> plan.shift[p]) & plan.mask[p];
+            atomicAdd(&sh[p * kRadix + d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P * kRadix; i += blockDim.x)
+        if (sh[i]) atomicAdd(ghist + i, (unsigned long long)sh[i]);
+}
+
+// exclusive scan of each pass histogram (one block of 256 threads per pass), in place
+__global__ void __launch_bounds__(kRadix) hist_scan_kernel(unsigned long long *ghist)
+{
+    __shared__ unsigned long long s[kRadix];
+    unsigned long long *h = ghist + (size_t)blockIdx.x * kRadix;
+    s[threadIdx.x] = h[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < kRadix; ++i) { unsigned long long c = s[i]; s[i] = run; run += c; }
+    }
+    __syncthreads();
+    h[threadIdx.x] = s[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// One radix pass.  Tile = BLOCK x ITEMS records, warp-striped so that loads coalesce and the
+// (warp, item, lane) order equals the input order (needed for LSD stability).
+template <int BLOCK, int ITEMS, bool HAS_W1>
+__global__ void __launch_bounds__(BLOCK) onesweep_kernel(
+    const uint64_t *__restrict__ in_w0, const uint64_t *__restrict__ in_w1, const uint32_t *__restrict__ in_v,
+    uint64_t *__restrict__ out_w0, uint64_t *__restrict__ out_w1, uint32_t *__restrict__ out_v, uint64_t n, int src,
+    int shift, uint32_t mask, const unsigned long long *__restrict__ digit_start, uint64_t *status,
+    uint32_t *ticket, uint32_t *err_flag)
+{
+    constexpr int TILE = BLOCK * ITEMS;
+    constexpr int NW = BLOCK / 32;
+    static_assert(BLOCK >= kRadix, "one look-back thread per digit");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *s_buf = reinterpret_cast<uint64_t *>(smem_raw);                       // TILE x 8 B exchange buffer
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TILE * 8);   // [NW][256]
+    uint8_t *s_dig = reinterpret_cast<uint8_t *>(s_hist + NW * kRadix);             // [TILE]
+    __shared__ uint32_t s_dbase[kRadix];
+    __shared__ uint64_t s_gbase[kRadix];
+    __shared__ uint32_t s_wsum[kRadix / 32];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);   // ticket order = start order: predecessors are resident or done
+    for (int j = lane; j < kRadix; j += 32) s_hist[w * kRadix + j] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t base = (uint64_t)tile * TILE;
+    const uint32_t n_tile = (uint32_t)min((uint64_t)TILE, n - base);
+    const uint64_t wbase = base + (uint64_t)w * (32 * ITEMS) + lane;
+
+    // ---- load the digit source (and the 32-bit payload early: its latency hides behind ranking)
+    uint64_t key[ITEMS];
+    uint32_t val[ITEMS];
+    const bool v_is_src = (src == SRC_V);
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint64_t idx = wbase + (uint64_t)i * 32;
+        bool ok = idx < n;
+        uint32_t vv = ok ? ldg_stream(in_v + idx) : 0xffffffffu;
+        val[i] = vv;
+        if (src == SRC_W0) key[i] = ok ? ldg_stream(in_w0 + idx) : ~0ull;
+        else if (HAS_W1 && src == SRC_W1) key[i] = ok ? ldg_stream(in_w1 + idx) : ~0ull;
+        else key[i] = ok ? (uint64_t)vv : ~0ull;
+    }
+
+    // ---- rank inside the warp, digit by digit (match-any multisplit); padding keys carry digit `mask`
+    uint16_t rk[ITEMS];
+    uint32_t *my_hist = s_hist + w * kRadix;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        uint32_t peers = __match_any_sync(kFull, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t before = __popc(peers & lanemask_lt());
+        uint32_t prev = 0;
+        if (lane == leader) {
+            prev = my_hist[d];
+            my_hist[d] = prev + __popc(peers);
+        }
+        prev = __shfl_sync(kFull, prev, leader);
+        rk[i] = (uint16_t)(prev + before);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive offsets over warps, tile count, tile-local digit base
+    uint32_t count = 0;
+    if (tid < kRadix) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < NW; ++ww) {
+            uint32_t c = s_hist[ww * kRadix + tid];
+            s_hist[ww * kRadix + tid] = run;
+            run += c;
+        }
+        count = run;
+        if ((uint32_t)tid == mask) count -= (uint32_t)(TILE - n_tile);   // padding sorts last inside digit `mask`
+    }
+    uint32_t incl = count;
+    if (tid < kRadix) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[w] = incl;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t x = (tid < kRadix / 32) ? s_wsum[tid] : 0;
+        uint32_t xi = x;
+#pragma unroll
+        for (int o = 1; o < kRadix / 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(kFull, xi, o);
+            if (lane >= o) xi += t;
+        }
+        if (tid < kRadix / 32) s_wsum[tid] = xi - x;
+    }
+    __syncthreads();
+
+    // ---- decoupled look-back, one thread per digit
+    if (tid < kRadix) {
+        const uint32_t dbase = incl - count + s_wsum[w];
+        uint64_t *my = status + (uint64_t)tile * kRadix + tid;
+        uint64_t excl = 0;
+        if (tile == 0) {
+            st_relaxed_gpu(my, kFlagIncl | (uint64_t)count);
+        } else {
+            st_relaxed_gpu(my, kFlagAgg | (uint64_t)count);
+            int64_t t = (int64_t)tile - 1;
+            uint32_t spins = 0;
+            while (true) {
+                uint64_t s = ld_relaxed_gpu(status + (uint64_t)t * kRadix + tid);
+                uint64_t f = s >> 62;
+                if (f == 0) {
+                    if (++spins > kSpinLimit || ((spins & 1023u) == 0 && *(volatile uint32_t *)err_flag)) {
+                        atomicExch(err_flag, 1u);
+                        break;
+                    }
+                    __nanosleep(40);
+                    continue;
+                }
+                excl += s & kValMask;
+                if (f == 2 || t == 0) break;
+                --t;
+            }
+            st_relaxed_gpu(my, kFlagIncl | (excl + count));
+        }
+        s_dbase[tid] = dbase;
+        s_gbase[tid] = (uint64_t)digit_start[tid] + excl - dbase;
+    }
+    __syncthreads();
+
+    // ---- exchange through shared memory: digit-sorted tile, then coalesced runs to HBM
+    uint16_t pos[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        uint32_t p = s_dbase[d] + my_hist[d] + rk[i];
+        pos[i] = (uint16_t)p;
+        s_dig[p] = (uint8_t)d;
+        if (!v_is_src) s_buf[p] = key[i];
+    }
+    __syncthreads();
+    if (!v_is_src) {
+        uint64_t *out_src = (HAS_W1 && src == SRC_W1) ? out_w1 : out_w0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            uint32_t p = tid + j * BLOCK;
+            if (p < n_tile) out_src[s_gbase[s_dig[p]] + p] = s_buf[p];
+        }
+        __syncthreads();
+    }
+    // the other 64-bit word(s)
+    const int n_other = v_is_src ? (HAS_W1 ? 2 : 1) : (HAS_W1 ? 1 : 0);
+    for (int o = 0; o < n_other; ++o) {
+        const bool take_w1 = HAS_W1 && (v_is_src ? (o == 1) : (src == SRC_W0));
+        const uint64_t *inp = take_w1 ? in_w1 : in_w0;
+        uint64_t *outp = take_w1 ? out_w1 : out_w0;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            uint64_t idx = wbase + (uint64_t)i * 32;
+            if (idx < n) s_buf[pos[i]] = ldg_stream(inp + idx);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            uint32_t p = tid + j * BLOCK;
+            if (p < n_tile) outp[s_gbase[s_dig[p]] + p] = s_buf[p];
+        }
+        __syncthreads();
+    }
+    // the 32-bit payload
+    uint32_t *s_v = reinterpret_cast<uint32_t *>(s_buf);
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) s_v[pos[i]] = val[i];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        uint32_t p = tid + j * BLOCK;
+        if (p < n_tile) out_v[s_gbase[s_dig[p]] + p] = s_v[p];
+    }
+}
+
+template <int BLOCK, int ITEMS>
+constexpr size_t onesweep_smem()
+{
+    return (size_t)BLOCK * ITEMS * 8 + (size_t)(BLOCK / 32) * kRadix * 4 + (size_t)BLOCK * ITEMS;
+}
+
+}  // namespace
+
+SortPlan plan_for_kmer_bits(int key_bits)
+{
+    SortPlan p{};
+    int done = 0;
+    while (done < key_bits) {
+        int src = done < 64 ? SRC_W0 : SRC_W1;
+        int in_word = done < 64 ? done : done - 64;
+        int bits = kRadixBits;
+        if (in_word + bits > 64) bits = 64 - in_word;
+        if (done + bits > key_bits) bits = key_bits - done;
+        p.pass[p.n_passes++] = SortPass{src, in_word, (1u << bits) - 1u};
+        done += bits;
+    }
+    return p;
+}
+
+int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint64_t n, const SortPlan &plan,
+               void *workspace, uint32_t *err_flag, uint64_t *launches)
+{
+    if (n == 0 || plan.n_passes == 0) return start_buf;
+    const bool has_w1 = buf.w1[0] != nullptr;
+    auto *ghist = reinterpret_cast<unsigned long long *>(workspace);
+    auto *ticket = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(workspace) + (size_t)kMaxPasses * kRadix * 8);
+    auto *status = reinterpret_cast<uint64_t *>(reinterpret_cast<char *>(workspace) + (size_t)kMaxPasses * kRadix * 8 + 256);
+    const uint64_t tiles = div_up<uint64_t>(n, kSortTile);
+    KASA_REQUIRE(tiles < (1ull << 32), -1, "radix_sort: too many records for one call");
+
+    PlanDev pd{};
+    pd.n_passes = plan.n_passes;
+    bool need[3] = {false, false, false};
+    for (int p = 0; p < plan.n_passes; ++p) {
+        pd.src[p] = plan.pass[p].src;
+        pd.shift[p] = plan.pass[p].shift;
+        pd.mask[p] = plan.pass[p].mask;
+        need[plan.pass[p].src] = true;
+    }
+    KASA_CUDA_TRY(cudaMemsetAsync(ghist, 0, (size_t)kMaxPasses * kRadix * 8 + 256, stream));
+    {
+        int grid = kSMs * 4;
+        uint64_t want = div_up<uint64_t>(n, 512);
+        if (want < (uint64_t)grid) grid = (int)want;
+        size_t sm = (size_t)plan.n_passes * kRadix * 4;
+        if (has_w1)
+            hist_kernel<true><<<grid, 512, sm, stream>>>(buf.w0[start_buf], buf.w1[start_buf], buf.v[start_buf], n, pd,
+                                                         need[0], need[1], need[2], ghist);
+        else
+            hist_kernel<false><<<grid, 512, sm, stream>>>(buf.w0[start_buf], nullptr, buf.v[start_buf], n, pd, need[0],
+                                                          need[1], need[2], ghist);
+        hist_scan_kernel<<<plan.n_passes, kRadix, 0, stream>>>(ghist);
+        *launches += 2;
+    }
+    constexpr size_t sm_pass = onesweep_smem<kSortBlock, kSortItems>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        KASA_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<kSortBlock, kSortItems, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pass));
+        KASA_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<kSortBlock, kSortItems, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pass));
+        attr_done = true;
+    }
+    int cur = start_buf;
+    for (int p = 0; p < plan.n_passes; ++p) {
+        KASA_CUDA_TRY(cudaMemsetAsync(ticket, 0, 4, stream));
+        KASA_CUDA_TRY(cudaMemsetAsync(status, 0, tiles * kRadix * 8, stream));
+        const int nxt = cur ^ 1;
+        if (has_w1)
+            onesweep_kernel<kSortBlock, kSortItems, true><<<(unsigned)tiles, kSortBlock, sm_pass, stream>>>(
+                buf.w0[cur], buf.w1[cur], buf.v[cur], buf.w0[nxt], buf.w1[nxt], buf.v[nxt], n, plan.pass[p].src,
+                plan.pass[p].shift, plan.pass[p].mask, ghist + (size_t)p * kRadix, status, ticket, err_flag);
+        else
+            onesweep_kernel<kSortBlock, kSortItems, false><<<(unsigned)tiles, kSortBlock, sm_pass, stream>>>(
+                buf.w0[cur], nullptr, buf.v[cur], buf.w0[nxt], nullptr, buf.v[nxt], n, plan.pass[p].src,
+                plan.pass[p].shift, plan.pass[p].mask, ghist + (size_t)p * kRadix, status, ticket, err_flag);
+        *launches += 1;
+        cur = nxt;
+    }
+    KASA_CUDA_TRY(cudaGetLastError());
+    return cur;
+}
+
+}  // namespace kasa

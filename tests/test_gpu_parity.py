@@ -1,0 +1,266 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI (libkasa_b200.so), against the
+CPU oracle (oracle/kasa_oracle.c, itself pinned on reference outputs) and against the golden outputs of the
+reference binary (tests/golden/*).
+
+Tolerances (stated here as the contract):
+  * k-mer encodings, sort order, index / trie / frequency bytes, unique counts, per-read taxa sets: bit-exact.
+  * non-unique counts (sum of 1/|taxa| in 2^-32 fixed point): <= 1e-6 relative to the oracle's doubles.
+  * per-read k-mer scores, KASA_SCORE_FAST (fp32, canonical order): <= 4e-6 relative to the reference's own
+    fp32 sums (the reference's order depends on the batch composition).
+"""
+import numpy as np
+import pytest
+
+import golden_util as G
+from kasa_b200 import Context, KasaError, Params, synth
+from kasa_b200 import capi
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FAST_RTOL = 4e-6
+COUNT_RTOL = 1e-6
+
+
+def _ctx(**kw):
+    p = Params(**kw)
+    return Context(p)
+
+
+def _k12_reads():
+    return [s for _, s in G.fastq("k12")]
+
+
+# ----------------------------------------------------------------------------------------- extraction
+@pytest.mark.parametrize("frames,k_low", [(6, 7), (3, 7), (6, 12), (3, 1)])
+def test_extract_matches_oracle_k12(frames, k_low):
+    reads = _k12_reads() + [b"", b"ACG", b"acgtnACGTN" * 30, b"N" * 40 + b"ACGT" * 20]
+    ctx = _ctx(frames=frames, k_low=k_low, k_high=12)
+    lo, hi, rid = ctx.dbg_extract(reads)
+    want_k, want_id = O.read_kmers([[r] for r in reads], 12, k_low, frames == 6)
+    assert len(lo) == len(want_k)
+    assert np.array_equal(lo, want_k[:, 0])
+    assert np.array_equal(rid, want_id)
+    ctx.close()
+
+
+def test_extract_matches_oracle_k25_paired():
+    a, b = G.fastq("k25", "reads_1.fq.gz"), G.fastq("k25", "reads_2.fq.gz")
+    seqs, first = [], [0]
+    for x, y in zip(a, b):
+        seqs += [x[1], y[1]]
+        first.append(len(seqs))
+    ctx = _ctx(highest_k=25, k_high=25, k_low=7, frames=6)
+    lo, hi, rid = ctx.dbg_extract(seqs, read_first_seq=np.array(first, dtype=np.uint32))
+    want_k, want_id = O.read_kmers([[x[1], y[1]] for x, y in zip(a, b)], 25, 7, True)
+    assert np.array_equal(lo, want_k[:, 0]) and np.array_equal(hi, want_k[:, 1])
+    assert np.array_equal(rid, want_id)
+    ctx.close()
+
+
+def test_custom_codon_table_is_a_parameter():
+    table = O.default_codon_table().copy()
+    table[0] = ord("Q")          # AAA -> Q instead of K
+    reads = [b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA", b"ACGTTGCAAAAGGGCCCTTTAAACCCGGGTTTACGTACGTAAAACGT"]
+    ctx = _ctx(codon_table=table)
+    lo, _, _ = ctx.dbg_extract(reads)
+    want, _ = O.read_kmers([[r] for r in reads], 12, 7, False, table)
+    assert np.array_equal(lo, want[:, 0])
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------- radix sort
+@pytest.mark.parametrize("n", [0, 1, 31, 4095, 4096, 4097, 100_003, 1_500_000])
+def test_radix_sort_pairs_matches_stable_sort(n):
+    rng = np.random.default_rng(n + 1)
+    keys = rng.integers(0, 1 << 60, size=n, dtype=np.uint64)
+    if n > 10:
+        keys[: n // 3] = keys[n // 3: 2 * (n // 3)]          # duplicates: LSD must be stable
+        keys[-3:] = [0, (1 << 60) - 1, 0]
+    vals = np.arange(n, dtype=np.uint32)
+    ctx = _ctx(max_batch_kmers=max(n, 1) + 8)
+    k, v = ctx.dbg_sort_pairs(keys, vals, 0, 60)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order])
+    assert np.array_equal(v, vals[order])
+    ctx.close()
+
+
+def test_radix_sort_partial_bits_and_skewed_digits():
+    n = 300_000
+    rng = np.random.default_rng(5)
+    keys = (rng.integers(0, 4, size=n, dtype=np.uint64) << np.uint64(40)) | rng.integers(0, 7, size=n, dtype=np.uint64)
+    vals = rng.integers(0, 1 << 32, size=n, dtype=np.uint32)
+    ctx = _ctx(max_batch_kmers=n + 8)
+    k, v = ctx.dbg_sort_pairs(keys, vals, 0, 44)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order]) and np.array_equal(v, vals[order])
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------- identify
+def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None):
+    _, taxids, _ = G.content(case)
+    idx = G.index(case)
+    if paired:
+        a, b = G.fastq(case, "reads_1.fq.gz"), G.fastq(case, "reads_2.fq.gz")
+        reads = [[x[1], y[1]] for x, y in zip(a, b)]
+    else:
+        reads = [[x[1]] for x in G.fastq(case)]
+    ctx = _ctx(highest_k=K, k_high=k_high, k_low=k_low, frames=6 if six else 3)
+    ctx.load_index(idx, taxids)
+    pieces = [reads] if split is None else [reads[:split], reads[split:]]
+    scores, n_kmers = [], 0
+    for part in pieces:
+        seqs, first = [], [0]
+        for mates in part:
+            seqs += mates
+            first.append(len(seqs))
+        n, sc, _ = ctx.identify_batch(seqs, np.array(first, dtype=np.uint32))
+        n_kmers += n
+        scores.append(sc)
+    scores = np.concatenate(scores)
+    ca, cu, total = ctx.identify_finish()
+    ctx.close()
+    ora = O.identify_reads(reads, idx, K, k_high, k_low, six, taxids)
+    assert n_kmers == total == ora.n_kmers == G.n_kmers(case, tag)
+    assert np.array_equal(cu, ora.count_unique)                               # exact integers
+    np.testing.assert_allclose(ca, ora.count_all, rtol=COUNT_RTOL, atol=1e-9)
+    assert np.array_equal(scores > 0, ora.scores > 0)                         # same taxa per read
+    np.testing.assert_allclose(scores, ora.scores, rtol=FAST_RTOL, atol=0)
+    # ... and against what the reference binary printed
+    pr = G.per_read(case, tag)
+    tax2idx = {int(t): i for i, t in enumerate(taxids)}
+    cells = 0
+    for r, rec in enumerate(pr):
+        mine = {int(taxids[t]) for t in range(1, len(taxids)) if scores[r, t] > 0}
+        assert mine == set(rec["hits"])
+        for tax, (score, _, _) in rec["hits"].items():
+            cells += 1
+            assert abs(float(scores[r, tax2idx[tax]]) - float(score)) <= FAST_RTOL * float(score)
+    assert cells > 0
+    _, rows = G.profile(case, tag)
+    numK = k_high - k_low + 1
+    for t in range(1, len(taxids)):
+        row = rows.get(int(taxids[t]))
+        if row is not None:
+            assert [int(x) for x in row[0:numK]] == [int(x) for x in cu[:, t]]
+    return scores, ca, cu
+
+
+def test_identify_k12_six_frames():
+    _identify_case("k12", "six_12_7", 12, 12, 7, True)
+
+
+def test_identify_k12_three_frames_k11_8():
+    _identify_case("k12", "three_11_8", 12, 11, 8, False)
+
+
+def test_identify_k12_single_level():
+    _identify_case("k12", "six_12_12", 12, 12, 12, True)
+
+
+def test_identify_k25_paired():
+    _identify_case("k25", "six_25_7", 25, 25, 7, True, paired=True)
+
+
+def test_identify_is_batch_independent_and_deterministic():
+    s1, ca1, cu1 = _identify_case("k12", "six_12_7", 12, 12, 7, True)
+    s2, ca2, cu2 = _identify_case("k12", "six_12_7", 12, 12, 7, True, split=137)
+    assert np.array_equal(s1, s2)            # canonical-order fp32 scores do not depend on the batching
+    assert np.array_equal(cu1, cu2)
+    np.testing.assert_allclose(ca1, ca2, rtol=1e-12)
+
+
+def test_identify_requires_index_and_reports_errors():
+    ctx = _ctx()
+    with pytest.raises(KasaError):
+        ctx.identify_batch([b"ACGT" * 20])
+    _, taxids, _ = G.content("k12")
+    idx = G.index("k12").copy()
+    idx["tax"][5] = 424242                      # taxid missing from the content table
+    with pytest.raises(KasaError):
+        ctx.load_index(idx, taxids)
+    bad = G.index("k12").copy()
+    bad[[10, 20]] = bad[[20, 10]]               # not sorted
+    with pytest.raises(KasaError):
+        ctx.load_index(bad, taxids)
+    ctx.close()
+
+
+def test_profile_only_mode_gives_same_counts():
+    _, taxids, _ = G.content("k12")
+    idx = G.index("k12")
+    reads = _k12_reads()
+    out = []
+    for mode in (capi.SCORE_NONE, capi.SCORE_FAST):
+        ctx = _ctx(frames=6, score_mode=mode)
+        ctx.load_index(idx, taxids)
+        ctx.identify_batch(reads)
+        out.append(ctx.identify_finish())
+        ctx.close()
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][0], out[1][0])
+
+
+# ----------------------------------------------------------------------------------------- build
+@pytest.mark.parametrize("case,K,six", [("k12", 12, False), ("k12_build6", 12, True), ("k25", 25, False)])
+def test_build_matches_reference_files(case, K, six):
+    strings = O.fasta_build_strings(G.gz(case, "ref.fa.gz"), G.acc2tax(case), K, six)
+    _, taxids, _ = G.content(case)
+    ctx = _ctx(highest_k=K, k_high=K, k_low=7, max_batch_kmers=1 << 20)
+    # several pushes, as the host would do per FASTA piece
+    step = max(1, len(strings) // 3)
+    for i in range(0, len(strings), step):
+        part = strings[i:i + step]
+        ctx.build_push([s for s, _ in part], [t for _, t in part])
+    rec, trie = ctx.build_finish()
+    assert rec.tobytes() == G.index(case).tobytes()
+    assert trie.tobytes() == G.trie(case).tobytes()
+    assert np.array_equal(ctx.build_frequency(taxids), G.frequency(case))
+    # the freshly built index is usable without a host round trip
+    ctx.index_from_build(taxids)
+    assert ctx.index_size == len(rec)
+    ctx.close()
+
+
+def test_build_brick_overflow_compacts_and_continues():
+    strings = O.fasta_build_strings(G.gz("k12", "ref.fa.gz"), G.acc2tax("k12"), 12, False)
+    ctx = _ctx(max_batch_kmers=60_000)      # smaller than the 48k windows x 2 pushes of duplicates
+    for _ in range(3):                       # the same data three times: dedup must absorb it
+        ctx.build_push([s for s, _ in strings], [t for _, t in strings])
+    rec, _ = ctx.build_finish()
+    assert rec.tobytes() == G.index("k12").tobytes()
+    ctx.close()
+
+
+def test_build_then_identify_round_trip_large():
+    """Property test at a size the oracle cannot reach in seconds: reads cut from the reference without errors
+    must hit their own taxon uniquely at k=12 wherever the 12-mer is unique; totals must be consistent."""
+    n_taxa, glen, n_reads = 8, 250_000, 40_000
+    ctx = _ctx(frames=6, max_batch_kmers=1 << 24, max_batch_seqs=1 << 16, max_batch_bases=1 << 23)
+    ctx.synth_build_reference(seed=21, n_taxa=n_taxa, genome_len=glen)
+    n_entries, n_trie = ctx.build_finish(fetch=False)
+    assert 0.98 * n_taxa * glen < n_entries <= n_taxa * (glen + 33)
+    taxids = np.array([0] + [1000 + t for t in range(n_taxa)], dtype=np.uint32)
+    ctx.index_from_build(taxids)
+    reads = ctx.synth_reads(21, 22, 0, n_reads, n_taxa, glen, 150, subst_ppm=0, n_ppm=0)
+    np.testing.assert_array_equal(reads, synth.reads_ascii(21, 22, 0, n_reads, n_taxa, glen, 150, 0, 0))
+    data = (reads.reshape(-1), np.arange(n_reads, dtype=np.uint64) * 150, np.full(n_reads, 150, dtype=np.uint32))
+    n_kmers, scores, _ = ctx.identify_batch(data)
+    assert n_kmers == n_reads * 260
+    truth, _, _ = synth.read_params(22, np.arange(n_reads), n_taxa, glen, 150)
+    assert np.array_equal(np.argmax(scores, axis=1) - 1, truth)
+    ca, cu, _ = ctx.identify_finish()
+    # an error-free 150 bp read has 115 windows free of marker letters at k=12 and 130 at k=7 on its matching strand;
+    # sum over taxa of the non-unique counts = number of matched instances
+    assert abs(ca[0].sum() - n_reads * 115) <= 0.01 * n_reads * 115
+    assert ca[-1].sum() >= n_reads * 130 * 0.999
+    assert np.all(np.diff(ca.sum(axis=1)) >= 0)          # lower k never matches less
+    ctx.close()
+
+
+def test_synth_generators_match_numpy():
+    ctx = _ctx()
+    r = ctx.synth_reads(3, 4, 1000, 500, 7, 5000, 150)
+    assert np.array_equal(r, synth.reads_ascii(3, 4, 1000, 500, 7, 5000, 150))
+    ctx.close()
