@@ -86,6 +86,19 @@ int kasa_ctx_synchronize(kasa_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t kasa_ctx_launch_count(const kasa_ctx *ctx);
 
+/* Device time per identify stage, summed over the batches since the last reset (CUDA events on the
+ * context's stream).  ms[KASA_N_STAGES]; *batches = number of batches summed; *sort_passes = radix passes
+ * summed (so ms[KASA_STAGE_SORT_PASSES] / *sort_passes is the average duration of the dominant kernel).   */
+#define KASA_STAGE_INPUT        0   /* H2D copies, 2-bit packing, k-mer counts and offsets                */
+#define KASA_STAGE_EXTRACT      1   /* translation + k-mer packing                                        */
+#define KASA_STAGE_SORT_HIST    2   /* digit histograms                                                   */
+#define KASA_STAGE_SORT_PASSES  3   /* all radix passes                                                   */
+#define KASA_STAGE_LOOKUP       4   /* partition + index lookup (match records)                           */
+#define KASA_STAGE_PER_READ     5   /* per-read scores and per-taxon counts                               */
+#define KASA_STAGE_OUTPUT       6   /* D2H of the score matrix                                            */
+#define KASA_N_STAGES           7
+int kasa_ctx_stage_times(kasa_ctx *ctx, double *ms, uint64_t *batches, uint64_t *sort_passes, uint64_t *kmers, int reset);
+
 /* --------------------------------------------------------------------------------------------------- */
 /* index                                                                                                */
 

@@ -26,7 +26,7 @@ TRIE = np.dtype([("count", "<u8"), ("prefix", "<u4")])                # packedBi
 
 EXPORTS = [
     "kasa_abi_version", "kasa_ctx_create", "kasa_ctx_destroy", "kasa_last_error", "kasa_ctx_set_stream",
-    "kasa_ctx_synchronize", "kasa_ctx_launch_count", "kasa_index_load", "kasa_index_from_build", "kasa_index_size",
+    "kasa_ctx_synchronize", "kasa_ctx_launch_count", "kasa_ctx_stage_times", "kasa_index_load", "kasa_index_from_build", "kasa_index_size",
     "kasa_identify_batch", "kasa_identify_finish", "kasa_build_push", "kasa_build_finish", "kasa_build_fetch",
     "kasa_build_frequency", "kasa_dbg_extract", "kasa_dbg_sort_pairs", "kasa_synth_build_reference", "kasa_synth_reads",
 ]
@@ -84,6 +84,8 @@ def load_library():
     L.kasa_ctx_synchronize.argtypes = [C.c_void_p]
     L.kasa_ctx_launch_count.argtypes = [C.c_void_p]
     L.kasa_ctx_launch_count.restype = C.c_uint64
+    L.kasa_ctx_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_uint64), C.c_int]
     L.kasa_index_size.argtypes = [C.c_void_p]
     L.kasa_index_size.restype = C.c_uint64
     L.kasa_index_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32]
@@ -171,6 +173,15 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.kasa_ctx_launch_count(self.h))
+
+    STAGES = ("input", "extract", "sort_hist", "sort_passes", "lookup", "per_read", "output")
+
+    def stage_times(self, reset: bool = False):
+        """-> (dict stage -> ms summed over batches, batches, radix passes, k-mers)."""
+        ms = np.zeros(len(self.STAGES), dtype=np.float64)
+        b, p, k = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.kasa_ctx_stage_times(self.h, _ptr(ms), C.byref(b), C.byref(p), C.byref(k), int(reset)))
+        return dict(zip(self.STAGES, ms.tolist())), int(b.value), int(p.value), int(k.value)
 
     @property
     def index_size(self) -> int:

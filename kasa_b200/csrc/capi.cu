@@ -55,6 +55,9 @@ struct kasa_ctx {
     uint64_t n_trie = 0;
     uint32_t *d_trie_words = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t sev[KASA_N_STAGES + 1] = {};
+    double stage_ms[KASA_N_STAGES] = {};
+    uint64_t stage_batches = 0, stage_passes = 0, stage_kmers = 0;
 };
 
 namespace {
@@ -137,7 +140,7 @@ void ensure_workspace(kasa_ctx *c)
     c->d_seq_len = dev_alloc<uint32_t>(c, (size_t)ns + 1);
     c->d_read_first = dev_alloc<uint32_t>(c, (size_t)ns + 1);
     c->d_taxid = dev_alloc<uint32_t>(c, (size_t)ns + 1);
-    c->d_part = dev_alloc<uint64_t>(c, 2 * (size_t)div_up<uint64_t>(cap, kLookupTile) + 2);
+    c->d_part = dev_alloc<uint64_t>(c, 2 * (size_t)div_up<uint64_t>(cap, 32) + 2);
     c->d_rec = dev_alloc<uint64_t>(c, (size_t)(cap + 2) * kRecWords);
     c->ws_ready = true;
 }
@@ -322,6 +325,7 @@ int kasa_ctx_create(const kasa_params *p, kasa_ctx **out)
         c->own_stream = true;
         KASA_CUDA_TRY(cudaEventCreate(&c->ev0));
         KASA_CUDA_TRY(cudaEventCreate(&c->ev1));
+        for (auto &e : c->sev) KASA_CUDA_TRY(cudaEventCreate(&e));
         uint8_t table[512];
         if (p->codon_table) std::memcpy(table, p->codon_table, 512); else builtin_codon_table(table);
         upload_codon_table(table);
@@ -341,6 +345,7 @@ void kasa_ctx_destroy(kasa_ctx *c)
     for (void *p : c->allocs) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (auto e : c->sev) if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -365,6 +370,20 @@ int kasa_ctx_synchronize(kasa_ctx *c)
 }
 
 uint64_t kasa_ctx_launch_count(const kasa_ctx *c) { return c ? c->launches : 0; }
+
+int kasa_ctx_stage_times(kasa_ctx *c, double *ms, uint64_t *batches, uint64_t *sort_passes, uint64_t *kmers, int reset)
+{
+    if (!c) return KASA_ERR_ARG;
+    if (ms) for (int i = 0; i < KASA_N_STAGES; ++i) ms[i] = c->stage_ms[i];
+    if (batches) *batches = c->stage_batches;
+    if (sort_passes) *sort_passes = c->stage_passes;
+    if (kmers) *kmers = c->stage_kmers;
+    if (reset) {
+        for (auto &x : c->stage_ms) x = 0;
+        c->stage_batches = c->stage_passes = c->stage_kmers = 0;
+    }
+    return KASA_OK;
+}
 uint64_t kasa_index_size(const kasa_ctx *c) { return c ? c->idx_n : 0; }
 
 int kasa_index_load(kasa_ctx *c, const void *entries, uint64_t n, int bits, const uint32_t *taxid_of_idx, uint32_t n_taxa)
@@ -463,6 +482,7 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in)
     exclusive_scan_u64(c->stream, c->d_koff, ns, c->d_scan_tmp, &c->launches);
     const uint64_t n = read_u64(c, c->d_koff + ns);
     KASA_REQUIRE(n <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "batch yields more k-mers than max_batch_kmers");
+    KASA_CUDA_TRY(cudaEventRecord(c->sev[1], c->stream));
     launch_extract_identify(c->stream, ps, kp, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     return n;
@@ -475,34 +495,51 @@ int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resul
     KASA_REQUIRE(c->idx_lo, KASA_ERR_STATE, "kasa_identify_batch before an index was loaded");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
     KASA_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(c->sev[0], c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(c->sev[1], c->stream));      // re-recorded by extract_batch when there is work
     const uint64_t n = extract_batch(c, in);
     out->n_kmers = n;
     const bool want_scores = c->p.score_mode != KASA_SCORE_NONE;
+    SortPlan plan = plan_for_kmer_bits(5 * c->K);
+    KASA_CUDA_TRY(cudaEventRecord(c->sev[2], c->stream));
     if (n) {
-        SortPlan plan = plan_for_kmer_bits(5 * c->K);
-        const int cur = radix_sort(c->stream, c->sb, 0, n, plan, c->sort_ws, c->d_err, &c->launches);
+        const int cur = radix_sort(c->stream, c->sb, 0, n, plan, c->sort_ws, c->d_err, &c->launches, c->sev[3]);
+        KASA_CUDA_TRY(cudaEventRecord(c->sev[4], c->stream));
         const uint32_t *first = in->read_first_seq
                                     ? stage_array(c, in->read_first_seq, (size_t)in->n_reads + 1, c->d_read_first, in->location)
                                     : nullptr;
         launch_read_offsets(c->stream, c->d_koff, first, in->n_reads, c->d_read_koff, &c->launches);
         IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n};
         LevelParams lp = level_params(c);
-        launch_partition(c->stream, c->sb.w0[cur], c->sb.w1[cur], n, idx, lp, c->d_part, &c->launches);
-        launch_lookup(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, idx, lp, c->d_part, c->d_rec, &c->launches);
+        const uint32_t tq = lookup_tile_queries(n, c->idx_n);
+        launch_partition(c->stream, c->sb.w0[cur], c->sb.w1[cur], n, idx, lp, c->d_part, tq, &c->launches);
+        launch_lookup(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, idx, lp, c->d_part, c->d_rec, tq, &c->launches);
+        KASA_CUDA_TRY(cudaEventRecord(c->sev[5], c->stream));
         launch_per_read(c->stream, c->d_rec, c->d_read_koff, in->n_reads, lp, want_scores ? c->d_scores : nullptr, c->d_cnt_fx,
                         c->d_cnt_un, &c->launches);
         launch_fold_counts(c->stream, c->d_cnt_fx, c->d_cnt_un, lp, c->d_tot_all, c->d_tot_un, &c->launches);
-    } else if (want_scores && in->n_reads) {
-        KASA_CUDA_TRY(cudaMemsetAsync(c->d_scores, 0, (size_t)in->n_reads * c->n_taxa * 4, c->stream));
+    } else {
+        for (int i = 3; i <= 5; ++i) KASA_CUDA_TRY(cudaEventRecord(c->sev[i], c->stream));
+        if (want_scores && in->n_reads) KASA_CUDA_TRY(cudaMemsetAsync(c->d_scores, 0, (size_t)in->n_reads * c->n_taxa * 4, c->stream));
     }
+    KASA_CUDA_TRY(cudaEventRecord(c->sev[6], c->stream));
     KASA_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     if (want_scores && out->scores && in->n_reads) {
         KASA_CUDA_TRY(cudaMemcpyAsync(out->scores, c->d_scores, (size_t)in->n_reads * c->n_taxa * 4,
                                       out->scores_location == KASA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                                       c->stream));
     }
+    KASA_CUDA_TRY(cudaEventRecord(c->sev[7], c->stream));
     check_device_flags(c);     // synchronises the stream
     KASA_CUDA_TRY(cudaEventElapsedTime(&out->gpu_ms, c->ev0, c->ev1));
+    for (int i = 0; i < KASA_N_STAGES; ++i) {
+        float ms = 0.f;
+        KASA_CUDA_TRY(cudaEventElapsedTime(&ms, c->sev[i], c->sev[i + 1]));
+        c->stage_ms[i] += ms;
+    }
+    c->stage_batches += 1;
+    c->stage_passes += n ? plan.n_passes : 0;
+    c->stage_kmers += n;
     c->n_kmers_total += n;
     KASA_API_END(c)
 }

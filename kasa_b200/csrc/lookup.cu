@@ -100,28 +100,31 @@ struct SmemAcc {
     __device__ __forceinline__ uint32_t taxon(int64_t i) const { return tax[i - a]; }
 };
 
+// first position in [lo, hi) whose key is >= q.  The trip count depends only on hi - lo, which is uniform
+// across a CTA in the lookup kernel, so the search does not diverge.
 template <bool W, class Acc>
 __device__ __forceinline__ int64_t lower_bound(const Acc &acc, int64_t lo, int64_t hi, const Key &q)
 {
-    while (lo < hi) {
-        int64_t mid = lo + ((hi - lo) >> 1);
-        if (key_lt<W>(acc.template key<W>(mid), q)) lo = mid + 1; else hi = mid;
+    int64_t n = hi - lo;
+    if (n <= 0) return lo;
+    while (n > 1) {
+        int64_t half = n >> 1;
+        if (key_lt<W>(acc.template key<W>(lo + half - 1), q)) lo += half;
+        n -= half;
     }
-    return lo;
+    return lo + (key_lt<W>(acc.template key<W>(lo), q) ? 1 : 0);
 }
 
+// R points at this thread's record column in shared memory: word wi lives at R[wi * kLookupBlock]
 template <int HB>
-__device__ __forceinline__ void rec_update(uint64_t (&R)[kRecWords], int slot, uint32_t h)
+__device__ __forceinline__ void rec_update(uint64_t *R, int slot, uint32_t h)
 {
     constexpr int FPW = 64 / HB;
     constexpr uint64_t HM = (1ull << HB) - 1;
     const int wi = slot / FPW, sh = (slot % FPW) * HB;
-    uint64_t w = wi == 0 ? R[0] : (wi == 1 ? R[1] : (wi == 2 ? R[2] : R[3]));
+    uint64_t w = R[wi * kLookupBlock];
     uint32_t cur = (uint32_t)(w >> sh) & (uint32_t)HM;
-    if (h > cur) {
-        uint64_t add = (uint64_t)(h - cur) << sh;
-        if (wi == 0) R[0] += add; else if (wi == 1) R[1] += add; else if (wi == 2) R[2] += add; else R[3] += add;
-    }
+    if (h > cur) R[wi * kLookupBlock] = w + ((uint64_t)(h - cur) << sh);
 }
 
 // Set semantics of Compare.hpp:785-1041 for one query instance: every index entry whose first c >= k_low
@@ -129,7 +132,7 @@ __device__ __forceinline__ void rec_update(uint64_t (&R)[kRecWords], int slot, u
 // level not killed by a '^' letter (Compare.hpp:836, 897).
 template <bool W, int HB, class Acc>
 __device__ __forceinline__ void match_query(const Acc &acc, int64_t a, int64_t b, const Key &q, const LevelParams &lp,
-                                            uint64_t (&R)[kRecWords])
+                                            uint64_t *R)
 {
     int kv = lp.k_low - 1;
     for (int k = lp.k_low; k <= lp.k_high; ++k) {
@@ -153,11 +156,11 @@ __device__ __forceinline__ void match_query(const Acc &acc, int64_t a, int64_t b
 template <bool W>
 __global__ void __launch_bounds__(256) partition_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
                                                         uint64_t n, IndexDev idx, LevelParams lp, uint64_t *__restrict__ part,
-                                                        uint64_t n_tiles)
+                                                        uint64_t n_tiles, uint32_t tq)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    uint64_t i0 = t * kLookupTile, i1 = min(n, i0 + kLookupTile) - 1;
+    uint64_t i0 = t * tq, i1 = min(n, i0 + tq) - 1;
     Key first{q_lo[i0], W ? q_hi[i0] : 0ull}, last{q_lo[i1], W ? q_hi[i1] : 0ull};
     GmemAcc acc{idx.key_lo, idx.key_hi, idx.tax};
     Key f = prefix_floor<W>(first, lp.k_low, lp.K), c = prefix_ceil<W>(last, lp.k_low, lp.K);
@@ -167,21 +170,22 @@ __global__ void __launch_bounds__(256) partition_kernel(const uint64_t *__restri
     part[2 * t + 1] = (uint64_t)b;
 }
 
-constexpr int kSpanCap = 4608;   // index entries staged per tile (avg span = tile * index/queries)
+constexpr int kSpanCap = 2560;   // index entries staged per tile (the tile size is chosen so that the average span is <= half of it)
 
 template <bool W, int HB>
 __global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
                                                               const uint32_t *__restrict__ inst, uint64_t n, IndexDev idx,
                                                               LevelParams lp, const uint64_t *__restrict__ part,
-                                                              uint64_t *__restrict__ rec)
+                                                              uint64_t *__restrict__ rec, uint32_t tq)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *s_klo = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *s_rec = reinterpret_cast<uint64_t *>(smem_raw);                 // [kRecWords][kLookupBlock]
+    uint64_t *s_klo = s_rec + kRecWords * kLookupBlock;
     uint64_t *s_khi = s_klo + (W ? kSpanCap : 0);
     uint16_t *s_tax = reinterpret_cast<uint16_t *>(s_khi + kSpanCap);
 
     const uint64_t tile = blockIdx.x;
-    const uint64_t q0 = tile * kLookupTile;
+    const uint64_t q0 = tile * tq;
     const int64_t a = (int64_t)part[2 * tile], b = (int64_t)part[2 * tile + 1];
     const int64_t span = b - a;
     const bool staged = span <= kSpanCap;
@@ -195,24 +199,40 @@ __global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint64_t *__
     __syncthreads();
     SmemAcc sacc{s_klo, s_khi, s_tax, a};
     GmemAcc gacc{idx.key_lo, idx.key_hi, idx.tax};
+    uint64_t *R = s_rec + threadIdx.x;
 #pragma unroll 1
-    for (int r = 0; r < kLookupTile / kLookupBlock; ++r) {
-        uint64_t i = q0 + (uint64_t)r * kLookupBlock + threadIdx.x;
-        if (i >= n) break;
-        Key q{ldg_stream(q_lo + i), W ? ldg_stream(q_hi + i) : 0ull};
-        uint64_t R[kRecWords] = {0, 0, 0, 0};
-        if (span > 0) {
-            if (staged) match_query<W, HB>(sacc, a, b, q, lp, R);
-            else match_query<W, HB>(gacc, a, b, q, lp, R);
+    for (uint32_t r = 0; r < tq; r += kLookupBlock) {      // uniform trip count: lanes stay converged
+        const uint64_t i = q0 + r + threadIdx.x;
+        const bool live = (r + threadIdx.x < tq) && (i < n);
+        if (live) {
+            Key q{ldg_stream(q_lo + i), W ? ldg_stream(q_hi + i) : 0ull};
+#pragma unroll
+            for (int wi = 0; wi < kRecWords; ++wi) R[wi * kLookupBlock] = 0;
+            if (span > 0) {
+                if (staged) match_query<W, HB>(sacc, a, b, q, lp, R);
+                else match_query<W, HB>(gacc, a, b, q, lp, R);
+            }
         }
-        uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)ldg_stream(inst + i) * kRecWords);
-        dst[0] = make_uint4((uint32_t)R[0], (uint32_t)(R[0] >> 32), (uint32_t)R[1], (uint32_t)(R[1] >> 32));
-        dst[1] = make_uint4((uint32_t)R[2], (uint32_t)(R[2] >> 32), (uint32_t)R[3], (uint32_t)(R[3] >> 32));
+        __syncwarp();                                        // reconverge after the data-dependent scans
+        if (live) {
+            const uint64_t r0 = R[0], r1 = R[kLookupBlock], r2 = R[2 * kLookupBlock], r3 = R[3 * kLookupBlock];
+            uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)ldg_stream(inst + i) * kRecWords);
+            dst[0] = make_uint4((uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32));
+            dst[1] = make_uint4((uint32_t)r2, (uint32_t)(r2 >> 32), (uint32_t)r3, (uint32_t)(r3 >> 32));
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 constexpr int kReadBlock = 128;
+
+// One thread per read: fp32 score accumulation is a dependent chain per (read, taxon), so reads are the
+// parallel dimension; each thread walks its instances in emission order and levels in ascending k — the
+// canonical order of KASA_SCORE_FAST.  Counts: 32-bit native shared-memory atomics on CTA accumulators
+// (64-bit shared atomics are CAS loops on sm_100), split so that they cannot overflow between flushes:
+//   |taxa| == 1  -> integer counter (this is also the unique count)
+//   |taxa| >= 2  -> 2^-32 fixed point of 1/|taxa| as two 16-bit halves
+constexpr int kReadChunk = 256;     // instances per thread between flushes: 128 * 256 * 65535 < 2^32
 
 template <int HB, int LW>
 __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__restrict__ rec, const uint64_t *__restrict__ read_koff,
@@ -223,15 +243,22 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
     constexpr int FPW = 64 / HB;
     constexpr uint64_t HM = (1ull << HB) - 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = lp.n_taxa, NK = lp.num_k;
-    unsigned long long *s_fx = reinterpret_cast<unsigned long long *>(smem_raw);   // [NK][T]
-    unsigned long long *s_un = s_fx + NK * T;                                      // [NK][T]
-    unsigned long long *s_invfx = s_un + NK * T;                                   // [256]
-    float *s_w = reinterpret_cast<float *>(s_invfx + 256);                         // [32]
-    float *s_score = s_w + 32;                                                     // [T][kReadBlock]
+    const int T = lp.n_taxa, NK = lp.num_k, cells = NK * T;
+    unsigned long long *s_tot_fx = reinterpret_cast<unsigned long long *>(smem_raw);   // [NK][T]
+    unsigned long long *s_tot_un = s_tot_fx + cells;                                   // [NK][T]
+    uint32_t *s_lo = reinterpret_cast<uint32_t *>(s_tot_un + cells);                   // [NK][T]
+    uint32_t *s_hi = s_lo + cells;
+    uint32_t *s_un = s_hi + cells;
+    uint32_t *s_invfx = s_un + cells;                                                  // [256]
+    float *s_w = reinterpret_cast<float *>(s_invfx + 256);                             // [32]
+    float *s_inv = s_w + 32;                                                           // [256] 1.f / n (Compare.hpp:924)
+    float *s_score = s_inv + 256;                                                      // [T][kReadBlock]
     const int tid = threadIdx.x;
-    for (int i = tid; i < 2 * NK * T; i += kReadBlock) s_fx[i] = 0;
-    for (int i = tid; i < 256; i += kReadBlock) s_invfx[i] = i ? (unsigned long long)(4294967296.0 / i + 0.5) : 0ull;
+    for (int i = tid; i < cells; i += kReadBlock) { s_tot_fx[i] = 0; s_tot_un[i] = 0; s_lo[i] = 0; s_hi[i] = 0; s_un[i] = 0; }
+    for (int i = tid; i < 256; i += kReadBlock) {
+        s_invfx[i] = i >= 2 ? (uint32_t)(4294967296.0 / i + 0.5) : 0u;
+        s_inv[i] = i ? 1.f / (float)i : 0.f;
+    }
     if (tid < 32) {
         int k = lp.k_low + tid;
         s_w[tid] = (float)(k * k) / 625.f;        // Compare.hpp:392 arrWeightingFactors[25 - k]
@@ -242,50 +269,72 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
         const uint64_t r = r0 + tid;
         if (scores)
             for (int t = 0; t < T; ++t) s_score[t * kReadBlock + tid] = 0.f;
-        if (r < n_reads) {
-            const uint64_t s_end = read_koff[r + 1];
-            for (uint64_t s = read_koff[r]; s < s_end; ++s) {
-                const uint4 x0 = __ldg(rec + 2 * s), x1 = __ldg(rec + 2 * s + 1);
-                uint64_t R[kRecWords] = {(uint64_t)x0.x | ((uint64_t)x0.y << 32), (uint64_t)x0.z | ((uint64_t)x0.w << 32),
-                                         (uint64_t)x1.x | ((uint64_t)x1.y << 32), (uint64_t)x1.z | ((uint64_t)x1.w << 32)};
-                if ((R[0] | R[1] | R[2] | R[3]) == 0) continue;
-                // pass 1: n_j = |taxa at level j| (byte counters)
-                uint64_t nl[LW];
-#pragma unroll
-                for (int i = 0; i < LW; ++i) nl[i] = 0;
-#pragma unroll
-                for (int wi = 0; wi < kRecWords; ++wi) {
-                    uint64_t w = R[wi];
-                    while (w) {
-                        int f = (__ffsll((long long)w) - 1) / HB;
-                        uint32_t h = (uint32_t)(R[wi] >> (f * HB)) & (uint32_t)HM;
-                        w &= ~(HM << (f * HB));
-                        if (LW == 1) nl[0] += 0x0101010101010101ull >> (8 * (8 - h));
-                        else
-                            for (uint32_t j = 0; j < h; ++j) nl[j >> 3] += 1ull << (8 * (j & 7));
-                    }
+        uint64_t cur = 0, s_end = 0;
+        if (r < n_reads) { cur = read_koff[r]; s_end = read_koff[r + 1]; }
+        while (__syncthreads_or(cur < s_end)) {
+            const uint32_t mine = (uint32_t)min((uint64_t)kReadChunk, s_end - cur);
+            const uint32_t trips = __reduce_max_sync(kFull, mine);     // warp-uniform trip count
+#pragma unroll 1
+            for (uint32_t it = 0; it < trips; ++it) {
+                uint64_t R[kRecWords] = {0, 0, 0, 0};
+                if (it < mine) {
+                    const uint4 x0 = __ldg(rec + 2 * (cur + it)), x1 = __ldg(rec + 2 * (cur + it) + 1);
+                    R[0] = (uint64_t)x0.x | ((uint64_t)x0.y << 32); R[1] = (uint64_t)x0.z | ((uint64_t)x0.w << 32);
+                    R[2] = (uint64_t)x1.x | ((uint64_t)x1.y << 32); R[3] = (uint64_t)x1.z | ((uint64_t)x1.w << 32);
                 }
-                // pass 2: contributions, k ascending (Compare.hpp:924-925: score = w(k) * (1.f / n), counts 1/n)
+                if ((R[0] | R[1] | R[2] | R[3]) != 0) {
+                    // pass 1: n_j = |taxa at level j| (byte counters)
+                    uint64_t nl[LW];
 #pragma unroll
-                for (int wi = 0; wi < kRecWords; ++wi) {
-                    uint64_t w = R[wi];
-                    while (w) {
-                        int f = (__ffsll((long long)w) - 1) / HB;
-                        uint32_t h = (uint32_t)(R[wi] >> (f * HB)) & (uint32_t)HM;
-                        w &= ~(HM << (f * HB));
-                        const int t = wi * FPW + f + 1;
-                        for (uint32_t j = 0; j < h; ++j) {
-                            uint32_t nj = (uint32_t)(nl[LW == 1 ? 0 : (j >> 3)] >> (8 * (j & 7))) & 255u;
-                            if (scores) s_score[t * kReadBlock + tid] += s_w[j] * (1.f / (float)nj);
-                            atomicAdd(&s_fx[j * T + t], s_invfx[nj]);
-                            if (nj == 1) atomicAdd(&s_un[j * T + t], 1ull);
+                    for (int i = 0; i < LW; ++i) nl[i] = 0;
+#pragma unroll
+                    for (int wi = 0; wi < kRecWords; ++wi) {
+                        uint64_t w = R[wi];
+                        while (w) {
+                            int f = (__ffsll((long long)w) - 1) / HB;
+                            uint32_t h = (uint32_t)(R[wi] >> (f * HB)) & (uint32_t)HM;
+                            w &= ~(HM << (f * HB));
+                            if (LW == 1) nl[0] += 0x0101010101010101ull >> (8 * (8 - h));
+                            else
+                                for (uint32_t j = 0; j < h; ++j) nl[j >> 3] += 1ull << (8 * (j & 7));
+                        }
+                    }
+                    // pass 2: contributions, k ascending (Compare.hpp:924-925: score = w(k) * (1.f / n), counts 1/n)
+#pragma unroll
+                    for (int wi = 0; wi < kRecWords; ++wi) {
+                        uint64_t w = R[wi];
+                        while (w) {
+                            int f = (__ffsll((long long)w) - 1) / HB;
+                            uint32_t h = (uint32_t)(R[wi] >> (f * HB)) & (uint32_t)HM;
+                            w &= ~(HM << (f * HB));
+                            const int t = wi * FPW + f + 1;
+                            float acc = scores ? s_score[t * kReadBlock + tid] : 0.f;
+                            for (uint32_t j = 0; j < h; ++j) {
+                                uint32_t nj = (uint32_t)(nl[LW == 1 ? 0 : (j >> 3)] >> (8 * (j & 7))) & 255u;
+                                acc += s_w[j] * s_inv[nj];
+                                const int c = j * T + t;
+                                if (nj == 1) atomicAdd(&s_un[c], 1u);
+                                else {
+                                    uint32_t fx = s_invfx[nj];
+                                    atomicAdd(&s_lo[c], fx & 0xffffu);
+                                    atomicAdd(&s_hi[c], fx >> 16);
+                                }
+                            }
+                            if (scores) s_score[t * kReadBlock + tid] = acc;
                         }
                     }
                 }
+                __syncwarp();       // lanes with empty records must not run ahead of the others
+            }
+            cur += mine;
+            __syncthreads();
+            for (int i = tid; i < cells; i += kReadBlock) {
+                s_tot_fx[i] += ((unsigned long long)s_hi[i] << 16) + s_lo[i];
+                s_tot_un[i] += s_un[i];
+                s_lo[i] = 0; s_hi[i] = 0; s_un[i] = 0;
             }
         }
         if (scores) {
-            __syncthreads();
             const uint64_t rows = min((uint64_t)kReadBlock, n_reads - r0);
             for (uint64_t i = tid; i < rows * T; i += kReadBlock) {
                 uint32_t rr = (uint32_t)(i / T), t = (uint32_t)(i % T);
@@ -295,9 +344,9 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
         }
     }
     __syncthreads();
-    for (int i = tid; i < NK * T; i += kReadBlock) {
-        if (s_fx[i]) atomicAdd(cnt_fx + i, s_fx[i]);
-        if (s_un[i]) atomicAdd(cnt_unique + i, s_un[i]);
+    for (int i = tid; i < cells; i += kReadBlock) {
+        if (s_tot_fx[i]) atomicAdd(cnt_fx + i, s_tot_fx[i]);
+        if (s_tot_un[i]) atomicAdd(cnt_unique + i, s_tot_un[i]);
     }
 }
 
@@ -316,7 +365,7 @@ __global__ void fold_counts_kernel(unsigned long long *cnt_fx, unsigned long lon
     if (i >= n) return;
     int j = i / lp.n_taxa, t = i % lp.n_taxa;
     int o = (lp.num_k - 1 - j) * lp.n_taxa + t;        // ik = 0 <-> k_high (kASA.hpp:299-302)
-    total_all[o] += (double)cnt_fx[i] * (1.0 / 4294967296.0);
+    total_all[o] += (double)cnt_fx[i] * (1.0 / 4294967296.0) + (double)cnt_unique[i];
     total_unique[o] += cnt_unique[i];
     cnt_fx[i] = 0;
     cnt_unique[i] = 0;
@@ -324,13 +373,14 @@ __global__ void fold_counts_kernel(unsigned long long *cnt_fx, unsigned long lon
 
 template <bool W>
 void launch_lookup_hb(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n, IndexDev idx,
-                      LevelParams lp, const uint64_t *part, uint64_t *rec)
+                      LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq)
 {
-    const unsigned tiles = (unsigned)div_up<uint64_t>(n, kLookupTile);
-    const size_t sm = (size_t)kSpanCap * (W ? 16 : 8) + (size_t)kSpanCap * 2;
+    const unsigned tiles = (unsigned)div_up<uint64_t>(n, tq);
+    const size_t sm = (size_t)kRecWords * kLookupBlock * 8 + (size_t)kSpanCap * (W ? 16 : 8) + (size_t)kSpanCap * 2;
     auto go = [&](auto kern) {
         KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        kern<<<tiles, kLookupBlock, sm, s>>>(q_lo, q_hi, inst, n, idx, lp, part, rec);
+        KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        kern<<<tiles, kLookupBlock, sm, s>>>(q_lo, q_hi, inst, n, idx, lp, part, rec, tq);
     };
     if (lp.hb == 3) go(lookup_kernel<W, 3>);
     else if (lp.hb == 4) go(lookup_kernel<W, 4>);
@@ -339,22 +389,32 @@ void launch_lookup_hb(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi
 
 }  // namespace
 
+uint32_t lookup_tile_queries(uint64_t n_queries, uint64_t n_index)
+{
+    // queries per CTA such that the expected index span (tile * index / queries) is about half the staging capacity
+    if (n_index == 0 || n_queries == 0) return kLookupTile;
+    double tq = 0.5 * kSpanCap * (double)n_queries / (double)n_index;
+    if (tq > kLookupTile) tq = kLookupTile;
+    if (tq < 32) tq = 32;
+    return (uint32_t)tq;
+}
+
 void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, uint64_t n, IndexDev idx, LevelParams lp,
-                      uint64_t *part, uint64_t *launches)
+                      uint64_t *part, uint32_t tq, uint64_t *launches)
 {
     if (!n) return;
-    const uint64_t tiles = div_up<uint64_t>(n, kLookupTile);
-    if (idx.key_hi) partition_kernel<true><<<(unsigned)div_up<uint64_t>(tiles, 256), 256, 0, s>>>(q_lo, q_hi, n, idx, lp, part, tiles);
-    else partition_kernel<false><<<(unsigned)div_up<uint64_t>(tiles, 256), 256, 0, s>>>(q_lo, q_hi, n, idx, lp, part, tiles);
+    const uint64_t tiles = div_up<uint64_t>(n, tq);
+    if (idx.key_hi) partition_kernel<true><<<(unsigned)div_up<uint64_t>(tiles, 256), 256, 0, s>>>(q_lo, q_hi, n, idx, lp, part, tiles, tq);
+    else partition_kernel<false><<<(unsigned)div_up<uint64_t>(tiles, 256), 256, 0, s>>>(q_lo, q_hi, n, idx, lp, part, tiles, tq);
     ++*launches;
 }
 
 void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n, IndexDev idx,
-                   LevelParams lp, const uint64_t *part, uint64_t *rec, uint64_t *launches)
+                   LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq, uint64_t *launches)
 {
     if (!n) return;
-    if (idx.key_hi) launch_lookup_hb<true>(s, q_lo, q_hi, inst, n, idx, lp, part, rec);
-    else launch_lookup_hb<false>(s, q_lo, q_hi, inst, n, idx, lp, part, rec);
+    if (idx.key_hi) launch_lookup_hb<true>(s, q_lo, q_hi, inst, n, idx, lp, part, rec, tq);
+    else launch_lookup_hb<false>(s, q_lo, q_hi, inst, n, idx, lp, part, rec, tq);
     ++*launches;
     KASA_CUDA_TRY(cudaGetLastError());
 }
@@ -363,7 +423,7 @@ void launch_per_read(cudaStream_t s, const uint64_t *rec, const uint64_t *read_k
                      float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, uint64_t *launches)
 {
     if (!n_reads) return;
-    const size_t sm = (size_t)2 * lp.num_k * lp.n_taxa * 8 + 256 * 8 + 32 * 4 + (scores ? (size_t)lp.n_taxa * kReadBlock * 4 : 0);
+    const size_t sm = (size_t)lp.num_k * lp.n_taxa * (16 + 12) + 256 * 4 + 32 * 4 + 256 * 4 + (scores ? (size_t)lp.n_taxa * kReadBlock * 4 : 0);
     unsigned grid = (unsigned)div_up<uint64_t>(n_reads, kReadBlock);
     if (grid > (unsigned)kSMs * 8) grid = kSMs * 8;
     auto go = [&](auto kern) {

@@ -23,7 +23,7 @@ struct LevelParams {
     int hb;        // bits per level field in a match record (3, 4 or 5)
 };
 
-constexpr int kLookupTile = 2048;      // sorted queries per CTA
+constexpr int kLookupTile = 1024;      // most sorted queries per CTA (see lookup_tile_queries)
 constexpr int kLookupBlock = 256;
 constexpr int kRecWords = 4;           // match record = 4 x u64 = one 32-byte sector
 
@@ -33,13 +33,14 @@ inline int record_taxa_capacity(int hb) { return kRecWords * (64 / hb); }
 
 // per-tile index spans: part[2t], part[2t+1] = [first entry sharing the k_low-prefix of the tile's first
 // query, one past the last entry sharing the k_low-prefix of its last query)
+uint32_t lookup_tile_queries(uint64_t n_queries, uint64_t n_index);
 void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, uint64_t n, IndexDev idx,
-                      LevelParams lp, uint64_t *part, uint64_t *launches);
+                      LevelParams lp, uint64_t *part, uint32_t tq, uint64_t *launches);
 
 // one 32-byte match record per k-mer instance, written at rec[inst[i]] (instance = emission order):
 // field t-1 = number of levels (from k_low upwards) at which taxon t is in taxa_k(prefix_k(q))
 void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n,
-                   IndexDev idx, LevelParams lp, const uint64_t *part, uint64_t *rec, uint64_t *launches);
+                   IndexDev idx, LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq, uint64_t *launches);
 
 // per read: fp32 scores in canonical order (instance order, k ascending) and the per-taxon per-level
 // counts: cnt_fx [num_k][n_taxa] fixed point 2^-32 (sum of 1/|taxa|), cnt_unique [num_k][n_taxa].

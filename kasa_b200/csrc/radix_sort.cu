@@ -65,8 +65,12 @@ __global__ void __launch_bounds__(kRadix) hist_scan_kernel(unsigned long long *g
 // ---------------------------------------------------------------------------------------------
 // One radix pass.  Tile = BLOCK x ITEMS records, warp-striped so that loads coalesce and the
 // (warp, item, lane) order equals the input order (needed for LSD stability).
+//
+// Resource plan (B200: 64 K registers, 227 KB shared memory per SM): 512 threads x 8 items at <= 64
+// registers -> 2 CTAs = 32 warps per SM; 52 KB dynamic shared memory per CTA.  The kernel is latency
+// bound per tile (rank chain + look-back), so resident warps are what buys bandwidth.
 template <int BLOCK, int ITEMS, bool HAS_W1>
-__global__ void __launch_bounds__(BLOCK) onesweep_kernel(
+__global__ void __launch_bounds__(BLOCK, 2) onesweep_kernel(
     const uint64_t *__restrict__ in_w0, const uint64_t *__restrict__ in_w1, const uint32_t *__restrict__ in_v,
     uint64_t *__restrict__ out_w0, uint64_t *__restrict__ out_w1, uint32_t *__restrict__ out_v, uint64_t n, int src,
     int shift, uint32_t mask, const unsigned long long *__restrict__ digit_start, uint64_t *status,
@@ -75,6 +79,7 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(
     constexpr int TILE = BLOCK * ITEMS;
     constexpr int NW = BLOCK / 32;
     static_assert(BLOCK >= kRadix, "one look-back thread per digit");
+    static_assert(TILE <= 65536, "tile positions are kept in 16 bits");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *s_buf = reinterpret_cast<uint64_t *>(smem_raw);                       // TILE x 8 B exchange buffer
@@ -93,20 +98,17 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(
     const uint64_t base = (uint64_t)tile * TILE;
     const uint32_t n_tile = (uint32_t)min((uint64_t)TILE, n - base);
     const uint64_t wbase = base + (uint64_t)w * (32 * ITEMS) + lane;
-
-    // ---- load the digit source (and the 32-bit payload early: its latency hides behind ranking)
-    uint64_t key[ITEMS];
-    uint32_t val[ITEMS];
     const bool v_is_src = (src == SRC_V);
+
+    // ---- load the digit source
+    uint64_t key[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         uint64_t idx = wbase + (uint64_t)i * 32;
         bool ok = idx < n;
-        uint32_t vv = ok ? ldg_stream(in_v + idx) : 0xffffffffu;
-        val[i] = vv;
         if (src == SRC_W0) key[i] = ok ? ldg_stream(in_w0 + idx) : ~0ull;
         else if (HAS_W1 && src == SRC_W1) key[i] = ok ? ldg_stream(in_w1 + idx) : ~0ull;
-        else key[i] = ok ? (uint64_t)vv : ~0ull;
+        else key[i] = ok ? (uint64_t)ldg_stream(in_v + idx) : ~0ull;
     }
 
     // ---- rank inside the warp, digit by digit (match-any multisplit); padding keys carry digit `mask`
@@ -164,6 +166,19 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(
     }
     __syncthreads();
 
+    // ---- the 32-bit payload is requested now: its latency hides behind the look-back
+    uint32_t val[ITEMS];
+    if (!v_is_src) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            uint64_t idx = wbase + (uint64_t)i * 32;
+            val[i] = idx < n ? ldg_stream(in_v + idx) : 0u;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) val[i] = (uint32_t)key[i];
+    }
+
     // ---- decoupled look-back, one thread per digit
     if (tid < kRadix) {
         const uint32_t dbase = incl - count + s_wsum[w];
@@ -183,7 +198,7 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(
                         atomicExch(err_flag, 1u);
                         break;
                     }
-                    __nanosleep(40);
+                    __nanosleep(20);
                     continue;
                 }
                 excl += s & kValMask;
@@ -273,9 +288,12 @@ SortPlan plan_for_kmer_bits(int key_bits)
 }
 
 int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint64_t n, const SortPlan &plan,
-               void *workspace, uint32_t *err_flag, uint64_t *launches)
+               void *workspace, uint32_t *err_flag, uint64_t *launches, cudaEvent_t after_hist)
 {
-    if (n == 0 || plan.n_passes == 0) return start_buf;
+    if (n == 0 || plan.n_passes == 0) {
+        if (after_hist) KASA_CUDA_TRY(cudaEventRecord(after_hist, stream));
+        return start_buf;
+    }
     const bool has_w1 = buf.w1[0] != nullptr;
     auto *ghist = reinterpret_cast<unsigned long long *>(workspace);
     auto *ticket = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(workspace) + (size_t)kMaxPasses * kRadix * 8);
@@ -307,6 +325,7 @@ int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint6
         hist_scan_kernel<<<plan.n_passes, kRadix, 0, stream>>>(ghist);
         *launches += 2;
     }
+    if (after_hist) KASA_CUDA_TRY(cudaEventRecord(after_hist, stream));
     constexpr size_t sm_pass = onesweep_smem<kSortBlock, kSortItems>();
     static bool attr_done = false;
     if (!attr_done) {
@@ -314,6 +333,10 @@ int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint6
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pass));
         KASA_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<kSortBlock, kSortItems, true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pass));
+        KASA_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<kSortBlock, kSortItems, false>,
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        KASA_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<kSortBlock, kSortItems, true>,
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     int cur = start_buf;

@@ -40,8 +40,8 @@ struct SortBuffers {         // ping-pong record arrays
     uint32_t *v[2];
 };
 
-constexpr int kSortBlock = 256;
-constexpr int kSortItems = 16;
+constexpr int kSortBlock = 512;
+constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortBlock * kSortItems;
 
 // workspace: [hist: kMaxPasses*256 u64][ticket+err: 64 B][status: tiles*256 u64]
@@ -55,7 +55,7 @@ inline size_t sort_workspace_bytes(uint64_t n)
 // (0/1) of the buffer set holding the sorted records.  Adds the number of kernel launches to
 // *launches.  err_flag (device u32) is set to 1 if the look-back watchdog trips.
 int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint64_t n, const SortPlan &plan,
-               void *workspace, uint32_t *err_flag, uint64_t *launches);
+               void *workspace, uint32_t *err_flag, uint64_t *launches, cudaEvent_t after_hist = nullptr);
 
 // plan for the identify sort: all significant bits of a K-letter k-mer (5 bits per letter)
 SortPlan plan_for_kmer_bits(int key_bits);

@@ -99,7 +99,7 @@ def test_radix_sort_partial_bits_and_skewed_digits():
 
 
 # ----------------------------------------------------------------------------------------- identify
-def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None):
+def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, rtol=FAST_RTOL):
     _, taxids, _ = G.content(case)
     idx = G.index(case)
     if paired:
@@ -127,7 +127,7 @@ def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None):
     assert np.array_equal(cu, ora.count_unique)                               # exact integers
     np.testing.assert_allclose(ca, ora.count_all, rtol=COUNT_RTOL, atol=1e-9)
     assert np.array_equal(scores > 0, ora.scores > 0)                         # same taxa per read
-    np.testing.assert_allclose(scores, ora.scores, rtol=FAST_RTOL, atol=0)
+    np.testing.assert_allclose(scores, ora.scores, rtol=rtol, atol=0)
     # ... and against what the reference binary printed
     pr = G.per_read(case, tag)
     tax2idx = {int(t): i for i, t in enumerate(taxids)}
@@ -137,7 +137,7 @@ def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None):
         assert mine == set(rec["hits"])
         for tax, (score, _, _) in rec["hits"].items():
             cells += 1
-            assert abs(float(scores[r, tax2idx[tax]]) - float(score)) <= FAST_RTOL * float(score)
+            assert abs(float(scores[r, tax2idx[tax]]) - float(score)) <= rtol * float(score)
     assert cells > 0
     _, rows = G.profile(case, tag)
     numK = k_high - k_low + 1
@@ -161,7 +161,8 @@ def test_identify_k12_single_level():
 
 
 def test_identify_k25_paired():
-    _identify_case("k25", "six_25_7", 25, 25, 7, True, paired=True)
+    # 19 levels x 520 k-mers: ~10^4 fp32 adds per cell, the order-dependent rounding grows accordingly
+    _identify_case("k25", "six_25_7", 25, 25, 7, True, paired=True, rtol=3e-5)
 
 
 def test_identify_is_batch_independent_and_deterministic():
