@@ -64,6 +64,9 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// leading k-mer bits the identify sort orders (4 radix passes); see launch_partition for why that is enough
+constexpr int kIdentifySortBits = 32;
+
 template <typename T>
 T *dev_alloc(kasa_ctx *c, size_t n)
 {
@@ -500,7 +503,9 @@ int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resul
     const uint64_t n = extract_batch(c, in);
     out->n_kmers = n;
     const bool want_scores = c->p.score_mode != KASA_SCORE_NONE;
-    SortPlan plan = plan_for_kmer_bits(5 * c->K);
+    // identify orders the k-mers on their leading kIdentifySortBits only (lookup.cuh: launch_partition)
+    const int sorted_from = std::max(0, 5 * c->K - kIdentifySortBits);
+    SortPlan plan = plan_for_bit_range(sorted_from, 5 * c->K);
     KASA_CUDA_TRY(cudaEventRecord(c->sev[2], c->stream));
     if (n) {
         const int cur = radix_sort(c->stream, c->sb, 0, n, plan, c->sort_ws, c->d_err, &c->launches, c->sev[3]);
@@ -512,7 +517,7 @@ int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resul
         IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n};
         LevelParams lp = level_params(c);
         const uint32_t tq = lookup_tile_queries(n, c->idx_n);
-        launch_partition(c->stream, c->sb.w0[cur], c->sb.w1[cur], n, idx, lp, c->d_part, tq, &c->launches);
+        launch_partition(c->stream, c->sb.w0[cur], c->sb.w1[cur], n, idx, lp, c->d_part, tq, sorted_from, &c->launches);
         launch_lookup(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, idx, lp, c->d_part, c->d_rec, tq, &c->launches);
         KASA_CUDA_TRY(cudaEventRecord(c->sev[5], c->stream));
         launch_per_read(c->stream, c->d_rec, c->d_read_koff, in->n_reads, lp, want_scores ? c->d_scores : nullptr, c->d_cnt_fx,

@@ -57,11 +57,10 @@ __device__ __forceinline__ uint32_t letter_at(const Key &q, int k, int K)
     return (uint32_t)((q.hi << (64 - sh)) | (q.lo >> sh)) & 31u;
 }
 
-// smallest / one-past-largest k-mer sharing the first k letters of q
+// smallest / one-past-largest k-mer sharing all bits above `sh` with q
 template <bool W>
-__device__ __forceinline__ Key prefix_floor(const Key &q, int k, int K)
+__device__ __forceinline__ Key prefix_floor(const Key &q, int sh)
 {
-    int sh = 5 * (K - k);
     Key r = q;
     if (!W) { r.lo = sh >= 64 ? 0 : (q.lo >> sh) << sh; return r; }
     if (sh >= 64) { r.lo = 0; r.hi = (sh - 64) >= 64 ? 0 : (q.hi >> (sh - 64)) << (sh - 64); }
@@ -69,10 +68,9 @@ __device__ __forceinline__ Key prefix_floor(const Key &q, int k, int K)
     return r;
 }
 template <bool W>
-__device__ __forceinline__ Key prefix_ceil(const Key &q, int k, int K)
+__device__ __forceinline__ Key prefix_ceil(const Key &q, int sh)
 {
-    int sh = 5 * (K - k);
-    Key r = prefix_floor<W>(q, k, K);
+    Key r = prefix_floor<W>(q, sh);
     if (!W) { r.lo += 1ull << sh; return r; }
     if (sh >= 64) r.hi += 1ull << (sh - 64);
     else {
@@ -113,6 +111,19 @@ __device__ __forceinline__ int64_t lower_bound(const Acc &acc, int64_t lo, int64
         n -= half;
     }
     return lo + (key_lt<W>(acc.template key<W>(lo), q) ? 1 : 0);
+}
+
+// 3-bit records: bit f of the result is set iff field f (bits 3f..3f+2) of w equals 1, i.e. the taxon matched at
+// k_low only.  Stride-3 bit compression in five mask-and-shift steps.
+__device__ __forceinline__ uint64_t dense_single_level(uint64_t w)
+{
+    uint64_t x = w & ~(w >> 1) & ~(w >> 2) & 0x1249249249249249ull;
+    x = (x | (x >> 2)) & 0x10c30c30c30c30c3ull;
+    x = (x | (x >> 4)) & 0x100f00f00f00f00full;
+    x = (x | (x >> 8)) & 0x001f0000ff0000ffull;
+    x = (x | (x >> 16)) & 0x001f00000000ffffull;
+    x = (x | (x >> 32)) & 0x00000000001fffffull;
+    return x;
 }
 
 // R points at this thread's record column in shared memory: word wi lives at R[wi * kLookupBlock]
@@ -156,14 +167,16 @@ __device__ __forceinline__ void match_query(const Acc &acc, int64_t a, int64_t b
 template <bool W>
 __global__ void __launch_bounds__(256) partition_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
                                                         uint64_t n, IndexDev idx, LevelParams lp, uint64_t *__restrict__ part,
-                                                        uint64_t n_tiles, uint32_t tq)
+                                                        uint64_t n_tiles, uint32_t tq, int span_shift)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     uint64_t i0 = t * tq, i1 = min(n, i0 + tq) - 1;
     Key first{q_lo[i0], W ? q_hi[i0] : 0ull}, last{q_lo[i1], W ? q_hi[i1] : 0ull};
     GmemAcc acc{idx.key_lo, idx.key_hi, idx.tax};
-    Key f = prefix_floor<W>(first, lp.k_low, lp.K), c = prefix_ceil<W>(last, lp.k_low, lp.K);
+    // queries are ordered on the bits above span_shift only; the span must hold every entry that shares the
+    // k_low-letter prefix with any query of the tile, which the coarser of the two prefixes guarantees
+    Key f = prefix_floor<W>(first, span_shift), c = prefix_ceil<W>(last, span_shift);
     int64_t a = lower_bound<W>(acc, 0, (int64_t)idx.n, f);
     int64_t b = lower_bound<W>(acc, a, (int64_t)idx.n, c);
     part[2 * t] = (uint64_t)a;
@@ -186,6 +199,20 @@ __global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint64_t *__
 
     const uint64_t tile = blockIdx.x;
     const uint64_t q0 = tile * tq;
+    // this thread's queries and instance ids are requested first: their latency overlaps the span staging
+    constexpr int QPT = kLookupTile / kLookupBlock;
+    Key qv[QPT];
+    uint32_t iv[QPT];
+    bool live[QPT];
+#pragma unroll
+    for (int r = 0; r < QPT; ++r) {
+        const uint32_t off = r * kLookupBlock + threadIdx.x;
+        const uint64_t i = q0 + off;
+        live[r] = off < tq && i < n;
+        qv[r].lo = live[r] ? ldg_stream(q_lo + i) : 0ull;
+        qv[r].hi = (W && live[r]) ? ldg_stream(q_hi + i) : 0ull;
+        iv[r] = live[r] ? ldg_stream(inst + i) : 0u;
+    }
     const int64_t a = (int64_t)part[2 * tile], b = (int64_t)part[2 * tile + 1];
     const int64_t span = b - a;
     const bool staged = span <= kSpanCap;
@@ -200,23 +227,23 @@ __global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint64_t *__
     SmemAcc sacc{s_klo, s_khi, s_tax, a};
     GmemAcc gacc{idx.key_lo, idx.key_hi, idx.tax};
     uint64_t *R = s_rec + threadIdx.x;
-#pragma unroll 1
-    for (uint32_t r = 0; r < tq; r += kLookupBlock) {      // uniform trip count: lanes stay converged
-        const uint64_t i = q0 + r + threadIdx.x;
-        const bool live = (r + threadIdx.x < tq) && (i < n);
-        if (live) {
-            Key q{ldg_stream(q_lo + i), W ? ldg_stream(q_hi + i) : 0ull};
+#pragma unroll
+    for (int r = 0; r < QPT; ++r) {
+        if (r * kLookupBlock >= (int)tq) break;             // CTA-uniform
+        if (live[r]) {
 #pragma unroll
             for (int wi = 0; wi < kRecWords; ++wi) R[wi * kLookupBlock] = 0;
             if (span > 0) {
-                if (staged) match_query<W, HB>(sacc, a, b, q, lp, R);
-                else match_query<W, HB>(gacc, a, b, q, lp, R);
+                if (staged) match_query<W, HB>(sacc, a, b, qv[r], lp, R);
+                else match_query<W, HB>(gacc, a, b, qv[r], lp, R);
             }
         }
         __syncwarp();                                        // reconverge after the data-dependent scans
-        if (live) {
-            const uint64_t r0 = R[0], r1 = R[kLookupBlock], r2 = R[2 * kLookupBlock], r3 = R[3 * kLookupBlock];
-            uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)ldg_stream(inst + i) * kRecWords);
+        if (live[r]) {
+            const uint64_t r0 = R[0], r1 = R[kLookupBlock], r2 = R[2 * kLookupBlock];
+            uint64_t r3 = R[3 * kLookupBlock];
+            if (HB == 3) r3 = dense_single_level(r0) | (dense_single_level(r1) << 21) | (dense_single_level(r2) << 42);
+            uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)iv[r] * kRecWords);
             dst[0] = make_uint4((uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32));
             dst[1] = make_uint4((uint32_t)r2, (uint32_t)(r2 >> 32), (uint32_t)r3, (uint32_t)(r3 >> 32));
         }
@@ -252,7 +279,9 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
     uint32_t *s_invfx = s_un + cells;                                                  // [256]
     float *s_w = reinterpret_cast<float *>(s_invfx + 256);                             // [32]
     float *s_inv = s_w + 32;                                                           // [256] 1.f / n (Compare.hpp:924)
-    float *s_score = s_inv + 256;                                                      // [T][kReadBlock]
+    uint32_t *s_carry = reinterpret_cast<uint32_t *>(s_inv + 256);                     // [T] level-0 carries
+    uint32_t *s_c0 = s_carry + ((T + 3) & ~3);                                         // [T][kReadBlock] private 2^-32 sums
+    float *s_score = reinterpret_cast<float *>(s_c0 + T * kReadBlock);                 // [T][kReadBlock]
     const int tid = threadIdx.x;
     for (int i = tid; i < cells; i += kReadBlock) { s_tot_fx[i] = 0; s_tot_un[i] = 0; s_lo[i] = 0; s_hi[i] = 0; s_un[i] = 0; }
     for (int i = tid; i < 256; i += kReadBlock) {
@@ -263,6 +292,10 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
         int k = lp.k_low + tid;
         s_w[tid] = (float)(k * k) / 625.f;        // Compare.hpp:392 arrWeightingFactors[25 - k]
     }
+    __syncthreads();
+
+    for (int t = 0; t < T; ++t) s_c0[t * kReadBlock + tid] = 0;
+    for (int t = tid; t < T; t += kReadBlock) s_carry[t] = 0;
     __syncthreads();
 
     for (uint64_t r0 = (uint64_t)blockIdx.x * kReadBlock; r0 < n_reads; r0 += (uint64_t)gridDim.x * kReadBlock) {
@@ -283,6 +316,7 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
                     R[2] = (uint64_t)x1.x | ((uint64_t)x1.y << 32); R[3] = (uint64_t)x1.z | ((uint64_t)x1.w << 32);
                 }
                 if ((R[0] | R[1] | R[2] | R[3]) != 0) {
+                    {
                     // pass 1: n_j = |taxa at level j| (byte counters)
                     uint64_t nl[LW];
 #pragma unroll
@@ -323,6 +357,7 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
                             if (scores) s_score[t * kReadBlock + tid] = acc;
                         }
                     }
+                    }
                 }
                 __syncwarp();       // lanes with empty records must not run ahead of the others
             }
@@ -332,6 +367,7 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
                 s_tot_fx[i] += ((unsigned long long)s_hi[i] << 16) + s_lo[i];
                 s_tot_un[i] += s_un[i];
                 s_lo[i] = 0; s_hi[i] = 0; s_un[i] = 0;
+                if (i < T) { s_tot_fx[i] += (unsigned long long)s_carry[i] << 32; s_carry[i] = 0; }
             }
         }
         if (scores) {
@@ -343,10 +379,240 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
             __syncthreads();
         }
     }
+    // residuals of the thread-private level-0 accumulators
+    for (int t = 0; t < T; ++t) {
+        const uint32_t v = s_c0[t * kReadBlock + tid];
+        if (v) { atomicAdd(&s_lo[t], v & 0xffffu); atomicAdd(&s_hi[t], v >> 16); }
+    }
     __syncthreads();
     for (int i = tid; i < cells; i += kReadBlock) {
+        s_tot_fx[i] += ((unsigned long long)s_hi[i] << 16) + s_lo[i];
         if (s_tot_fx[i]) atomicAdd(cnt_fx + i, s_tot_fx[i]);
         if (s_tot_un[i]) atomicAdd(cnt_unique + i, s_tot_un[i]);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// per-read accumulation, 3-bit records (num_k <= 7: the default k = 12..7; words 0-2 = 63 taxon fields,
+// word 3 = dense mask of the taxa matched at k_low only, written by the lookup kernel).
+//
+// Lane l of a warp owns read r0 + 32 w + l and walks its instances in emission order, one per iteration.
+// The (instance, taxon) members of the 32 records of an iteration are ragged (1 .. tens per record), so they
+// are first compacted into a shared-memory work list — members matched at k_low only from the front, members
+// matched at several levels from the back — and then processed with one member per lane.  Every (read, taxon)
+// cell is touched by exactly one lane per iteration and iterations are ordered, so the fp32 adds of a cell
+// happen in (instance, k ascending) order: the canonical order of KASA_SCORE_FAST.
+//   counts: |taxa| == 1 hits go to a per-read run cache (same taxon for consecutive instances) that is
+//   emptied with a few 32-bit shared atomics per read; k_low hits with |taxa| >= 2 go to a read-private
+//   2^-32 fixed-point column whose carries are counted; the rest (rare) uses 16-bit-split atomics.
+constexpr int kFlatBlock = 128;
+constexpr int kFlatWarps = kFlatBlock / 32;
+
+struct FlatSmem {
+    unsigned long long *tot_fx, *tot_un, *np;
+    uint32_t *lo, *hi, *un, *invfx, *carry, *c0, *tcur, *cu, *fx0;
+    uint16_t *list;
+    float *w, *inv, *score, *c0f;
+};
+
+__device__ __forceinline__ void flat_unique_hit(const FlatSmem &S, int T, int j, int t, int col)
+{
+    if ((int)S.tcur[col] != t) {
+        const int old = (int)S.tcur[col];
+#pragma unroll
+        for (int jj = 0; jj < 7; ++jj) {
+            const uint32_t v = S.cu[jj * kFlatBlock + col];
+            if (v) { atomicAdd(&S.un[jj * T + old], v); S.cu[jj * kFlatBlock + col] = 0; }
+        }
+        S.tcur[col] = (uint32_t)t;
+    }
+    S.cu[j * kFlatBlock + col] += 1;
+}
+
+__device__ __forceinline__ void flat_frac_level0(const FlatSmem &S, int t, int col, uint32_t fx)
+{
+    const uint32_t old = S.c0[t * kFlatBlock + col], now = old + fx;
+    S.c0[t * kFlatBlock + col] = now;
+    if (now < old) atomicAdd(&S.carry[t], 1u);
+}
+
+__global__ void __launch_bounds__(kFlatBlock) per_read_flat_kernel(const uint4 *__restrict__ rec, const uint64_t *__restrict__ read_koff,
+                                                                   uint32_t n_reads, LevelParams lp, float *__restrict__ scores,
+                                                                   unsigned long long *__restrict__ cnt_fx,
+                                                                   unsigned long long *__restrict__ cnt_unique)
+{
+    constexpr int FPW = 21;
+    constexpr uint64_t L = 0x1249249249249249ull;            // bit 3f, f = 0..20
+    constexpr unsigned long long kLevelOnes = 0x0000040810204080ull;   // 1 << 7j for j = 1..6
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = lp.n_taxa, NK = lp.num_k, cells = NK * T;
+    FlatSmem S;
+    S.tot_fx = reinterpret_cast<unsigned long long *>(smem_raw);
+    S.tot_un = S.tot_fx + cells;
+    S.np = S.tot_un + cells;                                  // [kFlatBlock] packed |taxa_j|, 7 bits per level
+    S.lo = reinterpret_cast<uint32_t *>(S.np + kFlatBlock);
+    S.hi = S.lo + cells;
+    S.un = S.hi + cells;
+    S.invfx = S.un + cells;                                   // [256]
+    S.carry = S.invfx + 256;                                  // [T rounded to 4]
+    S.tcur = S.carry + ((T + 3) & ~3);                        // [kFlatBlock]
+    S.fx0 = S.tcur + kFlatBlock;                              // [kFlatBlock] 2^32 / |taxa_0| of the current record (0: unique)
+    S.cu = S.fx0 + kFlatBlock;                                // [7][kFlatBlock]
+    S.c0 = S.cu + 7 * kFlatBlock;                             // [T][kFlatBlock]
+    S.w = reinterpret_cast<float *>(S.c0 + T * kFlatBlock);   // [32]
+    S.inv = S.w + 32;                                         // [256]
+    S.c0f = S.inv + 256;                                      // [kFlatBlock] w(k_low) / |taxa_0| of the current record
+    S.score = S.c0f + kFlatBlock;                             // [T][kFlatBlock]
+    S.list = reinterpret_cast<uint16_t *>(S.score + (scores ? T * kFlatBlock : 0));    // [kFlatWarps][32 * (T - 1)]
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < cells; i += kFlatBlock) { S.tot_fx[i] = 0; S.tot_un[i] = 0; S.lo[i] = 0; S.hi[i] = 0; S.un[i] = 0; }
+    for (int i = tid; i < 256; i += kFlatBlock) {
+        S.invfx[i] = i >= 2 ? (uint32_t)(4294967296.0 / i + 0.5) : 0u;
+        S.inv[i] = i ? 1.f / (float)i : 0.f;                  // Compare.hpp:924 (1.f / numOfEntries)
+    }
+    if (tid < 32) { int k = lp.k_low + tid; S.w[tid] = (float)(k * k) / 625.f; }   // Compare.hpp:392
+    for (int t = tid; t < T; t += kFlatBlock) S.carry[t] = 0;
+    for (int t = 0; t < T; ++t) S.c0[t * kFlatBlock + tid] = 0;
+    S.tcur[tid] = 0;
+#pragma unroll
+    for (int jj = 0; jj < 7; ++jj) S.cu[jj * kFlatBlock + tid] = 0;
+    __syncthreads();
+    const int list_cap = 32 * (T - 1);
+    uint16_t *listA = S.list + w * list_cap, *listB = listA + list_cap - 1;       // B grows downwards
+    const float w0 = S.w[0];
+
+    for (uint64_t r0 = (uint64_t)blockIdx.x * kFlatBlock; r0 < n_reads; r0 += (uint64_t)gridDim.x * kFlatBlock) {
+        const uint64_t r = r0 + tid;
+        if (scores)
+            for (int t = 0; t < T; ++t) S.score[t * kFlatBlock + tid] = 0.f;
+        uint64_t cur = 0, s_end = 0;
+        if (r < n_reads) { cur = read_koff[r]; s_end = read_koff[r + 1]; }
+        while (__syncthreads_or(cur < s_end)) {
+            const uint32_t mine = (uint32_t)min((uint64_t)kReadChunk, s_end - cur);
+            const uint32_t trips = __reduce_max_sync(kFull, mine);
+            uint4 n0v = make_uint4(0, 0, 0, 0), n1v = make_uint4(0, 0, 0, 0);
+            if (mine) { n0v = __ldg(rec + 2 * cur); n1v = __ldg(rec + 2 * cur + 1); }
+#pragma unroll 1
+            for (uint32_t it = 0; it < trips; ++it) {
+                const uint4 x0 = n0v, x1 = n1v;
+                if (it + 1 < mine) { n0v = __ldg(rec + 2 * (cur + it + 1)); n1v = __ldg(rec + 2 * (cur + it + 1) + 1); }   // next record in flight
+                uint64_t R[3] = {0, 0, 0}, single = 0;
+                if (it < mine) {
+                    R[0] = (uint64_t)x0.x | ((uint64_t)x0.y << 32); R[1] = (uint64_t)x0.z | ((uint64_t)x0.w << 32);
+                    R[2] = (uint64_t)x1.x | ((uint64_t)x1.y << 32); single = (uint64_t)x1.z | ((uint64_t)x1.w << 32);
+                }
+                // ---- phase A (lane = record): work-list slots
+                uint64_t more[3];
+                uint32_t nB = 0;
+#pragma unroll
+                for (int wi = 0; wi < 3; ++wi) {
+                    more[wi] = ((R[wi] >> 1) | (R[wi] >> 2)) & L;       // fields >= 2: matched above k_low
+                    nB += __popcll(more[wi]);
+                }
+                const uint32_t nA = __popcll(single), n0 = nA + nB;
+                const uint32_t both = nA | (nB << 16);
+                uint32_t incl = both;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const uint32_t totals = __shfl_sync(kFull, incl, 31);
+                const uint32_t totalA = totals & 0xffffu, totalB = totals >> 16;
+                uint32_t offA = (incl - both) & 0xffffu, offB = (incl - both) >> 16;
+                while (single) {                                       // dense mask: bit s <-> taxon s + 1
+                    const int t = __ffsll((long long)single);
+                    single &= single - 1;
+                    listA[offA++] = (uint16_t)((lane << 8) | t);
+                }
+                unsigned long long np = n0;                            // |taxa_j| = members matched at more than j levels
+                if (nB) {
+#pragma unroll
+                    for (int wi = 0; wi < 3; ++wi) {
+                        uint64_t m = more[wi];
+                        while (m) {
+                            const int f = ((__ffsll((long long)m) - 1) * 171) >> 9;
+                            const uint32_t h = (uint32_t)(R[wi] >> (3 * f)) & 7u;
+                            m &= ~(7ull << (3 * f));
+                            np += kLevelOnes & ((1ull << (7 * h)) - 1);
+                            *(listB - (offB++)) = (uint16_t)((lane << 11) | (h << 8) | (wi * FPW + f + 1));
+                        }
+                    }
+                }
+                S.np[tid] = np;
+                S.c0f[tid] = w0 * S.inv[n0];                           // Compare.hpp:924 weight * (1.f / n)
+                S.fx0[tid] = S.invfx[n0];
+                __syncwarp();
+                // ---- phase B1 (lane = member matched at k_low only)
+                for (uint32_t p = lane; p < totalA; p += 32) {
+                    const uint32_t e = listA[p];
+                    const int col = w * 32 + (int)(e >> 8), t = (int)(e & 255u);
+                    if (scores) S.score[t * kFlatBlock + col] += S.c0f[col];
+                    const uint32_t fx = S.fx0[col];
+                    if (fx == 0) flat_unique_hit(S, T, 0, t, col);
+                    else flat_frac_level0(S, t, col, fx);
+                }
+                // ---- phase B2 (lane = member matched at several levels)
+                for (uint32_t p = lane; p < totalB; p += 32) {
+                    const uint32_t e = *(listB - p);
+                    const int col = w * 32 + (int)(e >> 11), t = (int)(e & 255u);
+                    const int h = (int)((e >> 8) & 7u);
+                    const unsigned long long npk = S.np[col];
+                    float acc = scores ? S.score[t * kFlatBlock + col] : 0.f;
+#pragma unroll 1
+                    for (int j = 0; j < h; ++j) {
+                        const uint32_t nj = (uint32_t)(npk >> (7 * j)) & 127u;
+                        acc += S.w[j] * S.inv[nj];
+                        if (nj == 1) flat_unique_hit(S, T, j, t, col);
+                        else if (j == 0) flat_frac_level0(S, t, col, S.invfx[nj]);
+                        else {
+                            const uint32_t fx = S.invfx[nj];
+                            atomicAdd(&S.lo[j * T + t], fx & 0xffffu);
+                            atomicAdd(&S.hi[j * T + t], fx >> 16);
+                        }
+                    }
+                    if (scores) S.score[t * kFlatBlock + col] = acc;
+                }
+                __syncwarp();
+            }
+            cur += mine;
+            if (cur >= s_end && S.tcur[tid]) {       // read finished: empty its run cache
+                const int old = (int)S.tcur[tid];
+#pragma unroll
+                for (int jj = 0; jj < 7; ++jj) {
+                    const uint32_t v = S.cu[jj * kFlatBlock + tid];
+                    if (v) { atomicAdd(&S.un[jj * T + old], v); S.cu[jj * kFlatBlock + tid] = 0; }
+                }
+                S.tcur[tid] = 0;
+            }
+            __syncthreads();
+            for (int i = tid; i < cells; i += kFlatBlock) {
+                S.tot_fx[i] += ((unsigned long long)S.hi[i] << 16) + S.lo[i];
+                S.tot_un[i] += S.un[i];
+                S.lo[i] = 0; S.hi[i] = 0; S.un[i] = 0;
+                if (i < T) { S.tot_fx[i] += (unsigned long long)S.carry[i] << 32; S.carry[i] = 0; }
+            }
+        }
+        if (scores) {
+            const uint64_t rows = min((uint64_t)kFlatBlock, n_reads - r0);
+            for (uint64_t i = tid; i < rows * T; i += kFlatBlock) {
+                uint32_t rr = (uint32_t)(i / T), t = (uint32_t)(i % T);
+                scores[r0 * T + i] = S.score[t * kFlatBlock + rr];
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = 0; t < T; ++t) {                    // residuals of the read-private k_low accumulators
+        const uint32_t v = S.c0[t * kFlatBlock + tid];
+        if (v) { atomicAdd(&S.lo[t], v & 0xffffu); atomicAdd(&S.hi[t], v >> 16); }
+    }
+    __syncthreads();
+    for (int i = tid; i < cells; i += kFlatBlock) {
+        S.tot_fx[i] += ((unsigned long long)S.hi[i] << 16) + S.lo[i];
+        if (S.tot_fx[i]) atomicAdd(cnt_fx + i, S.tot_fx[i]);
+        if (S.tot_un[i]) atomicAdd(cnt_unique + i, S.tot_un[i]);
     }
 }
 
@@ -400,12 +666,14 @@ uint32_t lookup_tile_queries(uint64_t n_queries, uint64_t n_index)
 }
 
 void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, uint64_t n, IndexDev idx, LevelParams lp,
-                      uint64_t *part, uint32_t tq, uint64_t *launches)
+                      uint64_t *part, uint32_t tq, int sorted_from_bit, uint64_t *launches)
 {
     if (!n) return;
     const uint64_t tiles = div_up<uint64_t>(n, tq);
-    if (idx.key_hi) partition_kernel<true><<<(unsigned)div_up<uint64_t>(tiles, 256), 256, 0, s>>>(q_lo, q_hi, n, idx, lp, part, tiles, tq);
-    else partition_kernel<false><<<(unsigned)div_up<uint64_t>(tiles, 256), 256, 0, s>>>(q_lo, q_hi, n, idx, lp, part, tiles, tq);
+    const int klow_shift = 5 * (lp.K - lp.k_low);
+    const int sh = sorted_from_bit > klow_shift ? sorted_from_bit : klow_shift;
+    if (idx.key_hi) partition_kernel<true><<<(unsigned)div_up<uint64_t>(tiles, 256), 256, 0, s>>>(q_lo, q_hi, n, idx, lp, part, tiles, tq, sh);
+    else partition_kernel<false><<<(unsigned)div_up<uint64_t>(tiles, 256), 256, 0, s>>>(q_lo, q_hi, n, idx, lp, part, tiles, tq, sh);
     ++*launches;
 }
 
@@ -423,7 +691,8 @@ void launch_per_read(cudaStream_t s, const uint64_t *rec, const uint64_t *read_k
                      float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, uint64_t *launches)
 {
     if (!n_reads) return;
-    const size_t sm = (size_t)lp.num_k * lp.n_taxa * (16 + 12) + 256 * 4 + 32 * 4 + 256 * 4 + (scores ? (size_t)lp.n_taxa * kReadBlock * 4 : 0);
+    const size_t sm = (size_t)lp.num_k * lp.n_taxa * (16 + 12) + 256 * 4 + 32 * 4 + 256 * 4 + (size_t)((lp.n_taxa + 3) & ~3) * 4 +
+                      (size_t)lp.n_taxa * kReadBlock * 4 + (scores ? (size_t)lp.n_taxa * kReadBlock * 4 : 0);
     unsigned grid = (unsigned)div_up<uint64_t>(n_reads, kReadBlock);
     if (grid > (unsigned)kSMs * 8) grid = kSMs * 8;
     auto go = [&](auto kern) {
@@ -431,7 +700,15 @@ void launch_per_read(cudaStream_t s, const uint64_t *rec, const uint64_t *read_k
         kern<<<grid, kReadBlock, sm, s>>>(reinterpret_cast<const uint4 *>(rec), read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
     };
     const bool small = lp.num_k <= 8;
-    if (lp.hb == 3) go(per_read_kernel<3, 1>);
+    if (lp.hb == 3) {
+        const size_t cells = (size_t)lp.num_k * lp.n_taxa, T = lp.n_taxa;
+        const size_t smf = cells * 16 + kFlatBlock * 8 + cells * 12 + 256 * 4 + ((T + 3) & ~(size_t)3) * 4 + 2 * kFlatBlock * 4 +
+                           7 * kFlatBlock * 4 + T * kFlatBlock * 4 + 32 * 4 + 256 * 4 + kFlatBlock * 4 + (scores ? T * kFlatBlock * 4 : 0) +
+                           (size_t)kFlatWarps * 32 * (T - 1) * 2;
+        KASA_CUDA_TRY(cudaFuncSetAttribute(per_read_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+        KASA_CUDA_TRY(cudaFuncSetAttribute(per_read_flat_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        per_read_flat_kernel<<<grid, kFlatBlock, smf, s>>>(reinterpret_cast<const uint4 *>(rec), read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
+    }
     else if (lp.hb == 4) { if (small) go(per_read_kernel<4, 1>); else go(per_read_kernel<4, 4>); }
     else go(per_read_kernel<5, 4>);
     ++*launches;

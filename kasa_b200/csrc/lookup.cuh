@@ -29,13 +29,16 @@ constexpr int kRecWords = 4;           // match record = 4 x u64 = one 32-byte s
 
 // bits needed to store a level count 0..num_k, and how many taxa one record can describe
 inline int record_level_bits(int num_k) { return num_k <= 7 ? 3 : (num_k <= 15 ? 4 : 5); }
-inline int record_taxa_capacity(int hb) { return kRecWords * (64 / hb); }
+// 3-bit records keep their fourth word for a dense bit mask of the taxa matched at k_low only (see lookup.cu)
+inline int record_taxa_capacity(int hb) { return hb == 3 ? 63 : kRecWords * (64 / hb); }
 
-// per-tile index spans: part[2t], part[2t+1] = [first entry sharing the k_low-prefix of the tile's first
-// query, one past the last entry sharing the k_low-prefix of its last query)
+// per-tile index spans: part[2t], part[2t+1] = [first entry sharing the sorted prefix of the tile's first query,
+// one past the last entry sharing the sorted prefix of its last query).  The queries only need to be ordered
+// on their bits >= sorted_from_bit: every query searches the staged span on its own, so the order inside a
+// group of equal leading bits does not matter — this is what lets identify sort 32 of the 60 (125) key bits.
 uint32_t lookup_tile_queries(uint64_t n_queries, uint64_t n_index);
 void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, uint64_t n, IndexDev idx,
-                      LevelParams lp, uint64_t *part, uint32_t tq, uint64_t *launches);
+                      LevelParams lp, uint64_t *part, uint32_t tq, int sorted_from_bit, uint64_t *launches);
 
 // one 32-byte match record per k-mer instance, written at rec[inst[i]] (instance = emission order):
 // field t-1 = number of levels (from k_low upwards) at which taxon t is in taxa_k(prefix_k(q))

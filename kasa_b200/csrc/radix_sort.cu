@@ -117,7 +117,14 @@ __global__ void __launch_bounds__(BLOCK, 2) onesweep_kernel(
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-        uint32_t peers = __match_any_sync(kFull, d);
+        // lanes holding the same digit: eight ballots (VOTE is far cheaper than MATCH.ANY on the MIO pipe)
+        uint32_t peers = kFull;
+#pragma unroll
+        for (int bit = 0; bit < kRadixBits; ++bit) {
+            const bool one = (d >> bit) & 1u;
+            const uint32_t vote = __ballot_sync(kFull, one);
+            peers &= one ? vote : ~vote;
+        }
         int leader = __ffs(peers) - 1;
         uint32_t before = __popc(peers & lanemask_lt());
         uint32_t prev = 0;
@@ -213,6 +220,7 @@ __global__ void __launch_bounds__(BLOCK, 2) onesweep_kernel(
     __syncthreads();
 
     // ---- exchange through shared memory: digit-sorted tile, then coalesced runs to HBM
+    uint32_t *s_val = reinterpret_cast<uint32_t *>(s_dig + TILE);                    // TILE x 4 B payload buffer
     uint16_t pos[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
@@ -220,17 +228,21 @@ __global__ void __launch_bounds__(BLOCK, 2) onesweep_kernel(
         uint32_t p = s_dbase[d] + my_hist[d] + rk[i];
         pos[i] = (uint16_t)p;
         s_dig[p] = (uint8_t)d;
+        s_val[p] = val[i];
         if (!v_is_src) s_buf[p] = key[i];
     }
     __syncthreads();
-    if (!v_is_src) {
+    {
         uint64_t *out_src = (HAS_W1 && src == SRC_W1) ? out_w1 : out_w0;
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             uint32_t p = tid + j * BLOCK;
-            if (p < n_tile) out_src[s_gbase[s_dig[p]] + p] = s_buf[p];
+            if (p < n_tile) {
+                const uint64_t g = s_gbase[s_dig[p]] + p;
+                if (!v_is_src) out_src[g] = s_buf[p];
+                out_v[g] = s_val[p];
+            }
         }
-        __syncthreads();
     }
     // the other 64-bit word(s)
     const int n_other = v_is_src ? (HAS_W1 ? 2 : 1) : (HAS_W1 ? 1 : 0);
@@ -238,6 +250,7 @@ __global__ void __launch_bounds__(BLOCK, 2) onesweep_kernel(
         const bool take_w1 = HAS_W1 && (v_is_src ? (o == 1) : (src == SRC_W0));
         const uint64_t *inp = take_w1 ? in_w1 : in_w0;
         uint64_t *outp = take_w1 ? out_w1 : out_w0;
+        __syncthreads();
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             uint64_t idx = wbase + (uint64_t)i * 32;
@@ -249,43 +262,34 @@ __global__ void __launch_bounds__(BLOCK, 2) onesweep_kernel(
             uint32_t p = tid + j * BLOCK;
             if (p < n_tile) outp[s_gbase[s_dig[p]] + p] = s_buf[p];
         }
-        __syncthreads();
-    }
-    // the 32-bit payload
-    uint32_t *s_v = reinterpret_cast<uint32_t *>(s_buf);
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) s_v[pos[i]] = val[i];
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        uint32_t p = tid + j * BLOCK;
-        if (p < n_tile) out_v[s_gbase[s_dig[p]] + p] = s_v[p];
     }
 }
 
 template <int BLOCK, int ITEMS>
 constexpr size_t onesweep_smem()
 {
-    return (size_t)BLOCK * ITEMS * 8 + (size_t)(BLOCK / 32) * kRadix * 4 + (size_t)BLOCK * ITEMS;
+    return (size_t)BLOCK * ITEMS * 8 + (size_t)(BLOCK / 32) * kRadix * 4 + (size_t)BLOCK * ITEMS + (size_t)BLOCK * ITEMS * 4;
 }
 
 }  // namespace
 
-SortPlan plan_for_kmer_bits(int key_bits)
+SortPlan plan_for_bit_range(int bit_lo, int bit_hi)
 {
     SortPlan p{};
-    int done = 0;
-    while (done < key_bits) {
+    int done = bit_lo;
+    while (done < bit_hi) {
         int src = done < 64 ? SRC_W0 : SRC_W1;
         int in_word = done < 64 ? done : done - 64;
         int bits = kRadixBits;
         if (in_word + bits > 64) bits = 64 - in_word;
-        if (done + bits > key_bits) bits = key_bits - done;
+        if (done + bits > bit_hi) bits = bit_hi - done;
         p.pass[p.n_passes++] = SortPass{src, in_word, (1u << bits) - 1u};
         done += bits;
     }
     return p;
 }
+
+SortPlan plan_for_kmer_bits(int key_bits) { return plan_for_bit_range(0, key_bits); }
 
 int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint64_t n, const SortPlan &plan,
                void *workspace, uint32_t *err_flag, uint64_t *launches, cudaEvent_t after_hist)

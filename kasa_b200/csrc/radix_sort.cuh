@@ -59,5 +59,7 @@ int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint6
 
 // plan for the identify sort: all significant bits of a K-letter k-mer (5 bits per letter)
 SortPlan plan_for_kmer_bits(int key_bits);
+// LSD passes over key bits [bit_lo, bit_hi) (bit 64+ = second word)
+SortPlan plan_for_bit_range(int bit_lo, int bit_hi);
 
 }  // namespace kasa

@@ -226,8 +226,8 @@ def test_build_matches_reference_files(case, K, six):
 
 def test_build_brick_overflow_compacts_and_continues():
     strings = O.fasta_build_strings(G.gz("k12", "ref.fa.gz"), G.acc2tax("k12"), 12, False)
-    ctx = _ctx(max_batch_kmers=60_000)      # smaller than the 48k windows x 2 pushes of duplicates
-    for _ in range(3):                       # the same data three times: dedup must absorb it
+    ctx = _ctx(max_batch_kmers=100_000)     # 48k windows per push: the third push overflows the brick
+    for _ in range(4):                       # the same data four times: compaction (sort + dedup) must absorb it
         ctx.build_push([s for s, _ in strings], [t for _, t in strings])
     rec, _ = ctx.build_finish()
     assert rec.tobytes() == G.index("k12").tobytes()
