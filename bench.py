@@ -200,6 +200,7 @@ def main_ours(args):
     import torch
     import kasa_b200
     from kasa_b200 import capi
+    from kasa_b200.dist import reduce_counts, shard_first_read
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -238,7 +239,7 @@ def main_ours(args):
     torch.cuda.synchronize()
 
     def gen(step, buf, location):
-        first = (step * world + rank) * R        # ranks take disjoint read ranges
+        first = shard_first_read(step, world, rank, R)        # ranks take disjoint read ranges
         ctx.synth_reads(GENOME_SEED, READ_SEED, first, R, args.taxa, args.genome_len, READ_LEN, out=buf, out_location=location)
 
     for b in range(n_dev_batches):
@@ -341,10 +342,7 @@ def main_ours(args):
 
     # ---- job epilogue: reduce the per-taxon counts across ranks (the only collective of this path)
     ca, cu, total_kmers = ctx.identify_finish()
-    if dist is not None:
-        tca = torch.from_numpy(ca).cuda(); tcu = torch.from_numpy(cu.astype(np.int64)).cuda()
-        dist.all_reduce(tca); dist.all_reduce(tcu)
-        ca = tca.cpu().numpy()
+    ca, cu, total_kmers = reduce_counts(ca, cu, total_kmers, dist, torch.device("cuda", local))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -363,7 +361,7 @@ def main_ours(args):
             "config": workload_config(args, R), "index_entries": int(n_entries), "index_gb": n_entries * 12 / 1e9,
             "index_build_s": build_s, "stage_ms_per_step": stage_ms, "gpu_ms_per_step_lib": gpu_ms_sum / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "identified_frac_k12": float(ca[0].sum() / max(1, total_kmers * (world if dist is not None else 1))),
+            "identified_frac_k12": float(ca[0].sum() / max(1, total_kmers)),
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -408,9 +408,10 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
 //   2^-32 fixed-point column whose carries are counted; the rest (rare) uses 16-bit-split atomics.
 constexpr int kFlatBlock = 128;
 constexpr int kFlatWarps = kFlatBlock / 32;
+constexpr int kFlatMaxB = 8;      // multi-level members per record that go through the shared work list
 
 struct FlatSmem {
-    unsigned long long *tot_fx, *tot_un, *np;
+    unsigned long long *tot_fx, *tot_un, *np, *single;
     uint32_t *lo, *hi, *un, *invfx, *carry, *c0, *tcur, *cu, *fx0;
     uint16_t *list;
     float *w, *inv, *score, *c0f;
@@ -451,7 +452,8 @@ __global__ void __launch_bounds__(kFlatBlock) per_read_flat_kernel(const uint4 *
     S.tot_fx = reinterpret_cast<unsigned long long *>(smem_raw);
     S.tot_un = S.tot_fx + cells;
     S.np = S.tot_un + cells;                                  // [kFlatBlock] packed |taxa_j|, 7 bits per level
-    S.lo = reinterpret_cast<uint32_t *>(S.np + kFlatBlock);
+    S.single = S.np + kFlatBlock;                             // [kFlatBlock] dense k_low-only masks of the current records
+    S.lo = reinterpret_cast<uint32_t *>(S.single + kFlatBlock);
     S.hi = S.lo + cells;
     S.un = S.hi + cells;
     S.invfx = S.un + cells;                                   // [256]
@@ -479,8 +481,7 @@ __global__ void __launch_bounds__(kFlatBlock) per_read_flat_kernel(const uint4 *
 #pragma unroll
     for (int jj = 0; jj < 7; ++jj) S.cu[jj * kFlatBlock + tid] = 0;
     __syncthreads();
-    const int list_cap = 32 * (T - 1);
-    uint16_t *listA = S.list + w * list_cap, *listB = listA + list_cap - 1;       // B grows downwards
+    uint16_t *listB = S.list + w * (32 * kFlatMaxB);                              // [32 * kFlatMaxB] per warp
     const float w0 = S.w[0];
 
     for (uint64_t r0 = (uint64_t)blockIdx.x * kFlatBlock; r0 < n_reads; r0 += (uint64_t)gridDim.x * kFlatBlock) {
@@ -511,22 +512,17 @@ __global__ void __launch_bounds__(kFlatBlock) per_read_flat_kernel(const uint4 *
                     more[wi] = ((R[wi] >> 1) | (R[wi] >> 2)) & L;       // fields >= 2: matched above k_low
                     nB += __popcll(more[wi]);
                 }
-                const uint32_t nA = __popcll(single), n0 = nA + nB;
-                const uint32_t both = nA | (nB << 16);
-                uint32_t incl = both;
+                const uint32_t n0 = __popcll(single) + nB;
+                const bool big = nB > kFlatMaxB;                       // rare: many taxa share more than k_low letters
+                const uint32_t listed = big ? 0u : nB;
+                uint32_t incl = listed;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t up = __shfl_up_sync(kFull, incl, o);
                     if (lane >= o) incl += up;
                 }
-                const uint32_t totals = __shfl_sync(kFull, incl, 31);
-                const uint32_t totalA = totals & 0xffffu, totalB = totals >> 16;
-                uint32_t offA = (incl - both) & 0xffffu, offB = (incl - both) >> 16;
-                while (single) {                                       // dense mask: bit s <-> taxon s + 1
-                    const int t = __ffsll((long long)single);
-                    single &= single - 1;
-                    listA[offA++] = (uint16_t)((lane << 8) | t);
-                }
+                const uint32_t totalB = __shfl_sync(kFull, incl, 31);
+                uint32_t offB = incl - listed;
                 unsigned long long np = n0;                            // |taxa_j| = members matched at more than j levels
                 if (nB) {
 #pragma unroll
@@ -537,26 +533,38 @@ __global__ void __launch_bounds__(kFlatBlock) per_read_flat_kernel(const uint4 *
                             const uint32_t h = (uint32_t)(R[wi] >> (3 * f)) & 7u;
                             m &= ~(7ull << (3 * f));
                             np += kLevelOnes & ((1ull << (7 * h)) - 1);
-                            *(listB - (offB++)) = (uint16_t)((lane << 11) | (h << 8) | (wi * FPW + f + 1));
+                            if (!big) listB[offB++] = (uint16_t)((lane << 11) | (h << 8) | (wi * FPW + f + 1));
                         }
                     }
                 }
                 S.np[tid] = np;
+                S.single[tid] = single;
                 S.c0f[tid] = w0 * S.inv[n0];                           // Compare.hpp:924 weight * (1.f / n)
                 S.fx0[tid] = S.invfx[n0];
                 __syncwarp();
-                // ---- phase B1 (lane = member matched at k_low only)
-                for (uint32_t p = lane; p < totalA; p += 32) {
-                    const uint32_t e = listA[p];
-                    const int col = w * 32 + (int)(e >> 8), t = (int)(e & 255u);
-                    if (scores) S.score[t * kFlatBlock + col] += S.c0f[col];
-                    const uint32_t fx = S.fx0[col];
-                    if (fx == 0) flat_unique_hit(S, T, 0, t, col);
-                    else flat_frac_level0(S, t, col, fx);
+                // ---- phase B1: taxa matched at k_low only.  The set sizes are heavy tailed (1 .. all taxa), so the
+                // 32 masks are dealt out bytewise: lane x takes byte q (taxa 8q+1 .. 8q+8) of record (x + q) mod 32.
+                // A lane's load is then the sum of eight bytes of eight different records; the cells it touches are
+                // still disjoint from every other lane's, and a record's taxa keep the iteration order.
+                {
+                    const unsigned char *sb = reinterpret_cast<const unsigned char *>(S.single + w * 32);
+                    uint64_t work = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) work |= (uint64_t)sb[((lane + q) & 31) * 8 + q] << (8 * q);
+                    while (work) {
+                        const int b = __ffsll((long long)work) - 1;           // bit b <-> taxon b + 1, byte b >> 3
+                        work &= work - 1;
+                        const int col = w * 32 + ((lane + (b >> 3)) & 31), t = b + 1;
+                        if (scores) S.score[t * kFlatBlock + col] += S.c0f[col];
+                        const uint32_t fx = S.fx0[col];
+                        if (fx == 0) atomicAdd(&S.un[t], 1u);      // lone k_low hit of a stray taxon: would only thrash the run cache
+                        else flat_frac_level0(S, t, col, fx);
+                    }
                 }
+                __syncwarp();
                 // ---- phase B2 (lane = member matched at several levels)
                 for (uint32_t p = lane; p < totalB; p += 32) {
-                    const uint32_t e = *(listB - p);
+                    const uint32_t e = listB[p];
                     const int col = w * 32 + (int)(e >> 11), t = (int)(e & 255u);
                     const int h = (int)((e >> 8) & 7u);
                     const unsigned long long npk = S.np[col];
@@ -574,6 +582,32 @@ __global__ void __launch_bounds__(kFlatBlock) per_read_flat_kernel(const uint4 *
                         }
                     }
                     if (scores) S.score[t * kFlatBlock + col] = acc;
+                }
+                __syncwarp();
+                if (big) {                                             // own lane, level-major: same per-cell order
+#pragma unroll 1
+                    for (int wi = 0; wi < 3; ++wi) {
+                        uint64_t m = more[wi];
+                        while (m) {
+                            const int f = ((__ffsll((long long)m) - 1) * 171) >> 9;
+                            const int h = (int)((R[wi] >> (3 * f)) & 7u), t = wi * FPW + f + 1;
+                            m &= ~(7ull << (3 * f));
+                            float acc = scores ? S.score[t * kFlatBlock + tid] : 0.f;
+#pragma unroll 1
+                            for (int j = 0; j < h; ++j) {
+                                const uint32_t nj = (uint32_t)(np >> (7 * j)) & 127u;
+                                acc += S.w[j] * S.inv[nj];
+                                if (nj == 1) atomicAdd(&S.un[j * T + t], 1u);
+                                else if (j == 0) flat_frac_level0(S, t, tid, S.invfx[nj]);
+                                else {
+                                    const uint32_t fx = S.invfx[nj];
+                                    atomicAdd(&S.lo[j * T + t], fx & 0xffffu);
+                                    atomicAdd(&S.hi[j * T + t], fx >> 16);
+                                }
+                            }
+                            if (scores) S.score[t * kFlatBlock + tid] = acc;
+                        }
+                    }
                 }
                 __syncwarp();
             }
@@ -702,9 +736,9 @@ void launch_per_read(cudaStream_t s, const uint64_t *rec, const uint64_t *read_k
     const bool small = lp.num_k <= 8;
     if (lp.hb == 3) {
         const size_t cells = (size_t)lp.num_k * lp.n_taxa, T = lp.n_taxa;
-        const size_t smf = cells * 16 + kFlatBlock * 8 + cells * 12 + 256 * 4 + ((T + 3) & ~(size_t)3) * 4 + 2 * kFlatBlock * 4 +
+        const size_t smf = cells * 16 + 2 * kFlatBlock * 8 + cells * 12 + 256 * 4 + ((T + 3) & ~(size_t)3) * 4 + 2 * kFlatBlock * 4 +
                            7 * kFlatBlock * 4 + T * kFlatBlock * 4 + 32 * 4 + 256 * 4 + kFlatBlock * 4 + (scores ? T * kFlatBlock * 4 : 0) +
-                           (size_t)kFlatWarps * 32 * (T - 1) * 2;
+                           (size_t)kFlatWarps * 32 * kFlatMaxB * 2;
         KASA_CUDA_TRY(cudaFuncSetAttribute(per_read_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
         KASA_CUDA_TRY(cudaFuncSetAttribute(per_read_flat_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         per_read_flat_kernel<<<grid, kFlatBlock, smf, s>>>(reinterpret_cast<const uint4 *>(rec), read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
