@@ -8,6 +8,7 @@
 #include "../../include/kasa_b200.h"
 #include "build.cuh"
 #include "common.cuh"
+#include "exact.cuh"
 #include "extract.cuh"
 #include "lookup.cuh"
 #include "radix_sort.cuh"
@@ -54,6 +55,8 @@ struct kasa_ctx {
     bool build_done = false;
     uint64_t n_trie = 0;
     uint32_t *d_trie_words = nullptr;
+    ExactWorkspace xws{};
+    bool xws_ready = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t sev[KASA_N_STAGES + 1] = {};
     double stage_ms[KASA_N_STAGES] = {};
@@ -303,8 +306,7 @@ int kasa_ctx_create(const kasa_params *p, kasa_ctx **out)
         KASA_REQUIRE(p->k_low >= 1 && p->k_low <= p->k_high && p->k_high <= p->highest_k, KASA_ERR_ARG,
                      "need 1 <= k_low <= k_high <= highest_k");
         KASA_REQUIRE(p->frames == 3 || p->frames == 6, KASA_ERR_ARG, "frames must be 3 or 6 (--one is not supported)");
-        KASA_REQUIRE(p->score_mode == KASA_SCORE_NONE || p->score_mode == KASA_SCORE_FAST, KASA_ERR_ARG,
-                     "score_mode must be KASA_SCORE_NONE or KASA_SCORE_FAST in this version");
+        KASA_REQUIRE(p->score_mode >= KASA_SCORE_NONE && p->score_mode <= KASA_SCORE_EXACT, KASA_ERR_ARG, "unknown score_mode");
         KASA_REQUIRE(p->max_batch_kmers > 0 && p->max_batch_kmers < (1ull << 32) - 2 * kSortTile, KASA_ERR_ARG,
                      "max_batch_kmers must be in (0, 2^32)");
         KASA_REQUIRE(p->max_batch_seqs > 0 && p->max_batch_bases > 0, KASA_ERR_ARG, "max_batch_seqs / max_batch_bases must be > 0");
@@ -503,8 +505,10 @@ int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resul
     const uint64_t n = extract_batch(c, in);
     out->n_kmers = n;
     const bool want_scores = c->p.score_mode != KASA_SCORE_NONE;
-    // identify orders the k-mers on their leading kIdentifySortBits only (lookup.cuh: launch_partition)
-    const int sorted_from = std::max(0, 5 * c->K - kIdentifySortBits);
+    // identify orders the k-mers on their leading kIdentifySortBits only (lookup.cuh: launch_partition); the exact
+    // score mode needs the reference's complete order (its flush points are positions in the sorted array)
+    const bool exact = c->p.score_mode == KASA_SCORE_EXACT;
+    const int sorted_from = exact ? 0 : std::max(0, 5 * c->K - kIdentifySortBits);
     SortPlan plan = plan_for_bit_range(sorted_from, 5 * c->K);
     KASA_CUDA_TRY(cudaEventRecord(c->sev[2], c->stream));
     if (n) {
@@ -520,8 +524,28 @@ int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resul
         launch_partition(c->stream, c->sb.w0[cur], c->sb.w1[cur], n, idx, lp, c->d_part, tq, sorted_from, &c->launches);
         launch_lookup(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, idx, lp, c->d_part, c->d_rec, tq, &c->launches);
         KASA_CUDA_TRY(cudaEventRecord(c->sev[5], c->stream));
-        launch_per_read(c->stream, c->d_rec, c->d_read_koff, in->n_reads, lp, want_scores ? c->d_scores : nullptr, c->d_cnt_fx,
-                        c->d_cnt_un, &c->launches);
+        launch_per_read(c->stream, c->d_rec, c->d_read_koff, in->n_reads, lp, (want_scores && !exact) ? c->d_scores : nullptr,
+                        c->d_cnt_fx, c->d_cnt_un, &c->launches);
+        if (exact) {
+            if (!c->xws_ready) {
+                const uint64_t cap = c->p.max_batch_kmers;
+                c->xws.flags = dev_alloc<uint32_t>(c, cap + 1);
+                c->xws.first = dev_alloc<uint32_t>(c, exact_tiles(cap) * c->num_k + 1);
+                c->xws.next = dev_alloc<uint32_t>(c, exact_tiles(cap) * c->num_k + 1);
+                c->xws.trig = dev_alloc<uint32_t>(c, cap * c->num_k + 1);
+                c->xws.max_inst = dev_alloc<uint32_t>(c, 1);
+                c->xws_ready = true;
+            }
+            launch_exact_triggers(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, idx, lp, c->d_rec, c->xws, &c->launches);
+            launch_exact_max_instances(c->stream, c->d_read_koff, in->n_reads, c->xws.max_inst, &c->launches);
+            uint32_t max_inst = 0;
+            KASA_CUDA_TRY(cudaMemcpyAsync(&max_inst, c->xws.max_inst, 4, cudaMemcpyDeviceToHost, c->stream));
+            KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+            KASA_REQUIRE(launch_exact_scores(c->stream, c->d_rec, c->xws.trig, c->d_read_koff, in->n_reads, max_inst, lp, c->d_scores,
+                                             &c->launches),
+                         KASA_ERR_ARG, "KASA_SCORE_EXACT: a read has too many (k-mer, level) pairs for the shared-memory replay; "
+                                       "use KASA_SCORE_FAST for long reads");
+        }
         launch_fold_counts(c->stream, c->d_cnt_fx, c->d_cnt_un, lp, c->d_tot_all, c->d_tot_un, &c->launches);
     } else {
         for (int i = 3; i <= 5; ++i) KASA_CUDA_TRY(cudaEventRecord(c->sev[i], c->stream));

@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
                             float acc = scores ? s_score[t * kReadBlock + tid] : 0.f;
                             for (uint32_t j = 0; j < h; ++j) {
                                 uint32_t nj = (uint32_t)(nl[LW == 1 ? 0 : (j >> 3)] >> (8 * (j & 7))) & 255u;
-                                acc += s_w[j] * s_inv[nj];
+                                acc = __fadd_rn(acc, __fmul_rn(s_w[j], s_inv[nj]));   // no FMA: the reference rounds the product first
                                 const int c = j * T + t;
                                 if (nj == 1) atomicAdd(&s_un[c], 1u);
                                 else {
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(kFlatBlock) per_read_flat_kernel(const uint4 *
                 }
                 S.np[tid] = np;
                 S.single[tid] = single;
-                S.c0f[tid] = w0 * S.inv[n0];                           // Compare.hpp:924 weight * (1.f / n)
+                S.c0f[tid] = __fmul_rn(w0, S.inv[n0]);                           // Compare.hpp:924 weight * (1.f / n)
                 S.fx0[tid] = S.invfx[n0];
                 __syncwarp();
                 // ---- phase B1: taxa matched at k_low only.  The set sizes are heavy tailed (1 .. all taxa), so the
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(kFlatBlock) per_read_flat_kernel(const uint4 *
 #pragma unroll 1
                     for (int j = 0; j < h; ++j) {
                         const uint32_t nj = (uint32_t)(npk >> (7 * j)) & 127u;
-                        acc += S.w[j] * S.inv[nj];
+                        acc = __fadd_rn(acc, __fmul_rn(S.w[j], S.inv[nj]));   // no FMA: the reference rounds the product first
                         if (nj == 1) flat_unique_hit(S, T, j, t, col);
                         else if (j == 0) flat_frac_level0(S, t, col, S.invfx[nj]);
                         else {
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(kFlatBlock) per_read_flat_kernel(const uint4 *
 #pragma unroll 1
                             for (int j = 0; j < h; ++j) {
                                 const uint32_t nj = (uint32_t)(np >> (7 * j)) & 127u;
-                                acc += S.w[j] * S.inv[nj];
+                                acc = __fadd_rn(acc, __fmul_rn(S.w[j], S.inv[nj]));   // no FMA: the reference rounds the product first
                                 if (nj == 1) atomicAdd(&S.un[j * T + t], 1u);
                                 else if (j == 0) flat_frac_level0(S, t, tid, S.invfx[nj]);
                                 else {

@@ -99,7 +99,7 @@ def test_radix_sort_partial_bits_and_skewed_digits():
 
 
 # ----------------------------------------------------------------------------------------- identify
-def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, rtol=FAST_RTOL):
+def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, rtol=FAST_RTOL, exact=False):
     _, taxids, _ = G.content(case)
     idx = G.index(case)
     if paired:
@@ -107,7 +107,8 @@ def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, r
         reads = [[x[1], y[1]] for x, y in zip(a, b)]
     else:
         reads = [[x[1]] for x in G.fastq(case)]
-    ctx = _ctx(highest_k=K, k_high=k_high, k_low=k_low, frames=6 if six else 3)
+    ctx = _ctx(highest_k=K, k_high=k_high, k_low=k_low, frames=6 if six else 3,
+               score_mode=capi.SCORE_EXACT if exact else capi.SCORE_FAST)
     ctx.load_index(idx, taxids)
     pieces = [reads] if split is None else [reads[:split], reads[split:]]
     scores, n_kmers = [], 0
@@ -127,7 +128,11 @@ def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, r
     assert np.array_equal(cu, ora.count_unique)                               # exact integers
     np.testing.assert_allclose(ca, ora.count_all, rtol=COUNT_RTOL, atol=1e-9)
     assert np.array_equal(scores > 0, ora.scores > 0)                         # same taxa per read
-    np.testing.assert_allclose(scores, ora.scores, rtol=rtol, atol=0)
+    if exact:
+        assert np.array_equal(scores, ora.scores)      # fp32 in the reference's flush order: bit-exact
+        rtol = 0.0
+    else:
+        np.testing.assert_allclose(scores, ora.scores, rtol=rtol, atol=0)
     # ... and against what the reference binary printed
     pr = G.per_read(case, tag)
     tax2idx = {int(t): i for i, t in enumerate(taxids)}
@@ -163,6 +168,14 @@ def test_identify_k12_single_level():
 def test_identify_k25_paired():
     # 19 levels x 520 k-mers: ~10^4 fp32 adds per cell, the order-dependent rounding grows accordingly
     _identify_case("k25", "six_25_7", 25, 25, 7, True, paired=True, rtol=3e-5)
+
+
+@pytest.mark.parametrize("case,tag,K,kh,kl,six,paired", [
+    ("k12", "six_12_7", 12, 12, 7, True, False), ("k12", "three_11_8", 12, 11, 8, False, False),
+    ("k12", "six_12_12", 12, 12, 12, True, False), ("k25", "six_25_7", 25, 25, 7, True, True)])
+def test_identify_exact_mode_is_bit_identical_to_the_reference(case, tag, K, kh, kl, six, paired):
+    """KASA_SCORE_EXACT: every per-read k-mer score equals the fp32 value the reference binary printed."""
+    _identify_case(case, tag, K, kh, kl, six, paired=paired, exact=True)
 
 
 def test_identify_is_batch_independent_and_deterministic():
