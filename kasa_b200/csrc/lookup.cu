@@ -113,11 +113,11 @@ __device__ __forceinline__ int64_t lower_bound(const Acc &acc, int64_t lo, int64
     return lo + (key_lt<W>(acc.template key<W>(lo), q) ? 1 : 0);
 }
 
-// 3-bit records: bit f of the result is set iff field f (bits 3f..3f+2) of w equals 1, i.e. the taxon matched at
-// k_low only.  Stride-3 bit compression in five mask-and-shift steps.
-__device__ __forceinline__ uint64_t dense_single_level(uint64_t w)
+// 3-bit records: bit f of the result is set iff field f (bits 3f..3f+2) of w is non-zero, i.e. the taxon matched at
+// k_low.  Stride-3 bit compression in five mask-and-shift steps.
+__device__ __forceinline__ uint64_t dense_taxa_mask(uint64_t w)
 {
-    uint64_t x = w & ~(w >> 1) & ~(w >> 2) & 0x1249249249249249ull;
+    uint64_t x = (w | (w >> 1) | (w >> 2)) & 0x1249249249249249ull;
     x = (x | (x >> 2)) & 0x10c30c30c30c30c3ull;
     x = (x | (x >> 4)) & 0x100f00f00f00f00full;
     x = (x | (x >> 8)) & 0x001f0000ff0000ffull;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint64_t *__
         if (live[r]) {
             const uint64_t r0 = R[0], r1 = R[kLookupBlock], r2 = R[2 * kLookupBlock];
             uint64_t r3 = R[3 * kLookupBlock];
-            if (HB == 3) r3 = dense_single_level(r0) | (dense_single_level(r1) << 21) | (dense_single_level(r2) << 42);
+            if (HB == 3) r3 = dense_taxa_mask(r0) | (dense_taxa_mask(r1) << 21) | (dense_taxa_mask(r2) << 42);
             uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)iv[r] * kRecWords);
             dst[0] = make_uint4((uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32));
             dst[1] = make_uint4((uint32_t)r2, (uint32_t)(r2 >> 32), (uint32_t)r3, (uint32_t)(r3 >> 32));
@@ -393,263 +393,6 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// per-read accumulation, 3-bit records (num_k <= 7: the default k = 12..7; words 0-2 = 63 taxon fields,
-// word 3 = dense mask of the taxa matched at k_low only, written by the lookup kernel).
-//
-// Lane l of a warp owns read r0 + 32 w + l and walks its instances in emission order, one per iteration.
-// The (instance, taxon) members of the 32 records of an iteration are ragged (1 .. tens per record), so they
-// are first compacted into a shared-memory work list — members matched at k_low only from the front, members
-// matched at several levels from the back — and then processed with one member per lane.  Every (read, taxon)
-// cell is touched by exactly one lane per iteration and iterations are ordered, so the fp32 adds of a cell
-// happen in (instance, k ascending) order: the canonical order of KASA_SCORE_FAST.
-//   counts: |taxa| == 1 hits go to a per-read run cache (same taxon for consecutive instances) that is
-//   emptied with a few 32-bit shared atomics per read; k_low hits with |taxa| >= 2 go to a read-private
-//   2^-32 fixed-point column whose carries are counted; the rest (rare) uses 16-bit-split atomics.
-constexpr int kFlatBlock = 128;
-constexpr int kFlatWarps = kFlatBlock / 32;
-constexpr int kFlatMaxB = 8;      // multi-level members per record that go through the shared work list
-
-struct FlatSmem {
-    unsigned long long *tot_fx, *tot_un, *np, *single;
-    uint32_t *lo, *hi, *un, *invfx, *carry, *c0, *tcur, *cu, *fx0;
-    uint16_t *list;
-    float *w, *inv, *score, *c0f;
-};
-
-__device__ __forceinline__ void flat_unique_hit(const FlatSmem &S, int T, int j, int t, int col)
-{
-    if ((int)S.tcur[col] != t) {
-        const int old = (int)S.tcur[col];
-#pragma unroll
-        for (int jj = 0; jj < 7; ++jj) {
-            const uint32_t v = S.cu[jj * kFlatBlock + col];
-            if (v) { atomicAdd(&S.un[jj * T + old], v); S.cu[jj * kFlatBlock + col] = 0; }
-        }
-        S.tcur[col] = (uint32_t)t;
-    }
-    S.cu[j * kFlatBlock + col] += 1;
-}
-
-__device__ __forceinline__ void flat_frac_level0(const FlatSmem &S, int t, int col, uint32_t fx)
-{
-    const uint32_t old = S.c0[t * kFlatBlock + col], now = old + fx;
-    S.c0[t * kFlatBlock + col] = now;
-    if (now < old) atomicAdd(&S.carry[t], 1u);
-}
-
-__global__ void __launch_bounds__(kFlatBlock) per_read_flat_kernel(const uint4 *__restrict__ rec, const uint64_t *__restrict__ read_koff,
-                                                                   uint32_t n_reads, LevelParams lp, float *__restrict__ scores,
-                                                                   unsigned long long *__restrict__ cnt_fx,
-                                                                   unsigned long long *__restrict__ cnt_unique)
-{
-    constexpr int FPW = 21;
-    constexpr uint64_t L = 0x1249249249249249ull;            // bit 3f, f = 0..20
-    constexpr unsigned long long kLevelOnes = 0x0000040810204080ull;   // 1 << 7j for j = 1..6
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = lp.n_taxa, NK = lp.num_k, cells = NK * T;
-    FlatSmem S;
-    S.tot_fx = reinterpret_cast<unsigned long long *>(smem_raw);
-    S.tot_un = S.tot_fx + cells;
-    S.np = S.tot_un + cells;                                  // [kFlatBlock] packed |taxa_j|, 7 bits per level
-    S.single = S.np + kFlatBlock;                             // [kFlatBlock] dense k_low-only masks of the current records
-    S.lo = reinterpret_cast<uint32_t *>(S.single + kFlatBlock);
-    S.hi = S.lo + cells;
-    S.un = S.hi + cells;
-    S.invfx = S.un + cells;                                   // [256]
-    S.carry = S.invfx + 256;                                  // [T rounded to 4]
-    S.tcur = S.carry + ((T + 3) & ~3);                        // [kFlatBlock]
-    S.fx0 = S.tcur + kFlatBlock;                              // [kFlatBlock] 2^32 / |taxa_0| of the current record (0: unique)
-    S.cu = S.fx0 + kFlatBlock;                                // [7][kFlatBlock]
-    S.c0 = S.cu + 7 * kFlatBlock;                             // [T][kFlatBlock]
-    S.w = reinterpret_cast<float *>(S.c0 + T * kFlatBlock);   // [32]
-    S.inv = S.w + 32;                                         // [256]
-    S.c0f = S.inv + 256;                                      // [kFlatBlock] w(k_low) / |taxa_0| of the current record
-    S.score = S.c0f + kFlatBlock;                             // [T][kFlatBlock]
-    S.list = reinterpret_cast<uint16_t *>(S.score + (scores ? T * kFlatBlock : 0));    // [kFlatWarps][32 * (T - 1)]
-
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < cells; i += kFlatBlock) { S.tot_fx[i] = 0; S.tot_un[i] = 0; S.lo[i] = 0; S.hi[i] = 0; S.un[i] = 0; }
-    for (int i = tid; i < 256; i += kFlatBlock) {
-        S.invfx[i] = i >= 2 ? (uint32_t)(4294967296.0 / i + 0.5) : 0u;
-        S.inv[i] = i ? 1.f / (float)i : 0.f;                  // Compare.hpp:924 (1.f / numOfEntries)
-    }
-    if (tid < 32) { int k = lp.k_low + tid; S.w[tid] = (float)(k * k) / 625.f; }   // Compare.hpp:392
-    for (int t = tid; t < T; t += kFlatBlock) S.carry[t] = 0;
-    for (int t = 0; t < T; ++t) S.c0[t * kFlatBlock + tid] = 0;
-    S.tcur[tid] = 0;
-#pragma unroll
-    for (int jj = 0; jj < 7; ++jj) S.cu[jj * kFlatBlock + tid] = 0;
-    __syncthreads();
-    uint16_t *listB = S.list + w * (32 * kFlatMaxB);                              // [32 * kFlatMaxB] per warp
-    const float w0 = S.w[0];
-
-    for (uint64_t r0 = (uint64_t)blockIdx.x * kFlatBlock; r0 < n_reads; r0 += (uint64_t)gridDim.x * kFlatBlock) {
-        const uint64_t r = r0 + tid;
-        if (scores)
-            for (int t = 0; t < T; ++t) S.score[t * kFlatBlock + tid] = 0.f;
-        uint64_t cur = 0, s_end = 0;
-        if (r < n_reads) { cur = read_koff[r]; s_end = read_koff[r + 1]; }
-        while (__syncthreads_or(cur < s_end)) {
-            const uint32_t mine = (uint32_t)min((uint64_t)kReadChunk, s_end - cur);
-            const uint32_t trips = __reduce_max_sync(kFull, mine);
-            uint4 n0v = make_uint4(0, 0, 0, 0), n1v = make_uint4(0, 0, 0, 0);
-            if (mine) { n0v = __ldg(rec + 2 * cur); n1v = __ldg(rec + 2 * cur + 1); }
-#pragma unroll 1
-            for (uint32_t it = 0; it < trips; ++it) {
-                const uint4 x0 = n0v, x1 = n1v;
-                if (it + 1 < mine) { n0v = __ldg(rec + 2 * (cur + it + 1)); n1v = __ldg(rec + 2 * (cur + it + 1) + 1); }   // next record in flight
-                uint64_t R[3] = {0, 0, 0}, single = 0;
-                if (it < mine) {
-                    R[0] = (uint64_t)x0.x | ((uint64_t)x0.y << 32); R[1] = (uint64_t)x0.z | ((uint64_t)x0.w << 32);
-                    R[2] = (uint64_t)x1.x | ((uint64_t)x1.y << 32); single = (uint64_t)x1.z | ((uint64_t)x1.w << 32);
-                }
-                // ---- phase A (lane = record): work-list slots
-                uint64_t more[3];
-                uint32_t nB = 0;
-#pragma unroll
-                for (int wi = 0; wi < 3; ++wi) {
-                    more[wi] = ((R[wi] >> 1) | (R[wi] >> 2)) & L;       // fields >= 2: matched above k_low
-                    nB += __popcll(more[wi]);
-                }
-                const uint32_t n0 = __popcll(single) + nB;
-                const bool big = nB > kFlatMaxB;                       // rare: many taxa share more than k_low letters
-                const uint32_t listed = big ? 0u : nB;
-                uint32_t incl = listed;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t up = __shfl_up_sync(kFull, incl, o);
-                    if (lane >= o) incl += up;
-                }
-                const uint32_t totalB = __shfl_sync(kFull, incl, 31);
-                uint32_t offB = incl - listed;
-                unsigned long long np = n0;                            // |taxa_j| = members matched at more than j levels
-                if (nB) {
-#pragma unroll
-                    for (int wi = 0; wi < 3; ++wi) {
-                        uint64_t m = more[wi];
-                        while (m) {
-                            const int f = ((__ffsll((long long)m) - 1) * 171) >> 9;
-                            const uint32_t h = (uint32_t)(R[wi] >> (3 * f)) & 7u;
-                            m &= ~(7ull << (3 * f));
-                            np += kLevelOnes & ((1ull << (7 * h)) - 1);
-                            if (!big) listB[offB++] = (uint16_t)((lane << 11) | (h << 8) | (wi * FPW + f + 1));
-                        }
-                    }
-                }
-                S.np[tid] = np;
-                S.single[tid] = single;
-                S.c0f[tid] = __fmul_rn(w0, S.inv[n0]);                           // Compare.hpp:924 weight * (1.f / n)
-                S.fx0[tid] = S.invfx[n0];
-                __syncwarp();
-                // ---- phase B1: taxa matched at k_low only.  The set sizes are heavy tailed (1 .. all taxa), so the
-                // 32 masks are dealt out bytewise: lane x takes byte q (taxa 8q+1 .. 8q+8) of record (x + q) mod 32.
-                // A lane's load is then the sum of eight bytes of eight different records; the cells it touches are
-                // still disjoint from every other lane's, and a record's taxa keep the iteration order.
-                {
-                    const unsigned char *sb = reinterpret_cast<const unsigned char *>(S.single + w * 32);
-                    uint64_t work = 0;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) work |= (uint64_t)sb[((lane + q) & 31) * 8 + q] << (8 * q);
-                    while (work) {
-                        const int b = __ffsll((long long)work) - 1;           // bit b <-> taxon b + 1, byte b >> 3
-                        work &= work - 1;
-                        const int col = w * 32 + ((lane + (b >> 3)) & 31), t = b + 1;
-                        if (scores) S.score[t * kFlatBlock + col] += S.c0f[col];
-                        const uint32_t fx = S.fx0[col];
-                        if (fx == 0) atomicAdd(&S.un[t], 1u);      // lone k_low hit of a stray taxon: would only thrash the run cache
-                        else flat_frac_level0(S, t, col, fx);
-                    }
-                }
-                __syncwarp();
-                // ---- phase B2 (lane = member matched at several levels)
-                for (uint32_t p = lane; p < totalB; p += 32) {
-                    const uint32_t e = listB[p];
-                    const int col = w * 32 + (int)(e >> 11), t = (int)(e & 255u);
-                    const int h = (int)((e >> 8) & 7u);
-                    const unsigned long long npk = S.np[col];
-                    float acc = scores ? S.score[t * kFlatBlock + col] : 0.f;
-#pragma unroll 1
-                    for (int j = 0; j < h; ++j) {
-                        const uint32_t nj = (uint32_t)(npk >> (7 * j)) & 127u;
-                        acc = __fadd_rn(acc, __fmul_rn(S.w[j], S.inv[nj]));   // no FMA: the reference rounds the product first
-                        if (nj == 1) flat_unique_hit(S, T, j, t, col);
-                        else if (j == 0) flat_frac_level0(S, t, col, S.invfx[nj]);
-                        else {
-                            const uint32_t fx = S.invfx[nj];
-                            atomicAdd(&S.lo[j * T + t], fx & 0xffffu);
-                            atomicAdd(&S.hi[j * T + t], fx >> 16);
-                        }
-                    }
-                    if (scores) S.score[t * kFlatBlock + col] = acc;
-                }
-                __syncwarp();
-                if (big) {                                             // own lane, level-major: same per-cell order
-#pragma unroll 1
-                    for (int wi = 0; wi < 3; ++wi) {
-                        uint64_t m = more[wi];
-                        while (m) {
-                            const int f = ((__ffsll((long long)m) - 1) * 171) >> 9;
-                            const int h = (int)((R[wi] >> (3 * f)) & 7u), t = wi * FPW + f + 1;
-                            m &= ~(7ull << (3 * f));
-                            float acc = scores ? S.score[t * kFlatBlock + tid] : 0.f;
-#pragma unroll 1
-                            for (int j = 0; j < h; ++j) {
-                                const uint32_t nj = (uint32_t)(np >> (7 * j)) & 127u;
-                                acc = __fadd_rn(acc, __fmul_rn(S.w[j], S.inv[nj]));   // no FMA: the reference rounds the product first
-                                if (nj == 1) atomicAdd(&S.un[j * T + t], 1u);
-                                else if (j == 0) flat_frac_level0(S, t, tid, S.invfx[nj]);
-                                else {
-                                    const uint32_t fx = S.invfx[nj];
-                                    atomicAdd(&S.lo[j * T + t], fx & 0xffffu);
-                                    atomicAdd(&S.hi[j * T + t], fx >> 16);
-                                }
-                            }
-                            if (scores) S.score[t * kFlatBlock + tid] = acc;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-            cur += mine;
-            if (cur >= s_end && S.tcur[tid]) {       // read finished: empty its run cache
-                const int old = (int)S.tcur[tid];
-#pragma unroll
-                for (int jj = 0; jj < 7; ++jj) {
-                    const uint32_t v = S.cu[jj * kFlatBlock + tid];
-                    if (v) { atomicAdd(&S.un[jj * T + old], v); S.cu[jj * kFlatBlock + tid] = 0; }
-                }
-                S.tcur[tid] = 0;
-            }
-            __syncthreads();
-            for (int i = tid; i < cells; i += kFlatBlock) {
-                S.tot_fx[i] += ((unsigned long long)S.hi[i] << 16) + S.lo[i];
-                S.tot_un[i] += S.un[i];
-                S.lo[i] = 0; S.hi[i] = 0; S.un[i] = 0;
-                if (i < T) { S.tot_fx[i] += (unsigned long long)S.carry[i] << 32; S.carry[i] = 0; }
-            }
-        }
-        if (scores) {
-            const uint64_t rows = min((uint64_t)kFlatBlock, n_reads - r0);
-            for (uint64_t i = tid; i < rows * T; i += kFlatBlock) {
-                uint32_t rr = (uint32_t)(i / T), t = (uint32_t)(i % T);
-                scores[r0 * T + i] = S.score[t * kFlatBlock + rr];
-            }
-            __syncthreads();
-        }
-    }
-    for (int t = 0; t < T; ++t) {                    // residuals of the read-private k_low accumulators
-        const uint32_t v = S.c0[t * kFlatBlock + tid];
-        if (v) { atomicAdd(&S.lo[t], v & 0xffffu); atomicAdd(&S.hi[t], v >> 16); }
-    }
-    __syncthreads();
-    for (int i = tid; i < cells; i += kFlatBlock) {
-        S.tot_fx[i] += ((unsigned long long)S.hi[i] << 16) + S.lo[i];
-        if (S.tot_fx[i]) atomicAdd(cnt_fx + i, S.tot_fx[i]);
-        if (S.tot_un[i]) atomicAdd(cnt_unique + i, S.tot_un[i]);
-    }
-}
-
 __global__ void read_offsets_kernel(const uint64_t *__restrict__ koff, const uint32_t *__restrict__ first_seq, uint32_t n_reads,
                                     uint64_t *__restrict__ out)
 {
@@ -734,15 +477,7 @@ void launch_per_read(cudaStream_t s, const uint64_t *rec, const uint64_t *read_k
         kern<<<grid, kReadBlock, sm, s>>>(reinterpret_cast<const uint4 *>(rec), read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
     };
     const bool small = lp.num_k <= 8;
-    if (lp.hb == 3) {
-        const size_t cells = (size_t)lp.num_k * lp.n_taxa, T = lp.n_taxa;
-        const size_t smf = cells * 16 + 2 * kFlatBlock * 8 + cells * 12 + 256 * 4 + ((T + 3) & ~(size_t)3) * 4 + 2 * kFlatBlock * 4 +
-                           7 * kFlatBlock * 4 + T * kFlatBlock * 4 + 32 * 4 + 256 * 4 + kFlatBlock * 4 + (scores ? T * kFlatBlock * 4 : 0) +
-                           (size_t)kFlatWarps * 32 * kFlatMaxB * 2;
-        KASA_CUDA_TRY(cudaFuncSetAttribute(per_read_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
-        KASA_CUDA_TRY(cudaFuncSetAttribute(per_read_flat_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        per_read_flat_kernel<<<grid, kFlatBlock, smf, s>>>(reinterpret_cast<const uint4 *>(rec), read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
-    }
+    if (lp.hb == 3) launch_per_read_taxon(s, rec, read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
     else if (lp.hb == 4) { if (small) go(per_read_kernel<4, 1>); else go(per_read_kernel<4, 4>); }
     else go(per_read_kernel<5, 4>);
     ++*launches;

@@ -29,7 +29,7 @@ constexpr int kRecWords = 4;           // match record = 4 x u64 = one 32-byte s
 
 // bits needed to store a level count 0..num_k, and how many taxa one record can describe
 inline int record_level_bits(int num_k) { return num_k <= 7 ? 3 : (num_k <= 15 ? 4 : 5); }
-// 3-bit records keep their fourth word for a dense bit mask of the taxa matched at k_low only (see lookup.cu)
+// 3-bit records keep their fourth word for a dense bit mask of the taxa matched at k_low (see lookup.cu)
 inline int record_taxa_capacity(int hb) { return hb == 3 ? 63 : kRecWords * (64 / hb); }
 
 // per-tile index spans: part[2t], part[2t+1] = [first entry sharing the sorted prefix of the tile's first query,
@@ -50,6 +50,10 @@ void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, c
 // Level j = 0 is k_low.  scores may be nullptr (profile only).
 void launch_per_read(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp,
                      float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, uint64_t *launches);
+
+// 3-bit records (per_read.cu): warp per read, lane per taxon
+void launch_per_read_taxon(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp,
+                           float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique);
 
 // read_koff[r] = koff[read_first_seq[r]] (or koff[r])
 void launch_read_offsets(cudaStream_t s, const uint64_t *koff, const uint32_t *read_first_seq, uint32_t n_reads,

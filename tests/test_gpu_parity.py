@@ -18,7 +18,7 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FAST_RTOL = 4e-6
+FAST_RTOL = 1e-5
 COUNT_RTOL = 1e-6
 
 
