@@ -1,0 +1,431 @@
+// kasa_b200 host CLI — `build` and `identify` with kASA's flags, files and outputs (main.cpp:303-586 of the
+// reference for the flag names; formats per SURVEY.md §3.4 / Compare.hpp:1485-1890, 3466-3665).  FASTA/FASTQ(.gz)
+// parsing, content file, scoring and writers stay on the host; all k-mer work goes through libkasa_b200.so.
+#include <chrono>
+#include <iostream>
+
+#include "../../include/kasa_b200.h"
+#include "kasa_host.hpp"
+
+using namespace kasa_host;
+
+namespace {
+
+struct Args {
+    std::string mode, content, index, input, in1, in2, profile, rtt, tmp;
+    int k_high = 12, k_low = 7, highest_k = 12, beasts = 3, device = 0;
+    bool six = false, verbose = false, exact = false;
+    float threshold = 0.f;
+    std::string format = "json";
+    uint32_t batch_reads = 1u << 20;
+};
+
+[[noreturn]] void usage()
+{
+    std::cout << "kasa_b200 <build|identify> -c <content> -d <index> [-i <input> | -1 <fq> -2 <fq>] [-p <profile.csv>] [-q <per-read out>]\n"
+                 "          [-k <high> <low>] [--kH <12|25>] [--six] [--json|--jsonl|--tsv|--kraken] [-b <n>] [--threshold <f>] [-v]\n"
+                 "          [--exact-scores] [--device <n>] [--batch-reads <n>]   (-m -n -t -r -x are accepted and ignored)\n";
+    std::exit(0);
+}
+
+Args parse(int argc, char **argv)
+{
+    Args a;
+    if (argc < 2) usage();
+    a.mode = argv[1];
+    for (int i = 2; i < argc; ++i) {
+        const std::string p = argv[i];
+        auto next = [&]() -> std::string { if (i + 1 >= argc) throw std::runtime_error("missing value after " + p); return argv[++i]; };
+        if (p == "-c" || p == "--content") a.content = next();
+        else if (p == "-d" || p == "--database") a.index = next();
+        else if (p == "-i" || p == "--input") a.input = next();
+        else if (p == "-1") a.in1 = next();
+        else if (p == "-2") a.in2 = next();
+        else if (p == "-p" || p == "--profile") a.profile = next();
+        else if (p == "-q" || p == "--rtt") a.rtt = next();
+        else if (p == "-t" || p == "--temp") a.tmp = next();
+        else if (p == "-k") { a.k_high = std::stoi(next()); a.k_low = std::stoi(next()); }
+        else if (p == "--kH") a.highest_k = std::stoi(next()) > 12 ? 25 : 12;
+        else if (p == "--kL") (void)next();
+        else if (p == "-b" || p == "--beasts") { a.beasts = std::stoi(next()); if (a.beasts == 0) a.beasts = 1; }
+        else if (p == "--threshold") a.threshold = std::stof(next());
+        else if (p == "--six") a.six = true;
+        else if (p == "--three") a.six = false;
+        else if (p == "--json") a.format = "json";
+        else if (p == "--jsonl") a.format = "jsonl";
+        else if (p == "--tsv") a.format = "tsv";
+        else if (p == "--kraken") a.format = "kraken";
+        else if (p == "-v" || p == "--verbose") a.verbose = true;
+        else if (p == "--exact-scores") a.exact = true;
+        else if (p == "--device") a.device = std::stoi(next());
+        else if (p == "--batch-reads") a.batch_reads = (uint32_t)std::stoul(next());
+        else if (p == "-m" || p == "-n" || p == "-x") (void)next();
+        else if (p == "-r" || p == "--ram") {}
+        else if (p == "-h" || p == "--help") usage();
+        else throw std::runtime_error("unknown parameter " + p);
+    }
+    return a;
+}
+
+void check(int rc, kasa_ctx *ctx)
+{
+    if (rc != KASA_OK) throw std::runtime_error(kasa_last_error(ctx));
+}
+
+// ------------------------------------------------------------------------------------------------ build
+int run_build(const Args &a)
+{
+    const int K = a.highest_k;
+    Content content = load_content(a.content);
+    const std::string fasta = slurp(a.input);
+    kasa_params p{};
+    p.device = a.device; p.highest_k = K; p.k_high = K; p.k_low = std::min(7, K); p.frames = a.six ? 6 : 3;
+    p.score_mode = KASA_SCORE_NONE;
+    const uint64_t windows = (uint64_t)fasta.size() * (a.six ? 2 : 1) + (1u << 20);
+    p.max_batch_kmers = std::min<uint64_t>(std::max<uint64_t>(windows * 2, 1u << 22), (1ull << 32) - (1u << 20));
+    p.max_batch_seqs = 1u << 20;
+    p.max_batch_bases = 256ull << 20;
+    kasa_ctx *ctx = nullptr;
+    check(kasa_ctx_create(&p, &ctx), nullptr);
+    std::string chars;
+    std::vector<uint64_t> starts;
+    std::vector<uint32_t> lens, tax;
+    auto flush = [&]() {
+        if (starts.empty()) return;
+        kasa_seq_batch sb{(uint32_t)starts.size(), KASA_MEM_HOST, chars.data(), starts.data(), lens.data(), tax.data()};
+        check(kasa_build_push(ctx, &sb), ctx);
+        chars.clear(); starts.clear(); lens.clear(); tax.clear();
+    };
+    fasta_build_strings(fasta, content.acc2tax, K, a.six, [&](const std::string &s, uint32_t t) {
+        if (s.empty()) return;
+        if (chars.size() + s.size() > p.max_batch_bases - 64 || starts.size() + 1 >= p.max_batch_seqs) flush();
+        starts.push_back(chars.size());
+        lens.push_back((uint32_t)s.size());
+        tax.push_back(t);
+        chars += s;
+    });
+    flush();
+    uint64_t n = 0, nt = 0;
+    check(kasa_build_finish(ctx, &n, &nt), ctx);
+    const size_t rec = K > 12 ? 20 : 12, block = K > 12 ? 2048000 : 2101248;
+    std::vector<char> entries(n * rec), trie(nt * 12);
+    check(kasa_build_fetch(ctx, entries.data(), trie.data()), ctx);
+    write_padded(a.index, entries.data(), entries.size(), block);
+    {
+        std::ofstream f(a.index + "_info.txt");           // Build.hpp:466-470
+        f << n;
+        if (K > 12) f << std::endl << 128;
+    }
+    write_padded(a.index + "_trie", trie.data(), trie.size(), 2101248);
+    { std::ofstream f(a.index + "_trie.txt"); f << nt; }  // Trie.hpp:387-388
+    std::vector<uint64_t> freq(content.taxids.size() * (size_t)K);
+    check(kasa_build_frequency(ctx, content.taxids.data(), (uint32_t)content.taxids.size(), freq.data()), ctx);
+    {
+        std::ofstream f(a.index + "_f.txt");              // kASA.hpp:549-570
+        std::ifstream cf(a.content);
+        f << "non_unique";
+        for (int k = 0; k < K; ++k) f << "\t" << freq[k];
+        f << std::endl;
+        std::string line;
+        for (size_t j = 1; j < content.taxids.size() && std::getline(cf, line);) {
+            if (line.empty()) continue;
+            f << split(line, '\t')[0] << "\t" << freq[j * K];
+            for (int k = 1; k < K; ++k) f << "\t" << freq[j * K + k];
+            f << std::endl;
+            ++j;
+        }
+    }
+    kasa_ctx_destroy(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ identify
+struct Hit {
+    size_t idx;
+    float score;
+    double rel;
+};
+
+int run_identify(const Args &a)
+{
+    Content content = load_content(a.content);
+    const size_t T = content.taxids.size();
+    // index: <idx>_info.txt = count [\n 128 | 3] (main.cpp:982-991)
+    uint64_t n_idx = 0;
+    int bits = 64;
+    {
+        std::ifstream f(a.index + "_info.txt");
+        if (!f) throw std::runtime_error("Index info file not found: " + a.index + "_info.txt");
+        std::string tok;
+        f >> n_idx;
+        if (f >> tok) {
+            if (tok == "128") bits = 128;
+            else if (tok == "3") throw std::runtime_error("halved (6-byte) indices are not supported by kasa_b200");
+        }
+    }
+    const int K = bits == 128 ? 25 : 12;
+    const int k_high = std::min(a.k_high, K), k_low = a.k_low, numK = k_high - k_low + 1;
+    // frequencies: column for k_high (Compare.hpp:165-176)
+    std::vector<uint64_t> freq_high(T, 0);
+    {
+        std::ifstream f(a.index + "_f.txt");
+        if (!f) throw std::runtime_error("The content file or the frequency file cannot be found!");
+        std::string line;
+        size_t i = 0;
+        while (std::getline(f, line) && i < T) {
+            if (line.empty()) continue;
+            auto v = split(line, '\t');
+            const size_t nk = v.size() - 1;
+            freq_high[i++] = std::stoull(v[1 + nk - k_high]);
+        }
+    }
+    std::string rd1 = slurp(a.in1.empty() ? a.input : a.in1), rd2;
+    std::vector<ReadRec> reads = parse_reads(rd1), mates;
+    rd1.clear(); rd1.shrink_to_fit();
+    const bool paired = !a.in2.empty();
+    if (paired) { rd2 = slurp(a.in2); mates = parse_reads(rd2); rd2.clear(); }
+    if (paired && mates.size() != reads.size()) throw std::runtime_error("paired-end files differ in their number of reads");
+
+    kasa_params p{};
+    p.device = a.device; p.highest_k = K; p.k_high = k_high; p.k_low = k_low; p.frames = a.six ? 6 : 3;
+    p.score_mode = a.rtt.empty() ? KASA_SCORE_NONE : (a.exact ? KASA_SCORE_EXACT : KASA_SCORE_FAST);
+    const uint32_t per_batch = std::max<uint32_t>(1, std::min<uint32_t>(a.batch_reads, (uint32_t)reads.size()));
+    uint64_t max_bases = 0, max_kmers = 0;
+    const uint32_t marker = 3 * (K - k_low);
+    for (size_t b = 0; b < reads.size(); b += per_batch) {
+        uint64_t bases = 0, kmers = 0;
+        for (size_t r = b; r < std::min(reads.size(), b + per_batch); ++r)
+            for (int m = 0; m < (paired ? 2 : 1); ++m) {
+                const size_t L = (m ? mates[r] : reads[r]).seq.size();
+                bases += L;
+                if (L + marker > (size_t)(3 * K + 1)) kmers += (L + marker - 3 * K + 1) * (a.six ? 2 : 1);
+            }
+        max_bases = std::max(max_bases, bases); max_kmers = std::max(max_kmers, kmers);
+    }
+    p.max_batch_kmers = max_kmers + 4096; p.max_batch_seqs = per_batch * (paired ? 2 : 1) + 1; p.max_batch_bases = max_bases + 4096;
+    kasa_ctx *ctx = nullptr;
+    check(kasa_ctx_create(&p, &ctx), nullptr);
+    {
+        std::ifstream f(a.index, std::ios::binary);
+        if (!f) throw std::runtime_error("Index file not found: " + a.index);
+        std::vector<char> bytes(n_idx * (bits == 128 ? 20 : 12));
+        f.read(bytes.data(), (std::streamsize)bytes.size());
+        check(kasa_index_load(ctx, bytes.data(), n_idx, bits, content.taxids.data(), (uint32_t)T), ctx);
+    }
+
+    std::ofstream out;
+    if (!a.rtt.empty()) {
+        out.open(a.rtt);
+        if (!out) throw std::runtime_error("Readwise output file could not be created!");
+        if (a.format == "tsv") out << "#Read number\tSpecifier from input file\tMatched taxa\tNames\tScores{relative,k-mer}\tError\n";
+        else if (a.format == "json") out << "[\n";
+    }
+    const int frames = a.six ? 6 : 3;
+    uint64_t n_kmers_total = 0, read_no = 0;
+    std::vector<float> scores;
+    std::string chars, o;
+    std::vector<uint64_t> starts;
+    std::vector<uint32_t> lens, first;
+    std::vector<Hit> hits(T);
+    for (size_t b = 0; b < reads.size(); b += per_batch) {
+        const size_t e = std::min(reads.size(), b + per_batch);
+        chars.clear(); starts.clear(); lens.clear(); first.clear();
+        for (size_t r = b; r < e; ++r) {
+            first.push_back((uint32_t)starts.size());
+            for (int m = 0; m < (paired ? 2 : 1); ++m) {
+                const std::string &s = (m ? mates[r] : reads[r]).seq;
+                starts.push_back(chars.size()); lens.push_back((uint32_t)s.size()); chars += s;
+            }
+        }
+        first.push_back((uint32_t)starts.size());
+        kasa_read_batch in{};
+        in.n_reads = (uint32_t)(e - b); in.n_seqs = (uint32_t)starts.size(); in.format = KASA_SEQ_ASCII; in.location = KASA_MEM_HOST;
+        in.bases = chars.data(); in.seq_start = starts.data(); in.seq_len = lens.data(); in.read_first_seq = first.data();
+        kasa_batch_result res{};
+        scores.assign(a.rtt.empty() ? 0 : (e - b) * T, 0.f);
+        res.scores = scores.empty() ? nullptr : scores.data(); res.scores_location = KASA_MEM_HOST;
+        check(kasa_identify_batch(ctx, &in, &res), ctx);
+        n_kmers_total += res.n_kmers;
+        if (a.rtt.empty()) { read_no += e - b; continue; }
+        // ---- per-read output (Compare.hpp:1485-1890)
+        for (size_t r = b; r < e; ++r, ++read_no) {
+            std::string name = reads[r].name + " ";
+            uint32_t length = (uint32_t)reads[r].seq.size() + reads[r].lines;
+            if (paired) { name += mates[r].name + " "; length += (uint32_t)mates[r].seq.size() + mates[r].lines; }
+            const float best = best_score(length, k_high, k_low, frames);
+            const float *row = scores.data() + (r - b) * T;
+            size_t nh = 0;
+            for (size_t t = 1; t < T; ++t)
+                if (row[t] > 0.f) {
+                    const double rel = row[t] / (1.0 + std::log2((double)freq_high[t] * double(length - K * 3 + 1)));
+                    if (rel >= a.threshold) hits[nh++] = Hit{t, row[t], rel};
+                }
+            o.clear();
+            if (nh == 0) {
+                if (a.format == "tsv") { o += std::to_string(read_no) + "\t" + name + "\t-\t-\t-\t-\n"; }
+                else if (a.format == "json") {
+                    o += read_no == 0 ? "{\n" : ",\n{\n";
+                    o += "\t\"Read number\": " + std::to_string(read_no) + ",\n\t\"Specifier from input file\": \"" + name + "\",\n\t\"Length\": " +
+                         std::to_string(length) + ",\n\t\"Top hits\": [\n\t],\n\t\"Further hits\": [\n\t]\n}";
+                } else if (a.format == "jsonl") {
+                    o += "{ \"Read number\": " + std::to_string(read_no) + ", \"Specifier from input file\": \"" + name + "\", \"Length\": " +
+                         std::to_string(length) + ", \"Top hits\": [], \"Further hits\": [] }\n";
+                } else {
+                    o += "U\t" + name + "\t0\t";
+                    o += (char)length;                        // the reference appends the length as a raw char here (Compare.hpp:1568)
+                    o += "\tA:00\n";
+                }
+                out << o;
+                continue;
+            }
+            std::stable_sort(hits.begin(), hits.begin() + nh, [](const Hit &x, const Hit &y) { return x.rel > y.rel; });
+            float maxv = 0.f;
+            for (size_t i = 0; i < nh; ++i) maxv = std::max(maxv, hits[i].score);
+            size_t top = 1;
+            for (size_t i = 1; i < nh && (int64_t)i < a.beasts; ++i) { if (hits[i].score / maxv > 0.8f) ++top; else break; }
+            auto hit_json = [&](const Hit &h, bool lines) {
+                const char *sep = lines ? " " : "\n\t\t";
+                std::string s;
+                s += lines ? "{" : "\t{";
+                s += std::string(sep) + "\"tax ID\": \"" + std::to_string(content.taxids[h.idx]) + "\",";
+                s += std::string(sep) + "\"Name\": \"" + content.names[h.idx] + "\",";
+                s += std::string(sep) + "\"k-mer Score\": "; append_double((double)h.score, s); s += ",";
+                s += std::string(sep) + "\"Relative Score\": "; append_double(h.rel, s); s += ",";
+                s += std::string(sep) + "\"Error\": "; append_double((double)((best - h.score) / best), s);
+                s += lines ? "}" : "\n\t}";
+                return s;
+            };
+            // entries after the top hits: up to `beasts` distinct k-mer scores (Compare.hpp:1721-1752)
+            auto further = [&](auto fn) {
+                float before = 0;
+                for (size_t j = top, i = top; i < nh && (int64_t)j < a.beasts; ++i) {
+                    fn(hits[i], i == top);
+                    if (before != hits[i].score) { before = hits[i].score; ++j; }
+                }
+            };
+            if (a.format == "jsonl") {
+                o += "{ \"Read number\": " + std::to_string(read_no) + ", \"Specifier from input file\": \"" + name + "\", \"Length\": " +
+                     std::to_string(length) + ", \"Top hits\": [";
+                for (size_t i = 0; i < top; ++i) { if (i) o += ","; o += hit_json(hits[i], true); }
+                o += "], \"Further hits\": [";
+                further([&](const Hit &h, bool firstOne) { if (!firstOne) o += ", "; o += hit_json(h, true); });
+                o += "] }\n";
+            } else if (a.format == "json") {
+                o += read_no == 0 ? "{\n" : ",\n{\n";
+                o += "\t\"Read number\": " + std::to_string(read_no) + ",\n\t\"Specifier from input file\": \"" + name + "\",\n\t\"Length\": " +
+                     std::to_string(length) + ",\n\t\"Top hits\": [\n";
+                for (size_t i = 0; i < top; ++i) { if (i) o += ",\n"; o += hit_json(hits[i], false); }
+                o += "\n\t],\n\t\"Further hits\": [\n";
+                further([&](const Hit &h, bool firstOne) { if (!firstOne) o += ",\n"; o += hit_json(h, false); });
+                o += "\n\t]\n}";
+            } else if (a.format == "tsv") {
+                std::string s1 = std::to_string(read_no) + "\t" + name + "\t", s2, s3, s4;
+                float before = 0;
+                for (size_t j = 0, i = 0; i < nh && (int64_t)j < a.beasts; ++i) {
+                    s1 += std::to_string(content.taxids[hits[i].idx]) + ";";
+                    s2 += content.names[hits[i].idx] + ";";
+                    append_double(hits[i].rel, s3); s3 += ","; append_double((double)hits[i].score, s3); s3 += ";";
+                    append_double((double)((best - hits[i].score) / best), s4); s4 += ";";
+                    if (before != hits[i].score) { before = hits[i].score; ++j; }
+                }
+                for (std::string *s : {&s1, &s2, &s3, &s4}) if (!s->empty() && s->back() == ';') s->pop_back();
+                if (!s2.empty()) o += s1 + "\t" + s2 + "\t" + s3 + "\t" + s4 + "\n";
+            } else {
+                o += "C\t" + name + "\t" + std::to_string(content.taxids[hits[0].idx]) + "\t" + std::to_string(length) + "\t";
+                for (size_t i = 0; i < top; ++i) { o += std::to_string(content.taxids[hits[i].idx]) + ":"; append_double((double)hits[i].score, o); o += " "; }
+                further([&](const Hit &h, bool) { o += std::to_string(content.taxids[h.idx]) + ":"; append_double((double)h.score, o); o += " "; });
+                o += "\n";
+            }
+            out << o;
+        }
+    }
+    if (!a.rtt.empty() && a.format == "json") out << "\n]";
+    out.close();
+
+    // ---- profile (Compare.hpp:3466-3665)
+    std::vector<double> ca(numK * T);
+    std::vector<uint64_t> cu(numK * T);
+    check(kasa_identify_finish(ctx, ca.data(), cu.data(), nullptr), ctx);
+    std::vector<uint64_t> sum_u(numK, 0);
+    std::vector<double> sum_n(numK, 0.0);
+    for (size_t t = 1; t < T; ++t)
+        for (int ik = 0; ik < numK; ++ik) { sum_u[ik] += cu[ik * T + t]; sum_n[ik] += ca[ik * T + t]; }
+    if (!a.profile.empty()) {
+        std::vector<size_t> order;
+        for (size_t t = 0; t < T; ++t) order.push_back(t);
+        std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+            for (int ik = 0; ik < numK; ++ik) {
+                const uint64_t ux = x ? cu[ik * T + x] : 0, uy = y ? cu[ik * T + y] : 0;
+                if (ux != uy) return ux > uy;
+            }
+            return false;
+        });
+        std::vector<uint64_t> garbage(numK, 0);
+        for (int i = k_high - k_low, j = 0; i > 0; --i, ++j) garbage[j] = read_no * (uint64_t)frames * i;
+        std::ofstream tf(a.profile);
+        if (!tf) throw std::runtime_error("Profile file couldn't be opened for writing!");
+        std::ostringstream body;
+        tf << "#taxID,Name";
+        for (const char *h : {"Unique counts k=", "Unique rel. freq. k=", "Non-unique counts k=", "Non-unique rel. freq. k=", "Overall rel. freq. k=",
+                              "Overall unique rel. freq. k="})
+            for (int ik = 0; ik < numK; ++ik) tf << "," << h << k_high - ik;
+        tf << "\n";
+        std::vector<double> sum_id(numK, 0), sum_uid(numK, 0);
+        for (size_t t : order) {
+            if (t == 0 || !(ca[(numK - 1) * T + t] > 0)) continue;
+            body << content.taxids[t] << "," << content.names[t];
+            for (int ik = 0; ik < numK; ++ik) body << "," << cu[ik * T + t];
+            for (int ik = 0; ik < numK; ++ik) { if (cu[ik * T + t] == 0) body << "," << 0.0; else body << "," << (double)cu[ik * T + t] / sum_u[ik]; }
+            for (int ik = 0; ik < numK; ++ik) body << "," << ca[ik * T + t];
+            for (int ik = 0; ik < numK; ++ik) { if (ca[ik * T + t] == 0) body << "," << 0.0; else body << "," << ca[ik * T + t] / sum_n[ik]; }
+            for (int ik = 0; ik < numK; ++ik) { sum_id[ik] += ca[ik * T + t]; body << "," << ca[ik * T + t] / (double)(n_kmers_total - garbage[ik]); }
+            for (int ik = 0; ik < numK; ++ik) { sum_uid[ik] += (double)cu[ik * T + t]; body << "," << (double)cu[ik * T + t] / (double)(n_kmers_total - garbage[ik]); }
+            body << "\n";
+        }
+        tf << "0,not identified";
+        for (int i = 0; i < numK * 4; ++i) tf << "," << 0.0;
+        for (int ik = 0; ik < numK; ++ik) tf << "," << ((double)n_kmers_total - (double)garbage[ik] - sum_id[ik]) / ((double)n_kmers_total - (double)garbage[ik]);
+        for (int ik = 0; ik < numK; ++ik) tf << "," << ((double)n_kmers_total - (double)garbage[ik] - sum_uid[ik]) / ((double)n_kmers_total - (double)garbage[ik]);
+        tf << "\n" << body.str();
+    }
+    if (a.verbose) {
+        double all = 0;
+        for (size_t t = 1; t < T; ++t) all += ca[(numK - 1) * T + t];
+        std::cout << "OUT: Number of k-mers in input: " << n_kmers_total << " of which " << all / n_kmers_total * 100. << " % were identified." << std::endl;
+        std::cout << "OUT: Number of uniques:";
+        for (int ik = 0; ik < numK; ++ik) std::cout << " " << sum_u[ik];
+        std::cout << std::endl;
+    }
+    kasa_ctx_destroy(ctx);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    try {
+        const auto t0 = std::chrono::steady_clock::now();
+        Args a = parse(argc, argv);
+        int rc;
+        if (a.mode == "host-build-strings") {              // host-only (no device): the strings `build` would push
+            Content c = load_content(a.content);
+            fasta_build_strings(slurp(a.input), c.acc2tax, a.highest_k, a.six,
+                                [](const std::string &s, uint32_t t) { std::cout << t << "\t" << s << "\n"; });
+            return 0;
+        }
+        if (a.mode == "host-reads") {                      // host-only: parsed reads (name, +lines, sequence)
+            for (const ReadRec &r : parse_reads(slurp(a.input))) std::cout << r.name << "\t" << r.lines << "\t" << r.seq << "\n";
+            return 0;
+        }
+        if (a.mode == "build") rc = run_build(a);
+        else if (a.mode == "identify") rc = run_identify(a);
+        else if (a.mode == "-h" || a.mode == "--help") usage();
+        else throw std::runtime_error("mode not supported by kasa_b200: " + a.mode + " (build, identify)");
+        std::cout << "OUT: Time: " << std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count() << " s" << std::endl;
+        return rc;
+    } catch (const std::exception &e) {
+        std::cerr << "ERROR: " << e.what() << std::endl;      // main.cpp:1717-1720
+        return 1;
+    }
+}

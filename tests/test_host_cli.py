@@ -1,0 +1,167 @@
+"""The C++ host front end (kasa_b200/host, binary kasa_b200/kasa_b200_cli): kASA's flags, files and outputs above
+the C ABI.  CPU tests cover the host-only logic (FASTA piece/marker logic, read parsing, number formatting);
+the GPU tests run `build` / `identify` on the golden inputs and compare with what the reference binary wrote
+(tests/golden/*, oracle/make_golden.py): index / trie / info / frequency files byte for byte, per-read JSONL
+equal after JSON parsing (every float parses to the same double, --exact-scores), profile CSV numerically.
+"""
+import gzip
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util as G
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "kasa_b200", "kasa_b200_cli")
+
+
+def _cli(*args, cwd=None):
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "kasa_b200", "csrc")])
+    p = subprocess.run([CLI, *args], cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    return p.returncode, p.stdout, p.stderr
+
+
+def _g(case, name):
+    return os.path.join(G.GOLD, case, name)
+
+
+# ------------------------------------------------------------------------------------------- host only (CPU)
+@pytest.mark.parametrize("case,K,six", [("k12", 12, False), ("k12_build6", 12, True), ("k25", 25, False), ("k12", 12, True)])
+def test_build_strings_match_oracle(case, K, six):
+    """readFasta piece / marker logic incl. the 2048-byte chunk quirk (Read.hpp:2306-2578), reading .gz."""
+    args = ["host-build-strings", "-c", _g(case, "content.txt"), "-i", _g(case, "ref.fa.gz"), "--kH", str(K)] + (["--six"] if six else [])
+    rc, out, err = _cli(*args)
+    assert rc == 0, err
+    got = [(l.split(b"\t")[1], int(l.split(b"\t")[0])) for l in out.split(b"\n") if l]
+    want = [(s, t) for s, t in O.fasta_build_strings(G.gz(case, "ref.fa.gz"), G.acc2tax(case), K, six) if s]
+    assert got == want
+
+
+def test_read_parsing_fastq_fasta_gz(tmp_path):
+    rc, out, err = _cli("host-reads", "-i", _g("k12", "reads.fq.gz"))
+    assert rc == 0, err
+    got = [l.split(b"\t") for l in out.split(b"\n") if l]
+    want = G.fastq("k12")
+    assert [(g[0], g[2]) for g in got] == [(n, s) for n, s in want if True]
+    assert all(g[1] == b"1" for g in got)
+    # multi-line FASTA, CRLF, lower case and an empty record
+    fa = tmp_path / "r.fa"
+    fa.write_bytes(b">a desc\r\nACGT\r\nacgtn\r\n>b\n>c\nTTTT\nGG\nA\n")
+    rc, out, err = _cli("host-reads", "-i", str(fa))
+    assert rc == 0, err
+    got = [l.split(b"\t") for l in out.split(b"\n") if l]
+    assert [(g[0], g[1], g[2]) for g in got] == [(b"a desc", b"2", b"ACGTacgtn"), (b"b", b"0", b""), (b"c", b"3", b"TTTTGGA")]
+
+
+def test_cli_errors():
+    rc, _, err = _cli("identify", "-c", "/nonexistent", "-d", "/nonexistent", "-i", "/nonexistent")
+    assert rc == 1 and b"ERROR" in err
+    rc, _, err = _cli("shrink")
+    assert rc == 1 and b"not supported" in err
+
+
+# ------------------------------------------------------------------------------------------- through the GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,flags", [("k12", []), ("k12_build6", ["--six"]), ("k25", ["--kH", "25"])])
+def test_cli_build_files_byte_identical(case, flags, tmp_path):
+    idx = str(tmp_path / "idx")
+    rc, out, err = _cli("build", "-c", _g(case, "content.txt"), "-d", idx, "-i", _g(case, "ref.fa.gz"), "-m", "4", "-n", "1", *flags)
+    assert rc == 0, err
+    info = open(idx + "_info.txt").read()
+    assert info == G.text(case, "idx_info.txt")
+    n = int(info.split()[0])
+    rec = 20 if "128" in info.split()[1:] else 12
+    data = open(idx, "rb").read()
+    assert data[:n * rec] == G.gz(case, "idx.gz")
+    assert len(data) % (2048000 if rec == 20 else 2101248) == 0 and not any(data[n * rec:])
+    assert open(idx + "_trie.txt").read() == G.text(case, "idx_trie.txt")
+    nt = int(G.text(case, "idx_trie.txt").split()[0])
+    assert open(idx + "_trie", "rb").read()[:nt * 12] == G.gz(case, "idx_trie.gz")
+    assert open(idx + "_f.txt").read() == G.text(case, "idx_f.txt")
+
+
+def _write_index(case, tmp_path):
+    """golden index files laid out the way `identify -d` expects them."""
+    idx = str(tmp_path / "idx")
+    open(idx, "wb").write(G.gz(case, "idx.gz"))
+    for suf in ("_info.txt", "_f.txt", "_trie.txt"):
+        open(idx + suf, "w").write(G.text(case, "idx" + suf))
+    open(idx + "_trie", "wb").write(G.gz(case, "idx_trie.gz"))
+    return idx
+
+
+def _check_profile(path, case, tag):
+    want = G.text(case, tag + ".csv").splitlines()
+    got = open(path).read().splitlines()
+    assert got[0] == want[0]
+    assert [l.split(",")[:2] for l in got] == [l.split(",")[:2] for l in want]      # same taxa, same order
+    for lg, lw in zip(got[1:], want[1:]):
+        a = np.array(lg.split(",")[2:], dtype=np.float64)
+        b = np.array(lw.split(",")[2:], dtype=np.float64)
+        np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-12)                       # printed with 6 significant digits
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,tag,flags", [
+    ("k12", "six_12_7", ["--six"]),
+    ("k12", "three_11_8", ["-k", "11", "8"]),
+    ("k12", "six_12_12", ["--six", "-k", "12", "12"]),
+    ("k25", "six_25_7", ["--six", "-k", "25", "7"]),
+])
+def test_cli_identify_matches_reference_outputs(case, tag, flags, tmp_path):
+    idx = _write_index(case, tmp_path)
+    inp = ["-1", _g(case, "reads_1.fq.gz"), "-2", _g(case, "reads_2.fq.gz")] if case == "k25" else ["-i", _g(case, "reads.fq.gz")]
+    prof, rtt = str(tmp_path / "p.csv"), str(tmp_path / "q.jsonl")
+    rc, out, err = _cli("identify", "-c", _g(case, "content.txt"), "-d", idx, *inp, "-p", prof, "-q", rtt, "--jsonl", "-b", "100000",
+                        "-v", "--exact-scores", "--batch-reads", "128", *flags)
+    assert rc == 0, err
+    assert ("Number of k-mers in input: %d " % G.n_kmers(case, tag)).encode() in out
+    _check_profile(prof, case, tag)
+    want = [json.loads(l) for l in G.gz(case, tag + ".jsonl.gz").decode().splitlines()]
+    got = [json.loads(l) for l in open(rtt).read().splitlines()]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g == w, (g, w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["json", "tsv", "kraken"])
+def test_cli_other_formats_consistent_with_jsonl(fmt, tmp_path):
+    """default -b 3: the json / tsv / kraken writers list the same taxa and scores as the jsonl writer."""
+    case, tag = "k12", "six_12_7"
+    idx = _write_index(case, tmp_path)
+    base = ["identify", "-c", _g(case, "content.txt"), "-d", idx, "-i", _g(case, "reads.fq.gz"), "--six", "--exact-scores"]
+    rc, _, err = _cli(*base, "-q", str(tmp_path / "a.jsonl"), "--jsonl")
+    assert rc == 0, err
+    rc, _, err = _cli(*base, "-q", str(tmp_path / "b.out"), "--" + fmt)
+    assert rc == 0, err
+    ref = [json.loads(l) for l in open(tmp_path / "a.jsonl").read().splitlines()]
+    text = open(tmp_path / "b.out").read()
+    if fmt == "json":
+        got = json.loads(text)
+        assert got == ref
+    elif fmt == "tsv":
+        rows = [l.split("\t") for l in text.splitlines()[1:]]
+        assert len(rows) == len(ref)
+        for r, j in zip(rows, ref):
+            hits = j["Top hits"] + j["Further hits"]
+            assert int(r[0]) == j["Read number"] and r[1] == j["Specifier from input file"]
+            if not hits:
+                assert r[2:] == ["-", "-", "-", "-"]
+                continue
+            assert r[2].split(";") == [h["tax ID"] for h in hits]
+            assert [float(x.split(",")[1]) for x in r[4].split(";")] == [h["k-mer Score"] for h in hits]
+    else:
+        rows = [l.split("\t") for l in text.splitlines()]
+        assert len(rows) == len(ref)
+        for r, j in zip(rows, ref):
+            hits = j["Top hits"] + j["Further hits"]
+            assert r[0] == ("C" if hits else "U")
+            if hits:
+                assert r[2] == hits[0]["tax ID"] and int(r[3]) == j["Length"]
+                assert [x.split(":")[0] for x in r[4].split()] == [h["tax ID"] for h in hits]
