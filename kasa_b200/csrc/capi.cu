@@ -24,6 +24,7 @@ struct kasa_ctx {
     bool own_stream = false;
     uint64_t launches = 0;
     int K = 12, num_k = 6, hb = 3;
+    int sort_bits = 0;                  // leading k-mer bits identify sorts (tuning knob KASA_TUNE_SORT_BITS)
     bool wide = false;
     std::vector<void *> allocs;
 
@@ -326,6 +327,8 @@ int kasa_ctx_create(const kasa_params *p, kasa_ctx **out)
         c->wide = p->highest_k > 12;
         c->num_k = p->k_high - p->k_low + 1;
         c->hb = record_level_bits(c->num_k);
+        c->sort_bits = kIdentifySortBits;
+        if (const char *e = getenv("KASA_TUNE_SORT_BITS")) c->sort_bits = std::min(5 * c->K, std::max(8, atoi(e)));
         KASA_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
         KASA_CUDA_TRY(cudaEventCreate(&c->ev0));
@@ -508,7 +511,7 @@ int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resul
     // identify orders the k-mers on their leading kIdentifySortBits only (lookup.cuh: launch_partition); the exact
     // score mode needs the reference's complete order (its flush points are positions in the sorted array)
     const bool exact = c->p.score_mode == KASA_SCORE_EXACT;
-    const int sorted_from = exact ? 0 : std::max(0, 5 * c->K - kIdentifySortBits);
+    const int sorted_from = exact ? 0 : std::max(0, 5 * c->K - c->sort_bits);
     SortPlan plan = plan_for_bit_range(sorted_from, 5 * c->K);
     KASA_CUDA_TRY(cudaEventRecord(c->sev[2], c->stream));
     if (n) {
