@@ -113,17 +113,28 @@ __device__ __forceinline__ int64_t lower_bound(const Acc &acc, int64_t lo, int64
     return lo + (key_lt<W>(acc.template key<W>(lo), q) ? 1 : 0);
 }
 
-// 3-bit records: bit f of the result is set iff field f (bits 3f..3f+2) of w is non-zero, i.e. the taxon matched at
-// k_low.  Stride-3 bit compression in five mask-and-shift steps.
-__device__ __forceinline__ uint64_t dense_taxa_mask(uint64_t w)
+// 3-bit records: |taxa_j| for the levels j = 0..6 (j = 0 is k_low), one byte each, from the three field words: a taxon
+// with field h is in taxa_j for every j < h.  Bit-plane logic on the 21 fields of a word at once, then popcounts.
+// Stored as the fourth word of the record, it saves the per-read kernel a pass over the fields.
+__device__ __forceinline__ uint64_t level_sizes3(uint64_t r0, uint64_t r1, uint64_t r2)
 {
-    uint64_t x = (w | (w >> 1) | (w >> 2)) & 0x1249249249249249ull;
-    x = (x | (x >> 2)) & 0x10c30c30c30c30c3ull;
-    x = (x | (x >> 4)) & 0x100f00f00f00f00full;
-    x = (x | (x >> 8)) & 0x001f0000ff0000ffull;
-    x = (x | (x >> 16)) & 0x001f00000000ffffull;
-    x = (x | (x >> 32)) & 0x00000000001fffffull;
-    return x;
+    constexpr uint64_t L = 0x1249249249249249ull;
+    uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0, n4 = 0, n5 = 0, n6 = 0;
+    const uint64_t w[3] = {r0, r1, r2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const uint64_t b0 = w[i] & L, b1 = (w[i] >> 1) & L, b2 = (w[i] >> 2) & L;
+        const uint64_t any01 = b0 | b1, both01 = b0 & b1;
+        n0 += __popcll(any01 | b2);      // h >= 1
+        n1 += __popcll(b1 | b2);         // h >= 2
+        n2 += __popcll(b2 | both01);     // h >= 3
+        n3 += __popcll(b2);              // h >= 4
+        n4 += __popcll(b2 & any01);      // h >= 5
+        n5 += __popcll(b2 & b1);         // h >= 6
+        n6 += __popcll(b2 & both01);     // h == 7
+    }
+    return (uint64_t)n0 | ((uint64_t)n1 << 8) | ((uint64_t)n2 << 16) | ((uint64_t)n3 << 24) | ((uint64_t)n4 << 32) |
+           ((uint64_t)n5 << 40) | ((uint64_t)n6 << 48);
 }
 
 // R points at this thread's record column in shared memory: word wi lives at R[wi * kLookupBlock]
@@ -242,7 +253,7 @@ __global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint64_t *__
         if (live[r]) {
             const uint64_t r0 = R[0], r1 = R[kLookupBlock], r2 = R[2 * kLookupBlock];
             uint64_t r3 = R[3 * kLookupBlock];
-            if (HB == 3) r3 = dense_taxa_mask(r0) | (dense_taxa_mask(r1) << 21) | (dense_taxa_mask(r2) << 42);
+            if (HB == 3) r3 = level_sizes3(r0, r1, r2);
             uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)iv[r] * kRecWords);
             dst[0] = make_uint4((uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32));
             dst[1] = make_uint4((uint32_t)r2, (uint32_t)(r2 >> 32), (uint32_t)r3, (uint32_t)(r3 >> 32));
