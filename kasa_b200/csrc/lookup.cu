@@ -114,27 +114,28 @@ __device__ __forceinline__ int64_t lower_bound(const Acc &acc, int64_t lo, int64
 }
 
 // 3-bit records: |taxa_j| for the levels j = 0..6 (j = 0 is k_low), one byte each, from the three field words: a taxon
-// with field h is in taxa_j for every j < h.  Bit-plane logic on the 21 fields of a word at once, then popcounts.
-// Stored as the fourth word of the record, it saves the per-read kernel a pass over the fields.
+// with field h is in taxa_j for every j < h.  Level 0 is a popcount of the non-zero fields; the few taxa matched above
+// k_low (fields >= 2) are walked one by one.  Stored as the fourth word of the record, it saves the per-read kernel
+// a pass over the fields.
 __device__ __forceinline__ uint64_t level_sizes3(uint64_t r0, uint64_t r1, uint64_t r2)
 {
     constexpr uint64_t L = 0x1249249249249249ull;
-    uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0, n4 = 0, n5 = 0, n6 = 0;
+    constexpr uint64_t kOnes = 0x0001010101010100ull;       // one per level 1..6
     const uint64_t w[3] = {r0, r1, r2};
+    uint64_t np = 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const uint64_t b0 = w[i] & L, b1 = (w[i] >> 1) & L, b2 = (w[i] >> 2) & L;
-        const uint64_t any01 = b0 | b1, both01 = b0 & b1;
-        n0 += __popcll(any01 | b2);      // h >= 1
-        n1 += __popcll(b1 | b2);         // h >= 2
-        n2 += __popcll(b2 | both01);     // h >= 3
-        n3 += __popcll(b2);              // h >= 4
-        n4 += __popcll(b2 & any01);      // h >= 5
-        n5 += __popcll(b2 & b1);         // h >= 6
-        n6 += __popcll(b2 & both01);     // h == 7
+        const uint64_t hi = ((w[i] >> 1) | (w[i] >> 2)) & L;            // fields >= 2
+        np += (uint32_t)__popcll((w[i] & L) | hi);                      // fields >= 1
+        uint64_t m = hi;
+        while (m) {
+            const int p = __ffsll((long long)m) - 1;                    // = 3f
+            const uint32_t h = (uint32_t)(w[i] >> p) & 7u;
+            m &= m - 1;
+            np += kOnes & ((1ull << (8 * h)) - 1);                      // levels 1 .. h-1
+        }
     }
-    return (uint64_t)n0 | ((uint64_t)n1 << 8) | ((uint64_t)n2 << 16) | ((uint64_t)n3 << 24) | ((uint64_t)n4 << 32) |
-           ((uint64_t)n5 << 40) | ((uint64_t)n6 << 48);
+    return np;
 }
 
 // R points at this thread's record column in shared memory: word wi lives at R[wi * kLookupBlock]
@@ -196,6 +197,71 @@ __global__ void __launch_bounds__(256) partition_kernel(const uint64_t *__restri
 
 constexpr int kSpanCap = 2560;   // index entries staged per tile (the tile size is chosen so that the average span is <= half of it)
 
+// last level (as a k) not killed by a '^' letter at positions k_low..k_high, or k_low - 1 (Compare.hpp:836, 897)
+template <bool W>
+__device__ __forceinline__ int last_valid_level(const Key &q, const LevelParams &lp)
+{
+    if (!W) {
+        // exact zero-field test on q ^ ('^' in every field): bit 4 of a 5-bit field is set iff the letter is '^'
+        constexpr uint64_t M = 0x07bdef7bdef7bdefull, H = 0x0842108421084210ull;      // 01111 / 10000 in 12 fields
+        const uint64_t y = q.lo ^ (M << 1);                                             // 11110 = '^'
+        uint64_t z = ~(((y & M) + M) | y) & H;
+        const int top = 5 * (lp.K - lp.k_low) + 5, bot = 5 * (lp.K - lp.k_high);         // fields k_low .. k_high
+        z &= (top >= 64 ? ~0ull : (1ull << top) - 1) & ~((1ull << bot) - 1);
+        if (!z) return lp.k_high;
+        const int p = 63 - __clzll((long long)z);                                       // = 5 (K - k) + 4
+        return lp.K - (((p - 4) * 205) >> 10) - 1;
+    }
+    int kv = lp.k_low - 1;
+    for (int k = lp.k_low; k <= lp.k_high; ++k) {
+        if (letter_at<W>(q, k, lp.K) == kLetterCaret) break;
+        kv = k;
+    }
+    return kv;
+}
+
+// staged slot code of a taxon: record word and bit offset of its field, ready for addressing
+template <int HB>
+__device__ __forceinline__ uint16_t slot_code(uint32_t taxon)
+{
+    constexpr int FPW = 64 / HB;
+    const uint32_t sl = taxon - 1;
+    return (uint16_t)(((sl / FPW) << 6) | ((sl % FPW) * HB));
+}
+
+template <int HB>
+__device__ __forceinline__ void rec_update_code(uint64_t *R, uint32_t code, uint32_t h)
+{
+    constexpr uint64_t HM = (1ull << HB) - 1;
+    uint64_t *p = R + (code >> 6) * kLookupBlock;
+    const int sh = code & 63;
+    const uint64_t w = *p;
+    const uint32_t cur = (uint32_t)(w >> sh) & (uint32_t)HM;
+    if (h > cur) *p = w + ((uint64_t)(h - cur) << sh);
+}
+
+// One index entry of the staged span against one query: false = it does not share k_low letters (end of the scan)
+template <bool W, int HB>
+__device__ __forceinline__ bool match_entry(uint64_t e_lo, uint64_t e_hi, uint32_t code, const Key &q, int kv, const LevelParams &lp,
+                                            uint64_t *R)
+{
+    const int low_sh = 5 * (lp.K - lp.k_low);
+    int lead;
+    if (W) {
+        const uint64_t xh = e_hi ^ q.hi, xl = e_lo ^ q.lo;
+        const bool differs = low_sh >= 64 ? (xh >> (low_sh - 64)) != 0 : (xh != 0 || (xl >> low_sh) != 0);
+        if (differs) return false;
+        lead = xh ? __clzll((long long)xh) - (128 - 5 * lp.K) : (xl ? (5 * lp.K - 64) + __clzll((long long)xl) : 5 * lp.K);
+    } else {
+        const uint64_t x = e_lo ^ q.lo;
+        if (x >> low_sh) return false;
+        lead = x ? __clzll((long long)x) - (64 - 5 * lp.K) : 5 * lp.K;
+    }
+    const int c = (lead * 205) >> 10;                                    // lead / 5 for lead <= 125
+    rec_update_code<HB>(R, code, (uint32_t)(min(c, kv) - lp.k_low + 1));
+    return true;
+}
+
 template <bool W, int HB>
 __global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
                                                               const uint32_t *__restrict__ inst, uint64_t n, IndexDev idx,
@@ -206,7 +272,7 @@ __global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint64_t *__
     uint64_t *s_rec = reinterpret_cast<uint64_t *>(smem_raw);                 // [kRecWords][kLookupBlock]
     uint64_t *s_klo = s_rec + kRecWords * kLookupBlock;
     uint64_t *s_khi = s_klo + (W ? kSpanCap : 0);
-    uint16_t *s_tax = reinterpret_cast<uint16_t *>(s_khi + kSpanCap);
+    uint16_t *s_code = reinterpret_cast<uint16_t *>(s_khi + kSpanCap);         // slot codes of the entries' taxa
 
     const uint64_t tile = blockIdx.x;
     const uint64_t q0 = tile * tq;
@@ -225,28 +291,54 @@ __global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint64_t *__
         iv[r] = live[r] ? ldg_stream(inst + i) : 0u;
     }
     const int64_t a = (int64_t)part[2 * tile], b = (int64_t)part[2 * tile + 1];
-    const int64_t span = b - a;
+    const int span = (int)min((int64_t)(kSpanCap + 1), b - a);
     const bool staged = span <= kSpanCap;
     if (staged) {
-        for (int64_t j = threadIdx.x; j < span; j += kLookupBlock) {
+        for (int j = threadIdx.x; j < span; j += kLookupBlock) {
             s_klo[j] = ldg_stream(idx.key_lo + a + j);
             if (W) s_khi[j] = ldg_stream(idx.key_hi + a + j);
-            s_tax[j] = idx.tax[a + j];
+            s_code[j] = slot_code<HB>(idx.tax[a + j]);
         }
     }
     __syncthreads();
-    SmemAcc sacc{s_klo, s_khi, s_tax, a};
-    GmemAcc gacc{idx.key_lo, idx.key_hi, idx.tax};
     uint64_t *R = s_rec + threadIdx.x;
+
+    // ---- staged span (the rule): the QPT binary searches of a thread run in lockstep — independent chains of
+    // shared-memory loads — with 32-bit positions inside the span; the trip count is uniform across the CTA
+    int pos[QPT], kv[QPT];
+    if (staged && span > 0) {
+#pragma unroll
+        for (int r = 0; r < QPT; ++r) { pos[r] = 0; kv[r] = live[r] ? last_valid_level<W>(qv[r], lp) : 0; }
+        int nn = span;
+        while (nn > 1) {
+            const int half = nn >> 1;
+#pragma unroll
+            for (int r = 0; r < QPT; ++r) {
+                const int m = pos[r] + half - 1;
+                if (key_lt<W>(Key{s_klo[m], W ? s_khi[m] : 0ull}, qv[r])) pos[r] += half;
+            }
+            nn -= half;
+        }
+#pragma unroll
+        for (int r = 0; r < QPT; ++r)
+            if (key_lt<W>(Key{s_klo[pos[r]], W ? s_khi[pos[r]] : 0ull}, qv[r])) ++pos[r];
+    }
+    GmemAcc gacc{idx.key_lo, idx.key_hi, idx.tax};
 #pragma unroll
     for (int r = 0; r < QPT; ++r) {
         if (r * kLookupBlock >= (int)tq) break;             // CTA-uniform
         if (live[r]) {
 #pragma unroll
             for (int wi = 0; wi < kRecWords; ++wi) R[wi * kLookupBlock] = 0;
-            if (span > 0) {
-                if (staged) match_query<W, HB>(sacc, a, b, qv[r], lp, R);
-                else match_query<W, HB>(gacc, a, b, qv[r], lp, R);
+            if (staged) {
+                if (span > 0 && kv[r] >= lp.k_low) {
+                    for (int e = pos[r]; e < span; ++e)
+                        if (!match_entry<W, HB>(s_klo[e], W ? s_khi[e] : 0ull, s_code[e], qv[r], kv[r], lp, R)) break;
+                    for (int e = pos[r] - 1; e >= 0; --e)
+                        if (!match_entry<W, HB>(s_klo[e], W ? s_khi[e] : 0ull, s_code[e], qv[r], kv[r], lp, R)) break;
+                }
+            } else {
+                match_query<W, HB>(gacc, a, b, qv[r], lp, R);   // oversized span: search the index in place
             }
         }
         __syncwarp();                                        // reconverge after the data-dependent scans

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kRadix) hist_scan_kernel(unsigned long long *g
 // registers -> 2 CTAs = 32 warps per SM; 52 KB dynamic shared memory per CTA.  The kernel is latency
 // bound per tile (rank chain + look-back), so resident warps are what buys bandwidth.
 template <int BLOCK, int ITEMS, bool HAS_W1>
-__global__ void __launch_bounds__(BLOCK, 2) onesweep_kernel(
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
     const uint64_t *__restrict__ in_w0, const uint64_t *__restrict__ in_w1, const uint32_t *__restrict__ in_v,
     uint64_t *__restrict__ out_w0, uint64_t *__restrict__ out_w1, uint32_t *__restrict__ out_v, uint64_t n, int src,
     int shift, uint32_t mask, const unsigned long long *__restrict__ digit_start, uint64_t *status,

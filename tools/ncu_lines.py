@@ -30,4 +30,4 @@ te = sum(v[0] for v in agg.values()); ts = sum(v[1] for v in agg.values())
 src = open(os.path.join(os.path.dirname(os.path.abspath(obj)), "..", os.path.basename(obj).replace(".o", ".cu"))).read().splitlines()
 print("total warp instr %d, samples %d" % (te, ts))
 for ln, v in sorted(agg.items(), key=lambda x: -x[1][1])[:top]:
-    print("%5.1f%% samp %5.1f%% instr thr=%4.1f  L%-4s %s" % (100 * v[1] / ts, 100 * v[0] / te, v[2] / max(1, v[0]), ln, src[ln - 1].strip()[:95] if ln else ""))
+    print("%5.1f%% samp %5.1f%% instr thr=%4.1f  L%-4s %s" % (100 * v[1] / ts, 100 * v[0] / te, v[2] / max(1, v[0]), ln, (src[ln - 1].strip()[:95] if ln and ln <= len(src) else "")))
