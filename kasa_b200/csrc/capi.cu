@@ -406,14 +406,15 @@ int kasa_index_load(kasa_ctx *c, const void *entries, uint64_t n, int bits, cons
     const size_t words_per = c->wide ? 5 : 3;
     uint32_t *d_words = dev_alloc<uint32_t>(c, n * words_per + 1);
     uint32_t *d_tax32 = dev_alloc<uint32_t>(c, n + 1);
-    c->idx_lo = dev_alloc<uint64_t>(c, n + 1);
-    c->idx_hi = c->wide ? dev_alloc<uint64_t>(c, n + 1) : nullptr;
-    c->idx_tax = dev_alloc<uint16_t>(c, n + 1);
+    c->idx_lo = dev_alloc<uint64_t>(c, n + 16);
+    c->idx_hi = c->wide ? dev_alloc<uint64_t>(c, n + 16) : nullptr;
+    c->idx_tax = dev_alloc<uint16_t>(c, n + 16);
     KASA_CUDA_TRY(cudaMemcpyAsync(d_words, entries, n * words_per * 4, cudaMemcpyHostToDevice, c->stream));
     launch_unpack_records(c->stream, d_words, n, c->wide, c->idx_lo, c->idx_hi, d_tax32, &c->launches);
     launch_check_sorted(c->stream, c->idx_lo, c->idx_hi, d_tax32, n, c->d_err, &c->launches);
     TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
     launch_map_taxids(c->stream, d_tax32, n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
+    launch_slot_codes(c->stream, c->idx_tax, n, c->hb, &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     check_device_flags(c);
     dev_free(c, d_words); dev_free(c, d_tax32); dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
@@ -431,13 +432,14 @@ int kasa_index_from_build(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_
     set_taxa(c, n_taxa);
     const uint64_t n = c->build_fill;
     const int b = c->build_buf;
-    c->idx_lo = dev_alloc<uint64_t>(c, n + 1);
-    c->idx_hi = c->wide ? dev_alloc<uint64_t>(c, n + 1) : nullptr;
-    c->idx_tax = dev_alloc<uint16_t>(c, n + 1);
+    c->idx_lo = dev_alloc<uint64_t>(c, n + 16);
+    c->idx_hi = c->wide ? dev_alloc<uint64_t>(c, n + 16) : nullptr;
+    c->idx_tax = dev_alloc<uint16_t>(c, n + 16);
     KASA_CUDA_TRY(cudaMemcpyAsync(c->idx_lo, c->sb.w0[b], n * 8, cudaMemcpyDeviceToDevice, c->stream));
     if (c->wide) KASA_CUDA_TRY(cudaMemcpyAsync(c->idx_hi, c->sb.w1[b], n * 8, cudaMemcpyDeviceToDevice, c->stream));
     TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
     launch_map_taxids(c->stream, c->sb.v[b], n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
+    launch_slot_codes(c->stream, c->idx_tax, n, c->hb, &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     check_device_flags(c);
     dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);

@@ -138,64 +138,75 @@ __device__ __forceinline__ uint64_t level_sizes3(uint64_t r0, uint64_t r1, uint6
     return np;
 }
 
-// R points at this thread's record column in shared memory: word wi lives at R[wi * kLookupBlock]
+// record held in registers: raise the level field of a taxon (given by its slot code, see slot_code) to h
 template <int HB>
-__device__ __forceinline__ void rec_update(uint64_t *R, int slot, uint32_t h)
+__device__ __forceinline__ void rec_raise(uint64_t (&rw)[kRecWords], uint32_t code, uint32_t h)
 {
-    constexpr int FPW = 64 / HB;
     constexpr uint64_t HM = (1ull << HB) - 1;
-    const int wi = slot / FPW, sh = (slot % FPW) * HB;
-    uint64_t w = R[wi * kLookupBlock];
-    uint32_t cur = (uint32_t)(w >> sh) & (uint32_t)HM;
-    if (h > cur) R[wi * kLookupBlock] = w + ((uint64_t)(h - cur) << sh);
-}
-
-// Set semantics of Compare.hpp:785-1041 for one query instance: every index entry whose first c >= k_low
-// letters equal the query's belongs to taxa_k(prefix_k(q)) for k = k_low .. min(c, kv), where kv is the last
-// level not killed by a '^' letter (Compare.hpp:836, 897).
-template <bool W, int HB, class Acc>
-__device__ __forceinline__ void match_query(const Acc &acc, int64_t a, int64_t b, const Key &q, const LevelParams &lp,
-                                            uint64_t *R)
-{
-    int kv = lp.k_low - 1;
-    for (int k = lp.k_low; k <= lp.k_high; ++k) {
-        if (letter_at<W>(q, k, lp.K) == kLetterCaret) break;
-        kv = k;
-    }
-    if (kv < lp.k_low) return;
-    const int64_t pos = lower_bound<W>(acc, a, b, q);
-    for (int64_t e = pos; e < b; ++e) {
-        int c = common_letters<W>(acc.template key<W>(e), q, lp.K);
-        if (c < lp.k_low) break;
-        rec_update<HB>(R, (int)acc.taxon(e) - 1, (uint32_t)(min(c, kv) - lp.k_low + 1));
-    }
-    for (int64_t e = pos - 1; e >= a; --e) {
-        int c = common_letters<W>(acc.template key<W>(e), q, lp.K);
-        if (c < lp.k_low) break;
-        rec_update<HB>(R, (int)acc.taxon(e) - 1, (uint32_t)(min(c, kv) - lp.k_low + 1));
+    const uint32_t wi = code >> 6;
+    const int sh = code & 63;
+#pragma unroll
+    for (int i = 0; i < kRecWords; ++i) {
+        if (HB == 3 && i == 3) break;                 // 3-bit records keep their fields in three words
+        if ((uint32_t)i == wi) {
+            const uint32_t cur = (uint32_t)(rw[i] >> sh) & (uint32_t)HM;
+            if (h > cur) rw[i] += (uint64_t)(h - cur) << sh;
+        }
     }
 }
 
+// all bits >= sh equal, i.e. the first K - sh/5 letters agree
 template <bool W>
-__global__ void __launch_bounds__(256) partition_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
-                                                        uint64_t n, IndexDev idx, LevelParams lp, uint64_t *__restrict__ part,
-                                                        uint64_t n_tiles, uint32_t tq, int span_shift)
+__device__ __forceinline__ bool shares_prefix(const Key &a, const Key &b, int sh)
 {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tiles) return;
-    uint64_t i0 = t * tq, i1 = min(n, i0 + tq) - 1;
-    Key first{q_lo[i0], W ? q_hi[i0] : 0ull}, last{q_lo[i1], W ? q_hi[i1] : 0ull};
-    GmemAcc acc{idx.key_lo, idx.key_hi, idx.tax};
-    // queries are ordered on the bits above span_shift only; the span must hold every entry that shares the
-    // k_low-letter prefix with any query of the tile, which the coarser of the two prefixes guarantees
-    Key f = prefix_floor<W>(first, span_shift), c = prefix_ceil<W>(last, span_shift);
-    int64_t a = lower_bound<W>(acc, 0, (int64_t)idx.n, f);
-    int64_t b = lower_bound<W>(acc, a, (int64_t)idx.n, c);
-    part[2 * t] = (uint64_t)a;
-    part[2 * t + 1] = (uint64_t)b;
+    if (!W) return ((a.lo ^ b.lo) >> sh) == 0;
+    const uint64_t xh = a.hi ^ b.hi;
+    if (sh >= 64) return (xh >> (sh - 64)) == 0;
+    return xh == 0 && ((a.lo ^ b.lo) >> sh) == 0;
 }
 
-constexpr int kSpanCap = 2560;   // index entries staged per tile (the tile size is chosen so that the average span is <= half of it)
+// number of levels (from k_low up) at which an entry sharing >= k_low letters with q matches: min(common, kv) - k_low + 1
+template <bool W>
+__device__ __forceinline__ uint32_t match_levels(const Key &e, const Key &q, int kv, const LevelParams &lp)
+{
+    int lead;
+    if (W) {
+        const uint64_t xh = e.hi ^ q.hi, xl = e.lo ^ q.lo;
+        lead = xh ? __clzll((long long)xh) - (128 - 5 * lp.K) : (xl ? (5 * lp.K - 64) + __clzll((long long)xl) : 5 * lp.K);
+    } else {
+        const uint64_t x = e.lo ^ q.lo;
+        lead = x ? __clzll((long long)x) - (64 - 5 * lp.K) : 5 * lp.K;
+    }
+    const int c = (lead * 205) >> 10;                 // lead / 5 for lead <= 125
+    return (uint32_t)(min(c, kv) - lp.k_low + 1);
+}
+
+// bit i of x (i < 64 / HB) -> bit i * HB: a taxa bit mask becomes "level field = 1" for each of its taxa
+template <int HB>
+__device__ __forceinline__ uint64_t spread_fields(uint64_t x)
+{
+    if (HB == 3) {                                    // 21 bits, stride 3
+        x &= 0x1fffffull;
+        x = (x | (x << 32)) & 0x001f00000000ffffull;
+        x = (x | (x << 16)) & 0x001f0000ff0000ffull;
+        x = (x | (x << 8)) & 0x100f00f00f00f00full;
+        x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+        x = (x | (x << 2)) & 0x1249249249249249ull;
+        return x;
+    }
+    if (HB == 4) {                                    // 16 bits, stride 4
+        x &= 0xffffull;
+        x = (x | (x << 24)) & 0x000000ff000000ffull;
+        x = (x | (x << 12)) & 0x000f000f000f000full;
+        x = (x | (x << 6)) & 0x0303030303030303ull;
+        x = (x | (x << 3)) & 0x1111111111111111ull;
+        return x;
+    }
+    uint64_t r = 0;                                   // 12 bits, stride 5
+#pragma unroll
+    for (int i = 0; i < 12; ++i) r |= ((x >> i) & 1ull) << (5 * i);
+    return r;
+}
 
 // last level (as a k) not killed by a '^' letter at positions k_low..k_high, or k_low - 1 (Compare.hpp:836, 897)
 template <bool W>
@@ -220,7 +231,7 @@ __device__ __forceinline__ int last_valid_level(const Key &q, const LevelParams 
     return kv;
 }
 
-// staged slot code of a taxon: record word and bit offset of its field, ready for addressing
+// slot code of a taxon (1-based dense index): record word << 6 | bit offset of its level field
 template <int HB>
 __device__ __forceinline__ uint16_t slot_code(uint32_t taxon)
 {
@@ -228,128 +239,223 @@ __device__ __forceinline__ uint16_t slot_code(uint32_t taxon)
     const uint32_t sl = taxon - 1;
     return (uint16_t)(((sl / FPW) << 6) | ((sl % FPW) * HB));
 }
-
+// ... and back to the taxon's bit in a dense taxa mask (bit = taxon - 1)
 template <int HB>
-__device__ __forceinline__ void rec_update_code(uint64_t *R, uint32_t code, uint32_t h)
+__device__ __forceinline__ uint32_t code_to_bit(uint32_t code)
 {
-    constexpr uint64_t HM = (1ull << HB) - 1;
-    uint64_t *p = R + (code >> 6) * kLookupBlock;
-    const int sh = code & 63;
-    const uint64_t w = *p;
-    const uint32_t cur = (uint32_t)(w >> sh) & (uint32_t)HM;
-    if (h > cur) *p = w + ((uint64_t)(h - cur) << sh);
+    constexpr int FPW = 64 / HB;
+    return (code >> 6) * FPW + (code & 63u) / HB;
 }
 
-// One index entry of the staged span against one query: false = it does not share k_low letters (end of the scan)
+// Oversized span (rare): Set semantics of Compare.hpp:785-1041 for one query instance straight from the index in
+// HBM.  Every entry whose first c >= k_low letters equal the query's belongs to taxa_k(prefix_k(q)) for
+// k = k_low .. min(c, kv); those entries start at the lower bound of the query's k_low-letter prefix.
 template <bool W, int HB>
-__device__ __forceinline__ bool match_entry(uint64_t e_lo, uint64_t e_hi, uint32_t code, const Key &q, int kv, const LevelParams &lp,
-                                            uint64_t *R)
+__device__ __forceinline__ void match_query_gmem(const GmemAcc &acc, int64_t a, int64_t b, const Key &q, int kv,
+                                                 const LevelParams &lp, uint64_t (&rw)[kRecWords])
 {
     const int low_sh = 5 * (lp.K - lp.k_low);
-    int lead;
-    if (W) {
-        const uint64_t xh = e_hi ^ q.hi, xl = e_lo ^ q.lo;
-        const bool differs = low_sh >= 64 ? (xh >> (low_sh - 64)) != 0 : (xh != 0 || (xl >> low_sh) != 0);
-        if (differs) return false;
-        lead = xh ? __clzll((long long)xh) - (128 - 5 * lp.K) : (xl ? (5 * lp.K - 64) + __clzll((long long)xl) : 5 * lp.K);
-    } else {
-        const uint64_t x = e_lo ^ q.lo;
-        if (x >> low_sh) return false;
-        lead = x ? __clzll((long long)x) - (64 - 5 * lp.K) : 5 * lp.K;
+    for (int64_t e = lower_bound<W>(acc, a, b, prefix_floor<W>(q, low_sh)); e < b; ++e) {
+        const Key ek = acc.template key<W>(e);
+        if (!shares_prefix<W>(ek, q, low_sh)) break;
+        rec_raise<HB>(rw, acc.taxon(e), match_levels<W>(ek, q, kv, lp));
     }
-    const int c = (lead * 205) >> 10;                                    // lead / 5 for lead <= 125
-    rec_update_code<HB>(R, code, (uint32_t)(min(c, kv) - lp.k_low + 1));
-    return true;
 }
 
-template <bool W, int HB>
-__global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
-                                                              const uint32_t *__restrict__ inst, uint64_t n, IndexDev idx,
-                                                              LevelParams lp, const uint64_t *__restrict__ part,
-                                                              uint64_t *__restrict__ rec, uint32_t tq)
+template <bool W>
+__global__ void __launch_bounds__(256) partition_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
+                                                        uint64_t n, IndexDev idx, LevelParams lp, uint64_t *__restrict__ part,
+                                                        uint64_t n_tiles, uint32_t tq, int span_shift)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *s_rec = reinterpret_cast<uint64_t *>(smem_raw);                 // [kRecWords][kLookupBlock]
-    uint64_t *s_klo = s_rec + kRecWords * kLookupBlock;
-    uint64_t *s_khi = s_klo + (W ? kSpanCap : 0);
-    uint16_t *s_code = reinterpret_cast<uint16_t *>(s_khi + kSpanCap);         // slot codes of the entries' taxa
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    uint64_t i0 = t * tq, i1 = min(n, i0 + tq) - 1;
+    Key first{q_lo[i0], W ? q_hi[i0] : 0ull}, last{q_lo[i1], W ? q_hi[i1] : 0ull};
+    GmemAcc acc{idx.key_lo, idx.key_hi, idx.tax};
+    // queries are ordered on the bits above span_shift only; the span must hold every entry that shares the
+    // k_low-letter prefix with any query of the tile, which the coarser of the two prefixes guarantees
+    Key f = prefix_floor<W>(first, span_shift), c = prefix_ceil<W>(last, span_shift);
+    int64_t a = lower_bound<W>(acc, 0, (int64_t)idx.n, f);
+    int64_t b = lower_bound<W>(acc, a, (int64_t)idx.n, c);
+    part[2 * t] = (uint64_t)a;
+    part[2 * t + 1] = (uint64_t)b;
+}
 
-    const uint64_t tile = blockIdx.x;
-    const uint64_t q0 = tile * tq;
-    // this thread's queries and instance ids are requested first: their latency overlaps the span staging
+constexpr int kSpanCap = 2048;   // index entries staged per tile (the tile size is chosen so that the average span is <= half of it)
+
+// ---- TMA (bulk async copy) + mbarrier plumbing for the span staging
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// shared-memory stage of one tile's index span; bulk copies need 16-byte aligned addresses and sizes, so the
+// copies start at the aligned entry below the span and the arrays are padded
+constexpr int kKeyPad = 2, kCodePad = 16;
+
+template <bool W>
+struct SpanStage {
+    uint64_t klo[kSpanCap + kKeyPad];
+    uint64_t khi[W ? kSpanCap + kKeyPad : 2];
+    uint64_t gmask[kSpanCap];            // per entry: dense mask (bit = taxon - 1) of the taxa of its k_low-letter group
+    uint16_t code[kSpanCap + kCodePad];
+    uint64_t bar;                        // mbarrier of the bulk copies
+};
+
+// One CTA per tile of <= 1024 sorted queries.  The tile's index span (contiguous runs of the key and slot-code
+// arrays) arrives as TMA bulk copies on an mbarrier while the threads fetch their queries.  Then
+//   1. group pass: the entries of the span are cut into groups sharing their first k_low letters and every
+//      entry gets its group's taxa set as a 64-bit mask — computed once per tile instead of once per query;
+//   2. per query: one binary search (the QPT searches of a thread in lockstep: independent chains of LDS) for the
+//      first entry sharing k_low + 1 letters; the group mask of the entry found (or the one before) spreads
+//      into "level 1" fields; only the few entries sharing more than k_low letters are visited to raise fields;
+//   3. level sizes (fourth record word) and one 32-byte store to the instance's slot in emission order.
+// The record lives in registers throughout.
+template <bool W, int HB>
+__global__ void __launch_bounds__(kLookupBlock, W ? 3 : 5) lookup_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
+                                                                         const uint32_t *__restrict__ inst, uint64_t n, IndexDev idx,
+                                                                         LevelParams lp, const uint64_t *__restrict__ part,
+                                                                         uint64_t *__restrict__ rec, uint32_t tq)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SpanStage<W> &st = *reinterpret_cast<SpanStage<W> *>(smem_raw);
     constexpr int QPT = kLookupTile / kLookupBlock;
+    constexpr int FPW = 64 / HB;
+    const int tid = threadIdx.x;
+    const uint64_t tile = blockIdx.x;
+    const int64_t a = (int64_t)part[2 * tile], b = (int64_t)part[2 * tile + 1];
+    const bool staged = b - a <= kSpanCap;
+    const int span = staged ? (int)(b - a) : 0;
+    const int64_t ak = a & ~(int64_t)1, ac = a & ~(int64_t)7;
+    if (tid == 0 && span > 0) {
+        mbar_init(&st.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t kb = (uint32_t)(((b - ak) + 1) & ~(int64_t)1) * 8u, cb = (uint32_t)(((b - ac) + 7) & ~(int64_t)7) * 2u;
+        mbar_expect_tx(&st.bar, kb * (W ? 2u : 1u) + cb);
+        bulk_g2s(st.klo, idx.key_lo + ak, kb, &st.bar);
+        if (W) bulk_g2s(st.khi, idx.key_hi + ak, kb, &st.bar);
+        bulk_g2s(st.code, idx.tax + ac, cb, &st.bar);
+    }
+    // this thread's queries and instance ids: their latency overlaps the span staging
     Key qv[QPT];
     uint32_t iv[QPT];
     bool live[QPT];
 #pragma unroll
     for (int r = 0; r < QPT; ++r) {
-        const uint32_t off = r * kLookupBlock + threadIdx.x;
-        const uint64_t i = q0 + off;
+        const uint32_t off = r * kLookupBlock + tid;
+        const uint64_t i = tile * tq + off;
         live[r] = off < tq && i < n;
         qv[r].lo = live[r] ? ldg_stream(q_lo + i) : 0ull;
         qv[r].hi = (W && live[r]) ? ldg_stream(q_hi + i) : 0ull;
         iv[r] = live[r] ? ldg_stream(inst + i) : 0u;
     }
-    const int64_t a = (int64_t)part[2 * tile], b = (int64_t)part[2 * tile + 1];
-    const int span = (int)min((int64_t)(kSpanCap + 1), b - a);
-    const bool staged = span <= kSpanCap;
-    if (staged) {
-        for (int j = threadIdx.x; j < span; j += kLookupBlock) {
-            s_klo[j] = ldg_stream(idx.key_lo + a + j);
-            if (W) s_khi[j] = ldg_stream(idx.key_hi + a + j);
-            s_code[j] = slot_code<HB>(idx.tax[a + j]);
+    __syncthreads();                                          // the barrier word is initialised
+    const uint64_t *s_klo = st.klo + (a - ak);
+    const uint64_t *s_khi = st.khi + (W ? (a - ak) : 0);
+    const uint16_t *s_code = st.code + (a - ac);
+    const int low_sh = 5 * (lp.K - lp.k_low);                 // bits below the first k_low letters
+    const int up_sh = lp.k_low < lp.K ? low_sh - 5 : 0;       // ... below the first k_low + 1 letters
+    auto skey = [&](int e) { return Key{s_klo[e], W ? s_khi[e] : 0ull}; };
+
+    if (span > 0) {
+        mbar_wait(&st.bar, 0);
+        // ---- 1. group pass
+        for (int j = tid; j < span; j += kLookupBlock) {
+            const Key kj = skey(j);
+            if (j > 0 && shares_prefix<W>(skey(j - 1), kj, low_sh)) continue;       // not the first entry of its group
+            uint64_t m = 0;
+            int e = j;
+            do { m |= 1ull << code_to_bit<HB>(s_code[e]); ++e; } while (e < span && shares_prefix<W>(skey(e), kj, low_sh));
+            for (int x = j; x < e; ++x) st.gmask[x] = m;
         }
     }
     __syncthreads();
-    uint64_t *R = s_rec + threadIdx.x;
 
-    // ---- staged span (the rule): the QPT binary searches of a thread run in lockstep — independent chains of
-    // shared-memory loads — with 32-bit positions inside the span; the trip count is uniform across the CTA
+    // ---- 2. lockstep binary searches for the first entry >= the query's (k_low + 1)-letter prefix
     int pos[QPT], kv[QPT];
-    if (staged && span > 0) {
 #pragma unroll
-        for (int r = 0; r < QPT; ++r) { pos[r] = 0; kv[r] = live[r] ? last_valid_level<W>(qv[r], lp) : 0; }
+    for (int r = 0; r < QPT; ++r) { pos[r] = 0; kv[r] = live[r] ? last_valid_level<W>(qv[r], lp) : 0; }
+    if (span > 0) {
+        Key fl[QPT];
+#pragma unroll
+        for (int r = 0; r < QPT; ++r) fl[r] = prefix_floor<W>(qv[r], up_sh);
         int nn = span;
         while (nn > 1) {
             const int half = nn >> 1;
 #pragma unroll
-            for (int r = 0; r < QPT; ++r) {
-                const int m = pos[r] + half - 1;
-                if (key_lt<W>(Key{s_klo[m], W ? s_khi[m] : 0ull}, qv[r])) pos[r] += half;
-            }
+            for (int r = 0; r < QPT; ++r)
+                if (key_lt<W>(skey(pos[r] + half - 1), fl[r])) pos[r] += half;
             nn -= half;
         }
 #pragma unroll
         for (int r = 0; r < QPT; ++r)
-            if (key_lt<W>(Key{s_klo[pos[r]], W ? s_khi[pos[r]] : 0ull}, qv[r])) ++pos[r];
+            if (key_lt<W>(skey(pos[r]), fl[r])) ++pos[r];
     }
     GmemAcc gacc{idx.key_lo, idx.key_hi, idx.tax};
 #pragma unroll
     for (int r = 0; r < QPT; ++r) {
         if (r * kLookupBlock >= (int)tq) break;             // CTA-uniform
-        if (live[r]) {
-#pragma unroll
-            for (int wi = 0; wi < kRecWords; ++wi) R[wi * kLookupBlock] = 0;
+        if (!live[r]) continue;
+        uint64_t rw[kRecWords] = {0, 0, 0, 0};
+        if (kv[r] >= lp.k_low) {
             if (staged) {
-                if (span > 0 && kv[r] >= lp.k_low) {
-                    for (int e = pos[r]; e < span; ++e)
-                        if (!match_entry<W, HB>(s_klo[e], W ? s_khi[e] : 0ull, s_code[e], qv[r], kv[r], lp, R)) break;
-                    for (int e = pos[r] - 1; e >= 0; --e)
-                        if (!match_entry<W, HB>(s_klo[e], W ? s_khi[e] : 0ull, s_code[e], qv[r], kv[r], lp, R)) break;
+                // the query's group, if the index has it, holds the entry at pos or the one before
+                int g = -1;
+                if (pos[r] < span && shares_prefix<W>(skey(pos[r]), qv[r], low_sh)) g = pos[r];
+                else if (pos[r] > 0 && shares_prefix<W>(skey(pos[r] - 1), qv[r], low_sh)) g = pos[r] - 1;
+                if (g >= 0) {
+                    const uint64_t m = st.gmask[g];
+#pragma unroll
+                    for (int i = 0; i < kRecWords; ++i)
+                        if (i * FPW < 64 && !(HB == 3 && i == 3)) rw[i] = spread_fields<HB>(m >> (i * FPW));
+                    if (kv[r] > lp.k_low)
+                        for (int e = pos[r]; e < span; ++e) {
+                            const Key ek = skey(e);
+                            if (!shares_prefix<W>(ek, qv[r], up_sh)) break;
+                            rec_raise<HB>(rw, s_code[e], match_levels<W>(ek, qv[r], kv[r], lp));
+                        }
                 }
             } else {
-                match_query<W, HB>(gacc, a, b, qv[r], lp, R);   // oversized span: search the index in place
+                match_query_gmem<W, HB>(gacc, a, b, qv[r], kv[r], lp, rw);
             }
         }
-        __syncwarp();                                        // reconverge after the data-dependent scans
-        if (live[r]) {
-            const uint64_t r0 = R[0], r1 = R[kLookupBlock], r2 = R[2 * kLookupBlock];
-            uint64_t r3 = R[3 * kLookupBlock];
-            if (HB == 3) r3 = level_sizes3(r0, r1, r2);
-            uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)iv[r] * kRecWords);
-            dst[0] = make_uint4((uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32));
-            dst[1] = make_uint4((uint32_t)r2, (uint32_t)(r2 >> 32), (uint32_t)r3, (uint32_t)(r3 >> 32));
-        }
+        if (HB == 3) rw[3] = level_sizes3(rw[0], rw[1], rw[2]);
+        uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)iv[r] * kRecWords);
+        dst[0] = make_uint4((uint32_t)rw[0], (uint32_t)(rw[0] >> 32), (uint32_t)rw[1], (uint32_t)(rw[1] >> 32));
+        dst[1] = make_uint4((uint32_t)rw[2], (uint32_t)(rw[2] >> 32), (uint32_t)rw[3], (uint32_t)(rw[3] >> 32));
+    }
+}
+
+// taxon index (1-based) -> slot code of its record field, in place (done once when an index is installed)
+template <int HB>
+__global__ void slot_codes_kernel(uint16_t *tax, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t t = tax[i];
+        tax[i] = t ? slot_code<HB>(t) : 0;
     }
 }
 
@@ -522,7 +628,7 @@ void launch_lookup_hb(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi
                       LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq)
 {
     const unsigned tiles = (unsigned)div_up<uint64_t>(n, tq);
-    const size_t sm = (size_t)kRecWords * kLookupBlock * 8 + (size_t)kSpanCap * (W ? 16 : 8) + (size_t)kSpanCap * 2;
+    const size_t sm = sizeof(SpanStage<W>);
     auto go = [&](auto kern) {
         KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -543,6 +649,16 @@ uint32_t lookup_tile_queries(uint64_t n_queries, uint64_t n_index)
     if (tq > kLookupTile) tq = kLookupTile;
     if (tq < 32) tq = 32;
     return (uint32_t)tq;
+}
+
+void launch_slot_codes(cudaStream_t s, uint16_t *tax, uint64_t n, int hb, uint64_t *launches)
+{
+    if (!n) return;
+    const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(n, 256), (uint64_t)kSMs * 16);
+    if (hb == 3) slot_codes_kernel<3><<<grid, 256, 0, s>>>(tax, n);
+    else if (hb == 4) slot_codes_kernel<4><<<grid, 256, 0, s>>>(tax, n);
+    else slot_codes_kernel<5><<<grid, 256, 0, s>>>(tax, n);
+    ++*launches;
 }
 
 void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, uint64_t n, IndexDev idx, LevelParams lp,
