@@ -414,7 +414,6 @@ int kasa_index_load(kasa_ctx *c, const void *entries, uint64_t n, int bits, cons
     launch_check_sorted(c->stream, c->idx_lo, c->idx_hi, d_tax32, n, c->d_err, &c->launches);
     TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
     launch_map_taxids(c->stream, d_tax32, n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
-    launch_slot_codes(c->stream, c->idx_tax, n, c->hb, &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     check_device_flags(c);
     dev_free(c, d_words); dev_free(c, d_tax32); dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
@@ -439,7 +438,6 @@ int kasa_index_from_build(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_
     if (c->wide) KASA_CUDA_TRY(cudaMemcpyAsync(c->idx_hi, c->sb.w1[b], n * 8, cudaMemcpyDeviceToDevice, c->stream));
     TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
     launch_map_taxids(c->stream, c->sb.v[b], n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
-    launch_slot_codes(c->stream, c->idx_tax, n, c->hb, &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     check_device_flags(c);
     dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);

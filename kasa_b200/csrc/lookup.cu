@@ -113,44 +113,26 @@ __device__ __forceinline__ int64_t lower_bound(const Acc &acc, int64_t lo, int64
     return lo + (key_lt<W>(acc.template key<W>(lo), q) ? 1 : 0);
 }
 
-// 3-bit records: |taxa_j| for the levels j = 0..6 (j = 0 is k_low), one byte each, from the three field words: a taxon
-// with field h is in taxa_j for every j < h.  Level 0 is a popcount of the non-zero fields; the few taxa matched above
-// k_low (fields >= 2) are walked one by one.  Stored as the fourth word of the record, it saves the per-read kernel
-// a pass over the fields.
-__device__ __forceinline__ uint64_t level_sizes3(uint64_t r0, uint64_t r1, uint64_t r2)
-{
-    constexpr uint64_t L = 0x1249249249249249ull;
-    constexpr uint64_t kOnes = 0x0001010101010100ull;       // one per level 1..6
-    const uint64_t w[3] = {r0, r1, r2};
-    uint64_t np = 0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const uint64_t hi = ((w[i] >> 1) | (w[i] >> 2)) & L;            // fields >= 2
-        np += (uint32_t)__popcll((w[i] & L) | hi);                      // fields >= 1
-        uint64_t m = hi;
-        while (m) {
-            const int p = __ffsll((long long)m) - 1;                    // = 3f
-            const uint32_t h = (uint32_t)(w[i] >> p) & 7u;
-            m &= m - 1;
-            np += kOnes & ((1ull << (8 * h)) - 1);                      // levels 1 .. h-1
-        }
-    }
-    return np;
-}
-
-// record held in registers: raise the level field of a taxon (given by its slot code, see slot_code) to h
+// record held in registers: raise the level field of a taxon (1-based dense index) to h; `np` tracks the level
+// sizes |taxa_j| (one byte per level j, the fourth word of a 3-bit record): raising a field from cur to h adds
+// the taxon to the levels cur .. h-1
 template <int HB>
-__device__ __forceinline__ void rec_raise(uint64_t (&rw)[kRecWords], uint32_t code, uint32_t h)
+__device__ __forceinline__ void rec_raise(uint64_t (&rw)[kRecWords], uint64_t &np, uint32_t taxon, uint32_t h)
 {
+    constexpr int FPW = 64 / HB;
     constexpr uint64_t HM = (1ull << HB) - 1;
-    const uint32_t wi = code >> 6;
-    const int sh = code & 63;
+    constexpr uint64_t kOnes = 0x0101010101010101ull;
+    const uint32_t sl = taxon - 1, wi = sl / FPW;
+    const int sh = (int)(sl % FPW) * HB;
 #pragma unroll
     for (int i = 0; i < kRecWords; ++i) {
         if (HB == 3 && i == 3) break;                 // 3-bit records keep their fields in three words
         if ((uint32_t)i == wi) {
             const uint32_t cur = (uint32_t)(rw[i] >> sh) & (uint32_t)HM;
-            if (h > cur) rw[i] += (uint64_t)(h - cur) << sh;
+            if (h > cur) {
+                rw[i] += (uint64_t)(h - cur) << sh;
+                if (HB == 3) np += kOnes & (((1ull << (8 * h)) - 1) ^ ((1ull << (8 * cur)) - 1));
+            }
         }
     }
 }
@@ -231,34 +213,18 @@ __device__ __forceinline__ int last_valid_level(const Key &q, const LevelParams 
     return kv;
 }
 
-// slot code of a taxon (1-based dense index): record word << 6 | bit offset of its level field
-template <int HB>
-__device__ __forceinline__ uint16_t slot_code(uint32_t taxon)
-{
-    constexpr int FPW = 64 / HB;
-    const uint32_t sl = taxon - 1;
-    return (uint16_t)(((sl / FPW) << 6) | ((sl % FPW) * HB));
-}
-// ... and back to the taxon's bit in a dense taxa mask (bit = taxon - 1)
-template <int HB>
-__device__ __forceinline__ uint32_t code_to_bit(uint32_t code)
-{
-    constexpr int FPW = 64 / HB;
-    return (code >> 6) * FPW + (code & 63u) / HB;
-}
-
 // Oversized span (rare): Set semantics of Compare.hpp:785-1041 for one query instance straight from the index in
 // HBM.  Every entry whose first c >= k_low letters equal the query's belongs to taxa_k(prefix_k(q)) for
 // k = k_low .. min(c, kv); those entries start at the lower bound of the query's k_low-letter prefix.
 template <bool W, int HB>
 __device__ __forceinline__ void match_query_gmem(const GmemAcc &acc, int64_t a, int64_t b, const Key &q, int kv,
-                                                 const LevelParams &lp, uint64_t (&rw)[kRecWords])
+                                                 const LevelParams &lp, uint64_t (&rw)[kRecWords], uint64_t &np)
 {
     const int low_sh = 5 * (lp.K - lp.k_low);
     for (int64_t e = lower_bound<W>(acc, a, b, prefix_floor<W>(q, low_sh)); e < b; ++e) {
         const Key ek = acc.template key<W>(e);
         if (!shares_prefix<W>(ek, q, low_sh)) break;
-        rec_raise<HB>(rw, acc.taxon(e), match_levels<W>(ek, q, kv, lp));
+        rec_raise<HB>(rw, np, acc.taxon(e), match_levels<W>(ek, q, kv, lp));
     }
 }
 
@@ -282,6 +248,7 @@ __global__ void __launch_bounds__(256) partition_kernel(const uint64_t *__restri
 }
 
 constexpr int kSpanCap = 2048;   // index entries staged per tile (the tile size is chosen so that the average span is <= half of it)
+static_assert(kSpanCap < 4096, "span positions and counts are packed in 12 bits");
 
 // ---- TMA (bulk async copy) + mbarrier plumbing for the span staging
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -314,28 +281,28 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 
 // shared-memory stage of one tile's index span; bulk copies need 16-byte aligned addresses and sizes, so the
 // copies start at the aligned entry below the span and the arrays are padded
-constexpr int kKeyPad = 2, kCodePad = 16;
+constexpr int kKeyPad = 2, kTaxPad = 16;
 
 template <bool W>
 struct SpanStage {
     uint64_t klo[kSpanCap + kKeyPad];
     uint64_t khi[W ? kSpanCap + kKeyPad : 2];
-    uint64_t gmask[kSpanCap];            // per entry: dense mask (bit = taxon - 1) of the taxa of its k_low-letter group
-    uint16_t code[kSpanCap + kCodePad];
+    uint16_t tax[kSpanCap + kTaxPad];
     uint64_t bar;                        // mbarrier of the bulk copies
 };
 
-// One CTA per tile of <= 1024 sorted queries.  The tile's index span (contiguous runs of the key and slot-code
-// arrays) arrives as TMA bulk copies on an mbarrier while the threads fetch their queries.  Then
-//   1. group pass: the entries of the span are cut into groups sharing their first k_low letters and every
-//      entry gets its group's taxa set as a 64-bit mask — computed once per tile instead of once per query;
-//   2. per query: one binary search (the QPT searches of a thread in lockstep: independent chains of LDS) for the
-//      first entry sharing k_low + 1 letters; the group mask of the entry found (or the one before) spreads
-//      into "level 1" fields; only the few entries sharing more than k_low letters are visited to raise fields;
-//   3. level sizes (fourth record word) and one 32-byte store to the instance's slot in emission order.
-// The record lives in registers throughout.
+// One CTA per tile of <= 1024 sorted queries.  The tile's index span (contiguous runs of the key and taxon
+// arrays) arrives as TMA bulk copies on an mbarrier while the threads fetch their queries.  Per query:
+//   1. one binary search for the first entry sharing the query's first k_low letters — the QPT searches of a thread
+//      run in lockstep (independent chains of shared-memory loads, 32-bit positions, CTA-uniform trip count);
+//   2. a forward walk over those entries, again QPT queries in lockstep: the taxa seen are OR-ed into a 64-bit
+//      mask in a register, and the sub-range sharing more than k_low letters (contiguous, usually 0-2 entries)
+//      is remembered;
+//   3. the mask spreads into "level 1" fields, the remembered entries raise their taxa's fields, the level sizes
+//      follow from popcount + raises, and one 32-byte store puts the record into the instance's slot.
+// The record lives in registers throughout; shared memory only holds the span.
 template <bool W, int HB>
-__global__ void __launch_bounds__(kLookupBlock, W ? 3 : 5) lookup_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
+__global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
                                                                          const uint32_t *__restrict__ inst, uint64_t n, IndexDev idx,
                                                                          LevelParams lp, const uint64_t *__restrict__ part,
                                                                          uint64_t *__restrict__ rec, uint32_t tq)
@@ -357,7 +324,7 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 5) lookup_kernel(const u
         mbar_expect_tx(&st.bar, kb * (W ? 2u : 1u) + cb);
         bulk_g2s(st.klo, idx.key_lo + ak, kb, &st.bar);
         if (W) bulk_g2s(st.khi, idx.key_hi + ak, kb, &st.bar);
-        bulk_g2s(st.code, idx.tax + ac, cb, &st.bar);
+        bulk_g2s(st.tax, idx.tax + ac, cb, &st.bar);
     }
     // this thread's queries and instance ids: their latency overlaps the span staging
     Key qv[QPT];
@@ -375,87 +342,85 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 5) lookup_kernel(const u
     __syncthreads();                                          // the barrier word is initialised
     const uint64_t *s_klo = st.klo + (a - ak);
     const uint64_t *s_khi = st.khi + (W ? (a - ak) : 0);
-    const uint16_t *s_code = st.code + (a - ac);
+    const uint16_t *s_tax = st.tax + (a - ac);
     const int low_sh = 5 * (lp.K - lp.k_low);                 // bits below the first k_low letters
     const int up_sh = lp.k_low < lp.K ? low_sh - 5 : 0;       // ... below the first k_low + 1 letters
     auto skey = [&](int e) { return Key{s_klo[e], W ? s_khi[e] : 0ull}; };
 
+    int pos[QPT], kv[QPT];
+    uint64_t mask[QPT];
+    uint32_t up[QPT];                                         // entries sharing > k_low letters: first position << 12 | count (both <= kSpanCap < 4096)
+    uint32_t act = 0;
+#pragma unroll
+    for (int r = 0; r < QPT; ++r) {
+        pos[r] = 0; mask[r] = 0; up[r] = 0;
+        kv[r] = live[r] ? last_valid_level<W>(qv[r], lp) : 0;
+        if (live[r] && kv[r] >= lp.k_low) act |= 1u << r;
+    }
     if (span > 0) {
         mbar_wait(&st.bar, 0);
-        // ---- 1. group pass
-        for (int j = tid; j < span; j += kLookupBlock) {
-            const Key kj = skey(j);
-            if (j > 0 && shares_prefix<W>(skey(j - 1), kj, low_sh)) continue;       // not the first entry of its group
-            uint64_t m = 0;
-            int e = j;
-            do { m |= 1ull << code_to_bit<HB>(s_code[e]); ++e; } while (e < span && shares_prefix<W>(skey(e), kj, low_sh));
-            for (int x = j; x < e; ++x) st.gmask[x] = m;
-        }
-    }
-    __syncthreads();
-
-    // ---- 2. lockstep binary searches for the first entry >= the query's (k_low + 1)-letter prefix
-    int pos[QPT], kv[QPT];
+        // ---- 1. lockstep binary searches for the first entry >= the query's k_low-letter prefix
+        {
+            Key fl[QPT];
 #pragma unroll
-    for (int r = 0; r < QPT; ++r) { pos[r] = 0; kv[r] = live[r] ? last_valid_level<W>(qv[r], lp) : 0; }
-    if (span > 0) {
-        Key fl[QPT];
+            for (int r = 0; r < QPT; ++r) fl[r] = prefix_floor<W>(qv[r], low_sh);
+            int nn = span;
+            while (nn > 1) {
+                const int half = nn >> 1;
 #pragma unroll
-        for (int r = 0; r < QPT; ++r) fl[r] = prefix_floor<W>(qv[r], up_sh);
-        int nn = span;
-        while (nn > 1) {
-            const int half = nn >> 1;
+                for (int r = 0; r < QPT; ++r)
+                    if (key_lt<W>(skey(pos[r] + half - 1), fl[r])) pos[r] += half;
+                nn -= half;
+            }
 #pragma unroll
             for (int r = 0; r < QPT; ++r)
-                if (key_lt<W>(skey(pos[r] + half - 1), fl[r])) pos[r] += half;
-            nn -= half;
+                if (key_lt<W>(skey(pos[r]), fl[r])) ++pos[r];
         }
+        // ---- 2. lockstep forward walks over the entries sharing k_low letters
+        uint32_t go = act;
+        while (go) {
+            Key ek[QPT];
+            uint32_t tx[QPT];
 #pragma unroll
-        for (int r = 0; r < QPT; ++r)
-            if (key_lt<W>(skey(pos[r]), fl[r])) ++pos[r];
+            for (int r = 0; r < QPT; ++r) {                   // independent loads first
+                const int e = min(pos[r], span - 1);
+                ek[r] = skey(e);
+                tx[r] = s_tax[e];
+            }
+#pragma unroll
+            for (int r = 0; r < QPT; ++r) {
+                if (!((go >> r) & 1u)) continue;
+                if (pos[r] < span && shares_prefix<W>(ek[r], qv[r], low_sh)) {
+                    mask[r] |= 1ull << (tx[r] - 1);
+                    if (kv[r] > lp.k_low && shares_prefix<W>(ek[r], qv[r], up_sh)) up[r] = (up[r] ? up[r] : (uint32_t)pos[r] << 12) + 1;
+                    ++pos[r];
+                } else {
+                    go &= ~(1u << r);
+                }
+            }
+        }
     }
+    // ---- 3. records
     GmemAcc gacc{idx.key_lo, idx.key_hi, idx.tax};
 #pragma unroll
     for (int r = 0; r < QPT; ++r) {
         if (r * kLookupBlock >= (int)tq) break;             // CTA-uniform
         if (!live[r]) continue;
         uint64_t rw[kRecWords] = {0, 0, 0, 0};
-        if (kv[r] >= lp.k_low) {
-            if (staged) {
-                // the query's group, if the index has it, holds the entry at pos or the one before
-                int g = -1;
-                if (pos[r] < span && shares_prefix<W>(skey(pos[r]), qv[r], low_sh)) g = pos[r];
-                else if (pos[r] > 0 && shares_prefix<W>(skey(pos[r] - 1), qv[r], low_sh)) g = pos[r] - 1;
-                if (g >= 0) {
-                    const uint64_t m = st.gmask[g];
+        uint64_t np = (uint32_t)__popcll(mask[r]);
+        if (staged) {
 #pragma unroll
-                    for (int i = 0; i < kRecWords; ++i)
-                        if (i * FPW < 64 && !(HB == 3 && i == 3)) rw[i] = spread_fields<HB>(m >> (i * FPW));
-                    if (kv[r] > lp.k_low)
-                        for (int e = pos[r]; e < span; ++e) {
-                            const Key ek = skey(e);
-                            if (!shares_prefix<W>(ek, qv[r], up_sh)) break;
-                            rec_raise<HB>(rw, s_code[e], match_levels<W>(ek, qv[r], kv[r], lp));
-                        }
-                }
-            } else {
-                match_query_gmem<W, HB>(gacc, a, b, qv[r], kv[r], lp, rw);
-            }
+            for (int i = 0; i < kRecWords; ++i)
+                if (i * FPW < 64 && !(HB == 3 && i == 3)) rw[i] = spread_fields<HB>(mask[r] >> (i * FPW));
+            for (uint32_t e = up[r] >> 12, end = (up[r] >> 12) + (up[r] & 4095u); e < end; ++e)
+                rec_raise<HB>(rw, np, s_tax[e], match_levels<W>(skey((int)e), qv[r], kv[r], lp));
+        } else if ((act >> r) & 1u) {
+            match_query_gmem<W, HB>(gacc, a, b, qv[r], kv[r], lp, rw, np);
         }
-        if (HB == 3) rw[3] = level_sizes3(rw[0], rw[1], rw[2]);
+        if (HB == 3) rw[3] = np;
         uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)iv[r] * kRecWords);
         dst[0] = make_uint4((uint32_t)rw[0], (uint32_t)(rw[0] >> 32), (uint32_t)rw[1], (uint32_t)(rw[1] >> 32));
         dst[1] = make_uint4((uint32_t)rw[2], (uint32_t)(rw[2] >> 32), (uint32_t)rw[3], (uint32_t)(rw[3] >> 32));
-    }
-}
-
-// taxon index (1-based) -> slot code of its record field, in place (done once when an index is installed)
-template <int HB>
-__global__ void slot_codes_kernel(uint16_t *tax, uint64_t n)
-{
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t t = tax[i];
-        tax[i] = t ? slot_code<HB>(t) : 0;
     }
 }
 
@@ -649,16 +614,6 @@ uint32_t lookup_tile_queries(uint64_t n_queries, uint64_t n_index)
     if (tq > kLookupTile) tq = kLookupTile;
     if (tq < 32) tq = 32;
     return (uint32_t)tq;
-}
-
-void launch_slot_codes(cudaStream_t s, uint16_t *tax, uint64_t n, int hb, uint64_t *launches)
-{
-    if (!n) return;
-    const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(n, 256), (uint64_t)kSMs * 16);
-    if (hb == 3) slot_codes_kernel<3><<<grid, 256, 0, s>>>(tax, n);
-    else if (hb == 4) slot_codes_kernel<4><<<grid, 256, 0, s>>>(tax, n);
-    else slot_codes_kernel<5><<<grid, 256, 0, s>>>(tax, n);
-    ++*launches;
 }
 
 void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, uint64_t n, IndexDev idx, LevelParams lp,

@@ -11,7 +11,7 @@ namespace kasa {
 struct IndexDev {
     const uint64_t *key_lo;
     const uint64_t *key_hi;   // nullptr for 64-bit k-mers
-    const uint16_t *tax;      // slot code of the entry's taxon: record word << 6 | bit offset of its level field (launch_slot_codes)
+    const uint16_t *tax;      // dense taxon index (1-based: position in the content file)
     uint64_t n;
 };
 
@@ -31,9 +31,6 @@ constexpr int kRecWords = 4;           // match record = 4 x u64 = one 32-byte s
 inline int record_level_bits(int num_k) { return num_k <= 7 ? 3 : (num_k <= 15 ? 4 : 5); }
 // 3-bit records keep their fourth word for a dense bit mask of the taxa matched at k_low (see lookup.cu)
 inline int record_taxa_capacity(int hb) { return hb == 3 ? 63 : kRecWords * (64 / hb); }
-
-// dense taxon index (1-based position in the content file) -> slot code, in place; run once per installed index
-void launch_slot_codes(cudaStream_t s, uint16_t *tax, uint64_t n, int hb, uint64_t *launches);
 
 // per-tile index spans: part[2t], part[2t+1] = [first entry sharing the sorted prefix of the tile's first query,
 // one past the last entry sharing the sorted prefix of its last query).  The queries only need to be ordered
