@@ -148,6 +148,16 @@ typedef struct {
  * (Compare.hpp:3192).  Counts are accumulated inside ctx across batches.                               */
 int kasa_identify_batch(kasa_ctx *ctx, const kasa_read_batch *in, kasa_batch_result *out);
 
+/* The same work, pipelined (what the reference gets from its reader / worker threads, Compare.hpp:2983-3440):
+ * kasa_identify_submit() starts the batch's host->device copies on a copy stream, queues its kernels and returns
+ * once the batch's k-mer count is known; kasa_identify_wait() completes the OLDEST submitted batch (its scores
+ * are copied back on a second copy stream, overlapping the next batch's kernels) and fills the `out` given at
+ * submit time.  At most two batches are in flight; `in`'s host buffers must stay valid until the submit call
+ * returns, `out` and out->scores until the matching wait.  Typical loop: submit(0); for i >= 1 { submit(i);
+ * wait(i-1); }  wait(last).  kasa_identify_batch == submit + wait.                                            */
+int kasa_identify_submit(kasa_ctx *ctx, const kasa_read_batch *in, kasa_batch_result *out);
+int kasa_identify_wait(kasa_ctx *ctx);
+
 /* Replaces: the per-thread count reduction (Compare.hpp:3445-3454).  count_all / count_unique are
  * [numK][n_taxa], level 0 = k_high (kASA _aOfK, kASA.hpp:299-302).  Resets the accumulators
  * (Compare.hpp:3748-3752).                                                                             */

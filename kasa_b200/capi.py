@@ -27,7 +27,7 @@ TRIE = np.dtype([("count", "<u8"), ("prefix", "<u4")])                # packedBi
 EXPORTS = [
     "kasa_abi_version", "kasa_ctx_create", "kasa_ctx_destroy", "kasa_last_error", "kasa_ctx_set_stream",
     "kasa_ctx_synchronize", "kasa_ctx_launch_count", "kasa_ctx_stage_times", "kasa_index_load", "kasa_index_from_build", "kasa_index_size",
-    "kasa_identify_batch", "kasa_identify_finish", "kasa_build_push", "kasa_build_finish", "kasa_build_fetch",
+    "kasa_identify_batch", "kasa_identify_submit", "kasa_identify_wait", "kasa_identify_finish", "kasa_build_push", "kasa_build_finish", "kasa_build_fetch",
     "kasa_build_frequency", "kasa_dbg_extract", "kasa_dbg_sort_pairs", "kasa_synth_build_reference", "kasa_synth_reads",
 ]
 
@@ -91,6 +91,8 @@ def load_library():
     L.kasa_index_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32]
     L.kasa_index_from_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.kasa_identify_batch.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.POINTER(CBatchResult)]
+    L.kasa_identify_submit.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.POINTER(CBatchResult)]
+    L.kasa_identify_wait.argtypes = [C.c_void_p]
     L.kasa_identify_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     L.kasa_build_push.argtypes = [C.c_void_p, C.POINTER(CSeqBatch)]
     L.kasa_build_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -235,6 +237,34 @@ class Context:
 
     def identify_batch_raw(self, rb: CReadBatch, res: CBatchResult):
         self._check(self.lib.kasa_identify_batch(self.h, C.byref(rb), C.byref(res)))
+
+    # pipelined pair (kasa_identify_submit / kasa_identify_wait): at most two batches in flight; the caller keeps
+    # rb's buffers alive until submit returns and res (+ its score buffer) until the matching wait
+    def identify_submit_raw(self, rb: CReadBatch, res: CBatchResult):
+        self._check(self.lib.kasa_identify_submit(self.h, C.byref(rb), C.byref(res)))
+
+    def identify_wait(self):
+        self._check(self.lib.kasa_identify_wait(self.h))
+
+    def identify_stream(self, batches, read_first_seqs=None):
+        """Pipelined identify over an iterable of batches (each as for identify_batch); yields (n_kmers, scores, gpu_ms)
+        per batch in order."""
+        want = self.params.score_mode != SCORE_NONE
+        inflight = []
+        for i, seqs in enumerate(batches):
+            rb, keep, n_reads = self._read_batch(seqs, read_first_seqs[i] if read_first_seqs is not None else None)
+            scores = np.zeros((n_reads, self.n_taxa), dtype=np.float32) if want else None
+            res = CBatchResult(0, scores.ctypes.data if want and scores.size else None, MEM_HOST, 0.0)
+            self.identify_submit_raw(rb, res)
+            inflight.append((res, scores, keep))
+            if len(inflight) == 2:
+                self.identify_wait()
+                r, sc, _ = inflight.pop(0)
+                yield int(r.n_kmers), sc, float(r.gpu_ms)
+        while inflight:
+            self.identify_wait()
+            r, sc, _ = inflight.pop(0)
+            yield int(r.n_kmers), sc, float(r.gpu_ms)
 
     def identify_finish(self):
         ca = np.zeros((self.num_k, self.n_taxa), dtype=np.float64)

@@ -35,13 +35,12 @@ struct kasa_ctx {
     void *sort_ws = nullptr;
     uint32_t *d_err = nullptr;          // [4] device error flags
     // sequence staging
-    char *d_ascii = nullptr;
+    char *d_ascii = nullptr;            // = slot[0].ascii etc.: the build path stages through slot 0
     uint32_t *d_bases2 = nullptr, *d_nmask = nullptr;
     uint64_t *d_seq_start = nullptr, *d_pstart = nullptr, *d_koff = nullptr, *d_read_koff = nullptr, *d_scan_tmp = nullptr;
     uint32_t *d_seq_len = nullptr, *d_read_first = nullptr, *d_taxid = nullptr;
     // lookup / accumulation
     uint64_t *d_part = nullptr, *d_rec = nullptr;
-    float *d_scores = nullptr;
     unsigned long long *d_cnt_fx = nullptr, *d_cnt_un = nullptr, *d_tot_un = nullptr;
     double *d_tot_all = nullptr;
     uint64_t n_kmers_total = 0;
@@ -58,8 +57,23 @@ struct kasa_ctx {
     uint32_t *d_trie_words = nullptr;
     ExactWorkspace xws{};
     bool xws_ready = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t sev[KASA_N_STAGES + 1] = {};
+    // pipelined identify (kasa_identify_submit / _wait): two slots of input staging, score buffers and events;
+    // host->device copies run on cs_in, the scores' device->host copy on cs_out, kernels on `stream`
+    struct Slot {
+        char *ascii = nullptr;
+        uint64_t *seq_start = nullptr;
+        uint32_t *seq_len = nullptr, *read_first = nullptr;
+        float *scores = nullptr;
+        uint32_t *h_err = nullptr;                      // pinned copy of the device error flags at the end of the batch
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr, sev[KASA_N_STAGES + 1] = {};
+        cudaEvent_t h2d = nullptr, in_free = nullptr, done = nullptr, out = nullptr;
+        bool in_free_set = false, out_set = false, pending = false;
+        kasa_batch_result *res = nullptr;
+        uint64_t n = 0;
+        int n_passes = 0;
+    } slot[2];
+    cudaStream_t cs_in = nullptr, cs_out = nullptr;
+    uint64_t submitted = 0, completed = 0;
     double stage_ms[KASA_N_STAGES] = {};
     uint64_t stage_batches = 0, stage_passes = 0, stage_kmers = 0;
 };
@@ -135,17 +149,21 @@ void ensure_workspace(kasa_ctx *c)
     c->sort_ws = dev_alloc<char>(c, sort_workspace_bytes(cap));
     c->d_err = dev_alloc<uint32_t>(c, 4);
     KASA_CUDA_TRY(cudaMemset(c->d_err, 0, 16));
-    c->d_ascii = dev_alloc<char>(c, nb + 64);
+    for (auto &sl : c->slot) {
+        sl.ascii = dev_alloc<char>(c, nb + 64);
+        sl.seq_start = dev_alloc<uint64_t>(c, (size_t)ns + 1);
+        sl.seq_len = dev_alloc<uint32_t>(c, (size_t)ns + 1);
+        sl.read_first = dev_alloc<uint32_t>(c, (size_t)ns + 1);
+    }
+    c->d_ascii = c->slot[0].ascii; c->d_seq_start = c->slot[0].seq_start; c->d_seq_len = c->slot[0].seq_len;
+    c->d_read_first = c->slot[0].read_first;
     const uint64_t packed_bases = nb + 32ull * ns + 64;
     c->d_bases2 = dev_alloc<uint32_t>(c, packed_bases / 16 + 4);
     c->d_nmask = dev_alloc<uint32_t>(c, packed_bases / 32 + 4);
-    c->d_seq_start = dev_alloc<uint64_t>(c, (size_t)ns + 1);
     c->d_pstart = dev_alloc<uint64_t>(c, (size_t)ns + 1);
     c->d_koff = dev_alloc<uint64_t>(c, (size_t)ns + 1);
     c->d_read_koff = dev_alloc<uint64_t>(c, (size_t)ns + 1);
     c->d_scan_tmp = dev_alloc<uint64_t>(c, scan_tmp_elems(std::max<uint64_t>(cap + 1, ns + 1)) + 1);
-    c->d_seq_len = dev_alloc<uint32_t>(c, (size_t)ns + 1);
-    c->d_read_first = dev_alloc<uint32_t>(c, (size_t)ns + 1);
     c->d_taxid = dev_alloc<uint32_t>(c, (size_t)ns + 1);
     c->d_part = dev_alloc<uint64_t>(c, 2 * (size_t)div_up<uint64_t>(cap, 32) + 2);
     c->d_rec = dev_alloc<uint64_t>(c, (size_t)(cap + 2) * kRecWords);
@@ -216,16 +234,17 @@ void set_taxa(kasa_ctx *c, uint32_t n_taxa)
     KASA_CUDA_TRY(cudaMemsetAsync(c->d_cnt_un, 0, cells * 8, c->stream));
     KASA_CUDA_TRY(cudaMemsetAsync(c->d_tot_un, 0, cells * 8, c->stream));
     KASA_CUDA_TRY(cudaMemsetAsync(c->d_tot_all, 0, cells * 8, c->stream));
-    c->d_scores = dev_alloc<float>(c, (size_t)c->p.max_batch_seqs * n_taxa + 1);
+    for (auto &sl : c->slot) sl.scores = c->p.score_mode != KASA_SCORE_NONE ? dev_alloc<float>(c, (size_t)c->p.max_batch_seqs * n_taxa + 1) : nullptr;
     c->n_kmers_total = 0;
 }
 
 void drop_index(kasa_ctx *c)
 {
     dev_free(c, c->idx_lo); dev_free(c, c->idx_hi); dev_free(c, c->idx_tax);
-    dev_free(c, c->d_cnt_fx); dev_free(c, c->d_cnt_un); dev_free(c, c->d_tot_un); dev_free(c, c->d_tot_all); dev_free(c, c->d_scores);
+    dev_free(c, c->d_cnt_fx); dev_free(c, c->d_cnt_un); dev_free(c, c->d_tot_un); dev_free(c, c->d_tot_all);
+    for (auto &sl : c->slot) { dev_free(c, sl.scores); sl.scores = nullptr; }
     c->idx_lo = c->idx_hi = nullptr; c->idx_tax = nullptr;
-    c->d_cnt_fx = c->d_cnt_un = c->d_tot_un = nullptr; c->d_tot_all = nullptr; c->d_scores = nullptr;
+    c->d_cnt_fx = c->d_cnt_un = c->d_tot_un = nullptr; c->d_tot_all = nullptr;
     c->idx_n = 0; c->n_taxa = 0;
 }
 
@@ -283,6 +302,8 @@ int fail(kasa_ctx *c, const Error &e)
     return e.code;
 }
 
+#define KASA_REQUIRE_PLAIN(cond) \
+    if (!(cond)) return fail(nullptr, Error{KASA_ERR_ARG, "null argument"})
 #define KASA_API_BEGIN try {
 #define KASA_API_END(ctx)                                                                   \
     }                                                                                       \
@@ -331,9 +352,15 @@ int kasa_ctx_create(const kasa_params *p, kasa_ctx **out)
         if (const char *e = getenv("KASA_TUNE_SORT_BITS")) c->sort_bits = std::min(5 * c->K, std::max(8, atoi(e)));
         KASA_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
-        KASA_CUDA_TRY(cudaEventCreate(&c->ev0));
-        KASA_CUDA_TRY(cudaEventCreate(&c->ev1));
-        for (auto &e : c->sev) KASA_CUDA_TRY(cudaEventCreate(&e));
+        KASA_CUDA_TRY(cudaStreamCreateWithFlags(&c->cs_in, cudaStreamNonBlocking));
+        KASA_CUDA_TRY(cudaStreamCreateWithFlags(&c->cs_out, cudaStreamNonBlocking));
+        for (auto &sl : c->slot) {
+            KASA_CUDA_TRY(cudaEventCreate(&sl.ev0));
+            KASA_CUDA_TRY(cudaEventCreate(&sl.ev1));
+            for (auto &e : sl.sev) KASA_CUDA_TRY(cudaEventCreate(&e));
+            for (cudaEvent_t *e : {&sl.h2d, &sl.in_free, &sl.done, &sl.out}) KASA_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+            KASA_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_err), 16, cudaHostAllocDefault));
+        }
         uint8_t table[512];
         if (p->codon_table) std::memcpy(table, p->codon_table, 512); else builtin_codon_table(table);
         upload_codon_table(table);
@@ -351,9 +378,13 @@ void kasa_ctx_destroy(kasa_ctx *c)
     cudaSetDevice(c->p.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void *p : c->allocs) cudaFree(p);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
-    for (auto e : c->sev) if (e) cudaEventDestroy(e);
+    if (c->cs_in) { cudaStreamSynchronize(c->cs_in); cudaStreamDestroy(c->cs_in); }
+    if (c->cs_out) { cudaStreamSynchronize(c->cs_out); cudaStreamDestroy(c->cs_out); }
+    for (auto &sl : c->slot) {
+        for (cudaEvent_t e : {sl.ev0, sl.ev1, sl.h2d, sl.in_free, sl.done, sl.out}) if (e) cudaEventDestroy(e);
+        for (auto e : sl.sev) if (e) cudaEventDestroy(e);
+        if (sl.h_err) cudaFreeHost(sl.h_err);
+    }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -445,36 +476,52 @@ int kasa_index_from_build(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_
     KASA_API_END(c)
 }
 
-// shared front half of identify: stage + pack + count + extract; returns number of k-mers
-static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in)
+// Host -> device copy of one array of slot `sl` on the copy-in stream (device-resident input is used in place)
+extern "C++" template <typename T>
+const T *stage_in(kasa_ctx *c, const T *src, size_t n, T *dst, int location)
+{
+    if (location == KASA_MEM_DEVICE) return src;
+    KASA_CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, c->cs_in));
+    return dst;
+}
+
+// front half of identify for slot `sl`: stage (copy-in stream) + pack + count + extract (compute stream);
+// returns the number of k-mers; *read_first = device copy of in->read_first_seq (or nullptr)
+static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::Slot &sl, const uint32_t **read_first)
 {
     KASA_REQUIRE(in->n_seqs <= c->p.max_batch_seqs, KASA_ERR_NOMEM, "batch has more sequences than max_batch_seqs");
     KASA_REQUIRE(in->n_reads <= in->n_seqs, KASA_ERR_ARG, "n_reads > n_seqs");
     KASA_REQUIRE(in->format == KASA_SEQ_ASCII || in->format == KASA_SEQ_PACKED2, KASA_ERR_ARG, "unknown sequence format");
     KASA_REQUIRE(in->read_first_seq || in->n_reads == in->n_seqs, KASA_ERR_ARG, "read_first_seq is required when n_reads != n_seqs");
     ensure_workspace(c);
+    *read_first = nullptr;
     const uint32_t ns = in->n_seqs;
     if (ns == 0) return 0;
-    const uint64_t *seq_start = stage_array(c, in->seq_start, ns, c->d_seq_start, in->location);
-    const uint32_t *seq_len = stage_array(c, in->seq_len, ns, c->d_seq_len, in->location);
+    // the slot's staging arrays were last read by the extraction of the batch two submissions ago
+    if (sl.in_free_set) KASA_CUDA_TRY(cudaStreamWaitEvent(c->cs_in, sl.in_free, 0));
+    const uint64_t *seq_start = stage_in(c, in->seq_start, ns, sl.seq_start, in->location);
+    const uint32_t *seq_len = stage_in(c, in->seq_len, ns, sl.seq_len, in->location);
+    if (in->read_first_seq) *read_first = stage_in(c, in->read_first_seq, (size_t)in->n_reads + 1, sl.read_first, in->location);
+    const char *ascii = static_cast<const char *>(in->bases);
+    if (in->format == KASA_SEQ_ASCII && in->location == KASA_MEM_HOST) {
+        uint64_t total = host_total_bases(in->seq_start, in->seq_len, ns);
+        KASA_REQUIRE(total <= c->p.max_batch_bases, KASA_ERR_NOMEM, "batch has more bases than max_batch_bases");
+        KASA_CUDA_TRY(cudaMemcpyAsync(sl.ascii, in->bases, total, cudaMemcpyHostToDevice, c->cs_in));
+        ascii = sl.ascii;
+    }
+    KASA_CUDA_TRY(cudaEventRecord(sl.h2d, c->cs_in));
+    KASA_CUDA_TRY(cudaStreamWaitEvent(c->stream, sl.h2d, 0));
     PackedSeqs ps{};
     ps.n_seqs = ns;
     ps.seq_len = seq_len;
     if (in->format == KASA_SEQ_ASCII) {
-        const char *ascii = static_cast<const char *>(in->bases);
-        if (in->location == KASA_MEM_HOST) {
-            uint64_t total = host_total_bases(in->seq_start, in->seq_len, ns);
-            KASA_REQUIRE(total <= c->p.max_batch_bases, KASA_ERR_NOMEM, "batch has more bases than max_batch_bases");
-            KASA_CUDA_TRY(cudaMemcpyAsync(c->d_ascii, in->bases, total, cudaMemcpyHostToDevice, c->stream));
-            ascii = c->d_ascii;
-        }
         launch_pack_sizes(c->stream, seq_len, ns, c->d_pstart, &c->launches);
         exclusive_scan_u64(c->stream, c->d_pstart, ns, c->d_scan_tmp, &c->launches);
         launch_pack_ascii(c->stream, ascii, seq_start, seq_len, ns, c->d_pstart, c->d_bases2, c->d_nmask, &c->launches);
         ps.bases2 = c->d_bases2; ps.nmask = c->d_nmask; ps.seq_start = c->d_pstart;
     } else {
         KASA_REQUIRE(in->nmask, KASA_ERR_ARG, "PACKED2 input needs the non-ACGT plane");
-        if (in->location == KASA_MEM_HOST) {
+        if (in->location == KASA_MEM_HOST) {              // packed planes are not double-buffered: copied in stream order
             uint64_t total = host_total_bases(in->seq_start, in->seq_len, ns);
             KASA_REQUIRE(total <= c->p.max_batch_bases + 32ull * ns, KASA_ERR_NOMEM, "batch has more bases than max_batch_bases");
             KASA_CUDA_TRY(cudaMemcpyAsync(c->d_bases2, in->bases, div_up<uint64_t>(total, 16) * 4, cudaMemcpyHostToDevice, c->stream));
@@ -490,22 +537,53 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in)
     exclusive_scan_u64(c->stream, c->d_koff, ns, c->d_scan_tmp, &c->launches);
     const uint64_t n = read_u64(c, c->d_koff + ns);
     KASA_REQUIRE(n <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "batch yields more k-mers than max_batch_kmers");
-    KASA_CUDA_TRY(cudaEventRecord(c->sev[1], c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[1], c->stream));
     launch_extract_identify(c->stream, ps, kp, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     return n;
 }
 
-int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_result *out)
+// completes the oldest submitted batch: waits for its kernels and score copy, reports timings and device errors
+static void finish_slot(kasa_ctx *c, kasa_ctx::Slot &sl)
+{
+    sl.pending = false;
+    c->completed += 1;
+    KASA_CUDA_TRY(cudaEventSynchronize(sl.out_set ? sl.out : sl.done));
+    kasa_batch_result *out = sl.res;
+    KASA_CUDA_TRY(cudaEventElapsedTime(&out->gpu_ms, sl.ev0, sl.ev1));
+    for (int i = 0; i < KASA_N_STAGES; ++i) {
+        float ms = 0.f;
+        KASA_CUDA_TRY(cudaEventElapsedTime(&ms, sl.sev[i], sl.sev[i + 1]));
+        c->stage_ms[i] += ms;
+    }
+    c->stage_batches += 1;
+    c->stage_passes += sl.n_passes;
+    c->stage_kmers += sl.n;
+    c->n_kmers_total += sl.n;
+    const uint32_t f = sl.h_err[0] | sl.h_err[1] | sl.h_err[2] | sl.h_err[3];
+    if (f) {
+        KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        KASA_CUDA_TRY(cudaMemsetAsync(c->d_err, 0, 16, c->stream));
+        if (f == 1) throw Error{KASA_ERR_INTERNAL, "radix sort look-back watchdog tripped"};
+        throw Error{KASA_ERR_INTERNAL, "device error flag " + std::to_string(f)};
+    }
+}
+
+int kasa_identify_submit(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_result *out)
 {
     KASA_API_BEGIN
     KASA_REQUIRE(c && in && out, KASA_ERR_ARG, "null argument");
     KASA_REQUIRE(c->idx_lo, KASA_ERR_STATE, "kasa_identify_batch before an index was loaded");
+    KASA_REQUIRE(c->submitted - c->completed < 2, KASA_ERR_STATE, "two batches are in flight: call kasa_identify_wait first");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
-    KASA_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    KASA_CUDA_TRY(cudaEventRecord(c->sev[0], c->stream));
-    KASA_CUDA_TRY(cudaEventRecord(c->sev[1], c->stream));      // re-recorded by extract_batch when there is work
-    const uint64_t n = extract_batch(c, in);
+    kasa_ctx::Slot &sl = c->slot[c->submitted & 1];
+    KASA_CUDA_TRY(cudaEventRecord(sl.ev0, c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[0], c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[1], c->stream));      // re-recorded by extract_batch when there is work
+    const uint32_t *first = nullptr;
+    const uint64_t n = extract_batch(c, in, sl, &first);
+    KASA_CUDA_TRY(cudaEventRecord(sl.in_free, c->stream));
+    sl.in_free_set = true;
     out->n_kmers = n;
     const bool want_scores = c->p.score_mode != KASA_SCORE_NONE;
     // identify orders the k-mers on their leading kIdentifySortBits only (lookup.cuh: launch_partition); the exact
@@ -513,21 +591,21 @@ int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resul
     const bool exact = c->p.score_mode == KASA_SCORE_EXACT;
     const int sorted_from = exact ? 0 : std::max(0, 5 * c->K - c->sort_bits);
     SortPlan plan = plan_for_bit_range(sorted_from, 5 * c->K);
-    KASA_CUDA_TRY(cudaEventRecord(c->sev[2], c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[2], c->stream));
+    // the slot's score buffer may still be on its way to the host for the batch two submissions ago
+    if (sl.out_set) KASA_CUDA_TRY(cudaStreamWaitEvent(c->stream, sl.out, 0));
+    sl.out_set = false;
     if (n) {
-        const int cur = radix_sort(c->stream, c->sb, 0, n, plan, c->sort_ws, c->d_err, &c->launches, c->sev[3]);
-        KASA_CUDA_TRY(cudaEventRecord(c->sev[4], c->stream));
-        const uint32_t *first = in->read_first_seq
-                                    ? stage_array(c, in->read_first_seq, (size_t)in->n_reads + 1, c->d_read_first, in->location)
-                                    : nullptr;
+        const int cur = radix_sort(c->stream, c->sb, 0, n, plan, c->sort_ws, c->d_err, &c->launches, sl.sev[3]);
+        KASA_CUDA_TRY(cudaEventRecord(sl.sev[4], c->stream));
         launch_read_offsets(c->stream, c->d_koff, first, in->n_reads, c->d_read_koff, &c->launches);
         IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n};
         LevelParams lp = level_params(c);
         const uint32_t tq = lookup_tile_queries(n, c->idx_n);
         launch_partition(c->stream, c->sb.w0[cur], c->sb.w1[cur], n, idx, lp, c->d_part, tq, sorted_from, &c->launches);
         launch_lookup(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, idx, lp, c->d_part, c->d_rec, tq, &c->launches);
-        KASA_CUDA_TRY(cudaEventRecord(c->sev[5], c->stream));
-        launch_per_read(c->stream, c->d_rec, c->d_read_koff, in->n_reads, lp, (want_scores && !exact) ? c->d_scores : nullptr,
+        KASA_CUDA_TRY(cudaEventRecord(sl.sev[5], c->stream));
+        launch_per_read(c->stream, c->d_rec, c->d_read_koff, in->n_reads, lp, (want_scores && !exact) ? sl.scores : nullptr,
                         c->d_cnt_fx, c->d_cnt_un, &c->launches);
         if (exact) {
             if (!c->xws_ready) {
@@ -544,36 +622,62 @@ int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resul
             uint32_t max_inst = 0;
             KASA_CUDA_TRY(cudaMemcpyAsync(&max_inst, c->xws.max_inst, 4, cudaMemcpyDeviceToHost, c->stream));
             KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
-            KASA_REQUIRE(launch_exact_scores(c->stream, c->d_rec, c->xws.trig, c->d_read_koff, in->n_reads, max_inst, lp, c->d_scores,
+            KASA_REQUIRE(launch_exact_scores(c->stream, c->d_rec, c->xws.trig, c->d_read_koff, in->n_reads, max_inst, lp, sl.scores,
                                              &c->launches),
                          KASA_ERR_ARG, "KASA_SCORE_EXACT: a read has too many (k-mer, level) pairs for the shared-memory replay; "
                                        "use KASA_SCORE_FAST for long reads");
         }
         launch_fold_counts(c->stream, c->d_cnt_fx, c->d_cnt_un, lp, c->d_tot_all, c->d_tot_un, &c->launches);
     } else {
-        for (int i = 3; i <= 5; ++i) KASA_CUDA_TRY(cudaEventRecord(c->sev[i], c->stream));
-        if (want_scores && in->n_reads) KASA_CUDA_TRY(cudaMemsetAsync(c->d_scores, 0, (size_t)in->n_reads * c->n_taxa * 4, c->stream));
+        for (int i = 3; i <= 5; ++i) KASA_CUDA_TRY(cudaEventRecord(sl.sev[i], c->stream));
+        if (want_scores && in->n_reads) KASA_CUDA_TRY(cudaMemsetAsync(sl.scores, 0, (size_t)in->n_reads * c->n_taxa * 4, c->stream));
     }
-    KASA_CUDA_TRY(cudaEventRecord(c->sev[6], c->stream));
-    KASA_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
-    if (want_scores && out->scores && in->n_reads) {
-        KASA_CUDA_TRY(cudaMemcpyAsync(out->scores, c->d_scores, (size_t)in->n_reads * c->n_taxa * 4,
-                                      out->scores_location == KASA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
-                                      c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[6], c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(sl.ev1, c->stream));
+    const bool copy_scores = want_scores && out->scores && in->n_reads;
+    if (copy_scores && out->scores_location == KASA_MEM_DEVICE)
+        KASA_CUDA_TRY(cudaMemcpyAsync(out->scores, sl.scores, (size_t)in->n_reads * c->n_taxa * 4, cudaMemcpyDeviceToDevice, c->stream));
+    KASA_CUDA_TRY(cudaMemcpyAsync(sl.h_err, c->d_err, 16, cudaMemcpyDeviceToHost, c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[7], c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(sl.done, c->stream));
+    if (copy_scores && out->scores_location != KASA_MEM_DEVICE) {
+        // device -> host on its own stream: it overlaps the next batch's kernels
+        KASA_CUDA_TRY(cudaStreamWaitEvent(c->cs_out, sl.done, 0));
+        KASA_CUDA_TRY(cudaMemcpyAsync(out->scores, sl.scores, (size_t)in->n_reads * c->n_taxa * 4, cudaMemcpyDeviceToHost, c->cs_out));
+        KASA_CUDA_TRY(cudaEventRecord(sl.out, c->cs_out));
+        sl.out_set = true;
     }
-    KASA_CUDA_TRY(cudaEventRecord(c->sev[7], c->stream));
-    check_device_flags(c);     // synchronises the stream
-    KASA_CUDA_TRY(cudaEventElapsedTime(&out->gpu_ms, c->ev0, c->ev1));
-    for (int i = 0; i < KASA_N_STAGES; ++i) {
-        float ms = 0.f;
-        KASA_CUDA_TRY(cudaEventElapsedTime(&ms, c->sev[i], c->sev[i + 1]));
-        c->stage_ms[i] += ms;
-    }
-    c->stage_batches += 1;
-    c->stage_passes += n ? plan.n_passes : 0;
-    c->stage_kmers += n;
-    c->n_kmers_total += n;
+    sl.res = out;
+    sl.n = n;
+    sl.n_passes = n ? plan.n_passes : 0;
+    sl.pending = true;
+    c->submitted += 1;
     KASA_API_END(c)
+}
+
+int kasa_identify_wait(kasa_ctx *c)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
+    KASA_REQUIRE(c->submitted > c->completed, KASA_ERR_STATE, "kasa_identify_wait without a submitted batch");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    finish_slot(c, c->slot[c->completed & 1]);
+    KASA_API_END(c)
+}
+
+int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_result *out)
+{
+    KASA_REQUIRE_PLAIN(c && in && out);
+    while (c->submitted > c->completed) {
+        int rc = kasa_identify_wait(c);
+        if (rc != KASA_OK) return rc;
+    }
+    int rc = kasa_identify_submit(c, in, out);
+    if (rc != KASA_OK) {                                   // nothing stays in flight after a failed synchronous call
+        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->cs_in); cudaStreamSynchronize(c->cs_out);
+        return rc;
+    }
+    return kasa_identify_wait(c);
 }
 
 int kasa_identify_finish(kasa_ctx *c, double *count_all, uint64_t *count_unique, uint64_t *n_kmers_total)
@@ -582,6 +686,7 @@ int kasa_identify_finish(kasa_ctx *c, double *count_all, uint64_t *count_unique,
     KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
     KASA_REQUIRE(c->idx_lo, KASA_ERR_STATE, "kasa_identify_finish before an index was loaded");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    while (c->submitted > c->completed) finish_slot(c, c->slot[c->completed & 1]);
     const size_t cells = (size_t)c->num_k * c->n_taxa;
     if (count_all) KASA_CUDA_TRY(cudaMemcpyAsync(count_all, c->d_tot_all, cells * 8, cudaMemcpyDeviceToHost, c->stream));
     if (count_unique) KASA_CUDA_TRY(cudaMemcpyAsync(count_unique, c->d_tot_un, cells * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -715,7 +820,10 @@ int kasa_dbg_extract(kasa_ctx *c, const kasa_read_batch *in, uint64_t *kmers_lo,
     KASA_API_BEGIN
     KASA_REQUIRE(c && in && kmers_lo && n_kmers, KASA_ERR_ARG, "null argument");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
-    const uint64_t n = extract_batch(c, in);
+    const uint32_t *first_dev = nullptr;
+    const uint64_t n = extract_batch(c, in, c->slot[0], &first_dev);
+    KASA_CUDA_TRY(cudaEventRecord(c->slot[0].in_free, c->stream));
+    c->slot[0].in_free_set = true;
     *n_kmers = n;
     if (n) {
         KASA_CUDA_TRY(cudaMemcpyAsync(kmers_lo, c->sb.w0[0], n * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -222,31 +222,44 @@ int run_identify(const Args &a)
     }
     const int frames = a.six ? 6 : 3;
     uint64_t n_kmers_total = 0, read_no = 0;
-    std::vector<float> scores;
-    std::string chars, o;
-    std::vector<uint64_t> starts;
-    std::vector<uint32_t> lens, first;
+    // two host batches in flight (kasa_identify_submit / _wait): while the device works on batch i, batch i-1's
+    // per-read output is formatted and written here
+    struct HostBatch {
+        std::string chars;
+        std::vector<uint64_t> starts;
+        std::vector<uint32_t> lens, first;
+        std::vector<float> scores;
+        kasa_batch_result res{};
+        size_t b = 0, e = 0;
+    } hb[2];
+    std::string o;
     std::vector<Hit> hits(T);
-    for (size_t b = 0; b < reads.size(); b += per_batch) {
+    auto submit = [&](HostBatch &h, size_t b) {
         const size_t e = std::min(reads.size(), b + per_batch);
-        chars.clear(); starts.clear(); lens.clear(); first.clear();
+        h.b = b; h.e = e;
+        h.chars.clear(); h.starts.clear(); h.lens.clear(); h.first.clear();
         for (size_t r = b; r < e; ++r) {
-            first.push_back((uint32_t)starts.size());
+            h.first.push_back((uint32_t)h.starts.size());
             for (int m = 0; m < (paired ? 2 : 1); ++m) {
                 const std::string &s = (m ? mates[r] : reads[r]).seq;
-                starts.push_back(chars.size()); lens.push_back((uint32_t)s.size()); chars += s;
+                h.starts.push_back(h.chars.size()); h.lens.push_back((uint32_t)s.size()); h.chars += s;
             }
         }
-        first.push_back((uint32_t)starts.size());
+        h.first.push_back((uint32_t)h.starts.size());
         kasa_read_batch in{};
-        in.n_reads = (uint32_t)(e - b); in.n_seqs = (uint32_t)starts.size(); in.format = KASA_SEQ_ASCII; in.location = KASA_MEM_HOST;
-        in.bases = chars.data(); in.seq_start = starts.data(); in.seq_len = lens.data(); in.read_first_seq = first.data();
-        kasa_batch_result res{};
-        scores.assign(a.rtt.empty() ? 0 : (e - b) * T, 0.f);
-        res.scores = scores.empty() ? nullptr : scores.data(); res.scores_location = KASA_MEM_HOST;
-        check(kasa_identify_batch(ctx, &in, &res), ctx);
-        n_kmers_total += res.n_kmers;
-        if (a.rtt.empty()) { read_no += e - b; continue; }
+        in.n_reads = (uint32_t)(e - b); in.n_seqs = (uint32_t)h.starts.size(); in.format = KASA_SEQ_ASCII; in.location = KASA_MEM_HOST;
+        in.bases = h.chars.data(); in.seq_start = h.starts.data(); in.seq_len = h.lens.data(); in.read_first_seq = h.first.data();
+        h.res = kasa_batch_result{};
+        h.scores.assign(a.rtt.empty() ? 0 : (e - b) * T, 0.f);
+        h.res.scores = h.scores.empty() ? nullptr : h.scores.data(); h.res.scores_location = KASA_MEM_HOST;
+        check(kasa_identify_submit(ctx, &in, &h.res), ctx);
+    };
+    auto emit = [&](HostBatch &h) {
+        check(kasa_identify_wait(ctx), ctx);
+        const size_t b = h.b, e = h.e;
+        const std::vector<float> &scores = h.scores;
+        n_kmers_total += h.res.n_kmers;
+        if (a.rtt.empty()) { read_no += e - b; return; }
         // ---- per-read output (Compare.hpp:1485-1890)
         for (size_t r = b; r < e; ++r, ++read_no) {
             std::string name = reads[r].name + " ";
@@ -338,7 +351,13 @@ int run_identify(const Args &a)
             }
             out << o;
         }
+    };
+    size_t nb = 0;
+    for (size_t b = 0; b < reads.size(); b += per_batch, ++nb) {
+        submit(hb[nb & 1], b);
+        if (nb >= 1) emit(hb[(nb - 1) & 1]);
     }
+    if (nb >= 1) emit(hb[(nb - 1) & 1]);
     if (!a.rtt.empty() && a.format == "json") out << "\n]";
     out.close();
 

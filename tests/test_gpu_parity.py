@@ -278,3 +278,31 @@ def test_synth_generators_match_numpy():
     r = ctx.synth_reads(3, 4, 1000, 500, 7, 5000, 150)
     assert np.array_equal(r, synth.reads_ascii(3, 4, 1000, 500, 7, 5000, 150))
     ctx.close()
+
+
+def test_pipelined_submit_wait_matches_batch_calls():
+    """kasa_identify_submit / _wait (two batches in flight, copies on their own streams) == kasa_identify_batch."""
+    reads = _k12_reads()
+    idx = G.index("k12")
+    _, taxids, _ = G.content("k12")
+    chunks = [reads[i:i + 97] for i in range(0, len(reads), 97)]
+    outs = []
+    for mode in ("batch", "stream"):
+        ctx = _ctx(frames=6, k_high=12, k_low=7)
+        ctx.load_index(idx, taxids)
+        if mode == "batch":
+            res = [ctx.identify_batch(c) for c in chunks]
+        else:
+            res = list(ctx.identify_stream(chunks))
+        ca, cu, n = ctx.identify_finish()
+        outs.append((res, ca, cu, n))
+        ctx.close()
+    (ra, ca_a, cu_a, n_a), (rb, ca_b, cu_b, n_b) = outs
+    assert n_a == n_b and np.array_equal(cu_a, cu_b) and np.array_equal(ca_a, ca_b)
+    for (na, sa, _), (nb, sb, _) in zip(ra, rb):
+        assert na == nb and np.array_equal(sa, sb)
+    ctx = _ctx(frames=6, k_high=12, k_low=7)
+    ctx.load_index(idx, taxids)
+    with pytest.raises(KasaError):
+        ctx.identify_wait()                                   # nothing submitted
+    ctx.close()
