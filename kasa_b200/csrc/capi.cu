@@ -514,12 +514,7 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
     PackedSeqs ps{};
     ps.n_seqs = ns;
     ps.seq_len = seq_len;
-    if (in->format == KASA_SEQ_ASCII) {
-        launch_pack_sizes(c->stream, seq_len, ns, c->d_pstart, &c->launches);
-        exclusive_scan_u64(c->stream, c->d_pstart, ns, c->d_scan_tmp, &c->launches);
-        launch_pack_ascii(c->stream, ascii, seq_start, seq_len, ns, c->d_pstart, c->d_bases2, c->d_nmask, &c->launches);
-        ps.bases2 = c->d_bases2; ps.nmask = c->d_nmask; ps.seq_start = c->d_pstart;
-    } else {
+    if (in->format == KASA_SEQ_PACKED2) {
         KASA_REQUIRE(in->nmask, KASA_ERR_ARG, "PACKED2 input needs the non-ACGT plane");
         if (in->location == KASA_MEM_HOST) {              // packed planes are not double-buffered: copied in stream order
             uint64_t total = host_total_bases(in->seq_start, in->seq_len, ns);
@@ -538,7 +533,10 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
     const uint64_t n = read_u64(c, c->d_koff + ns);
     KASA_REQUIRE(n <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "batch yields more k-mers than max_batch_kmers");
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[1], c->stream));
-    launch_extract_identify(c->stream, ps, kp, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
+    if (in->format == KASA_SEQ_ASCII)
+        launch_extract_identify_ascii(c->stream, ascii, seq_start, seq_len, ns, kp, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
+    else
+        launch_extract_identify(c->stream, ps, kp, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     return n;
 }

@@ -81,46 +81,87 @@ __device__ __forceinline__ uint32_t code_at(const uint32_t *__restrict__ b2, con
     return isn ? 5u : (strand ? (two ^ 2u) : two);            // complement A0<->T2, C1<->G3 (kASA.hpp:54)
 }
 
-template <bool WIDE>
-__global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(PackedSeqs seqs, KmerParams p,
+// One warp per sequence.  For each strand and each segment of kSegR output positions:
+//   1. base codes of the prepared string (read / reverse complement + 'X' marker, Read.hpp:612-695) into shared
+//      memory — straight from the ASCII bytes (coalesced byte loads, cleaning of Read.hpp:657-675 on the fly) or
+//      from the 2-bit planes;
+//   2. letters: aa[j] = codon table[c_j, c_j+1, c_j+2];
+//   3. rolling k-mers: lane l owns 8 positions of one reading frame (j0, j0+3, ...): the first k-mer is assembled
+//      from K letters, each following one is (kmer << 5 | next letter) & mask — 3 instructions instead of 3 K;
+//   4. the segment's k-mers leave through shared memory as coalesced 8-byte stores; inst[i] = i.
+constexpr int kRoll = 8;                         // same-frame positions per lane
+constexpr int kSegR = 30 * kRoll;                // 240 output positions per segment (lanes 30, 31 only load / store)
+
+template <bool WIDE, bool ASCII>
+__global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(PackedSeqs seqs, const char *__restrict__ ascii,
+                                                                              const uint64_t *__restrict__ astart, KmerParams p,
                                                                               const uint64_t *__restrict__ koff,
                                                                               uint64_t *__restrict__ key_lo,
                                                                               uint64_t *__restrict__ key_hi,
                                                                               uint32_t *__restrict__ inst)
 {
-    __shared__ uint8_t s_aa[kExtractWarps][kSeg + kAaPad];
+    __shared__ uint8_t s_code[kExtractWarps][kSegR + kAaPad + 8];
+    __shared__ uint8_t s_aa[kExtractWarps][kSegR + kAaPad];
+    __shared__ uint64_t s_klo[kExtractWarps][kSegR];
+    __shared__ uint64_t s_khi[WIDE ? kExtractWarps : 1][WIDE ? kSegR : 1];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t s = blockIdx.x * kExtractWarps + w;
     if (s >= seqs.n_seqs) return;
     const uint32_t L = seqs.seq_len[s];
-    const uint64_t start = seqs.seq_start[s];
+    const uint64_t start = ASCII ? astart[s] : seqs.seq_start[s];
     const int K = p.K;
     const uint32_t n = (uint32_t)kmer_count((uint64_t)L + 3u * (K - p.k_low), K);
     if (n == 0) return;
     const uint64_t out0 = koff[s];
-    uint8_t *aa = s_aa[w];
+    uint8_t *code = s_code[w], *aa = s_aa[w];
+    const uint64_t mask_lo = WIDE ? ~0ull : ((1ull << (5 * K)) - 1);
+    const uint64_t mask_hi = WIDE ? ((1ull << (5 * K - 64)) - 1) : 0ull;
+    const int j0 = (lane / 3) * (3 * kRoll) + (lane % 3);
     for (int strand = 0; strand < p.strands; ++strand) {
         const uint64_t obase = out0 + (uint64_t)strand * n;
-        for (uint32_t p0 = 0; p0 < n; p0 += kSeg) {
-            const uint32_t cnt = min((uint32_t)kSeg, n - p0);
+        for (uint32_t p0 = 0; p0 < n; p0 += kSegR) {
+            const uint32_t cnt = min((uint32_t)kSegR, n - p0);
             const uint32_t naa = cnt + 3 * (K - 1);
-            for (uint32_t j = lane; j < naa; j += 32) {
-                uint32_t pos = p0 + j;
-                uint32_t c0 = code_at(seqs.bases2, seqs.nmask, start, L, strand, pos);
-                uint32_t c1 = code_at(seqs.bases2, seqs.nmask, start, L, strand, pos + 1);
-                uint32_t c2 = code_at(seqs.bases2, seqs.nmask, start, L, strand, pos + 2);
-                aa[j] = c_aa[c0 << 6 | c1 << 3 | c2];
+            for (uint32_t j = lane; j < naa + 2; j += 32) {
+                const uint32_t pos = p0 + j;
+                uint32_t c;
+                if (!ASCII) c = code_at(seqs.bases2, seqs.nmask, start, L, strand, pos);
+                else if (pos >= L) c = 4u;                                      // marker / padding 'X'
+                else {
+                    const char ch = ascii[start + (strand ? (L - 1 - pos) : pos)];
+                    // Read.hpp:657-675: only ACGTacgt survive, everything else becomes 'Z'
+                    const bool ok = (ch == 'A') | (ch == 'C') | (ch == 'G') | (ch == 'T') | (ch == 'a') | (ch == 'c') | (ch == 'g') | (ch == 't');
+                    const uint32_t two = (uint32_t)(ch & 14) >> 1;              // kASA.hpp:70-75: A0 C1 T2 G3
+                    c = ok ? (strand ? (two ^ 2u) : two) : 5u;                  // complement A0<->T2, C1<->G3 (kASA.hpp:54)
+                }
+                code[j] = (uint8_t)c;
             }
             __syncwarp();
-            for (uint32_t j = lane; j < cnt; j += 32) {
+            for (uint32_t j = lane; j < naa; j += 32) aa[j] = c_aa[(uint32_t)code[j] << 6 | (uint32_t)code[j + 1] << 3 | code[j + 2]];
+            __syncwarp();
+            if (lane < 30 && (uint32_t)j0 < cnt) {
                 uint64_t lo = 0, hi = 0;
                 for (int i = 0; i < K; ++i) {
                     if (WIDE) hi = (hi << 5) | (lo >> 59);
-                    lo = (lo << 5) | aa[j + 3 * i];
+                    lo = (lo << 5) | aa[j0 + 3 * i];
                 }
+                s_klo[w][j0] = lo;
+                if (WIDE) s_khi[w][j0] = hi;
+#pragma unroll
+                for (int t = 1; t < kRoll; ++t) {
+                    const int j = j0 + 3 * t;
+                    if ((uint32_t)j >= cnt) break;
+                    if (WIDE) hi = ((hi << 5) | (lo >> 59)) & mask_hi;
+                    lo = ((lo << 5) | aa[j + 3 * (K - 1)]) & mask_lo;
+                    s_klo[w][j] = lo;
+                    if (WIDE) s_khi[w][j] = hi;
+                }
+            }
+            __syncwarp();
+            for (uint32_t j = lane; j < cnt; j += 32) {
                 const uint64_t o = obase + p0 + j;
-                key_lo[o] = lo;
-                if (WIDE) key_hi[o] = hi;
+                key_lo[o] = s_klo[w][j];
+                if (WIDE) key_hi[o] = s_khi[w][j];
                 inst[o] = (uint32_t)o;
             }
             __syncwarp();
@@ -196,9 +237,23 @@ void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, cons
     if (!seqs.n_seqs) return;
     unsigned grid = div_up(seqs.n_seqs, (uint32_t)kExtractWarps);
     if (p.K > 12)
-        extract_identify_kernel<true><<<grid, kExtractWarps * 32, 0, s>>>(seqs, p, koff, key_lo, key_hi, inst);
+        extract_identify_kernel<true, false><<<grid, kExtractWarps * 32, 0, s>>>(seqs, nullptr, nullptr, p, koff, key_lo, key_hi, inst);
     else
-        extract_identify_kernel<false><<<grid, kExtractWarps * 32, 0, s>>>(seqs, p, koff, key_lo, key_hi, inst);
+        extract_identify_kernel<false, false><<<grid, kExtractWarps * 32, 0, s>>>(seqs, nullptr, nullptr, p, koff, key_lo, key_hi, inst);
+    ++*launches;
+}
+
+void launch_extract_identify_ascii(cudaStream_t s, const char *ascii, const uint64_t *ascii_start, const uint32_t *seq_len,
+                                   uint32_t n_seqs, KmerParams p, const uint64_t *koff, uint64_t *key_lo, uint64_t *key_hi,
+                                   uint32_t *inst, uint64_t *launches)
+{
+    if (!n_seqs) return;
+    PackedSeqs seqs{nullptr, nullptr, nullptr, seq_len, n_seqs};
+    unsigned grid = div_up(n_seqs, (uint32_t)kExtractWarps);
+    if (p.K > 12)
+        extract_identify_kernel<true, true><<<grid, kExtractWarps * 32, 0, s>>>(seqs, ascii, ascii_start, p, koff, key_lo, key_hi, inst);
+    else
+        extract_identify_kernel<false, true><<<grid, kExtractWarps * 32, 0, s>>>(seqs, ascii, ascii_start, p, koff, key_lo, key_hi, inst);
     ++*launches;
 }
 

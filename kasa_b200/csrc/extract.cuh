@@ -38,6 +38,11 @@ void launch_kmer_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs
 void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint64_t *koff, uint64_t *key_lo,
                              uint64_t *key_hi, uint32_t *inst, uint64_t *launches);
 
+// the same straight from raw ASCII sequences (KASA_SEQ_ASCII): cleaning, strands and markers on the fly, no packed copy
+void launch_extract_identify_ascii(cudaStream_t s, const char *ascii, const uint64_t *ascii_start, const uint32_t *seq_len,
+                                   uint32_t n_seqs, KmerParams p, const uint64_t *koff, uint64_t *key_lo, uint64_t *key_hi,
+                                   uint32_t *inst, uint64_t *launches);
+
 // build: one slot per window of each prepared ASCII string; windows holding '_' (31) or giving k-mer 0
 // get the sentinel key ~0 (dropped after the sort): Read.hpp:2016-2024, 2048-2059, 2097, 2122
 void launch_build_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, int K, uint64_t *woff, uint64_t *launches);

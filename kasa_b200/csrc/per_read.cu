@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(kTxBlock) per_read_taxon_kernel(const uint4 *_
             uint32_t rare_mask;
             {
                 const uint64_t s = c0 + lane;
+                if (s + 32 < s1) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 2 * (s + 32)));   // next chunk
                 uint64_t R0 = 0, R1 = 0, R2 = 0, np = 0;
                 if (s < s1) {
                     const uint4 x0 = __ldg(rec + 2 * s), x1 = __ldg(rec + 2 * s + 1);
@@ -143,11 +144,12 @@ __global__ void __launch_bounds__(kTxBlock) per_read_taxon_kernel(const uint4 *_
                 const int i = __ffs((int)m) - 1;
                 const uint64_t np = s_rec[w][3][i];
                 const int h0 = (int)((uint32_t)(fw0[i] >> sh0) & 7u), h1 = (int)((uint32_t)(fw1[i] >> sh1) & 7u);
+                uint64_t lv = (np >> 8) & 0x00fefefefefefefeull;                   // a bit in byte j-1 <=> |taxa_j| >= 2
 #pragma unroll 1
-                for (int j = 1; j < NK; ++j) {
-                    const uint32_t nj = (uint32_t)(np >> (8 * j)) & 255u;
-                    if (nj < 2) continue;                                          // warp-uniform
-                    const uint32_t v = s_invfx[nj & 127u];
+                while (lv) {                                                       // warp-uniform: np is a broadcast
+                    const int j = ((__ffsll((long long)lv) - 1) >> 3) + 1;
+                    lv &= ~(0xffull << (8 * (j - 1)));
+                    const uint32_t v = s_invfx[(uint32_t)(np >> (8 * j)) & 127u];
                     if (h0 > j) s_fr[w][j * 64 + my[0]] += v;
                     if (own1 && h1 > j) s_fr[w][j * 64 + my[1]] += v;
                 }
