@@ -89,8 +89,8 @@ __device__ __forceinline__ uint32_t code_at(const uint32_t *__restrict__ b2, con
 //   3. rolling k-mers: lane l owns 8 positions of one reading frame (j0, j0+3, ...): the first k-mer is assembled
 //      from K letters, each following one is (kmer << 5 | next letter) & mask — 3 instructions instead of 3 K;
 //   4. the segment's k-mers leave through shared memory as coalesced 8-byte stores; inst[i] = i.
-constexpr int kRoll = 8;                         // same-frame positions per lane
-constexpr int kSegR = 30 * kRoll;                // 240 output positions per segment (lanes 30, 31 only load / store)
+constexpr int kRoll = 5;                         // same-frame positions per lane
+constexpr int kSegR = 30 * kRoll;                // 150 output positions per segment: one segment per strand of a 150 bp read
 
 template <bool WIDE, bool ASCII>
 __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(PackedSeqs seqs, const char *__restrict__ ascii,

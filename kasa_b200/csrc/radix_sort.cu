@@ -8,6 +8,7 @@ namespace {
 constexpr uint64_t kFlagAgg = 1ull << 62;    // tile aggregate published
 constexpr uint64_t kFlagIncl = 2ull << 62;   // inclusive prefix published
 constexpr uint64_t kValMask = (1ull << 62) - 1;
+constexpr int kLookBatch = 2;                // predecessor status words requested per look-back round trip
 constexpr uint32_t kSpinLimit = 1u << 22;    // watchdog: ~seconds, never reached when healthy
 
 struct PlanDev {
@@ -89,9 +90,11 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
     __shared__ uint64_t s_gbase[kRadix];
     __shared__ uint32_t s_wsum[kRadix / 32];
     __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_cnt[kRadix];
 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);   // ticket order = start order: predecessors are resident or done
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    if (tid < kRadix) s_cnt[tid] = 0;   // ticket order = start order: predecessors are resident or done
     for (int j = lane; j < kRadix; j += 32) s_hist[w * kRadix + j] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -109,6 +112,19 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
         if (src == SRC_W0) key[i] = ok ? ldg_stream(in_w0 + idx) : ~0ull;
         else if (HAS_W1 && src == SRC_W1) key[i] = ok ? ldg_stream(in_w1 + idx) : ~0ull;
         else key[i] = ok ? (uint64_t)ldg_stream(in_v + idx) : ~0ull;
+    }
+
+    // ---- the tile's digit counts first (shared-memory atomics) and out to the status word: successors doing their
+    // look-back need nothing else from this tile, so its ranking below is off their critical path
+    {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) atomicAdd(&s_cnt[(uint32_t)(key[i] >> shift) & mask], 1u);
+        __syncthreads();
+        if (tid < kRadix) {
+            uint32_t c = s_cnt[tid];
+            if ((uint32_t)tid == mask) c -= (uint32_t)(TILE - n_tile);               // padding sorts last inside digit `mask`
+            st_relaxed_gpu(status + (uint64_t)tile * kRadix + tid, (tile == 0 ? kFlagIncl : kFlagAgg) | (uint64_t)c);
+        }
     }
 
     // ---- rank inside the warp, digit by digit (match-any multisplit); padding keys carry digit `mask`
@@ -191,26 +207,35 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
         const uint32_t dbase = incl - count + s_wsum[w];
         uint64_t *my = status + (uint64_t)tile * kRadix + tid;
         uint64_t excl = 0;
-        if (tile == 0) {
-            st_relaxed_gpu(my, kFlagIncl | (uint64_t)count);
-        } else {
-            st_relaxed_gpu(my, kFlagAgg | (uint64_t)count);
+        if (tile != 0) {
+            // predecessors are read kLookBatch at a time (independent loads in flight); tiles before the first count
+            // as "inclusive, 0"; an unpublished word restarts the batch at that tile
             int64_t t = (int64_t)tile - 1;
             uint32_t spins = 0;
-            while (true) {
-                uint64_t s = ld_relaxed_gpu(status + (uint64_t)t * kRadix + tid);
-                uint64_t f = s >> 62;
-                if (f == 0) {
+            bool done = false;
+            while (!done) {
+                uint64_t sv[kLookBatch];
+#pragma unroll
+                for (int k = 0; k < kLookBatch; ++k)
+                    sv[k] = (t - k >= 0) ? ld_relaxed_gpu(status + (uint64_t)(t - k) * kRadix + tid) : kFlagIncl;
+                int used = 0;
+#pragma unroll
+                for (int k = 0; k < kLookBatch; ++k) {
+                    const uint64_t f = sv[k] >> 62;
+                    if (!done && used == k && f != 0) {
+                        excl += sv[k] & kValMask;
+                        ++used;
+                        if (f == 2) done = true;
+                    }
+                }
+                t -= used;
+                if (!done && used < kLookBatch) {               // ran into a tile that has not published yet
                     if (++spins > kSpinLimit || ((spins & 1023u) == 0 && *(volatile uint32_t *)err_flag)) {
                         atomicExch(err_flag, 1u);
                         break;
                     }
                     __nanosleep(20);
-                    continue;
                 }
-                excl += s & kValMask;
-                if (f == 2 || t == 0) break;
-                --t;
             }
             st_relaxed_gpu(my, kFlagIncl | (excl + count));
         }
