@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--taxa", type=int, default=50)
     ap.add_argument("--genome-len", type=int, default=33_400_000)
     ap.add_argument("--reads-per-step", type=int, default=6_700_000)
+    ap.add_argument("--sharding", default="replicate", choices=["replicate", "prefix"],
+                    help="replicate: index copied to every GPU, reads sharded (default, SURVEY.md §8e mode 1); prefix: index "
+                         "sharded by k-mer prefix range as well, match records exchanged over NVLink peer memory (mode 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-reads", type=int, default=200_000)
@@ -189,10 +192,16 @@ def main_reference(args):
 
 
 def workload_config(args, reads_per_step):
-    return {"workload": "C2: identify k=12..7 --six, %d bp reads vs k=12 index of %d taxa x %d bp (index replicated, reads sharded)"
-                        % (READ_LEN, args.taxa, args.genome_len),
+    how = ("index sharded by k-mer prefix range, reads sharded, match records over NVLink peer memory" if args.sharding == "prefix"
+           else "index replicated, reads sharded")
+    return {"workload": "C2: identify k=12..7 --six, %d bp reads vs k=12 index of %d taxa x %d bp (%s)"
+                        % (READ_LEN, args.taxa, args.genome_len, how), "sharding": args.sharding,
             "reads_per_step_per_gpu": reads_per_step, "kmers_per_read": KMERS_PER_READ,
             "l2_policy": "inputs larger than L2 (each step streams > 10 GB; a fresh read batch per step)"}
+
+
+# dram bytes per record of one radix pass, from the committed ncu capture (profiles/r01_ncu_onesweep_kernel.txt)
+NCU_SORT_PASS_DRAM_BYTES_PER_RECORD = (3.121386e9 + 3.192160e9) / 2.6e8
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -209,9 +218,12 @@ def main_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dist = None
-    if world > 1:
+    prefix = args.sharding == "prefix"
+    if world > 1 or prefix:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
     R = args.reads_per_step
     n_windows = args.taxa * (args.genome_len + 33)
@@ -228,7 +240,13 @@ def main_ours(args):
     ctx.synth_build_reference(GENOME_SEED, args.taxa, args.genome_len)
     n_entries, n_trie = ctx.build_finish(fetch=False)
     taxids = np.array([0] + [1000 + t for t in range(args.taxa)], dtype=np.uint32)
-    ctx.index_from_build(taxids)
+    group = None
+    if prefix:
+        from kasa_b200.dist import ShardGroup
+        entry_begin, prefix_begin = ctx.index_from_build_shard(taxids, rank, world)     # keep 1/world of the index
+        group = ShardGroup(ctx, dist, prefix_begin, torch.device("cuda", local))
+    else:
+        ctx.index_from_build(taxids)
     build_s = time.perf_counter() - t0
     T = len(taxids)
 
@@ -249,7 +267,10 @@ def main_ours(args):
         buf = dev_reads[step % n_dev_batches]
         rb = capi.CReadBatch(R, R, capi.SEQ_ASCII, capi.MEM_DEVICE, buf.data_ptr(), None, seq_start.data_ptr(), seq_len.data_ptr(), None)
         res = capi.CBatchResult(0, None, capi.MEM_DEVICE, 0.0)
-        ctx.identify_batch_raw(rb, res)
+        if group is not None:
+            group.identify_batch_raw(rb, res)
+        else:
+            ctx.identify_batch_raw(rb, res)
         return res
 
     def barrier():
@@ -296,7 +317,10 @@ def main_ours(args):
     kmers_per_batch = stage_kmers / max(1, n_batches)
     achieved = BYTES_SORT_PASS * kmers_per_batch / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "onesweep_kernel (one 8-bit LSD radix pass over 12-byte records)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_SORT_PASS_DRAM_BYTES_PER_RECORD * kmers_per_batch,
+                "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one onesweep_kernel launch "
+                                  "(profiles/r01_ncu_onesweep_kernel.txt: 6.314 GB for 2.6e8 records), scaled per record to this launch",
                 "peak_source": peak_src, "bytes_per_unit": BYTES_SORT_PASS, "units_per_launch": kmers_per_batch,
                 "avg_launch_ms": pass_ms, "share_of_step": stages["sort_passes"] / max(1e-9, sum(stages.values())),
                 "whole_step_model": {"bytes_per_lookup": BYTES_PER_LOOKUP_MODEL + 12.0 * n_entries / max(1.0, kmers_per_batch),
@@ -321,6 +345,13 @@ def main_ours(args):
             """the production loop of the C ABI: kasa_identify_submit / kasa_identify_wait, two batches in flight — the
             next batch's host->device copy and the previous batch's score read-back overlap the kernels"""
             keep = []
+            for step in range(n_steps if group is not None else 0):        # prefix-sharded: one batch at a time
+                buf = host_reads[step % n_host]
+                rb = capi.CReadBatch(R, R, capi.SEQ_ASCII, capi.MEM_HOST, buf.data_ptr(), None, h_start.ctypes.data, h_len.ctypes.data, None)
+                res = capi.CBatchResult(0, host_scores[step % 2].data_ptr(), capi.MEM_HOST, 0.0)
+                group.identify_batch_raw(rb, res)
+            if group is not None:
+                return
             for step in range(n_steps):
                 buf = host_reads[step % n_host]
                 rb = capi.CReadBatch(R, R, capi.SEQ_ASCII, capi.MEM_HOST, buf.data_ptr(), None, h_start.ctypes.data, h_len.ctypes.data, None)
@@ -345,7 +376,8 @@ def main_ours(args):
         e2e = {"value": reads_total / (e2e_ms * 1e-3), "unit": "reads/s",
                "h2d_bytes_per_step": int(R * READ_LEN + R * 12), "d2h_bytes_per_step": int(R * T * 4),
                "ms_per_step": e2e_ms / args.steps, "checksum": float(host_scores[(args.steps - 1) % 2][: T * 1000].sum()),
-               "api": "kasa_identify_submit/_wait (2 batches in flight, pinned host buffers)"}
+               "api": ("kasa_shard_sort/_lookup/_score per batch (pinned host buffers)" if group is not None else
+                       "kasa_identify_submit/_wait (2 batches in flight, pinned host buffers)")}
 
     # ---- job epilogue: reduce the per-taxon counts across ranks (the only collective of this path)
     ca, cu, total_kmers = ctx.identify_finish()
@@ -366,6 +398,7 @@ def main_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(args, R), "index_entries": int(n_entries), "index_gb": n_entries * 12 / 1e9,
+            "index_entries_this_gpu": int(ctx.index_size),
             "index_build_s": build_s, "stage_ms_per_step": stage_ms, "gpu_ms_per_step_lib": gpu_ms_sum / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "identified_frac_k12": float(ca[0].sum() / max(1, total_kmers)),

@@ -164,6 +164,62 @@ int kasa_identify_wait(kasa_ctx *ctx);
 int kasa_identify_finish(kasa_ctx *ctx, double *count_all, uint64_t *count_unique, uint64_t *n_kmers_total);
 
 /* --------------------------------------------------------------------------------------------------- */
+/* identify against a PREFIX-SHARDED index (SURVEY.md §8e mode 2: one context per GPU, every context holds the
+ * index entries of one k-mer prefix range AND its own read batches).
+ *
+ * Replaces: the reference's "index does not fit memory" route — Trie::GetIndexRange per query (Trie.hpp:494-520)
+ * into an STXXL-paged index file (Compare.hpp:3130-3160): here the range owner is another GPU and the pages are
+ * reached over NVLink.  There is no staging all-to-all: after a context has sorted its batch, the owner of a prefix
+ * range runs the lookup kernel directly on the peer's sorted run (peer loads) and stores the 32-byte match records
+ * straight into the peer's record array (peer stores); the origin then scores its own reads as usual.  Host-side
+ * protocol per batch (the host exchanges the two small structs, e.g. with torch.distributed / MPI):
+ *     every rank:  kasa_shard_sort(ctx, in, &runs[rank])        -> all-gather `runs`
+ *     every rank:  kasa_shard_lookup(ctx, runs)                  -> barrier
+ *     every rank:  kasa_shard_score(ctx, &out)                   -> barrier before the next kasa_shard_sort
+ * Shard boundaries never split a group of k-mers sharing min(6, k_low) leading letters, so every level-k taxa set
+ * of SURVEY.md §3.1 lives on one shard and the results equal the unsharded ones (KASA_SCORE_FAST and NONE;
+ * KASA_SCORE_EXACT replays one global flush order and is rejected).                                            */
+
+#define KASA_MAX_SHARDS 16
+#define KASA_SHARD_NBUF 7          /* sort ping-pong w0[2], w1[2], v[2] and the match-record array              */
+
+typedef struct {
+    uint64_t pid;                  /* owner process: peers in the same process use `ptr`, others open `handle`  */
+    int32_t  device;
+    int32_t  reserved;
+    uint64_t ptr[KASA_SHARD_NBUF]; /* device addresses in the owner process (0 = buffer not used)               */
+    unsigned char handle[KASA_SHARD_NBUF][64];   /* cudaIpcMemHandle_t                                           */
+} kasa_shard_mem;
+
+typedef struct {
+    uint64_t n_kmers;              /* k-mers of the origin's batch                                              */
+    int32_t  cur;                  /* which half of the ping-pong holds the sorted run                          */
+    int32_t  reserved;
+    uint64_t begin[KASA_MAX_SHARDS + 1];   /* sorted positions: [begin[r], begin[r+1]) belongs to shard r       */
+} kasa_shard_runs;
+
+/* Host-only: cut a sorted index (file records as for kasa_index_load) into n_shards ranges of about equal size on
+ * boundaries of min(6, k_low)-letter prefixes.  entry_begin[n_shards+1] = record offsets; prefix_begin[n_shards+1] =
+ * the first 30-bit prefix (top six letters, the `_trie` key of Trie.hpp:371-386) of each shard, prefix_begin[0] = 0,
+ * prefix_begin[n_shards] = 2^30.                                                                               */
+int kasa_shard_plan(const void *entries, uint64_t n, int bits, int k_low, int n_shards,
+                    uint64_t *entry_begin, uint32_t *prefix_begin);
+
+/* The same plan for the index just built on this context (kasa_build_finish); keeps only shard `rank` of it in
+ * HBM as the context's index (like kasa_index_from_build).                                                     */
+int kasa_index_from_build_shard(kasa_ctx *ctx, const uint32_t *taxid_of_idx, uint32_t n_taxa, int rank, int n_shards,
+                                uint64_t *entry_begin, uint32_t *prefix_begin);
+
+/* Declare this context shard `rank` of n_shards (its index = the records [entry_begin[rank], entry_begin[rank+1]),
+ * loaded with kasa_index_load) and export its exchange buffers.                                                */
+int kasa_shard_init(kasa_ctx *ctx, int rank, int n_shards, const uint32_t *prefix_begin, kasa_shard_mem *mine);
+/* Map the peers' buffers (all[n_shards], all[rank] = mine).                                                    */
+int kasa_shard_connect(kasa_ctx *ctx, const kasa_shard_mem *all);
+int kasa_shard_sort(kasa_ctx *ctx, const kasa_read_batch *in, kasa_shard_runs *mine);
+int kasa_shard_lookup(kasa_ctx *ctx, const kasa_shard_runs *all);
+int kasa_shard_score(kasa_ctx *ctx, kasa_batch_result *out);
+
+/* --------------------------------------------------------------------------------------------------- */
 /* build                                                                                                */
 
 typedef struct {

@@ -28,7 +28,8 @@ EXPORTS = [
     "kasa_abi_version", "kasa_ctx_create", "kasa_ctx_destroy", "kasa_last_error", "kasa_ctx_set_stream",
     "kasa_ctx_synchronize", "kasa_ctx_launch_count", "kasa_ctx_stage_times", "kasa_index_load", "kasa_index_from_build", "kasa_index_size",
     "kasa_identify_batch", "kasa_identify_submit", "kasa_identify_wait", "kasa_identify_finish", "kasa_build_push", "kasa_build_finish", "kasa_build_fetch",
-    "kasa_build_frequency", "kasa_dbg_extract", "kasa_dbg_sort_pairs", "kasa_synth_build_reference", "kasa_synth_reads",
+    "kasa_shard_plan", "kasa_index_from_build_shard", "kasa_shard_init", "kasa_shard_connect", "kasa_shard_sort", "kasa_shard_lookup",
+    "kasa_shard_score", "kasa_build_frequency", "kasa_dbg_extract", "kasa_dbg_sort_pairs", "kasa_synth_build_reference", "kasa_synth_reads",
 ]
 
 
@@ -57,6 +58,18 @@ class CBatchResult(C.Structure):
 class CSeqBatch(C.Structure):
     _fields_ = [("n_seqs", C.c_uint32), ("location", C.c_int32), ("bases", C.c_void_p), ("seq_start", C.c_void_p),
                 ("seq_len", C.c_void_p), ("taxid", C.c_void_p)]
+
+
+MAX_SHARDS, SHARD_NBUF = 16, 7
+
+
+class CShardMem(C.Structure):
+    _fields_ = [("pid", C.c_uint64), ("device", C.c_int32), ("reserved", C.c_int32), ("ptr", C.c_uint64 * SHARD_NBUF),
+                ("handle", (C.c_ubyte * 64) * SHARD_NBUF)]
+
+
+class CShardRuns(C.Structure):
+    _fields_ = [("n_kmers", C.c_uint64), ("cur", C.c_int32), ("reserved", C.c_int32), ("begin", C.c_uint64 * (MAX_SHARDS + 1))]
 
 
 def library_path() -> str:
@@ -94,6 +107,13 @@ def load_library():
     L.kasa_identify_submit.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.POINTER(CBatchResult)]
     L.kasa_identify_wait.argtypes = [C.c_void_p]
     L.kasa_identify_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.kasa_shard_plan.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.kasa_index_from_build_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.kasa_shard_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(CShardMem)]
+    L.kasa_shard_connect.argtypes = [C.c_void_p, C.POINTER(CShardMem)]
+    L.kasa_shard_sort.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.POINTER(CShardRuns)]
+    L.kasa_shard_lookup.argtypes = [C.c_void_p, C.POINTER(CShardRuns)]
+    L.kasa_shard_score.argtypes = [C.c_void_p, C.POINTER(CBatchResult)]
     L.kasa_build_push.argtypes = [C.c_void_p, C.POINTER(CSeqBatch)]
     L.kasa_build_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.kasa_build_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -106,6 +126,19 @@ def load_library():
                                    C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
     _LIB = L
     return L
+
+
+def shard_plan(records: np.ndarray, k_low: int, n_shards: int):
+    """Host-only: cut a sorted index into n_shards prefix ranges (kasa_shard_plan) -> (entry_begin, prefix_begin)."""
+    L = load_library()
+    records = np.ascontiguousarray(records)
+    bits = 128 if records.dtype.itemsize == 20 else 64
+    eb = np.zeros(n_shards + 1, dtype=np.uint64)
+    pb = np.zeros(n_shards + 1, dtype=np.uint32)
+    rc = L.kasa_shard_plan(_ptr(records) if len(records) else None, len(records), bits, k_low, n_shards, _ptr(eb), _ptr(pb))
+    if rc != 0:
+        raise KasaError(rc, L.kasa_last_error(None).decode())
+    return eb, pb
 
 
 @dataclass
@@ -272,6 +305,50 @@ class Context:
         n = C.c_uint64(0)
         self._check(self.lib.kasa_identify_finish(self.h, _ptr(ca), _ptr(cu), C.byref(n)))
         return ca, cu, int(n.value)
+
+    # ---------------------------------------------------------------- prefix-sharded index (kasa_shard_*)
+    def index_from_build_shard(self, taxid_of_idx: np.ndarray, rank: int, n_shards: int):
+        """Keep shard `rank` of the index just built; -> (entry_begin u64[n_shards+1], prefix_begin u32[n_shards+1])."""
+        tax = np.ascontiguousarray(taxid_of_idx, dtype=np.uint32)
+        eb = np.zeros(n_shards + 1, dtype=np.uint64)
+        pb = np.zeros(n_shards + 1, dtype=np.uint32)
+        self._check(self.lib.kasa_index_from_build_shard(self.h, _ptr(tax), len(tax), rank, n_shards, _ptr(eb), _ptr(pb)))
+        self.n_taxa = len(tax)
+        return eb, pb
+
+    def shard_init(self, rank: int, n_shards: int, prefix_begin: np.ndarray) -> CShardMem:
+        pb = np.ascontiguousarray(prefix_begin, dtype=np.uint32)
+        assert len(pb) == n_shards + 1
+        mem = CShardMem()
+        self._check(self.lib.kasa_shard_init(self.h, rank, n_shards, _ptr(pb), C.byref(mem)))
+        return mem
+
+    def shard_connect(self, mems: list):
+        arr = (CShardMem * len(mems))(*mems)
+        self._check(self.lib.kasa_shard_connect(self.h, arr))
+
+    def shard_sort_raw(self, rb: CReadBatch) -> CShardRuns:
+        runs = CShardRuns()
+        self._check(self.lib.kasa_shard_sort(self.h, C.byref(rb), C.byref(runs)))
+        return runs
+
+    def shard_sort(self, seqs, read_first_seq=None):
+        rb, keep, n_reads = self._read_batch(seqs, read_first_seq)
+        return self.shard_sort_raw(rb), n_reads
+
+    def shard_lookup(self, runs: list):
+        arr = (CShardRuns * len(runs))(*runs)
+        self._check(self.lib.kasa_shard_lookup(self.h, arr))
+
+    def shard_score_raw(self, res: CBatchResult):
+        self._check(self.lib.kasa_shard_score(self.h, C.byref(res)))
+
+    def shard_score(self, n_reads: int):
+        want = self.params.score_mode != SCORE_NONE
+        scores = np.zeros((n_reads, self.n_taxa), dtype=np.float32) if want else None
+        res = CBatchResult(0, scores.ctypes.data if want and scores.size else None, MEM_HOST, 0.0)
+        self.shard_score_raw(res)
+        return int(res.n_kmers), scores, float(res.gpu_ms)
 
     # ---------------------------------------------------------------- build
     def build_push(self, strings: list[bytes], taxids):

@@ -1,4 +1,6 @@
 // capi.cu — the C ABI of include/kasa_b200.h: context, HBM layout, kernel orchestration.
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -13,6 +15,7 @@
 #include "lookup.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "shard.cuh"
 #include "synth.cuh"
 
 using namespace kasa;
@@ -76,6 +79,18 @@ struct kasa_ctx {
     uint64_t submitted = 0, completed = 0;
     double stage_ms[KASA_N_STAGES] = {};
     uint64_t stage_batches = 0, stage_passes = 0, stage_kmers = 0;
+    // prefix-sharded index (kasa_shard_*): this context is shard `rank` of `n`; peer[o][b] = shard o's exchange buffers
+    struct Shard {
+        bool on = false, connected = false;
+        int rank = 0, n = 1;
+        uint32_t *d_prefix_begin = nullptr;
+        uint64_t *d_begin = nullptr;
+        uint64_t peer[KASA_MAX_SHARDS][KASA_SHARD_NBUF] = {};
+        std::vector<void *> opened;                       // cudaIpcOpenMemHandle mappings
+        cudaEvent_t ev_score0 = nullptr;
+        int phase = 0;                                    // 0 idle, 1 sorted, 2 looked up
+        uint32_t n_reads = 0;
+    } sh;
 };
 
 namespace {
@@ -377,6 +392,8 @@ void kasa_ctx_destroy(kasa_ctx *c)
     if (!c) return;
     cudaSetDevice(c->p.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void *p : c->sh.opened) cudaIpcCloseMemHandle(p);
+    if (c->sh.ev_score0) cudaEventDestroy(c->sh.ev_score0);
     for (void *p : c->allocs) cudaFree(p);
     if (c->cs_in) { cudaStreamSynchronize(c->cs_in); cudaStreamDestroy(c->cs_in); }
     if (c->cs_out) { cudaStreamSynchronize(c->cs_out); cudaStreamDestroy(c->cs_out); }
@@ -693,6 +710,285 @@ int kasa_identify_finish(kasa_ctx *c, double *count_all, uint64_t *count_unique,
     KASA_CUDA_TRY(cudaMemsetAsync(c->d_tot_all, 0, cells * 8, c->stream));
     KASA_CUDA_TRY(cudaMemsetAsync(c->d_tot_un, 0, cells * 8, c->stream));
     c->n_kmers_total = 0;
+    KASA_API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prefix-sharded index (include/kasa_b200.h: kasa_shard_*)
+
+// top six letters of file record i (12-byte / 20-byte records, packedPairs.hpp:107-136)
+static uint32_t host_prefix30(const unsigned char *entries, uint64_t i, int bits, int K)
+{
+    uint64_t lo, hi = 0;
+    const unsigned char *p = entries + i * (bits == 128 ? 20 : 12);
+    std::memcpy(&lo, p, 8);
+    if (bits == 128) std::memcpy(&hi, p + 8, 8);
+    const int sh = 5 * K - 30;
+    return bits == 128 ? (uint32_t)(hi >> (sh - 64)) : (uint32_t)(lo >> sh);
+}
+
+int kasa_shard_plan(const void *entries, uint64_t n, int bits, int k_low, int n_shards, uint64_t *entry_begin, uint32_t *prefix_begin)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE((entries || n == 0) && entry_begin && prefix_begin, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(bits == 64 || bits == 128, KASA_ERR_ARG, "bits must be 64 or 128");
+    KASA_REQUIRE(n_shards >= 1 && n_shards <= KASA_MAX_SHARDS, KASA_ERR_ARG, "n_shards must be in [1, KASA_MAX_SHARDS]");
+    KASA_REQUIRE(k_low >= 1, KASA_ERR_ARG, "k_low must be >= 1");
+    const int K = bits == 128 ? 25 : 12;
+    const int align = std::min(6, k_low);
+    const uint32_t keep = ~((1u << (5 * (6 - align))) - 1u);
+    const unsigned char *e = static_cast<const unsigned char *>(entries);
+    entry_begin[0] = 0; prefix_begin[0] = 0;
+    for (int r = 1; r < n_shards; ++r) {
+        if (n == 0) { entry_begin[r] = 0; prefix_begin[r] = 1u << 30; continue; }
+        const uint64_t cand = (uint64_t)((unsigned __int128)n * (unsigned)r / (unsigned)n_shards);
+        const uint32_t p = host_prefix30(e, cand, bits, K) & keep;
+        uint64_t a = 0, b = n;
+        while (a < b) {
+            const uint64_t m = a + ((b - a) >> 1);
+            if (host_prefix30(e, m, bits, K) < p) a = m + 1; else b = m;
+        }
+        entry_begin[r] = a; prefix_begin[r] = p;
+    }
+    entry_begin[n_shards] = n; prefix_begin[n_shards] = 1u << 30;
+    KASA_API_END(nullptr)
+}
+
+static void shard_common_init(kasa_ctx *c, int rank, int n_shards, const uint32_t *prefix_begin)
+{
+    KASA_REQUIRE(n_shards >= 1 && n_shards <= KASA_MAX_SHARDS && rank >= 0 && rank < n_shards, KASA_ERR_ARG,
+                 "need 0 <= rank < n_shards <= KASA_MAX_SHARDS");
+    KASA_REQUIRE(c->p.score_mode != KASA_SCORE_EXACT, KASA_ERR_ARG,
+                 "KASA_SCORE_EXACT replays one global flush order and cannot run on a prefix-sharded index");
+    KASA_REQUIRE(c->sort_bits >= 30, KASA_ERR_ARG, "a prefix-sharded index needs the leading 30 k-mer bits sorted");
+    for (int r = 0; r < n_shards; ++r)
+        KASA_REQUIRE(prefix_begin[r] <= prefix_begin[r + 1], KASA_ERR_ARG, "prefix_begin must be non-decreasing");
+    KASA_REQUIRE(prefix_begin[0] == 0 && prefix_begin[n_shards] == (1u << 30), KASA_ERR_ARG, "prefix_begin must span [0, 2^30]");
+    ensure_workspace(c);
+    if (!c->sh.d_prefix_begin) {
+        c->sh.d_prefix_begin = dev_alloc<uint32_t>(c, KASA_MAX_SHARDS + 1);
+        c->sh.d_begin = dev_alloc<uint64_t>(c, KASA_MAX_SHARDS + 1);
+        KASA_CUDA_TRY(cudaEventCreate(&c->sh.ev_score0));
+    }
+    KASA_CUDA_TRY(cudaMemcpyAsync(c->sh.d_prefix_begin, prefix_begin, (n_shards + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->sh.on = true; c->sh.connected = false; c->sh.rank = rank; c->sh.n = n_shards; c->sh.phase = 0;
+}
+
+static void *const *shard_buffers(kasa_ctx *c, void *out[KASA_SHARD_NBUF])
+{
+    out[0] = c->sb.w0[0]; out[1] = c->sb.w0[1]; out[2] = c->sb.w1[0]; out[3] = c->sb.w1[1];
+    out[4] = c->sb.v[0]; out[5] = c->sb.v[1]; out[6] = c->d_rec;
+    return out;
+}
+
+int kasa_shard_init(kasa_ctx *c, int rank, int n_shards, const uint32_t *prefix_begin, kasa_shard_mem *mine)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && prefix_begin && mine, KASA_ERR_ARG, "null argument");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    shard_common_init(c, rank, n_shards, prefix_begin);
+    std::memset(mine, 0, sizeof(*mine));
+    mine->pid = (uint64_t)getpid();
+    mine->device = c->p.device;
+    void *buf[KASA_SHARD_NBUF];
+    shard_buffers(c, buf);
+    for (int b = 0; b < KASA_SHARD_NBUF; ++b) {
+        mine->ptr[b] = (uint64_t)(uintptr_t)buf[b];
+        if (!buf[b]) continue;
+        cudaIpcMemHandle_t h;
+        KASA_CUDA_TRY(cudaIpcGetMemHandle(&h, buf[b]));
+        static_assert(sizeof(h) <= 64, "cudaIpcMemHandle_t does not fit kasa_shard_mem::handle");
+        std::memcpy(mine->handle[b], &h, sizeof(h));
+    }
+    KASA_API_END(c)
+}
+
+int kasa_shard_connect(kasa_ctx *c, const kasa_shard_mem *all)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && all, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(c->sh.on, KASA_ERR_STATE, "kasa_shard_connect before kasa_shard_init");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    for (void *p : c->sh.opened) cudaIpcCloseMemHandle(p);
+    c->sh.opened.clear();
+    const uint64_t me = (uint64_t)getpid();
+    for (int o = 0; o < c->sh.n; ++o) {
+        const kasa_shard_mem &m = all[o];
+        if (m.pid == me && m.device != c->p.device) {       // same process, other GPU: plain peer access
+            int can = 0;
+            KASA_CUDA_TRY(cudaDeviceCanAccessPeer(&can, c->p.device, m.device));
+            KASA_REQUIRE(can, KASA_ERR_CUDA, "no peer access between device " + std::to_string(c->p.device) + " and " + std::to_string(m.device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(m.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) KASA_CUDA_TRY(e);
+            cudaGetLastError();
+        }
+        for (int b = 0; b < KASA_SHARD_NBUF; ++b) {
+            if (!m.ptr[b]) { c->sh.peer[o][b] = 0; continue; }
+            if (m.pid == me) { c->sh.peer[o][b] = m.ptr[b]; continue; }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, m.handle[b], sizeof(h));
+            void *p = nullptr;
+            KASA_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            c->sh.opened.push_back(p);
+            c->sh.peer[o][b] = (uint64_t)(uintptr_t)p;
+        }
+    }
+    c->sh.connected = true;
+    KASA_API_END(c)
+}
+
+int kasa_index_from_build_shard(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_taxa, int rank, int n_shards,
+                                uint64_t *entry_begin, uint32_t *prefix_begin)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && taxid_of_idx && entry_begin && prefix_begin, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(c->build_done, KASA_ERR_STATE, "kasa_index_from_build_shard needs a finished build (kasa_build_finish)");
+    KASA_REQUIRE(n_shards >= 1 && n_shards <= KASA_MAX_SHARDS && rank >= 0 && rank < n_shards, KASA_ERR_ARG,
+                 "need 0 <= rank < n_shards <= KASA_MAX_SHARDS");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    drop_index(c);
+    set_taxa(c, n_taxa);
+    const uint64_t n_all = c->build_fill;
+    const int b = c->build_buf;
+    uint64_t *d_eb = dev_alloc<uint64_t>(c, KASA_MAX_SHARDS + 1);
+    uint32_t *d_pb = dev_alloc<uint32_t>(c, KASA_MAX_SHARDS + 1);
+    launch_shard_plan(c->stream, c->sb.w0[b], c->wide ? c->sb.w1[b] : nullptr, n_all, c->K, std::min(6, c->p.k_low), n_shards, d_eb, d_pb,
+                      &c->launches);
+    KASA_CUDA_TRY(cudaMemcpyAsync(entry_begin, d_eb, (n_shards + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    KASA_CUDA_TRY(cudaMemcpyAsync(prefix_begin, d_pb, (n_shards + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    dev_free(c, d_eb); dev_free(c, d_pb);
+    const uint64_t o = entry_begin[rank], n = entry_begin[rank + 1] - o;
+    c->idx_lo = dev_alloc<uint64_t>(c, n + 16);
+    c->idx_hi = c->wide ? dev_alloc<uint64_t>(c, n + 16) : nullptr;
+    c->idx_tax = dev_alloc<uint16_t>(c, n + 16);
+    KASA_CUDA_TRY(cudaMemcpyAsync(c->idx_lo, c->sb.w0[b] + o, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->wide) KASA_CUDA_TRY(cudaMemcpyAsync(c->idx_hi, c->sb.w1[b] + o, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
+    launch_map_taxids(c->stream, c->sb.v[b] + o, n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
+    KASA_CUDA_TRY(cudaGetLastError());
+    check_device_flags(c);
+    dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
+    c->idx_n = n;
+    KASA_API_END(c)
+}
+
+int kasa_shard_sort(kasa_ctx *c, const kasa_read_batch *in, kasa_shard_runs *mine)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && in && mine, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(c->sh.on && c->sh.connected, KASA_ERR_STATE, "kasa_shard_sort before kasa_shard_init / kasa_shard_connect");
+    KASA_REQUIRE(c->idx_lo, KASA_ERR_STATE, "kasa_shard_sort before an index shard was loaded");
+    KASA_REQUIRE(c->submitted == c->completed, KASA_ERR_STATE, "pipelined batches are still in flight");
+    KASA_REQUIRE(c->sh.phase == 0, KASA_ERR_STATE, "kasa_shard_sort: the previous batch has not been scored");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    kasa_ctx::Slot &sl = c->slot[0];
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[0], c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[1], c->stream));
+    const uint32_t *first = nullptr;
+    const uint64_t n = extract_batch(c, in, sl, &first);
+    KASA_CUDA_TRY(cudaEventRecord(sl.in_free, c->stream));
+    sl.in_free_set = true;
+    const int sorted_from = std::max(0, 5 * c->K - c->sort_bits);
+    SortPlan plan = plan_for_bit_range(sorted_from, 5 * c->K);
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[2], c->stream));
+    std::memset(mine, 0, sizeof(*mine));
+    mine->n_kmers = n;
+    if (n) {
+        const int cur = radix_sort(c->stream, c->sb, 0, n, plan, c->sort_ws, c->d_err, &c->launches, sl.sev[3]);
+        mine->cur = cur;
+        launch_read_offsets(c->stream, c->d_koff, first, in->n_reads, c->d_read_koff, &c->launches);
+        launch_run_bounds(c->stream, c->sb.w0[cur], c->wide ? c->sb.w1[cur] : nullptr, n, c->K, c->sh.d_prefix_begin, c->sh.n, c->sh.d_begin,
+                          &c->launches);
+        KASA_CUDA_TRY(cudaMemcpyAsync(mine->begin, c->sh.d_begin, (c->sh.n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        KASA_CUDA_TRY(cudaEventRecord(sl.sev[3], c->stream));
+    }
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[4], c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));        // the sorted run is complete before any peer is told about it
+    sl.n = n;
+    sl.n_passes = n ? plan.n_passes : 0;
+    c->sh.n_reads = in->n_reads;
+    c->sh.phase = 1;
+    KASA_API_END(c)
+}
+
+int kasa_shard_lookup(kasa_ctx *c, const kasa_shard_runs *all)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && all, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(c->sh.on && c->sh.phase == 1, KASA_ERR_STATE, "kasa_shard_lookup must follow kasa_shard_sort");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    kasa_ctx::Slot &sl = c->slot[0];
+    IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n};
+    LevelParams lp = level_params(c);
+    const int sorted_from = std::max(0, 5 * c->K - c->sort_bits);
+    const int me = c->sh.rank;
+    // serve every origin's run of this shard's prefix range, starting with the local one (spreads the NVLink traffic):
+    // queries and instance ids are read from the origin's sorted buffers, records are stored into the origin's array
+    for (int i = 0; i < c->sh.n; ++i) {
+        const int o = (me + i) % c->sh.n;
+        const kasa_shard_runs &r = all[o];
+        KASA_REQUIRE(r.cur == 0 || r.cur == 1, KASA_ERR_ARG, "kasa_shard_runs.cur must be 0 or 1");
+        KASA_REQUIRE(r.begin[me] <= r.begin[me + 1] && r.begin[me + 1] <= r.n_kmers, KASA_ERR_ARG, "kasa_shard_runs.begin is not monotone");
+        const uint64_t b0 = r.begin[me], m = r.begin[me + 1] - b0;
+        if (!m) continue;
+        KASA_REQUIRE(m <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "a peer's run exceeds max_batch_kmers");
+        const uint64_t *q_lo = reinterpret_cast<const uint64_t *>(c->sh.peer[o][r.cur]) + b0;
+        const uint64_t *q_hi = c->wide ? reinterpret_cast<const uint64_t *>(c->sh.peer[o][2 + r.cur]) + b0 : nullptr;
+        const uint32_t *inst = reinterpret_cast<const uint32_t *>(c->sh.peer[o][4 + r.cur]) + b0;
+        uint64_t *rec = reinterpret_cast<uint64_t *>(c->sh.peer[o][6]);
+        const uint32_t tq = lookup_tile_queries(m, c->idx_n);
+        launch_partition(c->stream, q_lo, q_hi, m, idx, lp, c->d_part, tq, sorted_from, &c->launches);
+        launch_lookup(c->stream, q_lo, q_hi, inst, m, idx, lp, c->d_part, rec, tq, &c->launches);
+    }
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[5], c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));        // every record this shard owes is in its origin's HBM
+    c->sh.phase = 2;
+    KASA_API_END(c)
+}
+
+int kasa_shard_score(kasa_ctx *c, kasa_batch_result *out)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && out, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(c->sh.on && c->sh.phase == 2, KASA_ERR_STATE, "kasa_shard_score must follow kasa_shard_lookup");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    kasa_ctx::Slot &sl = c->slot[0];
+    const uint64_t n = sl.n;
+    const uint32_t n_reads = c->sh.n_reads;
+    const bool want_scores = c->p.score_mode != KASA_SCORE_NONE;
+    LevelParams lp = level_params(c);
+    KASA_CUDA_TRY(cudaEventRecord(c->sh.ev_score0, c->stream));
+    if (n) {
+        launch_per_read(c->stream, c->d_rec, c->d_read_koff, n_reads, lp, want_scores ? sl.scores : nullptr, c->d_cnt_fx, c->d_cnt_un,
+                        &c->launches);
+        launch_fold_counts(c->stream, c->d_cnt_fx, c->d_cnt_un, lp, c->d_tot_all, c->d_tot_un, &c->launches);
+    } else if (want_scores && n_reads) {
+        KASA_CUDA_TRY(cudaMemsetAsync(sl.scores, 0, (size_t)n_reads * c->n_taxa * 4, c->stream));
+    }
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[6], c->stream));
+    if (want_scores && out->scores && n_reads)
+        KASA_CUDA_TRY(cudaMemcpyAsync(out->scores, sl.scores, (size_t)n_reads * c->n_taxa * 4,
+                                      out->scores_location == KASA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    KASA_CUDA_TRY(cudaEventRecord(sl.sev[7], c->stream));
+    c->sh.phase = 0;
+    check_device_flags(c);
+    float total = 0.f;
+    for (int i = 0; i < KASA_N_STAGES; ++i) {
+        float ms = 0.f;
+        if (i == KASA_STAGE_PER_READ) KASA_CUDA_TRY(cudaEventElapsedTime(&ms, c->sh.ev_score0, sl.sev[6]));   // not the host barrier before it
+        else KASA_CUDA_TRY(cudaEventElapsedTime(&ms, sl.sev[i], sl.sev[i + 1]));
+        c->stage_ms[i] += ms;
+        total += ms;
+    }
+    c->stage_batches += 1;
+    c->stage_passes += sl.n_passes;
+    c->stage_kmers += n;
+    c->n_kmers_total += n;
+    out->n_kmers = n;
+    out->gpu_ms = total;
     KASA_API_END(c)
 }
 

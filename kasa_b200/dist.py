@@ -37,3 +37,67 @@ def reduce_counts(count_all: np.ndarray, count_unique: np.ndarray, n_kmers: int,
     dist.all_reduce(cu)
     dist.all_reduce(nk)
     return ca.cpu().numpy(), cu.cpu().numpy().astype(np.uint64), int(nk.item())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY.md §8e mode 2: index sharded by k-mer prefix range, reads sharded too.  There is no staging all-to-all:
+# the owner of a prefix range runs its lookup kernel directly on the peers' sorted runs and stores the match
+# records into the peers' HBM over NVLink (include/kasa_b200.h, kasa_shard_*).  The host exchanges two small
+# structs per batch; torch.distributed is that plumbing.
+
+def _gather_struct(dist, obj, device=None):
+    """all-gather one fixed-size ctypes struct per rank -> list of structs (rank order)."""
+    import ctypes as C
+    import torch
+    raw = bytes(obj)
+    t = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    on_gpu = dist.get_backend() == "nccl"
+    if on_gpu:
+        t = t.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    out = torch.empty(dist.get_world_size() * len(raw), dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    buf = out.cpu().numpy().tobytes()
+    cls = type(obj)
+    return [cls.from_buffer_copy(buf[i * len(raw):(i + 1) * len(raw)]) for i in range(dist.get_world_size())]
+
+
+class ShardGroup:
+    """One rank's handle on a prefix-sharded identify job: `ctx` already holds shard `rank` of the index."""
+
+    def __init__(self, ctx, dist, prefix_begin, device=None):
+        self.ctx, self.dist, self.device = ctx, dist, device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        mem = ctx.shard_init(self.rank, self.world, prefix_begin)
+        ctx.shard_connect(_gather_struct(dist, mem, device))
+        dist.barrier()
+
+    def identify_batch_raw(self, rb, res):
+        """One batch of this rank's reads against the whole (sharded) index; fills `res` like kasa_identify_batch."""
+        runs = self.ctx.shard_sort_raw(rb)                    # extract + sort + where the sorted run changes owner
+        all_runs = _gather_struct(self.dist, runs, self.device)
+        self.ctx.shard_lookup(all_runs)                       # serves every rank's queries of this shard's range
+        self.dist.barrier()                                   # all records have reached their origin
+        self.ctx.shard_score_raw(res)
+
+
+class LocalShardGroup:
+    """The same protocol for several contexts in ONE process (tests: n shards on one GPU; or one process driving
+    several GPUs): peers are reached through their raw device pointers."""
+
+    def __init__(self, ctxs, prefix_begin):
+        self.ctxs = list(ctxs)
+        n = len(self.ctxs)
+        mems = [c.shard_init(r, n, prefix_begin) for r, c in enumerate(self.ctxs)]
+        for c in self.ctxs:
+            c.shard_connect(mems)
+
+    def identify_batches(self, batches, read_first_seqs=None):
+        """batches[r] = the reads of rank r (as for Context.identify_batch) -> [(n_kmers, scores, gpu_ms)] per rank."""
+        runs, n_reads = [], []
+        for r, c in enumerate(self.ctxs):
+            ru, nr = c.shard_sort(batches[r], read_first_seqs[r] if read_first_seqs is not None else None)
+            runs.append(ru)
+            n_reads.append(nr)
+        for c in self.ctxs:
+            c.shard_lookup(runs)
+        return [c.shard_score(n_reads[r]) for r, c in enumerate(self.ctxs)]

@@ -38,16 +38,18 @@ def test_header_is_plain_c_and_ctypes_structs_match_it(tmp_path):
 #include <stddef.h>
 #include "kasa_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(kasa_params), sizeof(kasa_read_batch), sizeof(kasa_batch_result),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(kasa_params), sizeof(kasa_read_batch), sizeof(kasa_batch_result),
          sizeof(kasa_seq_batch), offsetof(kasa_params, max_batch_kmers), offsetof(kasa_params, codon_table),
-         offsetof(kasa_read_batch, read_first_seq), offsetof(kasa_batch_result, gpu_ms));
+         offsetof(kasa_read_batch, read_first_seq), offsetof(kasa_batch_result, gpu_ms),
+         sizeof(kasa_shard_mem), offsetof(kasa_shard_mem, handle), sizeof(kasa_shard_runs), offsetof(kasa_shard_runs, begin));
   return 0; }''')
     exe = tmp_path / "sz"
     subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(capi.CParams), ctypes.sizeof(capi.CReadBatch), ctypes.sizeof(capi.CBatchResult),
             ctypes.sizeof(capi.CSeqBatch), capi.CParams.max_batch_kmers.offset, capi.CParams.codon_table.offset,
-            capi.CReadBatch.read_first_seq.offset, capi.CBatchResult.gpu_ms.offset]
+            capi.CReadBatch.read_first_seq.offset, capi.CBatchResult.gpu_ms.offset,
+            ctypes.sizeof(capi.CShardMem), capi.CShardMem.handle.offset, ctypes.sizeof(capi.CShardRuns), capi.CShardRuns.begin.offset]
     assert got == want
     assert capi.REC64.itemsize == 12 and capi.REC128.itemsize == 20 and capi.TRIE.itemsize == 12
 
@@ -96,3 +98,46 @@ def test_read_sharding_covers_everything_once():
         assert seen == list(range(1001))
         firsts = sorted(shard_first_read(s, world, r, 10) for s in range(3) for r in range(world))
         assert firsts == [10 * i for i in range(3 * world)]
+
+
+def _prefix30(idx, K):
+    if K == 12:
+        return (idx["lo"] >> np.uint64(30)).astype(np.uint32)
+    return (idx["hi"] >> np.uint64(5 * K - 30 - 64)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("case,K", [("k12", 12), ("k25", 25)])
+@pytest.mark.parametrize("k_low", [1, 3, 6, 7])
+@pytest.mark.parametrize("n_shards", [1, 2, 5, 16])
+def test_shard_plan_cuts_on_prefix_groups(case, K, k_low, n_shards):
+    """kasa_shard_plan is host-only: boundaries never split a group of min(6, k_low) leading letters
+    (so every level-k taxa set of SURVEY.md §3.1 stays on one shard) and shards are about equal."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_util as G
+    idx = G.index(case)
+    eb, pb = capi.shard_plan(idx, k_low, n_shards)
+    p30 = _prefix30(idx, K)
+    align = min(6, k_low)
+    group = p30 >> np.uint32(5 * (6 - align))
+    assert eb[0] == 0 and eb[-1] == len(idx) and pb[0] == 0 and pb[-1] == 1 << 30
+    assert np.all(np.diff(eb.astype(np.int64)) >= 0) and np.all(np.diff(pb.astype(np.int64)) >= 0)
+    for r in range(1, n_shards):
+        b = int(eb[r])
+        assert pb[r] % (1 << (5 * (6 - align))) == 0
+        assert np.all(p30[:b] < pb[r]) and np.all(p30[b:] >= pb[r])
+        if 0 < b < len(idx):
+            assert group[b - 1] != group[b]
+        # the cut is the start of the group holding the equal-size candidate
+        cand = len(idx) * r // n_shards
+        assert b <= cand and (b == 0 or group[cand] == group[b])
+
+
+def test_shard_plan_rejects_bad_arguments():
+    idx = np.zeros(4, dtype=capi.REC64)
+    with pytest.raises(kasa_b200.KasaError):
+        capi.shard_plan(idx, 7, 0)
+    with pytest.raises(kasa_b200.KasaError):
+        capi.shard_plan(idx, 7, 17)
+    eb, pb = capi.shard_plan(np.zeros(0, dtype=capi.REC64), 7, 3)           # empty index: every shard empty
+    assert list(eb) == [0, 0, 0, 0] and pb[0] == 0 and pb[-1] == 1 << 30

@@ -1,0 +1,118 @@
+"""GPU parity of the prefix-sharded identify (SURVEY.md §8e mode 2; include/kasa_b200.h kasa_shard_*): n contexts,
+each holding one prefix range of the index and its own reads, must reproduce the unsharded results — per-read
+scores bit for bit (KASA_SCORE_FAST is a canonical order), unique counts exactly, non-unique counts to 1e-12 —
+which are themselves pinned on the reference binary in test_gpu_parity.py.  The contexts live in one process on
+one GPU here (peers reached through raw device pointers); the cross-process cudaIpc route is exercised by
+`bench.py --sharding prefix` under torchrun."""
+import numpy as np
+import pytest
+
+import golden_util as G
+from kasa_b200 import Context, KasaError, Params
+from kasa_b200 import capi
+from kasa_b200.dist import LocalShardGroup, shard_bounds
+
+pytestmark = pytest.mark.gpu
+
+
+def _reads(case, paired):
+    if not paired:
+        seqs = [s for _, s in G.fastq(case)]
+        return seqs, None
+    a, b = G.fastq(case, "reads_1.fq.gz"), G.fastq(case, "reads_2.fq.gz")
+    return [(x[1], y[1]) for x, y in zip(a, b)], True
+
+
+def _flatten(reads, paired):
+    if not paired:
+        return list(reads), None
+    seqs, first = [], [0]
+    for x, y in reads:
+        seqs += [x, y]
+        first.append(len(seqs))
+    return seqs, np.array(first, dtype=np.uint32)
+
+
+def _run(case, K, k_high, k_low, six, n_shards, paired=False):
+    _, taxids, _ = G.content(case)
+    idx = G.index(case)
+    reads, paired = _reads(case, paired)
+    kw = dict(highest_k=K, k_high=k_high, k_low=k_low, frames=6 if six else 3, score_mode=capi.SCORE_FAST)
+    # unsharded
+    ref = Context(Params(**kw))
+    ref.load_index(idx, taxids)
+    seqs, first = _flatten(reads, paired)
+    nk, want_scores, _ = ref.identify_batch(seqs, read_first_seq=first)
+    want_ca, want_cu, want_total = ref.identify_finish()
+    ref.close()
+    # sharded: index cut on prefix boundaries, reads dealt to the ranks
+    eb, pb = capi.shard_plan(idx, k_low, n_shards)
+    assert eb[0] == 0 and eb[-1] == len(idx) and np.all(np.diff(eb.astype(np.int64)) >= 0)
+    ctxs = []
+    for r in range(n_shards):
+        c = Context(Params(**kw))
+        c.load_index(idx[int(eb[r]):int(eb[r + 1])], taxids)
+        ctxs.append(c)
+    grp = LocalShardGroup(ctxs, pb)
+    batches, firsts, bounds = [], [], []
+    for r in range(n_shards):
+        lo, hi = shard_bounds(len(reads), n_shards, r)
+        s, f = _flatten(reads[lo:hi], paired)
+        batches.append(s)
+        firsts.append(f)
+        bounds.append((lo, hi))
+    for rnd in range(2):                                     # twice: buffers and phases are reusable
+        out = grp.identify_batches(batches, firsts if paired else None)
+        got = np.concatenate([o[1] for o in out], axis=0)
+        assert sum(o[0] for o in out) == nk
+        assert np.array_equal(got, want_scores), "per-read scores differ from the unsharded run"
+    ca = np.zeros_like(want_ca)
+    cu = np.zeros_like(want_cu)
+    total = 0
+    for c in ctxs:
+        a, u, t = c.identify_finish()
+        ca += a
+        cu += u
+        total += t
+        c.close()
+    assert total == 2 * want_total
+    assert np.array_equal(cu, 2 * want_cu)
+    np.testing.assert_allclose(ca, 2 * want_ca, rtol=1e-12)
+
+
+def test_sharded_k12_three_shards():
+    _run("k12", 12, 12, 7, True, 3)
+
+
+def test_sharded_k12_low_k_boundaries_respect_short_prefixes():
+    # k_low = 3 < 6 letters: shard boundaries must fall on 3-letter prefixes
+    _run("k12", 12, 12, 3, False, 4)
+
+
+def test_sharded_k25_paired_two_shards():
+    _run("k25", 25, 25, 7, True, 2, paired=True)
+
+
+def test_sharded_single_shard_equals_plain_identify():
+    _run("k12", 12, 11, 8, False, 1)
+
+
+def test_sharded_protocol_errors():
+    _, taxids, _ = G.content("k12")
+    idx = G.index("k12")
+    c = Context(Params(score_mode=capi.SCORE_EXACT))
+    c.load_index(idx, taxids)
+    with pytest.raises(KasaError):                           # exact mode replays one global order
+        c.shard_init(0, 2, np.array([0, 1 << 29, 1 << 30], dtype=np.uint32))
+    c.close()
+    c = Context(Params())
+    c.load_index(idx, taxids)
+    with pytest.raises(KasaError):                           # not spanning [0, 2^30]
+        c.shard_init(0, 2, np.array([0, 5, 9], dtype=np.uint32))
+    mem = c.shard_init(0, 1, np.array([0, 1 << 30], dtype=np.uint32))
+    with pytest.raises(KasaError):                           # sort before connect
+        c.shard_sort([b"ACGT" * 30])
+    c.shard_connect([mem])
+    with pytest.raises(KasaError):                           # score before lookup
+        c.shard_score(1)
+    c.close()
