@@ -181,7 +181,7 @@ int kasa_identify_finish(kasa_ctx *ctx, double *count_all, uint64_t *count_uniqu
  * KASA_SCORE_EXACT replays one global flush order and is rejected).                                            */
 
 #define KASA_MAX_SHARDS 16
-#define KASA_SHARD_NBUF 7          /* sort ping-pong w0[2], w1[2], v[2] and the match-record array              */
+#define KASA_SHARD_NBUF 8          /* sort ping-pong w0[2], w1[2], v[2], the match-record array, the record stage */
 
 typedef struct {
     uint64_t pid;                  /* owner process: peers in the same process use `ptr`, others open `handle`  */
@@ -217,7 +217,7 @@ int kasa_shard_init(kasa_ctx *ctx, int rank, int n_shards, const uint32_t *prefi
 int kasa_shard_connect(kasa_ctx *ctx, const kasa_shard_mem *all);
 int kasa_shard_sort(kasa_ctx *ctx, const kasa_read_batch *in, kasa_shard_runs *mine);
 int kasa_shard_lookup(kasa_ctx *ctx, const kasa_shard_runs *all);
-int kasa_shard_score(kasa_ctx *ctx, kasa_batch_result *out);
+int kasa_shard_score(kasa_ctx *ctx, const kasa_shard_runs *all, kasa_batch_result *out);
 
 /* --------------------------------------------------------------------------------------------------- */
 /* build                                                                                                */

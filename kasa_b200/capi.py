@@ -60,7 +60,7 @@ class CSeqBatch(C.Structure):
                 ("seq_len", C.c_void_p), ("taxid", C.c_void_p)]
 
 
-MAX_SHARDS, SHARD_NBUF = 16, 7
+MAX_SHARDS, SHARD_NBUF = 16, 8
 
 
 class CShardMem(C.Structure):
@@ -113,7 +113,7 @@ def load_library():
     L.kasa_shard_connect.argtypes = [C.c_void_p, C.POINTER(CShardMem)]
     L.kasa_shard_sort.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.POINTER(CShardRuns)]
     L.kasa_shard_lookup.argtypes = [C.c_void_p, C.POINTER(CShardRuns)]
-    L.kasa_shard_score.argtypes = [C.c_void_p, C.POINTER(CBatchResult)]
+    L.kasa_shard_score.argtypes = [C.c_void_p, C.POINTER(CShardRuns), C.POINTER(CBatchResult)]
     L.kasa_build_push.argtypes = [C.c_void_p, C.POINTER(CSeqBatch)]
     L.kasa_build_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.kasa_build_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -340,14 +340,15 @@ class Context:
         arr = (CShardRuns * len(runs))(*runs)
         self._check(self.lib.kasa_shard_lookup(self.h, arr))
 
-    def shard_score_raw(self, res: CBatchResult):
-        self._check(self.lib.kasa_shard_score(self.h, C.byref(res)))
+    def shard_score_raw(self, runs: list, res: CBatchResult):
+        arr = (CShardRuns * len(runs))(*runs)
+        self._check(self.lib.kasa_shard_score(self.h, arr, C.byref(res)))
 
-    def shard_score(self, n_reads: int):
+    def shard_score(self, runs: list, n_reads: int):
         want = self.params.score_mode != SCORE_NONE
         scores = np.zeros((n_reads, self.n_taxa), dtype=np.float32) if want else None
         res = CBatchResult(0, scores.ctypes.data if want and scores.size else None, MEM_HOST, 0.0)
-        self.shard_score_raw(res)
+        self.shard_score_raw(runs, res)
         return int(res.n_kmers), scores, float(res.gpu_ms)
 
     # ---------------------------------------------------------------- build

@@ -87,6 +87,7 @@ struct kasa_ctx {
         uint64_t *d_begin = nullptr;
         uint64_t peer[KASA_MAX_SHARDS][KASA_SHARD_NBUF] = {};
         std::vector<void *> opened;                       // cudaIpcOpenMemHandle mappings
+        uint64_t *d_stage = nullptr;                      // records this shard computed for its peers, in run order
         cudaEvent_t ev_score0 = nullptr;
         int phase = 0;                                    // 0 idle, 1 sorted, 2 looked up
         uint32_t n_reads = 0;
@@ -768,6 +769,7 @@ static void shard_common_init(kasa_ctx *c, int rank, int n_shards, const uint32_
     if (!c->sh.d_prefix_begin) {
         c->sh.d_prefix_begin = dev_alloc<uint32_t>(c, KASA_MAX_SHARDS + 1);
         c->sh.d_begin = dev_alloc<uint64_t>(c, KASA_MAX_SHARDS + 1);
+        c->sh.d_stage = n_shards > 1 ? dev_alloc<uint64_t>(c, (size_t)(c->p.max_batch_kmers + 2) * kRecWords) : nullptr;
         KASA_CUDA_TRY(cudaEventCreate(&c->sh.ev_score0));
     }
     KASA_CUDA_TRY(cudaMemcpyAsync(c->sh.d_prefix_begin, prefix_begin, (n_shards + 1) * 4, cudaMemcpyHostToDevice, c->stream));
@@ -778,7 +780,7 @@ static void shard_common_init(kasa_ctx *c, int rank, int n_shards, const uint32_
 static void *const *shard_buffers(kasa_ctx *c, void *out[KASA_SHARD_NBUF])
 {
     out[0] = c->sb.w0[0]; out[1] = c->sb.w0[1]; out[2] = c->sb.w1[0]; out[3] = c->sb.w1[1];
-    out[4] = c->sb.v[0]; out[5] = c->sb.v[1]; out[6] = c->d_rec;
+    out[4] = c->sb.v[0]; out[5] = c->sb.v[1]; out[6] = c->d_rec; out[7] = c->sh.d_stage;
     return out;
 }
 
@@ -926,19 +928,27 @@ int kasa_shard_lookup(kasa_ctx *c, const kasa_shard_runs *all)
     const int sorted_from = std::max(0, 5 * c->K - c->sort_bits);
     const int me = c->sh.rank;
     // serve every origin's run of this shard's prefix range, starting with the local one (spreads the NVLink traffic):
-    // queries and instance ids are read from the origin's sorted buffers, records are stored into the origin's array
-    for (int i = 0; i < c->sh.n; ++i) {
-        const int o = (me + i) % c->sh.n;
+    // queries are read from the origin's sorted buffer; the local run's records go straight to their instance slots,
+    // a peer's records are left in run order in the stage (segment o starts where the runs of the origins before o end)
+    uint64_t seg[KASA_MAX_SHARDS + 1] = {0};
+    for (int o = 0; o < c->sh.n; ++o) {
         const kasa_shard_runs &r = all[o];
         KASA_REQUIRE(r.cur == 0 || r.cur == 1, KASA_ERR_ARG, "kasa_shard_runs.cur must be 0 or 1");
         KASA_REQUIRE(r.begin[me] <= r.begin[me + 1] && r.begin[me + 1] <= r.n_kmers, KASA_ERR_ARG, "kasa_shard_runs.begin is not monotone");
+        seg[o + 1] = seg[o] + (o == me ? 0 : r.begin[me + 1] - r.begin[me]);
+    }
+    KASA_REQUIRE(seg[c->sh.n] <= c->p.max_batch_kmers, KASA_ERR_NOMEM,
+                 "the peers' runs of this shard's prefix range exceed max_batch_kmers records (unbalanced shards or batches)");
+    for (int i = 0; i < c->sh.n; ++i) {
+        const int o = (me + i) % c->sh.n;
+        const kasa_shard_runs &r = all[o];
         const uint64_t b0 = r.begin[me], m = r.begin[me + 1] - b0;
         if (!m) continue;
         KASA_REQUIRE(m <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "a peer's run exceeds max_batch_kmers");
         const uint64_t *q_lo = reinterpret_cast<const uint64_t *>(c->sh.peer[o][r.cur]) + b0;
         const uint64_t *q_hi = c->wide ? reinterpret_cast<const uint64_t *>(c->sh.peer[o][2 + r.cur]) + b0 : nullptr;
-        const uint32_t *inst = reinterpret_cast<const uint32_t *>(c->sh.peer[o][4 + r.cur]) + b0;
-        uint64_t *rec = reinterpret_cast<uint64_t *>(c->sh.peer[o][6]);
+        const uint32_t *inst = o == me ? c->sb.v[r.cur] + b0 : nullptr;
+        uint64_t *rec = o == me ? c->d_rec : c->sh.d_stage + seg[o] * kRecWords;
         const uint32_t tq = lookup_tile_queries(m, c->idx_n);
         launch_partition(c->stream, q_lo, q_hi, m, idx, lp, c->d_part, tq, sorted_from, &c->launches);
         launch_lookup(c->stream, q_lo, q_hi, inst, m, idx, lp, c->d_part, rec, tq, &c->launches);
@@ -949,10 +959,10 @@ int kasa_shard_lookup(kasa_ctx *c, const kasa_shard_runs *all)
     KASA_API_END(c)
 }
 
-int kasa_shard_score(kasa_ctx *c, kasa_batch_result *out)
+int kasa_shard_score(kasa_ctx *c, const kasa_shard_runs *all, kasa_batch_result *out)
 {
     KASA_API_BEGIN
-    KASA_REQUIRE(c && out, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(c && all && out, KASA_ERR_ARG, "null argument");
     KASA_REQUIRE(c->sh.on && c->sh.phase == 2, KASA_ERR_STATE, "kasa_shard_score must follow kasa_shard_lookup");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
     kasa_ctx::Slot &sl = c->slot[0];
@@ -961,6 +971,18 @@ int kasa_shard_score(kasa_ctx *c, kasa_batch_result *out)
     const bool want_scores = c->p.score_mode != KASA_SCORE_NONE;
     LevelParams lp = level_params(c);
     KASA_CUDA_TRY(cudaEventRecord(c->sh.ev_score0, c->stream));
+    // pull the records the peers computed for this context's sorted run into emission order
+    const int me = c->sh.rank;
+    const kasa_shard_runs &mine = all[me];
+    KASA_REQUIRE(mine.n_kmers == n, KASA_ERR_ARG, "kasa_shard_score: all[rank] is not this context's batch");
+    for (int i = 1; i < c->sh.n && n; ++i) {
+        const int w = (me + i) % c->sh.n;
+        uint64_t seg = 0;                                     // where owner w staged this origin's segment
+        for (int o = 0; o < me; ++o) seg += o == w ? 0 : all[o].begin[w + 1] - all[o].begin[w];
+        const uint64_t b0 = mine.begin[w], m = mine.begin[w + 1] - b0;
+        launch_scatter_records(c->stream, reinterpret_cast<const uint64_t *>(c->sh.peer[w][7]) + seg * kRecWords, c->sb.v[mine.cur] + b0, m,
+                               c->d_rec, &c->launches);
+    }
     if (n) {
         launch_per_read(c->stream, c->d_rec, c->d_read_koff, n_reads, lp, want_scores ? sl.scores : nullptr, c->d_cnt_fx, c->d_cnt_un,
                         &c->launches);

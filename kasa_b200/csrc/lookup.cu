@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
         live[r] = off < tq && i < n;
         qv[r].lo = live[r] ? ldg_stream(q_lo + i) : 0ull;
         qv[r].hi = (W && live[r]) ? ldg_stream(q_hi + i) : 0ull;
-        iv[r] = live[r] ? ldg_stream(inst + i) : 0u;
+        iv[r] = live[r] ? (inst ? ldg_stream(inst + i) : (uint32_t)i) : 0u;      // inst == nullptr: record i goes to slot i
     }
     __syncthreads();                                          // the barrier word is initialised
     const uint64_t *s_klo = st.klo + (a - ak);
@@ -418,10 +418,25 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
             match_query_gmem<W, HB>(gacc, a, b, qv[r], kv[r], lp, rw, np);
         }
         if (HB == 3) rw[3] = np;
-        uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)iv[r] * kRecWords);
-        dst[0] = make_uint4((uint32_t)rw[0], (uint32_t)(rw[0] >> 32), (uint32_t)rw[1], (uint32_t)(rw[1] >> 32));
-        dst[1] = make_uint4((uint32_t)rw[2], (uint32_t)(rw[2] >> 32), (uint32_t)rw[3], (uint32_t)(rw[3] >> 32));
+        // one 256-bit store = one full 32-byte sector per record (STG.256, sm_100)
+        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)iv[r] * kRecWords), "l"(rw[0]), "l"(rw[1]), "l"(rw[2]),
+                     "l"(rw[3])
+                     : "memory");
     }
+}
+
+// rec[inst[i]] = staged[i]: the origin of a prefix-sharded batch pulls the records a peer computed for its sorted
+// run (contiguous, so the NVLink side is a streaming read) and scatters them into emission order in its own HBM.
+// Scattered stores INTO peer memory run ~100x slower than this (measured: DESIGN.md §5), hence the pull.
+__global__ void __launch_bounds__(256) scatter_records_kernel(const uint64_t *__restrict__ staged, const uint32_t *__restrict__ inst,
+                                                              uint64_t n, uint64_t *__restrict__ rec)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t a, b, c, d;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(staged + i * kRecWords));
+    const uint32_t j = ldg_stream(inst + i);
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)j * kRecWords), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -605,6 +620,13 @@ void launch_lookup_hb(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi
 }
 
 }  // namespace
+
+void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32_t *inst, uint64_t n, uint64_t *rec, uint64_t *launches)
+{
+    if (!n) return;
+    scatter_records_kernel<<<(unsigned)div_up<uint64_t>(n, 256), 256, 0, s>>>(staged, inst, n, rec);
+    ++*launches;
+}
 
 uint32_t lookup_tile_queries(uint64_t n_queries, uint64_t n_index)
 {

@@ -45,6 +45,10 @@ void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi
 void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n,
                    IndexDev idx, LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq, uint64_t *launches);
 
+// inst == nullptr: record i is written to rec[i] (sorted position; the prefix-sharded path stages records this way)
+// rec[inst[i]] = staged[i] for i < n (staged may be peer memory)
+void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32_t *inst, uint64_t n, uint64_t *rec, uint64_t *launches);
+
 // per read: fp32 scores in canonical order (instance order, k ascending) and the per-taxon per-level
 // counts: cnt_fx [num_k][n_taxa] fixed point 2^-32 (sum of 1/|taxa|), cnt_unique [num_k][n_taxa].
 // Level j = 0 is k_low.  scores may be nullptr (profile only).

@@ -40,10 +40,10 @@ def reduce_counts(count_all: np.ndarray, count_unique: np.ndarray, n_kmers: int,
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# SURVEY.md §8e mode 2: index sharded by k-mer prefix range, reads sharded too.  There is no staging all-to-all:
-# the owner of a prefix range runs its lookup kernel directly on the peers' sorted runs and stores the match
-# records into the peers' HBM over NVLink (include/kasa_b200.h, kasa_shard_*).  The host exchanges two small
-# structs per batch; torch.distributed is that plumbing.
+# SURVEY.md §8e mode 2: index sharded by k-mer prefix range, reads sharded too.  There is no send/receive staging:
+# the owner of a prefix range runs its lookup kernel directly on the peers' sorted runs (streaming NVLink loads),
+# and each origin's scatter kernel pulls its match records back the same way (include/kasa_b200.h, kasa_shard_*).
+# The host exchanges one small struct per rank and batch; torch.distributed is that plumbing.
 
 def _gather_struct(dist, obj, device=None):
     """all-gather one fixed-size ctypes struct per rank -> list of structs (rank order)."""
@@ -77,7 +77,7 @@ class ShardGroup:
         all_runs = _gather_struct(self.dist, runs, self.device)
         self.ctx.shard_lookup(all_runs)                       # serves every rank's queries of this shard's range
         self.dist.barrier()                                   # all records have reached their origin
-        self.ctx.shard_score_raw(res)
+        self.ctx.shard_score_raw(all_runs, res)                # pulls the peers' records, scores this rank's reads
 
 
 class LocalShardGroup:
@@ -100,4 +100,4 @@ class LocalShardGroup:
             n_reads.append(nr)
         for c in self.ctxs:
             c.shard_lookup(runs)
-        return [c.shard_score(n_reads[r]) for r, c in enumerate(self.ctxs)]
+        return [c.shard_score(runs, n_reads[r]) for r, c in enumerate(self.ctxs)]

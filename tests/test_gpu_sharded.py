@@ -114,5 +114,5 @@ def test_sharded_protocol_errors():
         c.shard_sort([b"ACGT" * 30])
     c.shard_connect([mem])
     with pytest.raises(KasaError):                           # score before lookup
-        c.shard_score(1)
+        c.shard_score([capi.CShardRuns()], 1)
     c.close()
