@@ -219,6 +219,26 @@ int kasa_shard_sort(kasa_ctx *ctx, const kasa_read_batch *in, kasa_shard_runs *m
 int kasa_shard_lookup(kasa_ctx *ctx, const kasa_shard_runs *all);
 int kasa_shard_score(kasa_ctx *ctx, const kasa_shard_runs *all, kasa_batch_result *out);
 
+/* --- build of a prefix-sharded index (BASELINE config C4): every rank pushes its part of the reference sequences
+ * with kasa_build_push; the owners of the prefix ranges then pull "their" records from every peer's sorted brick
+ * (contiguous peer copies over NVLink), and sort / dedup / run-length encode them locally.  The shards, written one
+ * after the other in rank order, are byte for byte the file `kASA build` writes (index and `_trie`); the frequency
+ * tables add up.  Replaces Build::mergeTemporaries (Build.hpp:360-477): the k-way merge of sorted bricks becomes
+ * "route by prefix, then sort".  Protocol:
+ *     kasa_build_shard_local(ctx, hist, &n)      -> all-reduce(sum) hist over the ranks
+ *     kasa_shard_plan_hist(hist, ...)            (host only, same result on every rank)
+ *     kasa_shard_init / all-gather / kasa_shard_connect
+ *     kasa_build_shard_runs(ctx, &runs[rank])    -> all-gather runs
+ *     kasa_build_shard_pull(ctx, runs)           -> barrier
+ *     kasa_build_finish / _fetch / _frequency    as for a single GPU, now for this rank's shard                  */
+#define KASA_SHARD_HIST_BITS 15
+/* Sorts and dedups the local brick; hist[1 << KASA_SHARD_HIST_BITS] = local records per leading-15-bit bucket.   */
+int kasa_build_shard_local(kasa_ctx *ctx, uint64_t *hist, uint64_t *n_local);
+/* Host only: prefix_begin[n_shards+1] with about equal record counts per shard, on min(6, k_low)-letter boundaries. */
+int kasa_shard_plan_hist(const uint64_t *hist, int k_low, int n_shards, uint32_t *prefix_begin);
+int kasa_build_shard_runs(kasa_ctx *ctx, kasa_shard_runs *mine);
+int kasa_build_shard_pull(kasa_ctx *ctx, const kasa_shard_runs *all);
+
 /* --------------------------------------------------------------------------------------------------- */
 /* build                                                                                                */
 
@@ -264,6 +284,8 @@ int kasa_dbg_sort_pairs(kasa_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t 
  * C2 workload in HBM).  kasa_synth_build_reference pushes `n_taxa` genomes of `genome_len` bases
  * (taxid 1000+t) through the build path.  kasa_synth_reads writes n_reads x read_len ASCII bases.       */
 int kasa_synth_build_reference(kasa_ctx *ctx, uint64_t seed, uint32_t n_taxa, uint64_t genome_len);
+/* the same for taxa first_taxon .. first_taxon + n_taxa - 1 only (ranks of a sharded build push disjoint taxa)  */
+int kasa_synth_build_reference_range(kasa_ctx *ctx, uint64_t seed, uint32_t first_taxon, uint32_t n_taxa, uint64_t genome_len);
 int kasa_synth_reads(kasa_ctx *ctx, uint64_t genome_seed, uint64_t read_seed, uint64_t first_read,
                      uint32_t n_reads, uint32_t n_taxa, uint64_t genome_len, uint32_t read_len,
                      uint32_t subst_ppm, uint32_t n_ppm, char *out, int out_location);

@@ -29,7 +29,7 @@ EXPORTS = [
     "kasa_ctx_synchronize", "kasa_ctx_launch_count", "kasa_ctx_stage_times", "kasa_index_load", "kasa_index_from_build", "kasa_index_size",
     "kasa_identify_batch", "kasa_identify_submit", "kasa_identify_wait", "kasa_identify_finish", "kasa_build_push", "kasa_build_finish", "kasa_build_fetch",
     "kasa_shard_plan", "kasa_index_from_build_shard", "kasa_shard_init", "kasa_shard_connect", "kasa_shard_sort", "kasa_shard_lookup",
-    "kasa_shard_score", "kasa_build_frequency", "kasa_dbg_extract", "kasa_dbg_sort_pairs", "kasa_synth_build_reference", "kasa_synth_reads",
+    "kasa_shard_score", "kasa_build_shard_local", "kasa_shard_plan_hist", "kasa_build_shard_runs", "kasa_build_shard_pull", "kasa_build_frequency", "kasa_dbg_extract", "kasa_dbg_sort_pairs", "kasa_synth_build_reference", "kasa_synth_build_reference_range", "kasa_synth_reads",
 ]
 
 
@@ -60,7 +60,7 @@ class CSeqBatch(C.Structure):
                 ("seq_len", C.c_void_p), ("taxid", C.c_void_p)]
 
 
-MAX_SHARDS, SHARD_NBUF = 16, 8
+MAX_SHARDS, SHARD_NBUF, SHARD_HIST_BITS = 16, 8, 15
 
 
 class CShardMem(C.Structure):
@@ -114,6 +114,10 @@ def load_library():
     L.kasa_shard_sort.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.POINTER(CShardRuns)]
     L.kasa_shard_lookup.argtypes = [C.c_void_p, C.POINTER(CShardRuns)]
     L.kasa_shard_score.argtypes = [C.c_void_p, C.POINTER(CShardRuns), C.POINTER(CBatchResult)]
+    L.kasa_build_shard_local.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.kasa_shard_plan_hist.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.kasa_build_shard_runs.argtypes = [C.c_void_p, C.POINTER(CShardRuns)]
+    L.kasa_build_shard_pull.argtypes = [C.c_void_p, C.POINTER(CShardRuns)]
     L.kasa_build_push.argtypes = [C.c_void_p, C.POINTER(CSeqBatch)]
     L.kasa_build_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.kasa_build_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -122,6 +126,7 @@ def load_library():
                                    C.POINTER(C.c_uint64)]
     L.kasa_dbg_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
     L.kasa_synth_build_reference.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64]
+    L.kasa_synth_build_reference_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
     L.kasa_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64,
                                    C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
     _LIB = L
@@ -139,6 +144,18 @@ def shard_plan(records: np.ndarray, k_low: int, n_shards: int):
     if rc != 0:
         raise KasaError(rc, L.kasa_last_error(None).decode())
     return eb, pb
+
+
+def shard_plan_hist(hist: np.ndarray, k_low: int, n_shards: int) -> np.ndarray:
+    """Host-only: prefix_begin[n_shards+1] from the global leading-15-bit histogram (kasa_shard_plan_hist)."""
+    L = load_library()
+    hist = np.ascontiguousarray(hist, dtype=np.uint64)
+    assert len(hist) == 1 << SHARD_HIST_BITS
+    pb = np.zeros(n_shards + 1, dtype=np.uint32)
+    rc = L.kasa_shard_plan_hist(_ptr(hist), k_low, n_shards, _ptr(pb))
+    if rc != 0:
+        raise KasaError(rc, L.kasa_last_error(None).decode())
+    return pb
 
 
 @dataclass
@@ -351,6 +368,22 @@ class Context:
         self.shard_score_raw(runs, res)
         return int(res.n_kmers), scores, float(res.gpu_ms)
 
+    def build_shard_local(self):
+        """Sort + dedup the local brick -> (hist u64[2^15] of leading-15-bit buckets, n_local)."""
+        hist = np.zeros(1 << SHARD_HIST_BITS, dtype=np.uint64)
+        n = C.c_uint64(0)
+        self._check(self.lib.kasa_build_shard_local(self.h, _ptr(hist), C.byref(n)))
+        return hist, int(n.value)
+
+    def build_shard_runs(self) -> CShardRuns:
+        runs = CShardRuns()
+        self._check(self.lib.kasa_build_shard_runs(self.h, C.byref(runs)))
+        return runs
+
+    def build_shard_pull(self, runs: list):
+        arr = (CShardRuns * len(runs))(*runs)
+        self._check(self.lib.kasa_build_shard_pull(self.h, arr))
+
     # ---------------------------------------------------------------- build
     def build_push(self, strings: list[bytes], taxids):
         data, starts, lens = self.pack_reads(strings)
@@ -393,8 +426,8 @@ class Context:
         self._check(self.lib.kasa_dbg_sort_pairs(self.h, _ptr(keys), _ptr(vals), len(keys), bit_lo, bit_hi))
         return keys, vals
 
-    def synth_build_reference(self, seed: int, n_taxa: int, genome_len: int):
-        self._check(self.lib.kasa_synth_build_reference(self.h, seed, n_taxa, genome_len))
+    def synth_build_reference(self, seed: int, n_taxa: int, genome_len: int, first_taxon: int = 0):
+        self._check(self.lib.kasa_synth_build_reference_range(self.h, seed, first_taxon, n_taxa, genome_len))
 
     def synth_reads(self, genome_seed, read_seed, first_read, n_reads, n_taxa, genome_len, read_len=150,
                     subst_ppm=10000, n_ppm=1000, out=None, out_location=MEM_HOST):

@@ -89,6 +89,8 @@ struct kasa_ctx {
         std::vector<void *> opened;                       // cudaIpcOpenMemHandle mappings
         uint64_t *d_stage = nullptr;                      // records this shard computed for its peers, in run order
         cudaEvent_t ev_score0 = nullptr;
+        bool pull_pending = false;                        // kasa_build_shard_pull filled the free brick half with pulled_total records
+        uint64_t pulled_total = 0;
         int phase = 0;                                    // 0 idle, 1 sorted, 2 looked up
         uint32_t n_reads = 0;
     } sh;
@@ -769,9 +771,10 @@ static void shard_common_init(kasa_ctx *c, int rank, int n_shards, const uint32_
     if (!c->sh.d_prefix_begin) {
         c->sh.d_prefix_begin = dev_alloc<uint32_t>(c, KASA_MAX_SHARDS + 1);
         c->sh.d_begin = dev_alloc<uint64_t>(c, KASA_MAX_SHARDS + 1);
-        c->sh.d_stage = n_shards > 1 ? dev_alloc<uint64_t>(c, (size_t)(c->p.max_batch_kmers + 2) * kRecWords) : nullptr;
         KASA_CUDA_TRY(cudaEventCreate(&c->sh.ev_score0));
     }
+    // the record stage is only needed to answer peers' identify queries, i.e. when this context holds an index shard
+    if (n_shards > 1 && c->idx_lo && !c->sh.d_stage) c->sh.d_stage = dev_alloc<uint64_t>(c, (size_t)(c->p.max_batch_kmers + 2) * kRecWords);
     KASA_CUDA_TRY(cudaMemcpyAsync(c->sh.d_prefix_begin, prefix_begin, (n_shards + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->sh.on = true; c->sh.connected = false; c->sh.rank = rank; c->sh.n = n_shards; c->sh.phase = 0;
@@ -876,6 +879,103 @@ int kasa_index_from_build_shard(kasa_ctx *c, const uint32_t *taxid_of_idx, uint3
     KASA_API_END(c)
 }
 
+int kasa_shard_plan_hist(const uint64_t *hist, int k_low, int n_shards, uint32_t *prefix_begin)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(hist && prefix_begin, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(n_shards >= 1 && n_shards <= KASA_MAX_SHARDS && k_low >= 1, KASA_ERR_ARG, "need 1 <= n_shards <= KASA_MAX_SHARDS, k_low >= 1");
+    const int bits = KASA_SHARD_HIST_BITS;
+    const int align_bits = std::min(bits, 5 * std::min(6, k_low));       // boundaries on min(6, k_low)-letter prefixes
+    const uint32_t step = 1u << (bits - align_bits);
+    unsigned __int128 total = 0;
+    for (uint32_t b = 0; b < (1u << bits); ++b) total += hist[b];
+    prefix_begin[0] = 0;
+    uint32_t b = 0;
+    unsigned __int128 cum = 0;                                            // records in bins < b
+    for (int r = 1; r < n_shards; ++r) {
+        const unsigned __int128 want = total * (unsigned)r / (unsigned)n_shards;
+        // advance whole aligned groups while the group's END stays <= want (cut = start of the group holding the candidate)
+        while (b < (1u << bits)) {
+            unsigned __int128 g = 0;
+            for (uint32_t i = 0; i < step; ++i) g += hist[b + i];
+            if (cum + g > want) break;
+            cum += g; b += step;
+        }
+        prefix_begin[r] = b << (30 - bits);
+    }
+    prefix_begin[n_shards] = 1u << 30;
+    KASA_API_END(nullptr)
+}
+
+int kasa_build_shard_local(kasa_ctx *c, uint64_t *hist, uint64_t *n_local)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && hist, KASA_ERR_ARG, "null argument");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    ensure_workspace(c);
+    KASA_REQUIRE(!c->build_done, KASA_ERR_STATE, "kasa_build_shard_local after kasa_build_finish");
+    build_compact(c);
+    const size_t bins = (size_t)1 << KASA_SHARD_HIST_BITS;
+    uint64_t *d_hist = dev_alloc<uint64_t>(c, bins);
+    const int b = c->build_buf;
+    launch_prefix_hist(c->stream, c->sb.w0[b], c->wide ? c->sb.w1[b] : nullptr, c->build_fill, c->K, KASA_SHARD_HIST_BITS, d_hist, &c->launches);
+    KASA_CUDA_TRY(cudaMemcpyAsync(hist, d_hist, bins * 8, cudaMemcpyDeviceToHost, c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    dev_free(c, d_hist);
+    if (n_local) *n_local = c->build_fill;
+    KASA_API_END(c)
+}
+
+int kasa_build_shard_runs(kasa_ctx *c, kasa_shard_runs *mine)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && mine, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(c->sh.on && c->sh.connected, KASA_ERR_STATE, "kasa_build_shard_runs before kasa_shard_init / kasa_shard_connect");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    std::memset(mine, 0, sizeof(*mine));
+    const int b = c->build_buf;
+    mine->n_kmers = c->build_fill;
+    mine->cur = b;
+    launch_run_bounds(c->stream, c->sb.w0[b], c->wide ? c->sb.w1[b] : nullptr, c->build_fill, c->K, c->sh.d_prefix_begin, c->sh.n, c->sh.d_begin,
+                      &c->launches);
+    KASA_CUDA_TRY(cudaMemcpyAsync(mine->begin, c->sh.d_begin, (c->sh.n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    KASA_API_END(c)
+}
+
+int kasa_build_shard_pull(kasa_ctx *c, const kasa_shard_runs *all)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && all, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(c->sh.on && c->sh.connected, KASA_ERR_STATE, "kasa_build_shard_pull before kasa_shard_init / kasa_shard_connect");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    const int me = c->sh.rank, dst = c->build_buf ^ 1;
+    uint64_t total = 0;
+    for (int o = 0; o < c->sh.n; ++o) {
+        const kasa_shard_runs &r = all[o];
+        KASA_REQUIRE(r.cur == 0 || r.cur == 1, KASA_ERR_ARG, "kasa_shard_runs.cur must be 0 or 1");
+        KASA_REQUIRE(r.begin[me] <= r.begin[me + 1] && r.begin[me + 1] <= r.n_kmers, KASA_ERR_ARG, "kasa_shard_runs.begin is not monotone");
+        total += r.begin[me + 1] - r.begin[me];
+    }
+    KASA_REQUIRE(total <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "this shard's records exceed max_batch_kmers");
+    uint64_t off = 0;
+    for (int i = 0; i < c->sh.n; ++i) {
+        const int o = (me + i) % c->sh.n;                  // start with the local run: spreads the NVLink traffic
+        const kasa_shard_runs &r = all[o];
+        const uint64_t b0 = r.begin[me], m = r.begin[me + 1] - b0;
+        if (!m) continue;
+        KASA_CUDA_TRY(cudaMemcpyAsync(c->sb.w0[dst] + off, reinterpret_cast<const uint64_t *>(c->sh.peer[o][r.cur]) + b0, m * 8, cudaMemcpyDefault, c->stream));
+        if (c->wide)
+            KASA_CUDA_TRY(cudaMemcpyAsync(c->sb.w1[dst] + off, reinterpret_cast<const uint64_t *>(c->sh.peer[o][2 + r.cur]) + b0, m * 8, cudaMemcpyDefault, c->stream));
+        KASA_CUDA_TRY(cudaMemcpyAsync(c->sb.v[dst] + off, reinterpret_cast<const uint32_t *>(c->sh.peer[o][4 + r.cur]) + b0, m * 4, cudaMemcpyDefault, c->stream));
+        off += m;
+    }
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->sh.pull_pending = true;                              // adopted by kasa_build_finish, after the host's barrier
+    c->sh.pulled_total = total;
+    KASA_API_END(c)
+}
+
 int kasa_shard_sort(kasa_ctx *c, const kasa_read_batch *in, kasa_shard_runs *mine)
 {
     KASA_API_BEGIN
@@ -884,6 +984,7 @@ int kasa_shard_sort(kasa_ctx *c, const kasa_read_batch *in, kasa_shard_runs *min
     KASA_REQUIRE(c->idx_lo, KASA_ERR_STATE, "kasa_shard_sort before an index shard was loaded");
     KASA_REQUIRE(c->submitted == c->completed, KASA_ERR_STATE, "pipelined batches are still in flight");
     KASA_REQUIRE(c->sh.phase == 0, KASA_ERR_STATE, "kasa_shard_sort: the previous batch has not been scored");
+    KASA_REQUIRE(c->sh.n == 1 || c->sh.d_stage, KASA_ERR_STATE, "load the index shard before kasa_shard_init");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
     kasa_ctx::Slot &sl = c->slot[0];
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[0], c->stream));
@@ -1056,6 +1157,11 @@ int kasa_build_finish(kasa_ctx *c, uint64_t *n_entries, uint64_t *n_trie)
     KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
     ensure_workspace(c);
+    if (c->sh.pull_pending) {                               // prefix-sharded build: the brick is what this shard pulled from its peers
+        c->build_buf ^= 1;
+        c->build_fill = c->sh.pulled_total;
+        c->sh.pull_pending = false;
+    }
     build_compact(c);
     const uint64_t n = c->build_fill;
     const int b = c->build_buf;
@@ -1191,6 +1297,11 @@ int kasa_dbg_sort_pairs(kasa_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t n,
 
 int kasa_synth_build_reference(kasa_ctx *c, uint64_t seed, uint32_t n_taxa, uint64_t genome_len)
 {
+    return kasa_synth_build_reference_range(c, seed, 0, n_taxa, genome_len);
+}
+
+int kasa_synth_build_reference_range(kasa_ctx *c, uint64_t seed, uint32_t first_taxon, uint32_t n_taxa, uint64_t genome_len)
+{
     KASA_API_BEGIN
     KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
@@ -1198,7 +1309,7 @@ int kasa_synth_build_reference(kasa_ctx *c, uint64_t seed, uint32_t n_taxa, uint
     const uint32_t marker = 3 * (c->K - 1);
     KASA_REQUIRE(genome_len + marker <= c->p.max_batch_bases && genome_len < (1ull << 32) - 1024, KASA_ERR_NOMEM,
                  "genome_len exceeds max_batch_bases");
-    for (uint32_t t = 0; t < n_taxa; ++t) {
+    for (uint32_t t = first_taxon; t < first_taxon + n_taxa; ++t) {
         launch_synth_genome(c->stream, seed, t, genome_len, marker, c->d_ascii, &c->launches);
         uint64_t start = 0;
         uint32_t len = (uint32_t)(genome_len + marker), tax = 1000 + t;

@@ -43,7 +43,25 @@ __global__ void shard_plan_kernel(const uint64_t *lo, const uint64_t *hi, uint64
     entry_begin[r] = first_with_prefix_ge(lo, hi, n, K, p);
 }
 
+__global__ void prefix_hist_kernel(const uint64_t *lo, const uint64_t *hi, uint64_t n, int K, int bits, uint64_t *hist)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= (1u << bits)) return;
+    const int sh = 30 - bits;
+    const uint64_t p0 = first_with_prefix_ge(lo, hi, n, K, b << sh);
+    const uint64_t p1 = b + 1 == (1u << bits) ? n : first_with_prefix_ge(lo, hi, n, K, (b + 1) << sh);
+    hist[b] = p1 - p0;
+}
+
 }  // namespace
+
+void launch_prefix_hist(cudaStream_t s, const uint64_t *key_lo, const uint64_t *key_hi, uint64_t n, int K, int bits, uint64_t *hist,
+                        uint64_t *launches)
+{
+    const unsigned bins = 1u << bits;
+    prefix_hist_kernel<<<div_up(bins, 256u), 256, 0, s>>>(key_lo, key_hi, n, K, bits, hist);
+    ++*launches;
+}
 
 void launch_run_bounds(cudaStream_t s, const uint64_t *key_lo, const uint64_t *key_hi, uint64_t n, int K,
                        const uint32_t *prefix_begin, int n_shards, uint64_t *begin, uint64_t *launches)

@@ -16,4 +16,8 @@ void launch_run_bounds(cudaStream_t s, const uint64_t *key_lo, const uint64_t *k
 void launch_shard_plan(cudaStream_t s, const uint64_t *key_lo, const uint64_t *key_hi, uint64_t n, int K, int align_letters,
                        int n_shards, uint64_t *entry_begin, uint32_t *prefix_begin, uint64_t *launches);
 
+// hist[b] = number of sorted keys whose leading `bits` bits equal b, b < 2^bits (bits <= 30)
+void launch_prefix_hist(cudaStream_t s, const uint64_t *key_lo, const uint64_t *key_hi, uint64_t n, int K, int bits, uint64_t *hist,
+                        uint64_t *launches);
+
 }  // namespace kasa

@@ -61,6 +61,27 @@ def _gather_struct(dist, obj, device=None):
     return [cls.from_buffer_copy(buf[i * len(raw):(i + 1) * len(raw)]) for i in range(dist.get_world_size())]
 
 
+def sharded_build_finish(ctx, dist, k_low: int, device=None, fetch: bool = True):
+    """Finish a build whose reference sequences were pushed rank by rank (BASELINE config C4): route every record to the
+    owner of its prefix range (owners pull contiguous runs from the peers' sorted bricks over NVLink), then sort /
+    dedup / run-length encode locally.  Returns (prefix_begin, what Context.build_finish returns for this rank's
+    shard); the shards written in rank order are the reference's index file."""
+    import torch
+    from . import capi
+    hist, _ = ctx.build_shard_local()
+    h = torch.from_numpy(hist.astype(np.int64))
+    if dist.get_backend() == "nccl":
+        h = h.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(h)
+    prefix_begin = capi.shard_plan_hist(h.cpu().numpy().astype(np.uint64), k_low, dist.get_world_size())
+    mem = ctx.shard_init(dist.get_rank(), dist.get_world_size(), prefix_begin)
+    ctx.shard_connect(_gather_struct(dist, mem, device))
+    runs = _gather_struct(dist, ctx.build_shard_runs(), device)
+    ctx.build_shard_pull(runs)
+    dist.barrier()                                            # nobody reads a peer's brick any more
+    return prefix_begin, ctx.build_finish(fetch=fetch)
+
+
 class ShardGroup:
     """One rank's handle on a prefix-sharded identify job: `ctx` already holds shard `rank` of the index."""
 
@@ -101,3 +122,17 @@ class LocalShardGroup:
         for c in self.ctxs:
             c.shard_lookup(runs)
         return [c.shard_score(runs, n_reads[r]) for r, c in enumerate(self.ctxs)]
+
+
+def local_sharded_build_finish(ctxs, k_low: int):
+    """sharded_build_finish for several contexts in one process -> (prefix_begin, [(records, trie)] per shard)."""
+    from . import capi
+    hist = sum(c.build_shard_local()[0] for c in ctxs)
+    prefix_begin = capi.shard_plan_hist(hist, k_low, len(ctxs))
+    mems = [c.shard_init(r, len(ctxs), prefix_begin) for r, c in enumerate(ctxs)]
+    for c in ctxs:
+        c.shard_connect(mems)
+    runs = [c.build_shard_runs() for c in ctxs]
+    for c in ctxs:
+        c.build_shard_pull(runs)
+    return prefix_begin, [c.build_finish() for c in ctxs]

@@ -141,3 +141,21 @@ def test_shard_plan_rejects_bad_arguments():
         capi.shard_plan(idx, 7, 17)
     eb, pb = capi.shard_plan(np.zeros(0, dtype=capi.REC64), 7, 3)           # empty index: every shard empty
     assert list(eb) == [0, 0, 0, 0] and pb[0] == 0 and pb[-1] == 1 << 30
+
+
+def test_shard_plan_hist_balances_on_aligned_buckets():
+    rng = np.random.default_rng(5)
+    hist = rng.integers(0, 1000, size=1 << capi.SHARD_HIST_BITS).astype(np.uint64)
+    hist[:5000] = 0
+    for k_low, n in [(7, 8), (2, 3), (1, 4), (3, 16)]:
+        pb = capi.shard_plan_hist(hist, k_low, n)
+        align_bits = min(15, 5 * min(6, k_low))
+        assert pb[0] == 0 and pb[-1] == 1 << 30 and np.all(np.diff(pb.astype(np.int64)) >= 0)
+        assert np.all(pb[:-1] % (1 << (30 - align_bits)) == 0)
+        cum = np.concatenate([[0], np.cumsum(hist)])
+        total = int(cum[-1])
+        step = 1 << (15 - align_bits)
+        for r in range(1, n):
+            b = int(pb[r]) >> 15
+            want = total * r // n
+            assert int(cum[b]) <= want < int(cum[min(b + step, len(hist))]) or b == len(hist)

@@ -116,3 +116,34 @@ def test_sharded_protocol_errors():
     with pytest.raises(KasaError):                           # score before lookup
         c.shard_score([capi.CShardRuns()], 1)
     c.close()
+
+
+# ----------------------------------------------------------------------------------------- sharded build (C4)
+@pytest.mark.parametrize("case,K,six,n_shards", [("k12", 12, False, 3), ("k12_build6", 12, True, 2), ("k25", 25, False, 4)])
+def test_sharded_build_concatenates_to_the_reference_files(case, K, six, n_shards):
+    """Every rank pushes part of the reference strings; the shards written in rank order must be byte for byte the index
+    and `_trie` the reference binary wrote, and the per-shard frequency tables must add up to its `_f.txt`."""
+    from kasa_b200.dist import local_sharded_build_finish
+    from oracle import oracle as O
+    strings = O.fasta_build_strings(G.gz(case, "ref.fa.gz"), G.acc2tax(case), K, six)
+    _, taxids, _ = G.content(case)
+    ctxs = [Context(Params(highest_k=K, k_high=K, k_low=7, max_batch_kmers=1 << 20)) for _ in range(n_shards)]
+    for i, (s, t) in enumerate(strings):                     # deal the strings (so that every taxon is on several ranks)
+        ctxs[i % n_shards].build_push([s], [t])
+    for c in ctxs:                                           # duplicates across ranks must be removed by the owner
+        c.build_push([strings[0][0]], [strings[0][1]])
+    pb, shards = local_sharded_build_finish(ctxs, 7)
+    rec = np.concatenate([r for r, _ in shards])
+    trie = np.concatenate([t for _, t in shards])
+    assert rec.tobytes() == G.index(case).tobytes()
+    assert trie.tobytes() == G.trie(case).tobytes()
+    freq = sum(c.build_frequency(taxids) for c in ctxs)
+    assert np.array_equal(freq, G.frequency(case))
+    sizes = [len(r) for r, _ in shards]
+    assert max(sizes) < 2.0 * len(rec) / n_shards + 4096     # about equal shards
+    # the shards are directly usable as a prefix-sharded index
+    for c in ctxs:
+        c.index_from_build(taxids)
+    assert sum(c.index_size for c in ctxs) == len(rec)
+    for c in ctxs:
+        c.close()
