@@ -87,6 +87,7 @@ struct kasa_ctx {
         uint64_t *d_begin = nullptr;
         uint64_t peer[KASA_MAX_SHARDS][KASA_SHARD_NBUF] = {};
         std::vector<void *> opened;                       // cudaIpcOpenMemHandle mappings
+        std::vector<kasa_shard_mem> connected_to;         // what `opened` / `peer` were made from
         uint64_t *d_stage = nullptr;                      // records this shard computed for its peers, in run order
         cudaEvent_t ev_score0 = nullptr;
         bool pull_pending = false;                        // kasa_build_shard_pull filled the free brick half with pulled_total records
@@ -815,8 +816,14 @@ int kasa_shard_connect(kasa_ctx *c, const kasa_shard_mem *all)
     KASA_REQUIRE(c && all, KASA_ERR_ARG, "null argument");
     KASA_REQUIRE(c->sh.on, KASA_ERR_STATE, "kasa_shard_connect before kasa_shard_init");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    // mapping a peer's buffers costs ~0.1 s per GB-scale allocation: keep the mappings when the same buffers come again
+    if ((int)c->sh.connected_to.size() == c->sh.n && std::memcmp(c->sh.connected_to.data(), all, sizeof(kasa_shard_mem) * c->sh.n) == 0) {
+        c->sh.connected = true;
+        return KASA_OK;
+    }
     for (void *p : c->sh.opened) cudaIpcCloseMemHandle(p);
     c->sh.opened.clear();
+    c->sh.connected_to.clear();
     const uint64_t me = (uint64_t)getpid();
     for (int o = 0; o < c->sh.n; ++o) {
         const kasa_shard_mem &m = all[o];
@@ -839,6 +846,7 @@ int kasa_shard_connect(kasa_ctx *c, const kasa_shard_mem *all)
             c->sh.peer[o][b] = (uint64_t)(uintptr_t)p;
         }
     }
+    c->sh.connected_to.assign(all, all + c->sh.n);
     c->sh.connected = true;
     KASA_API_END(c)
 }

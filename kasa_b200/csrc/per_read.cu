@@ -105,9 +105,8 @@ __global__ void __launch_bounds__(kTxBlock) per_read_taxon_kernel(const uint4 *_
                 if (s + 32 < s1) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 2 * (s + 32)));   // next chunk
                 uint64_t R0 = 0, R1 = 0, R2 = 0, np = 0;
                 if (s < s1) {
-                    const uint4 x0 = __ldg(rec + 2 * s), x1 = __ldg(rec + 2 * s + 1);
-                    R0 = (uint64_t)x0.x | ((uint64_t)x0.y << 32); R1 = (uint64_t)x0.z | ((uint64_t)x0.w << 32);
-                    R2 = (uint64_t)x1.x | ((uint64_t)x1.y << 32); np = (uint64_t)x1.z | ((uint64_t)x1.w << 32);
+                    // one 256-bit load per record (LDG.256, sm_100)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(R0), "=l"(R1), "=l"(R2), "=l"(np) : "l"(rec + 2 * s));
                 }
                 s_rec[w][0][lane] = R0; s_rec[w][1][lane] = R1; s_rec[w][2][lane] = R2; s_rec[w][3][lane] = np;
                 // bytes of np equal to 1 -> 0x01 (exact zero-byte test on np ^ 0x0101..)

@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(kRadix) hist_scan_kernel(unsigned long long *g
 // Resource plan (B200: 64 K registers, 227 KB shared memory per SM): 512 threads x 8 items at <= 64
 // registers -> 2 CTAs = 32 warps per SM; 52 KB dynamic shared memory per CTA.  The kernel is latency
 // bound per tile (rank chain + look-back), so resident warps are what buys bandwidth.
+constexpr uint32_t kPrefetchAhead = 2 * kSMs;   // CTAs resident at once (2 per SM)
+
 template <int BLOCK, int ITEMS, bool HAS_W1>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
     const uint64_t *__restrict__ in_w0, const uint64_t *__restrict__ in_w1, const uint32_t *__restrict__ in_v,
@@ -102,6 +104,23 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
     const uint32_t n_tile = (uint32_t)min((uint64_t)TILE, n - base);
     const uint64_t wbase = base + (uint64_t)w * (32 * ITEMS) + lane;
     const bool v_is_src = (src == SRC_V);
+
+    // ---- pull the tile that will start when the resident ones retire into L2 (tickets are handed out in order, so
+    // that is tile + resident CTAs): its loads then see L2 latency instead of HBM latency at the head of its critical path
+    {
+        const uint64_t pbase = ((uint64_t)tile + kPrefetchAhead) * TILE;
+        if (pbase < n) {
+            const uint32_t m = (uint32_t)min((uint64_t)TILE, n - pbase);
+            for (uint32_t line = tid; line < TILE / 16; line += BLOCK) {          // 128-byte lines of the 64-bit words
+                if (line * 16 < m) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(in_w0 + pbase + line * 16));
+                    if (HAS_W1) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_w1 + pbase + line * 16));
+                }
+            }
+            for (uint32_t line = tid; line < TILE / 32; line += BLOCK)
+                if (line * 32 < m) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_v + pbase + line * 32));
+        }
+    }
 
     // ---- load the digit source
     uint64_t key[ITEMS];

@@ -66,9 +66,12 @@ def sharded_build_finish(ctx, dist, k_low: int, device=None, fetch: bool = True)
     owner of its prefix range (owners pull contiguous runs from the peers' sorted bricks over NVLink), then sort /
     dedup / run-length encode locally.  Returns (prefix_begin, what Context.build_finish returns for this rank's
     shard); the shards written in rank order are the reference's index file."""
+    import time
     import torch
     from . import capi
+    t = [time.perf_counter()]
     hist, _ = ctx.build_shard_local()
+    t.append(time.perf_counter())
     h = torch.from_numpy(hist.astype(np.int64))
     if dist.get_backend() == "nccl":
         h = h.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
@@ -76,10 +79,15 @@ def sharded_build_finish(ctx, dist, k_low: int, device=None, fetch: bool = True)
     prefix_begin = capi.shard_plan_hist(h.cpu().numpy().astype(np.uint64), k_low, dist.get_world_size())
     mem = ctx.shard_init(dist.get_rank(), dist.get_world_size(), prefix_begin)
     ctx.shard_connect(_gather_struct(dist, mem, device))
+    t.append(time.perf_counter())
     runs = _gather_struct(dist, ctx.build_shard_runs(), device)
     ctx.build_shard_pull(runs)
     dist.barrier()                                            # nobody reads a peer's brick any more
-    return prefix_begin, ctx.build_finish(fetch=fetch)
+    t.append(time.perf_counter())
+    out = ctx.build_finish(fetch=fetch)
+    t.append(time.perf_counter())
+    sharded_build_finish.last_phase_s = dict(zip(("local_sort_dedup", "plan_and_connect", "pull", "sort_dedup_trie"), np.diff(t).tolist()))
+    return prefix_begin, out
 
 
 class ShardGroup:

@@ -47,13 +47,13 @@ def main():
         t2 = time.perf_counter()
         tot = torch.tensor([n_entries, n_trie], dtype=torch.int64, device=dev)
         dist.all_reduce(tot)
-        times.append((t2 - t0, t1 - t0, int(tot[0]), int(tot[1]), n_entries))
+        times.append((t2 - t0, t1 - t0, int(tot[0]), int(tot[1]), n_entries, dict(sharded_build_finish.last_phase_s)))
     if rank == 0:
         best = min(times)
         print(json.dumps({"what": "sharded build (extract + route by prefix + sort + dedup + trie)", "n_gpus": world, "taxa": a.taxa,
                           "genome_len": a.genome_len, "bases": a.taxa * a.genome_len, "index_entries": best[2], "trie_records": best[3],
                           "entries_rank0": best[4], "seconds": best[0], "seconds_extract": best[1],
-                          "bases_per_s": a.taxa * a.genome_len / best[0], "all_runs_s": [t[0] for t in times]}), flush=True)
+                          "phases_s": best[5], "bases_per_s": a.taxa * a.genome_len / best[0], "all_runs_s": [t[0] for t in times]}), flush=True)
     ctx.close()
     dist.destroy_process_group()
 
