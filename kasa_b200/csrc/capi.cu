@@ -185,7 +185,7 @@ void ensure_workspace(kasa_ctx *c)
     c->d_scan_tmp = dev_alloc<uint64_t>(c, scan_tmp_elems(std::max<uint64_t>(cap + 1, ns + 1)) + 1);
     c->d_taxid = dev_alloc<uint32_t>(c, (size_t)ns + 1);
     c->d_part = dev_alloc<uint64_t>(c, 2 * (size_t)div_up<uint64_t>(cap, 32) + 2);
-    c->d_rec = dev_alloc<uint64_t>(c, (size_t)(cap + 2) * kRecWords);
+    c->d_rec = dev_alloc<uint64_t>(c, (size_t)(cap + 2) * record_words(c->hb));
     c->ws_ready = true;
 }
 
@@ -775,7 +775,7 @@ static void shard_common_init(kasa_ctx *c, int rank, int n_shards, const uint32_
         KASA_CUDA_TRY(cudaEventCreate(&c->sh.ev_score0));
     }
     // the record stage is only needed to answer peers' identify queries, i.e. when this context holds an index shard
-    if (n_shards > 1 && c->idx_lo && !c->sh.d_stage) c->sh.d_stage = dev_alloc<uint64_t>(c, (size_t)(c->p.max_batch_kmers + 2) * kRecWords);
+    if (n_shards > 1 && c->idx_lo && !c->sh.d_stage) c->sh.d_stage = dev_alloc<uint64_t>(c, (size_t)(c->p.max_batch_kmers + 2) * record_words(c->hb));
     KASA_CUDA_TRY(cudaMemcpyAsync(c->sh.d_prefix_begin, prefix_begin, (n_shards + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->sh.on = true; c->sh.connected = false; c->sh.rank = rank; c->sh.n = n_shards; c->sh.phase = 0;
@@ -1057,7 +1057,7 @@ int kasa_shard_lookup(kasa_ctx *c, const kasa_shard_runs *all)
         const uint64_t *q_lo = reinterpret_cast<const uint64_t *>(c->sh.peer[o][r.cur]) + b0;
         const uint64_t *q_hi = c->wide ? reinterpret_cast<const uint64_t *>(c->sh.peer[o][2 + r.cur]) + b0 : nullptr;
         const uint32_t *inst = o == me ? c->sb.v[r.cur] + b0 : nullptr;
-        uint64_t *rec = o == me ? c->d_rec : c->sh.d_stage + seg[o] * kRecWords;
+        uint64_t *rec = o == me ? c->d_rec : c->sh.d_stage + seg[o] * record_words(c->hb);
         const uint32_t tq = lookup_tile_queries(m, c->idx_n);
         launch_partition(c->stream, q_lo, q_hi, m, idx, lp, c->d_part, tq, sorted_from, &c->launches);
         launch_lookup(c->stream, q_lo, q_hi, inst, m, idx, lp, c->d_part, rec, tq, &c->launches);
@@ -1089,8 +1089,8 @@ int kasa_shard_score(kasa_ctx *c, const kasa_shard_runs *all, kasa_batch_result 
         uint64_t seg = 0;                                     // where owner w staged this origin's segment
         for (int o = 0; o < me; ++o) seg += o == w ? 0 : all[o].begin[w + 1] - all[o].begin[w];
         const uint64_t b0 = mine.begin[w], m = mine.begin[w + 1] - b0;
-        launch_scatter_records(c->stream, reinterpret_cast<const uint64_t *>(c->sh.peer[w][7]) + seg * kRecWords, c->sb.v[mine.cur] + b0, m,
-                               c->d_rec, &c->launches);
+        launch_scatter_records(c->stream, reinterpret_cast<const uint64_t *>(c->sh.peer[w][7]) + seg * record_words(c->hb), c->sb.v[mine.cur] + b0, m,
+                               c->d_rec, record_words(c->hb), &c->launches);
     }
     if (n) {
         launch_per_read(c->stream, c->d_rec, c->d_read_koff, n_reads, lp, want_scores ? sl.scores : nullptr, c->d_cnt_fx, c->d_cnt_un,

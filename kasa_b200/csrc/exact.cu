@@ -56,8 +56,10 @@ __global__ void __launch_bounds__(256) exact_flags_kernel(const uint64_t *__rest
         c = common_letters<W>(p, q, lp.K);
     }
     // levels matched = largest field of the record
-    const uint64_t *R = rec + (uint64_t)inst[i] * kRecWords;
-    uint64_t Rw[kRecWords] = {R[0], R[1], R[2], R[3]};
+    const int RWn = record_words(lp.hb);
+    const uint64_t *R = rec + (uint64_t)inst[i] * RWn;
+    uint64_t Rw[8];
+    for (int x = 0; x < RWn; ++x) Rw[x] = R[x];
     uint32_t hmax = 0;
     for (int s = 0; s < lp.n_taxa - 1; ++s) hmax = max(hmax, rec_field(Rw, s, lp.hb));
     // is the range prefix present?  closest index neighbours of q
@@ -139,7 +141,8 @@ __global__ void __launch_bounds__(kExactBlock) exact_scores_kernel(const uint64_
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *s_rec = reinterpret_cast<uint64_t *>(smem_raw);              // [max_inst][4]
-    uint64_t *s_key = s_rec + (size_t)max_inst * kRecWords;                // [cap_pairs]
+    const int RWn = record_words(lp.hb);
+    uint64_t *s_key = s_rec + (size_t)max_inst * RWn;                      // [cap_pairs]
     __shared__ uint32_t s_n;
     __shared__ float s_w[32];
     const int tid = threadIdx.x, T = lp.n_taxa, NK = lp.num_k;
@@ -148,14 +151,14 @@ __global__ void __launch_bounds__(kExactBlock) exact_scores_kernel(const uint64_
         const uint64_t s0 = read_koff[r];
         const uint32_t ni = (uint32_t)(read_koff[r + 1] - s0);
         if (tid == 0) s_n = 0;
-        for (uint32_t x = tid; x < ni * kRecWords; x += kExactBlock) s_rec[x] = rec[s0 * kRecWords + x];
+        for (uint32_t x = tid; x < ni * RWn; x += kExactBlock) s_rec[x] = rec[s0 * RWn + x];
         __syncthreads();
         // (instance, level) pairs with at least one taxon
         for (uint32_t x = tid; x < ni * (uint32_t)NK; x += kExactBlock) {
             const uint32_t s = x / NK;
             const int j = (int)(x % NK);
             uint32_t nj = 0;
-            for (int sl = 0; sl < T - 1; ++sl) nj += rec_field(s_rec + (size_t)s * kRecWords, sl, lp.hb) > (uint32_t)j;
+            for (int sl = 0; sl < T - 1; ++sl) nj += rec_field(s_rec + (size_t)s * RWn, sl, lp.hb) > (uint32_t)j;
             if (nj) {
                 const uint32_t o = atomicAdd(&s_n, 1u);
                 s_key[o] = ((uint64_t)trig[(s0 + s) * NK + j] << 29) | ((uint64_t)j << 24) | ((uint64_t)nj << 16) | s;
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(kExactBlock) exact_scores_kernel(const uint64_
                 const uint64_t key = s_key[x];
                 const uint32_t s = (uint32_t)key & 0xffffu, nj = (uint32_t)(key >> 16) & 0xffu;
                 const int j = (int)((key >> 24) & 31u);
-                if (rec_field(s_rec + (size_t)s * kRecWords, t - 1, lp.hb) > (uint32_t)j) acc = __fadd_rn(acc, __fmul_rn(s_w[j], __fdiv_rn(1.f, (float)nj)));   // Compare.hpp:924, 530: product rounded, then added
+                if (rec_field(s_rec + (size_t)s * RWn, t - 1, lp.hb) > (uint32_t)j) acc = __fadd_rn(acc, __fmul_rn(s_w[j], __fdiv_rn(1.f, (float)nj)));   // Compare.hpp:924, 530: product rounded, then added
             }
             scores[(uint64_t)r * T + t] = acc;
         }
@@ -226,7 +229,7 @@ bool launch_exact_scores(cudaStream_t s, const uint64_t *rec, const uint32_t *tr
     if (!n_reads) return true;
     uint64_t pairs = (uint64_t)max_inst * lp.num_k, cap = 1;
     while (cap < pairs) cap <<= 1;
-    const size_t sm = (size_t)max_inst * kRecWords * 8 + cap * 8;
+    const size_t sm = (size_t)max_inst * record_words(lp.hb) * 8 + cap * 8;
     if (max_inst > 65535 || sm > 200 * 1024) return false;
     KASA_CUDA_TRY(cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     unsigned grid = n_reads < (unsigned)kSMs * 8 ? n_reads : (unsigned)kSMs * 8;

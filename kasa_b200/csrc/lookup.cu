@@ -117,7 +117,7 @@ __device__ __forceinline__ int64_t lower_bound(const Acc &acc, int64_t lo, int64
 // sizes |taxa_j| (one byte per level j, the fourth word of a 3-bit record): raising a field from cur to h adds
 // the taxon to the levels cur .. h-1
 template <int HB>
-__device__ __forceinline__ void rec_raise(uint64_t (&rw)[kRecWords], uint64_t &np, uint32_t taxon, uint32_t h)
+__device__ __forceinline__ void rec_raise(uint64_t (&rw)[kRW<HB>], uint64_t &np, uint32_t taxon, uint32_t h)
 {
     constexpr int FPW = 64 / HB;
     constexpr uint64_t HM = (1ull << HB) - 1;
@@ -125,7 +125,7 @@ __device__ __forceinline__ void rec_raise(uint64_t (&rw)[kRecWords], uint64_t &n
     const uint32_t sl = taxon - 1, wi = sl / FPW;
     const int sh = (int)(sl % FPW) * HB;
 #pragma unroll
-    for (int i = 0; i < kRecWords; ++i) {
+    for (int i = 0; i < kRW<HB>; ++i) {
         if (HB == 3 && i == 3) break;                 // 3-bit records keep their fields in three words
         if ((uint32_t)i == wi) {
             const uint32_t cur = (uint32_t)(rw[i] >> sh) & (uint32_t)HM;
@@ -218,7 +218,7 @@ __device__ __forceinline__ int last_valid_level(const Key &q, const LevelParams 
 // k = k_low .. min(c, kv); those entries start at the lower bound of the query's k_low-letter prefix.
 template <bool W, int HB>
 __device__ __forceinline__ void match_query_gmem(const GmemAcc &acc, int64_t a, int64_t b, const Key &q, int kv,
-                                                 const LevelParams &lp, uint64_t (&rw)[kRecWords], uint64_t &np)
+                                                 const LevelParams &lp, uint64_t (&rw)[kRW<HB>], uint64_t &np)
 {
     const int low_sh = 5 * (lp.K - lp.k_low);
     for (int64_t e = lower_bound<W>(acc, a, b, prefix_floor<W>(q, low_sh)); e < b; ++e) {
@@ -406,11 +406,14 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
     for (int r = 0; r < QPT; ++r) {
         if (r * kLookupBlock >= (int)tq) break;             // CTA-uniform
         if (!live[r]) continue;
-        uint64_t rw[kRecWords] = {0, 0, 0, 0};
+        constexpr int RW = kRW<HB>;
+        uint64_t rw[RW];
+#pragma unroll
+        for (int i = 0; i < RW; ++i) rw[i] = 0;
         uint64_t np = (uint32_t)__popcll(mask[r]);
         if (staged) {
 #pragma unroll
-            for (int i = 0; i < kRecWords; ++i)
+            for (int i = 0; i < RW; ++i)
                 if (i * FPW < 64 && !(HB == 3 && i == 3)) rw[i] = spread_fields<HB>(mask[r] >> (i * FPW));
             for (uint32_t e = up[r] >> 12, end = (up[r] >> 12) + (up[r] & 4095u); e < end; ++e)
                 rec_raise<HB>(rw, np, s_tax[e], match_levels<W>(skey((int)e), qv[r], kv[r], lp));
@@ -419,9 +422,11 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
         }
         if (HB == 3) rw[3] = np;
         // one 256-bit store = one full 32-byte sector per record (STG.256, sm_100)
-        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)iv[r] * kRecWords), "l"(rw[0]), "l"(rw[1]), "l"(rw[2]),
-                     "l"(rw[3])
-                     : "memory");
+#pragma unroll
+        for (int i = 0; i < RW; i += 4)
+            asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)iv[r] * RW + i), "l"(rw[i]), "l"(rw[i + 1]),
+                         "l"(rw[i + 2]), "l"(rw[i + 3])
+                         : "memory");
     }
 }
 
@@ -429,14 +434,16 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
 // run (contiguous, so the NVLink side is a streaming read) and scatters them into emission order in its own HBM.
 // Scattered stores INTO peer memory run ~100x slower than this (measured: DESIGN.md §5), hence the pull.
 __global__ void __launch_bounds__(256) scatter_records_kernel(const uint64_t *__restrict__ staged, const uint32_t *__restrict__ inst,
-                                                              uint64_t n, uint64_t *__restrict__ rec)
+                                                              uint64_t n, uint64_t *__restrict__ rec, int rec_words)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t a, b, c, d;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(staged + i * kRecWords));
     const uint32_t j = ldg_stream(inst + i);
-    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)j * kRecWords), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+    for (int o = 0; o < rec_words; o += 4) {
+        uint64_t a, b, c, d;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(staged + i * rec_words + o));
+        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)j * rec_words + o), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -498,20 +505,27 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
             const uint32_t trips = __reduce_max_sync(kFull, mine);     // warp-uniform trip count
 #pragma unroll 1
             for (uint32_t it = 0; it < trips; ++it) {
-                uint64_t R[kRecWords] = {0, 0, 0, 0};
+                constexpr int RW = kRW<HB>;
+                uint64_t R[RW];
+                uint64_t any = 0;
+#pragma unroll
+                for (int i = 0; i < RW; ++i) R[i] = 0;
                 if (it < mine) {
-                    const uint4 x0 = __ldg(rec + 2 * (cur + it)), x1 = __ldg(rec + 2 * (cur + it) + 1);
-                    R[0] = (uint64_t)x0.x | ((uint64_t)x0.y << 32); R[1] = (uint64_t)x0.z | ((uint64_t)x0.w << 32);
-                    R[2] = (uint64_t)x1.x | ((uint64_t)x1.y << 32); R[3] = (uint64_t)x1.z | ((uint64_t)x1.w << 32);
+#pragma unroll
+                    for (int i = 0; i < RW / 2; ++i) {
+                        const uint4 x = __ldg(rec + (RW / 2) * (cur + it) + i);
+                        R[2 * i] = (uint64_t)x.x | ((uint64_t)x.y << 32); R[2 * i + 1] = (uint64_t)x.z | ((uint64_t)x.w << 32);
+                        any |= R[2 * i] | R[2 * i + 1];
+                    }
                 }
-                if ((R[0] | R[1] | R[2] | R[3]) != 0) {
+                if (any != 0) {
                     {
                     // pass 1: n_j = |taxa at level j| (byte counters)
                     uint64_t nl[LW];
 #pragma unroll
                     for (int i = 0; i < LW; ++i) nl[i] = 0;
 #pragma unroll
-                    for (int wi = 0; wi < kRecWords; ++wi) {
+                    for (int wi = 0; wi < RW; ++wi) {
                         uint64_t w = R[wi];
                         while (w) {
                             int f = (__ffsll((long long)w) - 1) / HB;
@@ -524,7 +538,7 @@ __global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__res
                     }
                     // pass 2: contributions, k ascending (Compare.hpp:924-925: score = w(k) * (1.f / n), counts 1/n)
 #pragma unroll
-                    for (int wi = 0; wi < kRecWords; ++wi) {
+                    for (int wi = 0; wi < RW; ++wi) {
                         uint64_t w = R[wi];
                         while (w) {
                             int f = (__ffsll((long long)w) - 1) / HB;
@@ -621,10 +635,11 @@ void launch_lookup_hb(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi
 
 }  // namespace
 
-void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32_t *inst, uint64_t n, uint64_t *rec, uint64_t *launches)
+void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32_t *inst, uint64_t n, uint64_t *rec, int rec_words,
+                            uint64_t *launches)
 {
     if (!n) return;
-    scatter_records_kernel<<<(unsigned)div_up<uint64_t>(n, 256), 256, 0, s>>>(staged, inst, n, rec);
+    scatter_records_kernel<<<(unsigned)div_up<uint64_t>(n, 256), 256, 0, s>>>(staged, inst, n, rec, rec_words);
     ++*launches;
 }
 

@@ -25,12 +25,17 @@ struct LevelParams {
 
 constexpr int kLookupTile = 1024;      // most sorted queries per CTA (see lookup_tile_queries)
 constexpr int kLookupBlock = 256;
-constexpr int kRecWords = 4;           // match record = 4 x u64 = one 32-byte sector
+// match record = 4 x u64 = one 32-byte sector for 3- and 4-bit level fields, 8 x u64 = two sectors for 5-bit fields
+// (16..31 levels, e.g. k = 25..7: 12 fields per word)
+constexpr int kRecWords = 4;
+template <int HB>
+constexpr int kRW = HB == 5 ? 8 : 4;
+__host__ __device__ inline int record_words(int hb) { return hb == 5 ? 8 : 4; }
 
 // bits needed to store a level count 0..num_k, and how many taxa one record can describe
 inline int record_level_bits(int num_k) { return num_k <= 7 ? 3 : (num_k <= 15 ? 4 : 5); }
-// 3-bit records keep their fourth word for a dense bit mask of the taxa matched at k_low (see lookup.cu)
-inline int record_taxa_capacity(int hb) { return hb == 3 ? 63 : kRecWords * (64 / hb); }
+// 3-bit records keep their fourth word for the level sizes (see lookup.cu); the lookup kernel's taxa set is a 64-bit mask
+inline int record_taxa_capacity(int hb) { return hb == 3 ? 63 : 64; }
 
 // per-tile index spans: part[2t], part[2t+1] = [first entry sharing the sorted prefix of the tile's first query,
 // one past the last entry sharing the sorted prefix of its last query).  The queries only need to be ordered
@@ -47,7 +52,8 @@ void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, c
 
 // inst == nullptr: record i is written to rec[i] (sorted position; the prefix-sharded path stages records this way)
 // rec[inst[i]] = staged[i] for i < n (staged may be peer memory)
-void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32_t *inst, uint64_t n, uint64_t *rec, uint64_t *launches);
+void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32_t *inst, uint64_t n, uint64_t *rec, int rec_words,
+                            uint64_t *launches);
 
 // per read: fp32 scores in canonical order (instance order, k ascending) and the per-taxon per-level
 // counts: cnt_fx [num_k][n_taxa] fixed point 2^-32 (sum of 1/|taxa|), cnt_unique [num_k][n_taxa].

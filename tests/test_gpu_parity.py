@@ -306,3 +306,51 @@ def test_pipelined_submit_wait_matches_batch_calls():
     with pytest.raises(KasaError):
         ctx.identify_wait()                                   # nothing submitted
     ctx.close()
+
+
+# ----------------------------------------------------------------------------------------- taxa capacity of the records
+@pytest.mark.parametrize("K,k_high,k_low,n_taxa", [(12, 12, 7, 63), (12, 12, 1, 64), (25, 25, 7, 64), (25, 25, 7, 50)])
+def test_identify_at_the_record_taxa_capacity(K, k_high, k_low, n_taxa):
+    """63 taxa with 3-bit level fields (<= 7 levels), 64 with 4-bit (<= 15) and 5-bit fields (<= 31 levels, two-sector
+    records: BASELINE config C3 = 50 taxa at k = 25..7).  Shared regions make many taxa meet in one k-mer group."""
+    glen, n_reads = 2500, 120
+    taxids = np.array([0] + [1000 + t for t in range(n_taxa)], dtype=np.uint32)
+    rng = np.random.default_rng(K * 1000 + n_taxa)
+    shared = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 400))
+    fasta, genomes = b"", []
+    for t in range(n_taxa):
+        g = bytearray(synth.genome_ascii(9, t, glen))
+        g[300:700] = shared                                   # every taxon carries the same 400 bp: groups of n_taxa taxa
+        if t % 2:
+            g[1000:1200] = shared[:200]
+        genomes.append(bytes(g))
+        fasta += b">" + synth.accession(t).encode() + b"\n" + bytes(g) + b"\n"
+    acc2tax = {synth.accession(t): 1000 + t for t in range(n_taxa)}
+    index, _ = O.build_index(fasta, acc2tax, K, six=False)
+    reads = []
+    for i in range(n_reads):
+        g = genomes[int(rng.integers(n_taxa))]
+        o = int(rng.integers(0, glen - 150))
+        reads.append(g[o:o + 150])
+    reads += [shared[:150], shared[100:250]]
+    ctx = _ctx(highest_k=K, k_high=k_high, k_low=k_low, frames=6, max_batch_kmers=1 << 20)
+    ctx.load_index(index, taxids)
+    n_kmers, scores, _ = ctx.identify_batch(reads)
+    ca, cu, _ = ctx.identify_finish()
+    ctx.close()
+    ora = O.identify_reads([[r] for r in reads], index, K, k_high, k_low, True, taxids)
+    assert n_kmers == ora.n_kmers
+    assert np.array_equal(cu, ora.count_unique)
+    np.testing.assert_allclose(ca, ora.count_all, rtol=COUNT_RTOL, atol=1e-9)
+    assert np.array_equal(scores > 0, ora.scores > 0)
+    # more levels = more fp32 adds per cell: the order-dependent rounding of the reference's sums grows (as in the k25 golden test)
+    np.testing.assert_allclose(scores, ora.scores, rtol=3e-5 if k_high - k_low + 1 > 7 else FAST_RTOL)
+
+
+def test_more_taxa_than_a_record_holds_is_rejected_loudly():
+    taxids = np.arange(66, dtype=np.uint32)                  # 65 taxa + "non_unique"
+    ctx = _ctx()
+    with pytest.raises(KasaError) as e:
+        ctx.load_index(np.zeros(0, dtype=capi.REC64), taxids)
+    assert "at most" in str(e.value)
+    ctx.close()
