@@ -1,4 +1,6 @@
 // radix_sort.cu — see radix_sort.cuh.
+#include <cstdlib>
+
 #include "radix_sort.cuh"
 
 namespace kasa {
@@ -31,16 +33,28 @@ __global__ void __launch_bounds__(512) hist_kernel(const uint64_t *__restrict__ 
     const int P = plan.n_passes;
     for (int i = threadIdx.x; i < P * kRadix; i += blockDim.x) sh[i] = 0;
     __syncthreads();
+    // four independent loads per thread and iteration: the kernel is bound by bytes in flight, not by the atomics
+    constexpr int U = 4;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint64_t a = need_w0 ? ldg_stream(w0 + i) : 0;
-        uint64_t b = (HAS_W1 && need_w1) ? ldg_stream(w1 + i) : 0;
-        uint64_t c = need_v ? (uint64_t)ldg_stream(v + i) : 0;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+        uint64_t a[U], b[U], c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + u * stride;
+            const bool ok = i < n;
+            a[u] = (need_w0 && ok) ? ldg_stream(w0 + i) : 0;
+            b[u] = (HAS_W1 && need_w1 && ok) ? ldg_stream(w1 + i) : 0;
+            c[u] = (need_v && ok) ? (uint64_t)ldg_stream(v + i) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * stride >= n) break;
 #pragma unroll 4
-        for (int p = 0; p < P; ++p) {
-            uint64_t word = plan.src[p] == SRC_W0 ? a : (plan.src[p] == SRC_W1 ? b : c);
-            uint32_t d = (uint32_t)(word >> plan.shift[p]) & plan.mask[p];
-            atomicAdd(&sh[p * kRadix + d], 1u);
+            for (int p = 0; p < P; ++p) {
+                uint64_t word = plan.src[p] == SRC_W0 ? a[u] : (plan.src[p] == SRC_W1 ? b[u] : c[u]);
+                uint32_t d = (uint32_t)(word >> plan.shift[p]) & plan.mask[p];
+                atomicAdd(&sh[p * kRadix + d], 1u);
+            }
         }
     }
     __syncthreads();
@@ -77,7 +91,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
     const uint64_t *__restrict__ in_w0, const uint64_t *__restrict__ in_w1, const uint32_t *__restrict__ in_v,
     uint64_t *__restrict__ out_w0, uint64_t *__restrict__ out_w1, uint32_t *__restrict__ out_v, uint64_t n, int src,
     int shift, uint32_t mask, const unsigned long long *__restrict__ digit_start, uint64_t *status,
-    uint32_t *ticket, uint32_t *err_flag)
+    uint32_t *ticket, uint32_t *err_flag, uint32_t prefetch_ahead)
 {
     constexpr int TILE = BLOCK * ITEMS;
     constexpr int NW = BLOCK / 32;
@@ -108,8 +122,8 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
     // ---- pull the tile that will start when the resident ones retire into L2 (tickets are handed out in order, so
     // that is tile + resident CTAs): its loads then see L2 latency instead of HBM latency at the head of its critical path
     {
-        const uint64_t pbase = ((uint64_t)tile + kPrefetchAhead) * TILE;
-        if (pbase < n) {
+        const uint64_t pbase = ((uint64_t)tile + prefetch_ahead) * TILE;
+        if (prefetch_ahead && pbase < n) {
             const uint32_t m = (uint32_t)min((uint64_t)TILE, n - pbase);
             for (uint32_t line = tid; line < TILE / 16; line += BLOCK) {          // 128-byte lines of the 64-bit words
                 if (line * 16 < m) {
@@ -387,6 +401,7 @@ int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint6
                                            cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
+    static const uint32_t ahead = [] { const char *e = getenv("KASA_TUNE_SORT_PREFETCH"); return e ? (uint32_t)atoi(e) : kPrefetchAhead; }();
     int cur = start_buf;
     for (int p = 0; p < plan.n_passes; ++p) {
         KASA_CUDA_TRY(cudaMemsetAsync(ticket, 0, 4, stream));
@@ -395,11 +410,11 @@ int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint6
         if (has_w1)
             onesweep_kernel<kSortBlock, kSortItems, true><<<(unsigned)tiles, kSortBlock, sm_pass, stream>>>(
                 buf.w0[cur], buf.w1[cur], buf.v[cur], buf.w0[nxt], buf.w1[nxt], buf.v[nxt], n, plan.pass[p].src,
-                plan.pass[p].shift, plan.pass[p].mask, ghist + (size_t)p * kRadix, status, ticket, err_flag);
+                plan.pass[p].shift, plan.pass[p].mask, ghist + (size_t)p * kRadix, status, ticket, err_flag, ahead);
         else
             onesweep_kernel<kSortBlock, kSortItems, false><<<(unsigned)tiles, kSortBlock, sm_pass, stream>>>(
                 buf.w0[cur], nullptr, buf.v[cur], buf.w0[nxt], nullptr, buf.v[nxt], n, plan.pass[p].src,
-                plan.pass[p].shift, plan.pass[p].mask, ghist + (size_t)p * kRadix, status, ticket, err_flag);
+                plan.pass[p].shift, plan.pass[p].mask, ghist + (size_t)p * kRadix, status, ticket, err_flag, ahead);
         *launches += 1;
         cur = nxt;
     }
