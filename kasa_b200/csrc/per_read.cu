@@ -13,7 +13,7 @@
 // time, by "their" lane, which turns the record's level sizes (|taxa_j|, the record's fourth word, written by
 // the lookup kernel) into an 8-entry table indexed by the level count h a taxon can have in this instance:
 //     entry[h] = one bit per level j < h with |taxa_j| == 1 (8-bit fields)
-// The main pass is then a branch-free, warp-uniform walk over the instances: every lane extracts its taxon's
+// The main pass is then a branch-free, warp-uniform walk over the instances with a non-empty record (rows are stored compacted): every lane extracts its taxon's
 // 3-bit field h from the record (LDS + SHF + LOP), fetches entry[h] (one conflict-free LDS.64), adds it to packed
 // per-level unique counters, and adds min(h, 1) * 2^32/|taxa_0| (shared k_low hits, the bulk: stray 7-mer hits)
 // to a 64-bit accumulator with one IMAD.WIDE.  No shared-memory read-modify-write, no atomics, no divergence.  Instances where a level above k_low is shared by several taxa (a few per cent) are
@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(kTxBlock) per_read_taxon_kernel(const uint4 *_
 #pragma unroll 1
         for (uint64_t c0 = s0; c0 < s1; c0 += 32, ++chunk) {
             // ---- pre-pass: lane = instance
-            uint32_t rare_mask;
+            uint32_t rare_mask, ne;
+            int n_ne;
             {
                 const uint64_t s = c0 + lane;
                 if (s + 32 < s1) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 2 * (s + 32)));   // next chunk
@@ -108,24 +109,28 @@ __global__ void __launch_bounds__(kTxBlock) per_read_taxon_kernel(const uint4 *_
                     // one 256-bit load per record (LDG.256, sm_100)
                     asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(R0), "=l"(R1), "=l"(R2), "=l"(np) : "l"(rec + 2 * s));
                 }
-                s_rec[w][0][lane] = R0; s_rec[w][1][lane] = R1; s_rec[w][2][lane] = R2; s_rec[w][3][lane] = np;
+                // rows are stored compacted: instances with a non-empty record first, so that the main pass only walks those
+                // (a quarter of the records of a typical read are empty); integer sums do not care about the order
+                ne = __ballot_sync(kFull, (uint32_t)np != 0u);
+                n_ne = __popc(ne);
+                const int row_i = ((uint32_t)np != 0u) ? __popc(ne & lanemask_lt()) : n_ne + __popc(~ne & lanemask_lt());
+                s_rec[w][0][row_i] = R0; s_rec[w][1][row_i] = R1; s_rec[w][2][row_i] = R2; s_rec[w][3][row_i] = np;
                 // bytes of np equal to 1 -> 0x01 (exact zero-byte test on np ^ 0x0101..)
                 const uint64_t y = np ^ 0x0101010101010101ull, m7 = 0x7f7f7f7f7f7f7f7full;
                 const uint64_t um = (~(((y & m7) + m7) | y | m7)) >> 7;
                 const uint32_t n0 = (uint32_t)np & 255u;
                 const uint32_t fx = s_invfx[n0 & 127u];                           // 0 for |taxa_0| < 2
                 rare_mask = __ballot_sync(kFull, ((np >> 8) & 0x00fefefefefefefeull) != 0);
-                s_fx[w][lane] = fx;
-                uint64_t *row = reinterpret_cast<uint64_t *>(s_tab[w] + lane * kRowBytes);
+                s_fx[w][row_i] = fx;
+                uint64_t *row = reinterpret_cast<uint64_t *>(s_tab[w] + row_i * kRowBytes);
                 row[0] = 0;
 #pragma unroll
                 for (int h = 1; h < 8; ++h) row[h] = um & ((1ull << (8 * h)) - 1);
             }
             __syncwarp();
             // ---- main pass: lane = taxon, warp-uniform, branch-free (rows past the end of the read are zero)
-            const int cnt = (int)min((uint64_t)32, s1 - c0);
 #pragma unroll 4
-            for (int i = 0; i < ((cnt + 3) & ~3); ++i) {
+            for (int i = 0; i < ((n_ne + 3) & ~3); ++i) {
                 const uint32_t fx = s_fx[w][i];
                 const uint32_t h0 = (uint32_t)(fw0[i] >> sh0) & 7u;
                 u8a += *reinterpret_cast<const uint64_t *>(tab + i * kRowBytes + h0 * 8);
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(kTxBlock) per_read_taxon_kernel(const uint4 *_
             if (rare_mask) any_shared = true;
 #pragma unroll 1
             for (uint32_t m = rare_mask; m; m &= m - 1) {
-                const int i = __ffs((int)m) - 1;
+                const int i = __popc(ne & ((1u << (__ffs((int)m) - 1)) - 1u));     // row of that lane's (non-empty) record
                 const uint64_t np = s_rec[w][3][i];
                 const int h0 = (int)((uint32_t)(fw0[i] >> sh0) & 7u), h1 = (int)((uint32_t)(fw1[i] >> sh1) & 7u);
                 uint64_t lv = (np >> 8) & 0x00fefefefefefefeull;                   // a bit in byte j-1 <=> |taxa_j| >= 2
