@@ -147,3 +147,56 @@ def test_sharded_build_concatenates_to_the_reference_files(case, K, six, n_shard
     assert sum(c.index_size for c in ctxs) == len(rec)
     for c in ctxs:
         c.close()
+
+
+# ----------------------------------------------------------------------------------------- long reads (C5 shape)
+def test_long_reads_sharded_and_plain_match_the_oracle():
+    """BASELINE config C5 in miniature: 10 kbp reads with 10 % errors (substitutions and indels) against a prefix-sharded
+    index.  19 960 k-mers per read: the per-read kernel walks them in 32-instance chunks, counters are widened on the way."""
+    from kasa_b200 import synth
+    from oracle import oracle as O
+    n_taxa, glen, n_reads, rlen = 6, 40_000, 12, 10_000
+    rng = np.random.default_rng(77)
+    fasta = b"".join(b">" + synth.accession(t).encode() + b"\n" + synth.genome_ascii(11, t, glen) + b"\n" for t in range(n_taxa))
+    acc2tax = {synth.accession(t): 1000 + t for t in range(n_taxa)}
+    taxids = np.array([0] + [1000 + t for t in range(n_taxa)], dtype=np.uint32)
+    index, _ = O.build_index(fasta, acc2tax, 12, six=False)
+    reads = []
+    for i in range(n_reads):
+        g = synth.genome_ascii(11, int(rng.integers(n_taxa)), glen)
+        o = int(rng.integers(0, glen - rlen))
+        out = bytearray()
+        for ch in g[o:o + rlen]:
+            u = rng.random()
+            if u < 0.05:
+                out.append(b"ACGT"[int(rng.integers(4))])          # substitution
+            elif u < 0.075:
+                continue                                            # deletion
+            elif u < 0.10:
+                out.append(ch); out.append(b"ACGT"[int(rng.integers(4))])   # insertion
+            else:
+                out.append(ch)
+        reads.append(bytes(out))
+    ora = O.identify_reads([[r] for r in reads], index, 12, 12, 7, True, taxids)
+    kw = dict(frames=6, max_batch_kmers=1 << 19, max_batch_seqs=64, max_batch_bases=1 << 18)
+    plain = Context(Params(**kw))
+    plain.load_index(index, taxids)
+    nk, scores, _ = plain.identify_batch(reads)
+    ca, cu, _ = plain.identify_finish()
+    plain.close()
+    assert nk == ora.n_kmers
+    assert np.array_equal(cu, ora.count_unique)
+    np.testing.assert_allclose(ca, ora.count_all, rtol=1e-6, atol=1e-9)
+    # the reference's score is an fp32 running sum of ~20 000 terms (here ~960: one ulp = 6e-5), ours is exact integer
+    # arithmetic rounded once: the difference is the reference's own rounding drift
+    np.testing.assert_allclose(scores, ora.scores, rtol=5e-5)
+    eb, pb = capi.shard_plan(index, 7, 2)
+    ctxs = []
+    for r in range(2):
+        c = Context(Params(**kw))
+        c.load_index(index[int(eb[r]):int(eb[r + 1])], taxids)
+        ctxs.append(c)
+    out = LocalShardGroup(ctxs, pb).identify_batches([reads[:5], reads[5:]])
+    assert np.array_equal(np.concatenate([o[1] for o in out]), scores)
+    for c in ctxs:
+        c.close()
