@@ -335,35 +335,36 @@ def main_ours(args):
     if not args.no_e2e:
         n_host = 3
         host_reads = [torch.empty(R * READ_LEN, dtype=torch.uint8, pin_memory=True) for _ in range(n_host)]
-        host_scores = [torch.empty(R * T, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        host_scores = [torch.empty(R * T, dtype=torch.float32, pin_memory=True) for _ in range(3)]
         h_start = (np.arange(R, dtype=np.uint64) * READ_LEN)
         h_len = np.full(R, READ_LEN, dtype=np.uint32)
         for b in range(n_host):
             gen(1000 + b, host_reads[b].data_ptr(), capi.MEM_HOST)
 
         def run_host_steps(n_steps):
-            """the production loop of the C ABI: kasa_identify_submit / kasa_identify_wait, two batches in flight — the
-            next batch's host->device copy and the previous batch's score read-back overlap the kernels"""
+            """the production loop of the C ABI: kasa_identify_submit / kasa_identify_wait, three batches in flight — the
+            next batch's host->device copy and the previous batch's score read-back overlap the kernels and each other"""
             keep = []
             for step in range(n_steps if group is not None else 0):        # prefix-sharded: one batch at a time
                 buf = host_reads[step % n_host]
                 rb = capi.CReadBatch(R, R, capi.SEQ_ASCII, capi.MEM_HOST, buf.data_ptr(), None, h_start.ctypes.data, h_len.ctypes.data, None)
-                res = capi.CBatchResult(0, host_scores[step % 2].data_ptr(), capi.MEM_HOST, 0.0)
+                res = capi.CBatchResult(0, host_scores[step % 3].data_ptr(), capi.MEM_HOST, 0.0)
                 group.identify_batch_raw(rb, res)
             if group is not None:
                 return
             for step in range(n_steps):
                 buf = host_reads[step % n_host]
                 rb = capi.CReadBatch(R, R, capi.SEQ_ASCII, capi.MEM_HOST, buf.data_ptr(), None, h_start.ctypes.data, h_len.ctypes.data, None)
-                res = capi.CBatchResult(0, host_scores[step % 2].data_ptr(), capi.MEM_HOST, 0.0)
+                res = capi.CBatchResult(0, host_scores[step % 3].data_ptr(), capi.MEM_HOST, 0.0)
                 ctx.identify_submit_raw(rb, res)
                 keep.append((rb, res))
-                if step >= 1:
+                if step >= 2:
                     ctx.identify_wait()
-            if n_steps:
+            for _ in range(min(2, n_steps)):
                 ctx.identify_wait()
 
         run_host_steps(min(2, args.warmup))
+        ctx.stage_times(reset=True)
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -373,11 +374,14 @@ def main_ours(args):
         barrier()
         wall = time.perf_counter() - t0
         e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3))
+        e2e_stages, e2e_batches, _, _ = ctx.stage_times(reset=True)
         e2e = {"value": reads_total / (e2e_ms * 1e-3), "unit": "reads/s",
                "h2d_bytes_per_step": int(R * READ_LEN + R * 12), "d2h_bytes_per_step": int(R * T * 4),
-               "ms_per_step": e2e_ms / args.steps, "checksum": float(host_scores[(args.steps - 1) % 2][: T * 1000].sum()),
+               "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall * 1e3 / args.steps,
+               "device_ms_per_step": e0.elapsed_time(e1) / args.steps,
+               "stage_ms_per_step": {k: v / max(1, e2e_batches) for k, v in e2e_stages.items()}, "checksum": float(host_scores[(args.steps - 1) % 3][: T * 1000].sum()),
                "api": ("kasa_shard_sort/_lookup/_score per batch (pinned host buffers)" if group is not None else
-                       "kasa_identify_submit/_wait (2 batches in flight, pinned host buffers)")}
+                       "kasa_identify_submit/_wait (3 batches in flight, pinned host buffers)")}
 
     # ---- job epilogue: reduce the per-taxon counts across ranks (the only collective of this path)
     ca, cu, total_kmers = ctx.identify_finish()

@@ -149,12 +149,13 @@ typedef struct {
 int kasa_identify_batch(kasa_ctx *ctx, const kasa_read_batch *in, kasa_batch_result *out);
 
 /* The same work, pipelined (what the reference gets from its reader / worker threads, Compare.hpp:2983-3440):
- * kasa_identify_submit() starts the batch's host->device copies on a copy stream, queues its kernels and returns
- * once the batch's k-mer count is known; kasa_identify_wait() completes the OLDEST submitted batch (its scores
- * are copied back on a second copy stream, overlapping the next batch's kernels) and fills the `out` given at
- * submit time.  At most two batches are in flight; `in`'s host buffers must stay valid until the submit call
- * returns, `out` and out->scores until the matching wait.  Typical loop: submit(0); for i >= 1 { submit(i);
- * wait(i-1); }  wait(last).  kasa_identify_batch == submit + wait.                                            */
+ * kasa_identify_submit() queues the batch's host->device copies on a copy stream and its kernels on the compute stream and
+ * returns without waiting for the device when the batch is host memory (its k-mer total is computed from seq_len on the
+ * host); kasa_identify_wait() completes the OLDEST submitted batch (its scores are copied back on a second copy stream,
+ * overlapping later batches' kernels and input copies) and fills the `out` given at submit time.  At most three batches are
+ * in flight; `in` itself may go away when submit returns, but the host buffers it points to, `out` and out->scores must
+ * stay valid until the matching wait.  Typical loop: submit(0); submit(1); for i >= 2 { submit(i); wait(i-2); }  then
+ * wait the rest.  kasa_identify_batch == submit + wait.                                                              */
 int kasa_identify_submit(kasa_ctx *ctx, const kasa_read_batch *in, kasa_batch_result *out);
 int kasa_identify_wait(kasa_ctx *ctx);
 

@@ -288,8 +288,8 @@ class Context:
     def identify_batch_raw(self, rb: CReadBatch, res: CBatchResult):
         self._check(self.lib.kasa_identify_batch(self.h, C.byref(rb), C.byref(res)))
 
-    # pipelined pair (kasa_identify_submit / kasa_identify_wait): at most two batches in flight; the caller keeps
-    # rb's buffers alive until submit returns and res (+ its score buffer) until the matching wait
+    # pipelined pair (kasa_identify_submit / kasa_identify_wait): at most three batches in flight; the caller keeps
+    # rb's buffers and res (+ its score buffer) alive until the matching wait
     def identify_submit_raw(self, rb: CReadBatch, res: CBatchResult):
         self._check(self.lib.kasa_identify_submit(self.h, C.byref(rb), C.byref(res)))
 
@@ -307,7 +307,7 @@ class Context:
             res = CBatchResult(0, scores.ctypes.data if want and scores.size else None, MEM_HOST, 0.0)
             self.identify_submit_raw(rb, res)
             inflight.append((res, scores, keep))
-            if len(inflight) == 2:
+            if len(inflight) == 3:
                 self.identify_wait()
                 r, sc, _ = inflight.pop(0)
                 yield int(r.n_kmers), sc, float(r.gpu_ms)

@@ -20,6 +20,8 @@
 
 using namespace kasa;
 
+constexpr int kSlots = 3;                // batches in flight (kasa_identify_submit / _wait)
+
 struct kasa_ctx {
     kasa_params p{};
     std::string err;
@@ -74,7 +76,7 @@ struct kasa_ctx {
         kasa_batch_result *res = nullptr;
         uint64_t n = 0;
         int n_passes = 0;
-    } slot[2];
+    } slot[kSlots];
     cudaStream_t cs_in = nullptr, cs_out = nullptr;
     uint64_t submitted = 0, completed = 0;
     double stage_ms[KASA_N_STAGES] = {};
@@ -289,6 +291,18 @@ uint64_t host_total_bases(const uint64_t *seq_start, const uint32_t *seq_len, ui
     uint64_t m = 0;
     for (uint32_t i = 0; i < n; ++i) m = std::max<uint64_t>(m, seq_start[i] + seq_len[i]);
     return m;
+}
+
+// sum of kMerCount over host-resident sequences (Read.hpp:36-57 with the marker of Read.hpp:1068-1078): what
+// kmer_counts_kernel + scan produce on the device, so that a host batch needs no device round trip before its launches
+uint64_t host_total_kmers(const uint32_t *seq_len, uint32_t n, int K, int k_low, int strands)
+{
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t len = (uint64_t)seq_len[i] + 3u * (K - k_low);
+        total += len > (uint64_t)(3 * K + 1) ? len - 3 * K + 1 : 0;
+    }
+    return total * strands;
 }
 
 // sorts the accumulated build records by (kmer, taxid), removes duplicates and sentinels; the result
@@ -551,7 +565,8 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
     KmerParams kp{c->K, c->p.k_low, c->p.frames == 6 ? 2 : 1};
     launch_kmer_counts(c->stream, seq_len, ns, kp, c->d_koff, &c->launches);
     exclusive_scan_u64(c->stream, c->d_koff, ns, c->d_scan_tmp, &c->launches);
-    const uint64_t n = read_u64(c, c->d_koff + ns);
+    // host batches: the total is known without asking the device, so submit returns without a stream synchronisation
+    const uint64_t n = in->location == KASA_MEM_HOST ? host_total_kmers(in->seq_len, ns, kp.K, kp.k_low, kp.strands) : read_u64(c, c->d_koff + ns);
     KASA_REQUIRE(n <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "batch yields more k-mers than max_batch_kmers");
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[1], c->stream));
     if (in->format == KASA_SEQ_ASCII)
@@ -593,9 +608,9 @@ int kasa_identify_submit(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resu
     KASA_API_BEGIN
     KASA_REQUIRE(c && in && out, KASA_ERR_ARG, "null argument");
     KASA_REQUIRE(c->idx_lo, KASA_ERR_STATE, "kasa_identify_batch before an index was loaded");
-    KASA_REQUIRE(c->submitted - c->completed < 2, KASA_ERR_STATE, "two batches are in flight: call kasa_identify_wait first");
+    KASA_REQUIRE(c->submitted - c->completed < (uint64_t)kSlots, KASA_ERR_STATE, "three batches are in flight: call kasa_identify_wait first");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
-    kasa_ctx::Slot &sl = c->slot[c->submitted & 1];
+    kasa_ctx::Slot &sl = c->slot[c->submitted % kSlots];
     KASA_CUDA_TRY(cudaEventRecord(sl.ev0, c->stream));
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[0], c->stream));
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[1], c->stream));      // re-recorded by extract_batch when there is work
@@ -680,7 +695,7 @@ int kasa_identify_wait(kasa_ctx *c)
     KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
     KASA_REQUIRE(c->submitted > c->completed, KASA_ERR_STATE, "kasa_identify_wait without a submitted batch");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
-    finish_slot(c, c->slot[c->completed & 1]);
+    finish_slot(c, c->slot[c->completed % kSlots]);
     KASA_API_END(c)
 }
 
@@ -705,7 +720,7 @@ int kasa_identify_finish(kasa_ctx *c, double *count_all, uint64_t *count_unique,
     KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
     KASA_REQUIRE(c->idx_lo, KASA_ERR_STATE, "kasa_identify_finish before an index was loaded");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
-    while (c->submitted > c->completed) finish_slot(c, c->slot[c->completed & 1]);
+    while (c->submitted > c->completed) finish_slot(c, c->slot[c->completed % kSlots]);
     const size_t cells = (size_t)c->num_k * c->n_taxa;
     if (count_all) KASA_CUDA_TRY(cudaMemcpyAsync(count_all, c->d_tot_all, cells * 8, cudaMemcpyDeviceToHost, c->stream));
     if (count_unique) KASA_CUDA_TRY(cudaMemcpyAsync(count_unique, c->d_tot_un, cells * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -281,7 +281,7 @@ def test_synth_generators_match_numpy():
 
 
 def test_pipelined_submit_wait_matches_batch_calls():
-    """kasa_identify_submit / _wait (two batches in flight, copies on their own streams) == kasa_identify_batch."""
+    """kasa_identify_submit / _wait (three batches in flight, copies on their own streams) == kasa_identify_batch."""
     reads = _k12_reads()
     idx = G.index("k12")
     _, taxids, _ = G.content("k12")
