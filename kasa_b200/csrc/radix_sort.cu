@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
     const uint64_t *__restrict__ in_w0, const uint64_t *__restrict__ in_w1, const uint32_t *__restrict__ in_v,
     uint64_t *__restrict__ out_w0, uint64_t *__restrict__ out_w1, uint32_t *__restrict__ out_v, uint64_t n, int src,
     int shift, uint32_t mask, const unsigned long long *__restrict__ digit_start, uint64_t *status,
-    uint32_t *ticket, uint32_t *err_flag, uint32_t prefetch_ahead, int ablate)
+    uint32_t *ticket, uint32_t *err_flag, uint32_t prefetch_ahead)
 {
     constexpr int TILE = BLOCK * ITEMS;
     constexpr int NW = BLOCK / 32;
@@ -166,7 +166,6 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-        if (ablate & 2) { rk[i] = 0; continue; }
         // lanes holding the same digit: eight ballots (VOTE is far cheaper than MATCH.ANY on the MIO pipe)
         uint32_t peers = kFull;
 #pragma unroll
@@ -241,7 +240,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
         const uint32_t dbase = incl - count + s_wsum[w];
         uint64_t *my = status + (uint64_t)tile * kRadix + tid;
         uint64_t excl = 0;
-        if (tile != 0 && !(ablate & 1)) {
+        if (tile != 0) {
             // predecessors are read kLookBatch at a time (independent loads in flight); tiles before the first count
             // as "inclusive, 0"; an unpublished word restarts the batch at that tile
             int64_t t = (int64_t)tile - 1;
@@ -296,7 +295,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             uint32_t p = tid + j * BLOCK;
-            if (p < n_tile && !(ablate & 4)) {
+            if (p < n_tile) {
                 const uint64_t g = s_gbase[s_dig[p]] + p;
                 if (!v_is_src) out_src[g] = s_buf[p];
                 out_v[g] = s_val[p];
@@ -403,7 +402,6 @@ int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint6
         attr_done = true;
     }
     static const uint32_t ahead = [] { const char *e = getenv("KASA_TUNE_SORT_PREFETCH"); return e ? (uint32_t)atoi(e) : kPrefetchAhead; }();
-    static const int ablate = [] { const char *e = getenv("KASA_TUNE_SORT_ABLATE"); return e ? atoi(e) : 0; }();   // timing experiments only
     int cur = start_buf;
     for (int p = 0; p < plan.n_passes; ++p) {
         KASA_CUDA_TRY(cudaMemsetAsync(ticket, 0, 4, stream));
@@ -412,11 +410,11 @@ int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint6
         if (has_w1)
             onesweep_kernel<kSortBlock, kSortItems, true><<<(unsigned)tiles, kSortBlock, sm_pass, stream>>>(
                 buf.w0[cur], buf.w1[cur], buf.v[cur], buf.w0[nxt], buf.w1[nxt], buf.v[nxt], n, plan.pass[p].src,
-                plan.pass[p].shift, plan.pass[p].mask, ghist + (size_t)p * kRadix, status, ticket, err_flag, ahead, plan.n_passes <= 4 ? ablate : 0);
+                plan.pass[p].shift, plan.pass[p].mask, ghist + (size_t)p * kRadix, status, ticket, err_flag, ahead);
         else
             onesweep_kernel<kSortBlock, kSortItems, false><<<(unsigned)tiles, kSortBlock, sm_pass, stream>>>(
                 buf.w0[cur], nullptr, buf.v[cur], buf.w0[nxt], nullptr, buf.v[nxt], n, plan.pass[p].src,
-                plan.pass[p].shift, plan.pass[p].mask, ghist + (size_t)p * kRadix, status, ticket, err_flag, ahead, plan.n_passes <= 4 ? ablate : 0);
+                plan.pass[p].shift, plan.pass[p].mask, ghist + (size_t)p * kRadix, status, ticket, err_flag, ahead);
         *launches += 1;
         cur = nxt;
     }
