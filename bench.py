@@ -201,7 +201,7 @@ def workload_config(args, reads_per_step):
 
 
 # dram bytes per record of one radix pass, from the committed ncu capture (profiles/r01_ncu_onesweep_kernel.txt)
-NCU_SORT_PASS_DRAM_BYTES_PER_RECORD = (3.121386e9 + 3.192160e9) / 2.6e8
+NCU_SORT_PASS_DRAM_BYTES_PER_RECORD = (3.120720e9 + 3.194830e9) / 2.6e8
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -320,7 +320,7 @@ def main_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_SORT_PASS_DRAM_BYTES_PER_RECORD * kmers_per_batch,
                 "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one onesweep_kernel launch "
-                                  "(profiles/r01_ncu_onesweep_kernel.txt: 6.314 GB for 2.6e8 records), scaled per record to this launch",
+                                  "(profiles/r01_ncu_onesweep_kernel.txt: 6.316 GB for 2.6e8 records), scaled per record to this launch",
                 "peak_source": peak_src, "bytes_per_unit": BYTES_SORT_PASS, "units_per_launch": kmers_per_batch,
                 "avg_launch_ms": pass_ms, "share_of_step": stages["sort_passes"] / max(1e-9, sum(stages.values())),
                 "whole_step_model": {"bytes_per_lookup": BYTES_PER_LOOKUP_MODEL + 12.0 * n_entries / max(1.0, kmers_per_batch),
