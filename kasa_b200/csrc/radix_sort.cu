@@ -111,7 +111,11 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     if (tid < kRadix) s_cnt[tid] = 0;   // ticket order = start order: predecessors are resident or done
-    for (int j = lane; j < kRadix; j += 32) s_hist[w * kRadix + j] = 0;
+    {
+        uint4 *h4 = reinterpret_cast<uint4 *>(s_hist + w * kRadix);          // 256 counters = 64 x 16 bytes per warp
+        h4[lane] = make_uint4(0, 0, 0, 0);
+        h4[lane + 32] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t base = (uint64_t)tile * TILE;
@@ -124,15 +128,18 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
     {
         const uint64_t pbase = ((uint64_t)tile + prefetch_ahead) * TILE;
         if (prefetch_ahead && pbase < n) {
+            // one 128-byte line per thread: threads 0..TILE/16-1 the 64-bit words, the next TILE/32 threads the payload
+            static_assert(BLOCK >= TILE / 16 + TILE / 32, "one prefetch per thread");
             const uint32_t m = (uint32_t)min((uint64_t)TILE, n - pbase);
-            for (uint32_t line = tid; line < TILE / 16; line += BLOCK) {          // 128-byte lines of the 64-bit words
-                if (line * 16 < m) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(in_w0 + pbase + line * 16));
-                    if (HAS_W1) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_w1 + pbase + line * 16));
+            if (tid < TILE / 16) {
+                if ((uint32_t)tid * 16 < m) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(in_w0 + pbase + tid * 16));
+                    if (HAS_W1) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_w1 + pbase + tid * 16));
                 }
+            } else if (tid < TILE / 16 + TILE / 32) {
+                const uint32_t l = tid - TILE / 16;
+                if (l * 32 < m) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_v + pbase + l * 32));
             }
-            for (uint32_t line = tid; line < TILE / 32; line += BLOCK)
-                if (line * 32 < m) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_v + pbase + line * 32));
         }
     }
 
