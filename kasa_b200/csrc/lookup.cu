@@ -9,6 +9,9 @@
 // accumulates is linear in the hit instances, so here each instance independently
 // finds the index entries sharing >= k_low leading letters with it (one binary search + a short scan of
 // a shared-memory copy of the tile's index span) and records, per taxon, up to which level it matches.
+#include <cstdlib>
+#include <cstring>
+
 #include "lookup.cuh"
 
 namespace kasa {
@@ -446,156 +449,6 @@ __global__ void __launch_bounds__(256) scatter_records_kernel(const uint64_t *__
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-constexpr int kReadBlock = 128;
-
-// One thread per read: fp32 score accumulation is a dependent chain per (read, taxon), so reads are the
-// parallel dimension; each thread walks its instances in emission order and levels in ascending k — the
-// canonical order of KASA_SCORE_FAST.  Counts: 32-bit native shared-memory atomics on CTA accumulators
-// (64-bit shared atomics are CAS loops on sm_100), split so that they cannot overflow between flushes:
-//   |taxa| == 1  -> integer counter (this is also the unique count)
-//   |taxa| >= 2  -> 2^-32 fixed point of 1/|taxa| as two 16-bit halves
-constexpr int kReadChunk = 256;     // instances per thread between flushes: 128 * 256 * 65535 < 2^32
-
-template <int HB, int LW>
-__global__ void __launch_bounds__(kReadBlock) per_read_kernel(const uint4 *__restrict__ rec, const uint64_t *__restrict__ read_koff,
-                                                              uint32_t n_reads, LevelParams lp, float *__restrict__ scores,
-                                                              unsigned long long *__restrict__ cnt_fx,
-                                                              unsigned long long *__restrict__ cnt_unique)
-{
-    constexpr int FPW = 64 / HB;
-    constexpr uint64_t HM = (1ull << HB) - 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = lp.n_taxa, NK = lp.num_k, cells = NK * T;
-    unsigned long long *s_tot_fx = reinterpret_cast<unsigned long long *>(smem_raw);   // [NK][T]
-    unsigned long long *s_tot_un = s_tot_fx + cells;                                   // [NK][T]
-    uint32_t *s_lo = reinterpret_cast<uint32_t *>(s_tot_un + cells);                   // [NK][T]
-    uint32_t *s_hi = s_lo + cells;
-    uint32_t *s_un = s_hi + cells;
-    uint32_t *s_invfx = s_un + cells;                                                  // [256]
-    float *s_w = reinterpret_cast<float *>(s_invfx + 256);                             // [32]
-    float *s_inv = s_w + 32;                                                           // [256] 1.f / n (Compare.hpp:924)
-    uint32_t *s_carry = reinterpret_cast<uint32_t *>(s_inv + 256);                     // [T] level-0 carries
-    uint32_t *s_c0 = s_carry + ((T + 3) & ~3);                                         // [T][kReadBlock] private 2^-32 sums
-    float *s_score = reinterpret_cast<float *>(s_c0 + T * kReadBlock);                 // [T][kReadBlock]
-    const int tid = threadIdx.x;
-    for (int i = tid; i < cells; i += kReadBlock) { s_tot_fx[i] = 0; s_tot_un[i] = 0; s_lo[i] = 0; s_hi[i] = 0; s_un[i] = 0; }
-    for (int i = tid; i < 256; i += kReadBlock) {
-        s_invfx[i] = i >= 2 ? (uint32_t)(4294967296.0 / i + 0.5) : 0u;
-        s_inv[i] = i ? 1.f / (float)i : 0.f;
-    }
-    if (tid < 32) {
-        int k = lp.k_low + tid;
-        s_w[tid] = (float)(k * k) / 625.f;        // Compare.hpp:392 arrWeightingFactors[25 - k]
-    }
-    __syncthreads();
-
-    for (int t = 0; t < T; ++t) s_c0[t * kReadBlock + tid] = 0;
-    for (int t = tid; t < T; t += kReadBlock) s_carry[t] = 0;
-    __syncthreads();
-
-    for (uint64_t r0 = (uint64_t)blockIdx.x * kReadBlock; r0 < n_reads; r0 += (uint64_t)gridDim.x * kReadBlock) {
-        const uint64_t r = r0 + tid;
-        if (scores)
-            for (int t = 0; t < T; ++t) s_score[t * kReadBlock + tid] = 0.f;
-        uint64_t cur = 0, s_end = 0;
-        if (r < n_reads) { cur = read_koff[r]; s_end = read_koff[r + 1]; }
-        while (__syncthreads_or(cur < s_end)) {
-            const uint32_t mine = (uint32_t)min((uint64_t)kReadChunk, s_end - cur);
-            const uint32_t trips = __reduce_max_sync(kFull, mine);     // warp-uniform trip count
-#pragma unroll 1
-            for (uint32_t it = 0; it < trips; ++it) {
-                constexpr int RW = kRW<HB>;
-                uint64_t R[RW];
-                uint64_t any = 0;
-#pragma unroll
-                for (int i = 0; i < RW; ++i) R[i] = 0;
-                if (it < mine) {
-#pragma unroll
-                    for (int i = 0; i < RW / 2; ++i) {
-                        const uint4 x = __ldg(rec + (RW / 2) * (cur + it) + i);
-                        R[2 * i] = (uint64_t)x.x | ((uint64_t)x.y << 32); R[2 * i + 1] = (uint64_t)x.z | ((uint64_t)x.w << 32);
-                        any |= R[2 * i] | R[2 * i + 1];
-                    }
-                }
-                if (any != 0) {
-                    {
-                    // pass 1: n_j = |taxa at level j| (byte counters)
-                    uint64_t nl[LW];
-#pragma unroll
-                    for (int i = 0; i < LW; ++i) nl[i] = 0;
-#pragma unroll
-                    for (int wi = 0; wi < RW; ++wi) {
-                        uint64_t w = R[wi];
-                        while (w) {
-                            int f = (__ffsll((long long)w) - 1) / HB;
-                            uint32_t h = (uint32_t)(R[wi] >> (f * HB)) & (uint32_t)HM;
-                            w &= ~(HM << (f * HB));
-                            if (LW == 1) nl[0] += 0x0101010101010101ull >> (8 * (8 - h));
-                            else
-                                for (uint32_t j = 0; j < h; ++j) nl[j >> 3] += 1ull << (8 * (j & 7));
-                        }
-                    }
-                    // pass 2: contributions, k ascending (Compare.hpp:924-925: score = w(k) * (1.f / n), counts 1/n)
-#pragma unroll
-                    for (int wi = 0; wi < RW; ++wi) {
-                        uint64_t w = R[wi];
-                        while (w) {
-                            int f = (__ffsll((long long)w) - 1) / HB;
-                            uint32_t h = (uint32_t)(R[wi] >> (f * HB)) & (uint32_t)HM;
-                            w &= ~(HM << (f * HB));
-                            const int t = wi * FPW + f + 1;
-                            float acc = scores ? s_score[t * kReadBlock + tid] : 0.f;
-                            for (uint32_t j = 0; j < h; ++j) {
-                                uint32_t nj = (uint32_t)(nl[LW == 1 ? 0 : (j >> 3)] >> (8 * (j & 7))) & 255u;
-                                acc = __fadd_rn(acc, __fmul_rn(s_w[j], s_inv[nj]));   // no FMA: the reference rounds the product first
-                                const int c = j * T + t;
-                                if (nj == 1) atomicAdd(&s_un[c], 1u);
-                                else {
-                                    uint32_t fx = s_invfx[nj];
-                                    atomicAdd(&s_lo[c], fx & 0xffffu);
-                                    atomicAdd(&s_hi[c], fx >> 16);
-                                }
-                            }
-                            if (scores) s_score[t * kReadBlock + tid] = acc;
-                        }
-                    }
-                    }
-                }
-                __syncwarp();       // lanes with empty records must not run ahead of the others
-            }
-            cur += mine;
-            __syncthreads();
-            for (int i = tid; i < cells; i += kReadBlock) {
-                s_tot_fx[i] += ((unsigned long long)s_hi[i] << 16) + s_lo[i];
-                s_tot_un[i] += s_un[i];
-                s_lo[i] = 0; s_hi[i] = 0; s_un[i] = 0;
-                if (i < T) { s_tot_fx[i] += (unsigned long long)s_carry[i] << 32; s_carry[i] = 0; }
-            }
-        }
-        if (scores) {
-            const uint64_t rows = min((uint64_t)kReadBlock, n_reads - r0);
-            for (uint64_t i = tid; i < rows * T; i += kReadBlock) {
-                uint32_t rr = (uint32_t)(i / T), t = (uint32_t)(i % T);
-                scores[r0 * T + i] = s_score[t * kReadBlock + rr];
-            }
-            __syncthreads();
-        }
-    }
-    // residuals of the thread-private level-0 accumulators
-    for (int t = 0; t < T; ++t) {
-        const uint32_t v = s_c0[t * kReadBlock + tid];
-        if (v) { atomicAdd(&s_lo[t], v & 0xffffu); atomicAdd(&s_hi[t], v >> 16); }
-    }
-    __syncthreads();
-    for (int i = tid; i < cells; i += kReadBlock) {
-        s_tot_fx[i] += ((unsigned long long)s_hi[i] << 16) + s_lo[i];
-        if (s_tot_fx[i]) atomicAdd(cnt_fx + i, s_tot_fx[i]);
-        if (s_tot_un[i]) atomicAdd(cnt_unique + i, s_tot_un[i]);
-    }
-}
-
-
 __global__ void read_offsets_kernel(const uint64_t *__restrict__ koff, const uint32_t *__restrict__ first_seq, uint32_t n_reads,
                                     uint64_t *__restrict__ out)
 {
@@ -679,18 +532,8 @@ void launch_per_read(cudaStream_t s, const uint64_t *rec, const uint64_t *read_k
                      float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, uint64_t *launches)
 {
     if (!n_reads) return;
-    const size_t sm = (size_t)lp.num_k * lp.n_taxa * (16 + 12) + 256 * 4 + 32 * 4 + 256 * 4 + (size_t)((lp.n_taxa + 3) & ~3) * 4 +
-                      (size_t)lp.n_taxa * kReadBlock * 4 + (scores ? (size_t)lp.n_taxa * kReadBlock * 4 : 0);
-    unsigned grid = (unsigned)div_up<uint64_t>(n_reads, kReadBlock);
-    if (grid > (unsigned)kSMs * 8) grid = kSMs * 8;
-    auto go = [&](auto kern) {
-        KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        kern<<<grid, kReadBlock, sm, s>>>(reinterpret_cast<const uint4 *>(rec), read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
-    };
-    const bool small = lp.num_k <= 8;
     if (lp.hb == 3) launch_per_read_taxon(s, rec, read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
-    else if (lp.hb == 4) { if (small) go(per_read_kernel<4, 1>); else go(per_read_kernel<4, 4>); }
-    else go(per_read_kernel<5, 4>);
+    else launch_per_read_wide(s, rec, read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
     ++*launches;
     KASA_CUDA_TRY(cudaGetLastError());
 }

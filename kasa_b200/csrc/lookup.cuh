@@ -65,6 +65,10 @@ void launch_per_read(cudaStream_t s, const uint64_t *rec, const uint64_t *read_k
 void launch_per_read_taxon(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp,
                            float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique);
 
+// 4- and 5-bit records (per_read.cu): the same organisation with the level sizes counted from the fields
+void launch_per_read_wide(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp,
+                          float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique);
+
 // read_koff[r] = koff[read_first_seq[r]] (or koff[r])
 void launch_read_offsets(cudaStream_t s, const uint64_t *koff, const uint32_t *read_first_seq, uint32_t n_reads,
                          uint64_t *read_koff, uint64_t *launches);

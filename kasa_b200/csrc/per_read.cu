@@ -199,6 +199,220 @@ __global__ void __launch_bounds__(kTxBlock) per_read_taxon_kernel(const uint4 *_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same organisation for 4- and 5-bit level fields (8..31 levels, e.g. k = 25..7 = 19 levels; 64 taxa, records of 4 / 8
+// words without a level-size word): warp per read, lane per taxon (lane l owns taxa l+1 and l+33).  Per 32-instance chunk
+//   pre-pass (lane = instance): load the record, count the level sizes |taxa_j| from its (few) non-zero fields into byte
+//     counters nl[NW words], derive um = one 0x01 byte per level with |taxa_j| == 1 and fx = 2^32 / |taxa_0|, store the
+//     rows compacted (non-empty records first);
+//   main pass (lane = taxon): h = my field of instance i; unique-hit counters (8 bits per level, NW words) += um & below[h];
+//     k_low shared hits += min(h, 1) * fx — branch-free, no atomics;
+//   instances with a level above k_low shared by several taxa (rare) add 2^32 / |taxa_j| per such level to the CTA's
+//     count cells (shared-memory atomics) and, times w(k), to a per-lane double.
+// Every 4 chunks the 8-bit counters are folded: counts into the CTA's cells, counts x w(k) into the score sum.
+// Integer / fixed-point sums in a fixed order: deterministic and batch independent, like the 3-bit kernel.
+template <int HB, int NW, int SLOTS>
+__global__ void __launch_bounds__(kTxBlock) per_read_wide_kernel(const uint64_t *__restrict__ rec, const uint64_t *__restrict__ read_koff,
+                                                                 uint32_t n_reads, LevelParams lp, float *__restrict__ scores,
+                                                                 unsigned long long *__restrict__ cnt_fx,
+                                                                 unsigned long long *__restrict__ cnt_unique)
+{
+    constexpr int RW = kRW<HB>, FPW = 64 / HB, RWU = (64 + FPW - 1) / FPW;     // words that can hold one of the 64 fields
+    constexpr uint32_t HM = (1u << HB) - 1u;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = lp.n_taxa, NK = lp.num_k;
+    uint64_t *s_below = reinterpret_cast<uint64_t *>(smem_raw);                 // [32][NW] bytes j < h -> 0xff
+    uint64_t *s_ones = s_below + 32 * NW;                                       // [32][NW] bytes j < h -> 0x01
+    unsigned long long *s_frtot = reinterpret_cast<unsigned long long *>(s_ones + 32 * NW);   // [NK][64] shared upper-level sums of the CTA
+    uint64_t *s_rec = reinterpret_cast<uint64_t *>(s_frtot + NK * 64);          // [warps][RWU][32]
+    uint64_t *s_um = s_rec + kTxWarps * RWU * 32;                               // [warps][NW][32]
+    uint64_t *s_nl = s_um + kTxWarps * NW * 32;                                 // [warps][NW][32]
+    uint32_t *s_un = reinterpret_cast<uint32_t *>(s_nl + kTxWarps * NW * 32);   // [NK][64] unique counts of the CTA
+    uint32_t *s_fx = s_un + NK * 64;                                            // [warps][32]
+    uint32_t *s_invfx = s_fx + kTxWarps * 32;                                   // [128]
+    float *s_w = reinterpret_cast<float *>(s_invfx + 128);                      // [32]
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < NK * 64; i += kTxBlock) { s_un[i] = 0; s_frtot[i] = 0; }
+    for (int i = tid; i < 128; i += kTxBlock) s_invfx[i] = i >= 2 ? (uint32_t)(4294967296.0 / i + 0.5) : 0u;
+    for (int i = tid; i < 32 * NW; i += kTxBlock) {
+        const int h = i / NW, k = i % NW;
+        const int nb = min(8, max(0, h - 8 * k));
+        const uint64_t ff = nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1);
+        s_below[i] = ff;
+        s_ones[i] = ff & 0x0101010101010101ull;
+    }
+    if (tid < 32) { int k = lp.k_low + tid; s_w[tid] = (float)(k * k) / 625.f; }   // Compare.hpp:392
+    __syncthreads();
+
+    const int my[2] = {lane + 1, lane + 33};
+    const bool own1 = SLOTS > 1 && my[1] < T;
+    uint64_t *w_rec = s_rec + w * RWU * 32, *w_um = s_um + w * NW * 32, *w_nl = s_nl + w * NW * 32;
+    uint32_t *w_fx = s_fx + w * 32;
+    const uint64_t *fw0 = w_rec + (lane / FPW) * 32;
+    const int sh0 = HB * (lane % FPW);
+    const uint64_t *fw1 = w_rec + (own1 ? (lane + 32) / FPW : 0) * 32;
+    const int sh1 = own1 ? HB * ((lane + 32) % FPW) : 0;
+    unsigned long long tot[2] = {0, 0};                       // k_low shared counts over all reads of this warp
+
+    const uint32_t warps_total = gridDim.x * kTxWarps;
+#pragma unroll 1
+    for (uint32_t r = blockIdx.x * kTxWarps + w; r < n_reads; r += warps_total) {
+        const uint64_t s0 = read_koff[r], s1 = read_koff[r + 1];
+        unsigned long long acc[2] = {0, 0};                   // k_low level: 2^-32 sums of my two taxa
+        unsigned long long u8[2][NW];                         // unique hits per level, 8-bit fields
+#pragma unroll
+        for (int k = 0; k < NW; ++k) { u8[0][k] = 0; u8[1][k] = 0; }
+        double x[2] = {0.0, 0.0};                             // sum_j w_j * (unique_j * 2^32 + shared_j), folded so far
+        uint32_t chunk = 0;
+
+        auto fold = [&]() {                                    // 8-bit counters -> the CTA's unique counts and the score sums
+#pragma unroll
+            for (int slot = 0; slot < SLOTS; ++slot) {
+                if (my[slot] >= T) continue;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) {
+                    unsigned long long v = u8[slot][k];
+                    u8[slot][k] = 0;
+                    while (v) {                                // few levels are non-zero
+                        const int byte = (__ffsll((long long)v) - 1) >> 3;
+                        const uint32_t u = (uint32_t)(v >> (8 * byte)) & 255u;
+                        v &= ~(0xffull << (8 * byte));
+                        const int j = 8 * k + byte;
+                        atomicAdd(&s_un[j * 64 + my[slot] - 1], u);            // cells are indexed by taxon - 1 (64 taxa)
+                        x[slot] += (double)u * 4294967296.0 * (double)s_w[j];
+                    }
+                }
+            }
+        };
+
+#pragma unroll 1
+        for (uint64_t c0 = s0; c0 < s1; c0 += 32, ++chunk) {
+            // ---- pre-pass: lane = instance
+            uint32_t rare_mask, ne;
+            int n_ne;
+            {
+                const uint64_t s = c0 + lane;
+                if (s + 32 < s1) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + RW * (s + 32)));   // next chunk
+                uint64_t R[RW];
+#pragma unroll
+                for (int i = 0; i < RW; ++i) R[i] = 0;
+                if (s < s1) {
+#pragma unroll
+                    for (int i = 0; i < RW; i += 4)
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];"
+                                     : "=l"(R[i]), "=l"(R[i + 1]), "=l"(R[i + 2]), "=l"(R[i + 3]) : "l"(rec + RW * s + i));
+                }
+                uint64_t nl[NW];
+#pragma unroll
+                for (int k = 0; k < NW; ++k) nl[k] = 0;
+#pragma unroll
+                for (int wi = 0; wi < RWU; ++wi) {
+                    uint64_t left = R[wi];
+                    while (left) {
+                        const int bit = __ffsll((long long)left) - 1;
+                        const int f = HB == 4 ? bit >> 2 : (bit * 205) >> 10;       // bit / HB
+                        const uint32_t h = (uint32_t)(R[wi] >> (f * HB)) & HM;
+                        left &= ~((uint64_t)HM << (f * HB));
+#pragma unroll
+                        for (int k = 0; k < NW; ++k) nl[k] += s_ones[h * NW + k];
+                    }
+                }
+                const bool nonempty = ((uint32_t)nl[0] & 255u) != 0u;
+                ne = __ballot_sync(kFull, nonempty);
+                n_ne = __popc(ne);
+                const int row_i = nonempty ? __popc(ne & lanemask_lt()) : n_ne + __popc(~ne & lanemask_lt());
+                bool rare = false;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) {
+                    // bytes equal to 1 -> 0x01 (exact zero-byte test on nl ^ 0x0101..)
+                    const uint64_t y = nl[k] ^ 0x0101010101010101ull, m7 = 0x7f7f7f7f7f7f7f7full;
+                    w_um[k * 32 + row_i] = (~(((y & m7) + m7) | y | m7)) >> 7;
+                    w_nl[k * 32 + row_i] = nl[k];
+                    rare |= ((k == 0 ? nl[k] >> 8 : nl[k]) & 0xfefefefefefefefeull & (k == 0 ? 0x00ffffffffffffffull : ~0ull)) != 0;
+                }
+                rare_mask = __ballot_sync(kFull, rare);
+#pragma unroll
+                for (int wi = 0; wi < RWU; ++wi) w_rec[wi * 32 + row_i] = R[wi];
+                w_fx[row_i] = s_invfx[(uint32_t)nl[0] & 127u];                    // 0 for |taxa_0| < 2
+            }
+            __syncwarp();
+            // ---- main pass: lane = taxon, warp-uniform, branch-free (rows of empty records are zero)
+#pragma unroll 2
+            for (int i = 0; i < ((n_ne + 1) & ~1); ++i) {
+                const uint32_t fx = w_fx[i];
+                uint64_t um[NW];
+#pragma unroll
+                for (int k = 0; k < NW; ++k) um[k] = w_um[k * 32 + i];
+                const uint32_t h0 = (uint32_t)(fw0[i] >> sh0) & HM;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) u8[0][k] += um[k] & s_below[h0 * NW + k];
+                acc[0] += (unsigned long long)min(h0, 1u) * fx;
+                if (SLOTS > 1) {
+                    const uint32_t h1 = own1 ? (uint32_t)(fw1[i] >> sh1) & HM : 0u;
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) u8[1][k] += um[k] & s_below[h1 * NW + k];
+                    acc[1] += (unsigned long long)min(h1, 1u) * fx;
+                }
+            }
+            // ---- instances with a level above k_low shared by several taxa
+#pragma unroll 1
+            for (uint32_t m = rare_mask; m; m &= m - 1) {
+                const int i = __popc(ne & ((1u << (__ffs((int)m) - 1)) - 1u));     // row of that lane's (non-empty) record
+                const int h0 = (int)((uint32_t)(fw0[i] >> sh0) & HM), h1 = own1 ? (int)((uint32_t)(fw1[i] >> sh1) & HM) : 0;
+#pragma unroll 1
+                for (int j = 1; j < NK; ++j) {                                     // warp-uniform: the level sizes are a broadcast
+                    const uint32_t nj = (uint32_t)(w_nl[(j >> 3) * 32 + i] >> (8 * (j & 7))) & 255u;
+                    if (nj < 2) continue;
+                    const uint32_t v = s_invfx[nj & 127u];
+                    if (h0 > j) { atomicAdd(&s_frtot[j * 64 + my[0] - 1], (unsigned long long)v); x[0] += (double)v * (double)s_w[j]; }
+                    if (own1 && h1 > j) { atomicAdd(&s_frtot[j * 64 + my[1] - 1], (unsigned long long)v); x[1] += (double)v * (double)s_w[j]; }
+                }
+            }
+            if ((chunk % kWidenEvery) == kWidenEvery - 1) fold();
+            __syncwarp();
+        }
+        // ---- read epilogue
+        fold();
+        tot[0] += acc[0];
+        tot[1] += acc[1];
+#pragma unroll
+        for (int slot = 0; slot < SLOTS; ++slot) {
+            const int t = my[slot];
+            if (t >= T) continue;
+            const double xs = x[slot] + (double)acc[slot] * (double)s_w[0];
+            if (scores) scores[(uint64_t)r * T + t] = (float)(xs * (1.0 / 4294967296.0));
+        }
+        if (scores && lane == 0) scores[(uint64_t)r * T] = 0.f;
+        __syncwarp();
+    }
+    if (my[0] < T && tot[0]) atomicAdd(cnt_fx + my[0], tot[0]);        // level 0 (k_low) row of the counts
+    if (own1 && tot[1]) atomicAdd(cnt_fx + my[1], tot[1]);
+    __syncthreads();
+    for (int i = tid; i < NK * 64; i += kTxBlock) {
+        const int j = i / 64, t = i % 64 + 1;
+        if (t >= T) continue;
+        if (s_un[i]) atomicAdd(cnt_unique + j * T + t, (unsigned long long)s_un[i]);
+        if (s_frtot[i]) atomicAdd(cnt_fx + j * T + t, s_frtot[i]);
+    }
+}
+
+template <int HB, int NW>
+void launch_wide(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp, float *scores,
+                 unsigned long long *cnt_fx, unsigned long long *cnt_unique)
+{
+    constexpr int FPW = 64 / HB, RWU = (64 + FPW - 1) / FPW;
+    const size_t sm = (size_t)2 * 32 * NW * 8 + (size_t)lp.num_k * 64 * 8 + (size_t)kTxWarps * RWU * 32 * 8 + (size_t)2 * kTxWarps * NW * 32 * 8 +
+                      (size_t)lp.num_k * 64 * 4 + (size_t)kTxWarps * 32 * 4 + 128 * 4 + 32 * 4;
+    unsigned grid = (unsigned)div_up<uint64_t>(n_reads, kTxWarps);
+    if (grid > (unsigned)kSMs * 16) grid = kSMs * 16;
+    auto go = [&](auto kern) {
+        KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        kern<<<grid, kTxBlock, sm, s>>>(rec, read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
+    };
+    if (lp.n_taxa <= 33) go(per_read_wide_kernel<HB, NW, 1>); else go(per_read_wide_kernel<HB, NW, 2>);
+}
+
 }  // namespace
 
 void launch_per_read_taxon(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp,
@@ -210,6 +424,15 @@ void launch_per_read_taxon(cudaStream_t s, const uint64_t *rec, const uint64_t *
         per_read_taxon_kernel<1><<<grid, kTxBlock, 0, s>>>(reinterpret_cast<const uint4 *>(rec), read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
     else
         per_read_taxon_kernel<2><<<grid, kTxBlock, 0, s>>>(reinterpret_cast<const uint4 *>(rec), read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
+}
+
+// 4- and 5-bit records (per_read_wide_kernel): 8..15 levels -> two words of byte counters, 16..24 -> three, 25..31 -> four
+void launch_per_read_wide(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp,
+                          float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique)
+{
+    if (lp.hb == 4) launch_wide<4, 2>(s, rec, read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
+    else if (lp.num_k <= 24) launch_wide<5, 3>(s, rec, read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
+    else launch_wide<5, 4>(s, rec, read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
 }
 
 }  // namespace kasa
