@@ -3,14 +3,16 @@
 
 namespace kasa {
 
-// 5-bit letter codes of the codon table (kASA.hpp:621-667: letter & 31), index c0<<6|c1<<3|c2
-__constant__ uint8_t c_aa[512];
+// 5-bit letter codes of the codon table (kASA.hpp:621-667: letter & 31), index c0<<6|c1<<3|c2.  Every lane looks up a
+// different codon, which constant memory would serialise (it broadcasts one address per request): the table lives in
+// global memory and each CTA stages its 512 bytes into shared memory with one 16-byte load per thread of its first warp.
+__device__ __align__(16) uint8_t g_aa[512];
 
 void upload_codon_table(const uint8_t table512[512])
 {
     uint8_t t[512];
     for (int i = 0; i < 512; ++i) t[i] = table512[i] & 31u;
-    KASA_CUDA_TRY(cudaMemcpyToSymbol(c_aa, t, 512));
+    KASA_CUDA_TRY(cudaMemcpyToSymbol(g_aa, t, 512));
 }
 
 namespace {
@@ -104,6 +106,9 @@ __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(Pa
     __shared__ uint8_t s_aa[kExtractWarps][kSegR + kAaPad];
     __shared__ uint64_t s_klo[kExtractWarps][kSegR];
     __shared__ uint64_t s_khi[WIDE ? kExtractWarps : 1][WIDE ? kSegR : 1];
+    __shared__ __align__(16) uint8_t s_tab[512];
+    if (threadIdx.x < 32) reinterpret_cast<uint4 *>(s_tab)[threadIdx.x] = reinterpret_cast<const uint4 *>(g_aa)[threadIdx.x];
+    __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t s = blockIdx.x * kExtractWarps + w;
     if (s >= seqs.n_seqs) return;
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(Pa
                 code[j] = (uint8_t)c;
             }
             __syncwarp();
-            for (uint32_t j = lane; j < naa; j += 32) aa[j] = c_aa[(uint32_t)code[j] << 6 | (uint32_t)code[j + 1] << 3 | code[j + 2]];
+            for (uint32_t j = lane; j < naa; j += 32) aa[j] = s_tab[(uint32_t)code[j] << 6 | (uint32_t)code[j + 1] << 3 | code[j + 2]];
             __syncwarp();
             if (lane < 30 && (uint32_t)j0 < cnt) {
                 uint64_t lo = 0, hi = 0;
@@ -182,6 +187,9 @@ __global__ void __launch_bounds__(256) extract_build_kernel(const char *__restri
                                                             uint64_t *__restrict__ key_lo, uint64_t *__restrict__ key_hi,
                                                             uint32_t *__restrict__ val)
 {
+    __shared__ __align__(16) uint8_t s_tab[512];
+    if (threadIdx.x < 32) reinterpret_cast<uint4 *>(s_tab)[threadIdx.x] = reinterpret_cast<const uint4 *>(g_aa)[threadIdx.x];
+    __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_windows; f += stride) {
         // sequence of this window: last s with woff[s] <= f
@@ -195,7 +203,7 @@ __global__ void __launch_bounds__(256) extract_build_kernel(const char *__restri
         bool bad = false;
         for (int i = 0; i < K; ++i) {
             uint32_t c0 = (uint8_t)ptr[3 * i], c1 = (uint8_t)ptr[3 * i + 1], c2 = (uint8_t)ptr[3 * i + 2];
-            uint32_t a = c_aa[((c0 & 14u) << 5) | ((c1 & 14u) << 2) | ((c2 & 14u) >> 1)];   // kASA.hpp:75
+            uint32_t a = s_tab[((c0 & 14u) << 5) | ((c1 & 14u) << 2) | ((c2 & 14u) >> 1)];   // kASA.hpp:75
             bad |= (a == kLetterUnder);
             if (WIDE) hi = (hi << 5) | (lo >> 59);
             lo = (lo << 5) | a;
