@@ -62,6 +62,43 @@ __global__ void __launch_bounds__(512) hist_kernel(const uint64_t *__restrict__ 
         if (sh[i]) atomicAdd(ghist + i, (unsigned long long)sh[i]);
 }
 
+// The identify sort takes every digit from the low k-mer word (<= 8 passes): the same histograms with the pass list
+// unrolled at compile time and the shifts / masks in registers — the general kernel above spends two thirds of its
+// instructions decoding the plan per (record, pass).
+template <int NP>
+__global__ void __launch_bounds__(512) hist_w0_kernel(const uint64_t *__restrict__ w0, uint64_t n, PlanDev plan,
+                                                      unsigned long long *__restrict__ ghist)
+{
+    __shared__ uint32_t sh[NP * kRadix];
+    for (int i = threadIdx.x; i < NP * kRadix; i += blockDim.x) sh[i] = 0;
+    int shift[NP];
+    uint32_t mask[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { shift[p] = plan.shift[p]; mask[p] = plan.mask[p]; }
+    __syncthreads();
+    constexpr int U = 4;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+        uint64_t a[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + u * stride;
+            ok[u] = i < n;
+            a[u] = ok[u] ? ldg_stream(w0 + i) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) atomicAdd(&sh[p * kRadix + ((uint32_t)(a[u] >> shift[p]) & mask[p])], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NP * kRadix; i += blockDim.x)
+        if (sh[i]) atomicAdd(ghist + i, (unsigned long long)sh[i]);
+}
+
 // exclusive scan of each pass histogram (one block of 256 threads per pass), in place
 __global__ void __launch_bounds__(kRadix) hist_scan_kernel(unsigned long long *ghist)
 {
@@ -385,7 +422,10 @@ int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint6
         uint64_t want = div_up<uint64_t>(n, 512);
         if (want < (uint64_t)grid) grid = (int)want;
         size_t sm = (size_t)plan.n_passes * kRadix * 4;
-        if (has_w1)
+        const bool only_w0 = need[0] && !need[1] && !need[2];
+        if (only_w0 && plan.n_passes == 4) hist_w0_kernel<4><<<grid, 512, 0, stream>>>(buf.w0[start_buf], n, pd, ghist);
+        else if (only_w0 && plan.n_passes == 8) hist_w0_kernel<8><<<grid, 512, 0, stream>>>(buf.w0[start_buf], n, pd, ghist);
+        else if (has_w1)
             hist_kernel<true><<<grid, 512, sm, stream>>>(buf.w0[start_buf], buf.w1[start_buf], buf.v[start_buf], n, pd,
                                                          need[0], need[1], need[2], ghist);
         else
