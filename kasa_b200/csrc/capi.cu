@@ -39,6 +39,7 @@ struct kasa_ctx {
     SortBuffers sb{};
     void *sort_ws = nullptr;
     uint32_t *d_err = nullptr;          // [4] device error flags
+    uint8_t *d_codon = nullptr;         // [512] 5-bit letter of every codon (built-in table or `-a`)
     // sequence staging
     char *d_ascii = nullptr;            // = slot[0].ascii etc.: the build path stages through slot 0
     uint32_t *d_bases2 = nullptr, *d_nmask = nullptr;
@@ -396,7 +397,8 @@ int kasa_ctx_create(const kasa_params *p, kasa_ctx **out)
         }
         uint8_t table[512];
         if (p->codon_table) std::memcpy(table, p->codon_table, 512); else builtin_codon_table(table);
-        upload_codon_table(table);
+        c->d_codon = dev_alloc<uint8_t>(c, 512);
+        upload_codon_table(table, c->d_codon, c->stream);
         *out = c;
     } catch (const Error &e) {
         if (c) kasa_ctx_destroy(c);
@@ -570,9 +572,9 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
     KASA_REQUIRE(n <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "batch yields more k-mers than max_batch_kmers");
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[1], c->stream));
     if (in->format == KASA_SEQ_ASCII)
-        launch_extract_identify_ascii(c->stream, ascii, seq_start, seq_len, ns, kp, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
+        launch_extract_identify_ascii(c->stream, ascii, seq_start, seq_len, ns, kp, c->d_codon, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
     else
-        launch_extract_identify(c->stream, ps, kp, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
+        launch_extract_identify(c->stream, ps, kp, c->d_codon, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     return n;
 }
@@ -1166,7 +1168,7 @@ int kasa_build_push(kasa_ctx *c, const kasa_seq_batch *in)
                  "index does not fit max_batch_kmers records (prefix-sharded multi-GPU build is not in this version)");
     const int b = c->build_buf;
     const uint64_t o = c->build_fill;
-    launch_extract_build(c->stream, ascii, seq_start, seq_len, taxid, ns, c->K, c->d_koff, nw, c->sb.w0[b] + o,
+    launch_extract_build(c->stream, ascii, seq_start, seq_len, taxid, ns, c->K, c->d_codon, c->d_koff, nw, c->sb.w0[b] + o,
                          c->wide ? c->sb.w1[b] + o : nullptr, c->sb.v[b] + o, &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));    // staging buffers are reused by the next push

@@ -5,14 +5,14 @@ namespace kasa {
 
 // 5-bit letter codes of the codon table (kASA.hpp:621-667: letter & 31), index c0<<6|c1<<3|c2.  Every lane looks up a
 // different codon, which constant memory would serialise (it broadcasts one address per request): the table lives in
-// global memory and each CTA stages its 512 bytes into shared memory with one 16-byte load per thread of its first warp.
-__device__ __align__(16) uint8_t g_aa[512];
-
-void upload_codon_table(const uint8_t table512[512])
+// global memory (one per context: `-a` tables differ between contexts) and each CTA stages its 512 bytes into shared
+// memory with one 16-byte load per thread of its first warp.
+void upload_codon_table(const uint8_t table512[512], uint8_t *d_table, cudaStream_t s)
 {
     uint8_t t[512];
     for (int i = 0; i < 512; ++i) t[i] = table512[i] & 31u;
-    KASA_CUDA_TRY(cudaMemcpyToSymbol(g_aa, t, 512));
+    KASA_CUDA_TRY(cudaMemcpyAsync(d_table, t, 512, cudaMemcpyHostToDevice, s));
+    KASA_CUDA_TRY(cudaStreamSynchronize(s));
 }
 
 namespace {
@@ -100,14 +100,15 @@ __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(Pa
                                                                               const uint64_t *__restrict__ koff,
                                                                               uint64_t *__restrict__ key_lo,
                                                                               uint64_t *__restrict__ key_hi,
-                                                                              uint32_t *__restrict__ inst)
+                                                                              uint32_t *__restrict__ inst,
+                                                                              const uint8_t *__restrict__ codon)
 {
     __shared__ uint8_t s_code[kExtractWarps][kSegR + kAaPad + 8];
     __shared__ uint8_t s_aa[kExtractWarps][kSegR + kAaPad];
     __shared__ uint64_t s_klo[kExtractWarps][kSegR];
     __shared__ uint64_t s_khi[WIDE ? kExtractWarps : 1][WIDE ? kSegR : 1];
     __shared__ __align__(16) uint8_t s_tab[512];
-    if (threadIdx.x < 32) reinterpret_cast<uint4 *>(s_tab)[threadIdx.x] = reinterpret_cast<const uint4 *>(g_aa)[threadIdx.x];
+    if (threadIdx.x < 32) reinterpret_cast<uint4 *>(s_tab)[threadIdx.x] = reinterpret_cast<const uint4 *>(codon)[threadIdx.x];
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t s = blockIdx.x * kExtractWarps + w;
@@ -185,10 +186,10 @@ __global__ void __launch_bounds__(256) extract_build_kernel(const char *__restri
                                                             const uint32_t *__restrict__ taxid, uint32_t n_seqs, int K,
                                                             const uint64_t *__restrict__ woff, uint64_t n_windows,
                                                             uint64_t *__restrict__ key_lo, uint64_t *__restrict__ key_hi,
-                                                            uint32_t *__restrict__ val)
+                                                            uint32_t *__restrict__ val, const uint8_t *__restrict__ codon)
 {
     __shared__ __align__(16) uint8_t s_tab[512];
-    if (threadIdx.x < 32) reinterpret_cast<uint4 *>(s_tab)[threadIdx.x] = reinterpret_cast<const uint4 *>(g_aa)[threadIdx.x];
+    if (threadIdx.x < 32) reinterpret_cast<uint4 *>(s_tab)[threadIdx.x] = reinterpret_cast<const uint4 *>(codon)[threadIdx.x];
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_windows; f += stride) {
@@ -239,29 +240,29 @@ void launch_kmer_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs
     ++*launches;
 }
 
-void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint64_t *koff, uint64_t *key_lo,
+void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo,
                              uint64_t *key_hi, uint32_t *inst, uint64_t *launches)
 {
     if (!seqs.n_seqs) return;
     unsigned grid = div_up(seqs.n_seqs, (uint32_t)kExtractWarps);
     if (p.K > 12)
-        extract_identify_kernel<true, false><<<grid, kExtractWarps * 32, 0, s>>>(seqs, nullptr, nullptr, p, koff, key_lo, key_hi, inst);
+        extract_identify_kernel<true, false><<<grid, kExtractWarps * 32, 0, s>>>(seqs, nullptr, nullptr, p, koff, key_lo, key_hi, inst, codon);
     else
-        extract_identify_kernel<false, false><<<grid, kExtractWarps * 32, 0, s>>>(seqs, nullptr, nullptr, p, koff, key_lo, key_hi, inst);
+        extract_identify_kernel<false, false><<<grid, kExtractWarps * 32, 0, s>>>(seqs, nullptr, nullptr, p, koff, key_lo, key_hi, inst, codon);
     ++*launches;
 }
 
 void launch_extract_identify_ascii(cudaStream_t s, const char *ascii, const uint64_t *ascii_start, const uint32_t *seq_len,
-                                   uint32_t n_seqs, KmerParams p, const uint64_t *koff, uint64_t *key_lo, uint64_t *key_hi,
-                                   uint32_t *inst, uint64_t *launches)
+                                   uint32_t n_seqs, KmerParams p, const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo,
+                                   uint64_t *key_hi, uint32_t *inst, uint64_t *launches)
 {
     if (!n_seqs) return;
     PackedSeqs seqs{nullptr, nullptr, nullptr, seq_len, n_seqs};
     unsigned grid = div_up(n_seqs, (uint32_t)kExtractWarps);
     if (p.K > 12)
-        extract_identify_kernel<true, true><<<grid, kExtractWarps * 32, 0, s>>>(seqs, ascii, ascii_start, p, koff, key_lo, key_hi, inst);
+        extract_identify_kernel<true, true><<<grid, kExtractWarps * 32, 0, s>>>(seqs, ascii, ascii_start, p, koff, key_lo, key_hi, inst, codon);
     else
-        extract_identify_kernel<false, true><<<grid, kExtractWarps * 32, 0, s>>>(seqs, ascii, ascii_start, p, koff, key_lo, key_hi, inst);
+        extract_identify_kernel<false, true><<<grid, kExtractWarps * 32, 0, s>>>(seqs, ascii, ascii_start, p, koff, key_lo, key_hi, inst, codon);
     ++*launches;
 }
 
@@ -273,7 +274,7 @@ void launch_build_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seq
 }
 
 void launch_extract_build(cudaStream_t s, const char *ascii, const uint64_t *seq_start, const uint32_t *seq_len,
-                          const uint32_t *taxid, uint32_t n_seqs, int K, const uint64_t *woff, uint64_t n_windows,
+                          const uint32_t *taxid, uint32_t n_seqs, int K, const uint8_t *codon, const uint64_t *woff, uint64_t n_windows,
                           uint64_t *key_lo, uint64_t *key_hi, uint32_t *val, uint64_t *launches)
 {
     (void)seq_len;
@@ -281,9 +282,9 @@ void launch_extract_build(cudaStream_t s, const char *ascii, const uint64_t *seq
     uint64_t want = div_up<uint64_t>(n_windows, 256);
     unsigned grid = (unsigned)(want < (uint64_t)kSMs * 32 ? want : (uint64_t)kSMs * 32);
     if (K > 12)
-        extract_build_kernel<true><<<grid, 256, 0, s>>>(ascii, seq_start, taxid, n_seqs, K, woff, n_windows, key_lo, key_hi, val);
+        extract_build_kernel<true><<<grid, 256, 0, s>>>(ascii, seq_start, taxid, n_seqs, K, woff, n_windows, key_lo, key_hi, val, codon);
     else
-        extract_build_kernel<false><<<grid, 256, 0, s>>>(ascii, seq_start, taxid, n_seqs, K, woff, n_windows, key_lo, key_hi, val);
+        extract_build_kernel<false><<<grid, 256, 0, s>>>(ascii, seq_start, taxid, n_seqs, K, woff, n_windows, key_lo, key_hi, val, codon);
     ++*launches;
 }
 

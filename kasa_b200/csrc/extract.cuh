@@ -23,7 +23,8 @@ struct KmerParams {
     int strands;    // 1 (three forward frames) or 2 (--six)
 };
 
-void upload_codon_table(const uint8_t table512[512]);   // -> __constant__ 5-bit letter codes
+// 5-bit letter codes of a 512-entry codon table -> d_table (512 bytes of device memory owned by the context)
+void upload_codon_table(const uint8_t table512[512], uint8_t *d_table, cudaStream_t s);
 
 // packed start of each sequence = exclusive scan of roundup32(len); writes pstart[n+1] inputs for the scan
 void launch_pack_sizes(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, uint64_t *pstart, uint64_t *launches);
@@ -35,19 +36,19 @@ void launch_pack_ascii(cudaStream_t s, const char *ascii, const uint64_t *ascii_
 void launch_kmer_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, KmerParams p, uint64_t *koff, uint64_t *launches);
 // k-mers in the reference's emission order (forward strand, then reverse strand, per sequence);
 // key_hi may be nullptr for K <= 12; inst[i] = i (sort payload = instance id)
-void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint64_t *koff, uint64_t *key_lo,
+void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo,
                              uint64_t *key_hi, uint32_t *inst, uint64_t *launches);
 
 // the same straight from raw ASCII sequences (KASA_SEQ_ASCII): cleaning, strands and markers on the fly, no packed copy
 void launch_extract_identify_ascii(cudaStream_t s, const char *ascii, const uint64_t *ascii_start, const uint32_t *seq_len,
-                                   uint32_t n_seqs, KmerParams p, const uint64_t *koff, uint64_t *key_lo, uint64_t *key_hi,
-                                   uint32_t *inst, uint64_t *launches);
+                                   uint32_t n_seqs, KmerParams p, const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo,
+                                   uint64_t *key_hi, uint32_t *inst, uint64_t *launches);
 
 // build: one slot per window of each prepared ASCII string; windows holding '_' (31) or giving k-mer 0
 // get the sentinel key ~0 (dropped after the sort): Read.hpp:2016-2024, 2048-2059, 2097, 2122
 void launch_build_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, int K, uint64_t *woff, uint64_t *launches);
 void launch_extract_build(cudaStream_t s, const char *ascii, const uint64_t *seq_start, const uint32_t *seq_len,
-                          const uint32_t *taxid, uint32_t n_seqs, int K, const uint64_t *woff, uint64_t n_windows,
+                          const uint32_t *taxid, uint32_t n_seqs, int K, const uint8_t *codon, const uint64_t *woff, uint64_t n_windows,
                           uint64_t *key_lo, uint64_t *key_hi, uint32_t *val, uint64_t *launches);
 
 }  // namespace kasa

@@ -62,11 +62,16 @@ def test_custom_codon_table_is_a_parameter():
     table = O.default_codon_table().copy()
     table[0] = ord("Q")          # AAA -> Q instead of K
     reads = [b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA", b"ACGTTGCAAAAGGGCCCTTTAAACCCGGGTTTACGTACGTAAAACGT"]
+    plain = _ctx()                                            # two contexts with different tables alive at once
     ctx = _ctx(codon_table=table)
     lo, _, _ = ctx.dbg_extract(reads)
     want, _ = O.read_kmers([[r] for r in reads], 12, 7, False, table)
     assert np.array_equal(lo, want[:, 0])
+    lo_plain, _, _ = plain.dbg_extract(reads)
+    want_plain, _ = O.read_kmers([[r] for r in reads], 12, 7, False)
+    assert np.array_equal(lo_plain, want_plain[:, 0]) and not np.array_equal(lo_plain, lo)
     ctx.close()
+    plain.close()
 
 
 # ----------------------------------------------------------------------------------------- radix sort
