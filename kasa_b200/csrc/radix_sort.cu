@@ -118,13 +118,14 @@ __global__ void __launch_bounds__(kRadix) hist_scan_kernel(unsigned long long *g
 // One radix pass.  Tile = BLOCK x ITEMS records, warp-striped so that loads coalesce and the
 // (warp, item, lane) order equals the input order (needed for LSD stability).
 //
-// Resource plan (B200: 64 K registers, 227 KB shared memory per SM): 512 threads x 8 items at <= 64
-// registers -> 2 CTAs = 32 warps per SM; 52 KB dynamic shared memory per CTA.  The kernel is latency
-// bound per tile (rank chain + look-back), so resident warps are what buys bandwidth.
-constexpr uint32_t kPrefetchAhead = 2 * kSMs;   // CTAs resident at once (2 per SM)
+// Resource plan (B200: 64 K registers, 227 KB shared memory per SM): 256 threads x 18 items at 80 registers
+// -> 3 CTAs = 24 warps per SM; 68 KB dynamic shared memory per CTA.  The kernel is latency bound per tile
+// (rank chain + look-back): many items per thread give independent work between the barriers, three
+// resident CTAs overlap the phases of different tiles (shapes measured: radix_sort.cuh).
+constexpr uint32_t kPrefetchAhead = kSortCtas * kSMs;   // CTAs resident at once
 
 template <int BLOCK, int ITEMS, bool HAS_W1>
-__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
+__global__ void __launch_bounds__(BLOCK, kSortCtas) onesweep_kernel(
     const uint64_t *__restrict__ in_w0, const uint64_t *__restrict__ in_w1, const uint32_t *__restrict__ in_v,
     uint64_t *__restrict__ out_w0, uint64_t *__restrict__ out_w1, uint32_t *__restrict__ out_v, uint64_t n, int src,
     int shift, uint32_t mask, const unsigned long long *__restrict__ digit_start, uint64_t *status,
@@ -165,17 +166,18 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) onesweep_kernel(
     {
         const uint64_t pbase = ((uint64_t)tile + prefetch_ahead) * TILE;
         if (prefetch_ahead && pbase < n) {
-            // one 128-byte line per thread: threads 0..TILE/16-1 the 64-bit words, the next TILE/32 threads the payload
-            static_assert(BLOCK >= TILE / 16 + TILE / 32, "one prefetch per thread");
+            // 128-byte lines: TILE/16 of the 64-bit words, then TILE/32 of the payload
             const uint32_t m = (uint32_t)min((uint64_t)TILE, n - pbase);
-            if (tid < TILE / 16) {
-                if ((uint32_t)tid * 16 < m) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(in_w0 + pbase + tid * 16));
-                    if (HAS_W1) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_w1 + pbase + tid * 16));
+            for (uint32_t l = tid; l < TILE / 16 + TILE / 32; l += BLOCK) {
+                if (l < TILE / 16) {
+                    if (l * 16 < m) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in_w0 + pbase + l * 16));
+                        if (HAS_W1) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_w1 + pbase + l * 16));
+                    }
+                } else {
+                    const uint32_t lv = l - TILE / 16;
+                    if (lv * 32 < m) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_v + pbase + lv * 32));
                 }
-            } else if (tid < TILE / 16 + TILE / 32) {
-                const uint32_t l = tid - TILE / 16;
-                if (l * 32 < m) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_v + pbase + l * 32));
             }
         }
     }
