@@ -201,7 +201,7 @@ def workload_config(args, reads_per_step):
 
 
 # dram bytes per record of one radix pass, from the committed ncu capture (profiles/r01_ncu_onesweep_kernel.txt)
-NCU_SORT_PASS_DRAM_BYTES_PER_RECORD = (3.120720e9 + 3.194830e9) / 2.6e8
+NCU_SORT_PASS_DRAM_BYTES_PER_RECORD = (3.195906e9 + 3.357949e9) / 2.6e8
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -316,11 +316,11 @@ def main_ours(args):
     pass_ms = stages["sort_passes"] / max(1, n_passes)
     kmers_per_batch = stage_kmers / max(1, n_batches)
     achieved = BYTES_SORT_PASS * kmers_per_batch / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "onesweep_kernel (one 8-bit LSD radix pass over 12-byte records)",
+    roofline = {"bound": "hbm", "kernel": "onesweep_kernel<256,18> (one 8-bit LSD radix pass over 12-byte records)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_SORT_PASS_DRAM_BYTES_PER_RECORD * kmers_per_batch,
                 "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one onesweep_kernel launch "
-                                  "(profiles/r01_ncu_onesweep_kernel.txt: 6.316 GB for 2.6e8 records), scaled per record to this launch",
+                                  "(profiles/r01_ncu_onesweep_kernel.txt: 6.554 GB for 2.6e8 records), scaled per record to this launch",
                 "peak_source": peak_src, "bytes_per_unit": BYTES_SORT_PASS, "units_per_launch": kmers_per_batch,
                 "avg_launch_ms": pass_ms, "share_of_step": stages["sort_passes"] / max(1e-9, sum(stages.values())),
                 "whole_step_model": {"bytes_per_lookup": BYTES_PER_LOOKUP_MODEL + 12.0 * n_entries / max(1.0, kmers_per_batch),
