@@ -96,6 +96,11 @@ __global__ void __launch_bounds__(kTxBlock) per_read_taxon_kernel(const uint4 *_
             }
         };
 
+        // software pipeline over the read's chunks: the record of this lane's instance in the NEXT chunk is requested (one
+        // 256-bit load, LDG.256) before the main pass of the current one, the chunk after that is pulled into L2
+        uint64_t N0 = 0, N1 = 0, N2 = 0, N3 = 0;
+        if (s0 + lane < s1)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(N0), "=l"(N1), "=l"(N2), "=l"(N3) : "l"(rec + 2 * (s0 + lane)));
 #pragma unroll 1
         for (uint64_t c0 = s0; c0 < s1; c0 += 32, ++chunk) {
             // ---- pre-pass: lane = instance
@@ -103,12 +108,11 @@ __global__ void __launch_bounds__(kTxBlock) per_read_taxon_kernel(const uint4 *_
             int n_ne;
             {
                 const uint64_t s = c0 + lane;
-                if (s + 32 < s1) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 2 * (s + 32)));   // next chunk
-                uint64_t R0 = 0, R1 = 0, R2 = 0, np = 0;
-                if (s < s1) {
-                    // one 256-bit load per record (LDG.256, sm_100)
-                    asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(R0), "=l"(R1), "=l"(R2), "=l"(np) : "l"(rec + 2 * s));
-                }
+                if (s + 64 < s1) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 2 * (s + 64)));
+                const uint64_t R0 = N0, R1 = N1, R2 = N2, np = N3;
+                N0 = N1 = N2 = N3 = 0;
+                if (s + 32 < s1)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(N0), "=l"(N1), "=l"(N2), "=l"(N3) : "l"(rec + 2 * (s + 32)));
                 // rows are stored compacted: instances with a non-empty record first, so that the main pass only walks those
                 // (a quarter of the records of a typical read are empty); integer sums do not care about the order
                 ne = __ballot_sync(kFull, (uint32_t)np != 0u);
