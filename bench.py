@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--sharding", default="replicate", choices=["replicate", "prefix"],
                     help="replicate: index copied to every GPU, reads sharded (default, SURVEY.md §8e mode 1); prefix: index "
                          "sharded by k-mer prefix range as well, match records exchanged over NVLink peer memory (mode 2)")
+    ap.add_argument("--score-mode", default="fast", choices=["fast", "exact", "none"],
+                    help="per-read scoring: fast = canonical-order fixed point (the bench line), exact = the reference's flush order "
+                         "(bit-identical to kASA -n 1), none = profile counts only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-reads", type=int, default=200_000)
@@ -195,7 +198,7 @@ def workload_config(args, reads_per_step):
     how = ("index sharded by k-mer prefix range, reads sharded, match records over NVLink peer memory" if args.sharding == "prefix"
            else "index replicated, reads sharded")
     return {"workload": "C2: identify k=12..7 --six, %d bp reads vs k=12 index of %d taxa x %d bp (%s)"
-                        % (READ_LEN, args.taxa, args.genome_len, how), "sharding": args.sharding,
+                        % (READ_LEN, args.taxa, args.genome_len, how), "sharding": args.sharding, "score_mode": args.score_mode,
             "reads_per_step_per_gpu": reads_per_step, "kmers_per_read": KMERS_PER_READ,
             "l2_policy": "inputs larger than L2 (each step streams > 10 GB; a fresh read batch per step)"}
 
@@ -228,7 +231,8 @@ def main_ours(args):
     R = args.reads_per_step
     n_windows = args.taxa * (args.genome_len + 33)
     cap = max(R * KMERS_PER_READ, n_windows) + 4096
-    params = kasa_b200.Params(device=local, highest_k=12, k_high=12, k_low=7, frames=6, score_mode=capi.SCORE_FAST,
+    score_mode = {"fast": capi.SCORE_FAST, "exact": capi.SCORE_EXACT, "none": capi.SCORE_NONE}[args.score_mode]
+    params = kasa_b200.Params(device=local, highest_k=12, k_high=12, k_low=7, frames=6, score_mode=score_mode,
                               max_batch_kmers=cap, max_batch_seqs=R, max_batch_bases=max(R * READ_LEN, args.genome_len + 64))
     ctx = kasa_b200.Context(params)
     stream = torch.cuda.Stream()
