@@ -359,3 +359,54 @@ def test_more_taxa_than_a_record_holds_is_rejected_loudly():
         ctx.load_index(np.zeros(0, dtype=capi.REC64), taxids)
     assert "at most" in str(e.value)
     ctx.close()
+
+
+# ----------------------------------------------------------------------------------------- KASA_SEQ_PACKED2 input
+def _pack2(seqs):
+    """Host-side packing of include/kasa_b200.h's KASA_SEQ_PACKED2: 2 bits per base (A0 C1 T2 G3, kASA.hpp:70-75), 16 bases per
+    uint32 LSB first, a 1-bit non-ACGT plane (32 bases per uint32), every sequence starting at a multiple of 32 bases."""
+    starts, pos = [], 0
+    for s in seqs:
+        starts.append(pos)
+        pos += (len(s) + 31) // 32 * 32
+    b2 = np.zeros(pos // 16 + 4, dtype=np.uint32)
+    nm = np.zeros(pos // 32 + 4, dtype=np.uint32)
+    for s, st in zip(seqs, starts):
+        for j, ch in enumerate(s):
+            g = st + j
+            if chr(ch) in "ACGTacgt":
+                b2[g >> 4] |= np.uint32(((ch & 14) >> 1) << (2 * (g & 15)))
+            else:
+                nm[g >> 5] |= np.uint32(1 << (g & 31))
+    return b2, nm, np.array(starts, dtype=np.uint64), np.array([len(s) for s in seqs], dtype=np.uint32)
+
+
+@pytest.mark.parametrize("K,k_low", [(12, 7), (25, 7)])
+def test_packed2_input_gives_the_same_kmers_and_scores_as_ascii(K, k_low):
+    import ctypes as C
+    reads = _k12_reads()[:150] + [b"", b"ACG", b"acgtnACGTN" * 30, b"N" * 40 + b"ACGT" * 20, b"ACGTRYKM" * 25]
+    case = "k12" if K == 12 else "k25"
+    _, taxids, _ = G.content(case)
+    ctx = _ctx(highest_k=K, k_high=K, k_low=k_low, frames=6)
+    ctx.load_index(G.index(case), taxids)
+    lo_a, hi_a, rid_a = ctx.dbg_extract(reads)
+    n_a, scores_a, _ = ctx.identify_batch(reads)
+    b2, nm, starts, lens = _pack2(reads)
+    rb = capi.CReadBatch(len(reads), len(reads), capi.SEQ_PACKED2, capi.MEM_HOST, b2.ctypes.data, nm.ctypes.data, starts.ctypes.data,
+                         lens.ctypes.data, None)
+    cap = ctx.params.max_batch_kmers
+    lo = np.zeros(cap, dtype=np.uint64)
+    hi = np.zeros(cap, dtype=np.uint64)
+    rid = np.zeros(cap, dtype=np.uint32)
+    n = C.c_uint64(0)
+    ctx._check(ctx.lib.kasa_dbg_extract(ctx.h, C.byref(rb), lo.ctypes.data, hi.ctypes.data, rid.ctypes.data, C.byref(n)))
+    n = int(n.value)
+    assert n == len(lo_a)
+    assert np.array_equal(lo[:n], lo_a) and np.array_equal(rid[:n], rid_a)
+    if K == 25:
+        assert np.array_equal(hi[:n], hi_a)
+    scores = np.zeros((len(reads), len(taxids)), dtype=np.float32)
+    res = capi.CBatchResult(0, scores.ctypes.data, capi.MEM_HOST, 0.0)
+    ctx.identify_batch_raw(rb, res)
+    assert int(res.n_kmers) == n_a and np.array_equal(scores, scores_a)
+    ctx.close()
