@@ -410,3 +410,27 @@ def test_packed2_input_gives_the_same_kmers_and_scores_as_ascii(K, k_low):
     ctx.identify_batch_raw(rb, res)
     assert int(res.n_kmers) == n_a and np.array_equal(scores, scores_a)
     ctx.close()
+
+
+def test_device_resident_batches_match_host_batches():
+    """location = KASA_MEM_DEVICE for the reads and the score matrix (what bench.py's device-resident steps use)."""
+    import torch
+    reads = _k12_reads()
+    _, taxids, _ = G.content("k12")
+    ctx = _ctx(frames=6)
+    ctx.load_index(G.index("k12"), taxids)
+    n_host, scores_host, _ = ctx.identify_batch(reads)
+    data, starts, lens = ctx.pack_reads(reads)
+    d_data = torch.from_numpy(data).cuda()
+    d_starts = torch.from_numpy(starts.astype(np.int64)).cuda()
+    d_lens = torch.from_numpy(lens.astype(np.int32)).cuda()
+    d_scores = torch.zeros(len(reads) * len(taxids), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    rb = capi.CReadBatch(len(reads), len(reads), capi.SEQ_ASCII, capi.MEM_DEVICE, d_data.data_ptr(), None, d_starts.data_ptr(),
+                         d_lens.data_ptr(), None)
+    res = capi.CBatchResult(0, d_scores.data_ptr(), capi.MEM_DEVICE, 0.0)
+    ctx.identify_batch_raw(rb, res)
+    ctx.synchronize()
+    assert int(res.n_kmers) == n_host
+    assert np.array_equal(d_scores.cpu().numpy().reshape(len(reads), len(taxids)), scores_host)
+    ctx.close()
