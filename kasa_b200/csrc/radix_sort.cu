@@ -438,8 +438,11 @@ int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint6
     }
     if (after_hist) KASA_CUDA_TRY(cudaEventRecord(after_hist, stream));
     constexpr size_t sm_pass = onesweep_smem<kSortBlock, kSortItems>();
-    static bool attr_done = false;
-    if (!attr_done) {
+    // function attributes are per device: one process may drive several GPUs (host CLI --gpus, LocalShardGroup)
+    static bool attr_done[64] = {};
+    int dev = 0;
+    KASA_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         KASA_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<kSortBlock, kSortItems, false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pass));
         KASA_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<kSortBlock, kSortItems, true>,
@@ -448,7 +451,7 @@ int radix_sort(cudaStream_t stream, const SortBuffers &buf, int start_buf, uint6
                                            cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         KASA_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<kSortBlock, kSortItems, true>,
                                            cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     static const uint32_t ahead = [] { const char *e = getenv("KASA_TUNE_SORT_PREFETCH"); return e ? (uint32_t)atoi(e) : kPrefetchAhead; }();
     int cur = start_buf;

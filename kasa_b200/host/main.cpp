@@ -1,6 +1,7 @@
 // kasa_b200 host CLI — `build` and `identify` with kASA's flags, files and outputs (main.cpp:303-586 of the
 // reference for the flag names; formats per SURVEY.md §3.4 / Compare.hpp:1485-1890, 3466-3665).  FASTA/FASTQ(.gz)
 // parsing, content file, scoring and writers stay on the host; all k-mer work goes through libkasa_b200.so.
+#include <cstdlib>
 #include <chrono>
 #include <iostream>
 
@@ -13,7 +14,7 @@ namespace {
 
 struct Args {
     std::string mode, content, index, input, in1, in2, profile, rtt, tmp;
-    int k_high = 12, k_low = 7, highest_k = 12, beasts = 3, device = 0;
+    int k_high = 12, k_low = 7, highest_k = 12, beasts = 3, device = 0, gpus = 1;
     bool six = false, verbose = false, exact = false;
     float threshold = 0.f;
     std::string format = "json";
@@ -24,7 +25,7 @@ struct Args {
 {
     std::cout << "kasa_b200 <build|identify> -c <content> -d <index> [-i <input> | -1 <fq> -2 <fq>] [-p <profile.csv>] [-q <per-read out>]\n"
                  "          [-k <high> <low>] [--kH <12|25>] [--six] [--json|--jsonl|--tsv|--kraken] [-b <n>] [--threshold <f>] [-v]\n"
-                 "          [--exact-scores] [--device <n>] [--batch-reads <n>]   (-m -n -t -r -x are accepted and ignored)\n";
+                 "          [--exact-scores] [--device <n>] [--gpus <n>] [--batch-reads <n>]   (-m -n -t -r -x are accepted and ignored)\n";
     std::exit(0);
 }
 
@@ -58,6 +59,7 @@ Args parse(int argc, char **argv)
         else if (p == "-v" || p == "--verbose") a.verbose = true;
         else if (p == "--exact-scores") a.exact = true;
         else if (p == "--device") a.device = std::stoi(next());
+        else if (p == "--gpus") a.gpus = std::max(1, std::stoi(next()));
         else if (p == "--batch-reads") a.batch_reads = (uint32_t)std::stoul(next());
         else if (p == "-m" || p == "-n" || p == "-x") (void)next();
         else if (p == "-r" || p == "--ram") {}
@@ -203,14 +205,22 @@ int run_identify(const Args &a)
         max_bases = std::max(max_bases, bases); max_kmers = std::max(max_kmers, kmers);
     }
     p.max_batch_kmers = max_kmers + 4096; p.max_batch_seqs = per_batch * (paired ? 2 : 1) + 1; p.max_batch_bases = max_bases + 4096;
-    kasa_ctx *ctx = nullptr;
-    check(kasa_ctx_create(&p, &ctx), nullptr);
+    // --gpus N: the index is replicated on devices device .. device + N - 1, batches are dealt round-robin (reads are
+    // independent; the reference's worker threads, Compare.hpp:3221-3310, become GPUs).  One host thread drives all of them:
+    // kasa_identify_submit does not wait for the device.
+    const int G = a.gpus;
+    std::vector<kasa_ctx *> ctxs(G, nullptr);
     {
         std::ifstream f(a.index, std::ios::binary);
         if (!f) throw std::runtime_error("Index file not found: " + a.index);
         std::vector<char> bytes(n_idx * (bits == 128 ? 20 : 12));
         f.read(bytes.data(), (std::streamsize)bytes.size());
-        check(kasa_index_load(ctx, bytes.data(), n_idx, bits, content.taxids.data(), (uint32_t)T), ctx);
+        const bool same_device = getenv("KASA_CLI_SAME_DEVICE") != nullptr;   // test hook: N contexts on one GPU
+        for (int g = 0; g < G; ++g) {
+            p.device = same_device ? a.device : a.device + g;
+            check(kasa_ctx_create(&p, &ctxs[g]), nullptr);
+            check(kasa_index_load(ctxs[g], bytes.data(), n_idx, bits, content.taxids.data(), (uint32_t)T), ctxs[g]);
+        }
     }
 
     std::ofstream out;
@@ -222,8 +232,8 @@ int run_identify(const Args &a)
     }
     const int frames = a.six ? 6 : 3;
     uint64_t n_kmers_total = 0, read_no = 0;
-    // two host batches in flight (kasa_identify_submit / _wait): while the device works on batch i, batch i-1's
-    // per-read output is formatted and written here
+    // two host batches in flight per GPU (kasa_identify_submit / _wait): while the devices work on the later batches, the
+    // oldest one's per-read output is formatted and written here, in input order
     struct HostBatch {
         std::string chars;
         std::vector<uint64_t> starts;
@@ -231,10 +241,13 @@ int run_identify(const Args &a)
         std::vector<float> scores;
         kasa_batch_result res{};
         size_t b = 0, e = 0;
-    } hb[2];
+        kasa_ctx *ctx = nullptr;
+    };
+    std::vector<HostBatch> hb(2 * (size_t)G);
     std::string o;
     std::vector<Hit> hits(T);
-    auto submit = [&](HostBatch &h, size_t b) {
+    auto submit = [&](HostBatch &h, size_t b, kasa_ctx *ctx) {
+        h.ctx = ctx;
         const size_t e = std::min(reads.size(), b + per_batch);
         h.b = b; h.e = e;
         h.chars.clear(); h.starts.clear(); h.lens.clear(); h.first.clear();
@@ -255,7 +268,8 @@ int run_identify(const Args &a)
         check(kasa_identify_submit(ctx, &in, &h.res), ctx);
     };
     auto emit = [&](HostBatch &h) {
-        check(kasa_identify_wait(ctx), ctx);
+        kasa_ctx *ctx = h.ctx;
+        check(kasa_identify_wait(ctx), ctx);                  // the oldest batch of that GPU = the oldest batch overall
         const size_t b = h.b, e = h.e;
         const std::vector<float> &scores = h.scores;
         n_kmers_total += h.res.n_kmers;
@@ -352,19 +366,27 @@ int run_identify(const Args &a)
             out << o;
         }
     };
-    size_t nb = 0;
+    // ring of 2 G host batches: batch nb runs on GPU nb % G; before its slot is reused, the batch that held it (2 G batches
+    // ago, the oldest in flight) is emitted
+    const size_t ring = hb.size();
+    size_t nb = 0, emitted = 0;
     for (size_t b = 0; b < reads.size(); b += per_batch, ++nb) {
-        submit(hb[nb & 1], b);
-        if (nb >= 1) emit(hb[(nb - 1) & 1]);
+        if (nb - emitted == ring) emit(hb[emitted++ % ring]);
+        submit(hb[nb % ring], b, ctxs[nb % (size_t)G]);
     }
-    if (nb >= 1) emit(hb[(nb - 1) & 1]);
+    while (emitted < nb) emit(hb[emitted++ % ring]);
     if (!a.rtt.empty() && a.format == "json") out << "\n]";
     out.close();
 
     // ---- profile (Compare.hpp:3466-3665)
-    std::vector<double> ca(numK * T);
-    std::vector<uint64_t> cu(numK * T);
-    check(kasa_identify_finish(ctx, ca.data(), cu.data(), nullptr), ctx);
+    std::vector<double> ca(numK * T, 0.0);
+    std::vector<uint64_t> cu(numK * T, 0);
+    for (kasa_ctx *c : ctxs) {                                // the per-thread reduction of Compare.hpp:3445-3454, over GPUs
+        std::vector<double> ca1(numK * T);
+        std::vector<uint64_t> cu1(numK * T);
+        check(kasa_identify_finish(c, ca1.data(), cu1.data(), nullptr), c);
+        for (size_t i = 0; i < ca.size(); ++i) { ca[i] += ca1[i]; cu[i] += cu1[i]; }
+    }
     std::vector<uint64_t> sum_u(numK, 0);
     std::vector<double> sum_n(numK, 0.0);
     for (size_t t = 1; t < T; ++t)
@@ -415,7 +437,7 @@ int run_identify(const Args &a)
         for (int ik = 0; ik < numK; ++ik) std::cout << " " << sum_u[ik];
         std::cout << std::endl;
     }
-    kasa_ctx_destroy(ctx);
+    for (kasa_ctx *c : ctxs) kasa_ctx_destroy(c);
     return 0;
 }
 

@@ -146,6 +146,23 @@ def test_cli_batching_does_not_change_output(tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_multi_gpu_round_robin_keeps_output_and_order(tmp_path, monkeypatch):
+    """--gpus N deals the batches round-robin over N contexts and writes the reads in input order; here the N contexts
+    share one device (KASA_CLI_SAME_DEVICE), which exercises the same host logic a multi-GPU box runs."""
+    case = "k12"
+    idx = _write_index(case, tmp_path)
+    base = ["identify", "-c", _g(case, "content.txt"), "-d", idx, "-i", _g(case, "reads.fq.gz"), "--six", "--jsonl", "-b", "100000"]
+    monkeypatch.setenv("KASA_CLI_SAME_DEVICE", "1")
+    outs = []
+    for i, (gpus, br) in enumerate([("1", "100000"), ("3", "17"), ("2", "50"), ("4", "1000")]):
+        rc, _, err = _cli(*base, "-p", str(tmp_path / ("p%d" % i)), "-q", str(tmp_path / ("q%d" % i)), "--batch-reads", br, "--gpus", gpus)
+        assert rc == 0, err
+        outs.append(open(tmp_path / ("q%d" % i)).read())
+        _check_profile(str(tmp_path / ("p%d" % i)), case, "six_12_7")
+    assert outs[0] == outs[1] == outs[2] == outs[3]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("fmt", ["json", "tsv", "kraken"])
 def test_cli_other_formats_consistent_with_jsonl(fmt, tmp_path):
     """default -b 3: the json / tsv / kraken writers list the same taxa and scores as the jsonl writer."""
