@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define KASA_B200_ABI_VERSION 1
+#define KASA_B200_ABI_VERSION 2
 
 typedef enum {
     KASA_OK = 0,
@@ -49,12 +49,17 @@ typedef struct kasa_ctx kasa_ctx;
 #define KASA_SEQ_PACKED2 1    /* 2 bits per base (A0 C1 T2 G3, kASA.hpp:70-75), 16 bases per uint32,
                                  LSB first, plus a 1-bit-per-base non-ACGT plane (32 bases per uint32) */
 
-/* Per-read scoring mode (Compare.hpp:516-532 scoreMatchNonAVX is the spec). */
-#define KASA_SCORE_NONE  0    /* profile only: counts, no per-read scores (kASA without -q)            */
-#define KASA_SCORE_FAST  1    /* fp32, canonical order (k-mer position in read, k ascending);
-                                 deterministic and batch independent; <= 4e-6 rel. of the reference    */
-#define KASA_SCORE_EXACT 2    /* fp32 in the reference's own flush order (Compare.hpp:917-955,
-                                 1032-1041) — bit-exact with `kASA -n 1` when the batch is the same     */
+/* Per-read scoring mode (Compare.hpp:516-532 scoreMatchNonAVX is the spec: a float32 running sum per (read, taxon), so the
+ * value depends on the order of the additions). */
+#define KASA_SCORE_NONE    0  /* profile only: counts, no per-read scores (kASA without -q)            */
+#define KASA_SCORE_ORDERED 1  /* float32 adds in (k-mer ascending, k ascending) order per read: deterministic, independent of
+                                 the batch composition and of index sharding.  Bit-identical to `kASA -n 1` for every read whose
+                                 k-mers fall into different 6-letter prefix ranges (all reads without low-complexity stretches);
+                                 otherwise within the spread the reference itself shows when the same read is scored in a
+                                 different batch (<= 2e-6 relative on the adversarial goldens, tests/test_gpu_parity.py)   */
+#define KASA_SCORE_FAST KASA_SCORE_ORDERED   /* name used by ABI version 1 */
+#define KASA_SCORE_EXACT   2  /* float32 adds in the reference's own flush order (Compare.hpp:917-955,
+                                 1032-1041) — bit-exact with `kASA -n 1` when the batch is the same; audits      */
 
 typedef struct {
     int32_t device;           /* CUDA device ordinal                                                   */
@@ -67,6 +72,8 @@ typedef struct {
     uint64_t max_batch_bases; /* largest number of bases per batch                                     */
     const uint8_t *codon_table; /* 512-byte table indexed c0<<6|c1<<3|c2 (kASA.hpp:621-667; `-a` file,
                                  kASA.hpp:579-615) or NULL for the built-in standard code               */
+    uint64_t max_batch_hits;  /* sparse per-read results (kasa_batch_result.hit_*): most (read, taxon) pairs with a
+                                 score per batch; 0 = dense score matrix only                           */
 } kasa_params;
 
 /* --------------------------------------------------------------------------------------------------- */
@@ -107,9 +114,11 @@ int kasa_ctx_stage_times(kasa_ctx *ctx, double *ms, uint64_t *batches, uint64_t 
  * (12 B, packedPairs.hpp:107-111) when bits == 64, or packedLargePair {u64 low, u64 high, u32 taxid}
  * (20 B, :132-136) when bits == 128; must be sorted by (kmer, taxid) as `kASA build` writes it.
  * taxid_of_idx[0] is the "non_unique" pseudo taxon (0); taxid_of_idx[i] the taxid of content line i
- * (Compare.hpp:124-147).  n_taxa (incl. index 0) <= 65535.  The prefix-table file (`_trie`) is NOT an
- * input: the lookup kernel searches the HBM-resident index directly.  The library copies
- * what it needs; the caller may free its buffers after return.                                         */
+ * (Compare.hpp:124-147).  n_taxa (incl. index 0) <= 65535 — the distinct-taxa sets of the lookup are lists, not
+ * bit masks, so any content file the 16-bit dense index can address is accepted (the reference's sBitArray,
+ * BitArray.hpp:18-147, is unbounded; its 6-byte half index has the same 16-bit limit, packedPairs.hpp:100-105).
+ * The prefix-table file (`_trie`) is NOT an input: the lookup kernel searches the HBM-resident index directly
+ * (DESIGN.md §4).  The library copies what it needs; the caller may free its buffers after return.      */
 int kasa_index_load(kasa_ctx *ctx, const void *entries, uint64_t n, int bits,
                     const uint32_t *taxid_of_idx, uint32_t n_taxa);
 
@@ -141,6 +150,17 @@ typedef struct {
                                  Utilities.hpp:592-636) or NULL; filled unless score_mode == NONE       */
     int32_t scores_location;  /* KASA_MEM_HOST | KASA_MEM_DEVICE                                        */
     float gpu_ms;             /* out: device time of this batch's kernels (CUDA events)                 */
+    /* Sparse results (needs kasa_params.max_batch_hits > 0; the way to score against thousands of taxa, where the
+     * dense matrix does not fit): the (taxon index, score) pairs of read r are hit_taxon / hit_score
+     * [hit_begin[r] .. hit_begin[r] + hit_count[r]).  Caller buffers, all in `hits_location`; hit_taxon / hit_score
+     * hold hit_capacity entries, hit_begin / hit_count n_reads entries.  All NULL = not wanted.          */
+    uint32_t *hit_taxon;
+    float *hit_score;
+    uint64_t *hit_begin;
+    uint32_t *hit_count;
+    uint64_t hit_capacity;
+    uint64_t n_hits;          /* out                                                                    */
+    int32_t hits_location;
 } kasa_batch_result;
 
 /* Replaces, per batch: Read::convertAndSort (Read.hpp:763-827) + Compare::sortInputAndCheckInvalidkMers_sta
@@ -178,11 +198,11 @@ int kasa_identify_finish(kasa_ctx *ctx, double *count_all, uint64_t *count_uniqu
  *     every rank:  kasa_shard_lookup(ctx, runs)                  -> barrier
  *     every rank:  kasa_shard_score(ctx, &out)                   -> barrier before the next kasa_shard_sort
  * Shard boundaries never split a group of k-mers sharing min(6, k_low) leading letters, so every level-k taxa set
- * of SURVEY.md §3.1 lives on one shard and the results equal the unsharded ones (KASA_SCORE_FAST and NONE;
+ * of SURVEY.md §3.1 lives on one shard and the results equal the unsharded ones bit for bit (KASA_SCORE_ORDERED and NONE;
  * KASA_SCORE_EXACT replays one global flush order and is rejected).                                            */
 
 #define KASA_MAX_SHARDS 16
-#define KASA_SHARD_NBUF 8          /* sort ping-pong w0[2], w1[2], v[2], the match-record array, the record stage */
+#define KASA_SHARD_NBUF 9          /* sort ping-pong w0[2], w1[2], v[2], the match-record array, the record stage, the overflow list */
 
 typedef struct {
     uint64_t pid;                  /* owner process: peers in the same process use `ptr`, others open `handle`  */

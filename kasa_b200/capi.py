@@ -18,7 +18,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 MEM_HOST, MEM_DEVICE = 0, 1
 SEQ_ASCII, SEQ_PACKED2 = 0, 1
-SCORE_NONE, SCORE_FAST, SCORE_EXACT = 0, 1, 2
+SCORE_NONE, SCORE_ORDERED, SCORE_EXACT = 0, 1, 2
+SCORE_FAST = SCORE_ORDERED      # name used by ABI version 1
 
 REC64 = np.dtype([("lo", "<u8"), ("tax", "<u4")])                     # packedBigPair, packedPairs.hpp:107-111
 REC128 = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("tax", "<u4")])     # packedLargePair, packedPairs.hpp:132-136
@@ -42,7 +43,8 @@ class KasaError(RuntimeError):
 class CParams(C.Structure):
     _fields_ = [("device", C.c_int32), ("highest_k", C.c_int32), ("k_high", C.c_int32), ("k_low", C.c_int32),
                 ("frames", C.c_int32), ("score_mode", C.c_int32), ("max_batch_kmers", C.c_uint64),
-                ("max_batch_seqs", C.c_uint32), ("max_batch_bases", C.c_uint64), ("codon_table", C.c_void_p)]
+                ("max_batch_seqs", C.c_uint32), ("max_batch_bases", C.c_uint64), ("codon_table", C.c_void_p),
+                ("max_batch_hits", C.c_uint64)]
 
 
 class CReadBatch(C.Structure):
@@ -52,7 +54,9 @@ class CReadBatch(C.Structure):
 
 
 class CBatchResult(C.Structure):
-    _fields_ = [("n_kmers", C.c_uint64), ("scores", C.c_void_p), ("scores_location", C.c_int32), ("gpu_ms", C.c_float)]
+    _fields_ = [("n_kmers", C.c_uint64), ("scores", C.c_void_p), ("scores_location", C.c_int32), ("gpu_ms", C.c_float),
+                ("hit_taxon", C.c_void_p), ("hit_score", C.c_void_p), ("hit_begin", C.c_void_p), ("hit_count", C.c_void_p),
+                ("hit_capacity", C.c_uint64), ("n_hits", C.c_uint64), ("hits_location", C.c_int32)]
 
 
 class CSeqBatch(C.Structure):
@@ -60,7 +64,7 @@ class CSeqBatch(C.Structure):
                 ("seq_len", C.c_void_p), ("taxid", C.c_void_p)]
 
 
-MAX_SHARDS, SHARD_NBUF, SHARD_HIST_BITS = 16, 8, 15
+MAX_SHARDS, SHARD_NBUF, SHARD_HIST_BITS = 16, 9, 15
 
 
 class CShardMem(C.Structure):
@@ -165,11 +169,12 @@ class Params:
     k_high: int = 12
     k_low: int = 7
     frames: int = 3
-    score_mode: int = SCORE_FAST
+    score_mode: int = SCORE_ORDERED
     max_batch_kmers: int = 1 << 22
     max_batch_seqs: int = 1 << 16
     max_batch_bases: int = 1 << 24
     codon_table: np.ndarray | None = None
+    max_batch_hits: int = 0
 
 
 def _ptr(a):
@@ -188,7 +193,7 @@ class Context:
         self.params = params
         self._table = None
         cp = CParams(params.device, params.highest_k, params.k_high, params.k_low, params.frames, params.score_mode,
-                     params.max_batch_kmers, params.max_batch_seqs, params.max_batch_bases, None)
+                     params.max_batch_kmers, params.max_batch_seqs, params.max_batch_bases, None, params.max_batch_hits)
         if params.codon_table is not None:
             self._table = np.ascontiguousarray(params.codon_table, dtype=np.uint8)
             cp.codon_table = self._table.ctypes.data
@@ -284,6 +289,20 @@ class Context:
         res = CBatchResult(0, scores.ctypes.data if want and scores.size else None, MEM_HOST, 0.0)
         self._check(self.lib.kasa_identify_batch(self.h, C.byref(rb), C.byref(res)))
         return int(res.n_kmers), scores, float(res.gpu_ms)
+
+    def identify_batch_hits(self, seqs, read_first_seq=None):
+        """Sparse results (Params.max_batch_hits > 0): -> (n_kmers, hit_begin u64[reads], hit_count u32[reads], hit_taxon u32[n_hits],
+        hit_score f32[n_hits]); the hits of read r are [hit_begin[r], hit_begin[r] + hit_count[r])."""
+        rb, keep, n_reads = self._read_batch(seqs, read_first_seq)
+        cap = self.params.max_batch_hits
+        tax = np.zeros(cap, dtype=np.uint32)
+        sc = np.zeros(cap, dtype=np.float32)
+        beg = np.zeros(max(n_reads, 1), dtype=np.uint64)
+        cnt = np.zeros(max(n_reads, 1), dtype=np.uint32)
+        res = CBatchResult(0, None, MEM_HOST, 0.0, tax.ctypes.data, sc.ctypes.data, beg.ctypes.data, cnt.ctypes.data, cap, 0, MEM_HOST)
+        self._check(self.lib.kasa_identify_batch(self.h, C.byref(rb), C.byref(res)))
+        n = int(res.n_hits)
+        return int(res.n_kmers), beg[:n_reads], cnt[:n_reads], tax[:n], sc[:n]
 
     def identify_batch_raw(self, rb: CReadBatch, res: CBatchResult):
         self._check(self.lib.kasa_identify_batch(self.h, C.byref(rb), C.byref(res)))

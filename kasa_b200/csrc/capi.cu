@@ -15,6 +15,7 @@
 #include "lookup.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "score.cuh"
 #include "shard.cuh"
 #include "synth.cuh"
 
@@ -28,7 +29,7 @@ struct kasa_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint64_t launches = 0;
-    int K = 12, num_k = 6, hb = 3;
+    int K = 12, num_k = 6;
     int sort_bits = 0;                  // leading k-mer bits identify sorts (tuning knob KASA_TUNE_SORT_BITS)
     bool wide = false;
     std::vector<void *> allocs;
@@ -37,6 +38,8 @@ struct kasa_ctx {
     bool ws_ready = false;
     uint64_t cap_kmers = 0;
     SortBuffers sb{};
+    char *sort_slab = nullptr;          // the six record arrays of `sb` in one allocation; the op streams of score.cu reuse it after the lookup
+    size_t sort_slab_bytes = 0;
     void *sort_ws = nullptr;
     uint32_t *d_err = nullptr;          // [4] device error flags
     uint8_t *d_codon = nullptr;         // [512] 5-bit letter of every codon (built-in table or `-a`)
@@ -47,6 +50,9 @@ struct kasa_ctx {
     uint32_t *d_seq_len = nullptr, *d_read_first = nullptr, *d_taxid = nullptr;
     // lookup / accumulation
     uint64_t *d_part = nullptr, *d_rec = nullptr;
+    OverflowBuf ovf{};                  // taxa sets that do not fit a match record
+    OpsWorkspace ops{};                 // op streams (alias the sort slab) + per-read tables
+    uint32_t *d_max_inst = nullptr;
     unsigned long long *d_cnt_fx = nullptr, *d_cnt_un = nullptr, *d_tot_un = nullptr;
     double *d_tot_all = nullptr;
     uint64_t n_kmers_total = 0;
@@ -55,6 +61,8 @@ struct kasa_ctx {
     uint64_t *idx_lo = nullptr, *idx_hi = nullptr;
     uint16_t *idx_tax = nullptr;
     uint32_t n_taxa = 0;
+    bool dense_scores = false;
+    uint32_t batch_epoch = 0;
     // build
     int build_buf = 0;
     uint64_t build_fill = 0;
@@ -73,6 +81,12 @@ struct kasa_ctx {
         uint32_t *h_err = nullptr;                      // pinned copy of the device error flags at the end of the batch
         cudaEvent_t ev0 = nullptr, ev1 = nullptr, sev[KASA_N_STAGES + 1] = {};
         cudaEvent_t h2d = nullptr, in_free = nullptr, done = nullptr, out = nullptr;
+        uint32_t *hit_taxon = nullptr, *hit_count = nullptr;      // sparse results (max_batch_hits > 0)
+        float *hit_score = nullptr;
+        uint64_t *hit_begin = nullptr;
+        unsigned long long *hit_cursor = nullptr;
+        unsigned long long *h_hits = nullptr;           // pinned copy of hit_cursor
+        uint32_t n_reads = 0;
         bool in_free_set = false, out_set = false, pending = false;
         kasa_batch_result *res = nullptr;
         uint64_t n = 0;
@@ -96,7 +110,7 @@ struct kasa_ctx {
         bool pull_pending = false;                        // kasa_build_shard_pull filled the free brick half with pulled_total records
         uint64_t pulled_total = 0;
         int phase = 0;                                    // 0 idle, 1 sorted, 2 looked up
-        uint32_t n_reads = 0;
+        uint32_t n_reads = 0, max_inst = 0;
     } sh;
 };
 
@@ -154,7 +168,7 @@ void builtin_codon_table(uint8_t t[512])
 
 LevelParams level_params(const kasa_ctx *c)
 {
-    return LevelParams{c->K, c->p.k_high, c->p.k_low, c->num_k, (int)c->n_taxa, c->hb};
+    return LevelParams{c->K, c->p.k_high, c->p.k_low, c->num_k, (int)c->n_taxa};
 }
 
 void ensure_workspace(kasa_ctx *c)
@@ -163,10 +177,20 @@ void ensure_workspace(kasa_ctx *c)
     const uint64_t cap = c->p.max_batch_kmers;
     const uint32_t ns = c->p.max_batch_seqs;
     const uint64_t nb = c->p.max_batch_bases;
-    for (int i = 0; i < 2; ++i) {
-        c->sb.w0[i] = dev_alloc<uint64_t>(c, cap);
-        c->sb.w1[i] = c->wide ? dev_alloc<uint64_t>(c, cap) : nullptr;
-        c->sb.v[i] = dev_alloc<uint32_t>(c, cap);
+    {   // sort ping-pong as one slab: [w0[0] | w0[1] | w1[0] | w1[1] | v[0] | v[1]]
+        const size_t a8 = ((size_t)cap * 8 + 255) & ~(size_t)255, a4 = ((size_t)cap * 4 + 255) & ~(size_t)255;
+        c->sort_slab_bytes = 2 * a8 + (c->wide ? 2 * a8 : 0) + 2 * a4;
+        c->sort_slab = dev_alloc<char>(c, c->sort_slab_bytes);
+        char *q = c->sort_slab;
+        for (int i = 0; i < 2; ++i) { c->sb.w0[i] = reinterpret_cast<uint64_t *>(q); q += a8; }
+        for (int i = 0; i < 2; ++i) { c->sb.w1[i] = c->wide ? reinterpret_cast<uint64_t *>(q) : nullptr; if (c->wide) q += a8; }
+        for (int i = 0; i < 2; ++i) { c->sb.v[i] = reinterpret_cast<uint32_t *>(q); q += a4; }
+        // the op streams of the scoring stage (score.cuh) live in the slab once the lookup has consumed the sorted records:
+        // 6 ops per k-mer of capacity for 64-bit k-mers, 10 for 128-bit; the (rarely used) level sizes have their own array
+        c->ops.ops = reinterpret_cast<uint32_t *>(c->sort_slab);
+        c->ops.ops_cap = c->sort_slab_bytes / 4;
+        c->ops.ext_cap = std::max<uint64_t>(cap, 1u << 16);
+        c->ops.ext = dev_alloc<uint16_t>(c, c->ops.ext_cap);
     }
     c->sort_ws = dev_alloc<char>(c, sort_workspace_bytes(cap));
     c->d_err = dev_alloc<uint32_t>(c, 4);
@@ -188,8 +212,28 @@ void ensure_workspace(kasa_ctx *c)
     c->d_scan_tmp = dev_alloc<uint64_t>(c, scan_tmp_elems(std::max<uint64_t>(cap + 1, ns + 1)) + 1);
     c->d_taxid = dev_alloc<uint32_t>(c, (size_t)ns + 1);
     c->d_part = dev_alloc<uint64_t>(c, 2 * (size_t)div_up<uint64_t>(cap, 32) + 2);
-    c->d_rec = dev_alloc<uint64_t>(c, (size_t)(cap + 2) * record_words(c->hb));
+    c->d_rec = dev_alloc<uint64_t>(c, (size_t)(cap + 2) * kRecWords);
+    c->ovf.cursor = dev_alloc<unsigned long long>(c, 4);     // the list itself is sized with the taxonomy (set_taxa)
+    c->ops.cursors = c->ovf.cursor + 1;
+    KASA_CUDA_TRY(cudaMemset(c->ovf.cursor, 0, 32));
+    c->ops.ops_start = dev_alloc<uint64_t>(c, (size_t)ns + 1);
+    c->ops.ops_count = dev_alloc<uint32_t>(c, (size_t)ns + 1);
+    c->ops.ext_start = dev_alloc<uint64_t>(c, (size_t)ns + 1);
+    c->d_max_inst = dev_alloc<uint32_t>(c, 1);
     c->ws_ready = true;
+}
+
+[[noreturn]] void throw_device_flags(uint32_t f)
+{
+    if (f == 1) throw Error{KASA_ERR_INTERNAL, "radix sort look-back watchdog tripped"};
+    if (f == 2) throw Error{KASA_ERR_DATA, "a taxid of the index is missing from the content table"};
+    if (f == 3) throw Error{KASA_ERR_DATA, "index records are not sorted by (kmer, taxid)"};
+    if (f & 8) throw Error{KASA_ERR_NOMEM, "the overflow list of taxa sets is full (max_batch_kmers / 2 entries for <= 64 taxa, 4 x max_batch_kmers beyond): use smaller batches relative to max_batch_kmers"};
+    if (f & 32) throw Error{KASA_ERR_NOMEM, "the op-stream workspace of the scoring stage is full: use smaller batches relative to max_batch_kmers"};
+    if (f & 64) throw Error{KASA_ERR_ARG, "KASA_SCORE_EXACT: a read has too many (k-mer, level) pairs for the shared-memory replay; use KASA_SCORE_ORDERED for long reads"};
+    if (f & 128) throw Error{KASA_ERR_NOMEM, "more (read, taxon) hits than hit_capacity / max_batch_hits"};
+    if (f & 256) throw Error{KASA_ERR_NOMEM, "a read hits more than 768 distinct taxa (limit of the sparse scoring cells)"};
+    throw Error{KASA_ERR_INTERNAL, "device error flag " + std::to_string(f)};
 }
 
 void check_device_flags(kasa_ctx *c)
@@ -200,10 +244,7 @@ void check_device_flags(kasa_ctx *c)
     if (h[0] | h[1] | h[2] | h[3]) {
         KASA_CUDA_TRY(cudaMemsetAsync(c->d_err, 0, 16, c->stream));
         uint32_t f = h[0] | h[1] | h[2] | h[3];
-        if (f == 1) throw Error{KASA_ERR_INTERNAL, "radix sort look-back watchdog tripped"};
-        if (f == 2) throw Error{KASA_ERR_DATA, "a taxid of the index is missing from the content table"};
-        if (f == 3) throw Error{KASA_ERR_DATA, "index records are not sorted by (kmer, taxid)"};
-        throw Error{KASA_ERR_INTERNAL, "device error flag " + std::to_string(f)};
+        throw_device_flags(f);
     }
 }
 
@@ -243,9 +284,6 @@ TaxTable upload_tax_table(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_
 void set_taxa(kasa_ctx *c, uint32_t n_taxa)
 {
     KASA_REQUIRE(n_taxa >= 1 && n_taxa <= 65535, KASA_ERR_ARG, "n_taxa must be in [1, 65535]");
-    KASA_REQUIRE((int)n_taxa - 1 <= record_taxa_capacity(c->hb), KASA_ERR_ARG,
-                 "this build supports at most " + std::to_string(record_taxa_capacity(c->hb)) +
-                     " taxa for the requested number of k levels (dense match records)");
     c->n_taxa = n_taxa;
     const size_t cells = (size_t)c->num_k * n_taxa;
     c->d_cnt_fx = dev_alloc<unsigned long long>(c, cells);
@@ -256,13 +294,35 @@ void set_taxa(kasa_ctx *c, uint32_t n_taxa)
     KASA_CUDA_TRY(cudaMemsetAsync(c->d_cnt_un, 0, cells * 8, c->stream));
     KASA_CUDA_TRY(cudaMemsetAsync(c->d_tot_un, 0, cells * 8, c->stream));
     KASA_CUDA_TRY(cudaMemsetAsync(c->d_tot_all, 0, cells * 8, c->stream));
-    for (auto &sl : c->slot) sl.scores = c->p.score_mode != KASA_SCORE_NONE ? dev_alloc<float>(c, (size_t)c->p.max_batch_seqs * n_taxa + 1) : nullptr;
+    // overflow list of taxa sets: content files of <= 64 taxa use mask records and need it only for k-mers whose upper levels name more
+    // than six taxa; larger taxonomies list every set of more than nine taxa there
+    c->ovf.cap = std::max<uint64_t>(n_taxa <= (uint32_t)kMaskTaxa ? c->p.max_batch_kmers / 2 : c->p.max_batch_kmers * 4, 1u << 22);
+    c->ovf.data = dev_alloc<uint32_t>(c, c->ovf.cap);
+    // dense score matrix [reads][taxa] (the reference's Non_contiguousArray) per pipeline slot, while that is a sane amount of HBM;
+    // larger taxonomies are scored through the sparse hit lists (kasa_params.max_batch_hits)
+    const size_t dense_bytes = (size_t)c->p.max_batch_seqs * n_taxa * 4;
+    c->dense_scores = c->p.score_mode != KASA_SCORE_NONE && dense_bytes * kSlots <= ((size_t)32 << 30);
+    for (auto &sl : c->slot) {
+        sl.scores = c->dense_scores ? dev_alloc<float>(c, (size_t)c->p.max_batch_seqs * n_taxa + 1) : nullptr;
+        if (c->p.max_batch_hits && c->p.score_mode != KASA_SCORE_NONE && !sl.hit_taxon) {
+            sl.hit_taxon = dev_alloc<uint32_t>(c, c->p.max_batch_hits);
+            sl.hit_score = dev_alloc<float>(c, c->p.max_batch_hits);
+            sl.hit_begin = dev_alloc<uint64_t>(c, (size_t)c->p.max_batch_seqs + 1);
+            sl.hit_count = dev_alloc<uint32_t>(c, (size_t)c->p.max_batch_seqs + 1);
+            sl.hit_cursor = dev_alloc<unsigned long long>(c, 1);
+        }
+    }
     c->n_kmers_total = 0;
 }
 
 void drop_index(kasa_ctx *c)
 {
     dev_free(c, c->idx_lo); dev_free(c, c->idx_hi); dev_free(c, c->idx_tax);
+    dev_free(c, c->ovf.data); c->ovf.data = nullptr;
+    for (auto &sl : c->slot) {
+        dev_free(c, sl.hit_taxon); dev_free(c, sl.hit_score); dev_free(c, sl.hit_begin); dev_free(c, sl.hit_count); dev_free(c, sl.hit_cursor);
+        sl.hit_taxon = sl.hit_count = nullptr; sl.hit_score = nullptr; sl.hit_begin = nullptr; sl.hit_cursor = nullptr;
+    }
     dev_free(c, c->d_cnt_fx); dev_free(c, c->d_cnt_un); dev_free(c, c->d_tot_un); dev_free(c, c->d_tot_all);
     for (auto &sl : c->slot) { dev_free(c, sl.scores); sl.scores = nullptr; }
     c->idx_lo = c->idx_hi = nullptr; c->idx_tax = nullptr;
@@ -296,14 +356,21 @@ uint64_t host_total_bases(const uint64_t *seq_start, const uint32_t *seq_len, ui
 
 // sum of kMerCount over host-resident sequences (Read.hpp:36-57 with the marker of Read.hpp:1068-1078): what
 // kmer_counts_kernel + scan produce on the device, so that a host batch needs no device round trip before its launches
-uint64_t host_total_kmers(const uint32_t *seq_len, uint32_t n, int K, int k_low, int strands)
+uint64_t host_total_kmers(const uint32_t *seq_len, uint32_t n, int K, int k_low, int strands, const uint32_t *read_first_seq,
+                           uint32_t n_reads, uint32_t *max_per_read)
 {
-    uint64_t total = 0;
+    uint64_t total = 0, best = 0, cur = 0;
+    uint32_t r = 0;
     for (uint32_t i = 0; i < n; ++i) {
+        if (read_first_seq) { while (r < n_reads && read_first_seq[r + 1] <= i) { ++r; cur = 0; } } else cur = 0;
         const uint64_t len = (uint64_t)seq_len[i] + 3u * (K - k_low);
-        total += len > (uint64_t)(3 * K + 1) ? len - 3 * K + 1 : 0;
+        const uint64_t k = (len > (uint64_t)(3 * K + 1) ? len - 3 * K + 1 : 0) * strands;
+        total += k;
+        cur += k;
+        best = std::max(best, cur);
     }
-    return total * strands;
+    if (max_per_read) *max_per_read = (uint32_t)std::min<uint64_t>(best, 0xffffffffu);
+    return total;
 }
 
 // sorts the accumulated build records by (kmer, taxid), removes duplicates and sentinels; the result
@@ -381,7 +448,6 @@ int kasa_ctx_create(const kasa_params *p, kasa_ctx **out)
         c->K = p->highest_k;
         c->wide = p->highest_k > 12;
         c->num_k = p->k_high - p->k_low + 1;
-        c->hb = record_level_bits(c->num_k);
         c->sort_bits = kIdentifySortBits;
         if (const char *e = getenv("KASA_TUNE_SORT_BITS")) c->sort_bits = std::min(5 * c->K, std::max(8, atoi(e)));
         KASA_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -394,6 +460,7 @@ int kasa_ctx_create(const kasa_params *p, kasa_ctx **out)
             for (auto &e : sl.sev) KASA_CUDA_TRY(cudaEventCreate(&e));
             for (cudaEvent_t *e : {&sl.h2d, &sl.in_free, &sl.done, &sl.out}) KASA_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
             KASA_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_err), 16, cudaHostAllocDefault));
+            KASA_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_hits), 8, cudaHostAllocDefault));
         }
         uint8_t table[512];
         if (p->codon_table) std::memcpy(table, p->codon_table, 512); else builtin_codon_table(table);
@@ -421,6 +488,7 @@ void kasa_ctx_destroy(kasa_ctx *c)
         for (cudaEvent_t e : {sl.ev0, sl.ev1, sl.h2d, sl.in_free, sl.done, sl.out}) if (e) cudaEventDestroy(e);
         for (auto e : sl.sev) if (e) cudaEventDestroy(e);
         if (sl.h_err) cudaFreeHost(sl.h_err);
+        if (sl.h_hits) cudaFreeHost(sl.h_hits);
     }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -482,6 +550,7 @@ int kasa_index_load(kasa_ctx *c, const void *entries, uint64_t n, int bits, cons
     launch_check_sorted(c->stream, c->idx_lo, c->idx_hi, d_tax32, n, c->d_err, &c->launches);
     TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
     launch_map_taxids(c->stream, d_tax32, n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
+    launch_index_flags(c->stream, c->idx_lo, c->idx_hi, c->idx_tax, n, c->K, c->p.k_low, &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     check_device_flags(c);
     dev_free(c, d_words); dev_free(c, d_tax32); dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
@@ -506,6 +575,7 @@ int kasa_index_from_build(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_
     if (c->wide) KASA_CUDA_TRY(cudaMemcpyAsync(c->idx_hi, c->sb.w1[b], n * 8, cudaMemcpyDeviceToDevice, c->stream));
     TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
     launch_map_taxids(c->stream, c->sb.v[b], n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
+    launch_index_flags(c->stream, c->idx_lo, c->idx_hi, c->idx_tax, n, c->K, c->p.k_low, &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     check_device_flags(c);
     dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
@@ -524,8 +594,11 @@ const T *stage_in(kasa_ctx *c, const T *src, size_t n, T *dst, int location)
 
 // front half of identify for slot `sl`: stage (copy-in stream) + pack + count + extract (compute stream);
 // returns the number of k-mers; *read_first = device copy of in->read_first_seq (or nullptr)
-static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::Slot &sl, const uint32_t **read_first)
+static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::Slot &sl, const uint32_t **read_first, uint32_t *max_inst = nullptr)
 {
+    KASA_REQUIRE(c->build_fill == 0 || c->build_done, KASA_ERR_STATE,
+                 "a build is open on this context (kasa_build_push without kasa_build_finish): its brick shares the record arrays");
+    if (c->build_done) { c->build_done = false; c->build_fill = 0; c->n_trie = 0; }   // the finished brick is overwritten from here on
     KASA_REQUIRE(in->n_seqs <= c->p.max_batch_seqs, KASA_ERR_NOMEM, "batch has more sequences than max_batch_seqs");
     KASA_REQUIRE(in->n_reads <= in->n_seqs, KASA_ERR_ARG, "n_reads > n_seqs");
     KASA_REQUIRE(in->format == KASA_SEQ_ASCII || in->format == KASA_SEQ_PACKED2, KASA_ERR_ARG, "unknown sequence format");
@@ -568,7 +641,17 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
     launch_kmer_counts(c->stream, seq_len, ns, kp, c->d_koff, &c->launches);
     exclusive_scan_u64(c->stream, c->d_koff, ns, c->d_scan_tmp, &c->launches);
     // host batches: the total is known without asking the device, so submit returns without a stream synchronisation
-    const uint64_t n = in->location == KASA_MEM_HOST ? host_total_kmers(in->seq_len, ns, kp.K, kp.k_low, kp.strands) : read_u64(c, c->d_koff + ns);
+    uint64_t n = 0;
+    uint32_t mi = 0;
+    if (in->location == KASA_MEM_HOST) {
+        n = host_total_kmers(in->seq_len, ns, kp.K, kp.k_low, kp.strands, in->read_first_seq, in->n_reads, &mi);
+    } else {
+        launch_read_offsets(c->stream, c->d_koff, *read_first, in->n_reads, c->d_read_koff, &c->launches);
+        launch_max_instances(c->stream, c->d_read_koff, in->n_reads, c->d_max_inst, &c->launches);
+        KASA_CUDA_TRY(cudaMemcpyAsync(&mi, c->d_max_inst, 4, cudaMemcpyDeviceToHost, c->stream));
+        n = read_u64(c, c->d_koff + ns);
+    }
+    if (max_inst) *max_inst = mi;
     KASA_REQUIRE(n <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "batch yields more k-mers than max_batch_kmers");
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[1], c->stream));
     if (in->format == KASA_SEQ_ASCII)
@@ -577,6 +660,65 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
         launch_extract_identify(c->stream, ps, kp, c->d_codon, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     return n;
+}
+
+// Scoring stage (score.cuh) after the match records of the batch are in c->d_rec: op streams in the reference's summation
+// order, then scores and counts.  `cur` = sort buffer holding the sorted queries (KASA_SCORE_EXACT reads them).
+static void score_stage(kasa_ctx *c, kasa_ctx::Slot &sl, uint64_t n, uint32_t n_reads, uint32_t max_inst, int cur, bool want_dense, bool want_hits)
+{
+    LevelParams lp = level_params(c);
+    const bool exact = c->p.score_mode == KASA_SCORE_EXACT;
+    const uint32_t *trig = nullptr;
+    if (exact) {
+        if (!c->xws_ready) {
+            const uint64_t cap = c->p.max_batch_kmers;
+            c->xws.flags = dev_alloc<uint32_t>(c, cap + 1);
+            c->xws.first = dev_alloc<uint32_t>(c, exact_tiles(cap) * c->num_k + 1);
+            c->xws.next = dev_alloc<uint32_t>(c, exact_tiles(cap) * c->num_k + 1);
+            c->xws.trig = dev_alloc<uint32_t>(c, cap * c->num_k + 1);
+            c->xws_ready = true;
+        }
+        IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n};
+        launch_exact_triggers(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, idx, lp, c->d_rec, c->xws, &c->launches);
+        trig = c->xws.trig;
+    }
+    OverflowPeers peers{};
+    for (int o = 0; o < 16; ++o) peers.base[o] = c->ovf.data;
+    if (c->sh.on) for (int o = 0; o < c->sh.n; ++o) peers.base[o] = o == c->sh.rank ? c->ovf.data : reinterpret_cast<const uint32_t *>(c->sh.peer[o][8]);
+    HitsOut hits{};
+    if (want_hits) {
+        hits = HitsOut{sl.hit_taxon, sl.hit_score, sl.hit_begin, sl.hit_count, sl.hit_cursor, c->p.max_batch_hits};
+        KASA_CUDA_TRY(cudaMemsetAsync(sl.hit_cursor, 0, 8, c->stream));
+    }
+    // The op streams live in the sort slab (6 words per k-mer of capacity for 64-bit k-mers); the reads are scored in four
+    // chunks, so a batch may average ~24 (taxon, read k-mer) pairs per k-mer before the workspace is the limit.
+    const uint32_t n_chunks = n_reads >= 4096 ? 4 : 1;
+    for (uint32_t ch = 0; ch < n_chunks; ++ch) {
+        const uint32_t r0 = (uint32_t)((uint64_t)n_reads * ch / n_chunks), r1 = (uint32_t)((uint64_t)n_reads * (ch + 1) / n_chunks);
+        KASA_CUDA_TRY(cudaMemsetAsync(c->ops.cursors, 0, 16, c->stream));
+        const bool counts_in_a = scores_counted_by_order_ops(lp, want_hits), emit = want_dense || want_hits || !counts_in_a;
+        launch_order_ops(c->stream, c->d_rec, c->d_read_koff, r0, r1, n, max_inst, lp, peers, c->ops, trig, counts_in_a, emit, c->d_cnt_fx, c->d_cnt_un,
+                         c->d_err, &c->launches);
+        if (emit) launch_accumulate(c->stream, c->ops, r0, r1, lp, exact, want_dense ? sl.scores : nullptr, hits, c->d_cnt_fx, c->d_cnt_un, c->d_err, &c->launches);
+    }
+    launch_fold_counts(c->stream, c->d_cnt_fx, c->d_cnt_un, lp, c->d_tot_all, c->d_tot_un, &c->launches);
+    if (want_hits) KASA_CUDA_TRY(cudaMemcpyAsync(sl.h_hits, sl.hit_cursor, 8, cudaMemcpyDeviceToHost, c->stream));
+}
+
+// sparse results of a finished batch -> the caller's buffers
+static void deliver_hits(kasa_ctx *c, kasa_ctx::Slot &sl, kasa_batch_result *out, uint32_t n_reads)
+{
+    out->n_hits = 0;
+    if (!out->hit_taxon || !sl.hit_taxon || !n_reads) return;
+    const uint64_t nh = *sl.h_hits;
+    KASA_REQUIRE(nh <= out->hit_capacity, KASA_ERR_NOMEM, "hit_capacity is smaller than the number of (read, taxon) hits of the batch");
+    const cudaMemcpyKind kind = out->hits_location == KASA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    KASA_CUDA_TRY(cudaMemcpyAsync(out->hit_taxon, sl.hit_taxon, nh * 4, kind, c->cs_out));
+    KASA_CUDA_TRY(cudaMemcpyAsync(out->hit_score, sl.hit_score, nh * 4, kind, c->cs_out));
+    KASA_CUDA_TRY(cudaMemcpyAsync(out->hit_begin, sl.hit_begin, (size_t)n_reads * 8, kind, c->cs_out));
+    KASA_CUDA_TRY(cudaMemcpyAsync(out->hit_count, sl.hit_count, (size_t)n_reads * 4, kind, c->cs_out));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->cs_out));
+    out->n_hits = nh;
 }
 
 // completes the oldest submitted batch: waits for its kernels and score copy, reports timings and device errors
@@ -600,9 +742,9 @@ static void finish_slot(kasa_ctx *c, kasa_ctx::Slot &sl)
     if (f) {
         KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
         KASA_CUDA_TRY(cudaMemsetAsync(c->d_err, 0, 16, c->stream));
-        if (f == 1) throw Error{KASA_ERR_INTERNAL, "radix sort look-back watchdog tripped"};
-        throw Error{KASA_ERR_INTERNAL, "device error flag " + std::to_string(f)};
+        throw_device_flags(f);
     }
+    deliver_hits(c, sl, out, sl.n_reads);
 }
 
 int kasa_identify_submit(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_result *out)
@@ -617,11 +759,20 @@ int kasa_identify_submit(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resu
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[0], c->stream));
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[1], c->stream));      // re-recorded by extract_batch when there is work
     const uint32_t *first = nullptr;
-    const uint64_t n = extract_batch(c, in, sl, &first);
+    uint32_t max_inst = 0;
+    const bool want_scores = c->p.score_mode != KASA_SCORE_NONE;
+    const bool want_hits = want_scores && out->hit_taxon != nullptr;
+    // the scores are computed whenever the score mode asks for them (into the slot's matrix); out->scores only decides about the copy
+    const bool want_dense = want_scores && (out->scores != nullptr || (!want_hits && c->dense_scores));
+    KASA_REQUIRE(!want_dense || c->dense_scores, KASA_ERR_ARG,
+                 "the dense score matrix [max_batch_seqs][n_taxa] is too large for this taxonomy: use the sparse results (max_batch_hits, hit_*)");
+    KASA_REQUIRE(!want_hits || (sl.hit_taxon && out->hit_score && out->hit_begin && out->hit_count), KASA_ERR_ARG,
+                 "sparse results need kasa_params.max_batch_hits > 0 and all four hit_* buffers");
+    const uint64_t n = extract_batch(c, in, sl, &first, &max_inst);
     KASA_CUDA_TRY(cudaEventRecord(sl.in_free, c->stream));
     sl.in_free_set = true;
     out->n_kmers = n;
-    const bool want_scores = c->p.score_mode != KASA_SCORE_NONE;
+    out->n_hits = 0;
     // identify orders the k-mers on their leading kIdentifySortBits only (lookup.cuh: launch_partition); the exact
     // score mode needs the reference's complete order (its flush points are positions in the sorted array)
     const bool exact = c->p.score_mode == KASA_SCORE_EXACT;
@@ -638,39 +789,24 @@ int kasa_identify_submit(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resu
         IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n};
         LevelParams lp = level_params(c);
         const uint32_t tq = lookup_tile_queries(n, c->idx_n);
+        KASA_CUDA_TRY(cudaMemsetAsync(c->ovf.cursor, 0, 8, c->stream));
         launch_partition(c->stream, c->sb.w0[cur], c->sb.w1[cur], n, idx, lp, c->d_part, tq, sorted_from, &c->launches);
-        launch_lookup(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, idx, lp, c->d_part, c->d_rec, tq, &c->launches);
+        launch_lookup(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, 0, idx, lp, c->d_part, c->d_rec, tq, c->ovf, 0, c->d_err,
+                      &c->launches);
         KASA_CUDA_TRY(cudaEventRecord(sl.sev[5], c->stream));
-        launch_per_read(c->stream, c->d_rec, c->d_read_koff, in->n_reads, lp, (want_scores && !exact) ? sl.scores : nullptr,
-                        c->d_cnt_fx, c->d_cnt_un, &c->launches);
-        if (exact) {
-            if (!c->xws_ready) {
-                const uint64_t cap = c->p.max_batch_kmers;
-                c->xws.flags = dev_alloc<uint32_t>(c, cap + 1);
-                c->xws.first = dev_alloc<uint32_t>(c, exact_tiles(cap) * c->num_k + 1);
-                c->xws.next = dev_alloc<uint32_t>(c, exact_tiles(cap) * c->num_k + 1);
-                c->xws.trig = dev_alloc<uint32_t>(c, cap * c->num_k + 1);
-                c->xws.max_inst = dev_alloc<uint32_t>(c, 1);
-                c->xws_ready = true;
-            }
-            launch_exact_triggers(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, idx, lp, c->d_rec, c->xws, &c->launches);
-            launch_exact_max_instances(c->stream, c->d_read_koff, in->n_reads, c->xws.max_inst, &c->launches);
-            uint32_t max_inst = 0;
-            KASA_CUDA_TRY(cudaMemcpyAsync(&max_inst, c->xws.max_inst, 4, cudaMemcpyDeviceToHost, c->stream));
-            KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
-            KASA_REQUIRE(launch_exact_scores(c->stream, c->d_rec, c->xws.trig, c->d_read_koff, in->n_reads, max_inst, lp, sl.scores,
-                                             &c->launches),
-                         KASA_ERR_ARG, "KASA_SCORE_EXACT: a read has too many (k-mer, level) pairs for the shared-memory replay; "
-                                       "use KASA_SCORE_FAST for long reads");
-        }
-        launch_fold_counts(c->stream, c->d_cnt_fx, c->d_cnt_un, lp, c->d_tot_all, c->d_tot_un, &c->launches);
+        score_stage(c, sl, n, in->n_reads, max_inst, cur, want_dense, want_hits);
     } else {
         for (int i = 3; i <= 5; ++i) KASA_CUDA_TRY(cudaEventRecord(sl.sev[i], c->stream));
-        if (want_scores && in->n_reads) KASA_CUDA_TRY(cudaMemsetAsync(sl.scores, 0, (size_t)in->n_reads * c->n_taxa * 4, c->stream));
+        if (want_dense && in->n_reads) KASA_CUDA_TRY(cudaMemsetAsync(sl.scores, 0, (size_t)in->n_reads * c->n_taxa * 4, c->stream));
+        if (want_hits && in->n_reads) {
+            KASA_CUDA_TRY(cudaMemsetAsync(sl.hit_count, 0, (size_t)in->n_reads * 4, c->stream));
+            KASA_CUDA_TRY(cudaMemsetAsync(sl.hit_begin, 0, (size_t)in->n_reads * 8, c->stream));
+            *sl.h_hits = 0;
+        }
     }
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[6], c->stream));
     KASA_CUDA_TRY(cudaEventRecord(sl.ev1, c->stream));
-    const bool copy_scores = want_scores && out->scores && in->n_reads;
+    const bool copy_scores = want_dense && out->scores && in->n_reads;
     if (copy_scores && out->scores_location == KASA_MEM_DEVICE)
         KASA_CUDA_TRY(cudaMemcpyAsync(out->scores, sl.scores, (size_t)in->n_reads * c->n_taxa * 4, cudaMemcpyDeviceToDevice, c->stream));
     KASA_CUDA_TRY(cudaMemcpyAsync(sl.h_err, c->d_err, 16, cudaMemcpyDeviceToHost, c->stream));
@@ -685,6 +821,7 @@ int kasa_identify_submit(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resu
     }
     sl.res = out;
     sl.n = n;
+    sl.n_reads = in->n_reads;
     sl.n_passes = n ? plan.n_passes : 0;
     sl.pending = true;
     c->submitted += 1;
@@ -792,7 +929,7 @@ static void shard_common_init(kasa_ctx *c, int rank, int n_shards, const uint32_
         KASA_CUDA_TRY(cudaEventCreate(&c->sh.ev_score0));
     }
     // the record stage is only needed to answer peers' identify queries, i.e. when this context holds an index shard
-    if (n_shards > 1 && c->idx_lo && !c->sh.d_stage) c->sh.d_stage = dev_alloc<uint64_t>(c, (size_t)(c->p.max_batch_kmers + 2) * record_words(c->hb));
+    if (n_shards > 1 && c->idx_lo && !c->sh.d_stage) c->sh.d_stage = dev_alloc<uint64_t>(c, (size_t)(c->p.max_batch_kmers + 2) * kRecWords);
     KASA_CUDA_TRY(cudaMemcpyAsync(c->sh.d_prefix_begin, prefix_begin, (n_shards + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->sh.on = true; c->sh.connected = false; c->sh.rank = rank; c->sh.n = n_shards; c->sh.phase = 0;
@@ -801,7 +938,7 @@ static void shard_common_init(kasa_ctx *c, int rank, int n_shards, const uint32_
 static void *const *shard_buffers(kasa_ctx *c, void *out[KASA_SHARD_NBUF])
 {
     out[0] = c->sb.w0[0]; out[1] = c->sb.w0[1]; out[2] = c->sb.w1[0]; out[3] = c->sb.w1[1];
-    out[4] = c->sb.v[0]; out[5] = c->sb.v[1]; out[6] = c->d_rec; out[7] = c->sh.d_stage;
+    out[4] = c->sb.v[0]; out[5] = c->sb.v[1]; out[6] = c->d_rec; out[7] = c->sh.d_stage; out[8] = c->ovf.data;
     return out;
 }
 
@@ -897,6 +1034,7 @@ int kasa_index_from_build_shard(kasa_ctx *c, const uint32_t *taxid_of_idx, uint3
     if (c->wide) KASA_CUDA_TRY(cudaMemcpyAsync(c->idx_hi, c->sb.w1[b] + o, n * 8, cudaMemcpyDeviceToDevice, c->stream));
     TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
     launch_map_taxids(c->stream, c->sb.v[b] + o, n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
+    launch_index_flags(c->stream, c->idx_lo, c->idx_hi, c->idx_tax, n, c->K, c->p.k_low, &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     check_device_flags(c);
     dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
@@ -1015,7 +1153,9 @@ int kasa_shard_sort(kasa_ctx *c, const kasa_read_batch *in, kasa_shard_runs *min
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[0], c->stream));
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[1], c->stream));
     const uint32_t *first = nullptr;
-    const uint64_t n = extract_batch(c, in, sl, &first);
+    uint32_t max_inst = 0;
+    const uint64_t n = extract_batch(c, in, sl, &first, &max_inst);
+    c->sh.max_inst = max_inst;
     KASA_CUDA_TRY(cudaEventRecord(sl.in_free, c->stream));
     sl.in_free_set = true;
     const int sorted_from = std::max(0, 5 * c->K - c->sort_bits);
@@ -1057,6 +1197,7 @@ int kasa_shard_lookup(kasa_ctx *c, const kasa_shard_runs *all)
     // queries are read from the origin's sorted buffer; the local run's records go straight to their instance slots,
     // a peer's records are left in run order in the stage (segment o starts where the runs of the origins before o end)
     uint64_t seg[KASA_MAX_SHARDS + 1] = {0};
+    KASA_CUDA_TRY(cudaMemsetAsync(c->ovf.cursor, 0, 8, c->stream));
     for (int o = 0; o < c->sh.n; ++o) {
         const kasa_shard_runs &r = all[o];
         KASA_REQUIRE(r.cur == 0 || r.cur == 1, KASA_ERR_ARG, "kasa_shard_runs.cur must be 0 or 1");
@@ -1074,10 +1215,11 @@ int kasa_shard_lookup(kasa_ctx *c, const kasa_shard_runs *all)
         const uint64_t *q_lo = reinterpret_cast<const uint64_t *>(c->sh.peer[o][r.cur]) + b0;
         const uint64_t *q_hi = c->wide ? reinterpret_cast<const uint64_t *>(c->sh.peer[o][2 + r.cur]) + b0 : nullptr;
         const uint32_t *inst = o == me ? c->sb.v[r.cur] + b0 : nullptr;
-        uint64_t *rec = o == me ? c->d_rec : c->sh.d_stage + seg[o] * record_words(c->hb);
+        uint64_t *rec = o == me ? c->d_rec : c->sh.d_stage + seg[o] * kRecWords;
         const uint32_t tq = lookup_tile_queries(m, c->idx_n);
         launch_partition(c->stream, q_lo, q_hi, m, idx, lp, c->d_part, tq, sorted_from, &c->launches);
-        launch_lookup(c->stream, q_lo, q_hi, inst, m, idx, lp, c->d_part, rec, tq, &c->launches);
+        // the rank of a k-mer is its position in the ORIGIN's sorted run; overflow lists stay in this shard's array (owner = me)
+        launch_lookup(c->stream, q_lo, q_hi, inst, m, b0, idx, lp, c->d_part, rec, tq, c->ovf, (uint32_t)me, c->d_err, &c->launches);
     }
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[5], c->stream));
     KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));        // every record this shard owes is in its origin's HBM
@@ -1106,23 +1248,34 @@ int kasa_shard_score(kasa_ctx *c, const kasa_shard_runs *all, kasa_batch_result 
         uint64_t seg = 0;                                     // where owner w staged this origin's segment
         for (int o = 0; o < me; ++o) seg += o == w ? 0 : all[o].begin[w + 1] - all[o].begin[w];
         const uint64_t b0 = mine.begin[w], m = mine.begin[w + 1] - b0;
-        launch_scatter_records(c->stream, reinterpret_cast<const uint64_t *>(c->sh.peer[w][7]) + seg * record_words(c->hb), c->sb.v[mine.cur] + b0, m,
-                               c->d_rec, record_words(c->hb), &c->launches);
+        launch_scatter_records(c->stream, reinterpret_cast<const uint64_t *>(c->sh.peer[w][7]) + seg * kRecWords, c->sb.v[mine.cur] + b0, m,
+                               c->d_rec, &c->launches);
     }
+    const bool want_hits = want_scores && out->hit_taxon != nullptr;
+    const bool want_dense = want_scores && (out->scores != nullptr || (!want_hits && c->dense_scores));
+    KASA_REQUIRE(!want_dense || c->dense_scores, KASA_ERR_ARG,
+                 "the dense score matrix [max_batch_seqs][n_taxa] is too large for this taxonomy: use the sparse results (max_batch_hits, hit_*)");
+    KASA_REQUIRE(!want_hits || (sl.hit_taxon && out->hit_score && out->hit_begin && out->hit_count), KASA_ERR_ARG,
+                 "sparse results need kasa_params.max_batch_hits > 0 and all four hit_* buffers");
+    (void)lp;
     if (n) {
-        launch_per_read(c->stream, c->d_rec, c->d_read_koff, n_reads, lp, want_scores ? sl.scores : nullptr, c->d_cnt_fx, c->d_cnt_un,
-                        &c->launches);
-        launch_fold_counts(c->stream, c->d_cnt_fx, c->d_cnt_un, lp, c->d_tot_all, c->d_tot_un, &c->launches);
-    } else if (want_scores && n_reads) {
-        KASA_CUDA_TRY(cudaMemsetAsync(sl.scores, 0, (size_t)n_reads * c->n_taxa * 4, c->stream));
+        score_stage(c, sl, n, n_reads, c->sh.max_inst, mine.cur, want_dense, want_hits);
+    } else {
+        if (want_dense && n_reads) KASA_CUDA_TRY(cudaMemsetAsync(sl.scores, 0, (size_t)n_reads * c->n_taxa * 4, c->stream));
+        if (want_hits && n_reads) {
+            KASA_CUDA_TRY(cudaMemsetAsync(sl.hit_count, 0, (size_t)n_reads * 4, c->stream));
+            KASA_CUDA_TRY(cudaMemsetAsync(sl.hit_begin, 0, (size_t)n_reads * 8, c->stream));
+            *sl.h_hits = 0;
+        }
     }
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[6], c->stream));
-    if (want_scores && out->scores && n_reads)
+    if (want_dense && out->scores && n_reads)
         KASA_CUDA_TRY(cudaMemcpyAsync(out->scores, sl.scores, (size_t)n_reads * c->n_taxa * 4,
                                       out->scores_location == KASA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[7], c->stream));
     c->sh.phase = 0;
     check_device_flags(c);
+    deliver_hits(c, sl, out, n_reads);
     float total = 0.f;
     for (int i = 0; i < KASA_N_STAGES; ++i) {
         float ms = 0.f;

@@ -5,8 +5,9 @@
 // A contribution (instance i, level j) is applied by the reference when the group holding i at level j is
 // flushed, i.e. at sorted position T_j(i) = the first position p > i where either a new matching group of level j
 // starts or a new valid trie range starts (SURVEY.md §3.1 "Floating-point order").  Sorting a read's
-// contributions by (T_j(i), j) and adding them sequentially reproduces the reference's rounding.
-// This path favours clarity over speed: it is the parity mode, KASA_SCORE_FAST is the throughput mode.
+// contributions by (T_j(i), j) and adding them sequentially reproduces the reference's rounding: this file computes
+// the T_j(i), score.cu orders and replays the contributions (the same two kernels as KASA_SCORE_ORDERED, with the
+// flush position as the sort key instead of the sorted rank).
 #pragma once
 #include "common.cuh"
 #include "lookup.cuh"
@@ -18,7 +19,6 @@ struct ExactWorkspace {
     uint32_t *first;     // [tiles][num_k] first flagged position inside the tile (or ~0)
     uint32_t *next;      // [tiles][num_k] first flagged position in any later tile (or ~0)
     uint32_t *trig;      // [n][num_k] T_j by instance
-    uint32_t *max_inst;  // [1]
 };
 
 constexpr int kExactTile = 1024;
@@ -27,12 +27,5 @@ inline size_t exact_tiles(uint64_t n) { return (size_t)div_up<uint64_t>(n ? n : 
 // fills ws.trig from the fully sorted queries, their instance ids and the match records written by the lookup kernel
 void launch_exact_triggers(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n,
                            IndexDev idx, LevelParams lp, const uint64_t *rec, ExactWorkspace ws, uint64_t *launches);
-
-// largest number of instances of any read -> ws.max_inst (host reads it back to size the shared memory)
-void launch_exact_max_instances(cudaStream_t s, const uint64_t *read_koff, uint32_t n_reads, uint32_t *max_inst, uint64_t *launches);
-
-// scores[r][t] in reference order; returns false if a read has too many (instance, level) pairs for shared memory
-bool launch_exact_scores(cudaStream_t s, const uint64_t *rec, const uint32_t *trig, const uint64_t *read_koff, uint32_t n_reads,
-                         uint32_t max_inst, LevelParams lp, float *scores, uint64_t *launches);
 
 }  // namespace kasa

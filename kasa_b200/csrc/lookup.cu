@@ -1,14 +1,22 @@
 // lookup.cu — see lookup.cuh.
 //
 // Data flow per batch (all arrays in HBM):
-//   sorted (q, inst)  --partition-->  per-tile index span  --lookup-->  rec[inst] (32 B, scattered
-//   back to emission order)  --per_read-->  scores[read][taxon], counts[level][taxon]
+//   sorted (q, inst)  --partition-->  per-tile index span  --lookup-->  rec[inst] (one 32-byte sector, scattered
+//   back to emission order)  --score.cu-->  scores[read][taxon], counts[level][taxon]
 //
 // The reference walks sorted queries and the sorted index with a sequential state machine and scores
 // "groups" (all query instances sharing a k-prefix) when the next group appears.  Every quantity it
 // accumulates is linear in the hit instances, so here each instance independently
 // finds the index entries sharing >= k_low leading letters with it (one binary search + a short scan of
-// a shared-memory copy of the tile's index span) and records, per taxon, up to which level it matches.
+// a shared-memory copy of the tile's index span) and records, per distinct taxon, up to which level it matches.
+// The distinct taxa of a k_low group are its flagged entries (lookup.cuh: IndexDev), so no per-query set
+// structure is needed and the number of taxa is only bounded by the 16-bit dense index.
+//
+// Measured on B200 (tools/mem_probe*.cu): HBM3e serves ~35 G random 32-byte sectors per second, reads and full-sector
+// writes alike, partial-sector writes ~20 G/s, whatever the size of the region (no gain from windows beyond L2).
+// One full-sector store per instance is therefore the cheapest way back from sorted order to emission order, and it
+// bounds this kernel: instances without any hit do not store at all (score.cu recognises their stale slots by the
+// batch epoch in the record).
 #include <cstdlib>
 #include <cstring>
 
@@ -26,38 +34,6 @@ __device__ __forceinline__ bool key_lt(const Key &a, const Key &b)
 {
     if (W && a.hi != b.hi) return a.hi < b.hi;
     return a.lo < b.lo;
-}
-
-// number of equal leading letters of two K-letter k-mers (5 bits per letter, first letter in the MSBs)
-template <bool W>
-__device__ __forceinline__ int common_letters(const Key &a, const Key &b, int K)
-{
-    int lead;
-    if (W) {
-        uint64_t xh = a.hi ^ b.hi;
-        if (xh) lead = __clzll((long long)xh) - (128 - 5 * K);
-        else {
-            uint64_t xl = a.lo ^ b.lo;
-            if (!xl) return K;
-            lead = (5 * K - 64) + __clzll((long long)xl);
-        }
-    } else {
-        uint64_t x = a.lo ^ b.lo;
-        if (!x) return K;
-        lead = __clzll((long long)x) - (64 - 5 * K);
-    }
-    return lead / 5;
-}
-
-// letter at 1-based position k
-template <bool W>
-__device__ __forceinline__ uint32_t letter_at(const Key &q, int k, int K)
-{
-    int sh = 5 * (K - k);
-    if (!W) return (uint32_t)(q.lo >> sh) & 31u;
-    if (sh >= 64) return (uint32_t)(q.hi >> (sh - 64)) & 31u;
-    if (sh + 5 <= 64) return (uint32_t)(q.lo >> sh) & 31u;
-    return (uint32_t)((q.hi << (64 - sh)) | (q.lo >> sh)) & 31u;
 }
 
 // smallest / one-past-largest k-mer sharing all bits above `sh` with q
@@ -84,21 +60,42 @@ __device__ __forceinline__ Key prefix_ceil(const Key &q, int sh)
     return r;
 }
 
+// letter at 1-based position k
+template <bool W>
+__device__ __forceinline__ uint32_t letter_at(const Key &q, int k, int K)
+{
+    int sh = 5 * (K - k);
+    if (!W) return (uint32_t)(q.lo >> sh) & 31u;
+    if (sh >= 64) return (uint32_t)(q.hi >> (sh - 64)) & 31u;
+    if (sh + 5 <= 64) return (uint32_t)(q.lo >> sh) & 31u;
+    return (uint32_t)((q.hi << (64 - sh)) | (q.lo >> sh)) & 31u;
+}
+
+// index entries as the kernels see them: key with the flag bit stripped, the flag, the taxon
+template <bool W>
+__device__ __forceinline__ Key strip(uint64_t lo, uint64_t hi)
+{
+    return W ? Key{lo, hi & ~kKeyFlag} : Key{lo & ~kKeyFlag, 0ull};
+}
+
 struct GmemAcc {
     const uint64_t *klo, *khi;
     const uint16_t *tax;
     template <bool W>
-    __device__ __forceinline__ Key key(int64_t i) const { return Key{__ldg(klo + i), W ? __ldg(khi + i) : 0ull}; }
+    __device__ __forceinline__ Key key(int64_t i) const { return strip<W>(__ldg(klo + i), W ? __ldg(khi + i) : 0ull); }
+    template <bool W>
+    __device__ __forceinline__ bool first(int64_t i) const { return ((W ? __ldg(khi + i) : __ldg(klo + i)) & kKeyFlag) != 0; }
     __device__ __forceinline__ uint32_t taxon(int64_t i) const { return __ldg(tax + i); }
 };
 
 struct SmemAcc {
     const uint64_t *klo, *khi;
     const uint16_t *tax;
-    int64_t a;     // global index of element 0
     template <bool W>
-    __device__ __forceinline__ Key key(int64_t i) const { return Key{klo[i - a], W ? khi[i - a] : 0ull}; }
-    __device__ __forceinline__ uint32_t taxon(int64_t i) const { return tax[i - a]; }
+    __device__ __forceinline__ Key key(int64_t i) const { return strip<W>(klo[i], W ? khi[i] : 0ull); }
+    template <bool W>
+    __device__ __forceinline__ bool first(int64_t i) const { return ((W ? khi[i] : klo[i]) & kKeyFlag) != 0; }
+    __device__ __forceinline__ uint32_t taxon(int64_t i) const { return tax[i]; }
 };
 
 // first position in [lo, hi) whose key is >= q.  The trip count depends only on hi - lo, which is uniform
@@ -114,30 +111,6 @@ __device__ __forceinline__ int64_t lower_bound(const Acc &acc, int64_t lo, int64
         n -= half;
     }
     return lo + (key_lt<W>(acc.template key<W>(lo), q) ? 1 : 0);
-}
-
-// record held in registers: raise the level field of a taxon (1-based dense index) to h; `np` tracks the level
-// sizes |taxa_j| (one byte per level j, the fourth word of a 3-bit record): raising a field from cur to h adds
-// the taxon to the levels cur .. h-1
-template <int HB>
-__device__ __forceinline__ void rec_raise(uint64_t (&rw)[kRW<HB>], uint64_t &np, uint32_t taxon, uint32_t h)
-{
-    constexpr int FPW = 64 / HB;
-    constexpr uint64_t HM = (1ull << HB) - 1;
-    constexpr uint64_t kOnes = 0x0101010101010101ull;
-    const uint32_t sl = taxon - 1, wi = sl / FPW;
-    const int sh = (int)(sl % FPW) * HB;
-#pragma unroll
-    for (int i = 0; i < kRW<HB>; ++i) {
-        if (HB == 3 && i == 3) break;                 // 3-bit records keep their fields in three words
-        if ((uint32_t)i == wi) {
-            const uint32_t cur = (uint32_t)(rw[i] >> sh) & (uint32_t)HM;
-            if (h > cur) {
-                rw[i] += (uint64_t)(h - cur) << sh;
-                if (HB == 3) np += kOnes & (((1ull << (8 * h)) - 1) ^ ((1ull << (8 * cur)) - 1));
-            }
-        }
-    }
 }
 
 // all bits >= sh equal, i.e. the first K - sh/5 letters agree
@@ -166,33 +139,6 @@ __device__ __forceinline__ uint32_t match_levels(const Key &e, const Key &q, int
     return (uint32_t)(min(c, kv) - lp.k_low + 1);
 }
 
-// bit i of x (i < 64 / HB) -> bit i * HB: a taxa bit mask becomes "level field = 1" for each of its taxa
-template <int HB>
-__device__ __forceinline__ uint64_t spread_fields(uint64_t x)
-{
-    if (HB == 3) {                                    // 21 bits, stride 3
-        x &= 0x1fffffull;
-        x = (x | (x << 32)) & 0x001f00000000ffffull;
-        x = (x | (x << 16)) & 0x001f0000ff0000ffull;
-        x = (x | (x << 8)) & 0x100f00f00f00f00full;
-        x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
-        x = (x | (x << 2)) & 0x1249249249249249ull;
-        return x;
-    }
-    if (HB == 4) {                                    // 16 bits, stride 4
-        x &= 0xffffull;
-        x = (x | (x << 24)) & 0x000000ff000000ffull;
-        x = (x | (x << 12)) & 0x000f000f000f000full;
-        x = (x | (x << 6)) & 0x0303030303030303ull;
-        x = (x | (x << 3)) & 0x1111111111111111ull;
-        return x;
-    }
-    uint64_t r = 0;                                   // 12 bits, stride 5
-#pragma unroll
-    for (int i = 0; i < 12; ++i) r |= ((x >> i) & 1ull) << (5 * i);
-    return r;
-}
-
 // last level (as a k) not killed by a '^' letter at positions k_low..k_high, or k_low - 1 (Compare.hpp:836, 897)
 template <bool W>
 __device__ __forceinline__ int last_valid_level(const Key &q, const LevelParams &lp)
@@ -216,19 +162,87 @@ __device__ __forceinline__ int last_valid_level(const Key &q, const LevelParams 
     return kv;
 }
 
-// Oversized span (rare): Set semantics of Compare.hpp:785-1041 for one query instance straight from the index in
-// HBM.  Every entry whose first c >= k_low letters equal the query's belongs to taxa_k(prefix_k(q)) for
-// k = k_low .. min(c, kv); those entries start at the lower bound of the query's k_low-letter prefix.
-template <bool W, int HB>
-__device__ __forceinline__ void match_query_gmem(const GmemAcc &acc, int64_t a, int64_t b, const Key &q, int kv,
-                                                 const LevelParams &lp, uint64_t (&rw)[kRW<HB>], uint64_t &np)
+// ---- a record's inline pairs, held in three registers
+__device__ __forceinline__ void pair_raise(uint64_t (&pw)[3], uint32_t count, uint32_t taxon, uint32_t h)
+{
+#pragma unroll
+    for (int k = 0; k < kRecInline; ++k) {
+        const int sh = kPairBits * (k % 3);
+        const uint32_t p = (uint32_t)(pw[k / 3] >> sh) & kPairMask;
+        if ((uint32_t)k < count && (p & 0xffffu) == taxon) {
+            const uint32_t cur = p >> 16;
+            if (h > cur) pw[k / 3] += (uint64_t)(h - cur) << (sh + 16);
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t rec_head(uint64_t rank, uint32_t count, uint32_t hmax, bool overflow, uint32_t owner)
+{
+    return (rank & 0xffffffffull) | ((uint64_t)(count & 0xffffu) << 32) | ((uint64_t)(hmax & 31u) << 48) | (overflow ? kRecOverflowBit : 0ull) |
+           ((uint64_t)(owner & 15u) << 54);
+}
+
+// mask format: raise (or add) the level count of a taxon among the <= kRecUpPairs pairs held in two registers;
+// false if a seventh distinct taxon would be needed
+__device__ __forceinline__ bool up_pair_raise(uint64_t (&uw)[2], uint32_t taxon, uint32_t h)
+{
+    bool done = false;
+#pragma unroll
+    for (int k = 0; k < kRecUpPairs; ++k) {
+        const int sh = kPairBits * (k % 3);
+        const uint32_t p = (uint32_t)(uw[k / 3] >> sh) & kPairMask;
+        if (done) continue;
+        if (!p) { uw[k / 3] |= (uint64_t)(taxon | (h << 16)) << sh; done = true; }
+        else if ((p & 0xffffu) == taxon) {
+            if (h > (p >> 16)) uw[k / 3] += (uint64_t)(h - (p >> 16)) << (sh + 16);
+            done = true;
+        }
+    }
+    return done;
+}
+
+// General path (oversized span read from HBM, or a taxa set that does not fit the record): Set semantics of
+// Compare.hpp:785-1041 for one query instance.  g0 = first entry of the query's k_low group, b = end of the span.
+// Every entry whose first c >= k_low letters equal the query's belongs to taxa_k(prefix_k(q)) for k = k_low .. min(c, kv).
+template <bool W, class Acc>
+__device__ __noinline__ void match_general(const Acc &acc, int64_t g0, int64_t b, const Key &q, int kv, const LevelParams &lp, OverflowBuf ovf,
+                                           uint32_t owner, uint32_t *err_flag, uint64_t rank, uint64_t (&out)[4])
 {
     const int low_sh = 5 * (lp.K - lp.k_low);
-    for (int64_t e = lower_bound<W>(acc, a, b, prefix_floor<W>(q, low_sh)); e < b; ++e) {
-        const Key ek = acc.template key<W>(e);
-        if (!shares_prefix<W>(ek, q, low_sh)) break;
-        rec_raise<HB>(rw, np, acc.taxon(e), match_levels<W>(ek, q, kv, lp));
+    out[0] = rank & 0xffffffffull; out[1] = out[2] = out[3] = 0;
+    uint32_t c = 0;
+    int64_t gend = g0;
+    for (; gend < b && shares_prefix<W>(acc.template key<W>(gend), q, low_sh); ++gend) c += acc.template first<W>(gend) ? 1u : 0u;
+    if (!c) return;
+    uint32_t hmax = 1;
+    if (c <= (uint32_t)kRecInline) {
+        uint64_t pw[3] = {0, 0, 0};
+        uint32_t k = 0;
+        for (int64_t e = g0; e < gend; ++e)
+            if (acc.template first<W>(e)) { pw[k / 3] |= (uint64_t)(acc.taxon(e) | (1u << 16)) << (kPairBits * (k % 3)); ++k; }
+        for (int64_t e = g0; e < gend; ++e) {
+            const uint32_t h = match_levels<W>(acc.template key<W>(e), q, kv, lp);
+            if (h > 1) { pair_raise(pw, c, acc.taxon(e), h); hmax = max(hmax, h); }
+        }
+        out[0] = rec_head(rank, c, hmax, false, owner); out[1] = pw[0]; out[2] = pw[1]; out[3] = pw[2];
+        return;
     }
+    if (c > 0xffffu) { atomicOr(err_flag, 16u); return; }      // cannot happen: <= 65535 taxa
+    const unsigned long long base = atomicAdd(ovf.cursor, (unsigned long long)c);
+    if (base + c > ovf.cap) { atomicOr(err_flag, 8u); return; }
+    uint32_t *list = ovf.data + base;
+    uint32_t k = 0;
+    for (int64_t e = g0; e < gend; ++e)
+        if (acc.template first<W>(e)) list[k++] = acc.taxon(e) | (1u << 16);
+    for (int64_t e = g0; e < gend; ++e) {
+        const uint32_t h = match_levels<W>(acc.template key<W>(e), q, kv, lp);
+        if (h <= 1) continue;
+        hmax = max(hmax, h);
+        const uint32_t t = acc.taxon(e);
+        for (uint32_t x = 0; x < c; ++x)
+            if ((list[x] & 0xffffu) == t) { if ((list[x] >> 16) < h) list[x] = t | (h << 16); break; }
+    }
+    out[0] = rec_head(rank, c, hmax, true, owner); out[1] = (uint64_t)base;
 }
 
 template <bool W>
@@ -286,11 +300,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // copies start at the aligned entry below the span and the arrays are padded
 constexpr int kKeyPad = 2, kTaxPad = 16;
 
-template <bool W>
+template <bool W, bool MASK>
 struct SpanStage {
     uint64_t klo[kSpanCap + kKeyPad];
     uint64_t khi[W ? kSpanCap + kKeyPad : 2];
     uint16_t tax[kSpanCap + kTaxPad];
+    uint64_t pw[3][MASK ? 1 : kLookupTile];   // list records: pair words of the tile's records, word-major (conflict-free per-thread slots)
     uint64_t bar;                        // mbarrier of the bulk copies
 };
 
@@ -298,22 +313,21 @@ struct SpanStage {
 // arrays) arrives as TMA bulk copies on an mbarrier while the threads fetch their queries.  Per query:
 //   1. one binary search for the first entry sharing the query's first k_low letters — the QPT searches of a thread
 //      run in lockstep (independent chains of shared-memory loads, 32-bit positions, CTA-uniform trip count);
-//   2. a forward walk over those entries, again QPT queries in lockstep: the taxa seen are OR-ed into a 64-bit
-//      mask in a register, and the sub-range sharing more than k_low letters (contiguous, usually 0-2 entries)
-//      is remembered;
-//   3. the mask spreads into "level 1" fields, the remembered entries raise their taxa's fields, the level sizes
-//      follow from popcount + raises, and one 32-byte store puts the record into the instance's slot.
-// The record lives in registers throughout; shared memory only holds the span.
-template <bool W, int HB>
+//   2. a forward walk over those entries, again QPT queries in lockstep: every flagged entry (first of its taxon in
+//      the group) appends a (taxon, 1 level) pair to the query's record in shared memory, and the sub-range sharing
+//      more than k_low letters (contiguous, usually 0-2 entries) is remembered;
+//   3. the remembered entries raise their taxa's level counts in registers, and one 32-byte store puts the record
+//      into the instance's slot.  Taxa sets of more than nine taxa go to the overflow list (match_general).
+template <bool W, bool MASK>
 __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
-                                                                         const uint32_t *__restrict__ inst, uint64_t n, IndexDev idx,
-                                                                         LevelParams lp, const uint64_t *__restrict__ part,
-                                                                         uint64_t *__restrict__ rec, uint32_t tq)
+                                                                         const uint32_t *__restrict__ inst, uint64_t n, uint64_t rank_base,
+                                                                         IndexDev idx, LevelParams lp, const uint64_t *__restrict__ part,
+                                                                         uint64_t *__restrict__ rec, uint32_t tq, OverflowBuf ovf,
+                                                                         uint32_t owner, uint32_t *__restrict__ err_flag)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    SpanStage<W> &st = *reinterpret_cast<SpanStage<W> *>(smem_raw);
+    SpanStage<W, MASK> &st = *reinterpret_cast<SpanStage<W, MASK> *>(smem_raw);
     constexpr int QPT = kLookupTile / kLookupBlock;
-    constexpr int FPW = 64 / HB;
     const int tid = threadIdx.x;
     const uint64_t tile = blockIdx.x;
     const int64_t a = (int64_t)part[2 * tile], b = (int64_t)part[2 * tile + 1];
@@ -343,23 +357,22 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
         iv[r] = live[r] ? (inst ? ldg_stream(inst + i) : (uint32_t)i) : 0u;      // inst == nullptr: record i goes to slot i
     }
     __syncthreads();                                          // the barrier word is initialised
-    const uint64_t *s_klo = st.klo + (a - ak);
-    const uint64_t *s_khi = st.khi + (W ? (a - ak) : 0);
-    const uint16_t *s_tax = st.tax + (a - ac);
+    SmemAcc sacc{st.klo + (a - ak), st.khi + (W ? (a - ak) : 0), st.tax + (a - ac)};
     const int low_sh = 5 * (lp.K - lp.k_low);                 // bits below the first k_low letters
     const int up_sh = lp.k_low < lp.K ? low_sh - 5 : 0;       // ... below the first k_low + 1 letters
-    auto skey = [&](int e) { return Key{s_klo[e], W ? s_khi[e] : 0ull}; };
 
     int pos[QPT], kv[QPT];
-    uint64_t mask[QPT];
+    uint32_t cnt[QPT];                                        // flagged entries seen = distinct taxa of the k_low group
+    uint64_t mask[QPT];                                       // MASK: the taxa of the k_low group
     uint32_t up[QPT];                                         // entries sharing > k_low letters: first position << 12 | count (both <= kSpanCap < 4096)
     uint32_t act = 0;
 #pragma unroll
     for (int r = 0; r < QPT; ++r) {
-        pos[r] = 0; mask[r] = 0; up[r] = 0;
+        pos[r] = 0; cnt[r] = 0; up[r] = 0; mask[r] = 0;
         kv[r] = live[r] ? last_valid_level<W>(qv[r], lp) : 0;
         if (live[r] && kv[r] >= lp.k_low) act |= 1u << r;
     }
+    int g0[QPT];
     if (span > 0) {
         mbar_wait(&st.bar, 0);
         // ---- 1. lockstep binary searches for the first entry >= the query's k_low-letter prefix
@@ -372,30 +385,42 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
                 const int half = nn >> 1;
 #pragma unroll
                 for (int r = 0; r < QPT; ++r)
-                    if (key_lt<W>(skey(pos[r] + half - 1), fl[r])) pos[r] += half;
+                    if (key_lt<W>(sacc.template key<W>(pos[r] + half - 1), fl[r])) pos[r] += half;
                 nn -= half;
             }
 #pragma unroll
             for (int r = 0; r < QPT; ++r)
-                if (key_lt<W>(skey(pos[r]), fl[r])) ++pos[r];
+                if (key_lt<W>(sacc.template key<W>(pos[r]), fl[r])) ++pos[r];
         }
+#pragma unroll
+        for (int r = 0; r < QPT; ++r) g0[r] = pos[r];
         // ---- 2. lockstep forward walks over the entries sharing k_low letters
         uint32_t go = act;
         while (go) {
-            Key ek[QPT];
+            uint64_t elo[QPT], ehi[QPT];
             uint32_t tx[QPT];
 #pragma unroll
             for (int r = 0; r < QPT; ++r) {                   // independent loads first
                 const int e = min(pos[r], span - 1);
-                ek[r] = skey(e);
-                tx[r] = s_tax[e];
+                elo[r] = sacc.klo[e];
+                ehi[r] = W ? sacc.khi[e] : 0ull;
+                tx[r] = sacc.tax[e];
             }
 #pragma unroll
             for (int r = 0; r < QPT; ++r) {
                 if (!((go >> r) & 1u)) continue;
-                if (pos[r] < span && shares_prefix<W>(ek[r], qv[r], low_sh)) {
-                    mask[r] |= 1ull << (tx[r] - 1);
-                    if (kv[r] > lp.k_low && shares_prefix<W>(ek[r], qv[r], up_sh)) up[r] = (up[r] ? up[r] : (uint32_t)pos[r] << 12) + 1;
+                const Key ek = strip<W>(elo[r], ehi[r]);
+                if (pos[r] < span && shares_prefix<W>(ek, qv[r], low_sh)) {
+                    if (MASK) mask[r] |= 1ull << (tx[r] - 1);
+                    else if ((W ? ehi[r] : elo[r]) & kKeyFlag) {
+                        const uint32_t k = cnt[r]++;
+                        if (!MASK && k < (uint32_t)kRecInline) {
+                            uint64_t *w = &st.pw[k / 3][MASK ? 0 : r * kLookupBlock + tid];
+                            const uint64_t p = (uint64_t)(tx[r] | (1u << 16)) << (kPairBits * (k % 3));
+                            *w = (k % 3) ? (*w | p) : p;
+                        }
+                    }
+                    if (kv[r] > lp.k_low && shares_prefix<W>(ek, qv[r], up_sh)) up[r] = (up[r] ? up[r] : (uint32_t)pos[r] << 12) + 1;
                     ++pos[r];
                 } else {
                     go &= ~(1u << r);
@@ -409,27 +434,49 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
     for (int r = 0; r < QPT; ++r) {
         if (r * kLookupBlock >= (int)tq) break;             // CTA-uniform
         if (!live[r]) continue;
-        constexpr int RW = kRW<HB>;
-        uint64_t rw[RW];
+        const uint64_t rank = rank_base + tile * tq + (uint64_t)(r * kLookupBlock + tid);
+        uint64_t out[4] = {rank & 0xffffffffull, 0, 0, 0};
+        if (staged && MASK) {
+            if (mask[r]) {
+                uint64_t uw[2] = {0, 0};
+                uint32_t hmax = 1;
+                bool fits = true;
+                for (uint32_t e = up[r] >> 12, end = (up[r] >> 12) + (up[r] & 4095u); e < end; ++e) {
+                    const uint32_t h = match_levels<W>(sacc.template key<W>((int64_t)e), qv[r], kv[r], lp);
+                    fits = up_pair_raise(uw, sacc.tax[e], h) && fits;
+                    hmax = max(hmax, h);
+                }
+                if (fits) {
+                    out[0] = rec_head(rank, (uint32_t)__popcll(mask[r]), hmax, false, owner) | kRecMaskBit;
+                    out[1] = mask[r]; out[2] = uw[0]; out[3] = uw[1];
+                } else {
+                    match_general<W>(sacc, (int64_t)g0[r], (int64_t)span, qv[r], kv[r], lp, ovf, owner, err_flag, rank, out);
+                }
+            }
+        } else if (staged) {
+            const uint32_t c = cnt[r];
+            if (c > (uint32_t)kRecInline) {
+                match_general<W>(sacc, (int64_t)g0[r], (int64_t)span, qv[r], kv[r], lp, ovf, owner, err_flag, rank, out);
+            } else if (c) {
+                uint64_t pw[3];
 #pragma unroll
-        for (int i = 0; i < RW; ++i) rw[i] = 0;
-        uint64_t np = (uint32_t)__popcll(mask[r]);
-        if (staged) {
-#pragma unroll
-            for (int i = 0; i < RW; ++i)
-                if (i * FPW < 64 && !(HB == 3 && i == 3)) rw[i] = spread_fields<HB>(mask[r] >> (i * FPW));
-            for (uint32_t e = up[r] >> 12, end = (up[r] >> 12) + (up[r] & 4095u); e < end; ++e)
-                rec_raise<HB>(rw, np, s_tax[e], match_levels<W>(skey((int)e), qv[r], kv[r], lp));
+                for (int w = 0; w < 3; ++w) pw[w] = c > 3u * w ? st.pw[w][MASK ? 0 : r * kLookupBlock + tid] : 0ull;
+                uint32_t hmax = 1;
+                for (uint32_t e = up[r] >> 12, end = (up[r] >> 12) + (up[r] & 4095u); e < end; ++e) {
+                    const uint32_t h = match_levels<W>(sacc.template key<W>((int64_t)e), qv[r], kv[r], lp);
+                    pair_raise(pw, c, sacc.tax[e], h);
+                    hmax = max(hmax, h);
+                }
+                out[0] = rec_head(rank, c, hmax, false, owner); out[1] = pw[0]; out[2] = pw[1]; out[3] = pw[2];
+            }
         } else if ((act >> r) & 1u) {
-            match_query_gmem<W, HB>(gacc, a, b, qv[r], kv[r], lp, rw, np);
+            const int64_t gg = lower_bound<W>(gacc, a, b, prefix_floor<W>(qv[r], low_sh));
+            match_general<W>(gacc, gg, b, qv[r], kv[r], lp, ovf, owner, err_flag, rank, out);
         }
-        if (HB == 3) rw[3] = np;
         // one 256-bit store = one full 32-byte sector per record (STG.256, sm_100)
-#pragma unroll
-        for (int i = 0; i < RW; i += 4)
-            asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)iv[r] * RW + i), "l"(rw[i]), "l"(rw[i + 1]),
-                         "l"(rw[i + 2]), "l"(rw[i + 3])
-                         : "memory");
+        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)iv[r] * kRecWords), "l"(out[0]), "l"(out[1]), "l"(out[2]),
+                     "l"(out[3])
+                     : "memory");
     }
 }
 
@@ -437,15 +484,38 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
 // run (contiguous, so the NVLink side is a streaming read) and scatters them into emission order in its own HBM.
 // Scattered stores INTO peer memory run ~100x slower than this (measured: DESIGN.md §5), hence the pull.
 __global__ void __launch_bounds__(256) scatter_records_kernel(const uint64_t *__restrict__ staged, const uint32_t *__restrict__ inst,
-                                                              uint64_t n, uint64_t *__restrict__ rec, int rec_words)
+                                                              uint64_t n, uint64_t *__restrict__ rec)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t j = ldg_stream(inst + i);
-    for (int o = 0; o < rec_words; o += 4) {
-        uint64_t a, b, c, d;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(staged + i * rec_words + o));
-        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)j * rec_words + o), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+    uint64_t a, b, c, d;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(staged + i * kRecWords));
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)j * kRecWords), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+// Taxon-first flags (lookup.cuh: IndexDev): entry e is flagged unless an earlier entry of its k_low-letter group has the
+// same taxon.  Thread per entry, backward scan to the start of the group (groups are short: 1.3 entries on average for
+// the saturated C2 index; the scan is quadratic in the group size, which only shows for k_low <= 3 on large indexes).
+// Keys are read with the flag bit stripped, so concurrent flagging of other entries is harmless.
+template <bool W>
+__global__ void __launch_bounds__(256) index_flags_kernel(uint64_t *__restrict__ key_lo, uint64_t *__restrict__ key_hi,
+                                                          const uint16_t *__restrict__ tax, uint64_t n, int low_sh)
+{
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    volatile uint64_t *vlo = key_lo, *vhi = key_hi;
+    const Key me = strip<W>(vlo[e], W ? vhi[e] : 0ull);
+    const uint32_t t = tax[e];
+    bool first = true;
+    for (uint64_t p = e; p-- > 0;) {
+        const Key o = strip<W>(vlo[p], W ? vhi[p] : 0ull);
+        if (!shares_prefix<W>(o, me, low_sh)) break;
+        if (tax[p] == t) { first = false; break; }
+    }
+    if (first) {
+        if (W) atomicOr(reinterpret_cast<unsigned long long *>(key_hi + e), (unsigned long long)kKeyFlag);
+        else atomicOr(reinterpret_cast<unsigned long long *>(key_lo + e), (unsigned long long)kKeyFlag);
     }
 }
 
@@ -470,29 +540,12 @@ __global__ void fold_counts_kernel(unsigned long long *cnt_fx, unsigned long lon
     cnt_unique[i] = 0;
 }
 
-template <bool W>
-void launch_lookup_hb(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n, IndexDev idx,
-                      LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq)
-{
-    const unsigned tiles = (unsigned)div_up<uint64_t>(n, tq);
-    const size_t sm = sizeof(SpanStage<W>);
-    auto go = [&](auto kern) {
-        KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        kern<<<tiles, kLookupBlock, sm, s>>>(q_lo, q_hi, inst, n, idx, lp, part, rec, tq);
-    };
-    if (lp.hb == 3) go(lookup_kernel<W, 3>);
-    else if (lp.hb == 4) go(lookup_kernel<W, 4>);
-    else go(lookup_kernel<W, 5>);
-}
-
 }  // namespace
 
-void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32_t *inst, uint64_t n, uint64_t *rec, int rec_words,
-                            uint64_t *launches)
+void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32_t *inst, uint64_t n, uint64_t *rec, uint64_t *launches)
 {
     if (!n) return;
-    scatter_records_kernel<<<(unsigned)div_up<uint64_t>(n, 256), 256, 0, s>>>(staged, inst, n, rec, rec_words);
+    scatter_records_kernel<<<(unsigned)div_up<uint64_t>(n, 256), 256, 0, s>>>(staged, inst, n, rec);
     ++*launches;
 }
 
@@ -518,24 +571,32 @@ void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi
     ++*launches;
 }
 
-void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n, IndexDev idx,
-                   LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq, uint64_t *launches)
+void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n, uint64_t rank_base,
+                   IndexDev idx, LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq, OverflowBuf ovf, uint32_t owner,
+                   uint32_t *err_flag, uint64_t *launches)
 {
     if (!n) return;
-    if (idx.key_hi) launch_lookup_hb<true>(s, q_lo, q_hi, inst, n, idx, lp, part, rec, tq);
-    else launch_lookup_hb<false>(s, q_lo, q_hi, inst, n, idx, lp, part, rec, tq);
+    const unsigned tiles = (unsigned)div_up<uint64_t>(n, tq);
+    auto go = [&](auto kern, size_t sm) {
+        KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        kern<<<tiles, kLookupBlock, sm, s>>>(q_lo, q_hi, inst, n, rank_base, idx, lp, part, rec, tq, ovf, owner, err_flag);
+    };
+    const bool mask = lp.n_taxa <= kMaskTaxa;
+    if (idx.key_hi) { if (mask) go(lookup_kernel<true, true>, sizeof(SpanStage<true, true>)); else go(lookup_kernel<true, false>, sizeof(SpanStage<true, false>)); }
+    else { if (mask) go(lookup_kernel<false, true>, sizeof(SpanStage<false, true>)); else go(lookup_kernel<false, false>, sizeof(SpanStage<false, false>)); }
     ++*launches;
     KASA_CUDA_TRY(cudaGetLastError());
 }
 
-void launch_per_read(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp,
-                     float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, uint64_t *launches)
+void launch_index_flags(cudaStream_t s, uint64_t *key_lo, uint64_t *key_hi, const uint16_t *tax, uint64_t n, int K, int k_low,
+                        uint64_t *launches)
 {
-    if (!n_reads) return;
-    if (lp.hb == 3) launch_per_read_taxon(s, rec, read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
-    else launch_per_read_wide(s, rec, read_koff, n_reads, lp, scores, cnt_fx, cnt_unique);
+    if (!n) return;
+    const int low_sh = 5 * (K - k_low);
+    if (key_hi) index_flags_kernel<true><<<(unsigned)div_up<uint64_t>(n, 256), 256, 0, s>>>(key_lo, key_hi, tax, n, low_sh);
+    else index_flags_kernel<false><<<(unsigned)div_up<uint64_t>(n, 256), 256, 0, s>>>(key_lo, key_hi, tax, n, low_sh);
     ++*launches;
-    KASA_CUDA_TRY(cudaGetLastError());
 }
 
 void launch_read_offsets(cudaStream_t s, const uint64_t *koff, const uint32_t *read_first_seq, uint32_t n_reads,

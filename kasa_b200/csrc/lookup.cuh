@@ -1,41 +1,70 @@
 // lookup.cuh — sorted read k-mers against the sorted (k-mer, taxon) index for every k in
 // [k_low, k_high] at once, and per-read / per-taxon accumulation.
 //   Compare::sortInputAndCheckInvalidkMers_sta range assignment (Compare.hpp:1074-1260, Trie.hpp:494-520)
-//   Compare::compareWithDatabase (Compare.hpp:679-1069), scoreMatchNonAVX (Compare.hpp:516-532)
+//   Compare::compareWithDatabase (Compare.hpp:679-1069), scoreMatchNonAVX (Compare.hpp:516-532),
+//   markTaxIDs / sBitArray distinct-taxa sets (Compare.hpp:396-441, BitArray.hpp:18-147)
 // restated as the set semantics of SURVEY.md §3.1 (what the state machine computes), not transcribed.
 #pragma once
 #include "common.cuh"
 
 namespace kasa {
 
+// Index in HBM, structure of arrays.  The top bit of an entry's most significant key word (bit 63 of key_hi for
+// 128-bit k-mers, of key_lo otherwise; k-mers use 125 / 60 bits) is the entry's TAXON-FIRST flag: set when no earlier
+// entry of the same k_low-letter group has the same taxon.  The flagged entries of a group are exactly its distinct
+// taxa — the reference's sBitArray (BitArray.hpp:18-147) precomputed once at index load for any number of taxa.
 struct IndexDev {
     const uint64_t *key_lo;
     const uint64_t *key_hi;   // nullptr for 64-bit k-mers
     const uint16_t *tax;      // dense taxon index (1-based: position in the content file)
     uint64_t n;
 };
+constexpr uint64_t kKeyFlag = 1ull << 63;
 
 struct LevelParams {
     int K;         // highest_k (letters per k-mer)
     int k_high, k_low;
-    int num_k;     // k_high - k_low + 1
-    int n_taxa;    // incl. index 0 ("non_unique")
-    int hb;        // bits per level field in a match record (3, 4 or 5)
+    int num_k;     // k_high - k_low + 1 (<= 25)
+    int n_taxa;    // incl. index 0 ("non_unique"), <= 65535
 };
 
 constexpr int kLookupTile = 1024;      // most sorted queries per CTA (see lookup_tile_queries)
 constexpr int kLookupBlock = 256;
-// match record = 4 x u64 = one 32-byte sector for 3- and 4-bit level fields, 8 x u64 = two sectors for 5-bit fields
-// (16..31 levels, e.g. k = 25..7: 12 fields per word)
-constexpr int kRecWords = 4;
-template <int HB>
-constexpr int kRW = HB == 5 ? 8 : 4;
-__host__ __device__ inline int record_words(int hb) { return hb == 5 ? 8 : 4; }
 
-// bits needed to store a level count 0..num_k, and how many taxa one record can describe
-inline int record_level_bits(int num_k) { return num_k <= 7 ? 3 : (num_k <= 15 ? 4 : 5); }
-// 3-bit records keep their fourth word for the level sizes (see lookup.cu); the lookup kernel's taxa set is a 64-bit mask
-inline int record_taxa_capacity(int hb) { return hb == 3 ? 63 : 64; }
+// ---- match record: 4 x u64 = one 32-byte sector per k-mer instance, written at rec[instance] (emission order)
+//   w0   bits  0..31  rank: position of the instance in the batch's sorted k-mer order (fixes the fp32 summation order)
+//        bits 32..47  count = |taxa_klow| = number of (taxon, levels) pairs
+//        bits 48..52  hmax  = largest number of levels any taxon matches
+//        bit  53      the pairs live in the overflow list (count > kRecInline)
+//        bits 54..57  shard that owns the overflow list (prefix-sharded index)
+//        bit  58      mask format (content files of <= 64 taxa)
+//   list format, count <= kRecInline:  w1..w3 hold the pairs, 21 bits each, three per word: taxon (16) | levels (5);
+//                         levels = number of levels from k_low upwards at which the taxon is in taxa_k(prefix_k(q))
+//   list format, otherwise:            w1 = first entry of the list in the owner's overflow array (u32 per pair: taxon | levels << 16)
+//   mask format:          w1 = bit t-1 set for every taxon t of taxa_klow (any set size), w2..w3 = up to kRecUpPairs pairs for the taxa
+//                         that match more than one level (the others match exactly the k_low level)
+constexpr int kRecWords = 4;
+constexpr int kRecInline = 9;
+constexpr int kPairBits = 21;
+constexpr uint32_t kPairMask = (1u << kPairBits) - 1u;
+constexpr uint64_t kRecOverflowBit = 1ull << 53;
+constexpr uint64_t kRecMaskBit = 1ull << 58;
+constexpr int kRecUpPairs = 6;
+constexpr int kMaskTaxa = 65;          // n_taxa (incl. index 0) up to which records use the mask format
+
+__host__ __device__ __forceinline__ uint32_t rec_rank(uint64_t w0) { return (uint32_t)w0; }
+__host__ __device__ __forceinline__ uint32_t rec_count(uint64_t w0) { return (uint32_t)(w0 >> 32) & 0xffffu; }
+__host__ __device__ __forceinline__ uint32_t rec_hmax(uint64_t w0) { return (uint32_t)(w0 >> 48) & 31u; }
+__host__ __device__ __forceinline__ bool rec_overflow(uint64_t w0) { return (w0 & kRecOverflowBit) != 0; }
+__host__ __device__ __forceinline__ uint32_t rec_owner(uint64_t w0) { return (uint32_t)(w0 >> 54) & 15u; }
+__host__ __device__ __forceinline__ bool rec_is_mask(uint64_t w0) { return (w0 & kRecMaskBit) != 0; }
+
+// append-only side list for instances whose taxa set does not fit a record (reset per batch)
+struct OverflowBuf {
+    uint32_t *data;
+    unsigned long long *cursor;
+    uint64_t cap;
+};
 
 // per-tile index spans: part[2t], part[2t+1] = [first entry sharing the sorted prefix of the tile's first query,
 // one past the last entry sharing the sorted prefix of its last query).  The queries only need to be ordered
@@ -45,29 +74,19 @@ uint32_t lookup_tile_queries(uint64_t n_queries, uint64_t n_index);
 void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, uint64_t n, IndexDev idx,
                       LevelParams lp, uint64_t *part, uint32_t tq, int sorted_from_bit, uint64_t *launches);
 
-// one 32-byte match record per k-mer instance, written at rec[inst[i]] (instance = emission order):
-// field t-1 = number of levels (from k_low upwards) at which taxon t is in taxa_k(prefix_k(q))
-void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n,
-                   IndexDev idx, LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq, uint64_t *launches);
+// one match record per k-mer instance, written at rec[inst[i]]; rank = rank_base + i.
+// inst == nullptr: record i is written to rec[i] (sorted position; the prefix-sharded path stages records this way).
+// err_flag |= 8 when the overflow list is full.
+void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n, uint64_t rank_base,
+                   IndexDev idx, LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq, OverflowBuf ovf, uint32_t owner,
+                   uint32_t *err_flag, uint64_t *launches);
 
-// inst == nullptr: record i is written to rec[i] (sorted position; the prefix-sharded path stages records this way)
 // rec[inst[i]] = staged[i] for i < n (staged may be peer memory)
-void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32_t *inst, uint64_t n, uint64_t *rec, int rec_words,
-                            uint64_t *launches);
+void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32_t *inst, uint64_t n, uint64_t *rec, uint64_t *launches);
 
-// per read: fp32 scores in canonical order (instance order, k ascending) and the per-taxon per-level
-// counts: cnt_fx [num_k][n_taxa] fixed point 2^-32 (sum of 1/|taxa|), cnt_unique [num_k][n_taxa].
-// Level j = 0 is k_low.  scores may be nullptr (profile only).
-void launch_per_read(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp,
-                     float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, uint64_t *launches);
-
-// 3-bit records (per_read.cu): warp per read, lane per taxon
-void launch_per_read_taxon(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp,
-                           float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique);
-
-// 4- and 5-bit records (per_read.cu): the same organisation with the level sizes counted from the fields
-void launch_per_read_wide(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp,
-                          float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique);
+// sets the taxon-first flags of a freshly loaded index (keys must be unflagged); k_low-letter groups
+void launch_index_flags(cudaStream_t s, uint64_t *key_lo, uint64_t *key_hi, const uint16_t *tax, uint64_t n, int K, int k_low,
+                        uint64_t *launches);
 
 // read_koff[r] = koff[read_first_seq[r]] (or koff[r])
 void launch_read_offsets(cudaStream_t s, const uint64_t *koff, const uint32_t *read_first_seq, uint32_t n_reads,

@@ -1,0 +1,881 @@
+// score.cu — see score.cuh.
+#include "score.cuh"
+
+namespace kasa {
+namespace {
+
+constexpr uint64_t kNib1 = 0x1111111111111111ull;
+
+// nibble j (j < h) = 1: adding it per (taxon, levels = h) pair counts the level sizes |taxa_j| (<= 9 per nibble for inline records)
+__device__ __forceinline__ void nib_below(uint32_t h, uint64_t &lo, uint64_t &hi)
+{
+    lo = h >= 16 ? kNib1 : (((1ull << (4 * h)) - 1) & kNib1);
+    hi = h > 16 ? (((1ull << (4 * (h - 16))) - 1) & kNib1) : 0ull;
+}
+__device__ __forceinline__ uint32_t nib_get(uint64_t lo, uint64_t hi, uint32_t j)
+{
+    return (uint32_t)((j < 16 ? lo >> (4 * j) : hi >> (4 * (j - 16))) & 15u);
+}
+
+__device__ __forceinline__ uint32_t inv_fx(uint32_t n) { return (uint32_t)((4294967296ull + (n >> 1)) / n); }   // 2^32 / n, n >= 2
+
+// pair k (taxon | levels << 16) of an inline list record / of the up-pairs of a mask record
+__device__ __forceinline__ uint32_t rec_pair(const uint64_t (&pw)[3], int k) { return (uint32_t)(pw[k / 3] >> (kPairBits * (k % 3))) & kPairMask; }
+__device__ __forceinline__ uint32_t up_pair(const uint64_t (&pw)[3], int k) { return (uint32_t)(pw[1 + k / 3] >> (kPairBits * (k % 3))) & kPairMask; }
+
+// levels of taxon t in a mask record (1 unless one of the up-pairs names it)
+__device__ __forceinline__ uint32_t mask_levels(const uint64_t (&pw)[3], uint32_t t)
+{
+    uint32_t h = 1;
+#pragma unroll
+    for (int k = 0; k < kRecUpPairs; ++k) { const uint32_t p = up_pair(pw, k); if ((p & 0xffffu) == t) h = p >> 16; }
+    return h;
+}
+
+// header words of an ordered-stream group from nibble-packed level sizes (levels >= 1 in lo / hi; score.cuh)
+__device__ __forceinline__ uint32_t header_word(uint32_t n0, uint64_t lo) { return kOpHeader | ((n0 < kOpNExt ? n0 : kOpNExt) << 21) | (((uint32_t)(lo >> 4) & 0xFFFFFu) << 1); }
+__device__ __forceinline__ uint32_t header_extra(int k, uint64_t lo, uint64_t hi)
+{
+    return k == 0 ? (uint32_t)(lo >> 24) : (k == 1 ? (uint32_t)((lo >> 56) | (hi << 8)) : (uint32_t)(hi >> 24));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// A: order the match records of a read and write the op stream
+constexpr int kAMaxWarps = 4;
+
+struct WarpMem {
+    uint64_t *key;      // [icap]  sort key << 32 | level << 16 | slot
+    uint64_t *pw;       // [3][cap] record words 1..3
+    uint32_t *meta;     // [cap]   count | hmax << 16 | overflow << 21 | owner << 22 | mask << 27
+    uint32_t *ioff;     // [cap]   instance offset inside the read (EXACT only)
+    uint32_t *bcnt;     // [nb + 1]
+    uint32_t *un;       // [num_k][64] unique hits of this warp's reads (COUNTS only)
+    uint16_t *tmp, *ord, *arr;   // [icap]
+};
+
+__host__ __device__ inline size_t warp_mem_bytes(uint32_t cap, uint32_t icap, uint32_t nb, bool exact, int count_levels)
+{
+    size_t b = (size_t)8 * icap + (size_t)24 * cap + (size_t)4 * cap + (exact ? (size_t)4 * cap : 0) + (size_t)4 * (nb + 1) + (size_t)256 * count_levels +
+               (size_t)6 * icap;
+    return (b + 15) & ~(size_t)15;
+}
+
+// nibble-packed sizes of the levels >= 1 of an inline / mask record
+__device__ __forceinline__ void level_sizes(const uint64_t (&pw)[3], uint32_t count, bool mask, uint64_t &lo, uint64_t &hi)
+{
+    lo = hi = 0;
+    if (mask) {
+#pragma unroll
+        for (int k = 0; k < kRecUpPairs; ++k) {
+            const uint32_t p = up_pair(pw, k);
+            if (p) { uint64_t a, b; nib_below(p >> 16, a, b); lo += a & ~15ull; hi += b; }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kRecInline; ++k) {
+            if ((uint32_t)k < count) { uint64_t a, b; nib_below(rec_pair(pw, k) >> 16, a, b); lo += a & ~15ull; hi += b; }
+        }
+    }
+}
+
+struct Decoded {
+    uint32_t count, hmax, sumh;
+    uint64_t npk_lo, npk_hi;      // nibble j = |taxa_j| for the levels j >= 1 (level 0: count); inline / mask records only
+    bool overflow, mask;
+};
+
+__device__ __forceinline__ Decoded decode_record(uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3, const OverflowPeers &peers)
+{
+    Decoded d;
+    d.count = rec_count(w0);
+    d.hmax = rec_hmax(w0);
+    d.overflow = rec_overflow(w0);
+    d.mask = rec_is_mask(w0);
+    d.npk_lo = d.npk_hi = 0;
+    d.sumh = 0;
+    if (!d.count) return d;
+    const uint64_t pw[3] = {w1, w2, w3};
+    if (d.mask) {
+        d.sumh = d.count;
+#pragma unroll
+        for (int k = 0; k < kRecUpPairs; ++k) {
+            const uint32_t p = up_pair(pw, k);
+            if (p) {
+                uint64_t lo, hi;
+                nib_below(p >> 16, lo, hi);
+                d.npk_lo += lo & ~15ull; d.npk_hi += hi;
+                d.sumh += (p >> 16) - 1;
+            }
+        }
+    } else if (!d.overflow) {
+#pragma unroll
+        for (int k = 0; k < kRecInline; ++k) {
+            if ((uint32_t)k < d.count) {
+                const uint32_t h = rec_pair(pw, k) >> 16;
+                uint64_t lo, hi;
+                nib_below(h, lo, hi);
+                d.npk_lo += lo & ~15ull; d.npk_hi += hi;
+                d.sumh += h;
+            }
+        }
+    } else {
+        const uint32_t *list = peers.base[rec_owner(w0)] + w1;
+        for (uint32_t k = 0; k < d.count; ++k) d.sumh += __ldg(list + k) >> 16;
+    }
+    return d;
+}
+
+// COUNTS (content files of <= 64 taxa): the per-taxon counts are accumulated here, order-free, lane = taxon (lane l owns the taxa
+// l+1 and l+33) over the records the warp holds in shared memory: level k_low hits as 2^-32 fixed point / integers in registers,
+// the levels above through packed per-read counters; kernel B then only replays the float32 scores.
+template <bool EXACT, bool COUNTS>
+__global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64_t *__restrict__ rec, const uint64_t *__restrict__ read_koff, uint32_t r0,
+                                                                    uint32_t r1, uint64_t n_kmers, LevelParams lp, OverflowPeers peers, OpsWorkspace ws,
+                                                                    const uint32_t *__restrict__ trig, uint32_t *__restrict__ err_flag, uint32_t cap,
+                                                                    uint32_t icap, uint32_t nb, uint32_t wbytes, unsigned long long *__restrict__ cnt_fx,
+                                                                    unsigned long long *__restrict__ cnt_unique, bool emit)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int w = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    WarpMem M;
+    {
+        unsigned char *base = smem_raw + (size_t)w * wbytes;
+        M.key = reinterpret_cast<uint64_t *>(base);
+        M.pw = M.key + icap;
+        M.meta = reinterpret_cast<uint32_t *>(M.pw + 3 * (size_t)cap);
+        M.ioff = M.meta + cap;
+        M.bcnt = EXACT ? M.ioff + cap : M.ioff;
+        M.un = M.bcnt + nb + 1;
+        M.tmp = reinterpret_cast<uint16_t *>(M.un + (COUNTS ? 64 * lp.num_k : 0));
+        M.ord = M.tmp + icap;
+        M.arr = M.ord + icap;
+    }
+    const uint32_t n_warps = blockDim.x >> 5;
+    const uint32_t warps_total = gridDim.x * n_warps;
+    const uint32_t NX = EXACT ? 0u : (uint32_t)ops_extra_words(lp.num_k);
+    const int T = lp.n_taxa, NK = lp.num_k;
+    // counts of this warp's reads (COUNTS): level k_low in registers, all unique hits in a per-warp table behind the per-warp arrays
+    // level k_low: 2^-32 sums and unique hits of this lane's two taxa over all the warp's reads
+    unsigned long long fx0a = 0, fx0b = 0, un0a = 0, un0b = 0;
+    __shared__ uint32_t s_invfx[kAMaxWarps][128];
+    if (COUNTS) {
+        for (int i = lane; i < NK * 64; i += 32) M.un[i] = 0;
+        for (int i = lane; i < 128; i += 32) s_invfx[w][i] = i >= 2 ? inv_fx((uint32_t)i) : 0u;
+    }
+    __syncwarp();
+    auto count_segment = [&](uint32_t m) {
+        // lane = taxon (lane l owns the taxa l+1 and l+33); warp-uniform walk over the segment's records
+        unsigned long long upa = 0, upb = 0;                        // unique hits of the levels 1..8, 8-bit fields (flushed every 128 records)
+        auto flush_up = [&]() {
+            for (int j = 1; j < NK && j <= 8; ++j) {
+                const uint32_t ua = (uint32_t)(upa >> (8 * (j - 1))) & 255u, ub = (uint32_t)(upb >> (8 * (j - 1))) & 255u;
+                if (ua) M.un[j * 64 + lane] += ua;
+                if (ub) M.un[j * 64 + 32 + lane] += ub;
+            }
+            upa = upb = 0;
+        };
+        // taxon t (0-based) of this lane matches the levels 1 .. h-1, each with `one` taxon
+        auto add_upper_unique = [&](uint32_t t, uint32_t h) {
+            const uint32_t top = h - 1 < 8u ? h - 1 : 8u;
+            const unsigned long long f = (top >= 8u ? ~0ull : ((1ull << (8 * top)) - 1)) & 0x0101010101010101ull;
+            if (t >> 5) upb += f; else upa += f;
+            for (uint32_t j = 9; j < h; ++j) M.un[j * 64 + t] += 1u;
+        };
+        for (uint32_t i = 0; i < m; ++i) {
+            const uint32_t meta = M.meta[i];
+            const uint32_t c = meta & 0xffffu, hmax = (meta >> 16) & 31u;
+            if ((meta >> 27) & 1u) {
+                const uint64_t mk = M.pw[i];
+                const uint32_t in0 = (uint32_t)(mk >> lane) & 1u, in1 = (uint32_t)(mk >> (lane + 32)) & 1u;
+                if (c == 1u) { un0a += in0; un0b += in1; }
+                else { const uint32_t f = s_invfx[w][c]; fx0a += (unsigned long long)(in0 * f); fx0b += (unsigned long long)(in1 * f); }
+                if (hmax > 1u) {
+                    const uint64_t pw[3] = {mk, M.pw[cap + i], M.pw[2 * (size_t)cap + i]};
+                    if ((pw[1] >> kPairBits) == 0 && pw[2] == 0) {
+                        // the usual case: one taxon above k_low, alone at each of its upper levels
+                        const uint32_t p = (uint32_t)pw[1] & kPairMask, t = (p & 0xffffu) - 1u;
+                        if ((t & 31u) == lane) add_upper_unique(t, p >> 16);
+                    } else {
+                        uint64_t lo, hi;
+                        level_sizes(pw, c, true, lo, hi);
+#pragma unroll
+                        for (int k = 0; k < kRecUpPairs; ++k) {
+                            const uint32_t p = up_pair(pw, k);
+                            if (!p) break;
+                            const uint32_t t = (p & 0xffffu) - 1u, h = p >> 16;
+                            if ((t & 31u) == lane) {
+                                for (uint32_t j = 1; j < h; ++j) {
+                                    const uint32_t nn = nib_get(lo, hi, j);
+                                    if (nn == 1u) M.un[j * 64 + t] += 1u;
+                                    else atomicAdd(cnt_fx + (size_t)j * T + t + 1, (unsigned long long)s_invfx[w][nn]);
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                // list records (more than six taxa above k_low, or a span read from HBM): pair by pair
+                const bool ovf = (meta >> 21) & 1u;
+                const uint64_t pw[3] = {M.pw[i], M.pw[cap + i], M.pw[2 * (size_t)cap + i]};
+                const uint32_t *list = ovf ? peers.base[(meta >> 22) & 15u] + pw[0] : nullptr;
+                uint32_t nj[32];
+                if (hmax > 1u) {
+                    for (uint32_t j = 0; j < hmax; ++j) nj[j] = 0;
+                    for (uint32_t k = 0; k < c; ++k) {
+                        const uint32_t h = (ovf ? __ldg(list + k) : (uint32_t)(pw[k / 3] >> (kPairBits * (k % 3))) & kPairMask) >> 16;
+                        for (uint32_t j = 0; j < h; ++j) ++nj[j];
+                    }
+                }
+                const uint32_t f0 = c >= 2u ? inv_fx(c) : 0u;
+                for (uint32_t k = 0; k < c; ++k) {
+                    const uint32_t e = ovf ? __ldg(list + k) : (uint32_t)(pw[k / 3] >> (kPairBits * (k % 3))) & kPairMask;
+                    const uint32_t t = (e & 0xffffu) - 1u, h = e >> 16;
+                    if ((t & 31u) != lane) continue;
+                    if (c == 1u) { if (t >> 5) un0b += 1; else un0a += 1; }
+                    else { if (t >> 5) fx0b += f0; else fx0a += f0; }
+                    for (uint32_t j = 1; j < h; ++j) {
+                        if (nj[j] == 1u) M.un[j * 64 + t] += 1u;
+                        else atomicAdd(cnt_fx + (size_t)j * T + t + 1, (unsigned long long)inv_fx(nj[j]));
+                    }
+                }
+            }
+            if ((i & 127u) == 127u) flush_up();
+        }
+        flush_up();
+    };
+
+    // sorts the `m` items in M.key and writes their groups at (o_cur, e_cur), which advance; keys in [lo, lo + range)
+    auto sort_emit = [&](uint32_t m, uint64_t lo, uint64_t range, uint64_t &o_cur, uint64_t &e_cur) {
+        if (!m) return;
+        for (uint32_t i = lane; i <= nb; i += 32) M.bcnt[i] = 0;
+        __syncwarp();
+        const float fscale = (float)nb / (float)(range ? range : 1) * 0.999999f;
+        auto bucket = [&](uint64_t key) {
+            const uint64_t pk = key >> 32;
+            const float f = (float)(pk > lo ? pk - lo : 0ull) * fscale;
+            const uint32_t b = f >= (float)nb ? nb - 1 : (uint32_t)f;
+            return b < nb ? b : nb - 1;
+        };
+        for (uint32_t x = lane; x < m; x += 32) M.arr[x] = (uint16_t)atomicAdd(&M.bcnt[bucket(M.key[x])], 1u);
+        __syncwarp();
+        {   // exclusive scan of the bucket counts (nb is a multiple of 32)
+            const uint32_t per = nb / 32;
+            uint32_t sum = 0;
+            for (uint32_t i = 0; i < per; ++i) sum += M.bcnt[lane * per + i];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(kFull, incl, d);
+                if ((int)lane >= d) incl += y;
+            }
+            uint32_t run = incl - sum;
+            for (uint32_t i = 0; i < per; ++i) { const uint32_t c = M.bcnt[lane * per + i]; M.bcnt[lane * per + i] = run; run += c; }
+            if (lane == 31) M.bcnt[nb] = run;
+        }
+        __syncwarp();
+        for (uint32_t x = lane; x < m; x += 32) M.tmp[M.bcnt[bucket(M.key[x])] + M.arr[x]] = (uint16_t)x;
+        __syncwarp();
+        for (uint32_t x = lane; x < m; x += 32) {
+            const uint64_t kx = M.key[x];
+            const uint32_t b = bucket(kx), b0 = M.bcnt[b], b1 = M.bcnt[b + 1];
+            uint32_t less = 0;
+            for (uint32_t y = b0; y < b1; ++y) less += M.key[M.tmp[y]] < kx ? 1u : 0u;
+            M.ord[b0 + less] = (uint16_t)x;
+        }
+        __syncwarp();
+        // ---- emission in sorted order: lane = item
+        for (uint32_t p0 = 0; p0 < m; p0 += 32) {
+            const uint32_t p = p0 + lane;
+            const bool valid = p < m;
+            const uint64_t key = valid ? M.key[M.ord[p]] : 0ull;
+            const uint32_t slot = (uint32_t)key & 0xffffu, lev = (uint32_t)(key >> 16) & 0xffffu;
+            uint32_t meta = 0, c = 0, hmax = 0;
+            bool ovf = false, msk = false;
+            uint64_t pw[3] = {0, 0, 0}, nlo = 0, nhi = 0;
+            uint32_t opc = 0, extc = 0, nlev = 0;                  // nlev: |taxa_lev| (EXACT)
+            const uint32_t *list = nullptr;
+            if (valid) {
+                meta = M.meta[slot];
+                c = meta & 0xffffu; hmax = (meta >> 16) & 31u; ovf = (meta >> 21) & 1u; msk = (meta >> 27) & 1u;
+                pw[0] = M.pw[slot]; pw[1] = M.pw[cap + slot]; pw[2] = M.pw[2 * (size_t)cap + slot];
+                if (ovf) list = peers.base[(meta >> 22) & 15u] + pw[0];
+                else level_sizes(pw, c, msk, nlo, nhi);
+                if (!EXACT) {
+                    opc = 1 + NX + c;
+                    extc = ovf ? hmax : 0u;                         // overflow records escape every level size (deterministic demand)
+                } else {
+                    if (!ovf) nlev = lev ? nib_get(nlo, nhi, lev) : c;
+                    else for (uint32_t k = 0; k < c; ++k) nlev += (__ldg(list + k) >> 16) > lev ? 1u : 0u;
+                    opc = 1 + nlev;
+                    extc = ovf ? 1u : 0u;
+                }
+            }
+            uint32_t io = opc, ie = extc;                  // inclusive scans
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t yo = __shfl_up_sync(kFull, io, d), ye = __shfl_up_sync(kFull, ie, d);
+                if ((int)lane >= d) { io += yo; ie += ye; }
+            }
+            const uint32_t tot_o = __shfl_sync(kFull, io, 31), tot_e = __shfl_sync(kFull, ie, 31);
+            uint32_t *op = ws.ops + o_cur + (io - opc);
+            uint16_t *ex = ws.ext + e_cur + (ie - extc);
+            if (valid && opc) {
+                if (!EXACT) {
+                    if (!ovf) {
+                        *op++ = header_word(c, nlo);
+                        for (uint32_t k = 0; k < NX; ++k) *op++ = header_extra((int)k, nlo, nhi);
+                        if (msk) {
+                            for (uint64_t left = pw[0]; left; left &= left - 1) {
+                                const uint32_t t = (uint32_t)__ffsll((long long)left);
+                                *op++ = t | (mask_levels(pw, t) << 16);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < kRecInline; ++k) {
+                                if ((uint32_t)k >= c) break;
+                                *op++ = rec_pair(pw, k);                  // already taxon | levels << 16
+                            }
+                        }
+                    } else {
+                        // level sizes by counting; all of them go through the ext stream: |taxa_klow|, then the levels 1 .. hmax-1
+                        uint16_t nj[32];
+                        for (uint32_t j = 0; j < 32; ++j) nj[j] = 0;
+                        for (uint32_t k = 0; k < c; ++k) { const uint32_t h = __ldg(list + k) >> 16; for (uint32_t j = 0; j < h; ++j) ++nj[j]; }
+                        uint64_t lo = 0, hi = 0;
+                        *ex++ = (uint16_t)c;
+                        for (uint32_t j = 1; j < hmax; ++j) {
+                            if (j < 16) lo |= (uint64_t)kOpNibExt << (4 * j); else hi |= (uint64_t)kOpNibExt << (4 * (j - 16));
+                            *ex++ = nj[j];
+                        }
+                        *op++ = header_word(kOpNExt, lo);
+                        for (uint32_t k = 0; k < NX; ++k) *op++ = header_extra((int)k, lo, hi);
+                        for (uint32_t k = 0; k < c; ++k) *op++ = __ldg(list + k);
+                    }
+                } else {
+                    *op++ = kOpHeader | ((ovf || nlev >= kOpNExt ? kOpNExt : nlev) << 21) | lev;
+                    if (ovf) *ex++ = (uint16_t)nlev;
+                    if (msk) {
+                        for (uint64_t left = pw[0]; left; left &= left - 1) {
+                            const uint32_t t = (uint32_t)__ffsll((long long)left);
+                            if (mask_levels(pw, t) > lev) *op++ = t;
+                        }
+                    } else {
+                        for (uint32_t k = 0; k < c; ++k) {
+                            uint32_t e;
+                            if (!ovf) e = (uint32_t)(pw[k / 3] >> (kPairBits * (k % 3))) & kPairMask;
+                            else e = __ldg(list + k);
+                            if ((e >> 16) > lev) *op++ = e & 0xffffu;
+                        }
+                    }
+                }
+            }
+            o_cur += tot_o; e_cur += tot_e;
+        }
+        __syncwarp();
+    };
+
+#pragma unroll 1
+    for (uint32_t r = r0 + blockIdx.x * n_warps + w; r < r1; r += warps_total) {
+        const uint64_t s0 = read_koff[r];
+        const uint32_t ni = (uint32_t)(read_koff[r + 1] - s0);
+        const bool single = ni <= cap;
+        // ---- totals (and, when the read fits, its records into shared memory)
+        uint32_t m = 0, my_ops = 0, my_ext = 0;
+        auto scan_records = [&](bool store, bool count, uint64_t lo, uint64_t hi) {
+            m = 0;
+            for (uint32_t x0 = 0; x0 < ni; x0 += 32) {
+                const uint32_t x = x0 + lane;
+                uint64_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                if (x < ni) asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(rec + (s0 + x) * kRecWords));
+                const uint32_t rank = rec_rank(w0);
+                const bool sel = rec_count(w0) != 0 && (uint64_t)rank >= lo && (uint64_t)rank < hi;
+                const uint32_t bal = __ballot_sync(kFull, sel);
+                if (sel) {
+                    Decoded d;
+                    if (EXACT) d = decode_record(w0, w1, w2, w3, peers);
+                    else { d.count = rec_count(w0); d.hmax = rec_hmax(w0); d.overflow = rec_overflow(w0); d.mask = rec_is_mask(w0); d.sumh = 0; }
+                    if (count) {
+                        if (!EXACT) my_ops += 1 + NX + d.count; else my_ops += d.hmax + d.sumh;
+                        my_ext += d.overflow ? d.hmax : 0u;
+                    }
+                    const uint32_t slot = m + __popc(bal & lanemask_lt());
+                    if (store && slot < cap) {
+                        M.pw[slot] = w1; M.pw[cap + slot] = w2; M.pw[2 * (size_t)cap + slot] = w3;
+                        M.meta[slot] = d.count | (d.hmax << 16) | ((d.overflow ? 1u : 0u) << 21) | (rec_owner(w0) << 22) | ((d.mask ? 1u : 0u) << 27);
+                        if (EXACT) M.ioff[slot] = x;
+                        if (!EXACT) M.key[slot] = ((uint64_t)rank << 32) | slot;
+                    }
+                }
+                m += __popc(bal);
+            }
+            __syncwarp();
+        };
+        scan_records(single, true, 0, ~0ull);
+        if (COUNTS && !emit) {
+            // profile only (no per-read scores wanted): the counts are all there is to do
+            if (single) count_segment(m);
+            else {
+                const uint64_t rmax = n_kmers ? n_kmers : 1;
+                uint64_t lo = 0, width = rmax / (uint64_t)(2ull * ni / cap + 1) + 1;
+                while (lo < rmax) {
+                    const uint64_t hi = lo + width < rmax ? lo + width : rmax;
+                    scan_records(true, false, lo, hi);
+                    if (m > cap) { width = (hi - lo) >> 1; if (!width) width = 1; continue; }
+                    count_segment(m);
+                    lo = hi;
+                }
+            }
+            continue;
+        }
+        uint32_t tot_ops = my_ops, tot_ext = my_ext;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { tot_ops += __shfl_xor_sync(kFull, tot_ops, d); tot_ext += __shfl_xor_sync(kFull, tot_ext, d); }
+        uint64_t o_base = 0, e_base = 0;
+        if (lane == 0) {
+            o_base = atomicAdd(ws.cursors + 0, (unsigned long long)((tot_ops + 3u) & ~3u));
+            e_base = atomicAdd(ws.cursors + 1, (unsigned long long)tot_ext);
+        }
+        o_base = __shfl_sync(kFull, o_base, 0);
+        e_base = __shfl_sync(kFull, e_base, 0);
+        bool ok = o_base + ((tot_ops + 3u) & ~3u) <= ws.ops_cap && e_base + tot_ext <= ws.ext_cap;
+        if (!ok && lane == 0) atomicOr(err_flag, 32u);
+        uint32_t n_items = m;
+        if (ok && EXACT) {
+            if (!single) { ok = false; if (lane == 0) atomicOr(err_flag, 64u); }
+            else {
+                // items = (instance, level) pairs with at least one taxon; key = flush position
+                uint32_t base_i = 0;
+                for (uint32_t x0 = 0; x0 < m && ok; x0 += 32) {
+                    const uint32_t x = x0 + lane;
+                    const uint32_t hm = x < m ? (M.meta[x] >> 16) & 31u : 0u;
+                    uint32_t incl = hm;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(kFull, incl, d); if ((int)lane >= d) incl += y; }
+                    const uint32_t tot = __shfl_sync(kFull, incl, 31);
+                    if (base_i + tot > icap) { ok = false; if (lane == 0) atomicOr(err_flag, 64u); break; }
+                    const uint32_t at = base_i + incl - hm;
+                    for (uint32_t j = 0; j < hm; ++j)
+                        M.key[at + j] = ((uint64_t)trig[(s0 + M.ioff[x]) * (uint64_t)lp.num_k + j] << 32) | ((uint64_t)j << 16) | x;
+                    base_i += tot;
+                }
+                n_items = base_i;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) { ws.ops_start[r] = o_base; ws.ops_count[r] = ok ? tot_ops : 0u; ws.ext_start[r] = e_base; }
+        if (!ok) continue;
+        uint64_t o_cur = o_base, e_cur = e_base;
+        if (single) {
+            if (COUNTS) count_segment(m);
+            sort_emit(n_items, 0, EXACT ? 0x100000000ull : (n_kmers ? n_kmers : 1), o_cur, e_cur);
+        } else {
+            // long read: rank ranges small enough for shared memory, in ascending order (records are re-read from L2)
+            const uint64_t rmax = n_kmers ? n_kmers : 1;
+            const uint64_t w0r = rmax / (uint64_t)(2ull * ni / cap + 1);
+            const uint64_t width0 = w0r ? w0r : 1;
+            uint64_t lo = 0, width = width0;
+            while (lo < rmax) {
+                const uint64_t hi = lo + width < rmax ? lo + width : rmax;
+                scan_records(true, false, lo, hi);
+                if (m > cap) { width = (hi - lo) >> 1; if (!width) width = 1; continue; }
+                if (COUNTS) count_segment(m);
+                sort_emit(m, lo, hi - lo, o_cur, e_cur);
+                lo = hi;
+                if (m < cap / 4 && width < rmax) width *= 2;
+            }
+        }
+        // pad the stream to a multiple of four words (B loads 16 bytes at a time)
+        if (lane < ((4u - (tot_ops & 3u)) & 3u)) ws.ops[o_base + tot_ops + lane] = 0;
+    }
+    if (COUNTS) {
+        __syncwarp();
+        const int ta = (int)lane + 1, tb = (int)lane + 33;
+        if (ta < T) {
+            if (fx0a) atomicAdd(cnt_fx + ta, fx0a);
+            if (un0a) atomicAdd(cnt_unique + ta, un0a);
+            for (int j = 1; j < NK; ++j) { const uint32_t u = M.un[j * 64 + ta - 1]; if (u) atomicAdd(cnt_unique + (size_t)j * T + ta, (unsigned long long)u); }
+        }
+        if (tb < T) {
+            if (fx0b) atomicAdd(cnt_fx + tb, fx0b);
+            if (un0b) atomicAdd(cnt_unique + tb, un0b);
+            for (int j = 1; j < NK; ++j) { const uint32_t u = M.un[j * 64 + tb - 1]; if (u) atomicAdd(cnt_unique + (size_t)j * T + tb, (unsigned long long)u); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// B: replay the op streams.  Thread per read; every thread owns a column of float32 cells (one per taxon) in shared memory,
+// so additions need neither atomics nor any cross-lane step, and a warp streams 32 reads' words with 16-byte loads.
+// (The counts of these small taxonomies are taken by kernel A.)
+constexpr int kInvTab = 128;
+constexpr int kDenseBlock = 128;
+
+template <int SLOTS>
+__global__ void __launch_bounds__(kDenseBlock) accumulate_dense_kernel(OpsWorkspace ws, uint32_t r0, uint32_t r1, LevelParams lp, bool exact_stream,
+                                                                       float *__restrict__ scores)
+{
+    constexpr int NC = 32 * SLOTS, BT = kDenseBlock;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, T = lp.n_taxa, NK = lp.num_k;
+    float *cellS = reinterpret_cast<float *>(smem_raw);                 // [NC][BT]
+    float *vbuf = cellS + (size_t)NC * BT;                              // [NK][BT] value of each level of the current group when an upper level is shared
+    float *s_w = vbuf + (size_t)NK * BT;                                // [32]
+    float *s_inv = s_w + 32;                                            // [kInvTab]
+    for (int i = tid; i < NC * BT; i += BT) cellS[i] = 0.f;
+    if (tid < 32) { const int k = lp.k_low + tid; s_w[tid] = (float)(k * k) / 625.f; }      // Compare.hpp:392
+    for (int i = tid; i < kInvTab; i += BT) s_inv[i] = i ? __fdiv_rn(1.f, (float)i) : 0.f;   // Compare.hpp:924: 1.f / numOfEntries
+    __syncthreads();
+    const uint32_t NX = exact_stream ? 0u : (uint32_t)ops_extra_words(NK);
+    auto inv_of = [&](uint32_t n) { return n < (uint32_t)kInvTab ? s_inv[n] : __fdiv_rn(1.f, (float)n); };
+
+    const uint32_t stride = gridDim.x * BT;
+#pragma unroll 1
+    for (uint32_t base = r0 + blockIdx.x * BT; base < r1; base += stride) {
+        const uint32_t r = base + tid;
+        const bool have = r < r1;
+        uint64_t cur = have ? ws.ops_start[r] : 0;
+        uint32_t left = have ? ws.ops_count[r] : 0;
+        uint64_t ecur = have ? ws.ext_start[r] : 0;
+        uint32_t it = 0;
+        uint4 buf = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+        if (left > 0) nxt = __ldg(reinterpret_cast<const uint4 *>(ws.ops + cur));
+        uint32_t pairs_left = 0, hdr_left = 0;                          // state of the current group
+        float v0 = 0.f;
+        bool uniq = true;
+        while (__any_sync(kFull, left > 0)) {
+            if ((it & 3u) == 0u) {
+                buf = nxt;                                               // software pipeline: the next 16 bytes are already on their way
+                if (left > 4) nxt = __ldg(reinterpret_cast<const uint4 *>(ws.ops + cur + 4));
+            }
+            const uint32_t sel = it & 3u;
+            const uint32_t word = sel == 0 ? buf.x : (sel == 1 ? buf.y : (sel == 2 ? buf.z : buf.w));
+            if (left > 0) {
+                if (pairs_left == 0 && hdr_left == 0) {
+                    // ---- header: sizes of the group's levels
+                    uint32_t n0 = (word >> 21) & 1023u;
+                    if (n0 == kOpNExt) n0 = ws.ext[ecur++];
+                    pairs_left = n0;
+                    if (exact_stream) {
+                        v0 = __fmul_rn(s_w[word & 31u], inv_of(n0));                          // Compare.hpp:924
+                    } else {
+                        hdr_left = NX;
+                        v0 = __fmul_rn(s_w[0], inv_of(n0));
+                        uniq = NX == 0 && ((word >> 1) & 0xEEEEEu) == 0u;
+                        if (!uniq) {
+                            for (int j = 1; j <= 5 && j < NK; ++j) {
+                                uint32_t nn = (word >> (1 + 4 * (j - 1))) & 15u;
+                                if (nn == kOpNibExt) nn = ws.ext[ecur++];
+                                vbuf[j * BT + tid] = nn ? __fmul_rn(s_w[j], inv_of(nn)) : 0.f;
+                            }
+                        }
+                    }
+                } else if (hdr_left > 0) {
+                    // ---- extra header word: levels 6 + 8 k .. (escapes of the levels are in level order, so they can be resolved here)
+                    const uint32_t k = NX - hdr_left;
+                    for (int i = 0; i < 8; ++i) {
+                        const int j = 6 + 8 * (int)k + i;
+                        if (j < NK) {
+                            uint32_t nn = (word >> (4 * i)) & 15u;
+                            if (nn == kOpNibExt) nn = ws.ext[ecur++];
+                            vbuf[j * BT + tid] = nn ? __fmul_rn(s_w[j], inv_of(nn)) : 0.f;
+                        }
+                    }
+                    --hdr_left;
+                } else {
+                    // ---- pair: taxon (| levels)
+                    const uint32_t cell = (word & 0xffffu) - 1u;
+                    float acc = __fadd_rn(cellS[cell * BT + tid], v0);                             // Compare.hpp:530
+                    if (!exact_stream) {
+                        const uint32_t h = (word >> 16) & 31u;
+                        if (uniq) { for (uint32_t j = 1; j < h; ++j) acc = __fadd_rn(acc, s_w[j]); }        // w * (1.f / 1) == w
+                        else { for (uint32_t j = 1; j < h; ++j) acc = __fadd_rn(acc, vbuf[j * BT + tid]); }
+                    }
+                    cellS[cell * BT + tid] = acc;
+                    --pairs_left;
+                }
+                ++cur; --left;
+            }
+            ++it;
+        }
+        // ---- end of the read: scores out
+        if (have) {
+            for (int c = 0; c < NC && c < T - 1; ++c) {
+                if (scores) scores[(uint64_t)r * T + c + 1] = cellS[c * BT + tid];
+                cellS[c * BT + tid] = 0.f;
+            }
+            if (scores) scores[(uint64_t)r * T] = 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// B for any number of taxa: warp per read, group after group; the taxa of a group are distinct, so its pairs are
+// applied in parallel (a lane per pair) to the cells of the read's taxa, which live in a shared-memory hash table.
+constexpr int kHBlock = 128;
+constexpr int kHWarps = kHBlock / 32;
+constexpr uint32_t kHashSlots = 1024;
+constexpr uint32_t kHashEmpty = 0xffffffffu;
+
+__global__ void __launch_bounds__(kHBlock) accumulate_hash_kernel(OpsWorkspace ws, uint32_t r0, uint32_t r1, LevelParams lp, bool exact_stream,
+                                                                  float *__restrict__ scores, HitsOut hits, unsigned long long *__restrict__ cnt_fx,
+                                                                  unsigned long long *__restrict__ cnt_unique, uint32_t *__restrict__ err_flag)
+{
+    __shared__ uint32_t s_key[kHWarps][kHashSlots];
+    __shared__ float s_acc[kHWarps][kHashSlots];
+    __shared__ uint16_t s_used[kHWarps][kHashSlots];
+    __shared__ uint32_t s_nused[kHWarps];
+    __shared__ float s_w[32];
+    __shared__ float s_v[kHWarps][32];          // value of each level of the current group
+    __shared__ uint32_t s_n[kHWarps][32];       // ... and its size
+    const int w = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const int T = lp.n_taxa, NK = lp.num_k;
+    for (uint32_t i = threadIdx.x; i < kHWarps * kHashSlots; i += kHBlock) { (&s_key[0][0])[i] = kHashEmpty; (&s_acc[0][0])[i] = 0.f; }
+    if (threadIdx.x < 32) { const int k = lp.k_low + threadIdx.x; s_w[threadIdx.x] = (float)(k * k) / 625.f; }
+    if (lane == 0) s_nused[w] = 0;
+    __syncthreads();
+    uint32_t *key = s_key[w];
+    float *accs = s_acc[w];
+    const uint32_t NX = exact_stream ? 0u : (uint32_t)ops_extra_words(NK);
+    const uint32_t warps_total = gridDim.x * kHWarps;
+#pragma unroll 1
+    for (uint32_t r = r0 + blockIdx.x * kHWarps + w; r < r1; r += warps_total) {
+        const uint64_t o0 = ws.ops_start[r];
+        const uint32_t n_ops = ws.ops_count[r];
+        uint64_t ecur = ws.ext_start[r];
+        if (scores) for (int t = lane; t < T; t += 32) scores[(uint64_t)r * T + t] = 0.f;
+        bool full = false;
+        // a read with more ops than the table safely holds taxa is replayed once per taxon range of <= kHashSlots / 2 taxa
+        const uint32_t width = (n_ops <= kHashSlots * 5 / 8 || (uint32_t)T <= kHashSlots * 5 / 8) ? (uint32_t)T : kHashSlots / 2;
+        const uint32_t n_pass = ((uint32_t)T + width - 1) / width;
+        uint64_t hb = 0;
+        uint32_t n_hits_read = 0;
+        // header of the group at `at`: group size, escapes consumed from the ext stream; fills the warp's level tables when `fill`
+        auto read_header = [&](uint32_t at, uint64_t &ec, uint32_t &lev, bool fill) {
+            const uint32_t hw = __ldg(ws.ops + o0 + at);
+            uint32_t n0 = (hw >> 21) & 1023u;
+            if (n0 == kOpNExt) n0 = ws.ext[ec++];
+            if (exact_stream) {
+                lev = hw & 31u;
+                if (fill && lane == 0) { s_n[w][lev] = n0; s_v[w][lev] = __fmul_rn(s_w[lev], __fdiv_rn(1.f, (float)n0)); }
+            } else {
+                // lane j decodes level j; escaped sizes come from the ext stream in level order
+                uint32_t nn = 0;
+                const int j = (int)lane;
+                if (j == 0) nn = n0;
+                else if (j < NK) {
+                    if (j <= 5) nn = (hw >> (1 + 4 * (j - 1))) & 15u;
+                    else nn = (__ldg(ws.ops + o0 + at + 1 + (j - 6) / 8) >> (4 * ((j - 6) % 8))) & 15u;
+                }
+                const bool escaped = j > 0 && j < NK && nn == kOpNibExt;
+                const uint32_t esc = __ballot_sync(kFull, escaped);
+                if (escaped) nn = ws.ext[ec + __popc(esc & lanemask_lt())];
+                ec += __popc(esc);
+                if (fill && j < NK) { s_n[w][j] = nn; s_v[w][j] = nn ? __fmul_rn(s_w[j], __fdiv_rn(1.f, (float)nn)) : 0.f; }
+            }
+            __syncwarp();
+            return n0;
+        };
+        if (hits.taxon && n_pass > 1) {
+            // the hits of a read are contiguous in the output: count its distinct taxa first, range by range, with the table alone
+            for (uint32_t pass = 0; pass < n_pass; ++pass) {
+                const uint32_t t_lo = pass * width, t_hi = t_lo + width;
+                uint64_t ec = ws.ext_start[r];
+                uint32_t at = 0, lev = 0;
+                while (at < n_ops) {
+                    const uint32_t n0 = read_header(at, ec, lev, false);
+                    at += 1 + NX;
+                    for (uint32_t p0 = 0; p0 < n0; p0 += 32) {
+                        const bool active = p0 + lane < n0;
+                        const uint32_t t = active ? __ldg(ws.ops + o0 + at + p0 + lane) & 0xffffu : 0u;
+                        if (active && t >= t_lo && t < t_hi) {
+                            uint32_t slot = (t * 2654435761u) >> 22;
+                            for (;;) {
+                                const uint32_t k = key[slot];
+                                if (k == t) break;
+                                if (k == kHashEmpty) {
+                                    const uint32_t old = atomicCAS(&key[slot], kHashEmpty, t);
+                                    if (old == kHashEmpty) { s_used[w][atomicAdd(&s_nused[w], 1u)] = (uint16_t)slot; break; }
+                                    if (old == t) break;
+                                }
+                                slot = (slot + 1) & (kHashSlots - 1);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    at += n0;
+                }
+                __syncwarp();
+                const uint32_t nu = s_nused[w];
+                n_hits_read += nu;
+                for (uint32_t i = lane; i < nu; i += 32) key[s_used[w][i]] = kHashEmpty;
+                __syncwarp();
+                if (lane == 0) s_nused[w] = 0;
+                __syncwarp();
+            }
+        }
+        uint32_t hits_done = 0;
+        bool hits_ok = false;
+        for (uint32_t pass = 0; pass < n_pass; ++pass) {
+        const uint32_t t_lo = pass * width, t_hi = t_lo + width;
+        ecur = ws.ext_start[r];
+        uint32_t at = 0;
+        while (at < n_ops) {
+            // ---- header (the same words for every lane)
+            uint32_t lev = 0;
+            const uint32_t n0 = read_header(at, ecur, lev, true);
+            at += 1 + NX;
+            // ---- pairs: a lane each
+            for (uint32_t p0 = 0; p0 < n0; p0 += 32) {
+                const bool active = p0 + lane < n0;
+                const uint32_t word = active ? __ldg(ws.ops + o0 + at + p0 + lane) : 0u;
+                const uint32_t t = word & 0xffffu, h = (word >> 16) & 31u;
+                if (active && t >= t_lo && t < t_hi) {
+                    uint32_t slot = (t * 2654435761u) >> 22;
+                    for (uint32_t probes = 0;; ++probes) {
+                        const uint32_t k = key[slot];
+                        if (k == t) break;
+                        if (k == kHashEmpty) {
+                            const uint32_t old = atomicCAS(&key[slot], kHashEmpty, t);
+                            if (old == kHashEmpty) { s_used[w][atomicAdd(&s_nused[w], 1u)] = (uint16_t)slot; break; }
+                            if (old == t) break;
+                        }
+                        slot = (slot + 1) & (kHashSlots - 1);
+                        if (probes > kHashSlots) { full = true; break; }
+                    }
+                    float acc = accs[slot];
+                    const uint32_t j0 = exact_stream ? lev : 0u, j1 = exact_stream ? lev + 1u : h;
+                    for (uint32_t j = j0; j < j1; ++j) {
+                        acc = __fadd_rn(acc, s_v[w][j]);                                   // Compare.hpp:924, 530
+                        const uint32_t nn = s_n[w][j];
+                        if (nn == 1u) atomicAdd(cnt_unique + (size_t)j * T + t, 1ull);
+                        else atomicAdd(cnt_fx + (size_t)j * T + t, (unsigned long long)inv_fx(nn));
+                    }
+                    accs[slot] = acc;
+                }
+                __syncwarp();
+                if (s_nused[w] > kHashSlots * 3 / 4) full = true;
+            }
+            at += n0;
+            __syncwarp();
+        }
+        // ---- results of this taxon range, then clear its cells
+        const uint32_t nu = s_nused[w];
+        if (hits.taxon && pass == 0) {
+            const uint32_t total = n_pass > 1 ? n_hits_read : nu;
+            if (lane == 0) {
+                hb = atomicAdd(hits.cursor, (unsigned long long)total);
+                if (hb + total > hits.cap) { atomicOr(err_flag, 128u); hits.begin[r] = 0; hits.count[r] = 0; }
+                else { hits.begin[r] = hb; hits.count[r] = total; }
+            }
+            hb = __shfl_sync(kFull, hb, 0);
+            hits_ok = hb + total <= hits.cap;
+        }
+        for (uint32_t i = lane; i < nu; i += 32) {
+            const uint32_t slot = s_used[w][i], t = key[slot];
+            const float v = accs[slot];
+            if (scores) scores[(uint64_t)r * T + t] = v;
+            if (hits.taxon && hits_ok) { hits.taxon[hb + hits_done + i] = t; hits.score[hb + hits_done + i] = v; }
+            key[slot] = kHashEmpty;
+            accs[slot] = 0.f;
+        }
+        hits_done += nu;
+        __syncwarp();
+        if (lane == 0) s_nused[w] = 0;
+        __syncwarp();
+        }   // taxon ranges
+        if (__any_sync(kFull, full) && lane == 0) atomicOr(err_flag, 256u);
+    }
+}
+
+__global__ void max_instances_kernel(const uint64_t *__restrict__ read_koff, uint32_t n_reads, uint32_t *out)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_reads) atomicMax(out, (uint32_t)(read_koff[r + 1] - read_koff[r]));
+}
+
+template <int SLOTS>
+void launch_dense(cudaStream_t s, OpsWorkspace ws, uint32_t r0, uint32_t r1, LevelParams lp, bool exact_stream, float *scores)
+{
+    constexpr int NC = 32 * SLOTS;
+    const size_t sm = (size_t)NC * kDenseBlock * 4 + (size_t)lp.num_k * kDenseBlock * 4 + 32 * 4 + kInvTab * 4;
+    auto kern = accumulate_dense_kernel<SLOTS>;
+    KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int per_sm = 1;
+    KASA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDenseBlock, sm));
+    unsigned grid = (unsigned)div_up<uint64_t>(r1 - r0, kDenseBlock);
+    const unsigned resident = (unsigned)(kSMs * (per_sm > 0 ? per_sm : 1));
+    if (grid > resident) grid = resident;
+    kern<<<grid, kDenseBlock, sm, s>>>(ws, r0, r1, lp, exact_stream, scores);
+}
+
+}  // namespace
+
+void launch_order_ops(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t r0, uint32_t r1, uint64_t n_kmers, uint32_t max_inst,
+                      LevelParams lp, OverflowPeers peers, OpsWorkspace ws, const uint32_t *trig, bool counts, bool emit, unsigned long long *cnt_fx,
+                      unsigned long long *cnt_unique, uint32_t *err_flag, uint64_t *launches)
+{
+    if (r1 <= r0) return;
+    const bool exact = trig != nullptr;
+    KASA_REQUIRE(!counts || lp.n_taxa <= kMaskTaxa, -6, "counts in the ordering kernel need <= 64 taxa");
+    // instances per shared-memory segment: the whole read when it is short, else a slice of the rank range (ORDERED only);
+    // four warps (reads) per CTA, fewer when a read needs more shared memory
+    uint32_t cap = max_inst < 32 ? 32 : (max_inst + 31) & ~31u;
+    uint32_t icap = 0, nb = 0, warps = kAMaxWarps;
+    size_t wbytes = 0, sm = 0;
+    const size_t budget = 224 * 1024;
+    for (;;) {
+        icap = exact ? cap * (uint32_t)lp.num_k : cap;
+        nb = 64;
+        while (nb < icap && nb < 4096) nb <<= 1;
+        wbytes = warp_mem_bytes(cap, icap, nb, exact, counts ? lp.num_k : 0);
+        sm = wbytes * warps;
+        if (sm <= budget) break;
+        if (!exact && cap > 512) { cap = (cap / 2 + 31) & ~31u; continue; }
+        if (warps > 1) { warps >>= 1; continue; }
+        if (!exact && cap > 64) { cap = (cap / 2 + 31) & ~31u; continue; }
+        break;
+    }
+    if (sm > budget || icap > 65535)      // KASA_SCORE_EXACT keeps a whole read in shared memory
+        throw Error{-1, "KASA_SCORE_EXACT: a read has too many (k-mer, level) pairs for the shared-memory replay; use KASA_SCORE_ORDERED for long reads"};
+    auto go = [&](auto kern) {
+        KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        int per_sm = 1;
+        KASA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)warps * 32, sm));
+        unsigned grid = (unsigned)div_up<uint64_t>(r1 - r0, warps);
+        const unsigned resident = (unsigned)(kSMs * (per_sm > 0 ? per_sm : 1));
+        if (grid > resident) grid = resident;
+        kern<<<grid, warps * 32, sm, s>>>(rec, read_koff, r0, r1, n_kmers, lp, peers, ws, trig, err_flag, cap, icap, nb, (uint32_t)wbytes, cnt_fx, cnt_unique, emit || !counts);
+    };
+    if (exact) { if (counts) go(order_ops_kernel<true, true>); else go(order_ops_kernel<true, false>); }
+    else { if (counts) go(order_ops_kernel<false, true>); else go(order_ops_kernel<false, false>); }
+    ++*launches;
+    KASA_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_accumulate(cudaStream_t s, OpsWorkspace ws, uint32_t r0, uint32_t r1, LevelParams lp, bool exact_stream, float *scores, HitsOut hits,
+                       unsigned long long *cnt_fx, unsigned long long *cnt_unique, uint32_t *err_flag, uint64_t *launches)
+{
+    if (r1 <= r0) return;
+    if (lp.n_taxa <= kMaskTaxa && !hits.taxon) {
+        // the counts of these reads were taken by launch_order_ops(counts = true)
+        if (lp.n_taxa <= 33) launch_dense<1>(s, ws, r0, r1, lp, exact_stream, scores); else launch_dense<2>(s, ws, r0, r1, lp, exact_stream, scores);
+    } else {
+        unsigned grid = (unsigned)div_up<uint64_t>(r1 - r0, kHWarps);
+        if (grid > (unsigned)kSMs * 8) grid = kSMs * 8;
+        accumulate_hash_kernel<<<grid, kHBlock, 0, s>>>(ws, r0, r1, lp, exact_stream, scores, hits, cnt_fx, cnt_unique, err_flag);
+    }
+    ++*launches;
+    KASA_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_max_instances(cudaStream_t s, const uint64_t *read_koff, uint32_t n_reads, uint32_t *out, uint64_t *launches)
+{
+    KASA_CUDA_TRY(cudaMemsetAsync(out, 0, 4, s));
+    if (!n_reads) return;
+    max_instances_kernel<<<div_up(n_reads, 256u), 256, 0, s>>>(read_koff, n_reads, out);
+    ++*launches;
+}
+
+}  // namespace kasa

@@ -403,6 +403,80 @@ int ko_identify(const uint64_t *kmers, const uint32_t *read_id, uint64_t nq,
     return 0;
 }
 
+/* ------------------------------------------------------------------------- */
+/* KASA_SCORE_ORDERED of the CUDA library, restated on the CPU so that the GPU path can be checked bit for bit:
+ * the same set semantics, but score[read][taxon] is summed in float32 in the order
+ * (position of the instance in the stable sort of the queries on their leading `sort_bits` key bits, k ascending).
+ * For instances that the reference flushes level by level in k-mer order this is the reference's own order
+ * (Compare.hpp:917-955, 1032-1041); the value added is the reference's float(w(k) * (1.f / n)) (Compare.hpp:924).
+ * count_all is accumulated in double per instance (the GPU uses 2^-32 fixed point; compare at 1e-6).            */
+typedef struct { kmer_t top; uint32_t seq; } oq_t;
+static int cmp_oq(const void *a, const void *b)
+{
+    const oq_t *x = a, *y = b;
+    if (x->top != y->top) return x->top < y->top ? -1 : 1;
+    return x->seq < y->seq ? -1 : (x->seq > y->seq);
+}
+
+int ko_identify_ordered(const uint64_t *kmers, const uint32_t *read_id, uint64_t nq,
+                        const uint8_t *index, uint64_t nidx, int bits, int K, int kHigh, int kLow, int sort_bits,
+                        const uint32_t *taxid_of_idx, uint32_t T,
+                        double *count_all, uint64_t *count_unique, float *scores)
+{
+    int numK = kHigh - kLow + 1;
+    float w[32];
+    for (int j = 0; j < numK; ++j) { int k = kLow + j; w[j] = (float)(k * k) / 625.f; }      /* level j = 0 <-> kLow */
+    entry_t *idx = malloc((nidx ? nidx : 1) * sizeof(entry_t));
+    uint32_t *dense = malloc((nidx ? nidx : 1) * sizeof(uint32_t));
+    taxmap_t m = taxmap_make(taxid_of_idx, T);
+    for (uint64_t i = 0; i < nidx; ++i) {
+        idx[i] = load_entry(index + i * rec_size(bits), bits);
+        int64_t d = taxmap_find(&m, idx[i].tax);
+        if (d < 0) { free(idx); free(dense); free(m.map); return -1; }
+        dense[i] = (uint32_t)d;
+    }
+    int drop = 5 * K - sort_bits; if (drop < 0) drop = 0;
+    oq_t *q = malloc((nq ? nq : 1) * sizeof(oq_t));
+    for (uint64_t i = 0; i < nq; ++i) { kmer_t k = ((kmer_t)kmers[2 * i + 1] << 64) | kmers[2 * i]; q[i].top = k >> drop; q[i].seq = (uint32_t)i; }
+    qsort(q, nq, sizeof(oq_t), cmp_oq);
+    uint32_t *h = calloc(T ? T : 1, sizeof(uint32_t)), *touched = malloc(4 * (size_t)(T ? T : 1)), nj[32];
+    int shLow = 5 * (K - kLow);
+    for (uint64_t s = 0; s < nq; ++s) {
+        uint64_t i = q[s].seq;
+        kmer_t key = ((kmer_t)kmers[2 * i + 1] << 64) | kmers[2 * i];
+        /* last level not killed by '^' (Compare.hpp:836, 897) */
+        int kv = kLow - 1;
+        for (int k = kLow; k <= kHigh; ++k) { if (((uint32_t)(key >> (5 * (K - k))) & 31u) == 30u) break; kv = k; }
+        if (kv < kLow) continue;
+        uint64_t a = lower_pre(idx, 0, nidx, key >> shLow, shLow);
+        uint32_t nt = 0;
+        for (uint64_t e = a; e < nidx && (idx[e].k >> shLow) == (key >> shLow); ++e) {
+            kmer_t x = idx[e].k ^ key;
+            int c = K;                                  /* common leading letters */
+            for (int k = 1; k <= K; ++k) if ((x >> (5 * (K - k))) != 0) { c = k - 1; break; }
+            if (c > kv) c = kv;
+            uint32_t lev = (uint32_t)(c - kLow + 1), t = dense[e];
+            if (!h[t]) touched[nt++] = t;
+            if (lev > h[t]) h[t] = lev;
+        }
+        if (!nt) continue;
+        for (int j = 0; j < numK; ++j) nj[j] = 0;
+        for (uint32_t x = 0; x < nt; ++x) for (uint32_t j = 0; j < h[touched[x]]; ++j) ++nj[j];
+        for (uint32_t x = 0; x < nt; ++x) {
+            uint32_t t = touched[x];
+            for (uint32_t j = 0; j < h[t]; ++j) {
+                size_t ci = (size_t)(numK - 1 - j) * T + t;                  /* ik = 0 <-> kHigh */
+                count_all[ci] += 1.0 / nj[j];
+                if (nj[j] == 1) count_unique[ci] += 1;
+                if (scores) scores[(size_t)read_id[i] * T + t] += w[j] * (1.f / nj[j]);
+            }
+            h[t] = 0;
+        }
+    }
+    free(h); free(touched); free(q); free(idx); free(dense); free(m.map);
+    return 0;
+}
+
 /* Compare.hpp:1452-1481 calculateBestScore (DNA): float accumulation, k ascending. */
 float ko_best_score(uint32_t read_len, int kHigh, int kLow, int frames)
 {

@@ -54,6 +54,9 @@ def lib():
         L.ko_identify.restype = C.c_int
         L.ko_identify.argtypes = [u64p, u32p, C.c_uint64, u8p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
                                   u32p, C.c_uint32, f64p, u64p, f32p, u64p]
+        L.ko_identify_ordered.restype = C.c_int
+        L.ko_identify_ordered.argtypes = [u64p, u32p, C.c_uint64, u8p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          u32p, C.c_uint32, f64p, u64p, f32p]
         L.ko_best_score.restype = C.c_float
         L.ko_best_score.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_int]
         L.ko_relative_score.restype = C.c_double
@@ -319,6 +322,32 @@ def identify_kmers(kmers: np.ndarray, read_id: np.ndarray, n_reads: int, index: 
     if rc:
         raise KeyError("index taxid missing from content")
     return IdentifyResult(len(read_id), ca, cu, sc)
+
+
+def identify_kmers_ordered(kmers: np.ndarray, read_id: np.ndarray, n_reads: int, index: np.ndarray, K: int, k_high: int,
+                           k_low: int, taxid_of_idx: np.ndarray, sort_bits: int = 32) -> IdentifyResult:
+    """The CUDA library's KASA_SCORE_ORDERED summation order on the CPU (ko_identify_ordered): the bit-exact check of the GPU path."""
+    bits = 128 if index.dtype.itemsize == 20 else 64
+    T = len(taxid_of_idx)
+    numK = k_high - k_low + 1
+    ca = np.zeros((numK, T), dtype=np.float64)
+    cu = np.zeros((numK, T), dtype=np.uint64)
+    sc = np.zeros((n_reads, T), dtype=np.float32)
+    kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+    read_id = np.ascontiguousarray(read_id, dtype=np.uint32)
+    tax = np.ascontiguousarray(taxid_of_idx, dtype=np.uint32)
+    index = np.ascontiguousarray(index)
+    rc = lib().ko_identify_ordered(_p(kmers, u64p), _p(read_id, u32p), len(read_id), index.ctypes.data_as(u8p), len(index),
+                                   bits, K, k_high, k_low, sort_bits, _p(tax, u32p), T, _p(ca, f64p), _p(cu, u64p), _p(sc, f32p))
+    if rc:
+        raise KeyError("index taxid missing from content")
+    return IdentifyResult(len(read_id), ca, cu, sc)
+
+
+def identify_reads_ordered(reads: list[list[bytes]], index: np.ndarray, K: int, k_high: int, k_low: int, six: bool,
+                           taxid_of_idx: np.ndarray, table: np.ndarray | None = None, sort_bits: int = 32) -> IdentifyResult:
+    k, ids = read_kmers(reads, K, k_low, six, table)
+    return identify_kmers_ordered(k, ids, len(reads), index, K, k_high, k_low, taxid_of_idx, sort_bits)
 
 
 def read_kmers(reads: list[list[bytes]], K: int, k_low: int, six: bool, table: np.ndarray | None = None):

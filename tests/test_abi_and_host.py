@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libkasa_b200.so does not export %s" % n
     assert set(capi.EXPORTS) <= set(names)
-    assert lib.kasa_abi_version() == 1
+    assert lib.kasa_abi_version() == 2
 
 
 def test_header_is_plain_c_and_ctypes_structs_match_it(tmp_path):
@@ -38,6 +38,8 @@ def test_header_is_plain_c_and_ctypes_structs_match_it(tmp_path):
 #include <stddef.h>
 #include "kasa_b200.h"
 int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\\n", offsetof(kasa_params, max_batch_hits), offsetof(kasa_batch_result, hit_taxon), offsetof(kasa_batch_result, hit_count),
+         offsetof(kasa_batch_result, hit_capacity), offsetof(kasa_batch_result, n_hits), offsetof(kasa_batch_result, hits_location), sizeof(kasa_batch_result));
   printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(kasa_params), sizeof(kasa_read_batch), sizeof(kasa_batch_result),
          sizeof(kasa_seq_batch), offsetof(kasa_params, max_batch_kmers), offsetof(kasa_params, codon_table),
          offsetof(kasa_read_batch, read_first_seq), offsetof(kasa_batch_result, gpu_ms),
@@ -46,7 +48,10 @@ int main(void) {
     exe = tmp_path / "sz"
     subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    want = [ctypes.sizeof(capi.CParams), ctypes.sizeof(capi.CReadBatch), ctypes.sizeof(capi.CBatchResult),
+    want = [capi.CParams.max_batch_hits.offset, capi.CBatchResult.hit_taxon.offset, capi.CBatchResult.hit_count.offset,
+            capi.CBatchResult.hit_capacity.offset, capi.CBatchResult.n_hits.offset, capi.CBatchResult.hits_location.offset,
+            ctypes.sizeof(capi.CBatchResult),
+            ctypes.sizeof(capi.CParams), ctypes.sizeof(capi.CReadBatch), ctypes.sizeof(capi.CBatchResult),
             ctypes.sizeof(capi.CSeqBatch), capi.CParams.max_batch_kmers.offset, capi.CParams.codon_table.offset,
             capi.CReadBatch.read_first_seq.offset, capi.CBatchResult.gpu_ms.offset,
             ctypes.sizeof(capi.CShardMem), capi.CShardMem.handle.offset, ctypes.sizeof(capi.CShardRuns), capi.CShardRuns.begin.offset]

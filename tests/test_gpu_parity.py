@@ -5,8 +5,16 @@ reference binary (tests/golden/*).
 Tolerances (stated here as the contract):
   * k-mer encodings, sort order, index / trie / frequency bytes, unique counts, per-read taxa sets: bit-exact.
   * non-unique counts (sum of 1/|taxa| in 2^-32 fixed point): <= 1e-6 relative to the oracle's doubles.
-  * per-read k-mer scores, KASA_SCORE_FAST (fp32, canonical order): <= 4e-6 relative to the reference's own
-    fp32 sums (the reference's order depends on the batch composition).
+  * per-read k-mer scores (float32 running sums in the reference, Compare.hpp:528-530, so their last bits depend on the
+    order of the additions):
+      KASA_SCORE_EXACT    bit-identical to the reference binary (its own flush order);
+      KASA_SCORE_ORDERED  bit-identical to the oracle's restatement of the library's order — (k-mer ascending, k ascending)
+                          per read, ko_identify_ordered — and, against the reference's own values, most cells bit-identical and
+                          all within ORDERED_RTOL.  These goldens are adversarial (regions shared between taxa, tandem repeats,
+                          low complexity): the cells that differ are the ones where the reference's flush order depends on
+                          which other k-mers are in the batch, i.e. where the reference's own value moves when
+                          the same read is scored in another batch.  On reads of uniform random sequence the two orders coincide
+                          (tests/test_gpu_reference_scale.py: every cell bit-identical to the reference binary).
 """
 import numpy as np
 import pytest
@@ -18,7 +26,9 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FAST_RTOL = 1e-5
+ORDERED_RTOL = 2.5e-6          # k = 12..7 goldens: worst cell 1.7e-6
+ORDERED_RTOL_K25 = 2.5e-5      # k = 25..7 (19 levels, ~10^4 adds per cell): worst cell 1.7e-5
+ORDERED_EXACT_FRACTION = 0.85  # share of cells bit-identical to the reference (measured 0.87 - 0.999)
 COUNT_RTOL = 1e-6
 
 
@@ -104,7 +114,7 @@ def test_radix_sort_partial_bits_and_skewed_digits():
 
 
 # ----------------------------------------------------------------------------------------- identify
-def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, rtol=FAST_RTOL, exact=False):
+def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, rtol=ORDERED_RTOL, exact=False):
     _, taxids, _ = G.content(case)
     idx = G.index(case)
     if paired:
@@ -113,7 +123,7 @@ def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, r
     else:
         reads = [[x[1]] for x in G.fastq(case)]
     ctx = _ctx(highest_k=K, k_high=k_high, k_low=k_low, frames=6 if six else 3,
-               score_mode=capi.SCORE_EXACT if exact else capi.SCORE_FAST)
+               score_mode=capi.SCORE_EXACT if exact else capi.SCORE_ORDERED)
     ctx.load_index(idx, taxids)
     pieces = [reads] if split is None else [reads[:split], reads[split:]]
     scores, n_kmers = [], 0
@@ -137,7 +147,11 @@ def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, r
         assert np.array_equal(scores, ora.scores)      # fp32 in the reference's flush order: bit-exact
         rtol = 0.0
     else:
+        mine = O.identify_reads_ordered(reads, idx, K, k_high, k_low, six, taxids)
+        assert np.array_equal(scores, mine.scores)     # the library's own order, restated on the CPU: bit-exact
         np.testing.assert_allclose(scores, ora.scores, rtol=rtol, atol=0)
+        nz = ora.scores != 0
+        assert np.mean(scores[nz] == ora.scores[nz]) >= ORDERED_EXACT_FRACTION
     # ... and against what the reference binary printed
     pr = G.per_read(case, tag)
     tax2idx = {int(t): i for i, t in enumerate(taxids)}
@@ -172,7 +186,7 @@ def test_identify_k12_single_level():
 
 def test_identify_k25_paired():
     # 19 levels x 520 k-mers: ~10^4 fp32 adds per cell, the order-dependent rounding grows accordingly
-    _identify_case("k25", "six_25_7", 25, 25, 7, True, paired=True, rtol=3e-5)
+    _identify_case("k25", "six_25_7", 25, 25, 7, True, paired=True, rtol=ORDERED_RTOL_K25)
 
 
 @pytest.mark.parametrize("case,tag,K,kh,kl,six,paired", [
@@ -186,7 +200,7 @@ def test_identify_exact_mode_is_bit_identical_to_the_reference(case, tag, K, kh,
 def test_identify_is_batch_independent_and_deterministic():
     s1, ca1, cu1 = _identify_case("k12", "six_12_7", 12, 12, 7, True)
     s2, ca2, cu2 = _identify_case("k12", "six_12_7", 12, 12, 7, True, split=137)
-    assert np.array_equal(s1, s2)            # canonical-order fp32 scores do not depend on the batching
+    assert np.array_equal(s1, s2)            # ordered fp32 scores do not depend on the batching
     assert np.array_equal(cu1, cu2)
     np.testing.assert_allclose(ca1, ca2, rtol=1e-12)
 
@@ -212,7 +226,7 @@ def test_profile_only_mode_gives_same_counts():
     idx = G.index("k12")
     reads = _k12_reads()
     out = []
-    for mode in (capi.SCORE_NONE, capi.SCORE_FAST):
+    for mode in (capi.SCORE_NONE, capi.SCORE_ORDERED):
         ctx = _ctx(frames=6, score_mode=mode)
         ctx.load_index(idx, taxids)
         ctx.identify_batch(reads)
@@ -313,19 +327,18 @@ def test_pipelined_submit_wait_matches_batch_calls():
     ctx.close()
 
 
-# ----------------------------------------------------------------------------------------- taxa capacity of the records
-@pytest.mark.parametrize("K,k_high,k_low,n_taxa", [(12, 12, 7, 63), (12, 12, 1, 64), (25, 25, 7, 64), (25, 25, 7, 50)])
-def test_identify_at_the_record_taxa_capacity(K, k_high, k_low, n_taxa):
-    """63 taxa with 3-bit level fields (<= 7 levels), 64 with 4-bit (<= 15) and 5-bit fields (<= 31 levels, two-sector
-    records: BASELINE config C3 = 50 taxa at k = 25..7).  Shared regions make many taxa meet in one k-mer group."""
-    glen, n_reads = 2500, 120
+# ----------------------------------------------------------------------------------------- taxonomies of any size
+def _shared_region_case(K, n_taxa, n_reads, seed, glen=2500, share_every=1):
+    """Synthetic genomes that all carry the same 400 bp (and every second one another 200 bp): k-mer groups naming up to n_taxa taxa
+    (taxa sets far beyond the nine pairs a match record holds inline -> the overflow lists), plus reads cut from them."""
     taxids = np.array([0] + [1000 + t for t in range(n_taxa)], dtype=np.uint32)
-    rng = np.random.default_rng(K * 1000 + n_taxa)
+    rng = np.random.default_rng(seed)
     shared = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 400))
     fasta, genomes = b"", []
     for t in range(n_taxa):
         g = bytearray(synth.genome_ascii(9, t, glen))
-        g[300:700] = shared                                   # every taxon carries the same 400 bp: groups of n_taxa taxa
+        if t % share_every == 0:
+            g[300:700] = shared
         if t % 2:
             g[1000:1200] = shared[:200]
         genomes.append(bytes(g))
@@ -338,27 +351,79 @@ def test_identify_at_the_record_taxa_capacity(K, k_high, k_low, n_taxa):
         o = int(rng.integers(0, glen - 150))
         reads.append(g[o:o + 150])
     reads += [shared[:150], shared[100:250]]
+    return taxids, index, reads
+
+
+def _check_against_oracles(scores, ca, cu, n_kmers, reads, index, K, k_high, k_low, taxids, rtol):
+    ora = O.identify_reads([[r] for r in reads], index, K, k_high, k_low, True, taxids)
+    mine = O.identify_reads_ordered([[r] for r in reads], index, K, k_high, k_low, True, taxids)
+    assert n_kmers == ora.n_kmers
+    assert np.array_equal(cu, ora.count_unique)
+    np.testing.assert_allclose(ca, ora.count_all, rtol=COUNT_RTOL, atol=1e-9)
+    assert np.array_equal(scores > 0, ora.scores > 0)
+    assert np.array_equal(scores, mine.scores)
+    np.testing.assert_allclose(scores, ora.scores, rtol=rtol)
+
+
+@pytest.mark.parametrize("K,k_high,k_low,n_taxa", [(12, 12, 7, 63), (12, 12, 1, 64), (25, 25, 7, 64), (25, 25, 7, 50), (12, 12, 7, 9), (12, 12, 7, 10),
+                                                   (12, 12, 7, 33)])
+def test_identify_small_taxonomies_dense_cells(K, k_high, k_low, n_taxa):
+    """<= 64 taxa: thread-per-read accumulation with one cell per taxon (score.cu accumulate_dense_kernel), 6 / 12 / 19 levels;
+    shared regions make up to n_taxa taxa meet in one k-mer group (inline records up to 9 taxa, overflow lists beyond)."""
+    taxids, index, reads = _shared_region_case(K, n_taxa, 120, K * 1000 + n_taxa)
     ctx = _ctx(highest_k=K, k_high=k_high, k_low=k_low, frames=6, max_batch_kmers=1 << 20)
     ctx.load_index(index, taxids)
     n_kmers, scores, _ = ctx.identify_batch(reads)
     ca, cu, _ = ctx.identify_finish()
     ctx.close()
-    ora = O.identify_reads([[r] for r in reads], index, K, k_high, k_low, True, taxids)
-    assert n_kmers == ora.n_kmers
-    assert np.array_equal(cu, ora.count_unique)
-    np.testing.assert_allclose(ca, ora.count_all, rtol=COUNT_RTOL, atol=1e-9)
-    assert np.array_equal(scores > 0, ora.scores > 0)
-    # more levels = more fp32 adds per cell: the order-dependent rounding of the reference's sums grows (as in the k25 golden test)
-    np.testing.assert_allclose(scores, ora.scores, rtol=3e-5 if k_high - k_low + 1 > 7 else FAST_RTOL)
+    _check_against_oracles(scores, ca, cu, n_kmers, reads, index, K, k_high, k_low, taxids,
+                           ORDERED_RTOL_K25 if k_high - k_low + 1 > 7 else ORDERED_RTOL)
 
 
-def test_more_taxa_than_a_record_holds_is_rejected_loudly():
-    taxids = np.arange(66, dtype=np.uint32)                  # 65 taxa + "non_unique"
-    ctx = _ctx()
-    with pytest.raises(KasaError) as e:
-        ctx.load_index(np.zeros(0, dtype=capi.REC64), taxids)
-    assert "at most" in str(e.value)
+@pytest.mark.parametrize("n_taxa,share_every", [(500, 1), (4096, 8), (4096, 4)])
+def test_identify_large_taxonomies_dense_and_sparse_results(n_taxa, share_every):
+    """Content files with hundreds to thousands of taxa (the reference's sBitArray / score matrix are unbounded: BitArray.hpp:18-147,
+    Utilities.hpp:592-636): taxa sets as lists, hashed cells per read, results as the dense matrix and as sparse (read, taxon) hits."""
+    # (4096, 4): 1024 taxa share a region, more than the 768 cells a read's hash table holds -> replay by taxon range
+    taxids, index, reads = _shared_region_case(12, n_taxa, 100, 77 + n_taxa, glen=1600, share_every=share_every)
+    ctx = _ctx(frames=6, max_batch_kmers=1 << 23, max_batch_seqs=1 << 10, max_batch_hits=1 << 20)
+    ctx.load_index(index, taxids)
+    n_kmers, scores, _ = ctx.identify_batch(reads)
+    ca, cu, _ = ctx.identify_finish()
+    _check_against_oracles(scores, ca, cu, n_kmers, reads, index, 12, 12, 7, taxids, ORDERED_RTOL)
+    n2, beg, cnt, tax, sc = ctx.identify_batch_hits(reads)
+    ca2, cu2, _ = ctx.identify_finish()
+    assert n2 == n_kmers and np.array_equal(cu2, cu)
+    sparse = np.zeros_like(scores)
+    for r in range(len(reads)):
+        t = tax[int(beg[r]):int(beg[r]) + int(cnt[r])]
+        assert len(set(t.tolist())) == len(t)
+        sparse[r, t] = sc[int(beg[r]):int(beg[r]) + int(cnt[r])]
+    assert np.array_equal(sparse, scores)
+    assert int(cnt.sum()) == len(tax) == int((scores > 0).sum())
     ctx.close()
+
+
+def test_the_taxon_index_is_sixteen_bits():
+    taxids = np.arange(65537, dtype=np.uint32)               # 65536 taxa + "non_unique"
+    ctx = _ctx()
+    with pytest.raises(KasaError):
+        ctx.load_index(np.zeros(0, dtype=capi.REC64), taxids)
+    ctx.load_index(np.zeros(0, dtype=capi.REC64), taxids[:65535])
+    ctx.close()
+
+
+def test_reads_longer_than_the_shared_memory_segment_are_ordered_in_slices():
+    """A 9 kbp read (~18 000 k-mers) is ordered rank slice by rank slice (score.cu order_ops_kernel) with the same result."""
+    taxids, index, _ = _shared_region_case(12, 12, 0, 5, glen=12000)
+    g = synth.genome_ascii(9, 3, 12000)
+    reads = [bytes(g[100:9100]), bytes(g[5000:5150]), b"ACGT" * 2000, bytes(g[2000:11000])]
+    ctx = _ctx(frames=6, max_batch_kmers=1 << 20, max_batch_bases=1 << 20)
+    ctx.load_index(index, taxids)
+    n_kmers, scores, _ = ctx.identify_batch(reads)
+    ca, cu, _ = ctx.identify_finish()
+    ctx.close()
+    _check_against_oracles(scores, ca, cu, n_kmers, reads, index, 12, 12, 7, taxids, 2e-5)
 
 
 # ----------------------------------------------------------------------------------------- KASA_SEQ_PACKED2 input

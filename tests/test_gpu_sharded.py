@@ -1,6 +1,6 @@
 """GPU parity of the prefix-sharded identify (SURVEY.md §8e mode 2; include/kasa_b200.h kasa_shard_*): n contexts,
 each holding one prefix range of the index and its own reads, must reproduce the unsharded results — per-read
-scores bit for bit (KASA_SCORE_FAST is a canonical order), unique counts exactly, non-unique counts to 1e-12 —
+scores bit for bit (KASA_SCORE_ORDERED is a batch- and shard-independent order), unique counts exactly, non-unique counts to 1e-12 —
 which are themselves pinned on the reference binary in test_gpu_parity.py.  The contexts live in one process on
 one GPU here (peers reached through raw device pointers); the cross-process cudaIpc route is exercised by
 `bench.py --sharding prefix` under torchrun."""
@@ -13,6 +13,8 @@ from kasa_b200 import capi
 from kasa_b200.dist import LocalShardGroup, shard_bounds
 
 pytestmark = pytest.mark.gpu
+
+LONG_READ_RTOL = 5e-6      # 10 kbp reads: ~10^4 float32 adds per cell, against the reference's own flush order
 
 
 def _reads(case, paired):
@@ -37,7 +39,7 @@ def _run(case, K, k_high, k_low, six, n_shards, paired=False):
     _, taxids, _ = G.content(case)
     idx = G.index(case)
     reads, paired = _reads(case, paired)
-    kw = dict(highest_k=K, k_high=k_high, k_low=k_low, frames=6 if six else 3, score_mode=capi.SCORE_FAST)
+    kw = dict(highest_k=K, k_high=k_high, k_low=k_low, frames=6 if six else 3, score_mode=capi.SCORE_ORDERED)
     # unsharded
     ref = Context(Params(**kw))
     ref.load_index(idx, taxids)
@@ -152,7 +154,7 @@ def test_sharded_build_concatenates_to_the_reference_files(case, K, six, n_shard
 # ----------------------------------------------------------------------------------------- long reads (C5 shape)
 def test_long_reads_sharded_and_plain_match_the_oracle():
     """BASELINE config C5 in miniature: 10 kbp reads with 10 % errors (substitutions and indels) against a prefix-sharded
-    index.  19 960 k-mers per read: the per-read kernel walks them in 32-instance chunks, counters are widened on the way."""
+    index.  19 960 k-mers per read."""
     from kasa_b200 import synth
     from oracle import oracle as O
     n_taxa, glen, n_reads, rlen = 6, 40_000, 12, 10_000
@@ -187,9 +189,10 @@ def test_long_reads_sharded_and_plain_match_the_oracle():
     assert nk == ora.n_kmers
     assert np.array_equal(cu, ora.count_unique)
     np.testing.assert_allclose(ca, ora.count_all, rtol=1e-6, atol=1e-9)
-    # the reference's score is an fp32 running sum of ~20 000 terms (here ~960: one ulp = 6e-5), ours is exact integer
-    # arithmetic rounded once: the difference is the reference's own rounding drift
-    np.testing.assert_allclose(scores, ora.scores, rtol=5e-5)
+    # ~20 000 k-mers per read: ordered rank slice by rank slice (score.cu), bit-identical to the CPU restatement of that order
+    mine = O.identify_reads_ordered([[r] for r in reads], index, 12, 12, 7, True, taxids)
+    assert np.array_equal(scores, mine.scores)
+    np.testing.assert_allclose(scores, ora.scores, rtol=LONG_READ_RTOL)
     eb, pb = capi.shard_plan(index, 7, 2)
     ctxs = []
     for r in range(2):
