@@ -1,4 +1,6 @@
 // score.cu — see score.cuh.
+#include <algorithm>
+
 #include "score.cuh"
 
 namespace kasa {
@@ -44,19 +46,16 @@ __device__ __forceinline__ uint32_t header_extra(int k, uint64_t lo, uint64_t hi
 constexpr int kAMaxWarps = 4;
 
 struct WarpMem {
-    uint64_t *key;      // [icap]  sort key << 32 | level << 16 | slot
-    uint64_t *pw;       // [3][cap] record words 1..3
-    uint32_t *meta;     // [cap]   count | hmax << 16 | overflow << 21 | owner << 22 | mask << 27
-    uint32_t *ioff;     // [cap]   instance offset inside the read (EXACT only)
-    uint32_t *bcnt;     // [nb + 1]
-    uint32_t *un;       // [num_k][64] unique hits of this warp's reads (COUNTS only)
+    ulonglong2 *rlo, *rhi;   // [cap] record words (w0, w1) / (w2, w3) by slot
+    uint64_t *key;           // [icap]  sort key << 32 | level << 16 | slot
+    uint32_t *bcnt;          // [nb + 1]
+    uint32_t *un;            // [num_k][64] unique hits of this warp's reads (COUNTS only)
     uint16_t *tmp, *ord, *arr;   // [icap]
 };
 
-__host__ __device__ inline size_t warp_mem_bytes(uint32_t cap, uint32_t icap, uint32_t nb, bool exact, int count_levels)
+__host__ __device__ inline size_t warp_mem_bytes(uint32_t cap, uint32_t icap, uint32_t nb, int count_levels)
 {
-    size_t b = (size_t)8 * icap + (size_t)24 * cap + (size_t)4 * cap + (exact ? (size_t)4 * cap : 0) + (size_t)4 * (nb + 1) + (size_t)256 * count_levels +
-               (size_t)6 * icap;
+    size_t b = (size_t)32 * cap + (size_t)8 * icap + (size_t)4 * (nb + 1) + (size_t)256 * count_levels + (size_t)6 * icap;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -78,84 +77,62 @@ __device__ __forceinline__ void level_sizes(const uint64_t (&pw)[3], uint32_t co
     }
 }
 
-struct Decoded {
-    uint32_t count, hmax, sumh;
-    uint64_t npk_lo, npk_hi;      // nibble j = |taxa_j| for the levels j >= 1 (level 0: count); inline / mask records only
-    bool overflow, mask;
-};
-
-__device__ __forceinline__ Decoded decode_record(uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3, const OverflowPeers &peers)
+// sum of the level counts of a record's pairs (= number of (taxon, level) contributions)
+__device__ __forceinline__ uint32_t record_sumh(uint64_t w0, const uint64_t (&pw)[3], const OverflowPeers &peers)
 {
-    Decoded d;
-    d.count = rec_count(w0);
-    d.hmax = rec_hmax(w0);
-    d.overflow = rec_overflow(w0);
-    d.mask = rec_is_mask(w0);
-    d.npk_lo = d.npk_hi = 0;
-    d.sumh = 0;
-    if (!d.count) return d;
-    const uint64_t pw[3] = {w1, w2, w3};
-    if (d.mask) {
-        d.sumh = d.count;
+    const uint32_t c = rec_count(w0);
+    uint32_t sumh = 0;
+    if (rec_is_mask(w0)) {
+        sumh = c;
 #pragma unroll
-        for (int k = 0; k < kRecUpPairs; ++k) {
-            const uint32_t p = up_pair(pw, k);
-            if (p) {
-                uint64_t lo, hi;
-                nib_below(p >> 16, lo, hi);
-                d.npk_lo += lo & ~15ull; d.npk_hi += hi;
-                d.sumh += (p >> 16) - 1;
-            }
-        }
-    } else if (!d.overflow) {
+        for (int k = 0; k < kRecUpPairs; ++k) { const uint32_t p = up_pair(pw, k); if (p) sumh += (p >> 16) - 1; }
+    } else if (!rec_overflow(w0)) {
 #pragma unroll
-        for (int k = 0; k < kRecInline; ++k) {
-            if ((uint32_t)k < d.count) {
-                const uint32_t h = rec_pair(pw, k) >> 16;
-                uint64_t lo, hi;
-                nib_below(h, lo, hi);
-                d.npk_lo += lo & ~15ull; d.npk_hi += hi;
-                d.sumh += h;
-            }
-        }
+        for (int k = 0; k < kRecInline; ++k) if ((uint32_t)k < c) sumh += rec_pair(pw, k) >> 16;
     } else {
-        const uint32_t *list = peers.base[rec_owner(w0)] + w1;
-        for (uint32_t k = 0; k < d.count; ++k) d.sumh += __ldg(list + k) >> 16;
+        const uint32_t *list = peers.base[rec_owner(w0)] + pw[0];
+        for (uint32_t k = 0; k < c; ++k) sumh += __ldg(list + k) >> 16;
     }
-    return d;
+    return sumh;
 }
 
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+// STREAM: 0 = pair stream in rank order, 1 = pair stream in the reference's flush order (EXACT), 2 = mask stream in rank order
+// (<= 64 taxa and <= 6 levels: groups of 16 bytes, see accumulate_mask_kernel).
 // COUNTS (content files of <= 64 taxa): the per-taxon counts are accumulated here, order-free, lane = taxon (lane l owns the taxa
 // l+1 and l+33) over the records the warp holds in shared memory: level k_low hits as 2^-32 fixed point / integers in registers,
 // the levels above through packed per-read counters; kernel B then only replays the float32 scores.
-template <bool EXACT, bool COUNTS>
+template <int STREAM, bool COUNTS>
 __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64_t *__restrict__ rec, const uint64_t *__restrict__ read_koff, uint32_t r0,
                                                                     uint32_t r1, uint64_t n_kmers, LevelParams lp, OverflowPeers peers, OpsWorkspace ws,
                                                                     const uint32_t *__restrict__ trig, uint32_t *__restrict__ err_flag, uint32_t cap,
                                                                     uint32_t icap, uint32_t nb, uint32_t wbytes, unsigned long long *__restrict__ cnt_fx,
                                                                     unsigned long long *__restrict__ cnt_unique, bool emit)
 {
+    constexpr bool EXACT = STREAM == 1, MASKS = STREAM == 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int w = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
+    const int T = lp.n_taxa, NK = lp.num_k;
     WarpMem M;
     {
         unsigned char *base = smem_raw + (size_t)w * wbytes;
-        M.key = reinterpret_cast<uint64_t *>(base);
-        M.pw = M.key + icap;
-        M.meta = reinterpret_cast<uint32_t *>(M.pw + 3 * (size_t)cap);
-        M.ioff = M.meta + cap;
-        M.bcnt = EXACT ? M.ioff + cap : M.ioff;
+        M.rlo = reinterpret_cast<ulonglong2 *>(base);
+        M.rhi = M.rlo + cap;
+        M.key = reinterpret_cast<uint64_t *>(M.rhi + cap);
+        M.bcnt = reinterpret_cast<uint32_t *>(M.key + icap);
         M.un = M.bcnt + nb + 1;
-        M.tmp = reinterpret_cast<uint16_t *>(M.un + (COUNTS ? 64 * lp.num_k : 0));
+        M.tmp = reinterpret_cast<uint16_t *>(M.un + (COUNTS ? 64 * NK : 0));
         M.ord = M.tmp + icap;
         M.arr = M.ord + icap;
     }
     const uint32_t n_warps = blockDim.x >> 5;
     const uint32_t warps_total = gridDim.x * n_warps;
-    const uint32_t NX = EXACT ? 0u : (uint32_t)ops_extra_words(lp.num_k);
-    const int T = lp.n_taxa, NK = lp.num_k;
-    // counts of this warp's reads (COUNTS): level k_low in registers, all unique hits in a per-warp table behind the per-warp arrays
+    const uint32_t NX = STREAM == 0 ? (uint32_t)ops_extra_words(NK) : 0u;
     // level k_low: 2^-32 sums and unique hits of this lane's two taxa over all the warp's reads
     unsigned long long fx0a = 0, fx0b = 0, un0a = 0, un0b = 0;
     __shared__ uint32_t s_invfx[kAMaxWarps][128];
@@ -164,8 +141,24 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
         for (int i = lane; i < 128; i += 32) s_invfx[w][i] = i >= 2 ? inv_fx((uint32_t)i) : 0u;
     }
     __syncwarp();
-    auto count_segment = [&](uint32_t m) {
-        // lane = taxon (lane l owns the taxa l+1 and l+33); warp-uniform walk over the segment's records
+
+    // words the group of a record takes in the stream (ordered streams)
+    auto group_words = [&](uint64_t w0, uint64_t w2, uint64_t w3) -> uint32_t {
+        const uint32_t c = rec_count(w0);
+        if (!MASKS) return 1 + NX + c;
+        uint32_t nup;
+        if (rec_is_mask(w0)) {
+            nup = 0;
+#pragma unroll
+            for (int k = 0; k < kRecUpPairs; ++k) nup += ((uint32_t)((k < 3 ? w2 : w3) >> (kPairBits * (k % 3))) & kPairMask) ? 1u : 0u;
+        } else {
+            nup = c;                                           // list records: every pair is written as an up pair (levels >= 1 too)
+        }
+        return 4u + (nup > 1u ? 4u * ((nup - 1u + 3u) / 4u) : 0u);
+    };
+
+    auto count_slots = [&](uint32_t n_slots) {
+        // lane = taxon (lane l owns the taxa l+1 and l+33); warp-uniform walk over the records in shared memory
         unsigned long long upa = 0, upb = 0;                        // unique hits of the levels 1..8, 8-bit fields (flushed every 128 records)
         auto flush_up = [&]() {
             for (int j = 1; j < NK && j <= 8; ++j) {
@@ -175,28 +168,32 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
             }
             upa = upb = 0;
         };
-        // taxon t (0-based) of this lane matches the levels 1 .. h-1, each with `one` taxon
-        auto add_upper_unique = [&](uint32_t t, uint32_t h) {
+        auto add_upper_unique = [&](uint32_t t, uint32_t h) {       // taxon t (0-based) is alone at each of the levels 1 .. h-1
             const uint32_t top = h - 1 < 8u ? h - 1 : 8u;
             const unsigned long long f = (top >= 8u ? ~0ull : ((1ull << (8 * top)) - 1)) & 0x0101010101010101ull;
             if (t >> 5) upb += f; else upa += f;
             for (uint32_t j = 9; j < h; ++j) M.un[j * 64 + t] += 1u;
         };
-        for (uint32_t i = 0; i < m; ++i) {
-            const uint32_t meta = M.meta[i];
-            const uint32_t c = meta & 0xffffu, hmax = (meta >> 16) & 31u;
-            if ((meta >> 27) & 1u) {
-                const uint64_t mk = M.pw[i];
+#pragma unroll 2
+        for (uint32_t i = 0; i < n_slots; ++i) {
+            const ulonglong2 a = M.rlo[i];
+            const uint64_t w0 = a.x;
+            const uint32_t c = rec_count(w0), hmax = rec_hmax(w0);
+            if (!c) continue;
+            if (rec_is_mask(w0)) {
+                const uint64_t mk = a.y;
                 const uint32_t in0 = (uint32_t)(mk >> lane) & 1u, in1 = (uint32_t)(mk >> (lane + 32)) & 1u;
-                if (c == 1u) { un0a += in0; un0b += in1; }
-                else { const uint32_t f = s_invfx[w][c]; fx0a += (unsigned long long)(in0 * f); fx0b += (unsigned long long)(in1 * f); }
+                const uint32_t one = c == 1u ? 1u : 0u, f = s_invfx[w][c & 127u];
+                un0a += in0 & one; un0b += in1 & one;
+                fx0a += (unsigned long long)(in0 * f); fx0b += (unsigned long long)(in1 * f);
                 if (hmax > 1u) {
-                    const uint64_t pw[3] = {mk, M.pw[cap + i], M.pw[2 * (size_t)cap + i]};
-                    if ((pw[1] >> kPairBits) == 0 && pw[2] == 0) {
+                    const ulonglong2 b = M.rhi[i];
+                    if ((b.x >> kPairBits) == 0 && b.y == 0) {
                         // the usual case: one taxon above k_low, alone at each of its upper levels
-                        const uint32_t p = (uint32_t)pw[1] & kPairMask, t = (p & 0xffffu) - 1u;
+                        const uint32_t p = (uint32_t)b.x & kPairMask, t = (p & 0xffffu) - 1u;
                         if ((t & 31u) == lane) add_upper_unique(t, p >> 16);
                     } else {
+                        const uint64_t pw[3] = {mk, b.x, b.y};
                         uint64_t lo, hi;
                         level_sizes(pw, c, true, lo, hi);
 #pragma unroll
@@ -208,7 +205,7 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
                                 for (uint32_t j = 1; j < h; ++j) {
                                     const uint32_t nn = nib_get(lo, hi, j);
                                     if (nn == 1u) M.un[j * 64 + t] += 1u;
-                                    else atomicAdd(cnt_fx + (size_t)j * T + t + 1, (unsigned long long)s_invfx[w][nn]);
+                                    else atomicAdd(cnt_fx + (size_t)j * T + t + 1, (unsigned long long)s_invfx[w][nn & 127u]);
                                 }
                             }
                         }
@@ -216,9 +213,10 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
                 }
             } else {
                 // list records (more than six taxa above k_low, or a span read from HBM): pair by pair
-                const bool ovf = (meta >> 21) & 1u;
-                const uint64_t pw[3] = {M.pw[i], M.pw[cap + i], M.pw[2 * (size_t)cap + i]};
-                const uint32_t *list = ovf ? peers.base[(meta >> 22) & 15u] + pw[0] : nullptr;
+                const bool ovf = rec_overflow(w0);
+                const ulonglong2 b = M.rhi[i];
+                const uint64_t pw[3] = {a.y, b.x, b.y};
+                const uint32_t *list = ovf ? peers.base[rec_owner(w0)] + pw[0] : nullptr;
                 uint32_t nj[32];
                 if (hmax > 1u) {
                     for (uint32_t j = 0; j < hmax; ++j) nj[j] = 0;
@@ -227,7 +225,7 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
                         for (uint32_t j = 0; j < h; ++j) ++nj[j];
                     }
                 }
-                const uint32_t f0 = c >= 2u ? inv_fx(c) : 0u;
+                const uint32_t f0 = c >= 2u ? (c < 128u ? s_invfx[w][c] : inv_fx(c)) : 0u;
                 for (uint32_t k = 0; k < c; ++k) {
                     const uint32_t e = ovf ? __ldg(list + k) : (uint32_t)(pw[k / 3] >> (kPairBits * (k % 3))) & kPairMask;
                     const uint32_t t = (e & 0xffffu) - 1u, h = e >> 16;
@@ -236,7 +234,7 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
                     else { if (t >> 5) fx0b += f0; else fx0a += f0; }
                     for (uint32_t j = 1; j < h; ++j) {
                         if (nj[j] == 1u) M.un[j * 64 + t] += 1u;
-                        else atomicAdd(cnt_fx + (size_t)j * T + t + 1, (unsigned long long)inv_fx(nj[j]));
+                        else atomicAdd(cnt_fx + (size_t)j * T + t + 1, (unsigned long long)(nj[j] < 128u ? s_invfx[w][nj[j]] : inv_fx(nj[j])));
                     }
                 }
             }
@@ -290,20 +288,20 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
             const bool valid = p < m;
             const uint64_t key = valid ? M.key[M.ord[p]] : 0ull;
             const uint32_t slot = (uint32_t)key & 0xffffu, lev = (uint32_t)(key >> 16) & 0xffffu;
-            uint32_t meta = 0, c = 0, hmax = 0;
+            uint32_t c = 0, hmax = 0;
             bool ovf = false, msk = false;
-            uint64_t pw[3] = {0, 0, 0}, nlo = 0, nhi = 0;
+            uint64_t w0 = 0, pw[3] = {0, 0, 0}, nlo = 0, nhi = 0;
             uint32_t opc = 0, extc = 0, nlev = 0;                  // nlev: |taxa_lev| (EXACT)
             const uint32_t *list = nullptr;
             if (valid) {
-                meta = M.meta[slot];
-                c = meta & 0xffffu; hmax = (meta >> 16) & 31u; ovf = (meta >> 21) & 1u; msk = (meta >> 27) & 1u;
-                pw[0] = M.pw[slot]; pw[1] = M.pw[cap + slot]; pw[2] = M.pw[2 * (size_t)cap + slot];
-                if (ovf) list = peers.base[(meta >> 22) & 15u] + pw[0];
-                else level_sizes(pw, c, msk, nlo, nhi);
+                const ulonglong2 a = M.rlo[slot], b = M.rhi[slot];
+                w0 = a.x; pw[0] = a.y; pw[1] = b.x; pw[2] = b.y;
+                c = rec_count(w0); hmax = rec_hmax(w0); ovf = rec_overflow(w0); msk = rec_is_mask(w0);
+                if (ovf) list = peers.base[rec_owner(w0)] + pw[0];
+                else if (!MASKS) level_sizes(pw, c, msk, nlo, nhi);
                 if (!EXACT) {
-                    opc = 1 + NX + c;
-                    extc = ovf ? hmax : 0u;                         // overflow records escape every level size (deterministic demand)
+                    opc = group_words(w0, pw[1], pw[2]);
+                    extc = (!MASKS && ovf) ? hmax : 0u;             // overflow records escape every level size (deterministic demand)
                 } else {
                     if (!ovf) nlev = lev ? nib_get(nlo, nhi, lev) : c;
                     else for (uint32_t k = 0; k < c; ++k) nlev += (__ldg(list + k) >> 16) > lev ? 1u : 0u;
@@ -321,7 +319,39 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
             uint32_t *op = ws.ops + o_cur + (io - opc);
             uint16_t *ex = ws.ext + e_cur + (ie - extc);
             if (valid && opc) {
-                if (!EXACT) {
+                if (MASKS) {
+                    // 16-byte groups: [header | n0 << 24 | nup << 17][mask lo][mask hi][up pair 0], then the other up pairs four per block
+                    uint4 g;
+                    if (msk) {
+                        uint32_t nup = 0;
+#pragma unroll
+                        for (int k = 0; k < kRecUpPairs; ++k) nup += up_pair(pw, k) ? 1u : 0u;
+                        g = make_uint4(kOpHeader | (c << 24) | (nup << 17), (uint32_t)pw[0], (uint32_t)(pw[0] >> 32), up_pair(pw, 0));
+                        *reinterpret_cast<uint4 *>(op) = g;
+                        if (nup > 1u) {
+                            uint32_t e4[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+                            for (int k = 1; k < kRecUpPairs; ++k) e4[k - 1] = up_pair(pw, k);
+                            *reinterpret_cast<uint4 *>(op + 4) = make_uint4(e4[0], e4[1], e4[2], e4[3]);
+                            if (nup > 5u) *reinterpret_cast<uint4 *>(op + 8) = make_uint4(e4[4], 0, 0, 0);
+                        }
+                    } else {
+                        // list record of a small taxonomy: the mask from the pairs, every pair as an up pair
+                        uint64_t mk = 0;
+                        for (uint32_t k = 0; k < c; ++k) {
+                            const uint32_t e = ovf ? __ldg(list + k) : (uint32_t)(pw[k / 3] >> (kPairBits * (k % 3))) & kPairMask;
+                            mk |= 1ull << ((e & 0xffffu) - 1u);
+                        }
+                        const uint32_t first = ovf ? __ldg(list) : (uint32_t)pw[0] & kPairMask;
+                        *reinterpret_cast<uint4 *>(op) = make_uint4(kOpHeader | (c << 24) | (c << 17), (uint32_t)mk, (uint32_t)(mk >> 32), first);
+                        for (uint32_t k = 1; k < c; k += 4) {
+                            uint32_t e4[4] = {0, 0, 0, 0};
+                            for (uint32_t i = 0; i < 4 && k + i < c; ++i)
+                                e4[i] = ovf ? __ldg(list + k + i) : (uint32_t)(pw[(k + i) / 3] >> (kPairBits * ((k + i) % 3))) & kPairMask;
+                            *reinterpret_cast<uint4 *>(op + 4 + (k - 1)) = make_uint4(e4[0], e4[1], e4[2], e4[3]);
+                        }
+                    }
+                } else if (!EXACT) {
                     if (!ovf) {
                         *op++ = header_word(c, nlo);
                         for (uint32_t k = 0; k < NX; ++k) *op++ = header_extra((int)k, nlo, nhi);
@@ -342,14 +372,14 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
                         uint16_t nj[32];
                         for (uint32_t j = 0; j < 32; ++j) nj[j] = 0;
                         for (uint32_t k = 0; k < c; ++k) { const uint32_t h = __ldg(list + k) >> 16; for (uint32_t j = 0; j < h; ++j) ++nj[j]; }
-                        uint64_t lo = 0, hi = 0;
+                        uint64_t lo2 = 0, hi2 = 0;
                         *ex++ = (uint16_t)c;
                         for (uint32_t j = 1; j < hmax; ++j) {
-                            if (j < 16) lo |= (uint64_t)kOpNibExt << (4 * j); else hi |= (uint64_t)kOpNibExt << (4 * (j - 16));
+                            if (j < 16) lo2 |= (uint64_t)kOpNibExt << (4 * j); else hi2 |= (uint64_t)kOpNibExt << (4 * (j - 16));
                             *ex++ = nj[j];
                         }
-                        *op++ = header_word(kOpNExt, lo);
-                        for (uint32_t k = 0; k < NX; ++k) *op++ = header_extra((int)k, lo, hi);
+                        *op++ = header_word(kOpNExt, lo2);
+                        for (uint32_t k = 0; k < NX; ++k) *op++ = header_extra((int)k, lo2, hi2);
                         for (uint32_t k = 0; k < c; ++k) *op++ = __ldg(list + k);
                     }
                 } else {
@@ -380,9 +410,44 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
         const uint64_t s0 = read_koff[r];
         const uint32_t ni = (uint32_t)(read_koff[r + 1] - s0);
         const bool single = ni <= cap;
-        // ---- totals (and, when the read fits, its records into shared memory)
         uint32_t m = 0, my_ops = 0, my_ext = 0;
-        auto scan_records = [&](bool store, bool count, uint64_t lo, uint64_t hi) {
+        // demand of one record on the op / ext streams
+        auto demand = [&](uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3) {
+            if (!EXACT) { my_ops += group_words(w0, w2, w3); if (!MASKS) my_ext += rec_overflow(w0) ? rec_hmax(w0) : 0u; }
+            else { const uint64_t pw[3] = {w1, w2, w3}; my_ops += rec_hmax(w0) + record_sumh(w0, pw, peers); my_ext += rec_overflow(w0) ? rec_hmax(w0) : 0u; }
+        };
+        if (single) {
+            // ---- the whole read into shared memory with asynchronous copies (all its sectors in flight at once), slot = instance
+            for (uint32_t x = lane; x < ni; x += 32) {
+                const uint64_t *g = rec + (s0 + x) * kRecWords;
+                cp_async16(&M.rlo[x], g);
+                cp_async16(&M.rhi[x], g + 2);
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            for (uint32_t x0 = 0; x0 < ni; x0 += 32) {
+                const uint32_t x = x0 + lane;
+                const bool sel = x < ni && rec_count(M.rlo[x].x) != 0;
+                const uint32_t bal = __ballot_sync(kFull, sel);
+                if (sel) {
+                    const ulonglong2 a = M.rlo[x], b = M.rhi[x];
+                    demand(a.x, a.y, b.x, b.y);
+                    if (!EXACT) M.key[m + __popc(bal & lanemask_lt())] = ((uint64_t)rec_rank(a.x) << 32) | x;
+                }
+                m += __popc(bal);
+            }
+            __syncwarp();
+        } else {
+            // ---- long read: only the totals now; the records come in rank slices below
+            for (uint32_t x0 = 0; x0 < ni; x0 += 32) {
+                const uint32_t x = x0 + lane;
+                uint64_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                if (x < ni) asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(rec + (s0 + x) * kRecWords));
+                if (rec_count(w0)) demand(w0, w1, w2, w3);
+            }
+        }
+        // records of the rank slice [lo, hi) of a long read into shared memory, compacted; m = their number (may exceed cap: retry)
+        auto load_slice = [&](uint64_t lo, uint64_t hi) {
             m = 0;
             for (uint32_t x0 = 0; x0 < ni; x0 += 32) {
                 const uint32_t x = x0 + lane;
@@ -391,38 +456,26 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
                 const uint32_t rank = rec_rank(w0);
                 const bool sel = rec_count(w0) != 0 && (uint64_t)rank >= lo && (uint64_t)rank < hi;
                 const uint32_t bal = __ballot_sync(kFull, sel);
-                if (sel) {
-                    Decoded d;
-                    if (EXACT) d = decode_record(w0, w1, w2, w3, peers);
-                    else { d.count = rec_count(w0); d.hmax = rec_hmax(w0); d.overflow = rec_overflow(w0); d.mask = rec_is_mask(w0); d.sumh = 0; }
-                    if (count) {
-                        if (!EXACT) my_ops += 1 + NX + d.count; else my_ops += d.hmax + d.sumh;
-                        my_ext += d.overflow ? d.hmax : 0u;
-                    }
-                    const uint32_t slot = m + __popc(bal & lanemask_lt());
-                    if (store && slot < cap) {
-                        M.pw[slot] = w1; M.pw[cap + slot] = w2; M.pw[2 * (size_t)cap + slot] = w3;
-                        M.meta[slot] = d.count | (d.hmax << 16) | ((d.overflow ? 1u : 0u) << 21) | (rec_owner(w0) << 22) | ((d.mask ? 1u : 0u) << 27);
-                        if (EXACT) M.ioff[slot] = x;
-                        if (!EXACT) M.key[slot] = ((uint64_t)rank << 32) | slot;
-                    }
+                const uint32_t slot = m + __popc(bal & lanemask_lt());
+                if (sel && slot < cap) {
+                    M.rlo[slot] = make_ulonglong2(w0, w1); M.rhi[slot] = make_ulonglong2(w2, w3);
+                    M.key[slot] = ((uint64_t)rank << 32) | slot;
                 }
                 m += __popc(bal);
             }
             __syncwarp();
         };
-        scan_records(single, true, 0, ~0ull);
+        const uint64_t rmax = n_kmers ? n_kmers : 1;
         if (COUNTS && !emit) {
             // profile only (no per-read scores wanted): the counts are all there is to do
-            if (single) count_segment(m);
+            if (single) count_slots(ni);
             else {
-                const uint64_t rmax = n_kmers ? n_kmers : 1;
                 uint64_t lo = 0, width = rmax / (uint64_t)(2ull * ni / cap + 1) + 1;
                 while (lo < rmax) {
                     const uint64_t hi = lo + width < rmax ? lo + width : rmax;
-                    scan_records(true, false, lo, hi);
+                    load_slice(lo, hi);
                     if (m > cap) { width = (hi - lo) >> 1; if (!width) width = 1; continue; }
-                    count_segment(m);
+                    count_slots(m);
                     lo = hi;
                 }
             }
@@ -431,11 +484,13 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
         uint32_t tot_ops = my_ops, tot_ext = my_ext;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { tot_ops += __shfl_xor_sync(kFull, tot_ops, d); tot_ext += __shfl_xor_sync(kFull, tot_ext, d); }
+        // space in the streams: one atomic per read, asked for before the counts so that its latency is hidden behind them
         uint64_t o_base = 0, e_base = 0;
         if (lane == 0) {
             o_base = atomicAdd(ws.cursors + 0, (unsigned long long)((tot_ops + 3u) & ~3u));
-            e_base = atomicAdd(ws.cursors + 1, (unsigned long long)tot_ext);
+            e_base = tot_ext ? atomicAdd(ws.cursors + 1, (unsigned long long)tot_ext) : 0ull;
         }
+        if (COUNTS && single) count_slots(ni);
         o_base = __shfl_sync(kFull, o_base, 0);
         e_base = __shfl_sync(kFull, e_base, 0);
         bool ok = o_base + ((tot_ops + 3u) & ~3u) <= ws.ops_cap && e_base + tot_ext <= ws.ext_cap;
@@ -446,9 +501,9 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
             else {
                 // items = (instance, level) pairs with at least one taxon; key = flush position
                 uint32_t base_i = 0;
-                for (uint32_t x0 = 0; x0 < m && ok; x0 += 32) {
+                for (uint32_t x0 = 0; x0 < ni && ok; x0 += 32) {
                     const uint32_t x = x0 + lane;
-                    const uint32_t hm = x < m ? (M.meta[x] >> 16) & 31u : 0u;
+                    const uint32_t hm = x < ni && rec_count(M.rlo[x].x) ? rec_hmax(M.rlo[x].x) : 0u;
                     uint32_t incl = hm;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(kFull, incl, d); if ((int)lane >= d) incl += y; }
@@ -456,7 +511,7 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
                     if (base_i + tot > icap) { ok = false; if (lane == 0) atomicOr(err_flag, 64u); break; }
                     const uint32_t at = base_i + incl - hm;
                     for (uint32_t j = 0; j < hm; ++j)
-                        M.key[at + j] = ((uint64_t)trig[(s0 + M.ioff[x]) * (uint64_t)lp.num_k + j] << 32) | ((uint64_t)j << 16) | x;
+                        M.key[at + j] = ((uint64_t)trig[(s0 + x) * (uint64_t)NK + j] << 32) | ((uint64_t)j << 16) | x;
                     base_i += tot;
                 }
                 n_items = base_i;
@@ -467,19 +522,17 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
         if (!ok) continue;
         uint64_t o_cur = o_base, e_cur = e_base;
         if (single) {
-            if (COUNTS) count_segment(m);
-            sort_emit(n_items, 0, EXACT ? 0x100000000ull : (n_kmers ? n_kmers : 1), o_cur, e_cur);
+            sort_emit(n_items, 0, EXACT ? 0x100000000ull : rmax, o_cur, e_cur);
         } else {
-            // long read: rank ranges small enough for shared memory, in ascending order (records are re-read from L2)
-            const uint64_t rmax = n_kmers ? n_kmers : 1;
+            // long read: rank slices small enough for shared memory, in ascending order (its records are re-read from L2)
             const uint64_t w0r = rmax / (uint64_t)(2ull * ni / cap + 1);
             const uint64_t width0 = w0r ? w0r : 1;
             uint64_t lo = 0, width = width0;
             while (lo < rmax) {
                 const uint64_t hi = lo + width < rmax ? lo + width : rmax;
-                scan_records(true, false, lo, hi);
+                load_slice(lo, hi);
                 if (m > cap) { width = (hi - lo) >> 1; if (!width) width = 1; continue; }
-                if (COUNTS) count_segment(m);
+                if (COUNTS) count_slots(m);
                 sort_emit(m, lo, hi - lo, o_cur, e_cur);
                 lo = hi;
                 if (m < cap / 4 && width < rmax) width *= 2;
@@ -501,6 +554,134 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
             if (un0b) atomicAdd(cnt_unique + tb, un0b);
             for (int j = 1; j < NK; ++j) { const uint32_t u = M.un[j * 64 + tb - 1]; if (u) atomicAdd(cnt_unique + (size_t)j * T + tb, (unsigned long long)u); }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// B for the mask stream (<= 64 taxa, <= 6 levels, rank order): thread per read, a 16-byte group per k-mer instance.
+//   [header | n0 << 24 | nup << 17][mask lo][mask hi][up pair 0]   (+ blocks of four further up pairs when nup > 1)
+// Every taxon of the mask gets float(w_0 * (1.f / n0)); a taxon named by an up pair (taxon | h << 16) then gets the levels
+// 1 .. h-1, each float(w_j * (1.f / n_j)) with n_j = number of up pairs reaching level j.  Scores and the k_low share of the
+// counts are two columns of shared-memory cells per thread (nothing is atomic, nothing crosses lanes); the rarer events —
+// a k-mer with a single taxon, taxa above k_low — go to small per-CTA tables with shared-memory atomics.
+constexpr int kMaskBlock = 128;
+constexpr int kFxShift = 8;           // per-thread k_low sums in 2^-24 units (a read's sum fits 32 bits), the totals in 2^-32
+
+template <int SLOTS>
+__global__ void __launch_bounds__(kMaskBlock) accumulate_mask_kernel(OpsWorkspace ws, uint32_t r0, uint32_t r1, LevelParams lp, float *__restrict__ scores,
+                                                                     unsigned long long *__restrict__ cnt_fx, unsigned long long *__restrict__ cnt_unique)
+{
+    constexpr int NC = 32 * SLOTS, BT = kMaskBlock;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, T = lp.n_taxa, NK = lp.num_k;
+    float *cellS = reinterpret_cast<float *>(smem_raw);                 // [NC][BT] score of the thread's read
+    uint32_t *cellF = reinterpret_cast<uint32_t *>(cellS + NC * BT);    // [NC][BT] sum of 1 / n0 over the read's k-mers with n0 >= 2, 2^-24 units
+    __shared__ float s_inv[72];
+    __shared__ uint32_t s_q[72];                                        // 2^24 / n rounded to nearest (0 for n < 2)
+    __shared__ uint32_t s_q32[72];                                      // 2^32 / n
+    __shared__ unsigned long long s_fx[6 * 64];                         // CTA totals [level][taxon - 1], 2^-32 units
+    __shared__ uint32_t s_un[6 * 64];
+    __shared__ uint32_t s_hist[64 * 8];                                 // [taxon - 1][h]: k-mers where the taxon is alone at its levels 1 .. h-1
+    for (int i = tid; i < NC * BT; i += BT) { cellS[i] = 0.f; cellF[i] = 0u; }
+    for (int i = tid; i < 6 * 64; i += BT) { s_fx[i] = 0; s_un[i] = 0; }
+    for (int i = tid; i < 64 * 8; i += BT) s_hist[i] = 0;
+    if (tid < 72) {
+        s_inv[tid] = tid ? __fdiv_rn(1.f, (float)tid) : 0.f;             // Compare.hpp:924: 1.f / numOfEntries, up to 64 taxa
+        s_q[tid] = tid >= 2 ? (uint32_t)(((1u << 24) + (tid >> 1)) / tid) : 0u;
+        s_q32[tid] = tid >= 2 ? inv_fx((uint32_t)tid) : 0u;
+    }
+    __syncthreads();
+    float wj[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { const int k = lp.k_low + j; wj[j] = (float)(k * k) / 625.f; }      // Compare.hpp:392
+
+    const uint32_t stride = gridDim.x * BT;
+#pragma unroll 1
+    for (uint32_t base = r0 + blockIdx.x * BT; base < r1; base += stride) {
+        const uint32_t r = base + tid;
+        const bool have = r < r1;
+        const uint4 *cur = reinterpret_cast<const uint4 *>(ws.ops + (have ? ws.ops_start[r] : 0));
+        uint32_t left = have ? ws.ops_count[r] / 4u : 0u;               // 16-byte blocks
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (left) nxt = __ldg(cur);
+        while (__any_sync(kFull, left > 0)) {
+            if (left) {
+                const uint4 g = nxt;
+                const uint32_t n0 = (g.x >> 24) & 127u, nup = (g.x >> 17) & 127u;
+                const uint32_t blocks = 1u + (nup > 1u ? (nup - 1u + 3u) / 4u : 0u);
+                if (left > blocks) nxt = __ldg(cur + blocks);            // next group: on its way while this one is applied
+                const float v0 = __fmul_rn(wj[0], s_inv[n0]);
+                const uint32_t q0 = s_q[n0];
+                uint64_t mk = ((uint64_t)g.z << 32) | g.y;
+                if (n0 == 1u) {
+                    const int c = __ffsll((long long)mk) - 1;
+                    cellS[c * BT + tid] = __fadd_rn(cellS[c * BT + tid], v0);
+                    atomicAdd(&s_un[c], 1u);
+                } else {
+                    // two taxa per iteration: distinct cells, independent read-modify-write chains
+                    while (mk) {
+                        const int c0 = __ffsll((long long)mk) - 1;
+                        mk &= mk - 1;
+                        const bool two = mk != 0;
+                        const int c1 = two ? __ffsll((long long)mk) - 1 : c0;
+                        mk &= mk - 1;
+                        const float a0 = cellS[c0 * BT + tid], a1 = cellS[c1 * BT + tid];
+                        const uint32_t f0 = cellF[c0 * BT + tid], f1 = cellF[c1 * BT + tid];
+                        cellS[c0 * BT + tid] = __fadd_rn(a0, v0);                         // Compare.hpp:530, level k_low
+                        cellF[c0 * BT + tid] = f0 + q0;
+                        if (two) { cellS[c1 * BT + tid] = __fadd_rn(a1, v0); cellF[c1 * BT + tid] = f1 + q0; }
+                    }
+                }
+                if (nup == 1u) {
+                    const uint32_t c = (g.w & 0xffffu) - 1u, h = g.w >> 16;
+                    float acc = cellS[c * BT + tid];
+#pragma unroll
+                    for (int j = 1; j < 6; ++j) if ((uint32_t)j < h) acc = __fadd_rn(acc, wj[j]);       // w * (1.f / 1) == w
+                    cellS[c * BT + tid] = acc;
+                    atomicAdd(&s_hist[c * 8 + (h & 7u)], 1u);
+                } else if (nup > 1u) {
+                    // several taxa above k_low: level sizes by counting the up pairs, then pair by pair
+                    const uint32_t *ups = reinterpret_cast<const uint32_t *>(cur + 1);
+                    uint64_t nlev = 0;                                   // 8 bits per level j = 1..5: number of up pairs with h > j
+                    for (uint32_t k = 0; k < nup; ++k) {
+                        const uint32_t h = (k ? __ldg(ups + k - 1) : g.w) >> 16;
+                        for (uint32_t j = 1; j < h && j < 6; ++j) nlev += 1ull << (8 * (j - 1));
+                    }
+                    for (uint32_t k = 0; k < nup; ++k) {
+                        const uint32_t e = k ? __ldg(ups + k - 1) : g.w;
+                        const uint32_t c = (e & 0xffffu) - 1u, h = e >> 16;
+                        float acc = cellS[c * BT + tid];
+                        for (uint32_t j = 1; j < h && j < 6; ++j) {
+                            const uint32_t nn = (uint32_t)(nlev >> (8 * (j - 1))) & 127u;
+                            acc = __fadd_rn(acc, __fmul_rn(wj[j], s_inv[nn]));
+                            if (nn == 1u) atomicAdd(&s_un[j * 64 + c], 1u);
+                            else atomicAdd(&s_fx[j * 64 + c], (unsigned long long)s_q32[nn]);
+                        }
+                        cellS[c * BT + tid] = acc;
+                    }
+                }
+                cur += blocks; left -= blocks;
+            }
+        }
+        // ---- end of the read: scores out, its k_low sums into the CTA's totals
+        if (have) {
+            for (int c = 0; c < NC && c < T - 1; ++c) {
+                if (scores) scores[(uint64_t)r * T + c + 1] = cellS[c * BT + tid];
+                cellS[c * BT + tid] = 0.f;
+                const uint32_t f = cellF[c * BT + tid];
+                if (f) { cellF[c * BT + tid] = 0u; atomicAdd(&s_fx[c], (unsigned long long)f << kFxShift); }
+            }
+            if (scores) scores[(uint64_t)r * T] = 0.f;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < NK * 64; i += BT) {
+        const int j = i / 64, c = i % 64;
+        if (c >= T - 1) continue;
+        unsigned long long u = s_un[i];
+        if (j >= 1) for (int h = j + 1; h < 8; ++h) u += s_hist[c * 8 + h];     // alone at the levels 1 .. h-1
+        if (u) atomicAdd(cnt_unique + (size_t)j * T + c + 1, u);
+        if (s_fx[i]) atomicAdd(cnt_fx + (size_t)j * T + c + 1, s_fx[i]);
     }
 }
 
@@ -825,19 +1006,25 @@ void launch_order_ops(cudaStream_t s, const uint64_t *rec, const uint64_t *read_
     uint32_t icap = 0, nb = 0, warps = kAMaxWarps;
     size_t wbytes = 0, sm = 0;
     const size_t budget = 224 * 1024;
+    const int count_levels = counts && !(!exact && ops_mask_stream(lp) && emit) ? lp.num_k : 0;
+    KASA_REQUIRE(!exact || cap <= 4096, -1, "KASA_SCORE_EXACT: a read has too many k-mers for the shared-memory replay; use KASA_SCORE_ORDERED for long reads");
+    // EXACT sorts (k-mer, level) items: at most cap * num_k of them, in practice far fewer (only levels with a hit); the kernel reports
+    // a read that does not fit (error 64)
+    uint32_t items = exact ? std::min<uint32_t>(cap * (uint32_t)lp.num_k, 65535u) : 0u;
     for (;;) {
-        icap = exact ? cap * (uint32_t)lp.num_k : cap;
+        icap = exact ? items : cap;
         nb = 64;
         while (nb < icap && nb < 4096) nb <<= 1;
-        wbytes = warp_mem_bytes(cap, icap, nb, exact, counts ? lp.num_k : 0);
+        wbytes = warp_mem_bytes(cap, icap, nb, count_levels);
         sm = wbytes * warps;
         if (sm <= budget) break;
         if (!exact && cap > 512) { cap = (cap / 2 + 31) & ~31u; continue; }
         if (warps > 1) { warps >>= 1; continue; }
+        if (exact && items > 2 * cap) { items = items * 3 / 4; continue; }
         if (!exact && cap > 64) { cap = (cap / 2 + 31) & ~31u; continue; }
         break;
     }
-    if (sm > budget || icap > 65535)      // KASA_SCORE_EXACT keeps a whole read in shared memory
+    if (sm > budget)
         throw Error{-1, "KASA_SCORE_EXACT: a read has too many (k-mer, level) pairs for the shared-memory replay; use KASA_SCORE_ORDERED for long reads"};
     auto go = [&](auto kern) {
         KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -848,8 +1035,10 @@ void launch_order_ops(cudaStream_t s, const uint64_t *rec, const uint64_t *read_
         if (grid > resident) grid = resident;
         kern<<<grid, warps * 32, sm, s>>>(rec, read_koff, r0, r1, n_kmers, lp, peers, ws, trig, err_flag, cap, icap, nb, (uint32_t)wbytes, cnt_fx, cnt_unique, emit || !counts);
     };
-    if (exact) { if (counts) go(order_ops_kernel<true, true>); else go(order_ops_kernel<true, false>); }
-    else { if (counts) go(order_ops_kernel<false, true>); else go(order_ops_kernel<false, false>); }
+    const bool masks = !exact && ops_mask_stream(lp) && counts && emit;       // mask stream: small taxonomy scored densely; counts in kernel B
+    if (exact) { if (counts) go(order_ops_kernel<1, true>); else go(order_ops_kernel<1, false>); }
+    else if (masks) go(order_ops_kernel<2, false>);
+    else { if (counts) go(order_ops_kernel<0, true>); else go(order_ops_kernel<0, false>); }
     ++*launches;
     KASA_CUDA_TRY(cudaGetLastError());
 }
@@ -860,7 +1049,20 @@ void launch_accumulate(cudaStream_t s, OpsWorkspace ws, uint32_t r0, uint32_t r1
     if (r1 <= r0) return;
     if (lp.n_taxa <= kMaskTaxa && !hits.taxon) {
         // the counts of these reads were taken by launch_order_ops(counts = true)
-        if (lp.n_taxa <= 33) launch_dense<1>(s, ws, r0, r1, lp, exact_stream, scores); else launch_dense<2>(s, ws, r0, r1, lp, exact_stream, scores);
+        if (!exact_stream && ops_mask_stream(lp)) {
+            auto go = [&](auto kern, int nc) {
+                const size_t sm = (size_t)nc * kMaskBlock * 8;
+                KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                int per_sm = 1;
+                KASA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMaskBlock, sm));
+                unsigned grid = (unsigned)div_up<uint64_t>(r1 - r0, kMaskBlock);
+                const unsigned resident = (unsigned)(kSMs * (per_sm > 0 ? per_sm : 1));
+                if (grid > resident) grid = resident;
+                kern<<<grid, kMaskBlock, sm, s>>>(ws, r0, r1, lp, scores, cnt_fx, cnt_unique);
+            };
+            if (lp.n_taxa <= 33) go(accumulate_mask_kernel<1>, 32); else go(accumulate_mask_kernel<2>, 64);
+        } else if (lp.n_taxa <= 33) launch_dense<1>(s, ws, r0, r1, lp, exact_stream, scores);
+        else launch_dense<2>(s, ws, r0, r1, lp, exact_stream, scores);
     } else {
         unsigned grid = (unsigned)div_up<uint64_t>(r1 - r0, kHWarps);
         if (grid > (unsigned)kSMs * 8) grid = kSMs * 8;

@@ -29,6 +29,10 @@ constexpr uint32_t kOpHeader = 1u << 31;
 constexpr uint32_t kOpNExt = 1023u;
 constexpr uint32_t kOpNibExt = 15u;
 __host__ __device__ __forceinline__ int ops_extra_words(int num_k) { return num_k > 6 ? (num_k - 6 + 7) / 8 : 0; }
+// mask stream (KASA_SCORE_ORDERED with <= 64 taxa and <= 6 levels — the default k = 12..7 against a small content file): 16-byte groups
+//   [header | |taxa_klow| << 24 | nup << 17][taxa mask lo][taxa mask hi][up pair 0]  + blocks of four further up pairs when nup > 1,
+//   an up pair = taxon | levels << 16 for a taxon that matches more than the k_low level (score.cu accumulate_mask_kernel)
+inline bool ops_mask_stream(const LevelParams &lp) { return lp.n_taxa <= kMaskTaxa && lp.num_k <= 6; }
 
 struct OpsWorkspace {
     uint32_t *ops;                    // op streams, one contiguous run per read (start multiple of 4)

@@ -232,7 +232,9 @@ def test_profile_only_mode_gives_same_counts():
         ctx.identify_batch(reads)
         out.append(ctx.identify_finish())
         ctx.close()
-    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    # the shared k_low hits are summed in 2^-32 fixed point by the profile-only path and in 2^-24 per read by the scoring path
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=COUNT_RTOL)
 
 
 # ----------------------------------------------------------------------------------------- build
