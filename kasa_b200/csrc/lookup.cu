@@ -435,7 +435,10 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
         if (r * kLookupBlock >= (int)tq) break;             // CTA-uniform
         if (!live[r]) continue;
         const uint64_t rank = rank_base + tile * tq + (uint64_t)(r * kLookupBlock + tid);
-        uint64_t out[4] = {rank & 0xffffffffull, 0, 0, 0};
+        // the record stays in registers on the common paths; only the general path (out of line) goes through an array
+        uint64_t o0 = rank & 0xffffffffull, o1 = 0, o2 = 0, o3 = 0;
+        bool general = false;
+        int64_t gen_g0 = 0, gen_b = 0;
         if (staged && MASK) {
             if (mask[r]) {
                 uint64_t uw[2] = {0, 0};
@@ -447,17 +450,14 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
                     hmax = max(hmax, h);
                 }
                 if (fits) {
-                    out[0] = rec_head(rank, (uint32_t)__popcll(mask[r]), hmax, false, owner) | kRecMaskBit;
-                    out[1] = mask[r]; out[2] = uw[0]; out[3] = uw[1];
-                } else {
-                    match_general<W>(sacc, (int64_t)g0[r], (int64_t)span, qv[r], kv[r], lp, ovf, owner, err_flag, rank, out);
-                }
+                    o0 = rec_head(rank, (uint32_t)__popcll(mask[r]), hmax, false, owner) | kRecMaskBit;
+                    o1 = mask[r]; o2 = uw[0]; o3 = uw[1];
+                } else { general = true; gen_g0 = g0[r]; gen_b = span; }
             }
         } else if (staged) {
             const uint32_t c = cnt[r];
-            if (c > (uint32_t)kRecInline) {
-                match_general<W>(sacc, (int64_t)g0[r], (int64_t)span, qv[r], kv[r], lp, ovf, owner, err_flag, rank, out);
-            } else if (c) {
+            if (c > (uint32_t)kRecInline) { general = true; gen_g0 = g0[r]; gen_b = span; }
+            else if (c) {
                 uint64_t pw[3];
 #pragma unroll
                 for (int w = 0; w < 3; ++w) pw[w] = c > 3u * w ? st.pw[w][MASK ? 0 : r * kLookupBlock + tid] : 0ull;
@@ -467,16 +467,21 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
                     pair_raise(pw, c, sacc.tax[e], h);
                     hmax = max(hmax, h);
                 }
-                out[0] = rec_head(rank, c, hmax, false, owner); out[1] = pw[0]; out[2] = pw[1]; out[3] = pw[2];
+                o0 = rec_head(rank, c, hmax, false, owner); o1 = pw[0]; o2 = pw[1]; o3 = pw[2];
             }
         } else if ((act >> r) & 1u) {
+            uint64_t out[4];
             const int64_t gg = lower_bound<W>(gacc, a, b, prefix_floor<W>(qv[r], low_sh));
             match_general<W>(gacc, gg, b, qv[r], kv[r], lp, ovf, owner, err_flag, rank, out);
+            o0 = out[0]; o1 = out[1]; o2 = out[2]; o3 = out[3];
+        }
+        if (general) {
+            uint64_t out[4];
+            match_general<W>(sacc, gen_g0, gen_b, qv[r], kv[r], lp, ovf, owner, err_flag, rank, out);
+            o0 = out[0]; o1 = out[1]; o2 = out[2]; o3 = out[3];
         }
         // one 256-bit store = one full 32-byte sector per record (STG.256, sm_100)
-        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)iv[r] * kRecWords), "l"(out[0]), "l"(out[1]), "l"(out[2]),
-                     "l"(out[3])
-                     : "memory");
+        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (uint64_t)iv[r] * kRecWords), "l"(o0), "l"(o1), "l"(o2), "l"(o3) : "memory");
     }
 }
 

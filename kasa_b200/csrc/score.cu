@@ -55,7 +55,7 @@ struct WarpMem {
 
 __host__ __device__ inline size_t warp_mem_bytes(uint32_t cap, uint32_t icap, uint32_t nb, int count_levels)
 {
-    size_t b = (size_t)32 * cap + (size_t)8 * icap + (size_t)4 * (nb + 1) + (size_t)256 * count_levels + (size_t)6 * icap;
+    size_t b = (size_t)32 * cap + (size_t)8 * icap + (size_t)4 * (nb + 1) + (count_levels ? (size_t)256 * count_levels + 512 : 0) + (size_t)4 * icap;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -126,19 +126,19 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
         M.key = reinterpret_cast<uint64_t *>(M.rhi + cap);
         M.bcnt = reinterpret_cast<uint32_t *>(M.key + icap);
         M.un = M.bcnt + nb + 1;
-        M.tmp = reinterpret_cast<uint16_t *>(M.un + (COUNTS ? 64 * NK : 0));
+        M.tmp = reinterpret_cast<uint16_t *>(M.un + (COUNTS ? 64 * NK + 128 : 0));
         M.ord = M.tmp + icap;
-        M.arr = M.ord + icap;
+        M.arr = M.ord;          // the arrival index of an item is consumed before its final position is written
     }
     const uint32_t n_warps = blockDim.x >> 5;
     const uint32_t warps_total = gridDim.x * n_warps;
     const uint32_t NX = STREAM == 0 ? (uint32_t)ops_extra_words(NK) : 0u;
     // level k_low: 2^-32 sums and unique hits of this lane's two taxa over all the warp's reads
     unsigned long long fx0a = 0, fx0b = 0, un0a = 0, un0b = 0;
-    __shared__ uint32_t s_invfx[kAMaxWarps][128];
+    uint32_t *s_invfx_w = M.un + 64 * NK;                              // [128] 2^32 / n (COUNTS only)
     if (COUNTS) {
         for (int i = lane; i < NK * 64; i += 32) M.un[i] = 0;
-        for (int i = lane; i < 128; i += 32) s_invfx[w][i] = i >= 2 ? inv_fx((uint32_t)i) : 0u;
+        for (int i = lane; i < 128; i += 32) s_invfx_w[i] = i >= 2 ? inv_fx((uint32_t)i) : 0u;
     }
     __syncwarp();
 
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
             if (rec_is_mask(w0)) {
                 const uint64_t mk = a.y;
                 const uint32_t in0 = (uint32_t)(mk >> lane) & 1u, in1 = (uint32_t)(mk >> (lane + 32)) & 1u;
-                const uint32_t one = c == 1u ? 1u : 0u, f = s_invfx[w][c & 127u];
+                const uint32_t one = c == 1u ? 1u : 0u, f = s_invfx_w[c & 127u];
                 un0a += in0 & one; un0b += in1 & one;
                 fx0a += (unsigned long long)(in0 * f); fx0b += (unsigned long long)(in1 * f);
                 if (hmax > 1u) {
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
                                 for (uint32_t j = 1; j < h; ++j) {
                                     const uint32_t nn = nib_get(lo, hi, j);
                                     if (nn == 1u) M.un[j * 64 + t] += 1u;
-                                    else atomicAdd(cnt_fx + (size_t)j * T + t + 1, (unsigned long long)s_invfx[w][nn & 127u]);
+                                    else atomicAdd(cnt_fx + (size_t)j * T + t + 1, (unsigned long long)s_invfx_w[nn & 127u]);
                                 }
                             }
                         }
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
                         for (uint32_t j = 0; j < h; ++j) ++nj[j];
                     }
                 }
-                const uint32_t f0 = c >= 2u ? (c < 128u ? s_invfx[w][c] : inv_fx(c)) : 0u;
+                const uint32_t f0 = c >= 2u ? (c < 128u ? s_invfx_w[c] : inv_fx(c)) : 0u;
                 for (uint32_t k = 0; k < c; ++k) {
                     const uint32_t e = ovf ? __ldg(list + k) : (uint32_t)(pw[k / 3] >> (kPairBits * (k % 3))) & kPairMask;
                     const uint32_t t = (e & 0xffffu) - 1u, h = e >> 16;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kAMaxWarps * 32) order_ops_kernel(const uint64
                     else { if (t >> 5) fx0b += f0; else fx0a += f0; }
                     for (uint32_t j = 1; j < h; ++j) {
                         if (nj[j] == 1u) M.un[j * 64 + t] += 1u;
-                        else atomicAdd(cnt_fx + (size_t)j * T + t + 1, (unsigned long long)(nj[j] < 128u ? s_invfx[w][nj[j]] : inv_fx(nj[j])));
+                        else atomicAdd(cnt_fx + (size_t)j * T + t + 1, (unsigned long long)(nj[j] < 128u ? s_invfx_w[nj[j]] : inv_fx(nj[j])));
                     }
                 }
             }
@@ -574,15 +574,16 @@ __global__ void __launch_bounds__(kMaskBlock) accumulate_mask_kernel(OpsWorkspac
     constexpr int NC = 32 * SLOTS, BT = kMaskBlock;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, T = lp.n_taxa, NK = lp.num_k;
-    float *cellS = reinterpret_cast<float *>(smem_raw);                 // [NC][BT] score of the thread's read
-    uint32_t *cellF = reinterpret_cast<uint32_t *>(cellS + NC * BT);    // [NC][BT] sum of 1 / n0 over the read's k-mers with n0 >= 2, 2^-24 units
+    // [NC][BT] per thread and taxon: .x = score of the thread's read (float bits), .y = sum of 1 / n0 over the read's k-mers with
+    // n0 >= 2 in 2^-24 units — one 8-byte shared-memory access reads or writes both
+    uint2 *cell = reinterpret_cast<uint2 *>(smem_raw);
     __shared__ float s_inv[72];
     __shared__ uint32_t s_q[72];                                        // 2^24 / n rounded to nearest (0 for n < 2)
     __shared__ uint32_t s_q32[72];                                      // 2^32 / n
     __shared__ unsigned long long s_fx[6 * 64];                         // CTA totals [level][taxon - 1], 2^-32 units
     __shared__ uint32_t s_un[6 * 64];
     __shared__ uint32_t s_hist[64 * 8];                                 // [taxon - 1][h]: k-mers where the taxon is alone at its levels 1 .. h-1
-    for (int i = tid; i < NC * BT; i += BT) { cellS[i] = 0.f; cellF[i] = 0u; }
+    for (int i = tid; i < NC * BT; i += BT) cell[i] = make_uint2(0u, 0u);
     for (int i = tid; i < 6 * 64; i += BT) { s_fx[i] = 0; s_un[i] = 0; }
     for (int i = tid; i < 64 * 8; i += BT) s_hist[i] = 0;
     if (tid < 72) {
@@ -615,29 +616,33 @@ __global__ void __launch_bounds__(kMaskBlock) accumulate_mask_kernel(OpsWorkspac
                 uint64_t mk = ((uint64_t)g.z << 32) | g.y;
                 if (n0 == 1u) {
                     const int c = __ffsll((long long)mk) - 1;
-                    cellS[c * BT + tid] = __fadd_rn(cellS[c * BT + tid], v0);
+                    uint2 x = cell[c * BT + tid];
+                    x.x = __float_as_uint(__fadd_rn(__uint_as_float(x.x), v0));
+                    cell[c * BT + tid] = x;
                     atomicAdd(&s_un[c], 1u);
                 } else {
-                    // two taxa per iteration: distinct cells, independent read-modify-write chains
+                    // four taxa per iteration: distinct cells, independent read-modify-write chains (Compare.hpp:530, level k_low)
                     while (mk) {
-                        const int c0 = __ffsll((long long)mk) - 1;
-                        mk &= mk - 1;
-                        const bool two = mk != 0;
-                        const int c1 = two ? __ffsll((long long)mk) - 1 : c0;
-                        mk &= mk - 1;
-                        const float a0 = cellS[c0 * BT + tid], a1 = cellS[c1 * BT + tid];
-                        const uint32_t f0 = cellF[c0 * BT + tid], f1 = cellF[c1 * BT + tid];
-                        cellS[c0 * BT + tid] = __fadd_rn(a0, v0);                         // Compare.hpp:530, level k_low
-                        cellF[c0 * BT + tid] = f0 + q0;
-                        if (two) { cellS[c1 * BT + tid] = __fadd_rn(a1, v0); cellF[c1 * BT + tid] = f1 + q0; }
+                        int c[4];
+                        bool on[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { on[u] = mk != 0; c[u] = on[u] ? __ffsll((long long)mk) - 1 : 0; mk &= mk - 1; }
+                        uint2 x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) x[u] = cell[c[u] * BT + tid];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (on[u]) cell[c[u] * BT + tid] = make_uint2(__float_as_uint(__fadd_rn(__uint_as_float(x[u].x), v0)), x[u].y + q0);
                     }
                 }
                 if (nup == 1u) {
                     const uint32_t c = (g.w & 0xffffu) - 1u, h = g.w >> 16;
-                    float acc = cellS[c * BT + tid];
+                    uint2 x = cell[c * BT + tid];
+                    float acc = __uint_as_float(x.x);
 #pragma unroll
                     for (int j = 1; j < 6; ++j) if ((uint32_t)j < h) acc = __fadd_rn(acc, wj[j]);       // w * (1.f / 1) == w
-                    cellS[c * BT + tid] = acc;
+                    x.x = __float_as_uint(acc);
+                    cell[c * BT + tid] = x;
                     atomicAdd(&s_hist[c * 8 + (h & 7u)], 1u);
                 } else if (nup > 1u) {
                     // several taxa above k_low: level sizes by counting the up pairs, then pair by pair
@@ -645,19 +650,21 @@ __global__ void __launch_bounds__(kMaskBlock) accumulate_mask_kernel(OpsWorkspac
                     uint64_t nlev = 0;                                   // 8 bits per level j = 1..5: number of up pairs with h > j
                     for (uint32_t k = 0; k < nup; ++k) {
                         const uint32_t h = (k ? __ldg(ups + k - 1) : g.w) >> 16;
-                        for (uint32_t j = 1; j < h && j < 6; ++j) nlev += 1ull << (8 * (j - 1));
+                        nlev += (h >= 6u ? 0x0101010101ull : ((1ull << (8 * (h - 1))) - 1) & 0x0101010101ull);
                     }
                     for (uint32_t k = 0; k < nup; ++k) {
                         const uint32_t e = k ? __ldg(ups + k - 1) : g.w;
                         const uint32_t c = (e & 0xffffu) - 1u, h = e >> 16;
-                        float acc = cellS[c * BT + tid];
+                        uint2 x = cell[c * BT + tid];
+                        float acc = __uint_as_float(x.x);
                         for (uint32_t j = 1; j < h && j < 6; ++j) {
                             const uint32_t nn = (uint32_t)(nlev >> (8 * (j - 1))) & 127u;
                             acc = __fadd_rn(acc, __fmul_rn(wj[j], s_inv[nn]));
                             if (nn == 1u) atomicAdd(&s_un[j * 64 + c], 1u);
                             else atomicAdd(&s_fx[j * 64 + c], (unsigned long long)s_q32[nn]);
                         }
-                        cellS[c * BT + tid] = acc;
+                        x.x = __float_as_uint(acc);
+                        cell[c * BT + tid] = x;
                     }
                 }
                 cur += blocks; left -= blocks;
@@ -666,10 +673,10 @@ __global__ void __launch_bounds__(kMaskBlock) accumulate_mask_kernel(OpsWorkspac
         // ---- end of the read: scores out, its k_low sums into the CTA's totals
         if (have) {
             for (int c = 0; c < NC && c < T - 1; ++c) {
-                if (scores) scores[(uint64_t)r * T + c + 1] = cellS[c * BT + tid];
-                cellS[c * BT + tid] = 0.f;
-                const uint32_t f = cellF[c * BT + tid];
-                if (f) { cellF[c * BT + tid] = 0u; atomicAdd(&s_fx[c], (unsigned long long)f << kFxShift); }
+                const uint2 x = cell[c * BT + tid];
+                if (scores) scores[(uint64_t)r * T + c + 1] = __uint_as_float(x.x);
+                if (x.x | x.y) cell[c * BT + tid] = make_uint2(0u, 0u);
+                if (x.y) atomicAdd(&s_fx[c], (unsigned long long)x.y << kFxShift);
             }
             if (scores) scores[(uint64_t)r * T] = 0.f;
         }
@@ -1015,6 +1022,7 @@ void launch_order_ops(cudaStream_t s, const uint64_t *rec, const uint64_t *read_
         icap = exact ? items : cap;
         nb = 64;
         while (nb < icap && nb < 4096) nb <<= 1;
+        if (nb > 256 && icap <= 512) nb = 256;                  // short reads: 256 buckets (about one item each) keep four CTAs on an SM
         wbytes = warp_mem_bytes(cap, icap, nb, count_levels);
         sm = wbytes * warps;
         if (sm <= budget) break;
