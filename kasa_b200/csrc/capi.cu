@@ -31,6 +31,8 @@ struct kasa_ctx {
     uint64_t launches = 0;
     int K = 12, num_k = 6;
     int sort_bits = 0;                  // leading k-mer bits identify sorts (tuning knob KASA_TUNE_SORT_BITS)
+    bool score_sorted = true;           // presorted batches are scored straight from the records (KASA_TUNE_SCORE_SORTED=0: always via op streams)
+    int score_lanes = 0;                // threads per read of that kernel (KASA_TUNE_SCORE_LANES; 0 = default)
     bool wide = false;
     std::vector<void *> allocs;
 
@@ -60,6 +62,7 @@ struct kasa_ctx {
     uint64_t idx_n = 0;
     uint64_t *idx_lo = nullptr, *idx_hi = nullptr;
     uint16_t *idx_tax = nullptr;
+    uint64_t *idx_gmask = nullptr;      // taxa mask of every entry's k_low group (content files of <= 64 taxa; lookup.cuh IndexDev)
     uint32_t n_taxa = 0;
     bool dense_scores = false;
     uint32_t batch_epoch = 0;
@@ -317,7 +320,8 @@ void set_taxa(kasa_ctx *c, uint32_t n_taxa)
 
 void drop_index(kasa_ctx *c)
 {
-    dev_free(c, c->idx_lo); dev_free(c, c->idx_hi); dev_free(c, c->idx_tax);
+    dev_free(c, c->idx_lo); dev_free(c, c->idx_hi); dev_free(c, c->idx_tax); dev_free(c, c->idx_gmask);
+    c->idx_gmask = nullptr;
     dev_free(c, c->ovf.data); c->ovf.data = nullptr;
     for (auto &sl : c->slot) {
         dev_free(c, sl.hit_taxon); dev_free(c, sl.hit_score); dev_free(c, sl.hit_begin); dev_free(c, sl.hit_count); dev_free(c, sl.hit_cursor);
@@ -450,6 +454,8 @@ int kasa_ctx_create(const kasa_params *p, kasa_ctx **out)
         c->num_k = p->k_high - p->k_low + 1;
         c->sort_bits = kIdentifySortBits;
         if (const char *e = getenv("KASA_TUNE_SORT_BITS")) c->sort_bits = std::min(5 * c->K, std::max(8, atoi(e)));
+        if (const char *e = getenv("KASA_TUNE_SCORE_SORTED")) c->score_sorted = atoi(e) != 0;
+        if (const char *e = getenv("KASA_TUNE_SCORE_LANES")) c->score_lanes = atoi(e);
         KASA_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
         KASA_CUDA_TRY(cudaStreamCreateWithFlags(&c->cs_in, cudaStreamNonBlocking));
@@ -530,6 +536,25 @@ int kasa_ctx_stage_times(kasa_ctx *c, double *ms, uint64_t *batches, uint64_t *s
 }
 uint64_t kasa_index_size(const kasa_ctx *c) { return c ? c->idx_n : 0; }
 
+// Last step of every index load: the taxon-first flags (any number of taxa) and, for content files of <= 64 taxa, the taxa mask of
+// every k_low-letter group (markTaxIDs of level k_low, Compare.hpp:396-441, done once instead of once per query).
+static void finalize_index(kasa_ctx *c, uint64_t n)
+{
+    launch_index_flags(c->stream, c->idx_lo, c->idx_hi, c->idx_tax, n, c->K, c->p.k_low, &c->launches);
+    if (c->n_taxa > (uint32_t)kMaskTaxa || n == 0) return;
+    c->idx_gmask = dev_alloc<uint64_t>(c, n + 16);
+    uint64_t *tmp = dev_alloc<uint64_t>(c, scan_tmp_elems(n) + 1);
+    launch_group_heads(c->stream, c->idx_lo, c->idx_hi, n, c->K, c->p.k_low, c->idx_gmask, &c->launches);
+    exclusive_scan_u64(c->stream, c->idx_gmask, n, tmp, &c->launches);
+    const uint64_t groups = read_u64(c, c->idx_gmask + n);
+    uint64_t *gm = dev_alloc<uint64_t>(c, groups + 1);
+    KASA_CUDA_TRY(cudaMemsetAsync(gm, 0, (groups + 1) * 8, c->stream));
+    launch_group_masks(c->stream, c->idx_lo, c->idx_hi, c->idx_tax, n, c->K, c->p.k_low, gm, c->idx_gmask, &c->launches);
+    KASA_CUDA_TRY(cudaMemsetAsync(c->idx_gmask + n, 0, 16 * 8, c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    dev_free(c, gm); dev_free(c, tmp);
+}
+
 int kasa_index_load(kasa_ctx *c, const void *entries, uint64_t n, int bits, const uint32_t *taxid_of_idx, uint32_t n_taxa)
 {
     KASA_API_BEGIN
@@ -550,7 +575,7 @@ int kasa_index_load(kasa_ctx *c, const void *entries, uint64_t n, int bits, cons
     launch_check_sorted(c->stream, c->idx_lo, c->idx_hi, d_tax32, n, c->d_err, &c->launches);
     TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
     launch_map_taxids(c->stream, d_tax32, n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
-    launch_index_flags(c->stream, c->idx_lo, c->idx_hi, c->idx_tax, n, c->K, c->p.k_low, &c->launches);
+    finalize_index(c, n);
     KASA_CUDA_TRY(cudaGetLastError());
     check_device_flags(c);
     dev_free(c, d_words); dev_free(c, d_tax32); dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
@@ -575,7 +600,7 @@ int kasa_index_from_build(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_
     if (c->wide) KASA_CUDA_TRY(cudaMemcpyAsync(c->idx_hi, c->sb.w1[b], n * 8, cudaMemcpyDeviceToDevice, c->stream));
     TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
     launch_map_taxids(c->stream, c->sb.v[b], n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
-    launch_index_flags(c->stream, c->idx_lo, c->idx_hi, c->idx_tax, n, c->K, c->p.k_low, &c->launches);
+    finalize_index(c, n);
     KASA_CUDA_TRY(cudaGetLastError());
     check_device_flags(c);
     dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
@@ -655,9 +680,10 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
     KASA_REQUIRE(n <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "batch yields more k-mers than max_batch_kmers");
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[1], c->stream));
     if (in->format == KASA_SEQ_ASCII)
-        launch_extract_identify_ascii(c->stream, ascii, seq_start, seq_len, ns, kp, c->d_codon, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
+        launch_extract_identify_ascii(c->stream, ascii, seq_start, seq_len, ns, kp, c->d_codon, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], *read_first,
+                                      in->n_reads, mi, &c->launches);
     else
-        launch_extract_identify(c->stream, ps, kp, c->d_codon, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
+        launch_extract_identify(c->stream, ps, kp, c->d_codon, c->d_koff, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], *read_first, in->n_reads, mi, &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     return n;
 }
@@ -678,7 +704,7 @@ static void score_stage(kasa_ctx *c, kasa_ctx::Slot &sl, uint64_t n, uint32_t n_
             c->xws.trig = dev_alloc<uint32_t>(c, cap * c->num_k + 1);
             c->xws_ready = true;
         }
-        IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n};
+        IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n, c->idx_gmask};
         launch_exact_triggers(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, idx, lp, c->d_rec, c->xws, &c->launches);
         trig = c->xws.trig;
     }
@@ -690,9 +716,19 @@ static void score_stage(kasa_ctx *c, kasa_ctx::Slot &sl, uint64_t n, uint32_t n_
         hits = HitsOut{sl.hit_taxon, sl.hit_score, sl.hit_begin, sl.hit_count, sl.hit_cursor, c->p.max_batch_hits};
         KASA_CUDA_TRY(cudaMemsetAsync(sl.hit_cursor, 0, 8, c->stream));
     }
+    // Presorted batch (every read was emitted in ascending k-mer order, extract.cuh) against a small content file: the records lie
+    // in summation order, scores and counts come straight from them.
+    if (!exact && !want_hits && ops_mask_stream(lp) && max_inst <= (uint32_t)kPresortMax && c->score_sorted) {
+        launch_score_sorted(c->stream, c->d_rec, c->d_read_koff, n_reads, lp, peers, want_dense ? sl.scores : nullptr, c->d_cnt_fx, c->d_cnt_un,
+                            c->score_lanes, &c->launches);
+        launch_fold_counts(c->stream, c->d_cnt_fx, c->d_cnt_un, lp, c->d_tot_all, c->d_tot_un, &c->launches);
+        return;
+    }
     // The op streams live in the sort slab (6 words per k-mer of capacity for 64-bit k-mers); the reads are scored in four
     // chunks, so a batch may average ~24 (taxon, read k-mer) pairs per k-mer before the workspace is the limit.
-    const uint32_t n_chunks = n_reads >= 4096 ? 4 : 1;
+    // KASA_SCORE_EXACT writes one group per (instance, level): up to ~2 num_k words per k-mer, hence more and smaller chunks.
+    uint32_t n_chunks = n_reads >= 4096 ? 4 : 1;
+    if (exact) n_chunks = std::max<uint32_t>(1, std::min<uint32_t>(n_reads, std::max<uint32_t>(n_chunks, 2u * (uint32_t)c->num_k)));
     for (uint32_t ch = 0; ch < n_chunks; ++ch) {
         const uint32_t r0 = (uint32_t)((uint64_t)n_reads * ch / n_chunks), r1 = (uint32_t)((uint64_t)n_reads * (ch + 1) / n_chunks);
         KASA_CUDA_TRY(cudaMemsetAsync(c->ops.cursors, 0, 16, c->stream));
@@ -786,7 +822,7 @@ int kasa_identify_submit(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resu
         const int cur = radix_sort(c->stream, c->sb, 0, n, plan, c->sort_ws, c->d_err, &c->launches, sl.sev[3]);
         KASA_CUDA_TRY(cudaEventRecord(sl.sev[4], c->stream));
         launch_read_offsets(c->stream, c->d_koff, first, in->n_reads, c->d_read_koff, &c->launches);
-        IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n};
+        IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n, c->idx_gmask};
         LevelParams lp = level_params(c);
         const uint32_t tq = lookup_tile_queries(n, c->idx_n);
         KASA_CUDA_TRY(cudaMemsetAsync(c->ovf.cursor, 0, 8, c->stream));
@@ -1034,7 +1070,7 @@ int kasa_index_from_build_shard(kasa_ctx *c, const uint32_t *taxid_of_idx, uint3
     if (c->wide) KASA_CUDA_TRY(cudaMemcpyAsync(c->idx_hi, c->sb.w1[b] + o, n * 8, cudaMemcpyDeviceToDevice, c->stream));
     TaxTable tt = upload_tax_table(c, taxid_of_idx, n_taxa);
     launch_map_taxids(c->stream, c->sb.v[b] + o, n, tt.d_taxid, tt.d_idx, tt.n, c->idx_tax, c->d_err, &c->launches);
-    launch_index_flags(c->stream, c->idx_lo, c->idx_hi, c->idx_tax, n, c->K, c->p.k_low, &c->launches);
+    finalize_index(c, n);
     KASA_CUDA_TRY(cudaGetLastError());
     check_device_flags(c);
     dev_free(c, tt.d_taxid); dev_free(c, tt.d_idx);
@@ -1189,7 +1225,7 @@ int kasa_shard_lookup(kasa_ctx *c, const kasa_shard_runs *all)
     KASA_REQUIRE(c->sh.on && c->sh.phase == 1, KASA_ERR_STATE, "kasa_shard_lookup must follow kasa_shard_sort");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
     kasa_ctx::Slot &sl = c->slot[0];
-    IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n};
+    IndexDev idx{c->idx_lo, c->idx_hi, c->idx_tax, c->idx_n, c->idx_gmask};
     LevelParams lp = level_params(c);
     const int sorted_from = std::max(0, 5 * c->K - c->sort_bits);
     const int me = c->sh.rank;

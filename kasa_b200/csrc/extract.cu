@@ -1,4 +1,6 @@
 // extract.cu — see extract.cuh.
+#include <algorithm>
+
 #include "extract.cuh"
 
 namespace kasa {
@@ -83,16 +85,35 @@ __device__ __forceinline__ uint32_t code_at(const uint32_t *__restrict__ b2, con
     return isn ? 5u : (strand ? (two ^ 2u) : two);            // complement A0<->T2, C1<->G3 (kASA.hpp:54)
 }
 
-// One warp per sequence.  For each strand and each segment of kSegR output positions:
+// One warp per READ (all its sequences: both mates of a pair).  For each sequence, strand and segment of kSegR output positions:
 //   1. base codes of the prepared string (read / reverse complement + 'X' marker, Read.hpp:612-695) into shared
 //      memory — straight from the ASCII bytes (coalesced byte loads, cleaning of Read.hpp:657-675 on the fly) or
 //      from the 2-bit planes;
 //   2. letters: aa[j] = codon table[c_j, c_j+1, c_j+2];
-//   3. rolling k-mers: lane l owns 8 positions of one reading frame (j0, j0+3, ...): the first k-mer is assembled
+//   3. rolling k-mers: lane l owns 5 positions of one reading frame (j0, j0+3, ...): the first k-mer is assembled
 //      from K letters, each following one is (kmer << 5 | next letter) & mask — 3 instructions instead of 3 K;
-//   4. the segment's k-mers leave through shared memory as coalesced 8-byte stores; inst[i] = i.
+//   4. the k-mers leave through shared memory as coalesced 8-byte stores; inst[i] = i.
+// PRESORTED EMISSION.  The reference scores a read's k-mers in the order of its sorted k-mer vector (Compare.hpp:1077, 917-955),
+// and a float32 running sum depends on that order (score.cuh).  A read of at most kPresortMax k-mers is therefore emitted with its
+// k-mers ALREADY in ascending order: all of them are collected in the warp's shared memory and ordered there (512 buckets on the
+// leading nine key bits, then ranks inside each bucket by counting — ~2 comparisons per k-mer for ordinary reads, quadratic only
+// for a read that is one repeated letter) before they are stored.  The batch sort is stable, so the match records of such a read
+// come back in slot order = k-mer order, and the scoring stage replays them without ordering anything.  Longer reads keep the
+// reference's emission order (forward strand, then reverse strand, per sequence) and are ordered by rank later (order_ops_kernel).
 constexpr int kRoll = 5;                         // same-frame positions per lane
 constexpr int kSegR = 30 * kRoll;                // 150 output positions per segment: one segment per strand of a 150 bp read
+#ifndef KASA_SORT_BUCKET_BITS
+#define KASA_SORT_BUCKET_BITS 9                  // 9: 4 KB less shared memory per warp than 10 (= two letters), 3 instead of 2 CTAs per SM
+#endif
+constexpr int kSortBucketBits = KASA_SORT_BUCKET_BITS;
+constexpr int kSortBuckets = 1 << kSortBucketBits;
+
+// dynamic shared memory of one warp: 2 x [cap] low words, 2 x [cap] high words (WIDE), [kSortBuckets + 4] bucket counters, [cap] u32, codes, letters
+__host__ __device__ inline size_t extract_warp_bytes(bool wide, uint32_t cap)
+{
+    size_t b = (size_t)cap * (wide ? 32 : 16) + (size_t)4 * (kSortBuckets + 4) + (size_t)4 * cap + 2 * (size_t)(kSegR + kAaPad + 8);
+    return (b + 15) & ~(size_t)15;
+}
 
 template <bool WIDE, bool ASCII>
 __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(PackedSeqs seqs, const char *__restrict__ ascii,
@@ -101,77 +122,166 @@ __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(Pa
                                                                               uint64_t *__restrict__ key_lo,
                                                                               uint64_t *__restrict__ key_hi,
                                                                               uint32_t *__restrict__ inst,
-                                                                              const uint8_t *__restrict__ codon)
+                                                                              const uint8_t *__restrict__ codon,
+                                                                              const uint32_t *__restrict__ read_first, uint32_t n_reads,
+                                                                              uint32_t cap, uint32_t wbytes)
 {
-    __shared__ uint8_t s_code[kExtractWarps][kSegR + kAaPad + 8];
-    __shared__ uint8_t s_aa[kExtractWarps][kSegR + kAaPad];
-    __shared__ uint64_t s_klo[kExtractWarps][kSegR];
-    __shared__ uint64_t s_khi[WIDE ? kExtractWarps : 1][WIDE ? kSegR : 1];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(16) uint8_t s_tab[512];
     if (threadIdx.x < 32) reinterpret_cast<uint4 *>(s_tab)[threadIdx.x] = reinterpret_cast<const uint4 *>(codon)[threadIdx.x];
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t s = blockIdx.x * kExtractWarps + w;
-    if (s >= seqs.n_seqs) return;
-    const uint32_t L = seqs.seq_len[s];
-    const uint64_t start = ASCII ? astart[s] : seqs.seq_start[s];
+    const uint32_t r = blockIdx.x * (blockDim.x >> 5) + w;
+    if (r >= n_reads) return;
+    unsigned char *base = smem_raw + (size_t)w * wbytes;
+    uint64_t *klo = reinterpret_cast<uint64_t *>(base);                        // (cap is a multiple of 8: every array is 16-byte aligned)
+    uint64_t *khi = klo + (WIDE ? cap : 0);
+    uint64_t *glo = khi + cap;
+    uint64_t *ghi = glo + (WIDE ? cap : 0);
+    uint32_t *bcnt = reinterpret_cast<uint32_t *>(ghi + cap);
+    uint32_t *ba = bcnt + kSortBuckets + 4;
+    uint8_t *code = reinterpret_cast<uint8_t *>(ba + cap);
+    uint8_t *aa = code + (kSegR + kAaPad + 8);
+
+    const uint32_t s_begin = read_first ? read_first[r] : r, s_end = read_first ? read_first[r + 1] : r + 1;
+    const uint64_t out0 = koff[s_begin];
+    const uint32_t n_read = (uint32_t)min((uint64_t)0xffffffffu, koff[s_end] - out0);
+    if (n_read == 0) return;
+    const bool presort = n_read <= (uint32_t)kPresortMax && n_read <= cap;      // cap >= min(largest read, kPresortMax): see the launcher
     const int K = p.K;
-    const uint32_t n = (uint32_t)kmer_count((uint64_t)L + 3u * (K - p.k_low), K);
-    if (n == 0) return;
-    const uint64_t out0 = koff[s];
-    uint8_t *code = s_code[w], *aa = s_aa[w];
     const uint64_t mask_lo = WIDE ? ~0ull : ((1ull << (5 * K)) - 1);
     const uint64_t mask_hi = WIDE ? ((1ull << (5 * K - 64)) - 1) : 0ull;
     const int j0 = (lane / 3) * (3 * kRoll) + (lane % 3);
-    for (int strand = 0; strand < p.strands; ++strand) {
-        const uint64_t obase = out0 + (uint64_t)strand * n;
-        for (uint32_t p0 = 0; p0 < n; p0 += kSegR) {
-            const uint32_t cnt = min((uint32_t)kSegR, n - p0);
-            const uint32_t naa = cnt + 3 * (K - 1);
-            for (uint32_t j = lane; j < naa + 2; j += 32) {
-                const uint32_t pos = p0 + j;
-                uint32_t c;
-                if (!ASCII) c = code_at(seqs.bases2, seqs.nmask, start, L, strand, pos);
-                else if (pos >= L) c = 4u;                                      // marker / padding 'X'
-                else {
-                    const char ch = ascii[start + (strand ? (L - 1 - pos) : pos)];
-                    // Read.hpp:657-675: only ACGTacgt survive, everything else becomes 'Z'
-                    const bool ok = (ch == 'A') | (ch == 'C') | (ch == 'G') | (ch == 'T') | (ch == 'a') | (ch == 'c') | (ch == 'g') | (ch == 't');
-                    const uint32_t two = (uint32_t)(ch & 14) >> 1;              // kASA.hpp:70-75: A0 C1 T2 G3
-                    c = ok ? (strand ? (two ^ 2u) : two) : 5u;                  // complement A0<->T2, C1<->G3 (kASA.hpp:54)
+    uint32_t roff = 0;                                                            // k-mers of the read emitted so far
+    for (uint32_t s = s_begin; s < s_end; ++s) {
+        const uint32_t L = seqs.seq_len[s];
+        const uint64_t start = ASCII ? astart[s] : seqs.seq_start[s];
+        const uint32_t n = (uint32_t)kmer_count((uint64_t)L + 3u * (K - p.k_low), K);
+        if (n == 0) continue;
+        for (int strand = 0; strand < p.strands; ++strand) {
+            for (uint32_t p0 = 0; p0 < n; p0 += kSegR) {
+                const uint32_t cnt = min((uint32_t)kSegR, n - p0);
+                const uint32_t naa = cnt + 3 * (K - 1);
+                for (uint32_t j = lane; j < naa + 2; j += 32) {
+                    const uint32_t pos = p0 + j;
+                    uint32_t c;
+                    if (!ASCII) c = code_at(seqs.bases2, seqs.nmask, start, L, strand, pos);
+                    else if (pos >= L) c = 4u;                                      // marker / padding 'X'
+                    else {
+                        const char ch = ascii[start + (strand ? (L - 1 - pos) : pos)];
+                        // Read.hpp:657-675: only ACGTacgt survive, everything else becomes 'Z'
+                        const bool ok = (ch == 'A') | (ch == 'C') | (ch == 'G') | (ch == 'T') | (ch == 'a') | (ch == 'c') | (ch == 'g') | (ch == 't');
+                        const uint32_t two = (uint32_t)(ch & 14) >> 1;              // kASA.hpp:70-75: A0 C1 T2 G3
+                        c = ok ? (strand ? (two ^ 2u) : two) : 5u;                  // complement A0<->T2, C1<->G3 (kASA.hpp:54)
+                    }
+                    code[j] = (uint8_t)c;
                 }
-                code[j] = (uint8_t)c;
-            }
-            __syncwarp();
-            for (uint32_t j = lane; j < naa; j += 32) aa[j] = s_tab[(uint32_t)code[j] << 6 | (uint32_t)code[j + 1] << 3 | code[j + 2]];
-            __syncwarp();
-            if (lane < 30 && (uint32_t)j0 < cnt) {
-                uint64_t lo = 0, hi = 0;
-                for (int i = 0; i < K; ++i) {
-                    if (WIDE) hi = (hi << 5) | (lo >> 59);
-                    lo = (lo << 5) | aa[j0 + 3 * i];
-                }
-                s_klo[w][j0] = lo;
-                if (WIDE) s_khi[w][j0] = hi;
+                __syncwarp();
+                for (uint32_t j = lane; j < naa; j += 32) aa[j] = s_tab[(uint32_t)code[j] << 6 | (uint32_t)code[j + 1] << 3 | code[j + 2]];
+                __syncwarp();
+                // presorted reads collect all their k-mers; the others pass segment by segment through the first kSegR slots
+                uint64_t *dlo = presort ? klo + roff : klo, *dhi = presort ? khi + roff : khi;
+                if (lane < 30 && (uint32_t)j0 < cnt) {
+                    uint64_t lo = 0, hi = 0;
+                    for (int i = 0; i < K; ++i) {
+                        if (WIDE) hi = (hi << 5) | (lo >> 59);
+                        lo = (lo << 5) | aa[j0 + 3 * i];
+                    }
+                    dlo[j0] = lo;
+                    if (WIDE) dhi[j0] = hi;
 #pragma unroll
-                for (int t = 1; t < kRoll; ++t) {
-                    const int j = j0 + 3 * t;
-                    if ((uint32_t)j >= cnt) break;
-                    if (WIDE) hi = ((hi << 5) | (lo >> 59)) & mask_hi;
-                    lo = ((lo << 5) | aa[j + 3 * (K - 1)]) & mask_lo;
-                    s_klo[w][j] = lo;
-                    if (WIDE) s_khi[w][j] = hi;
+                    for (int t = 1; t < kRoll; ++t) {
+                        const int j = j0 + 3 * t;
+                        if ((uint32_t)j >= cnt) break;
+                        if (WIDE) hi = ((hi << 5) | (lo >> 59)) & mask_hi;
+                        lo = ((lo << 5) | aa[j + 3 * (K - 1)]) & mask_lo;
+                        dlo[j] = lo;
+                        if (WIDE) dhi[j] = hi;
+                    }
                 }
+                __syncwarp();
+                if (!presort) {
+                    const uint64_t obase = out0 + roff;
+                    for (uint32_t j = lane; j < cnt; j += 32) {
+                        const uint64_t o = obase + j;
+                        key_lo[o] = klo[j];
+                        if (WIDE) key_hi[o] = khi[j];
+                        inst[o] = (uint32_t)o;
+                    }
+                    __syncwarp();
+                }
+                roff += cnt;
             }
-            __syncwarp();
-            for (uint32_t j = lane; j < cnt; j += 32) {
-                const uint64_t o = obase + p0 + j;
-                key_lo[o] = s_klo[w][j];
-                if (WIDE) key_hi[o] = s_khi[w][j];
-                inst[o] = (uint32_t)o;
-            }
-            __syncwarp();
         }
+    }
+    if (!presort) return;
+    // ---- order the read's k-mers: bucket on the leading bits of the key, then rank inside the bucket
+    const uint32_t m = roff;
+    const int bsh = WIDE ? 5 * K - 64 - kSortBucketBits : 5 * K - kSortBucketBits;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(bcnt);
+        for (uint32_t i = lane; i < kSortBuckets / 4 + 1; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncwarp();
+    for (uint32_t x = lane; x < m; x += 32) {
+        const uint32_t bk = (uint32_t)((WIDE ? khi[x] : klo[x]) >> bsh) & (kSortBuckets - 1);
+        ba[x] = bk | (atomicAdd(&bcnt[bk], 1u) << kSortBucketBits);                           // bucket | arrival index inside the bucket
+    }
+    __syncwarp();
+    {   // exclusive scan of the bucket counts
+        constexpr uint32_t per = kSortBuckets / 32;
+        uint32_t c[per], sum = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < per; i += 4) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(bcnt + lane * per + i);
+            c[i] = v.x; c[i + 1] = v.y; c[i + 2] = v.z; c[i + 3] = v.w;
+            sum += v.x + v.y + v.z + v.w;
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += y;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (uint32_t i = 0; i < per; i += 4) {
+            uint4 v;
+            v.x = run; run += c[i]; v.y = run; run += c[i + 1]; v.z = run; run += c[i + 2]; v.w = run; run += c[i + 3];
+            *reinterpret_cast<uint4 *>(bcnt + lane * per + i) = v;
+        }
+        if (lane == 31) bcnt[kSortBuckets] = run;
+    }
+    __syncwarp();
+    // the k-mers grouped by bucket, contiguous (second copy)
+    for (uint32_t x = lane; x < m; x += 32) {
+        const uint32_t e = ba[x], g = bcnt[e & (kSortBuckets - 1)] + (e >> kSortBucketBits);
+        glo[g] = klo[x];
+        if (WIDE) ghi[g] = khi[x];
+    }
+    __syncwarp();
+    // rank inside the bucket by counting; the first copy receives the k-mers in their final order
+    for (uint32_t g = lane; g < m; g += 32) {
+        const uint64_t xl = glo[g], xh = WIDE ? ghi[g] : 0ull;
+        const uint32_t bk = (uint32_t)((WIDE ? xh : xl) >> bsh) & (kSortBuckets - 1);
+        const uint32_t b0 = bcnt[bk], b1 = bcnt[bk + 1];
+        uint32_t less = 0;
+        for (uint32_t y = b0; y < b1; ++y) {
+            const uint64_t ol = glo[y];
+            bool lt;
+            if (WIDE) { const uint64_t oh = ghi[y]; lt = oh != xh ? oh < xh : (ol != xl ? ol < xl : y < g); }
+            else lt = ol != xl ? ol < xl : y < g;                  // equal k-mers: any fixed order (their records are identical)
+            less += lt ? 1u : 0u;
+        }
+        klo[b0 + less] = xl;
+        if (WIDE) khi[b0 + less] = xh;
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < m; j += 32) {
+        const uint64_t o = out0 + j;
+        key_lo[o] = klo[j];
+        if (WIDE) key_hi[o] = khi[j];
+        inst[o] = (uint32_t)o;
     }
 }
 
@@ -240,29 +350,41 @@ void launch_kmer_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs
     ++*launches;
 }
 
-void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo,
-                             uint64_t *key_hi, uint32_t *inst, uint64_t *launches)
+// shared memory per warp follows the largest read of the batch (a resource choice only: which reads are presorted depends on
+// their own length, never on the batch)
+template <class Kern>
+static void launch_extract_kernel(Kern kern, cudaStream_t s, bool wide, PackedSeqs seqs, const char *ascii, const uint64_t *astart, KmerParams p,
+                                  const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo, uint64_t *key_hi, uint32_t *inst,
+                                  const uint32_t *read_first, uint32_t n_reads, uint32_t max_inst)
 {
-    if (!seqs.n_seqs) return;
-    unsigned grid = div_up(seqs.n_seqs, (uint32_t)kExtractWarps);
-    if (p.K > 12)
-        extract_identify_kernel<true, false><<<grid, kExtractWarps * 32, 0, s>>>(seqs, nullptr, nullptr, p, koff, key_lo, key_hi, inst, codon);
-    else
-        extract_identify_kernel<false, false><<<grid, kExtractWarps * 32, 0, s>>>(seqs, nullptr, nullptr, p, koff, key_lo, key_hi, inst, codon);
+    uint32_t cap = std::min<uint32_t>(std::max<uint32_t>(max_inst, (uint32_t)kSegR), (uint32_t)kPresortMax);
+    cap = (cap + 7u) & ~7u;
+    const size_t wbytes = extract_warp_bytes(wide, cap);
+    uint32_t warps = kExtractWarps;                                     // fewer warps per CTA when the reads are long (shared memory)
+    while (warps > 1 && wbytes * warps > (size_t)200 * 1024) warps >>= 1;
+    const size_t sm = wbytes * warps;
+    KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<div_up(n_reads, warps), warps * 32, sm, s>>>(seqs, ascii, astart, p, koff, key_lo, key_hi, inst, codon, read_first, n_reads, cap, (uint32_t)wbytes);
+}
+
+void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo,
+                             uint64_t *key_hi, uint32_t *inst, const uint32_t *read_first, uint32_t n_reads, uint32_t max_inst, uint64_t *launches)
+{
+    if (!seqs.n_seqs || !n_reads) return;
+    if (p.K > 12) launch_extract_kernel(extract_identify_kernel<true, false>, s, true, seqs, nullptr, nullptr, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads, max_inst);
+    else launch_extract_kernel(extract_identify_kernel<false, false>, s, false, seqs, nullptr, nullptr, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads, max_inst);
     ++*launches;
 }
 
 void launch_extract_identify_ascii(cudaStream_t s, const char *ascii, const uint64_t *ascii_start, const uint32_t *seq_len,
                                    uint32_t n_seqs, KmerParams p, const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo,
-                                   uint64_t *key_hi, uint32_t *inst, uint64_t *launches)
+                                   uint64_t *key_hi, uint32_t *inst, const uint32_t *read_first, uint32_t n_reads, uint32_t max_inst,
+                                   uint64_t *launches)
 {
-    if (!n_seqs) return;
+    if (!n_seqs || !n_reads) return;
     PackedSeqs seqs{nullptr, nullptr, nullptr, seq_len, n_seqs};
-    unsigned grid = div_up(n_seqs, (uint32_t)kExtractWarps);
-    if (p.K > 12)
-        extract_identify_kernel<true, true><<<grid, kExtractWarps * 32, 0, s>>>(seqs, ascii, ascii_start, p, koff, key_lo, key_hi, inst, codon);
-    else
-        extract_identify_kernel<false, true><<<grid, kExtractWarps * 32, 0, s>>>(seqs, ascii, ascii_start, p, koff, key_lo, key_hi, inst, codon);
+    if (p.K > 12) launch_extract_kernel(extract_identify_kernel<true, true>, s, true, seqs, ascii, ascii_start, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads, max_inst);
+    else launch_extract_kernel(extract_identify_kernel<false, true>, s, false, seqs, ascii, ascii_start, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads, max_inst);
     ++*launches;
 }
 

@@ -34,15 +34,19 @@ void launch_pack_ascii(cudaStream_t s, const char *ascii, const uint64_t *ascii_
 
 // per-sequence k-mer counts (Read.hpp:36-57) into koff[0..n_seqs); scan afterwards
 void launch_kmer_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, KmerParams p, uint64_t *koff, uint64_t *launches);
-// k-mers in the reference's emission order (forward strand, then reverse strand, per sequence);
-// key_hi may be nullptr for K <= 12; inst[i] = i (sort payload = instance id)
+// Reads of at most kPresortMax k-mers are emitted with their k-mers in ascending order (the order in which the reference scores
+// them: extract.cu "presorted emission"); longer reads in the reference's emission order (forward strand, then reverse strand, per
+// sequence).  A read = the sequences [read_first[r], read_first[r+1]) (read_first == nullptr: one sequence per read);
+// max_inst = most k-mers of any read of the batch (sizes the shared memory).  key_hi may be nullptr for K <= 12; inst[i] = i.
+constexpr int kPresortMax = 1024;
 void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo,
-                             uint64_t *key_hi, uint32_t *inst, uint64_t *launches);
+                             uint64_t *key_hi, uint32_t *inst, const uint32_t *read_first, uint32_t n_reads, uint32_t max_inst, uint64_t *launches);
 
 // the same straight from raw ASCII sequences (KASA_SEQ_ASCII): cleaning, strands and markers on the fly, no packed copy
 void launch_extract_identify_ascii(cudaStream_t s, const char *ascii, const uint64_t *ascii_start, const uint32_t *seq_len,
                                    uint32_t n_seqs, KmerParams p, const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo,
-                                   uint64_t *key_hi, uint32_t *inst, uint64_t *launches);
+                                   uint64_t *key_hi, uint32_t *inst, const uint32_t *read_first, uint32_t n_reads, uint32_t max_inst,
+                                   uint64_t *launches);
 
 // build: one slot per window of each prepared ASCII string; windows holding '_' (31) or giving k-mer 0
 // get the sentinel key ~0 (dropped after the sort): Read.hpp:2016-2024, 2048-2059, 2097, 2122

@@ -305,6 +305,7 @@ struct SpanStage {
     uint64_t klo[kSpanCap + kKeyPad];
     uint64_t khi[W ? kSpanCap + kKeyPad : 2];
     uint16_t tax[kSpanCap + kTaxPad];
+    alignas(16) uint64_t gm[MASK ? kSpanCap + kKeyPad : 2];   // mask records: taxa mask of every entry's k_low group (IndexDev::gmask); bulk-copy target
     uint64_t pw[3][MASK ? 1 : kLookupTile];   // list records: pair words of the tile's records, word-major (conflict-free per-thread slots)
     uint64_t bar;                        // mbarrier of the bulk copies
 };
@@ -318,6 +319,11 @@ struct SpanStage {
 //      more than k_low letters (contiguous, usually 0-2 entries) is remembered;
 //   3. the remembered entries raise their taxa's level counts in registers, and one 32-byte store puts the record
 //      into the instance's slot.  Taxa sets of more than nine taxa go to the overflow list (match_general).
+// MASK (content files of <= 64 taxa): the taxa set of every k_low group was computed once at index load (IndexDev::gmask) and is
+// staged with the span, so step 1 searches for the query itself and step 2 shrinks to: one mask load from a neighbour that shares
+// k_low letters, and a walk over the entries sharing MORE than k_low letters (they surround the search position; usually 0-2).
+// The walk over the whole k_low group — whose trip count is the largest group among the 128 queries of a warp, dozens of
+// entries for k-mers of frequent amino acids against a saturated index — took 2/3 of this kernel's instructions.
 template <bool W, bool MASK>
 __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
                                                                          const uint32_t *__restrict__ inst, uint64_t n, uint64_t rank_base,
@@ -338,9 +344,10 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
         mbar_init(&st.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t kb = (uint32_t)(((b - ak) + 1) & ~(int64_t)1) * 8u, cb = (uint32_t)(((b - ac) + 7) & ~(int64_t)7) * 2u;
-        mbar_expect_tx(&st.bar, kb * (W ? 2u : 1u) + cb);
+        mbar_expect_tx(&st.bar, kb * ((W ? 2u : 1u) + (MASK ? 1u : 0u)) + cb);
         bulk_g2s(st.klo, idx.key_lo + ak, kb, &st.bar);
         if (W) bulk_g2s(st.khi, idx.key_hi + ak, kb, &st.bar);
+        if (MASK) bulk_g2s(st.gm, idx.gmask + ak, kb, &st.bar);
         bulk_g2s(st.tax, idx.tax + ac, cb, &st.bar);
     }
     // this thread's queries and instance ids: their latency overlaps the span staging
@@ -379,7 +386,7 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
         {
             Key fl[QPT];
 #pragma unroll
-            for (int r = 0; r < QPT; ++r) fl[r] = prefix_floor<W>(qv[r], low_sh);
+            for (int r = 0; r < QPT; ++r) fl[r] = MASK ? qv[r] : prefix_floor<W>(qv[r], low_sh);
             int nn = span;
             while (nn > 1) {
                 const int half = nn >> 1;
@@ -394,8 +401,40 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
         }
 #pragma unroll
         for (int r = 0; r < QPT; ++r) g0[r] = pos[r];
+        if (MASK) {
+            // ---- 2 (mask records). the group's taxa from a neighbour sharing k_low letters ...
+            const uint64_t *gms = st.gm + (a - ak);
+            uint32_t goL = 0, goR = 0;
+            int lo_p[QPT], hi_p[QPT];
+#pragma unroll
+            for (int r = 0; r < QPT; ++r) {
+                lo_p[r] = hi_p[r] = pos[r];
+                if (!((act >> r) & 1u)) continue;
+                const int e1 = min(pos[r], span - 1), e0 = max(pos[r] - 1, 0);
+                const bool in1 = pos[r] < span && shares_prefix<W>(sacc.template key<W>(e1), qv[r], low_sh);
+                const bool in0 = pos[r] > 0 && shares_prefix<W>(sacc.template key<W>(e0), qv[r], low_sh);
+                mask[r] = in1 ? gms[e1] : (in0 ? gms[e0] : 0ull);
+                if (mask[r] && kv[r] > lp.k_low) { goL |= 1u << r; goR |= 1u << r; }
+            }
+            // ... and the entries sharing more than k_low letters: a contiguous run around the search position
+            while (goL | goR) {
+#pragma unroll
+                for (int r = 0; r < QPT; ++r) {
+                    if ((goL >> r) & 1u) {
+                        const int e = lo_p[r] - 1;
+                        if (e >= 0 && shares_prefix<W>(sacc.template key<W>(max(e, 0)), qv[r], up_sh)) lo_p[r] = e; else goL &= ~(1u << r);
+                    }
+                    if ((goR >> r) & 1u) {
+                        const int e = hi_p[r];
+                        if (e < span && shares_prefix<W>(sacc.template key<W>(min(e, span - 1)), qv[r], up_sh)) hi_p[r] = e + 1; else goR &= ~(1u << r);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < QPT; ++r) up[r] = hi_p[r] > lo_p[r] ? ((uint32_t)lo_p[r] << 12) + (uint32_t)(hi_p[r] - lo_p[r]) : 0u;
+        }
         // ---- 2. lockstep forward walks over the entries sharing k_low letters
-        uint32_t go = act;
+        uint32_t go = MASK ? 0u : act;
         while (go) {
             uint64_t elo[QPT], ehi[QPT];
             uint32_t tx[QPT];
@@ -452,7 +491,11 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
                 if (fits) {
                     o0 = rec_head(rank, (uint32_t)__popcll(mask[r]), hmax, false, owner) | kRecMaskBit;
                     o1 = mask[r]; o2 = uw[0]; o3 = uw[1];
-                } else { general = true; gen_g0 = g0[r]; gen_b = span; }
+                } else {
+                    // more than six taxa above k_low: list record from the whole group (its first entry is searched for only now)
+                    general = true; gen_b = span;
+                    gen_g0 = lower_bound<W>(sacc, 0, (int64_t)span, prefix_floor<W>(qv[r], low_sh));
+                }
             }
         } else if (staged) {
             const uint32_t c = cnt[r];
@@ -524,6 +567,44 @@ __global__ void __launch_bounds__(256) index_flags_kernel(uint64_t *__restrict__
     }
 }
 
+// ---- taxa mask of every k_low-letter group, stored with each of its entries (IndexDev::gmask; content files of <= 64 taxa).
+// Group heads -> exclusive scan = group number -> atomicOr of the entries' taxon bits into one word per group -> every entry
+// fetches its group's word.  One pass per step over the index at load time.
+template <bool W>
+__device__ __forceinline__ bool group_head(const uint64_t *__restrict__ key_lo, const uint64_t *__restrict__ key_hi, uint64_t e, int low_sh)
+{
+    if (e == 0) return true;
+    const Key me = strip<W>(key_lo[e], W ? key_hi[e] : 0ull), pr = strip<W>(key_lo[e - 1], W ? key_hi[e - 1] : 0ull);
+    return !shares_prefix<W>(pr, me, low_sh);
+}
+template <bool W>
+__global__ void __launch_bounds__(256) group_heads_kernel(const uint64_t *__restrict__ key_lo, const uint64_t *__restrict__ key_hi, uint64_t n, int low_sh,
+                                                          uint64_t *__restrict__ out)
+{
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = group_head<W>(key_lo, key_hi, e, low_sh) ? 1ull : 0ull;
+}
+template <bool W>
+__global__ void __launch_bounds__(256) group_or_kernel(const uint64_t *__restrict__ key_lo, const uint64_t *__restrict__ key_hi,
+                                                       const uint16_t *__restrict__ tax, uint64_t n, int low_sh, const uint64_t *__restrict__ before,
+                                                       unsigned long long *__restrict__ gm)
+{
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const uint64_t g = before[e] + (group_head<W>(key_lo, key_hi, e, low_sh) ? 1ull : 0ull) - 1ull;
+    const uint32_t t = tax[e];
+    if (t >= 1u && t <= 64u) atomicOr(gm + g, 1ull << (t - 1u));
+}
+template <bool W>
+__global__ void __launch_bounds__(256) group_expand_kernel(const uint64_t *__restrict__ key_lo, const uint64_t *__restrict__ key_hi, uint64_t n, int low_sh,
+                                                           const uint64_t *__restrict__ gm, uint64_t *__restrict__ inout)
+{
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const uint64_t g = inout[e] + (group_head<W>(key_lo, key_hi, e, low_sh) ? 1ull : 0ull) - 1ull;
+    inout[e] = gm[g];
+}
+
 __global__ void read_offsets_kernel(const uint64_t *__restrict__ koff, const uint32_t *__restrict__ first_seq, uint32_t n_reads,
                                     uint64_t *__restrict__ out)
 {
@@ -588,6 +669,7 @@ void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, c
         kern<<<tiles, kLookupBlock, sm, s>>>(q_lo, q_hi, inst, n, rank_base, idx, lp, part, rec, tq, ovf, owner, err_flag);
     };
     const bool mask = lp.n_taxa <= kMaskTaxa;
+    KASA_REQUIRE(!mask || idx.gmask, -4, "the index of a small content file has no group masks (launch_group_masks)");
     if (idx.key_hi) { if (mask) go(lookup_kernel<true, true>, sizeof(SpanStage<true, true>)); else go(lookup_kernel<true, false>, sizeof(SpanStage<true, false>)); }
     else { if (mask) go(lookup_kernel<false, true>, sizeof(SpanStage<false, true>)); else go(lookup_kernel<false, false>, sizeof(SpanStage<false, false>)); }
     ++*launches;
@@ -602,6 +684,32 @@ void launch_index_flags(cudaStream_t s, uint64_t *key_lo, uint64_t *key_hi, cons
     if (key_hi) index_flags_kernel<true><<<(unsigned)div_up<uint64_t>(n, 256), 256, 0, s>>>(key_lo, key_hi, tax, n, low_sh);
     else index_flags_kernel<false><<<(unsigned)div_up<uint64_t>(n, 256), 256, 0, s>>>(key_lo, key_hi, tax, n, low_sh);
     ++*launches;
+}
+
+void launch_group_heads(cudaStream_t s, const uint64_t *key_lo, const uint64_t *key_hi, uint64_t n, int K, int k_low, uint64_t *out, uint64_t *launches)
+{
+    if (!n) return;
+    const int low_sh = 5 * (K - k_low);
+    const unsigned grid = (unsigned)div_up<uint64_t>(n, 256);
+    if (key_hi) group_heads_kernel<true><<<grid, 256, 0, s>>>(key_lo, key_hi, n, low_sh, out);
+    else group_heads_kernel<false><<<grid, 256, 0, s>>>(key_lo, key_hi, n, low_sh, out);
+    ++*launches;
+}
+
+void launch_group_masks(cudaStream_t s, const uint64_t *key_lo, const uint64_t *key_hi, const uint16_t *tax, uint64_t n, int K, int k_low,
+                        uint64_t *gm, uint64_t *inout, uint64_t *launches)
+{
+    if (!n) return;
+    const int low_sh = 5 * (K - k_low);
+    const unsigned grid = (unsigned)div_up<uint64_t>(n, 256);
+    if (key_hi) {
+        group_or_kernel<true><<<grid, 256, 0, s>>>(key_lo, key_hi, tax, n, low_sh, inout, reinterpret_cast<unsigned long long *>(gm));
+        group_expand_kernel<true><<<grid, 256, 0, s>>>(key_lo, key_hi, n, low_sh, gm, inout);
+    } else {
+        group_or_kernel<false><<<grid, 256, 0, s>>>(key_lo, key_hi, tax, n, low_sh, inout, reinterpret_cast<unsigned long long *>(gm));
+        group_expand_kernel<false><<<grid, 256, 0, s>>>(key_lo, key_hi, n, low_sh, gm, inout);
+    }
+    *launches += 2;
 }
 
 void launch_read_offsets(cudaStream_t s, const uint64_t *koff, const uint32_t *read_first_seq, uint32_t n_reads,

@@ -18,6 +18,8 @@ struct IndexDev {
     const uint64_t *key_hi;   // nullptr for 64-bit k-mers
     const uint16_t *tax;      // dense taxon index (1-based: position in the content file)
     uint64_t n;
+    const uint64_t *gmask;    // content files of <= 64 taxa: bit t-1 set for every taxon t of the entry's k_low-letter group (same word for
+                              // all entries of a group) — markTaxIDs of level k_low (Compare.hpp:396-441) done once at index load; else nullptr
 };
 constexpr uint64_t kKeyFlag = 1ull << 63;
 
@@ -87,6 +89,14 @@ void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32
 // sets the taxon-first flags of a freshly loaded index (keys must be unflagged); k_low-letter groups
 void launch_index_flags(cudaStream_t s, uint64_t *key_lo, uint64_t *key_hi, const uint16_t *tax, uint64_t n, int K, int k_low,
                         uint64_t *launches);
+
+// group masks of a freshly loaded index (IndexDev::gmask), in three steps:
+//   launch_group_heads   out[e] = 1 if entry e starts a k_low-letter group, else 0            (out holds n + 1 words)
+//   exclusive_scan_u64   in place: out[e] = groups started before e, out[n] = number of groups (scan.cuh)
+//   launch_group_masks   gm[groups] (zeroed by the caller) collects the taxon bits per group; inout[e] (the scan) becomes the mask of e's group
+void launch_group_heads(cudaStream_t s, const uint64_t *key_lo, const uint64_t *key_hi, uint64_t n, int K, int k_low, uint64_t *out, uint64_t *launches);
+void launch_group_masks(cudaStream_t s, const uint64_t *key_lo, const uint64_t *key_hi, const uint16_t *tax, uint64_t n, int K, int k_low,
+                        uint64_t *gm, uint64_t *inout, uint64_t *launches);
 
 // read_koff[r] = koff[read_first_seq[r]] (or koff[r])
 void launch_read_offsets(cudaStream_t s, const uint64_t *koff, const uint32_t *read_first_seq, uint32_t n_reads,

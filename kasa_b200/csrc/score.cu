@@ -605,8 +605,17 @@ __global__ void __launch_bounds__(kMaskBlock) accumulate_mask_kernel(OpsWorkspac
         uint32_t left = have ? ws.ops_count[r] / 4u : 0u;               // 16-byte blocks
         uint4 nxt = make_uint4(0, 0, 0, 0);
         if (left) nxt = __ldg(cur);
+        uint32_t since = 0;                                              // groups since the k_low sums were last handed on
         while (__any_sync(kFull, left > 0)) {
             if (left) {
+                if (++since == 256u) {
+                    // a k-mer adds at most 2^23 units to a k_low sum: long reads hand their sums on before 32 bits could overflow
+                    since = 0;
+                    for (int c = 0; c < NC && c < T - 1; ++c) {
+                        uint2 x = cell[c * BT + tid];
+                        if (x.y) { atomicAdd(&s_fx[c], (unsigned long long)x.y << kFxShift); x.y = 0u; cell[c * BT + tid] = x; }
+                    }
+                }
                 const uint4 g = nxt;
                 const uint32_t n0 = (g.x >> 24) & 127u, nup = (g.x >> 17) & 127u;
                 const uint32_t blocks = 1u + (nup > 1u ? (nup - 1u + 3u) / 4u : 0u);
@@ -998,6 +1007,401 @@ void launch_dense(cudaStream_t s, OpsWorkspace ws, uint32_t r0, uint32_t r1, Lev
     kern<<<grid, kDenseBlock, sm, s>>>(ws, r0, r1, lp, exact_stream, scores);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// PRESORTED READS (extract.cu emits a read of <= kPresortMax k-mers in ascending k-mer order, the batch sort is stable): the
+// match records of a read already lie in HBM in the order in which the reference adds them up, so for content files of <= 64 taxa
+// and <= 6 levels scores and counts come straight from the records — no ordering pass, no op stream.
+//   LANES threads per read, each owning NT taxa (taxon - 1 in [lane * NT, lane * NT + NT)); every thread reads the read's records
+//   (one 32-byte sector per k-mer, the LANES loads of a read coalesce into one request, four records in flight per thread) and keeps
+//   the float32 score and the k_low share of the count of its taxa IN REGISTERS:
+//     level k_low   a predicated scan over the thread's slice of the record's taxa mask: NT independent add chains, no divergence;
+//     levels above  the (few) up pairs of the record: the owner selects the taxon's register through a select tree, adds the
+//                   levels in order and writes it back through predicated moves — registers cannot be indexed, and keeping such
+//                   taxa in shared-memory cells instead costs more: against a saturated index a read meets ~10 of 50 taxa above
+//                   k_low somewhere, so most k_low adds would take the slow path.
+//   Rarer events (a k-mer with a single taxon, counts above k_low) go to small per-CTA tables with shared-memory atomics.
+constexpr int kSortedBlock = 128;
+constexpr int kSortedDepth = 4;         // records in flight per thread
+
+// sc[s] for a run-time s < NT: select tree on the bits of s (NT - 1 selects)
+template <int LO, int N>
+__device__ __forceinline__ float tree_select(const float *sc, uint32_t s)
+{
+    if constexpr (N == 1) return sc[LO];
+    else {
+        constexpr int H = 1 << (31 - __builtin_clz((unsigned)(N - 1)));     // largest power of two < N
+        const float lo = tree_select<LO, H>(sc, s);
+        const float hi = tree_select<LO + H, N - H>(sc, s);
+        return (s & (uint32_t)H) ? hi : lo;
+    }
+}
+
+template <int LANES, int NT>
+__global__ void __launch_bounds__(kSortedBlock) score_sorted_kernel(const uint64_t *__restrict__ rec, const uint64_t *__restrict__ read_koff, uint32_t n_reads,
+                                                                     LevelParams lp, OverflowPeers peers, float *__restrict__ scores,
+                                                                     unsigned long long *__restrict__ cnt_fx, unsigned long long *__restrict__ cnt_unique)
+{
+    static_assert(NT <= 32 && LANES * NT <= 64 + NT, "slice of the taxa mask must fit 32 bits");
+    constexpr int BT = kSortedBlock, D = kSortedDepth;
+    constexpr uint32_t kSlice = NT >= 32 ? 0xffffffffu : ((1u << NT) - 1u);
+    __shared__ float2 s_vq[72];                                         // [n]: .x = float(w_0 * (1.f / n)), .y = bits of 2^24 / n (0 for n < 2)
+    __shared__ float s_inv[72];
+    __shared__ uint32_t s_q32[72];                                      // 2^32 / n
+    __shared__ unsigned long long s_fx[6 * 64];                         // CTA totals [level][taxon - 1], 2^-32 units
+    __shared__ uint32_t s_un[6 * 64];
+    __shared__ uint32_t s_hist[64 * 8];                                 // [taxon - 1][h]: k-mers where the taxon is alone at its levels 1 .. h-1
+    const int tid = threadIdx.x, T = lp.n_taxa, NK = lp.num_k;
+    const int q = tid / LANES, l = tid % LANES, tbase = l * NT;
+    float wj[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { const int k = lp.k_low + j; wj[j] = (float)(k * k) / 625.f; }      // Compare.hpp:392
+    for (int i = tid; i < 6 * 64; i += BT) { s_fx[i] = 0; s_un[i] = 0; }
+    for (int i = tid; i < 64 * 8; i += BT) s_hist[i] = 0;
+    if (tid < 72) {
+        const float inv = tid ? __fdiv_rn(1.f, (float)tid) : 0.f;       // Compare.hpp:924: 1.f / numOfEntries
+        s_inv[tid] = inv;
+        s_vq[tid] = make_float2(__fmul_rn(wj[0], inv), __uint_as_float(tid >= 2 ? (uint32_t)(((1u << 24) + (tid >> 1)) / tid) : 0u));
+        s_q32[tid] = tid >= 2 ? inv_fx((uint32_t)tid) : 0u;
+    }
+    __syncthreads();
+
+    float sc[NT];
+    uint32_t fq[NT];
+    // adds the levels 1 .. h-1 of taxon c (0-based) to its score; nj = level sizes (nullptr: the taxon is alone at each of them)
+    auto add_upper = [&](uint32_t c, uint32_t h, const uint32_t *nj) {
+        const uint32_t s = c - (uint32_t)tbase;
+        if (s >= (uint32_t)NT || h < 2u) return;
+        float v = tree_select<0, NT>(sc, s);
+#pragma unroll
+        for (int j = 1; j < 6; ++j) {
+            if ((uint32_t)j >= h) break;
+            if (!nj) v = __fadd_rn(v, wj[j]);                            // w * (1.f / 1) == w
+            else {
+                v = __fadd_rn(v, __fmul_rn(wj[j], s_inv[nj[j]]));
+                if (nj[j] == 1u) atomicAdd(&s_un[j * 64 + c], 1u);
+                else atomicAdd(&s_fx[j * 64 + c], (unsigned long long)s_q32[nj[j]]);
+            }
+        }
+        if (!nj) atomicAdd(&s_hist[c * 8 + (h & 7u)], 1u);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) sc[t] = s == (uint32_t)t ? v : sc[t];
+    };
+    auto flush_fq = [&]() {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            if (fq[t]) atomicAdd(&s_fx[tbase + t], (unsigned long long)fq[t] << kFxShift);
+            fq[t] = 0u;
+        }
+    };
+    // one match record
+    auto apply = [&](const uint64_t (&w)[4]) {
+        const uint32_t n0 = rec_count(w[0]);                             // 0: no hit (mask and pairs are zero too)
+        const uint32_t hmax = rec_hmax(w[0]);
+        if (n0 && !rec_is_mask(w[0])) {
+            // ---- list record inside a small taxonomy (more than six taxa above k_low, or a span read from HBM): pair by pair
+            const bool ovf = rec_overflow(w[0]);
+            const uint32_t *list = ovf ? peers.base[rec_owner(w[0])] + w[1] : nullptr;
+            auto pair_at = [&](uint32_t k) -> uint32_t { return ovf ? __ldg(list + k) : (uint32_t)(w[1 + k / 3] >> (kPairBits * (k % 3))) & kPairMask; };
+            uint32_t nj[6] = {0, 0, 0, 0, 0, 0};
+            for (uint32_t k = 0; k < n0; ++k) {
+                const uint32_t h = pair_at(k) >> 16;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) nj[j] += (uint32_t)j < h ? 1u : 0u;
+            }
+            const float2 vq = s_vq[n0 < 72u ? n0 : 0u];
+            for (uint32_t k = 0; k < n0; ++k) {
+                const uint32_t e = pair_at(k), c = (e & 0xffffu) - 1u, h = e >> 16, s = c - (uint32_t)tbase;
+                if (s >= (uint32_t)NT) continue;
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+                    if (s == (uint32_t)t) { sc[t] = __fadd_rn(sc[t], vq.x); fq[t] += __float_as_uint(vq.y); }
+                if (n0 == 1u) atomicAdd(&s_un[c], 1u);
+                add_upper(c, h, nj);
+            }
+            return;
+        }
+        // ---- mask record, level k_low (Compare.hpp:530): every taxon of the mask gets float(w_0 * (1.f / n0))
+        const float2 vq = s_vq[n0];
+        const float v0 = vq.x;
+        const uint32_t q0 = __float_as_uint(vq.y);
+        const uint32_t bits = (uint32_t)(w[1] >> tbase) & kSlice;
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+            if ((bits >> t) & 1u) { sc[t] = __fadd_rn(sc[t], v0); fq[t] += q0; }
+        if (n0 == 1u && bits) atomicAdd(&s_un[tbase + __ffs((int)bits) - 1], 1u);           // alone at k_low: a unique hit
+        // ---- levels above k_low: up pairs (taxon | levels << 16), 21 bits each, three per word
+        if (hmax > 1u) {
+            const uint32_t p0 = (uint32_t)w[2] & kPairMask;
+            if ((w[2] >> kPairBits) == 0 && w[3] == 0) add_upper((p0 & 0xffffu) - 1u, p0 >> 16, nullptr);
+            else {
+                const uint64_t pw[3] = {w[1], w[2], w[3]};
+                uint32_t nj[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+                for (int k = 0; k < kRecUpPairs; ++k) {
+                    const uint32_t h = up_pair(pw, k) >> 16;                                    // 0 for an empty pair
+#pragma unroll
+                    for (int j = 1; j < 6; ++j) nj[j] += (uint32_t)j < h ? 1u : 0u;
+                }
+#pragma unroll 1
+                for (int k = 0; k < kRecUpPairs; ++k) {
+                    const uint32_t e = (uint32_t)(pw[1 + k / 3] >> (kPairBits * (k % 3))) & kPairMask;
+                    if (!e) break;
+                    add_upper((e & 0xffffu) - 1u, e >> 16, nj);
+                }
+            }
+        }
+    };
+    auto load_rec = [&](const uint64_t *p, uint64_t (&w)[4]) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p));
+    };
+
+#pragma unroll 1
+    for (uint32_t r = blockIdx.x * (BT / LANES) + q; r < n_reads; r += gridDim.x * (BT / LANES)) {
+        const uint64_t s0 = read_koff[r];
+        const uint32_t ni = (uint32_t)(read_koff[r + 1] - s0);
+        const uint64_t *p = rec + s0 * kRecWords;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { sc[t] = 0.f; fq[t] = 0u; }
+        uint64_t buf[D][4];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            buf[d][0] = buf[d][1] = buf[d][2] = buf[d][3] = 0;
+            if ((uint32_t)d < ni) load_rec(p + (uint64_t)d * kRecWords, buf[d]);
+        }
+#pragma unroll 1
+        for (uint32_t i = 0; i < ni; i += D) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                if (i + d < ni) {
+                    uint64_t w[4] = {buf[d][0], buf[d][1], buf[d][2], buf[d][3]};
+                    if (i + d + D < ni) load_rec(p + (uint64_t)(i + d + D) * kRecWords, buf[d]);
+                    apply(w);
+                }
+            }
+            // a k-mer adds at most 2^23 units to a k_low sum: hand the sums to the CTA's totals before 32 bits could overflow
+            if ((i & 255u) == 256u - D) flush_fq();
+        }
+        // ---- end of the read: scores out, its k_low sums into the CTA's totals
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int c = tbase + t;
+            if (c < T - 1 && scores) scores[(uint64_t)r * T + c + 1] = sc[t];
+        }
+        flush_fq();
+        if (scores && l == 0) scores[(uint64_t)r * T] = 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < NK * 64; i += BT) {
+        const int j = i / 64, c = i % 64;
+        if (c >= T - 1) continue;
+        unsigned long long u = s_un[i];
+        if (j >= 1) for (int h = j + 1; h < 8; ++h) u += s_hist[c * 8 + h];     // alone at the levels 1 .. h-1
+        if (u) atomicAdd(cnt_unique + (size_t)j * T + c + 1, u);
+        if (s_fx[i]) atomicAdd(cnt_fx + (size_t)j * T + c + 1, s_fx[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PRESORTED READS, second organisation: WARP PER READ, 32 k-mers at a time.
+//   setup   lane = k-mer: the 32 records of the block arrive as one coalesced 1 KB load; every lane publishes its k-mer's value
+//           float(w_0 * (1.f / n0)) and its up pairs in shared memory; the 32 taxa masks are TRANSPOSED with warp shuffles (five
+//           butterfly stages per 32 x 32 bit block), after which
+//   main    lane = taxon holds, per taxon word, the bit vector of the block's k-mers that name ITS taxon — and walks only those
+//           bits, in k-mer order, adding into its own float32 register.  No lane touches a k-mer that does not concern it: a
+//           k-mer names ~4.5 of 50 taxa against a saturated index, so the dense organisations above (one predicated add per
+//           taxon and k-mer) spend > 90 % of their issue slots on nothing.  The walk is as long as the busiest lane's (the read's
+//           own taxon: ~15 of 32 k-mers, most of them with upper levels); branches on record shape are rare and cheap.
+// Counts: the k_low shares ride along in the walk; unique k_low hits are a popcount against the ballot of "n0 == 1".
+constexpr int kBlkWarps = 8;
+
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane)
+{
+    // row `lane` in, column `lane` out: bit i of the result = bit `lane` of lane i's input
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;   // columns with (col & j) == 0
+        const uint32_t y = __shfl_xor_sync(kFull, x, j);
+        x = (lane & (uint32_t)j) ? ((x & ~m) | ((y & ~m) >> j)) : ((x & m) | ((y & m) << j));
+    }
+    return x;
+}
+
+struct BlkWarpMem {
+    float2 vq[32];            // per k-mer of the block: .x = float(w_0 * (1.f / n0)), .y = bits of 2^24 / n0 (0 for n0 < 2)
+    uint32_t up[32];          // 0: no taxon above k_low; 0xffffffff: see rec[]; else the only up pair (taxon | levels << 16)
+    uint64_t rec[32][4];      // records with several up pairs or in list format
+};
+
+template <bool TWO>
+__global__ void __launch_bounds__(kBlkWarps * 32) score_blocks_kernel(const uint64_t *__restrict__ rec, const uint64_t *__restrict__ read_koff, uint32_t n_reads,
+                                                                       LevelParams lp, OverflowPeers peers, float *__restrict__ scores,
+                                                                       unsigned long long *__restrict__ cnt_fx, unsigned long long *__restrict__ cnt_unique)
+{
+    __shared__ BlkWarpMem s_w[kBlkWarps];
+    __shared__ float2 s_vqtab[72];
+    __shared__ float s_inv[72];
+    __shared__ uint32_t s_q32[72];                                      // 2^32 / n
+    __shared__ unsigned long long s_fx[6 * 64];                         // CTA totals [level][taxon - 1], 2^-32 units (levels above k_low)
+    __shared__ uint32_t s_un[6 * 64];
+    __shared__ uint32_t s_hist[64 * 8];                                 // [taxon - 1][h]: k-mers where the taxon is alone at its levels 1 .. h-1
+    const int tid = threadIdx.x, T = lp.n_taxa, NK = lp.num_k;
+    const uint32_t lane = tid & 31u;
+    const int w = tid >> 5;
+    BlkWarpMem &M = s_w[w];
+    float wj[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { const int k = lp.k_low + j; wj[j] = (float)(k * k) / 625.f; }      // Compare.hpp:392
+    for (int i = tid; i < 6 * 64; i += blockDim.x) { s_fx[i] = 0; s_un[i] = 0; }
+    for (int i = tid; i < 64 * 8; i += blockDim.x) s_hist[i] = 0;
+    if (tid < 72) {
+        const float inv = tid ? __fdiv_rn(1.f, (float)tid) : 0.f;       // Compare.hpp:924: 1.f / numOfEntries
+        s_inv[tid] = inv;
+        s_vqtab[tid] = make_float2(__fmul_rn(wj[0], inv), __uint_as_float(tid >= 2 ? (uint32_t)(((1u << 24) + (tid >> 1)) / tid) : 0u));
+        s_q32[tid] = tid >= 2 ? inv_fx((uint32_t)tid) : 0u;
+    }
+    __syncthreads();
+    unsigned long long fa64 = 0, fb64 = 0;                              // k_low sums of this lane's taxa (lane + 1, lane + 33), 2^-24 units
+    uint32_t ua = 0, ub = 0;                                            // their unique k_low hits
+
+    // the levels 1 .. h-1 of taxon c (0-based) at k-mer i of the block
+    auto upper = [&](uint32_t i, uint32_t c, float acc) -> float {
+        const uint32_t u = M.up[i];
+        if (u != 0xffffffffu) {
+            const uint32_t h = u >> 16;
+#pragma unroll
+            for (int j = 1; j < 6; ++j) if ((uint32_t)j < h) acc = __fadd_rn(acc, wj[j]);            // alone there: w * (1.f / 1) == w
+            atomicAdd(&s_hist[c * 8 + (h & 7u)], 1u);
+            return acc;
+        }
+        // several taxa above k_low (or a list record): this taxon's levels and the level sizes from the record's pairs
+        const uint64_t w0 = M.rec[i][0], w1 = M.rec[i][1], w2 = M.rec[i][2], w3 = M.rec[i][3];
+        uint32_t nj[6] = {0, 0, 0, 0, 0, 0}, hme = 0;
+        auto see = [&](uint32_t e) {
+            const uint32_t h = e >> 16;
+            if ((e & 0xffffu) == c + 1u) hme = h;
+#pragma unroll
+            for (int j = 1; j < 6; ++j) nj[j] += (uint32_t)j < h ? 1u : 0u;
+        };
+        if (rec_is_mask(w0)) {
+            const uint64_t pw[3] = {w1, w2, w3};
+#pragma unroll
+            for (int k = 0; k < kRecUpPairs; ++k) { const uint32_t e = up_pair(pw, k); if (e) see(e); }
+        } else {
+            const uint32_t n = rec_count(w0);
+            const uint32_t *list = rec_overflow(w0) ? peers.base[rec_owner(w0)] + w1 : nullptr;
+            for (uint32_t k = 0; k < n; ++k) see(list ? __ldg(list + k) : (uint32_t)((k < 3 ? w1 : k < 6 ? w2 : w3) >> (kPairBits * (k % 3))) & kPairMask);
+        }
+#pragma unroll
+        for (int j = 1; j < 6; ++j) {
+            if ((uint32_t)j >= hme) break;
+            acc = __fadd_rn(acc, __fmul_rn(wj[j], s_inv[nj[j] < 72u ? nj[j] : 0u]));
+            if (nj[j] == 1u) atomicAdd(&s_un[j * 64 + c], 1u);
+            else atomicAdd(&s_fx[j * 64 + c], (unsigned long long)s_q32[nj[j] < 72u ? nj[j] : 0u]);
+        }
+        return acc;
+    };
+
+    const uint32_t warps_total = gridDim.x * kBlkWarps;
+#pragma unroll 1
+    for (uint32_t r = blockIdx.x * kBlkWarps + w; r < n_reads; r += warps_total) {
+        const uint64_t s0 = read_koff[r];
+        const uint32_t ni = (uint32_t)(read_koff[r + 1] - s0);
+        const uint64_t *p = rec + s0 * kRecWords;
+        float sa = 0.f, sb = 0.f;
+        uint32_t fa = 0, fb = 0;
+        uint64_t nx[4] = {0, 0, 0, 0};
+        if (lane < ni) asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(p + (uint64_t)lane * kRecWords));
+#pragma unroll 1
+        for (uint32_t b0 = 0; b0 < ni; b0 += 32) {
+            // ---- setup, lane = k-mer b0 + lane
+            const uint64_t w0 = nx[0], w1 = nx[1], w2 = nx[2], w3 = nx[3];
+            nx[0] = nx[1] = nx[2] = nx[3] = 0;
+            if (b0 + 32 + lane < ni)
+                asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(p + (uint64_t)(b0 + 32 + lane) * kRecWords));
+            const uint32_t n0 = rec_count(w0), hmax = rec_hmax(w0);
+            uint64_t mk = w1, um = 0;
+            uint32_t upd = 0;
+            if (n0 && !rec_is_mask(w0)) {
+                // list record inside a small taxonomy (more than six taxa above k_low, or a span read from HBM): mask from its pairs
+                const uint32_t *list = rec_overflow(w0) ? peers.base[rec_owner(w0)] + w1 : nullptr;
+                mk = 0;
+                for (uint32_t k = 0; k < n0; ++k) {
+                    const uint32_t e = list ? __ldg(list + k) : (uint32_t)((k < 3 ? w1 : k < 6 ? w2 : w3) >> (kPairBits * (k % 3))) & kPairMask;
+                    mk |= 1ull << ((e & 0xffffu) - 1u);
+                    if ((e >> 16) > 1u) um |= 1ull << ((e & 0xffffu) - 1u);
+                }
+                upd = um ? 0xffffffffu : 0u;
+            } else if (hmax > 1u) {
+                const uint32_t p0 = (uint32_t)w2 & kPairMask;
+                if ((w2 >> kPairBits) == 0 && w3 == 0) { upd = p0; um = 1ull << ((p0 & 0xffffu) - 1u); }
+                else {
+                    const uint64_t pw[3] = {w1, w2, w3};
+#pragma unroll
+                    for (int k = 0; k < kRecUpPairs; ++k) { const uint32_t e = up_pair(pw, k); if (e) um |= 1ull << ((e & 0xffffu) - 1u); }
+                    upd = 0xffffffffu;
+                }
+            }
+            M.vq[lane] = s_vqtab[n0 < 72u ? n0 : 0u];
+            M.up[lane] = upd;
+            if (upd == 0xffffffffu) { M.rec[lane][0] = w0; M.rec[lane][1] = w1; M.rec[lane][2] = w2; M.rec[lane][3] = w3; }
+            const uint32_t uni = __ballot_sync(kFull, n0 == 1u);
+            const bool any_up = __any_sync(kFull, um != 0);
+            // ---- transposes: lane = taxon from here on
+            const uint32_t tlo = transpose32((uint32_t)mk, lane);
+            const uint32_t thi = TWO ? transpose32((uint32_t)(mk >> 32), lane) : 0u;
+            uint32_t xlo = 0, xhi = 0;
+            if (any_up) { xlo = transpose32((uint32_t)um, lane); if (TWO) xhi = transpose32((uint32_t)(um >> 32), lane); }
+            __syncwarp();
+            ua += __popc(tlo & uni);
+            if (TWO) ub += __popc(thi & uni);
+            // ---- main: this lane's k-mers only, in order (Compare.hpp:530 for level k_low, then the levels above)
+            for (uint32_t bits = tlo; bits; bits &= bits - 1u) {
+                const uint32_t i = (uint32_t)__ffs((int)bits) - 1u;
+                const float2 vq = M.vq[i];
+                sa = __fadd_rn(sa, vq.x);
+                fa += __float_as_uint(vq.y);
+                if ((xlo >> i) & 1u) sa = upper(i, lane, sa);
+            }
+            if (TWO) {
+                for (uint32_t bits = thi; bits; bits &= bits - 1u) {
+                    const uint32_t i = (uint32_t)__ffs((int)bits) - 1u;
+                    const float2 vq = M.vq[i];
+                    sb = __fadd_rn(sb, vq.x);
+                    fb += __float_as_uint(vq.y);
+                    if ((xhi >> i) & 1u) sb = upper(i, lane + 32u, sb);
+                }
+            }
+            // a k-mer adds at most 2^23 units to a k_low sum: widen before 32 bits could overflow
+            if ((b0 & 255u) == 224u) { fa64 += fa; fb64 += fb; fa = fb = 0; }
+            __syncwarp();
+        }
+        fa64 += fa; fb64 += fb;
+        if (scores) {
+            float *row = scores + (uint64_t)r * T;
+            if (lane == 0) row[0] = 0.f;
+            if ((int)lane + 1 < T) row[lane + 1] = sa;
+            if (TWO && (int)lane + 33 < T) row[lane + 33] = sb;
+        }
+    }
+    if ((int)lane + 1 < T) {
+        if (fa64) atomicAdd(&s_fx[lane], fa64 << kFxShift);
+        if (ua) atomicAdd(&s_un[lane], ua);
+    }
+    if (TWO && (int)lane + 33 < T) {
+        if (fb64) atomicAdd(&s_fx[lane + 32], fb64 << kFxShift);
+        if (ub) atomicAdd(&s_un[lane + 32], ub);
+    }
+    __syncthreads();
+    for (int i = tid; i < NK * 64; i += blockDim.x) {
+        const int j = i / 64, c = i % 64;
+        if (c >= T - 1) continue;
+        unsigned long long u = s_un[i];
+        if (j >= 1) for (int h = j + 1; h < 8; ++h) u += s_hist[c * 8 + h];     // alone at the levels 1 .. h-1
+        if (u) atomicAdd(cnt_unique + (size_t)j * T + c + 1, u);
+        if (s_fx[i]) atomicAdd(cnt_fx + (size_t)j * T + c + 1, s_fx[i]);
+    }
+}
+
 }  // namespace
 
 void launch_order_ops(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t r0, uint32_t r1, uint64_t n_kmers, uint32_t max_inst,
@@ -1086,6 +1490,45 @@ void launch_max_instances(cudaStream_t s, const uint64_t *read_koff, uint32_t n_
     if (!n_reads) return;
     max_instances_kernel<<<div_up(n_reads, 256u), 256, 0, s>>>(read_koff, n_reads, out);
     ++*launches;
+}
+
+void launch_score_sorted(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp, OverflowPeers peers,
+                         float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, int lanes_hint, uint64_t *launches)
+{
+    if (!n_reads) return;
+    KASA_REQUIRE(ops_mask_stream(lp), -6, "the presorted scoring kernel needs <= 64 taxa and <= 6 levels");
+    auto go = [&](auto kern, int lanes) {
+        int per_sm = 1;
+        KASA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSortedBlock, 0));
+        unsigned grid = (unsigned)div_up<uint64_t>(n_reads, kSortedBlock / lanes);
+        const unsigned resident = (unsigned)(kSMs * (per_sm > 0 ? per_sm : 1));
+        if (grid > resident) grid = resident;
+        kern<<<grid, kSortedBlock, 0, s>>>(rec, read_koff, n_reads, lp, peers, scores, cnt_fx, cnt_unique);
+    };
+    const int taxa = lp.n_taxa - 1;
+    if (lanes_hint == 0 || lanes_hint == 32) {
+        // warp per read, 32 k-mers at a time (score_blocks_kernel): the default
+        auto gow = [&](auto kern) {
+            int per_sm = 1;
+            KASA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlkWarps * 32, 0));
+            unsigned grid = (unsigned)div_up<uint64_t>(n_reads, kBlkWarps);
+            const unsigned resident = (unsigned)(kSMs * (per_sm > 0 ? per_sm : 1));
+            if (grid > resident) grid = resident;
+            kern<<<grid, kBlkWarps * 32, 0, s>>>(rec, read_koff, n_reads, lp, peers, scores, cnt_fx, cnt_unique);
+        };
+        if (taxa > 32) gow(score_blocks_kernel<true>); else gow(score_blocks_kernel<false>);
+        ++*launches;
+        KASA_CUDA_TRY(cudaGetLastError());
+        return;
+    }
+    // threads per read x taxa per thread (lanes_hint = 1, 2 or 4: tuning knob KASA_TUNE_SCORE_LANES)
+    if (taxa <= 8) go(score_sorted_kernel<1, 8>, 1);
+    else if (taxa <= 16) { if (lanes_hint == 1) go(score_sorted_kernel<1, 16>, 1); else go(score_sorted_kernel<2, 8>, 2); }
+    else if (taxa <= 32) { if (lanes_hint == 1) go(score_sorted_kernel<1, 32>, 1); else if (lanes_hint == 2) go(score_sorted_kernel<2, 16>, 2); else go(score_sorted_kernel<4, 8>, 4); }
+    else if (taxa <= 52) { if (lanes_hint == 2) go(score_sorted_kernel<2, 26>, 2); else go(score_sorted_kernel<4, 13>, 4); }
+    else { if (lanes_hint == 2) go(score_sorted_kernel<2, 32>, 2); else go(score_sorted_kernel<4, 16>, 4); }
+    ++*launches;
+    KASA_CUDA_TRY(cudaGetLastError());
 }
 
 }  // namespace kasa

@@ -74,6 +74,12 @@ inline bool scores_counted_by_order_ops(const LevelParams &lp, bool sparse_hits)
 void launch_accumulate(cudaStream_t s, OpsWorkspace ws, uint32_t r0, uint32_t r1, LevelParams lp, bool exact_stream, float *scores, HitsOut hits,
                        unsigned long long *cnt_fx, unsigned long long *cnt_unique, uint32_t *err_flag, uint64_t *launches);
 
+// Presorted batches (every read has <= kPresortMax k-mers, extract.cuh) of a content file with <= 64 taxa and <= 6 levels
+// (ops_mask_stream): scores (dense [reads][n_taxa] or nullptr = profile only) and counts straight from the match records, which
+// lie in summation order already; replaces launch_order_ops + launch_accumulate.  lanes_hint: 0 = default threads per read.
+void launch_score_sorted(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp, OverflowPeers peers,
+                         float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, int lanes_hint, uint64_t *launches);
+
 // largest number of instances of any read -> *out (device u32)
 void launch_max_instances(cudaStream_t s, const uint64_t *read_koff, uint32_t n_reads, uint32_t *out, uint64_t *launches);
 

@@ -344,9 +344,29 @@ def identify_kmers_ordered(kmers: np.ndarray, read_id: np.ndarray, n_reads: int,
     return IdentifyResult(len(read_id), ca, cu, sc)
 
 
+PRESORT_MAX = 1024     # kasa_b200/csrc/extract.cuh kPresortMax
+
+
+def presorted_emission(kmers: np.ndarray, read_id: np.ndarray, presort_max: int = PRESORT_MAX):
+    """The CUDA library's emission order (extract.cu "presorted emission"): the k-mers of a read of at most `presort_max` k-mers in
+    ascending order (equal k-mers keep the reference's emission order), longer reads untouched.  read_id is non-decreasing."""
+    n = len(read_id)
+    if n == 0:
+        return kmers, read_id
+    pos = np.arange(n, dtype=np.uint64)
+    long_read = np.bincount(read_id)[read_id] > presort_max
+    hi = np.where(long_read, np.uint64(0), kmers[:, 1])
+    lo = np.where(long_read, pos, kmers[:, 0])
+    order = np.lexsort((pos, lo, hi, read_id))
+    return np.ascontiguousarray(kmers[order]), np.ascontiguousarray(read_id[order])
+
+
 def identify_reads_ordered(reads: list[list[bytes]], index: np.ndarray, K: int, k_high: int, k_low: int, six: bool,
                            taxid_of_idx: np.ndarray, table: np.ndarray | None = None, sort_bits: int = 32) -> IdentifyResult:
-    k, ids = read_kmers(reads, K, k_low, six, table)
+    """KASA_SCORE_ORDERED: the library emits the k-mers of ordinary reads presorted and sorts the batch stably on the leading
+    `sort_bits` key bits, so a read's scores are summed in ascending k-mer order (reads longer than PRESORT_MAX k-mers: ascending
+    on the leading sort_bits, then emission order)."""
+    k, ids = presorted_emission(*read_kmers(reads, K, k_low, six, table))
     return identify_kmers_ordered(k, ids, len(reads), index, K, k_high, k_low, taxid_of_idx, sort_bits)
 
 

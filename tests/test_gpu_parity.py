@@ -44,10 +44,12 @@ def _k12_reads():
 # ----------------------------------------------------------------------------------------- extraction
 @pytest.mark.parametrize("frames,k_low", [(6, 7), (3, 7), (6, 12), (3, 1)])
 def test_extract_matches_oracle_k12(frames, k_low):
-    reads = _k12_reads() + [b"", b"ACG", b"acgtnACGTN" * 30, b"N" * 40 + b"ACGT" * 20]
+    rng = np.random.default_rng(11)
+    long_read = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=2500))      # > 1024 k-mers: not presorted
+    reads = _k12_reads() + [b"", b"ACG", b"acgtnACGTN" * 30, b"N" * 40 + b"ACGT" * 20, b"A" * 250, long_read, b"ACGTTGCA" * 60, long_read[:530]]
     ctx = _ctx(frames=frames, k_low=k_low, k_high=12)
     lo, hi, rid = ctx.dbg_extract(reads)
-    want_k, want_id = O.read_kmers([[r] for r in reads], 12, k_low, frames == 6)
+    want_k, want_id = O.presorted_emission(*O.read_kmers([[r] for r in reads], 12, k_low, frames == 6))
     assert len(lo) == len(want_k)
     assert np.array_equal(lo, want_k[:, 0])
     assert np.array_equal(rid, want_id)
@@ -62,7 +64,7 @@ def test_extract_matches_oracle_k25_paired():
         first.append(len(seqs))
     ctx = _ctx(highest_k=25, k_high=25, k_low=7, frames=6)
     lo, hi, rid = ctx.dbg_extract(seqs, read_first_seq=np.array(first, dtype=np.uint32))
-    want_k, want_id = O.read_kmers([[x[1], y[1]] for x, y in zip(a, b)], 25, 7, True)
+    want_k, want_id = O.presorted_emission(*O.read_kmers([[x[1], y[1]] for x, y in zip(a, b)], 25, 7, True))
     assert np.array_equal(lo, want_k[:, 0]) and np.array_equal(hi, want_k[:, 1])
     assert np.array_equal(rid, want_id)
     ctx.close()
@@ -75,10 +77,10 @@ def test_custom_codon_table_is_a_parameter():
     plain = _ctx()                                            # two contexts with different tables alive at once
     ctx = _ctx(codon_table=table)
     lo, _, _ = ctx.dbg_extract(reads)
-    want, _ = O.read_kmers([[r] for r in reads], 12, 7, False, table)
+    want, _ = O.presorted_emission(*O.read_kmers([[r] for r in reads], 12, 7, False, table))
     assert np.array_equal(lo, want[:, 0])
     lo_plain, _, _ = plain.dbg_extract(reads)
-    want_plain, _ = O.read_kmers([[r] for r in reads], 12, 7, False)
+    want_plain, _ = O.presorted_emission(*O.read_kmers([[r] for r in reads], 12, 7, False))
     assert np.array_equal(lo_plain, want_plain[:, 0]) and not np.array_equal(lo_plain, lo)
     ctx.close()
     plain.close()
