@@ -179,6 +179,14 @@ int kasa_identify_batch(kasa_ctx *ctx, const kasa_read_batch *in, kasa_batch_res
 int kasa_identify_submit(kasa_ctx *ctx, const kasa_read_batch *in, kasa_batch_result *out);
 int kasa_identify_wait(kasa_ctx *ctx);
 
+/* Page-locked host memory for the buffers of a batch.  kasa_identify_submit() is only asynchronous when the host buffers it
+ * copies from and into (bases, seq_start, seq_len, read_first_seq, scores, hit_*) are page-locked: from pageable memory the CUDA
+ * copies are staged synchronously and every submit waits for its own batch (results are the same, the overlap is lost).  The
+ * reference has no counterpart (its batches live in std::vector / STXXL memory, Compare.hpp:2983-3110); a caller that keeps
+ * its own buffers may cudaHostRegister them instead.                                                                    */
+int kasa_host_alloc(void **ptr, uint64_t bytes);
+int kasa_host_free(void *ptr);
+
 /* Replaces: the per-thread count reduction (Compare.hpp:3445-3454).  count_all / count_unique are
  * [numK][n_taxa], level 0 = k_high (kASA _aOfK, kASA.hpp:299-302).  Resets the accumulators
  * (Compare.hpp:3748-3752).                                                                             */

@@ -874,6 +874,20 @@ int kasa_identify_wait(kasa_ctx *c)
     KASA_API_END(c)
 }
 
+int kasa_host_alloc(void **ptr, uint64_t bytes)
+{
+    if (!ptr) return KASA_ERR_ARG;
+    *ptr = nullptr;
+    if (bytes == 0) return KASA_OK;
+    return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? KASA_OK : KASA_ERR_NOMEM;
+}
+
+int kasa_host_free(void *ptr)
+{
+    if (!ptr) return KASA_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? KASA_OK : KASA_ERR_CUDA;
+}
+
 int kasa_identify_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_result *out)
 {
     KASA_REQUIRE_PLAIN(c && in && out);

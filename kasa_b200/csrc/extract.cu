@@ -19,7 +19,7 @@ void upload_codon_table(const uint8_t table512[512], uint8_t *d_table, cudaStrea
 
 namespace {
 
-constexpr int kExtractWarps = 8;
+constexpr int kExtractWarps = 4;      // shared memory per warp (presort buffers) sets the occupancy: small CTAs waste less of it
 constexpr int kSeg = 256;              // output positions per shared-memory segment
 constexpr int kAaPad = 3 * 24 + 8;     // 3*(K-1) extra letters for K <= 25
 
@@ -265,13 +265,20 @@ __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(Pa
         const uint64_t xl = glo[g], xh = WIDE ? ghi[g] : 0ull;
         const uint32_t bk = (uint32_t)((WIDE ? xh : xl) >> bsh) & (kSortBuckets - 1);
         const uint32_t b0 = bcnt[bk], b1 = bcnt[bk + 1];
+        // the high 32-bit word of the key decides almost always; only equal high words need the whole k-mer
+        const uint32_t *top = reinterpret_cast<const uint32_t *>(WIDE ? ghi : glo);
+        const uint32_t xt = top[2 * g + 1];
         uint32_t less = 0;
         for (uint32_t y = b0; y < b1; ++y) {
-            const uint64_t ol = glo[y];
-            bool lt;
-            if (WIDE) { const uint64_t oh = ghi[y]; lt = oh != xh ? oh < xh : (ol != xl ? ol < xl : y < g); }
-            else lt = ol != xl ? ol < xl : y < g;                  // equal k-mers: any fixed order (their records are identical)
-            less += lt ? 1u : 0u;
+            const uint32_t ot = top[2 * y + 1];
+            less += ot < xt ? 1u : 0u;
+            if (ot == xt && y != g) {
+                const uint64_t ol = glo[y];
+                bool lt;
+                if (WIDE) { const uint64_t oh = ghi[y]; lt = oh != xh ? oh < xh : (ol != xl ? ol < xl : y < g); }
+                else lt = ol != xl ? ol < xl : y < g;              // equal k-mers: any fixed order (their records are identical)
+                less += lt ? 1u : 0u;
+            }
         }
         klo[b0 + less] = xl;
         if (WIDE) khi[b0 + less] = xh;

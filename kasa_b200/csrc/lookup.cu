@@ -336,6 +336,19 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
     constexpr int QPT = kLookupTile / kLookupBlock;
     const int tid = threadIdx.x;
     const uint64_t tile = blockIdx.x;
+    // the tile's span bounds and its queries are requested together (the queries' first use comes after the span copies are issued)
+    Key qv[QPT];
+    uint32_t iv[QPT];
+    bool live[QPT];
+#pragma unroll
+    for (int r = 0; r < QPT; ++r) {
+        const uint32_t off = r * kLookupBlock + tid;
+        const uint64_t i = tile * tq + off;
+        live[r] = off < tq && i < n;
+        qv[r].lo = live[r] ? ldg_stream(q_lo + i) : 0ull;
+        qv[r].hi = (W && live[r]) ? ldg_stream(q_hi + i) : 0ull;
+        iv[r] = live[r] ? (inst ? ldg_stream(inst + i) : (uint32_t)i) : 0u;      // inst == nullptr: record i goes to slot i
+    }
     const int64_t a = (int64_t)part[2 * tile], b = (int64_t)part[2 * tile + 1];
     const bool staged = b - a <= kSpanCap;
     const int span = staged ? (int)(b - a) : 0;
@@ -349,19 +362,6 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
         if (W) bulk_g2s(st.khi, idx.key_hi + ak, kb, &st.bar);
         if (MASK) bulk_g2s(st.gm, idx.gmask + ak, kb, &st.bar);
         bulk_g2s(st.tax, idx.tax + ac, cb, &st.bar);
-    }
-    // this thread's queries and instance ids: their latency overlaps the span staging
-    Key qv[QPT];
-    uint32_t iv[QPT];
-    bool live[QPT];
-#pragma unroll
-    for (int r = 0; r < QPT; ++r) {
-        const uint32_t off = r * kLookupBlock + tid;
-        const uint64_t i = tile * tq + off;
-        live[r] = off < tq && i < n;
-        qv[r].lo = live[r] ? ldg_stream(q_lo + i) : 0ull;
-        qv[r].hi = (W && live[r]) ? ldg_stream(q_hi + i) : 0ull;
-        iv[r] = live[r] ? (inst ? ldg_stream(inst + i) : (uint32_t)i) : 0u;      // inst == nullptr: record i goes to slot i
     }
     __syncthreads();                                          // the barrier word is initialised
     SmemAcc sacc{st.klo + (a - ak), st.khi + (W ? (a - ak) : 0), st.tax + (a - ac)};

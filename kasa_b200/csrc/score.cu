@@ -1228,8 +1228,8 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane)
 
 struct BlkWarpMem {
     float2 vq[32];            // per k-mer of the block: .x = float(w_0 * (1.f / n0)), .y = bits of 2^24 / n0 (0 for n0 < 2)
-    uint32_t up[32];          // 0: no taxon above k_low; 0xffffffff: see rec[]; else the only up pair (taxon | levels << 16)
-    uint64_t rec[32][4];      // records with several up pairs or in list format
+    float val[32][8];         // k-mers with taxa above k_low: [j - 1] = float(w_j * (1.f / n_j)) for the levels j = 1 .. 5
+    uint8_t h[32][64];        // ... and [taxon - 1] = number of levels that taxon matches (only the entries of up pairs are written)
 };
 
 template <bool TWO>
@@ -1237,7 +1237,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_blocks_kernel(const uint
                                                                        LevelParams lp, OverflowPeers peers, float *__restrict__ scores,
                                                                        unsigned long long *__restrict__ cnt_fx, unsigned long long *__restrict__ cnt_unique)
 {
-    __shared__ BlkWarpMem s_w[kBlkWarps];
+    __shared__ __align__(16) BlkWarpMem s_w[kBlkWarps];
     __shared__ float2 s_vqtab[72];
     __shared__ float s_inv[72];
     __shared__ uint32_t s_q32[72];                                      // 2^32 / n
@@ -1263,41 +1263,16 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_blocks_kernel(const uint
     unsigned long long fa64 = 0, fb64 = 0;                              // k_low sums of this lane's taxa (lane + 1, lane + 33), 2^-24 units
     uint32_t ua = 0, ub = 0;                                            // their unique k_low hits
 
-    // the levels 1 .. h-1 of taxon c (0-based) at k-mer i of the block
+    // the levels 1 .. h-1 of taxon c (0-based) at k-mer i of the block: values and level count were laid out by the k-mer's lane
     auto upper = [&](uint32_t i, uint32_t c, float acc) -> float {
-        const uint32_t u = M.up[i];
-        if (u != 0xffffffffu) {
-            const uint32_t h = u >> 16;
-#pragma unroll
-            for (int j = 1; j < 6; ++j) if ((uint32_t)j < h) acc = __fadd_rn(acc, wj[j]);            // alone there: w * (1.f / 1) == w
-            atomicAdd(&s_hist[c * 8 + (h & 7u)], 1u);
-            return acc;
-        }
-        // several taxa above k_low (or a list record): this taxon's levels and the level sizes from the record's pairs
-        const uint64_t w0 = M.rec[i][0], w1 = M.rec[i][1], w2 = M.rec[i][2], w3 = M.rec[i][3];
-        uint32_t nj[6] = {0, 0, 0, 0, 0, 0}, hme = 0;
-        auto see = [&](uint32_t e) {
-            const uint32_t h = e >> 16;
-            if ((e & 0xffffu) == c + 1u) hme = h;
-#pragma unroll
-            for (int j = 1; j < 6; ++j) nj[j] += (uint32_t)j < h ? 1u : 0u;
-        };
-        if (rec_is_mask(w0)) {
-            const uint64_t pw[3] = {w1, w2, w3};
-#pragma unroll
-            for (int k = 0; k < kRecUpPairs; ++k) { const uint32_t e = up_pair(pw, k); if (e) see(e); }
-        } else {
-            const uint32_t n = rec_count(w0);
-            const uint32_t *list = rec_overflow(w0) ? peers.base[rec_owner(w0)] + w1 : nullptr;
-            for (uint32_t k = 0; k < n; ++k) see(list ? __ldg(list + k) : (uint32_t)((k < 3 ? w1 : k < 6 ? w2 : w3) >> (kPairBits * (k % 3))) & kPairMask);
-        }
-#pragma unroll
-        for (int j = 1; j < 6; ++j) {
-            if ((uint32_t)j >= hme) break;
-            acc = __fadd_rn(acc, __fmul_rn(wj[j], s_inv[nj[j] < 72u ? nj[j] : 0u]));
-            if (nj[j] == 1u) atomicAdd(&s_un[j * 64 + c], 1u);
-            else atomicAdd(&s_fx[j * 64 + c], (unsigned long long)s_q32[nj[j] < 72u ? nj[j] : 0u]);
-        }
+        const uint32_t h = M.h[i][c];
+        const float4 v = *reinterpret_cast<const float4 *>(&M.val[i][0]);
+        const float v5 = M.val[i][4];
+        if (h > 1u) acc = __fadd_rn(acc, v.x);
+        if (h > 2u) acc = __fadd_rn(acc, v.y);
+        if (h > 3u) acc = __fadd_rn(acc, v.z);
+        if (h > 4u) acc = __fadd_rn(acc, v.w);
+        if (h > 5u) acc = __fadd_rn(acc, v5);
         return acc;
     };
 
@@ -1320,7 +1295,51 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_blocks_kernel(const uint
                 asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(p + (uint64_t)(b0 + 32 + lane) * kRecWords));
             const uint32_t n0 = rec_count(w0), hmax = rec_hmax(w0);
             uint64_t mk = w1, um = 0;
-            uint32_t upd = 0;
+            if (n0 && hmax > 1u) {
+                // taxa above k_low: every up pair (taxon | levels << 16) leaves its level count, the k-mer its level values, and the
+                // counts of the levels above k_low are taken here (all lanes at once) rather than in the walk (one lane at a time)
+                const bool is_mask = rec_is_mask(w0);
+                const uint32_t p0 = (uint32_t)w2 & kPairMask;
+                if (is_mask && (w2 >> kPairBits) == 0 && w3 == 0) {
+                    const uint32_t c = (p0 & 0xffffu) - 1u, h = p0 >> 16;                     // the usual case: one taxon, alone at its levels
+                    um = 1ull << c;
+                    M.h[lane][c] = (uint8_t)h;
+                    *reinterpret_cast<float4 *>(&M.val[lane][0]) = make_float4(wj[1], wj[2], wj[3], wj[4]);      // w * (1.f / 1) == w
+                    M.val[lane][4] = wj[5];
+                    atomicAdd(&s_hist[c * 8 + (h & 7u)], 1u);
+                } else {
+                    const uint32_t *list = !is_mask && rec_overflow(w0) ? peers.base[rec_owner(w0)] + w1 : nullptr;
+                    const uint32_t np = is_mask ? (uint32_t)kRecUpPairs : n0;
+                    auto pair_at = [&](uint32_t k) -> uint32_t {
+                        if (list) return __ldg(list + k);
+                        const uint32_t word = is_mask ? 3u + k : k;                            // mask records keep their pairs in w2, w3
+                        return (uint32_t)((word < 3u ? w1 : word < 6u ? w2 : w3) >> (kPairBits * (word % 3u))) & kPairMask;
+                    };
+                    uint32_t nj[6] = {0, 0, 0, 0, 0, 0};
+                    for (uint32_t k = 0; k < np; ++k) {
+                        const uint32_t h = pair_at(k) >> 16;                                   // 0 for an empty pair
+#pragma unroll
+                        for (int j = 1; j < 6; ++j) nj[j] += (uint32_t)j < h ? 1u : 0u;
+                    }
+                    float vj[6];
+#pragma unroll
+                    for (int j = 1; j < 6; ++j) vj[j] = __fmul_rn(wj[j], s_inv[nj[j] < 72u ? nj[j] : 0u]);
+                    *reinterpret_cast<float4 *>(&M.val[lane][0]) = make_float4(vj[1], vj[2], vj[3], vj[4]);
+                    M.val[lane][4] = vj[5];
+                    for (uint32_t k = 0; k < np; ++k) {
+                        const uint32_t e = pair_at(k), c = (e & 0xffffu) - 1u, h = e >> 16;
+                        if (h < 2u) continue;
+                        um |= 1ull << c;
+                        M.h[lane][c] = (uint8_t)h;
+#pragma unroll
+                        for (int j = 1; j < 6; ++j) {
+                            if ((uint32_t)j >= h) break;
+                            if (nj[j] == 1u) atomicAdd(&s_un[j * 64 + c], 1u);
+                            else atomicAdd(&s_fx[j * 64 + c], (unsigned long long)s_q32[nj[j] < 72u ? nj[j] : 0u]);
+                        }
+                    }
+                }
+            }
             if (n0 && !rec_is_mask(w0)) {
                 // list record inside a small taxonomy (more than six taxa above k_low, or a span read from HBM): mask from its pairs
                 const uint32_t *list = rec_overflow(w0) ? peers.base[rec_owner(w0)] + w1 : nullptr;
@@ -1328,22 +1347,9 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_blocks_kernel(const uint
                 for (uint32_t k = 0; k < n0; ++k) {
                     const uint32_t e = list ? __ldg(list + k) : (uint32_t)((k < 3 ? w1 : k < 6 ? w2 : w3) >> (kPairBits * (k % 3))) & kPairMask;
                     mk |= 1ull << ((e & 0xffffu) - 1u);
-                    if ((e >> 16) > 1u) um |= 1ull << ((e & 0xffffu) - 1u);
-                }
-                upd = um ? 0xffffffffu : 0u;
-            } else if (hmax > 1u) {
-                const uint32_t p0 = (uint32_t)w2 & kPairMask;
-                if ((w2 >> kPairBits) == 0 && w3 == 0) { upd = p0; um = 1ull << ((p0 & 0xffffu) - 1u); }
-                else {
-                    const uint64_t pw[3] = {w1, w2, w3};
-#pragma unroll
-                    for (int k = 0; k < kRecUpPairs; ++k) { const uint32_t e = up_pair(pw, k); if (e) um |= 1ull << ((e & 0xffffu) - 1u); }
-                    upd = 0xffffffffu;
                 }
             }
             M.vq[lane] = s_vqtab[n0 < 72u ? n0 : 0u];
-            M.up[lane] = upd;
-            if (upd == 0xffffffffu) { M.rec[lane][0] = w0; M.rec[lane][1] = w1; M.rec[lane][2] = w2; M.rec[lane][3] = w3; }
             const uint32_t uni = __ballot_sync(kFull, n0 == 1u);
             const bool any_up = __any_sync(kFull, um != 0);
             // ---- transposes: lane = taxon from here on

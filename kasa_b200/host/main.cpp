@@ -1,7 +1,9 @@
 // kasa_b200 host CLI — `build` and `identify` with kASA's flags, files and outputs (main.cpp:303-586 of the
 // reference for the flag names; formats per SURVEY.md §3.4 / Compare.hpp:1485-1890, 3466-3665).  FASTA/FASTQ(.gz)
 // parsing, content file, scoring and writers stay on the host; all k-mer work goes through libkasa_b200.so.
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <chrono>
 #include <iostream>
 
@@ -11,6 +13,37 @@
 using namespace kasa_host;
 
 namespace {
+
+// Growable array in page-locked host memory (kasa_host_alloc): the staging buffers of a batch.  Only the few vector operations
+// the batch loop uses; the contents are trivially copyable.
+template <typename T>
+struct Pinned {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    Pinned() = default;
+    Pinned(const Pinned &) = delete;
+    Pinned &operator=(const Pinned &) = delete;
+    Pinned(Pinned &&o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    ~Pinned() { kasa_host_free(p); }
+    void reserve(size_t want)
+    {
+        if (want <= cap) return;
+        size_t c = std::max<size_t>(want, cap * 2 + 64);
+        void *q = nullptr;
+        if (kasa_host_alloc(&q, c * sizeof(T)) != KASA_OK) throw std::runtime_error("page-locked host memory could not be allocated");
+        if (n) std::memcpy(q, p, n * sizeof(T));
+        kasa_host_free(p);
+        p = static_cast<T *>(q); cap = c;
+    }
+    void clear() { n = 0; }
+    void push_back(const T &v) { reserve(n + 1); p[n++] = v; }
+    void append(const T *src, size_t k) { reserve(n + k); std::memcpy(p + n, src, k * sizeof(T)); n += k; }
+    void assign(size_t k, const T &v) { reserve(k); std::fill(p, p + k, v); n = k; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+};
 
 struct Args {
     std::string mode, content, index, input, in1, in2, profile, rtt, tmp;
@@ -234,11 +267,12 @@ int run_identify(const Args &a)
     uint64_t n_kmers_total = 0, read_no = 0;
     // two host batches in flight per GPU (kasa_identify_submit / _wait): while the devices work on the later batches, the
     // oldest one's per-read output is formatted and written here, in input order
+    // (the staging buffers are page-locked, kasa_host_alloc: only then does submit return before the copies and kernels ran)
     struct HostBatch {
-        std::string chars;
-        std::vector<uint64_t> starts;
-        std::vector<uint32_t> lens, first;
-        std::vector<float> scores;
+        Pinned<char> chars;
+        Pinned<uint64_t> starts;
+        Pinned<uint32_t> lens, first;
+        Pinned<float> scores;
         kasa_batch_result res{};
         size_t b = 0, e = 0;
         kasa_ctx *ctx = nullptr;
@@ -255,7 +289,7 @@ int run_identify(const Args &a)
             h.first.push_back((uint32_t)h.starts.size());
             for (int m = 0; m < (paired ? 2 : 1); ++m) {
                 const std::string &s = (m ? mates[r] : reads[r]).seq;
-                h.starts.push_back(h.chars.size()); h.lens.push_back((uint32_t)s.size()); h.chars += s;
+                h.starts.push_back(h.chars.size()); h.lens.push_back((uint32_t)s.size()); h.chars.append(s.data(), s.size());
             }
         }
         h.first.push_back((uint32_t)h.starts.size());
@@ -271,7 +305,7 @@ int run_identify(const Args &a)
         kasa_ctx *ctx = h.ctx;
         check(kasa_identify_wait(ctx), ctx);                  // the oldest batch of that GPU = the oldest batch overall
         const size_t b = h.b, e = h.e;
-        const std::vector<float> &scores = h.scores;
+        const Pinned<float> &scores = h.scores;
         n_kmers_total += h.res.n_kmers;
         if (a.rtt.empty()) { read_no += e - b; return; }
         // ---- per-read output (Compare.hpp:1485-1890)
