@@ -236,6 +236,7 @@ void ensure_workspace(kasa_ctx *c)
     if (f & 64) throw Error{KASA_ERR_ARG, "KASA_SCORE_EXACT: a read has too many (k-mer, level) pairs for the shared-memory replay; use KASA_SCORE_ORDERED for long reads"};
     if (f & 128) throw Error{KASA_ERR_NOMEM, "more (read, taxon) hits than hit_capacity / max_batch_hits"};
     if (f & 256) throw Error{KASA_ERR_NOMEM, "a read hits more than 768 distinct taxa (limit of the sparse scoring cells)"};
+    if (f & 512) throw Error{KASA_ERR_INTERNAL, "the dense scoring kernel met a match record that is not in two-mask format"};
     throw Error{KASA_ERR_INTERNAL, "device error flag " + std::to_string(f)};
 }
 
@@ -688,6 +689,15 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
     return n;
 }
 
+// Presorted batch (every read was emitted in ascending k-mer order, extract.cuh) against a small content file: scores and counts come
+// straight from the match records (score.cuh launch_score_sorted); decided before the lookup, which then writes the record format
+// that kernel reads.
+static bool scores_straight_from_records(const kasa_ctx *c, uint32_t max_inst, bool want_hits)
+{
+    return c->p.score_mode != KASA_SCORE_EXACT && !want_hits && ops_mask_stream(level_params(c)) && max_inst <= (uint32_t)kPresortMax && c->score_sorted &&
+           !c->sh.on;
+}
+
 // Scoring stage (score.cuh) after the match records of the batch are in c->d_rec: op streams in the reference's summation
 // order, then scores and counts.  `cur` = sort buffer holding the sorted queries (KASA_SCORE_EXACT reads them).
 static void score_stage(kasa_ctx *c, kasa_ctx::Slot &sl, uint64_t n, uint32_t n_reads, uint32_t max_inst, int cur, bool want_dense, bool want_hits)
@@ -718,9 +728,9 @@ static void score_stage(kasa_ctx *c, kasa_ctx::Slot &sl, uint64_t n, uint32_t n_
     }
     // Presorted batch (every read was emitted in ascending k-mer order, extract.cuh) against a small content file: the records lie
     // in summation order, scores and counts come straight from them.
-    if (!exact && !want_hits && ops_mask_stream(lp) && max_inst <= (uint32_t)kPresortMax && c->score_sorted) {
+    if (scores_straight_from_records(c, max_inst, want_hits)) {
         launch_score_sorted(c->stream, c->d_rec, c->d_read_koff, n_reads, lp, peers, want_dense ? sl.scores : nullptr, c->d_cnt_fx, c->d_cnt_un,
-                            c->score_lanes, &c->launches);
+                            c->score_lanes, c->d_err, &c->launches);
         launch_fold_counts(c->stream, c->d_cnt_fx, c->d_cnt_un, lp, c->d_tot_all, c->d_tot_un, &c->launches);
         return;
     }
@@ -828,7 +838,7 @@ int kasa_identify_submit(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resu
         KASA_CUDA_TRY(cudaMemsetAsync(c->ovf.cursor, 0, 8, c->stream));
         launch_partition(c->stream, c->sb.w0[cur], c->sb.w1[cur], n, idx, lp, c->d_part, tq, sorted_from, &c->launches);
         launch_lookup(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, 0, idx, lp, c->d_part, c->d_rec, tq, c->ovf, 0, c->d_err,
-                      &c->launches);
+                      &c->launches, scores_straight_from_records(c, max_inst, want_hits) && score_sorted_two_masks(c->score_lanes));
         KASA_CUDA_TRY(cudaEventRecord(sl.sev[5], c->stream));
         score_stage(c, sl, n, in->n_reads, max_inst, cur, want_dense, want_hits);
     } else {

@@ -201,6 +201,24 @@ __device__ __forceinline__ bool up_pair_raise(uint64_t (&uw)[2], uint32_t taxon,
     return done;
 }
 
+// two-mask format: raise (or add) the level count of a taxon among the <= 3 pairs of one word; false if a fourth taxon would be needed
+__device__ __forceinline__ bool up3_pair_raise(uint64_t &uw, uint32_t taxon, uint32_t h)
+{
+    bool done = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int sh = kPairBits * k;
+        const uint32_t p = (uint32_t)(uw >> sh) & kPairMask;
+        if (done) continue;
+        if (!p) { uw |= (uint64_t)(taxon | (h << 16)) << sh; done = true; }
+        else if ((p & 0xffffu) == taxon) {
+            if (h > (p >> 16)) uw += (uint64_t)(h - (p >> 16)) << (sh + 16);
+            done = true;
+        }
+    }
+    return done;
+}
+
 // General path (oversized span read from HBM, or a taxa set that does not fit the record): Set semantics of
 // Compare.hpp:785-1041 for one query instance.  g0 = first entry of the query's k_low group, b = end of the span.
 // Every entry whose first c >= k_low letters equal the query's belongs to taxa_k(prefix_k(q)) for k = k_low .. min(c, kv).
@@ -324,7 +342,7 @@ struct SpanStage {
 // k_low letters, and a walk over the entries sharing MORE than k_low letters (they surround the search position; usually 0-2).
 // The walk over the whole k_low group — whose trip count is the largest group among the 128 queries of a warp, dozens of
 // entries for k-mers of frequent amino acids against a saturated index — took 2/3 of this kernel's instructions.
-template <bool W, bool MASK>
+template <bool W, bool MASK, bool M2>
 __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const uint64_t *__restrict__ q_lo, const uint64_t *__restrict__ q_hi,
                                                                          const uint32_t *__restrict__ inst, uint64_t n, uint64_t rank_base,
                                                                          IndexDev idx, LevelParams lp, const uint64_t *__restrict__ part,
@@ -481,16 +499,18 @@ __global__ void __launch_bounds__(kLookupBlock, W ? 3 : 4) lookup_kernel(const u
         if (staged && MASK) {
             if (mask[r]) {
                 uint64_t uw[2] = {0, 0};
+                uint64_t m1 = 0;                                  // M2: the taxa matching at least k_low + 1 letters
                 uint32_t hmax = 1;
                 bool fits = true;
                 for (uint32_t e = up[r] >> 12, end = (up[r] >> 12) + (up[r] & 4095u); e < end; ++e) {
                     const uint32_t h = match_levels<W>(sacc.template key<W>((int64_t)e), qv[r], kv[r], lp);
-                    fits = up_pair_raise(uw, sacc.tax[e], h) && fits;
+                    if (M2) { m1 |= 1ull << (sacc.tax[e] - 1); if (h >= 3u) fits = up3_pair_raise(uw[0], sacc.tax[e], h) && fits; }
+                    else fits = up_pair_raise(uw, sacc.tax[e], h) && fits;
                     hmax = max(hmax, h);
                 }
                 if (fits) {
-                    o0 = rec_head(rank, (uint32_t)__popcll(mask[r]), hmax, false, owner) | kRecMaskBit;
-                    o1 = mask[r]; o2 = uw[0]; o3 = uw[1];
+                    o0 = rec_head(rank, (uint32_t)__popcll(mask[r]), hmax, false, owner) | kRecMaskBit | (M2 ? kRecMask2Bit : 0ull);
+                    o1 = mask[r]; o2 = M2 ? m1 : uw[0]; o3 = M2 ? uw[0] : uw[1];
                 } else {
                     // more than six taxa above k_low: list record from the whole group (its first entry is searched for only now)
                     general = true; gen_b = span;
@@ -659,7 +679,7 @@ void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi
 
 void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n, uint64_t rank_base,
                    IndexDev idx, LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq, OverflowBuf ovf, uint32_t owner,
-                   uint32_t *err_flag, uint64_t *launches)
+                   uint32_t *err_flag, uint64_t *launches, bool two_masks)
 {
     if (!n) return;
     const unsigned tiles = (unsigned)div_up<uint64_t>(n, tq);
@@ -670,8 +690,16 @@ void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, c
     };
     const bool mask = lp.n_taxa <= kMaskTaxa;
     KASA_REQUIRE(!mask || idx.gmask, -4, "the index of a small content file has no group masks (launch_group_masks)");
-    if (idx.key_hi) { if (mask) go(lookup_kernel<true, true>, sizeof(SpanStage<true, true>)); else go(lookup_kernel<true, false>, sizeof(SpanStage<true, false>)); }
-    else { if (mask) go(lookup_kernel<false, true>, sizeof(SpanStage<false, true>)); else go(lookup_kernel<false, false>, sizeof(SpanStage<false, false>)); }
+    KASA_REQUIRE(!two_masks || mask, -6, "two-mask records need a content file of <= 64 taxa");
+    if (idx.key_hi) {
+        if (mask && two_masks) go(lookup_kernel<true, true, true>, sizeof(SpanStage<true, true>));
+        else if (mask) go(lookup_kernel<true, true, false>, sizeof(SpanStage<true, true>));
+        else go(lookup_kernel<true, false, false>, sizeof(SpanStage<true, false>));
+    } else {
+        if (mask && two_masks) go(lookup_kernel<false, true, true>, sizeof(SpanStage<false, true>));
+        else if (mask) go(lookup_kernel<false, true, false>, sizeof(SpanStage<false, true>));
+        else go(lookup_kernel<false, false, false>, sizeof(SpanStage<false, false>));
+    }
     ++*launches;
     KASA_CUDA_TRY(cudaGetLastError());
 }

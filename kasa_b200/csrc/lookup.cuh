@@ -45,12 +45,17 @@ constexpr int kLookupBlock = 256;
 //   list format, otherwise:            w1 = first entry of the list in the owner's overflow array (u32 per pair: taxon | levels << 16)
 //   mask format:          w1 = bit t-1 set for every taxon t of taxa_klow (any set size), w2..w3 = up to kRecUpPairs pairs for the taxa
 //                         that match more than one level (the others match exactly the k_low level)
+//   two-mask format (bit 59; only on request, for the dense scoring kernel of presorted batches): w1 as above, w2 = the same kind
+//                         of mask for level k_low + 1, w3 = up to three pairs for the taxa that match three or more levels.  Against
+//                         a saturated index taxa reach k_low + 1 by chance in every fourth k-mer; as a mask they cost the scorer one
+//                         more predicated add per lane instead of a chain per pair.
 constexpr int kRecWords = 4;
 constexpr int kRecInline = 9;
 constexpr int kPairBits = 21;
 constexpr uint32_t kPairMask = (1u << kPairBits) - 1u;
 constexpr uint64_t kRecOverflowBit = 1ull << 53;
 constexpr uint64_t kRecMaskBit = 1ull << 58;
+constexpr uint64_t kRecMask2Bit = 1ull << 59;
 constexpr int kRecUpPairs = 6;
 constexpr int kMaskTaxa = 65;          // n_taxa (incl. index 0) up to which records use the mask format
 
@@ -60,6 +65,7 @@ __host__ __device__ __forceinline__ uint32_t rec_hmax(uint64_t w0) { return (uin
 __host__ __device__ __forceinline__ bool rec_overflow(uint64_t w0) { return (w0 & kRecOverflowBit) != 0; }
 __host__ __device__ __forceinline__ uint32_t rec_owner(uint64_t w0) { return (uint32_t)(w0 >> 54) & 15u; }
 __host__ __device__ __forceinline__ bool rec_is_mask(uint64_t w0) { return (w0 & kRecMaskBit) != 0; }
+__host__ __device__ __forceinline__ bool rec_is_mask2(uint64_t w0) { return (w0 & kRecMask2Bit) != 0; }
 
 // append-only side list for instances whose taxa set does not fit a record (reset per batch)
 struct OverflowBuf {
@@ -81,7 +87,7 @@ void launch_partition(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi
 // err_flag |= 8 when the overflow list is full.
 void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, const uint32_t *inst, uint64_t n, uint64_t rank_base,
                    IndexDev idx, LevelParams lp, const uint64_t *part, uint64_t *rec, uint32_t tq, OverflowBuf ovf, uint32_t owner,
-                   uint32_t *err_flag, uint64_t *launches);
+                   uint32_t *err_flag, uint64_t *launches, bool two_masks = false);
 
 // rec[inst[i]] = staged[i] for i < n (staged may be peer memory)
 void launch_scatter_records(cudaStream_t s, const uint64_t *staged, const uint32_t *inst, uint64_t n, uint64_t *rec, uint64_t *launches);

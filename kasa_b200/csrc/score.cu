@@ -1408,6 +1408,433 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_blocks_kernel(const uint
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// PRESORTED READS, third organisation: THREAD PER READ, ONE (k-mer, taxon) ITEM PER ITERATION.
+// The two organisations above waste issue slots in opposite ways: the dense scan executes one predicated add per taxon and k-mer
+// (a k-mer names ~4.5 of 50 taxa), the warp-per-read walk runs at the pace of the read's own taxon while 31 lanes idle.  Here
+// every lane works through ITS OWN read as a stream of items — pop the next taxon of the current record's mask, add into that
+// taxon's cell, fetch the next record when the mask is empty — so every lane does useful work in every iteration, whatever the
+// taxa sets look like.  The per-taxon cells (float32 score + k_low share of the count) are a column of shared memory per thread:
+// dynamic indexing without bank conflicts; records are 32-byte sectors read one ahead.  Records with several taxa above k_low
+// lay out their level values and a bit-plane map taxon -> levels when they are fetched.
+constexpr int kItemBlock = 128;
+
+template <bool TWO>
+__global__ void __launch_bounds__(kItemBlock) score_items_kernel(const uint64_t *__restrict__ rec, const uint64_t *__restrict__ read_koff, uint32_t n_reads,
+                                                                  LevelParams lp, OverflowPeers peers, float *__restrict__ scores,
+                                                                  unsigned long long *__restrict__ cnt_fx, unsigned long long *__restrict__ cnt_unique)
+{
+    constexpr int BT = kItemBlock;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, T = lp.n_taxa, NK = lp.num_k;
+    uint2 *cell = reinterpret_cast<uint2 *>(smem_raw);                  // [T - 1][BT]: .x = score bits, .y = k_low sum (2^-24 units)
+    float *s_val = reinterpret_cast<float *>(cell + (size_t)(T - 1) * BT);   // [5][BT]: level values of the thread's current record (several up pairs)
+    __shared__ float2 s_vq[72];                                         // [n]: .x = float(w_0 * (1.f / n)), .y = bits of 2^24 / n (0 for n < 2)
+    __shared__ float s_inv[72];
+    __shared__ uint32_t s_q32[72];                                      // 2^32 / n
+    __shared__ unsigned long long s_fx[6 * 64];                         // CTA totals [level][taxon - 1], 2^-32 units
+    __shared__ uint32_t s_un[6 * 64];
+    __shared__ uint32_t s_hist[64 * 8];                                 // [taxon - 1][h]: k-mers where the taxon is alone at its levels 1 .. h-1
+    float wj[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { const int k = lp.k_low + j; wj[j] = (float)(k * k) / 625.f; }      // Compare.hpp:392
+    for (int i = tid; i < (T - 1) * BT; i += BT) cell[i] = make_uint2(0u, 0u);
+    for (int i = tid; i < 6 * 64; i += BT) { s_fx[i] = 0; s_un[i] = 0; }
+    for (int i = tid; i < 64 * 8; i += BT) s_hist[i] = 0;
+    if (tid < 72) {
+        const float inv = tid ? __fdiv_rn(1.f, (float)tid) : 0.f;       // Compare.hpp:924: 1.f / numOfEntries
+        s_inv[tid] = inv;
+        s_vq[tid] = make_float2(__fmul_rn(wj[0], inv), __uint_as_float(tid >= 2 ? (uint32_t)(((1u << 24) + (tid >> 1)) / tid) : 0u));
+        s_q32[tid] = tid >= 2 ? inv_fx((uint32_t)tid) : 0u;
+    }
+    __syncthreads();
+    constexpr uint32_t kNone = 0xffffffffu;
+
+#pragma unroll 1
+    for (uint32_t base = blockIdx.x * BT; base < n_reads; base += gridDim.x * BT) {
+        const uint32_t r = base + tid;
+        const bool have = r < n_reads;
+        const uint64_t s0 = have ? read_koff[r] : 0;
+        const uint32_t ni = have ? (uint32_t)(read_koff[r + 1] - s0) : 0u;
+        const uint64_t *p = rec + s0 * kRecWords;
+        uint32_t i = 0;                                                  // records fetched so far
+        uint32_t mlo = 0, mhi = 0;                                       // taxa of the current record still to be added
+        float v0 = 0.f;
+        uint32_t q0 = 0;
+        uint32_t upc = kNone, uph = 0;                                   // the current record's only up pair (taxon 0-based, levels)
+        bool cplx = false;                                               // ... or several: levels of taxon c = bit c of the three planes
+        uint64_t pl0 = 0, pl1 = 0, pl2 = 0;
+        uint64_t nx[4] = {0, 0, 0, 0};
+        if (ni) asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(p));
+        bool active = ni > 0;
+        while (__any_sync(kFull, active)) {
+            if (active && (mlo | mhi) == 0u) {
+                if (i == ni) active = false;
+                else {
+                    // ---- fetch record i (the next one is requested right away)
+                    const uint64_t w0 = nx[0], w1 = nx[1], w2 = nx[2], w3 = nx[3];
+                    ++i;
+                    if (i < ni) asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(p + (uint64_t)i * kRecWords));
+                    if ((i & 255u) == 0u) {
+                        // a k-mer adds at most 2^23 units to a k_low sum: hand the sums on before 32 bits could overflow
+                        for (int t = 0; t < T - 1; ++t) {
+                            uint2 x = cell[t * BT + tid];
+                            if (x.y) { atomicAdd(&s_fx[t], (unsigned long long)x.y << kFxShift); x.y = 0u; cell[t * BT + tid] = x; }
+                        }
+                    }
+                    const uint32_t n0 = rec_count(w0), hmax = rec_hmax(w0);
+                    upc = kNone; cplx = false;
+                    if (n0) {
+                        const float2 vq = s_vq[n0 < 72u ? n0 : 0u];
+                        v0 = vq.x; q0 = __float_as_uint(vq.y);
+                        if (rec_is_mask(w0)) {
+                            mlo = (uint32_t)w1; mhi = (uint32_t)(w1 >> 32);
+                            if (n0 == 1u) atomicAdd(&s_un[w1 ? __ffsll((long long)w1) - 1 : 0], 1u);       // alone at k_low: a unique hit
+                            if (hmax > 1u) {
+                                const uint32_t e0 = (uint32_t)w2 & kPairMask;
+                                if ((w2 >> kPairBits) == 0 && w3 == 0) {
+                                    upc = (e0 & 0xffffu) - 1u; uph = e0 >> 16;                 // the usual case: one taxon, alone at its levels
+                                    atomicAdd(&s_hist[upc * 8 + (uph & 7u)], 1u);
+                                } else {
+                                    // several taxa above k_low: level sizes (nibbles), level values, planes, counts
+                                    const uint32_t e[kRecUpPairs] = {e0, (uint32_t)(w2 >> kPairBits) & kPairMask, (uint32_t)(w2 >> (2 * kPairBits)) & kPairMask,
+                                                                     (uint32_t)w3 & kPairMask, (uint32_t)(w3 >> kPairBits) & kPairMask, (uint32_t)(w3 >> (2 * kPairBits)) & kPairMask};
+                                    uint32_t njp = 0;                                          // nibble j - 1 = number of pairs reaching level j (<= 6)
+#pragma unroll
+                                    for (int k = 0; k < kRecUpPairs; ++k) { const uint32_t h = e[k] >> 16; njp += h ? ((1u << (4 * (h - 1u))) - 1u) & 0x11111u : 0u; }
+                                    pl0 = pl1 = pl2 = 0;
+#pragma unroll
+                                    for (int j = 1; j < 6; ++j) s_val[(j - 1) * BT + tid] = __fmul_rn(wj[j], s_inv[(njp >> (4 * (j - 1))) & 15u]);
+#pragma unroll
+                                    for (int k = 0; k < kRecUpPairs; ++k) {
+                                        const uint32_t h = e[k] >> 16, c = (e[k] & 0xffffu) - 1u;
+                                        if (h < 2u) continue;
+                                        pl0 |= (uint64_t)(h & 1u) << c; pl1 |= (uint64_t)((h >> 1) & 1u) << c; pl2 |= (uint64_t)(h >> 2) << c;
+#pragma unroll
+                                        for (int j = 1; j < 6; ++j) {
+                                            if ((uint32_t)j >= h) break;
+                                            const uint32_t nn = (njp >> (4 * (j - 1))) & 15u;
+                                            if (nn == 1u) atomicAdd(&s_un[j * 64 + c], 1u);
+                                            else atomicAdd(&s_fx[j * 64 + c], (unsigned long long)s_q32[nn]);
+                                        }
+                                    }
+                                    cplx = true;
+                                }
+                            }
+                        } else {
+                            // list record inside a small taxonomy (more than six taxa above k_low, or a span read from HBM): the same from its pairs
+                            const uint32_t *list = rec_overflow(w0) ? peers.base[rec_owner(w0)] + w1 : nullptr;
+                            auto pair_at = [&](uint32_t k) -> uint32_t {
+                                return list ? __ldg(list + k) : (uint32_t)((k < 3u ? w1 : k < 6u ? w2 : w3) >> (kPairBits * (k % 3u))) & kPairMask;
+                            };
+                            uint32_t nj[6] = {0, 0, 0, 0, 0, 0};
+                            uint64_t mk = 0;
+                            pl0 = pl1 = pl2 = 0;
+                            for (uint32_t k = 0; k < n0; ++k) {
+                                const uint32_t e = pair_at(k), h = e >> 16, c = (e & 0xffffu) - 1u;
+                                mk |= 1ull << c;
+#pragma unroll
+                                for (int j = 1; j < 6; ++j) nj[j] += (uint32_t)j < h ? 1u : 0u;
+                                if (h >= 2u) { pl0 |= (uint64_t)(h & 1u) << c; pl1 |= (uint64_t)((h >> 1) & 1u) << c; pl2 |= (uint64_t)((h >> 2) & 1u) << c; }
+                            }
+                            mlo = (uint32_t)mk; mhi = (uint32_t)(mk >> 32);
+                            if (n0 == 1u) atomicAdd(&s_un[__ffsll((long long)mk) - 1], 1u);
+#pragma unroll
+                            for (int j = 1; j < 6; ++j) s_val[(j - 1) * BT + tid] = __fmul_rn(wj[j], s_inv[nj[j] < 72u ? nj[j] : 0u]);
+                            for (uint32_t k = 0; k < n0 && hmax > 1u; ++k) {
+                                const uint32_t e = pair_at(k), h = e >> 16, c = (e & 0xffffu) - 1u;
+                                for (uint32_t j = 1; j < h && j < 6u; ++j) {
+                                    if (nj[j] == 1u) atomicAdd(&s_un[j * 64 + c], 1u);
+                                    else atomicAdd(&s_fx[j * 64 + c], (unsigned long long)s_q32[nj[j] < 72u ? nj[j] : 0u]);
+                                }
+                            }
+                            cplx = (pl0 | pl1 | pl2) != 0;
+                        }
+                    }
+                }
+            }
+            if (active && (mlo | mhi) != 0u) {
+                // ---- one item: the next taxon of the record (Compare.hpp:530 for level k_low, then its levels above, in order)
+                uint32_t c;
+                if (!TWO || mlo) { c = (uint32_t)__ffs((int)mlo) - 1u; mlo &= mlo - 1u; }
+                else { c = 32u + (uint32_t)__ffs((int)mhi) - 1u; mhi &= mhi - 1u; }
+                const uint2 x = cell[c * BT + tid];
+                float acc = __fadd_rn(__uint_as_float(x.x), v0);
+                if (c == upc) {
+#pragma unroll
+                    for (int j = 1; j < 6; ++j) if ((uint32_t)j < uph) acc = __fadd_rn(acc, wj[j]);          // alone there: w * (1.f / 1) == w
+                } else if (cplx) {
+                    const uint32_t h = ((uint32_t)(pl0 >> c) & 1u) | (((uint32_t)(pl1 >> c) & 1u) << 1) | (((uint32_t)(pl2 >> c) & 1u) << 2);
+#pragma unroll
+                    for (int j = 1; j < 6; ++j) if ((uint32_t)j < h) acc = __fadd_rn(acc, s_val[(j - 1) * BT + tid]);
+                }
+                cell[c * BT + tid] = make_uint2(__float_as_uint(acc), x.y + q0);
+            }
+        }
+        // ---- end of the reads of this pass: scores out, k_low sums into the CTA's totals
+        if (have) {
+            for (int t = 0; t < T - 1; ++t) {
+                const uint2 x = cell[t * BT + tid];
+                if (scores) scores[(uint64_t)r * T + t + 1] = __uint_as_float(x.x);
+                if (x.x | x.y) cell[t * BT + tid] = make_uint2(0u, 0u);
+                if (x.y) atomicAdd(&s_fx[t], (unsigned long long)x.y << kFxShift);
+            }
+            if (scores) scores[(uint64_t)r * T] = 0.f;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < NK * 64; i += BT) {
+        const int j = i / 64, c = i % 64;
+        if (c >= T - 1) continue;
+        unsigned long long u = s_un[i];
+        if (j >= 1) for (int h = j + 1; h < 8; ++h) u += s_hist[c * 8 + h];     // alone at the levels 1 .. h-1
+        if (u) atomicAdd(cnt_unique + (size_t)j * T + c + 1, u);
+        if (s_fx[i]) atomicAdd(cnt_fx + (size_t)j * T + c + 1, s_fx[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PRESORTED READS, fourth organisation: WARP PER READ, LANE PER TAXON, UNIFORM CONTROL FLOW.
+//   setup  lane = k-mer: the 32 records of a block arrive as one coalesced 1 KB load; each lane publishes, in shared memory, its
+//          k-mer's taxa mask, its k_low value float(w_0 * (1.f / n0)) and what its up pairs need (levels, level values);
+//   main   lane = taxon (lane l owns the taxa l + 1 and l + 33): the 32 k-mers are replayed in order with BROADCAST loads; a lane adds
+//          when its bit is set (two predicated adds per k-mer), the lane named by an up pair adds the levels above — every branch is
+//          warp-uniform, nothing is indexed dynamically, nothing depends on how many taxa a k-mer names.
+// The sparse organisations above execute fewer useful lanes' worth of work but pay full price for every rare path a single lane takes;
+// against a saturated index (C2: 0.6 up pairs per k-mer, 10 % of the records with several) this one issues the fewest instructions.
+struct DenseWarpMem {
+    uint4 a[32];              // per k-mer: taxa mask of level k_low (lo, hi), bits of float(w_0 * (1.f / n0)), 2^24 / n0 (0 for n0 < 2)
+    uint4 b[32];              // the same for level k_low + 1 (two-mask records, lookup.cuh)
+    uint32_t up[32];          // bit 31: b[] is not empty; bits 0..30: 0 = no taxon at three or more levels, 0x7fffffff = several (pairs[],
+                              // val[]), else the only such pair (taxon | levels << 16); 0xfffffffe = list record (head[], pairs[])
+    uint4 pairs[32];          // .xy = the record's pair word w3 when it holds several pairs; list records: the words w2, w3
+    uint4 head[32];           // list records: the words w0, w1
+    float4 val[32];           // float(w_j * (1.f / n_j)) for the levels j = 2 .. 5 of a record with several pairs
+};
+
+template <bool TWO>
+__global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint64_t *__restrict__ rec, const uint64_t *__restrict__ read_koff, uint32_t n_reads,
+                                                                      LevelParams lp, OverflowPeers peers, float *__restrict__ scores,
+                                                                      unsigned long long *__restrict__ cnt_fx, unsigned long long *__restrict__ cnt_unique,
+                                                                      uint32_t *__restrict__ err_flag)
+{
+    __shared__ __align__(16) DenseWarpMem s_w[kBlkWarps];
+    __shared__ float2 s_vq0[72], s_vq1[72];                             // [n]: .x = float(w_j * (1.f / n)) for j = 0, 1; .y = bits of 2^24 / n resp. 2^32 / n (0 for n < 2)
+    __shared__ float s_inv[72];
+    __shared__ uint32_t s_q32[72];                                      // 2^32 / n
+    __shared__ unsigned long long s_fx[6 * 64];                         // CTA totals [level][taxon - 1], 2^-32 units
+    __shared__ uint32_t s_un[6 * 64];
+    __shared__ uint32_t s_hist[64 * 8];                                 // [taxon - 1][h]: k-mers where the taxon is alone at its levels 2 .. h-1
+    const int tid = threadIdx.x, T = lp.n_taxa, NK = lp.num_k;
+    const uint32_t lane = tid & 31u;
+    const int w = tid >> 5;
+    DenseWarpMem &M = s_w[w];
+    float wj[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { const int k = lp.k_low + j; wj[j] = (float)(k * k) / 625.f; }      // Compare.hpp:392
+    for (int i = tid; i < 6 * 64; i += blockDim.x) { s_fx[i] = 0; s_un[i] = 0; }
+    for (int i = tid; i < 64 * 8; i += blockDim.x) s_hist[i] = 0;
+    if (tid < 72) {
+        const float inv = tid ? __fdiv_rn(1.f, (float)tid) : 0.f;       // Compare.hpp:924: 1.f / numOfEntries
+        const float q = __uint_as_float(tid >= 2 ? (uint32_t)(((1u << 24) + (tid >> 1)) / tid) : 0u);
+        s_inv[tid] = inv;
+        s_vq0[tid] = make_float2(__fmul_rn(wj[0], inv), q);
+        s_vq1[tid] = make_float2(__fmul_rn(wj[1], inv), __uint_as_float(tid >= 2 ? inv_fx((uint32_t)tid) : 0u));     // (.y in 2^-32 units: levels above k_low)
+        s_q32[tid] = tid >= 2 ? inv_fx((uint32_t)tid) : 0u;
+    }
+    __syncthreads();
+    unsigned long long fa64 = 0, fb64 = 0, ga64 = 0, gb64 = 0;          // sums of 1 / n of this lane's taxa (lane + 1, lane + 33): k_low in 2^-24, k_low + 1 in 2^-32 units
+    const uint32_t lbit = 1u << lane;
+    constexpr uint32_t kList = 0xfffffffeu, kSeveral = 0x7fffffffu;
+
+    const uint32_t warps_total = gridDim.x * kBlkWarps;
+#pragma unroll 1
+    for (uint32_t r = blockIdx.x * kBlkWarps + w; r < n_reads; r += warps_total) {
+        const uint64_t s0 = read_koff[r];
+        const uint32_t ni = (uint32_t)(read_koff[r + 1] - s0);
+        const uint64_t *p = rec + s0 * kRecWords;
+        float sa = 0.f, sb = 0.f;
+        uint32_t fa = 0, fb = 0;
+        uint64_t nx[4] = {0, 0, 0, 0};
+        if (lane < ni) asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(p + (uint64_t)lane * kRecWords));
+#pragma unroll 1
+        for (uint32_t b0 = 0; b0 < ni; b0 += 32) {
+            // ---- setup, lane = k-mer b0 + lane
+            const uint64_t w0 = nx[0], w1 = nx[1], w2 = nx[2], w3 = nx[3];
+            nx[0] = nx[1] = nx[2] = nx[3] = 0;
+            if (b0 + 32 + lane < ni)
+                asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(p + (uint64_t)(b0 + 32 + lane) * kRecWords));
+            const uint32_t n0 = rec_count(w0), hmax = rec_hmax(w0);
+            uint64_t mk = n0 ? w1 : 0ull, m1 = 0;
+            uint32_t upd = 0;
+            if (n0 && !rec_is_mask(w0)) {
+                // list record inside a small taxonomy (more than three taxa at three or more levels, or a span read from HBM; rare): mask
+                // from its pairs here, its levels above k_low in the main pass (every lane looks its own taxa up in the pairs)
+                const uint32_t *list = rec_overflow(w0) ? peers.base[rec_owner(w0)] + w1 : nullptr;
+                mk = 0;
+                for (uint32_t k = 0; k < n0; ++k) {
+                    const uint32_t e = list ? __ldg(list + k) : (uint32_t)((k < 3u ? w1 : k < 6u ? w2 : w3) >> (kPairBits * (k % 3u))) & kPairMask;
+                    mk |= 1ull << ((e & 0xffffu) - 1u);
+                }
+                if (hmax > 1u) {
+                    upd = kList;
+                    M.head[lane] = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+                    M.pairs[lane] = make_uint4((uint32_t)w2, (uint32_t)(w2 >> 32), (uint32_t)w3, (uint32_t)(w3 >> 32));
+                }
+            } else if (n0 && hmax > 1u) {
+                if (!rec_is_mask2(w0)) atomicOr(err_flag, 512u);                              // this kernel reads two-mask records only
+                m1 = w2;
+                const uint32_t n1 = (uint32_t)__popcll(m1);
+                if (n1 == 1u) atomicAdd(&s_un[64 + __ffsll((long long)m1) - 1], 1u);           // alone at k_low + 1
+                upd = 0x80000000u;
+                const uint32_t e0 = (uint32_t)w3 & kPairMask;
+                if (e0 && (w3 >> kPairBits) == 0) {
+                    upd |= e0;                                                                // the usual case: one taxon, alone at its levels 2 ..
+                    atomicAdd(&s_hist[((e0 & 0xffffu) - 1u) * 8 + ((e0 >> 16) & 7u)], 1u);
+                } else if (e0) {
+                    // several taxa at three or more levels: level sizes (nibbles), level values, counts
+                    const uint32_t e[3] = {e0, (uint32_t)(w3 >> kPairBits) & kPairMask, (uint32_t)(w3 >> (2 * kPairBits)) & kPairMask};
+                    uint32_t njp = 0;                                                         // nibble j - 1 = number of pairs reaching level j
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { const uint32_t h = e[k] >> 16; njp += h ? ((1u << (4 * (h - 1u))) - 1u) & 0x11111u : 0u; }
+                    float vj[6];
+#pragma unroll
+                    for (int j = 2; j < 6; ++j) vj[j] = __fmul_rn(wj[j], s_inv[(njp >> (4 * (j - 1))) & 15u]);
+                    M.val[lane] = make_float4(vj[2], vj[3], vj[4], vj[5]);
+                    M.pairs[lane] = make_uint4((uint32_t)w3, (uint32_t)(w3 >> 32), 0u, 0u);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const uint32_t h = e[k] >> 16, c = (e[k] & 0xffffu) - 1u;
+#pragma unroll
+                        for (int j = 2; j < 6; ++j) {
+                            if ((uint32_t)j >= h) break;
+                            const uint32_t nn = (njp >> (4 * (j - 1))) & 15u;
+                            if (nn == 1u) atomicAdd(&s_un[j * 64 + c], 1u);
+                            else atomicAdd(&s_fx[j * 64 + c], (unsigned long long)s_q32[nn]);
+                        }
+                    }
+                    upd |= kSeveral;
+                }
+            }
+            if (n0 == 1u && mk) atomicAdd(&s_un[__ffsll((long long)mk) - 1], 1u);             // alone at k_low: a unique hit
+            {
+                const float2 vq = s_vq0[n0 < 72u ? n0 : 0u];
+                M.a[lane] = make_uint4((uint32_t)mk, (uint32_t)(mk >> 32), __float_as_uint(vq.x), __float_as_uint(vq.y));
+                if (m1) {
+                    const float2 v1 = s_vq1[__popcll(m1)];
+                    M.b[lane] = make_uint4((uint32_t)m1, (uint32_t)(m1 >> 32), __float_as_uint(v1.x), __float_as_uint(v1.y));
+                }
+                M.up[lane] = upd;
+            }
+            __syncwarp();
+            // ---- main, lane = taxon: the block's k-mers in order (Compare.hpp:530 for level k_low, then the levels above)
+            const uint32_t nblk = min(32u, ni - b0);
+#pragma unroll 1
+            for (uint32_t i = 0; i < nblk; ++i) {
+                const uint4 a = M.a[i];
+                const float v0 = __uint_as_float(a.z);
+                if (a.x & lbit) { sa = __fadd_rn(sa, v0); fa += a.w; }
+                if (TWO && (a.y & lbit)) { sb = __fadd_rn(sb, v0); fb += a.w; }
+                const uint32_t u = M.up[i];
+                if (u == 0u) continue;
+                if (u == kList) {
+                    // list record: level sizes by counting its pairs (every lane, the same values), this lane's taxa looked up on the way
+                    const uint4 hd = M.head[i], pw = M.pairs[i];
+                    const uint64_t l0 = ((uint64_t)hd.y << 32) | hd.x, l1 = ((uint64_t)hd.w << 32) | hd.z;
+                    const uint64_t l2 = ((uint64_t)pw.y << 32) | pw.x, l3 = ((uint64_t)pw.w << 32) | pw.z;
+                    const uint32_t np = rec_count(l0);
+                    const uint32_t *list = rec_overflow(l0) ? peers.base[rec_owner(l0)] + l1 : nullptr;
+                    uint32_t nj[6] = {0, 0, 0, 0, 0, 0}, ha = 0, hb = 0;
+                    for (uint32_t k = 0; k < np; ++k) {
+                        const uint32_t e = list ? __ldg(list + k) : (uint32_t)((k < 3u ? l1 : k < 6u ? l2 : l3) >> (kPairBits * (k % 3u))) & kPairMask;
+                        const uint32_t c = (e & 0xffffu) - 1u, h = e >> 16;
+#pragma unroll
+                        for (int j = 1; j < 6; ++j) nj[j] += (uint32_t)j < h ? 1u : 0u;
+                        if (c == lane) ha = h;
+                        if (c == lane + 32u) hb = h;
+                    }
+#pragma unroll
+                    for (int j = 1; j < 6; ++j) {
+                        const uint32_t nn = nj[j] < 72u ? nj[j] : 0u;
+                        const float vj = __fmul_rn(wj[j], s_inv[nn]);
+                        if ((uint32_t)j < ha) {
+                            sa = __fadd_rn(sa, vj);
+                            if (nn == 1u) atomicAdd(&s_un[j * 64 + lane], 1u); else atomicAdd(&s_fx[j * 64 + lane], (unsigned long long)s_q32[nn]);
+                        }
+                        if ((uint32_t)j < hb) {
+                            sb = __fadd_rn(sb, vj);
+                            if (nn == 1u) atomicAdd(&s_un[j * 64 + lane + 32], 1u); else atomicAdd(&s_fx[j * 64 + lane + 32], (unsigned long long)s_q32[nn]);
+                        }
+                    }
+                    continue;
+                }
+                {   // level k_low + 1: a second mask
+                    const uint4 b = M.b[i];
+                    const float v1 = __uint_as_float(b.z);
+                    if (b.x & lbit) { sa = __fadd_rn(sa, v1); ga64 += b.w; }
+                    if (TWO && (b.y & lbit)) { sb = __fadd_rn(sb, v1); gb64 += b.w; }
+                }
+                const uint32_t ud = u & kSeveral;
+                if (ud == 0u) continue;
+                if (ud != kSeveral) {
+                    const uint32_t c = (ud & 0xffffu) - 1u, h = ud >> 16;                      // h >= 3
+                    const bool mine = (c & 31u) == lane;
+                    float x = (TWO && c >= 32u) ? sb : sa;
+                    x = __fadd_rn(x, wj[2]);                                                   // alone there: w * (1.f / 1) == w
+                    if (h > 3u) x = __fadd_rn(x, wj[3]);
+                    if (h > 4u) x = __fadd_rn(x, wj[4]);
+                    if (h > 5u) x = __fadd_rn(x, wj[5]);
+                    if (mine) { if (TWO && c >= 32u) sb = x; else sa = x; }
+                } else {
+                    const uint4 pw = M.pairs[i];
+                    const float4 v = M.val[i];
+                    const uint64_t p3 = ((uint64_t)pw.y << 32) | pw.x;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const uint32_t e = (uint32_t)(p3 >> (kPairBits * k)) & kPairMask;
+                        if (!e) break;                                                         // uniform: pairs fill from slot 0
+                        const uint32_t c = (e & 0xffffu) - 1u, h = e >> 16;
+                        const bool mine = (c & 31u) == lane;
+                        float x = (TWO && c >= 32u) ? sb : sa;
+                        x = __fadd_rn(x, v.x);
+                        if (h > 3u) x = __fadd_rn(x, v.y);
+                        if (h > 4u) x = __fadd_rn(x, v.z);
+                        if (h > 5u) x = __fadd_rn(x, v.w);
+                        if (mine) { if (TWO && c >= 32u) sb = x; else sa = x; }
+                    }
+                }
+            }
+            // a k-mer adds at most 2^23 units to a sum: widen before 32 bits could overflow
+            if ((b0 & 255u) == 224u) { fa64 += fa; fb64 += fb; fa = fb = 0; }
+            __syncwarp();
+        }
+        fa64 += fa; fb64 += fb;
+        if (scores) {
+            float *row = scores + (uint64_t)r * T;
+            if (lane == 0) row[0] = 0.f;
+            if ((int)lane + 1 < T) row[lane + 1] = sa;
+            if (TWO && (int)lane + 33 < T) row[lane + 33] = sb;
+        }
+    }
+    if ((int)lane + 1 < T) {
+        if (fa64) atomicAdd(&s_fx[lane], fa64 << kFxShift);
+        if (ga64) atomicAdd(&s_fx[64 + lane], ga64);
+    }
+    if (TWO && (int)lane + 33 < T) {
+        if (fb64) atomicAdd(&s_fx[lane + 32], fb64 << kFxShift);
+        if (gb64) atomicAdd(&s_fx[64 + lane + 32], gb64);
+    }
+    __syncthreads();
+    for (int i = tid; i < NK * 64; i += blockDim.x) {
+        const int j = i / 64, c = i % 64;
+        if (c >= T - 1) continue;
+        unsigned long long u = s_un[i];
+        if (j >= 2) for (int h = j + 1; h < 8; ++h) u += s_hist[c * 8 + h];     // alone at the levels 2 .. h-1
+        if (u) atomicAdd(cnt_unique + (size_t)j * T + c + 1, u);
+        if (s_fx[i]) atomicAdd(cnt_fx + (size_t)j * T + c + 1, s_fx[i]);
+    }
+}
+
 }  // namespace
 
 void launch_order_ops(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t r0, uint32_t r1, uint64_t n_kmers, uint32_t max_inst,
@@ -1499,7 +1926,7 @@ void launch_max_instances(cudaStream_t s, const uint64_t *read_koff, uint32_t n_
 }
 
 void launch_score_sorted(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp, OverflowPeers peers,
-                         float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, int lanes_hint, uint64_t *launches)
+                         float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, int lanes_hint, uint32_t *err_flag, uint64_t *launches)
 {
     if (!n_reads) return;
     KASA_REQUIRE(ops_mask_stream(lp), -6, "the presorted scoring kernel needs <= 64 taxa and <= 6 levels");
@@ -1512,8 +1939,40 @@ void launch_score_sorted(cudaStream_t s, const uint64_t *rec, const uint64_t *re
         kern<<<grid, kSortedBlock, 0, s>>>(rec, read_koff, n_reads, lp, peers, scores, cnt_fx, cnt_unique);
     };
     const int taxa = lp.n_taxa - 1;
-    if (lanes_hint == 0 || lanes_hint == 32) {
-        // warp per read, 32 k-mers at a time (score_blocks_kernel): the default
+    if (lanes_hint == 100) {
+        // thread per read, one (k-mer, taxon) item per iteration (score_items_kernel)
+        auto goi = [&](auto kern) {
+            const size_t sm = (size_t)std::max(taxa, 1) * kItemBlock * 8 + (size_t)5 * kItemBlock * 4;
+            KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            int per_sm = 1;
+            KASA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kItemBlock, sm));
+            unsigned grid = (unsigned)div_up<uint64_t>(n_reads, kItemBlock);
+            const unsigned resident = (unsigned)(kSMs * (per_sm > 0 ? per_sm : 1));
+            if (grid > resident) grid = resident;
+            kern<<<grid, kItemBlock, sm, s>>>(rec, read_koff, n_reads, lp, peers, scores, cnt_fx, cnt_unique);
+        };
+        if (taxa > 32) goi(score_items_kernel<true>); else goi(score_items_kernel<false>);
+        ++*launches;
+        KASA_CUDA_TRY(cudaGetLastError());
+        return;
+    }
+    if (lanes_hint == 0 || lanes_hint == 64) {
+        // warp per read, lane per taxon, uniform control flow over two-mask records (score_dense_kernel): the default
+        auto god = [&](auto kern) {
+            int per_sm = 1;
+            KASA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlkWarps * 32, 0));
+            unsigned grid = (unsigned)div_up<uint64_t>(n_reads, kBlkWarps);
+            const unsigned resident = (unsigned)(kSMs * (per_sm > 0 ? per_sm : 1));
+            if (grid > resident) grid = resident;
+            kern<<<grid, kBlkWarps * 32, 0, s>>>(rec, read_koff, n_reads, lp, peers, scores, cnt_fx, cnt_unique, err_flag);
+        };
+        if (taxa > 32) god(score_dense_kernel<true>); else god(score_dense_kernel<false>);
+        ++*launches;
+        KASA_CUDA_TRY(cudaGetLastError());
+        return;
+    }
+    if (lanes_hint == 32) {
+        // warp per read, 32 k-mers at a time (score_blocks_kernel)
         auto gow = [&](auto kern) {
             int per_sm = 1;
             KASA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlkWarps * 32, 0));
