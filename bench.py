@@ -40,6 +40,10 @@ BYTES_SORT_PASS = 24.0        # one radix pass: read + write of a 12-byte record
 BYTES_PER_LOOKUP_MODEL = 233.2
 
 
+def kmers_per_read(read_len: int) -> int:
+    return 2 * (read_len + 3 * (12 - 7) - 3 * 12 + 1)      # both strands, marker of 3 (K - k_low) 'X' (Read.hpp:36-57, 1068-1078)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -48,18 +52,26 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--taxa", type=int, default=50)
     ap.add_argument("--genome-len", type=int, default=33_400_000)
-    ap.add_argument("--reads-per-step", type=int, default=6_700_000)
+    ap.add_argument("--reads-per-step", type=int, default=0, help="default: 6.7 M reads of 150 bp (1.742 G k-mers) or as many longer reads")
+    ap.add_argument("--read-len", type=int, default=150, help="150 = C2 (the bench line); 10000 = the long reads of C5")
     ap.add_argument("--sharding", default="replicate", choices=["replicate", "prefix"],
                     help="replicate: index copied to every GPU, reads sharded (default, SURVEY.md §8e mode 1); prefix: index "
                          "sharded by k-mer prefix range as well, match records exchanged over NVLink peer memory (mode 2)")
-    ap.add_argument("--score-mode", default="fast", choices=["fast", "exact", "none"],
-                    help="per-read scoring: fast = canonical-order fixed point (the bench line), exact = the reference's flush order "
-                         "(bit-identical to kASA -n 1), none = profile counts only")
+    ap.add_argument("--score-mode", default="ordered", choices=["ordered", "fast", "exact", "none"],
+                    help="per-read scoring: ordered = float32 sums in ascending k-mer order per read (the bench line; <= 1e-6 of the reference, "
+                         "tests/test_gpu_reference_scale.py; 'fast' is its old name), exact = the reference's flush order (bit-identical to "
+                         "kASA -n 1), none = profile counts only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-reads", type=int, default=200_000)
-    ap.add_argument("--cpu-genome-len", type=int, default=1_000_000)
-    return ap.parse_args()
+    ap.add_argument("--cpu-reads", type=int, default=200_000,
+                    help="reads per step of the CPU reference (a bounded sample of the workload; the reference arm shrinks it further "
+                         "when --steps is large)")
+    ap.add_argument("--cpu-genome-len", type=int, default=4_000_000,
+                    help="genome length per taxon of the CPU reference's index (default: BASELINE's C1, 50 x 4 Mbp = 2.4 GB index)")
+    a = ap.parse_args()
+    if a.reads_per_step <= 0:
+        a.reads_per_step = 6_700_000 if a.read_len == READ_LEN else max(1, 6_700_000 * KMERS_PER_READ // kmers_per_read(a.read_len))
+    return a
 
 
 def measured_peak():
@@ -131,7 +143,7 @@ def cpu_reference_run(n_reads: int, n_taxa: int, genome_len: int, steps: int, wa
     try:
         os.makedirs(os.path.join(work, "tmp"))
         synth.write_reference(os.path.join(work, "ref.fa"), os.path.join(work, "content.txt"), GENOME_SEED, n_taxa, genome_len)
-        times, kmers = [], 0
+        times, kmers, hot_ns = [], 0, []
         if os.path.exists(exe):
             kind = "reference"
             mem = "16"
@@ -146,11 +158,17 @@ def cpu_reference_run(n_reads: int, n_taxa: int, genome_len: int, steps: int, wa
                 dt = time.perf_counter() - t0
                 if s >= warmup:
                     times.append(dt)
+                ns = 0
                 for l in out.splitlines():
                     if "Number of k-mers in input" in l:
                         kmers = int(l.split(":")[2].split()[0])
-            sample = ("oracle/_ref/kASA identify --six -r -n %d: %d reads x %d bp per step vs an index of %d taxa x %d bp "
-                      "(C2 scaled down so a step is seconds of CPU; wall time incl. index load and JSONL output)"
+                    if "Time fastq:" in l or "Time compare:" in l:          # -v: read conversion / sort + compare (Compare.hpp:3689-3690)
+                        ns += int(l.split(":")[2].split()[0])
+                if s >= warmup and ns:
+                    hot_ns.append(ns)
+            sample = ("oracle/_ref/kASA identify --six -r -n %d: %d reads x %d bp per step vs an index of %d taxa x %d bp (the reference's own "
+                      "CPU-runnable configuration C1 for the index; value = reads / wall time incl. process start, index load and JSONL "
+                      "output; hot_path_lookups_per_s = k-mers / (Time fastq + Time compare) as the binary reports them with -v)"
                       % (cores, n_reads, READ_LEN, n_taxa, genome_len))
         else:
             kind = "port"
@@ -171,7 +189,8 @@ def cpu_reference_run(n_reads: int, n_taxa: int, genome_len: int, steps: int, wa
                     times.append(dt)
             sample = "oracle port (kasa_oracle.c, 1 thread): %d reads per step vs %d taxa x %d bp" % (n_reads, n_taxa, genome_len)
         t = float(np.mean(times))
-        return {"value": n_reads / t, "lookups_per_s": kmers / t, "unit": "reads/s", "cores": cores, "kind": kind,
+        hot = kmers / (float(np.mean(hot_ns)) * 1e-9) if hot_ns else None
+        return {"value": n_reads / t, "lookups_per_s": kmers / t, "hot_path_lookups_per_s": hot, "unit": "reads/s", "cores": cores, "kind": kind,
                 "sample": sample, "ms_per_step": t * 1e3, "n_reads": n_reads}
     finally:
         shutil.rmtree(work, ignore_errors=True)
@@ -181,13 +200,16 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.cpu_reads, args.taxa, args.cpu_genome_len, args.steps, args.warmup)
+    # a step = a bounded sample: the whole run (index build + W + K identify processes) stays within a few minutes
+    n_reads = max(20_000, min(args.cpu_reads, 2_000_000 // max(1, args.steps + args.warmup)))
+    r = cpu_reference_run(n_reads, args.taxa, args.cpu_genome_len, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "identify reads/s (k=12..7, six frames)", "value": r["value"], "unit": "reads/s",
         "lookups_per_s": r["lookups_per_s"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": workload_config(args, r["n_reads"]),
-        "cpu_baseline": {"value": r["value"], "unit": "reads/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": "reads/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                         "hot_path_lookups_per_s": r["hot_path_lookups_per_s"]},
         "e2e": {"value": r["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -197,14 +219,16 @@ def main_reference(args):
 def workload_config(args, reads_per_step):
     how = ("index sharded by k-mer prefix range, reads sharded, match records over NVLink peer memory" if args.sharding == "prefix"
            else "index replicated, reads sharded")
-    return {"workload": "C2: identify k=12..7 --six, %d bp reads vs k=12 index of %d taxa x %d bp (%s)"
-                        % (READ_LEN, args.taxa, args.genome_len, how), "sharding": args.sharding, "score_mode": args.score_mode,
-            "reads_per_step_per_gpu": reads_per_step, "kmers_per_read": KMERS_PER_READ,
+    name = "C2" if args.read_len == READ_LEN else "C5 shape (long reads) on the C2 index"
+    return {"workload": "%s: identify k=12..7 --six, %d bp reads vs k=12 index of %d taxa x %d bp (%s)"
+                        % (name, args.read_len, args.taxa, args.genome_len, how), "sharding": args.sharding, "score_mode": args.score_mode,
+            "reads_per_step_per_gpu": reads_per_step, "kmers_per_read": kmers_per_read(args.read_len),
             "l2_policy": "inputs larger than L2 (each step streams > 10 GB; a fresh read batch per step)"}
 
 
-# dram bytes per record of one radix pass, from the committed ncu capture (profiles/r01_ncu_onesweep_kernel.txt)
-NCU_SORT_PASS_DRAM_BYTES_PER_RECORD = (3.195906e9 + 3.357949e9) / 2.6e8
+# DRAM bytes per k-mer (dram__bytes_read.sum + dram__bytes_write.sum of one launch / k-mers of the launch) from the committed ncu
+# captures at this workload's full size (profiles/r02_ncu_*.txt; the radix pass from profiles/r01_ncu_onesweep_kernel.txt)
+NCU_DRAM_BYTES = {"extract": None, "sort_pass": (3.195906e9 + 3.357949e9) / 2.6e8, "lookup": None, "score": None}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -229,11 +253,14 @@ def main_ours(args):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
     R = args.reads_per_step
+    RL, KPR = args.read_len, kmers_per_read(args.read_len)
     n_windows = args.taxa * (args.genome_len + 33)
-    cap = max(R * KMERS_PER_READ, n_windows) + 4096
-    score_mode = {"fast": capi.SCORE_FAST, "exact": capi.SCORE_EXACT, "none": capi.SCORE_NONE}[args.score_mode]
+    cap = max(R * KPR, n_windows) + 4096
+    if args.score_mode == "fast":
+        args.score_mode = "ordered"
+    score_mode = {"ordered": capi.SCORE_ORDERED, "exact": capi.SCORE_EXACT, "none": capi.SCORE_NONE}[args.score_mode]
     params = kasa_b200.Params(device=local, highest_k=12, k_high=12, k_low=7, frames=6, score_mode=score_mode,
-                              max_batch_kmers=cap, max_batch_seqs=R, max_batch_bases=max(R * READ_LEN, args.genome_len + 64))
+                              max_batch_kmers=cap, max_batch_seqs=R, max_batch_bases=max(R * RL, args.genome_len + 64))
     ctx = kasa_b200.Context(params)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -255,14 +282,14 @@ def main_ours(args):
     T = len(taxids)
 
     n_dev_batches = 4
-    dev_reads = [torch.empty(R * READ_LEN, dtype=torch.uint8, device="cuda") for _ in range(n_dev_batches)]
-    seq_start = torch.arange(R, dtype=torch.int64, device="cuda") * READ_LEN
-    seq_len = torch.full((R,), READ_LEN, dtype=torch.int32, device="cuda")
+    dev_reads = [torch.empty(R * RL, dtype=torch.uint8, device="cuda") for _ in range(n_dev_batches)]
+    seq_start = torch.arange(R, dtype=torch.int64, device="cuda") * RL
+    seq_len = torch.full((R,), RL, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
 
     def gen(step, buf, location):
         first = shard_first_read(step, world, rank, R)        # ranks take disjoint read ranges
-        ctx.synth_reads(GENOME_SEED, READ_SEED, first, R, args.taxa, args.genome_len, READ_LEN, out=buf, out_location=location)
+        ctx.synth_reads(GENOME_SEED, READ_SEED, first, R, args.taxa, args.genome_len, RL, out=buf, out_location=location)
 
     for b in range(n_dev_batches):
         gen(b, dev_reads[b].data_ptr(), capi.MEM_DEVICE)
@@ -315,20 +342,41 @@ def main_ours(args):
     value = reads_total / (ms_total * 1e-3)
     lookups = world * n_kmers / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (one radix pass), CUDA events on the launching stream
+    # ---- roofline: every stage's kernel against its algorithmic bytes, the dominant one (longest launch) as the
+    # line's `roofline`; durations are CUDA events on the launching stream (kasa_ctx_stage_times)
     peak, peak_src = measured_peak()
-    pass_ms = stages["sort_passes"] / max(1, n_passes)
     kmers_per_batch = stage_kmers / max(1, n_batches)
-    achieved = BYTES_SORT_PASS * kmers_per_batch / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "onesweep_kernel<256,18> (one 8-bit LSD radix pass over 12-byte records)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_SORT_PASS_DRAM_BYTES_PER_RECORD * kmers_per_batch,
-                "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one onesweep_kernel launch "
-                                  "(profiles/r01_ncu_onesweep_kernel.txt: 6.554 GB for 2.6e8 records), scaled per record to this launch",
-                "peak_source": peak_src, "bytes_per_unit": BYTES_SORT_PASS, "units_per_launch": kmers_per_batch,
-                "avg_launch_ms": pass_ms, "share_of_step": stages["sort_passes"] / max(1e-9, sum(stages.values())),
-                "whole_step_model": {"bytes_per_lookup": BYTES_PER_LOOKUP_MODEL + 12.0 * n_entries / max(1.0, kmers_per_batch),
-                                     "achieved_GBps": None}}
+    passes_per_batch = n_passes / max(1, n_batches)
+    index_bytes_per_lookup = 12.0 * n_entries / max(1.0, kmers_per_batch)
+    per = {k: v / max(1, n_batches) for k, v in stages.items()}
+    kernels = {
+        "extract": ("extract_identify_kernel (translation, k-mer packing, per-read presort)", 12.4, per["extract"], 1.0, NCU_DRAM_BYTES["extract"]),
+        "sort_pass": ("onesweep_kernel<256,18> (one 8-bit LSD radix pass over 12-byte records)", BYTES_SORT_PASS,
+                      per["sort_passes"] / max(1.0, passes_per_batch), passes_per_batch, NCU_DRAM_BYTES["sort_pass"]),
+        "lookup": ("lookup_kernel (sorted k-mers against the index span of their tile, one 32-byte match record each)",
+                   20.0 + index_bytes_per_lookup, per["lookup"], 1.0, NCU_DRAM_BYTES["lookup"]),
+        "score": ("score_dense_kernel (ordered float32 per-read scores and counts from the match records)" if args.score_mode == "ordered"
+                  else "scoring stage (%s)" % args.score_mode, 0.8, per["per_read"], 1.0, NCU_DRAM_BYTES["score"]),
+    }
+    stage_roofline = {}
+    for key, (name, bytes_unit, ms, launches_per_step, ncu_b) in kernels.items():
+        ach = bytes_unit * kmers_per_batch / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        stage_roofline[key] = {"kernel": name, "bytes_per_unit": bytes_unit, "avg_launch_ms": ms, "launches_per_step": launches_per_step,
+                               "achieved": ach, "frac": ach / peak,
+                               "dram_bytes_per_unit_ncu": ncu_b, "dram_GBps": (ncu_b * kmers_per_batch / (ms * 1e-3) / 1e9) if (ncu_b and ms > 0) else None}
+    dom = max(stage_roofline, key=lambda k: stage_roofline[k]["avg_launch_ms"])
+    d = stage_roofline[dom]
+    roofline = {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved"], "peak": peak, "unit": "GB/s", "frac": d["frac"],
+                "traffic": (d["dram_bytes_per_unit_ncu"] * kmers_per_batch) if d["dram_bytes_per_unit_ncu"] else None,
+                "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this workload's "
+                                  "size (profiles/r02_ncu_*.txt), per k-mer, scaled to this launch",
+                "peak_source": peak_src, "bytes_per_unit": d["bytes_per_unit"], "units_per_launch": kmers_per_batch,
+                "avg_launch_ms": d["avg_launch_ms"], "share_of_step": d["avg_launch_ms"] * d["launches_per_step"] / max(1e-9, sum(per.values())),
+                "note": "dominant kernel = the longest launch of the step; its algorithmic bytes are SURVEY.md §8d's figure for the stage (the "
+                        "accumulate stage is counted there as the dense score write-back only: the kernel is issue-bound, not HBM-bound); "
+                        "whole_step_model is the figure comparable across stages and rounds",
+                "stages": stage_roofline,
+                "whole_step_model": {"bytes_per_lookup": BYTES_PER_LOOKUP_MODEL + index_bytes_per_lookup, "achieved_GBps": None}}
     model_bytes = roofline["whole_step_model"]["bytes_per_lookup"]
     roofline["whole_step_model"]["achieved_GBps"] = (n_kmers / args.steps) * model_bytes / (ms_total / args.steps * 1e-3) / 1e9
     roofline["whole_step_model"]["frac"] = roofline["whole_step_model"]["achieved_GBps"] / peak
@@ -338,10 +386,10 @@ def main_ours(args):
     e2e = None
     if not args.no_e2e:
         n_host = 3
-        host_reads = [torch.empty(R * READ_LEN, dtype=torch.uint8, pin_memory=True) for _ in range(n_host)]
+        host_reads = [torch.empty(R * RL, dtype=torch.uint8, pin_memory=True) for _ in range(n_host)]
         host_scores = [torch.empty(R * T, dtype=torch.float32, pin_memory=True) for _ in range(3)]
-        h_start = (np.arange(R, dtype=np.uint64) * READ_LEN)
-        h_len = np.full(R, READ_LEN, dtype=np.uint32)
+        h_start = (np.arange(R, dtype=np.uint64) * RL)
+        h_len = np.full(R, RL, dtype=np.uint32)
         for b in range(n_host):
             gen(1000 + b, host_reads[b].data_ptr(), capi.MEM_HOST)
 
@@ -380,7 +428,7 @@ def main_ours(args):
         e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3))
         e2e_stages, e2e_batches, _, _ = ctx.stage_times(reset=True)
         e2e = {"value": reads_total / (e2e_ms * 1e-3), "unit": "reads/s",
-               "h2d_bytes_per_step": int(R * READ_LEN + R * 12), "d2h_bytes_per_step": int(R * T * 4),
+               "h2d_bytes_per_step": int(R * RL + R * 12), "d2h_bytes_per_step": int(R * T * 4),
                "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall * 1e3 / args.steps,
                "device_ms_per_step": e0.elapsed_time(e1) / args.steps,
                "stage_ms_per_step": {k: v / max(1, e2e_batches) for k, v in e2e_stages.items()}, "checksum": float(host_scores[(args.steps - 1) % 3][: T * 1000].sum()),
@@ -396,7 +444,7 @@ def main_ours(args):
         try:
             r = cpu_reference_run(args.cpu_reads, args.taxa, args.cpu_genome_len, steps=1, warmup=0)
             cpu = {"value": r["value"], "unit": "reads/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-                   "lookups_per_s": r["lookups_per_s"]}
+                   "lookups_per_s": r["lookups_per_s"], "hot_path_lookups_per_s": r["hot_path_lookups_per_s"]}
         except Exception as e:            # the baseline must never take the bench line down
             cpu = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
 

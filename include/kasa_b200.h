@@ -81,6 +81,9 @@ typedef struct {
 
 /* Replaces: Compare<...> kASAObj construction (main.cpp:1023/1070) resp. Read<...> (main.cpp:664).     */
 int kasa_ctx_create(const kasa_params *params, kasa_ctx **out);
+/* The built-in table kasa_params.codon_table == NULL stands for (kASA.hpp:621-667), for hosts that patch single codons from a
+ * `-a <gc.prt> <id>` file the way kASA::setCodonTable does (kASA.hpp:579-615) before handing the table over.              */
+int kasa_builtin_codon_table(uint8_t *table512);
 void kasa_ctx_destroy(kasa_ctx *ctx);
 const char *kasa_last_error(const kasa_ctx *ctx);   /* never NULL; ctx may be NULL (creation errors)   */
 int kasa_abi_version(void);

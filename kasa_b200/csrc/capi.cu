@@ -884,6 +884,13 @@ int kasa_identify_wait(kasa_ctx *c)
     KASA_API_END(c)
 }
 
+int kasa_builtin_codon_table(uint8_t *table512)
+{
+    if (!table512) return KASA_ERR_ARG;
+    builtin_codon_table(table512);
+    return KASA_OK;
+}
+
 int kasa_host_alloc(void **ptr, uint64_t bytes)
 {
     if (!ptr) return KASA_ERR_ARG;

@@ -1639,11 +1639,13 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
         const float q = __uint_as_float(tid >= 2 ? (uint32_t)(((1u << 24) + (tid >> 1)) / tid) : 0u);
         s_inv[tid] = inv;
         s_vq0[tid] = make_float2(__fmul_rn(wj[0], inv), q);
-        s_vq1[tid] = make_float2(__fmul_rn(wj[1], inv), __uint_as_float(tid >= 2 ? inv_fx((uint32_t)tid) : 0u));     // (.y in 2^-32 units: levels above k_low)
+        s_vq1[tid] = make_float2(__fmul_rn(wj[1], inv), q);
         s_q32[tid] = tid >= 2 ? inv_fx((uint32_t)tid) : 0u;
     }
     __syncthreads();
-    unsigned long long fa64 = 0, fb64 = 0, ga64 = 0, gb64 = 0;          // sums of 1 / n of this lane's taxa (lane + 1, lane + 33): k_low in 2^-24, k_low + 1 in 2^-32 units
+    // sums of 1 / n of this lane's taxa (lane + 1, lane + 33) at k_low and k_low + 1, 2^-24 units (shared-memory atomics per k-mer
+    // for the second level were measured: + 8 ms per step)
+    unsigned long long fa64 = 0, fb64 = 0, ga64 = 0, gb64 = 0;
     const uint32_t lbit = 1u << lane;
     constexpr uint32_t kList = 0xfffffffeu, kSeveral = 0x7fffffffu;
 
@@ -1654,7 +1656,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
         const uint32_t ni = (uint32_t)(read_koff[r + 1] - s0);
         const uint64_t *p = rec + s0 * kRecWords;
         float sa = 0.f, sb = 0.f;
-        uint32_t fa = 0, fb = 0;
+        uint32_t fa = 0, fb = 0, ga = 0, gb = 0;
         uint64_t nx[4] = {0, 0, 0, 0};
         if (lane < ni) asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(p + (uint64_t)lane * kRecWords));
 #pragma unroll 1
@@ -1771,8 +1773,8 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                 {   // level k_low + 1: a second mask
                     const uint4 b = M.b[i];
                     const float v1 = __uint_as_float(b.z);
-                    if (b.x & lbit) { sa = __fadd_rn(sa, v1); ga64 += b.w; }
-                    if (TWO && (b.y & lbit)) { sb = __fadd_rn(sb, v1); gb64 += b.w; }
+                    if (b.x & lbit) { sa = __fadd_rn(sa, v1); ga += b.w; }
+                    if (TWO && (b.y & lbit)) { sb = __fadd_rn(sb, v1); gb += b.w; }
                 }
                 const uint32_t ud = u & kSeveral;
                 if (ud == 0u) continue;
@@ -1805,10 +1807,10 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                 }
             }
             // a k-mer adds at most 2^23 units to a sum: widen before 32 bits could overflow
-            if ((b0 & 255u) == 224u) { fa64 += fa; fb64 += fb; fa = fb = 0; }
+            if ((b0 & 255u) == 224u) { fa64 += fa; fb64 += fb; ga64 += ga; gb64 += gb; fa = fb = ga = gb = 0; }
             __syncwarp();
         }
-        fa64 += fa; fb64 += fb;
+        fa64 += fa; fb64 += fb; ga64 += ga; gb64 += gb;
         if (scores) {
             float *row = scores + (uint64_t)r * T;
             if (lane == 0) row[0] = 0.f;
@@ -1818,11 +1820,11 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
     }
     if ((int)lane + 1 < T) {
         if (fa64) atomicAdd(&s_fx[lane], fa64 << kFxShift);
-        if (ga64) atomicAdd(&s_fx[64 + lane], ga64);
+        if (ga64) atomicAdd(&s_fx[64 + lane], ga64 << kFxShift);
     }
     if (TWO && (int)lane + 33 < T) {
         if (fb64) atomicAdd(&s_fx[lane + 32], fb64 << kFxShift);
-        if (gb64) atomicAdd(&s_fx[64 + lane + 32], gb64);
+        if (gb64) atomicAdd(&s_fx[64 + lane + 32], gb64 << kFxShift);
     }
     __syncthreads();
     for (int i = tid; i < NK * 64; i += blockDim.x) {

@@ -46,7 +46,7 @@ struct Pinned {
 };
 
 struct Args {
-    std::string mode, content, index, input, in1, in2, profile, rtt, tmp;
+    std::string mode, content, index, input, in1, in2, profile, rtt, tmp, alphabet_file, alphabet_id;
     int k_high = 12, k_low = 7, highest_k = 12, beasts = 3, device = 0, gpus = 1;
     bool six = false, verbose = false, exact = false;
     float threshold = 0.f;
@@ -58,6 +58,7 @@ struct Args {
 {
     std::cout << "kasa_b200 <build|identify> -c <content> -d <index> [-i <input> | -1 <fq> -2 <fq>] [-p <profile.csv>] [-q <per-read out>]\n"
                  "          [-k <high> <low>] [--kH <12|25>] [--six] [--json|--jsonl|--tsv|--kraken] [-b <n>] [--threshold <f>] [-v]\n"
+                 "          [-a <gc.prt> <id>]\n"
                  "          [--exact-scores] [--device <n>] [--gpus <n>] [--batch-reads <n>]   (-m -n -t -r -x are accepted and ignored)\n";
     std::exit(0);
 }
@@ -81,6 +82,7 @@ Args parse(int argc, char **argv)
         else if (p == "-k") { a.k_high = std::stoi(next()); a.k_low = std::stoi(next()); }
         else if (p == "--kH") a.highest_k = std::stoi(next()) > 12 ? 25 : 12;
         else if (p == "--kL") (void)next();
+        else if (p == "-a" || p == "--alphabet") { a.alphabet_file = next(); a.alphabet_id = next(); }
         else if (p == "-b" || p == "--beasts") { a.beasts = std::stoi(next()); if (a.beasts == 0) a.beasts = 1; }
         else if (p == "--threshold") a.threshold = std::stof(next());
         else if (p == "--six") a.six = true;
@@ -107,6 +109,26 @@ void check(int rc, kasa_ctx *ctx)
     if (rc != KASA_OK) throw std::runtime_error(kasa_last_error(ctx));
 }
 
+// `-a <file> <id>`: the translation table `id` of an NCBI gc.prt file replaces the codons it names in the built-in table
+// (kASA::setCodonTable, kASA.hpp:579-615: same lookup of "  id <n> ,", same five lines, '*' becomes '[').
+// Returns false (built-in table stays, with the reference's warning) when the id is not in the file.
+bool load_codon_table(const std::string &file, const std::string &id, uint8_t table[512])
+{
+    kasa_builtin_codon_table(table);
+    std::ifstream f(file);
+    std::string line;
+    bool found = false;
+    while (std::getline(f, line))
+        if (line.find("  id " + id + " ,") != std::string::npos) { found = true; break; }
+    if (!found) { std::cerr << "WARNING: codon table not found in file. Using built-in." << std::endl; return false; }
+    std::string aa, dummy, b1, b2, b3;
+    std::getline(f, aa); std::getline(f, dummy); std::getline(f, b1); std::getline(f, b2); std::getline(f, b3);
+    size_t pa = aa.find_first_of('"') + 1, pb = b1.find_first_of("TGCA");
+    for (; pb != std::string::npos && pb < b1.size() && pb < b2.size() && pb < b3.size() && pa < aa.size(); ++pb, ++pa)
+        table[((b1[pb] & 14) << 5) | ((b2[pb] & 14) << 2) | ((b3[pb] & 14) >> 1)] = aa[pa] == '*' ? (uint8_t)'[' : (uint8_t)aa[pa];
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------ build
 int run_build(const Args &a)
 {
@@ -116,6 +138,8 @@ int run_build(const Args &a)
     kasa_params p{};
     p.device = a.device; p.highest_k = K; p.k_high = K; p.k_low = std::min(7, K); p.frames = a.six ? 6 : 3;
     p.score_mode = KASA_SCORE_NONE;
+    uint8_t codon[512];
+    if (!a.alphabet_file.empty() && load_codon_table(a.alphabet_file, a.alphabet_id, codon)) p.codon_table = codon;
     const uint64_t windows = (uint64_t)fasta.size() * (a.six ? 2 : 1) + (1u << 20);
     p.max_batch_kmers = std::min<uint64_t>(std::max<uint64_t>(windows * 2, 1u << 22), (1ull << 32) - (1u << 20));
     p.max_batch_seqs = 1u << 20;
@@ -223,7 +247,9 @@ int run_identify(const Args &a)
 
     kasa_params p{};
     p.device = a.device; p.highest_k = K; p.k_high = k_high; p.k_low = k_low; p.frames = a.six ? 6 : 3;
-    p.score_mode = a.rtt.empty() ? KASA_SCORE_NONE : (a.exact ? KASA_SCORE_EXACT : KASA_SCORE_FAST);
+    p.score_mode = a.rtt.empty() ? KASA_SCORE_NONE : (a.exact ? KASA_SCORE_EXACT : KASA_SCORE_ORDERED);
+    uint8_t codon[512];
+    if (!a.alphabet_file.empty() && load_codon_table(a.alphabet_file, a.alphabet_id, codon)) p.codon_table = codon;
     const uint32_t per_batch = std::max<uint32_t>(1, std::min<uint32_t>(a.batch_reads, (uint32_t)reads.size()));
     uint64_t max_bases = 0, max_kmers = 0;
     const uint32_t marker = 3 * (K - k_low);

@@ -79,7 +79,9 @@ def _run(case, K, k_high, k_low, six, n_shards, paired=False):
         c.close()
     assert total == 2 * want_total
     assert np.array_equal(cu, 2 * want_cu)
-    np.testing.assert_allclose(ca, 2 * want_ca, rtol=1e-12)
+    # counts are sums of 1 / n in fixed point; the unsharded run may take level k_low + 1 in 2^-24 units (dense scoring kernel of
+    # presorted batches), the sharded one in 2^-32: both far inside the 1e-6 the oracle comparison asks for
+    np.testing.assert_allclose(ca, 2 * want_ca, rtol=1e-7)
 
 
 def test_sharded_k12_three_shards():

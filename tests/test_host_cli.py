@@ -85,6 +85,22 @@ def test_cli_build_files_byte_identical(case, flags, tmp_path):
     assert open(idx + "_f.txt").read() == G.text(case, "idx_f.txt")
 
 
+@pytest.mark.gpu
+def test_cli_build_with_another_codon_table(tmp_path):
+    """`-a <gc.prt> <id>` (kASA::setCodonTable, kASA.hpp:579-615): the index equals the one `kASA build -a` wrote for the same file
+    (translation table 4: TGA = W instead of stop; tests/golden/k12/alt_codon_sha256.txt from oracle/_ref/kASA_scalar)."""
+    import hashlib
+    idx = str(tmp_path / "idx")
+    rc, out, err = _cli("build", "-c", _g("k12", "content.txt"), "-d", idx, "-i", _g("k12", "ref.fa.gz"), "-a", _g("k12", "gc.prt"), "4")
+    assert rc == 0, err
+    n_want, sha_want = G.text("k12", "alt_codon_sha256.txt").split()
+    n = int(open(idx + "_info.txt").read().split()[0])
+    assert n == int(n_want)
+    data = open(idx, "rb").read()[:n * 12]
+    assert hashlib.sha256(data).hexdigest() == sha_want
+    assert data != G.gz("k12", "idx.gz")          # and it differs from the standard-code index
+
+
 def _write_index(case, tmp_path):
     """golden index files laid out the way `identify -d` expects them."""
     idx = str(tmp_path / "idx")
