@@ -284,12 +284,18 @@ typedef struct {
     const uint32_t *taxid;    /* [n_seqs]                                                               */
 } kasa_seq_batch;
 
-/* Replaces: Read::dnaTokMers + Build::addToInt (Read.hpp:1991-2139, Build.hpp:116-130).                */
+/* Replaces: Read::dnaTokMers + Build::addToInt (Read.hpp:1991-2139, Build.hpp:116-130).
+ * The records collect in a device brick of max_batch_kmers records.  A full brick is sorted and deduplicated in place; if it
+ * is still more than half full of distinct records it leaves for host memory (the reference's spill to a temporary file,
+ * Build.hpp:328-352) and a new brick starts, so the size of an index is bounded by host memory, not by max_batch_kmers or HBM.
+ * One push may not yield more than max_batch_kmers windows.                                                              */
 int kasa_build_push(kasa_ctx *ctx, const kasa_seq_batch *in);
 
 /* Replaces: Build::IntToExtPart + mergeTemporaries (Build.hpp:305-477), Trie::SaveToStxxlVec
  * (Trie.hpp:366-394).  Sorts by (kmer, taxid), removes duplicates, run-length encodes the 6-letter
- * prefixes.  Outputs the counts; fetch the data with kasa_build_fetch.                                  */
+ * prefixes.  Outputs the counts; fetch the data with kasa_build_fetch.  When bricks were spilled they are merged here, one
+ * range of six-letter prefixes at a time through the device brick; the merged index then stays in host memory
+ * (kasa_build_fetch / _frequency / kasa_index_from_build work as usual, kasa_index_from_build needs it to fit the device). */
 int kasa_build_finish(kasa_ctx *ctx, uint64_t *n_entries, uint64_t *n_trie);
 
 /* Copy out the built index in file layout: entries = packedBigPair / packedLargePair records,

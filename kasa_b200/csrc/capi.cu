@@ -72,6 +72,13 @@ struct kasa_ctx {
     bool build_done = false;
     uint64_t n_trie = 0;
     uint32_t *d_trie_words = nullptr;
+    // build larger than one brick: full bricks (sorted, distinct) wait in host memory and are merged by prefix range when the build
+    // finishes (Build::IntToExtPart / mergeTemporaries, Build.hpp:305-477); the merged index then lives in host memory too
+    struct HostBrick { std::vector<uint64_t> lo, hi; std::vector<uint32_t> tax; };
+    std::vector<HostBrick> spills;
+    bool host_result = false;
+    uint64_t host_n = 0;
+    std::vector<uint32_t> host_words, host_trie;      // file records (3 or 5 words each) / prefix-table records (3 words each)
     ExactWorkspace xws{};
     bool xws_ready = false;
     // pipelined identify (kasa_identify_submit / _wait): two slots of input staging, score buffers and events;
@@ -402,6 +409,119 @@ void build_compact(kasa_ctx *c)
     c->build_fill = n_unique;
 }
 
+// Trie.hpp:366-394 for the brick in c->build_buf: run lengths of the first six letters -> c->d_trie_words, c->n_trie.
+// Scratch lives in d_rec: [flags/pos: n+1 u64][run starts: n_runs+1 u64][trie words: 3 u32 per run]
+void build_trie(kasa_ctx *c)
+{
+    const uint64_t n = c->build_fill;
+    const int b = c->build_buf;
+    c->n_trie = 0;
+    if (!n) return;
+    uint64_t *flags = c->d_rec;
+    launch_prefix_flags(c->stream, c->sb.w0[b], c->sb.w1[b], n, c->K, flags, &c->launches);
+    exclusive_scan_u64(c->stream, flags, n, c->d_scan_tmp, &c->launches);
+    const uint64_t runs = read_u64(c, flags + n);
+    uint64_t *starts = flags + n + 1;
+    c->d_trie_words = reinterpret_cast<uint32_t *>(starts + runs + 1);
+    launch_trie_records(c->stream, c->sb.w0[b], c->sb.w1[b], n, c->K, flags, runs, starts, c->d_trie_words, &c->launches);
+    KASA_CUDA_TRY(cudaGetLastError());
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->n_trie = runs;
+}
+
+// the compacted brick (sorted, distinct records) leaves for host memory: Build::IntToExtPart's spill (Build.hpp:328-352)
+void spill_brick(kasa_ctx *c)
+{
+    const uint64_t n = c->build_fill;
+    if (!n) return;
+    const int b = c->build_buf;
+    kasa_ctx::HostBrick hb;
+    hb.lo.resize(n); hb.tax.resize(n);
+    KASA_CUDA_TRY(cudaMemcpyAsync(hb.lo.data(), c->sb.w0[b], n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (c->wide) { hb.hi.resize(n); KASA_CUDA_TRY(cudaMemcpyAsync(hb.hi.data(), c->sb.w1[b], n * 8, cudaMemcpyDeviceToHost, c->stream)); }
+    KASA_CUDA_TRY(cudaMemcpyAsync(hb.tax.data(), c->sb.v[b], n * 4, cudaMemcpyDeviceToHost, c->stream));
+    KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->spills.push_back(std::move(hb));
+    c->build_fill = 0;
+    c->build_buf = 0;
+}
+
+// first record of brick `hb` whose six-letter prefix is >= p (the bricks are sorted by k-mer)
+static uint64_t brick_lower(const kasa_ctx *c, const kasa_ctx::HostBrick &hb, uint64_t p)
+{
+    const int sh = c->wide ? 5 * c->K - 30 - 64 : 5 * c->K - 30;
+    const std::vector<uint64_t> &key = c->wide ? hb.hi : hb.lo;
+    return (uint64_t)(std::partition_point(key.begin(), key.end(), [&](uint64_t k) { return (k >> sh) < p; }) - key.begin());
+}
+
+// Build::mergeTemporaries (Build.hpp:360-477) without its priority queue: the key space is cut at six-letter prefixes into
+// ranges whose records — over all spilled bricks — fit one device brick; every range is copied in, sorted and deduplicated
+// by the same kernels as a single brick, run-length encoded, and appended to the host-side result.  The ranges concatenate
+// to the file `kASA build` writes (the prefix table is per prefix, so its pieces concatenate too).
+void merge_spills(kasa_ctx *c)
+{
+    const uint64_t cap = c->p.max_batch_kmers;
+    const size_t wpr = c->wide ? 5 : 3;
+    c->host_words.clear(); c->host_trie.clear(); c->host_n = 0;
+    uint64_t total_trie = 0;
+    const uint64_t p_end = 1ull << 30;
+    std::vector<uint64_t> at(c->spills.size()), to(c->spills.size());
+    for (size_t i = 0; i < c->spills.size(); ++i) at[i] = 0;
+    uint64_t p = 0;
+    while (p < p_end) {
+        // largest q > p with at most cap records in [p, q)
+        auto count_to = [&](uint64_t q) { uint64_t n = 0; for (size_t i = 0; i < c->spills.size(); ++i) n += brick_lower(c, c->spills[i], q) - at[i]; return n; };
+        uint64_t q = p_end;
+        if (count_to(q) > cap) {
+            uint64_t lo = p + 1, hi = p_end;                 // count_to(lo) may exceed cap: checked below
+            while (lo < hi) { const uint64_t mid = lo + (hi - lo + 1) / 2; if (count_to(mid) <= cap) lo = mid; else hi = mid - 1; }
+            q = lo;
+            KASA_REQUIRE(count_to(q) <= cap, KASA_ERR_NOMEM, "one six-letter prefix holds more records than max_batch_kmers: the bricks cannot be merged");
+        }
+        uint64_t n = 0;
+        for (size_t i = 0; i < c->spills.size(); ++i) {
+            const kasa_ctx::HostBrick &hb = c->spills[i];
+            to[i] = brick_lower(c, hb, q);
+            const uint64_t m = to[i] - at[i];
+            if (m) {
+                KASA_CUDA_TRY(cudaMemcpyAsync(c->sb.w0[0] + n, hb.lo.data() + at[i], m * 8, cudaMemcpyHostToDevice, c->stream));
+                if (c->wide) KASA_CUDA_TRY(cudaMemcpyAsync(c->sb.w1[0] + n, hb.hi.data() + at[i], m * 8, cudaMemcpyHostToDevice, c->stream));
+                KASA_CUDA_TRY(cudaMemcpyAsync(c->sb.v[0] + n, hb.tax.data() + at[i], m * 4, cudaMemcpyHostToDevice, c->stream));
+            }
+            n += m;
+            at[i] = to[i];
+        }
+        p = q;
+        if (!n) continue;
+        c->build_buf = 0; c->build_fill = n;
+        build_compact(c);                                     // sort + dedup of the range (duplicates across bricks go here)
+        build_trie(c);
+        const uint64_t m = c->build_fill;
+        const int b = c->build_buf;
+        // file records through the free half of the sort ping-pong, in chunks
+        uint32_t *stage = reinterpret_cast<uint32_t *>(c->sb.w0[b ^ 1]);
+        const uint64_t chunk = std::max<uint64_t>(1, cap * 8 / (wpr * 4));
+        c->host_words.resize((size_t)(c->host_n + m) * wpr);
+        for (uint64_t o = 0; o < m; o += chunk) {
+            const uint64_t k = std::min(chunk, m - o);
+            launch_pack_records(c->stream, c->sb.w0[b] + o, c->wide ? c->sb.w1[b] + o : nullptr, c->sb.v[b] + o, k, stage, &c->launches);
+            KASA_CUDA_TRY(cudaMemcpyAsync(c->host_words.data() + (size_t)(c->host_n + o) * wpr, stage, k * wpr * 4, cudaMemcpyDeviceToHost, c->stream));
+            KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+        c->host_trie.resize((size_t)(total_trie + c->n_trie) * 3);
+        if (c->n_trie) {
+            KASA_CUDA_TRY(cudaMemcpyAsync(c->host_trie.data() + (size_t)total_trie * 3, c->d_trie_words, c->n_trie * 12, cudaMemcpyDeviceToHost, c->stream));
+            KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+        c->host_n += m;
+        total_trie += c->n_trie;
+    }
+    c->spills.clear(); c->spills.shrink_to_fit();
+    c->n_trie = total_trie;
+    c->build_fill = 0; c->build_buf = 0;
+    c->host_result = true;
+}
+
 int fail(kasa_ctx *c, const Error &e)
 {
     if (c) c->err = e.msg; else g_create_error = e.msg;
@@ -590,6 +710,12 @@ int kasa_index_from_build(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_
     KASA_REQUIRE(c && taxid_of_idx, KASA_ERR_ARG, "null argument");
     KASA_REQUIRE(c->build_done, KASA_ERR_STATE, "kasa_index_from_build needs a finished build (kasa_build_finish)");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    if (c->host_result) {
+        // a build that spilled bricks left its merged index in host memory: loaded like an index file
+        const int rc = kasa_index_load(c, c->host_words.data(), c->host_n, c->wide ? 128 : 64, taxid_of_idx, n_taxa);
+        if (rc != KASA_OK) throw Error{rc, c->err};
+        return KASA_OK;
+    }
     drop_index(c);
     set_taxa(c, n_taxa);
     const uint64_t n = c->build_fill;
@@ -694,7 +820,7 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
 // that kernel reads.
 static bool scores_straight_from_records(const kasa_ctx *c, uint32_t max_inst, bool want_hits)
 {
-    return c->p.score_mode != KASA_SCORE_EXACT && !want_hits && ops_mask_stream(level_params(c)) && max_inst <= (uint32_t)kPresortMax && c->score_sorted &&
+    return c->p.score_mode != KASA_SCORE_EXACT && !want_hits && c->n_taxa <= (uint32_t)kMaskTaxa && max_inst <= (uint32_t)kPresortMax && c->score_sorted &&
            !c->sh.on;
 }
 
@@ -838,7 +964,7 @@ int kasa_identify_submit(kasa_ctx *c, const kasa_read_batch *in, kasa_batch_resu
         KASA_CUDA_TRY(cudaMemsetAsync(c->ovf.cursor, 0, 8, c->stream));
         launch_partition(c->stream, c->sb.w0[cur], c->sb.w1[cur], n, idx, lp, c->d_part, tq, sorted_from, &c->launches);
         launch_lookup(c->stream, c->sb.w0[cur], c->sb.w1[cur], c->sb.v[cur], n, 0, idx, lp, c->d_part, c->d_rec, tq, c->ovf, 0, c->d_err,
-                      &c->launches, scores_straight_from_records(c, max_inst, want_hits) && score_sorted_two_masks(c->score_lanes));
+                      &c->launches, scores_straight_from_records(c, max_inst, want_hits) && score_sorted_two_masks(c->score_lanes, lp));
         KASA_CUDA_TRY(cudaEventRecord(sl.sev[5], c->stream));
         score_stage(c, sl, n, in->n_reads, max_inst, cur, want_dense, want_hits);
     } else {
@@ -1078,6 +1204,7 @@ int kasa_index_from_build_shard(kasa_ctx *c, const uint32_t *taxid_of_idx, uint3
     KASA_API_BEGIN
     KASA_REQUIRE(c && taxid_of_idx && entry_begin && prefix_begin, KASA_ERR_ARG, "null argument");
     KASA_REQUIRE(c->build_done, KASA_ERR_STATE, "kasa_index_from_build_shard needs a finished build (kasa_build_finish)");
+    KASA_REQUIRE(!c->host_result, KASA_ERR_STATE, "the build spilled bricks to host memory: fetch it (kasa_build_fetch) and load the shards with kasa_index_load");
     KASA_REQUIRE(n_shards >= 1 && n_shards <= KASA_MAX_SHARDS && rank >= 0 && rank < n_shards, KASA_ERR_ARG,
                  "need 0 <= rank < n_shards <= KASA_MAX_SHARDS");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
@@ -1367,7 +1494,7 @@ int kasa_build_push(kasa_ctx *c, const kasa_seq_batch *in)
     KASA_REQUIRE(in->n_seqs <= c->p.max_batch_seqs, KASA_ERR_NOMEM, "batch has more sequences than max_batch_seqs");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
     ensure_workspace(c);
-    if (c->build_done) { c->build_done = false; c->build_fill = 0; c->build_buf = 0; }
+    if (c->build_done) { c->build_done = false; c->build_fill = 0; c->build_buf = 0; c->host_result = false; c->host_n = 0; c->host_words.clear(); c->host_trie.clear(); }
     const uint32_t ns = in->n_seqs;
     if (ns == 0) return KASA_OK;
     const char *ascii = in->bases;
@@ -1383,9 +1510,15 @@ int kasa_build_push(kasa_ctx *c, const kasa_seq_batch *in)
     launch_build_counts(c->stream, seq_len, ns, c->K, c->d_koff, &c->launches);
     exclusive_scan_u64(c->stream, c->d_koff, ns, c->d_scan_tmp, &c->launches);
     const uint64_t nw = read_u64(c, c->d_koff + ns);
-    if (c->build_fill + nw > c->p.max_batch_kmers) build_compact(c);     // the brick is full: Build.hpp:116-122
-    KASA_REQUIRE(c->build_fill + nw <= c->p.max_batch_kmers, KASA_ERR_NOMEM,
-                 "index does not fit max_batch_kmers records (prefix-sharded multi-GPU build is not in this version)");
+    KASA_REQUIRE(nw <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "one push yields more k-mer windows than max_batch_kmers: push fewer sequences at a time");
+    if (c->build_fill + nw > c->p.max_batch_kmers) {                     // the brick is full: Build.hpp:116-122
+        build_compact(c);
+        // still (more than half) full of distinct records: it leaves for host memory and a new brick starts (Build.hpp:328-352)
+        if (c->build_fill + nw > c->p.max_batch_kmers || c->build_fill > c->p.max_batch_kmers / 2) {
+            KASA_REQUIRE(!c->sh.on, KASA_ERR_NOMEM, "the brick of a prefix-sharded build is full: use more shards or a larger max_batch_kmers");
+            spill_brick(c);
+        }
+    }
     const int b = c->build_buf;
     const uint64_t o = c->build_fill;
     launch_extract_build(c->stream, ascii, seq_start, seq_len, taxid, ns, c->K, c->d_codon, c->d_koff, nw, c->sb.w0[b] + o,
@@ -1408,22 +1541,13 @@ int kasa_build_finish(kasa_ctx *c, uint64_t *n_entries, uint64_t *n_trie)
         c->sh.pull_pending = false;
     }
     build_compact(c);
-    const uint64_t n = c->build_fill;
-    const int b = c->build_buf;
-    c->n_trie = 0;
-    if (n) {
-        // Trie.hpp:366-394: run lengths of the first six letters.  Scratch lives in d_rec:
-        // [flags/pos: n+1 u64][run starts: n_runs+1 u64][trie words: 3 u32 per run]
-        uint64_t *flags = c->d_rec;
-        launch_prefix_flags(c->stream, c->sb.w0[b], c->sb.w1[b], n, c->K, flags, &c->launches);
-        exclusive_scan_u64(c->stream, flags, n, c->d_scan_tmp, &c->launches);
-        const uint64_t runs = read_u64(c, flags + n);
-        uint64_t *starts = flags + n + 1;
-        c->d_trie_words = reinterpret_cast<uint32_t *>(starts + runs + 1);
-        launch_trie_records(c->stream, c->sb.w0[b], c->sb.w1[b], n, c->K, flags, runs, starts, c->d_trie_words, &c->launches);
-        KASA_CUDA_TRY(cudaGetLastError());
-        KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
-        c->n_trie = runs;
+    uint64_t n = c->build_fill;
+    if (!c->spills.empty()) {
+        spill_brick(c);                                      // the last brick joins the others; the merged index lives in host memory
+        merge_spills(c);
+        n = c->host_n;
+    } else {
+        build_trie(c);
     }
     c->build_done = true;
     if (n_entries) *n_entries = n;
@@ -1437,6 +1561,11 @@ int kasa_build_fetch(kasa_ctx *c, void *entries, void *trie)
     KASA_REQUIRE(c, KASA_ERR_ARG, "null context");
     KASA_REQUIRE(c->build_done, KASA_ERR_STATE, "kasa_build_fetch before kasa_build_finish");
     KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    if (c->host_result) {
+        if (trie && c->n_trie) std::memcpy(trie, c->host_trie.data(), c->n_trie * 12);
+        if (entries && c->host_n) std::memcpy(entries, c->host_words.data(), c->host_words.size() * 4);
+        return KASA_OK;
+    }
     const uint64_t n = c->build_fill;
     const int b = c->build_buf;
     if (trie && c->n_trie) {
@@ -1472,8 +1601,23 @@ int kasa_build_frequency(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_t
     uint16_t *dense = reinterpret_cast<uint16_t *>(c->sb.v[b ^ 1]);     // free half of the ping-pong
     unsigned long long *d_freq = dev_alloc<unsigned long long>(c, cells);
     KASA_CUDA_TRY(cudaMemsetAsync(d_freq, 0, cells * 8, c->stream));
+    if (c->host_result) {
+        // merged index in host memory: streamed through the device brick by brick
+        const size_t wpr = c->wide ? 5 : 3;
+        const uint64_t chunk = std::max<uint64_t>(1, c->p.max_batch_kmers * 8 / (wpr * 4));
+        uint32_t *stage = reinterpret_cast<uint32_t *>(c->sb.w0[1]);
+        for (uint64_t o = 0; o < c->host_n; o += chunk) {
+            const uint64_t k = std::min(chunk, c->host_n - o);
+            KASA_CUDA_TRY(cudaMemcpyAsync(stage, c->host_words.data() + (size_t)o * wpr, k * wpr * 4, cudaMemcpyHostToDevice, c->stream));
+            launch_unpack_records(c->stream, stage, k, c->wide, c->sb.w0[0], c->sb.w1[0], c->sb.v[0], &c->launches);
+            launch_map_taxids(c->stream, c->sb.v[0], k, tt.d_taxid, tt.d_idx, tt.n, reinterpret_cast<uint16_t *>(c->sb.v[1]), c->d_err, &c->launches);
+            launch_frequency(c->stream, c->sb.w0[0], c->sb.w1[0], reinterpret_cast<uint16_t *>(c->sb.v[1]), k, c->K, n_taxa, d_freq, &c->launches);
+            KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+    } else {
     launch_map_taxids(c->stream, c->sb.v[b], n, tt.d_taxid, tt.d_idx, tt.n, dense, c->d_err, &c->launches);
     launch_frequency(c->stream, c->sb.w0[b], c->sb.w1[b], dense, n, c->K, n_taxa, d_freq, &c->launches);
+    }
     KASA_CUDA_TRY(cudaGetLastError());
     KASA_CUDA_TRY(cudaMemcpyAsync(freq, d_freq, cells * 8, cudaMemcpyDeviceToHost, c->stream));
     check_device_flags(c);

@@ -1602,6 +1602,7 @@ __global__ void __launch_bounds__(kItemBlock) score_items_kernel(const uint64_t 
 //          warp-uniform, nothing is indexed dynamically, nothing depends on how many taxa a k-mer names.
 // The sparse organisations above execute fewer useful lanes' worth of work but pay full price for every rare path a single lane takes;
 // against a saturated index (C2: 0.6 up pairs per k-mer, 10 % of the records with several) this one issues the fewest instructions.
+template <int ML>
 struct DenseWarpMem {
     uint4 a[32];              // per k-mer: taxa mask of level k_low (lo, hi), bits of float(w_0 * (1.f / n0)), 2^24 / n0 (0 for n0 < 2)
     uint4 b[32];              // the same for level k_low + 1 (two-mask records, lookup.cuh)
@@ -1609,31 +1610,35 @@ struct DenseWarpMem {
                               // val[]), else the only such pair (taxon | levels << 16); 0xfffffffe = list record (head[], pairs[])
     uint4 pairs[32];          // .xy = the record's pair word w3 when it holds several pairs; list records: the words w2, w3
     uint4 head[32];           // list records: the words w0, w1
-    float4 val[32];           // float(w_j * (1.f / n_j)) for the levels j = 2 .. 5 of a record with several pairs
+    float val[32][ML <= 6 ? 4 : 24];   // float(w_j * (1.f / n_j)) for the levels j = 2 .. ML - 1 of a record with several pairs
 };
 
-template <bool TWO>
+// ML = 6: the default k = 12..7 (six levels, chains unrolled); ML = 26: up to 26 levels (k = 25..7 and every other range kASA allows)
+template <bool TWO, int ML>
 __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint64_t *__restrict__ rec, const uint64_t *__restrict__ read_koff, uint32_t n_reads,
                                                                       LevelParams lp, OverflowPeers peers, float *__restrict__ scores,
                                                                       unsigned long long *__restrict__ cnt_fx, unsigned long long *__restrict__ cnt_unique,
                                                                       uint32_t *__restrict__ err_flag)
 {
-    __shared__ __align__(16) DenseWarpMem s_w[kBlkWarps];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DenseWarpMem<ML> *s_w = reinterpret_cast<DenseWarpMem<ML> *>(smem_raw);        // [kBlkWarps]
     __shared__ float2 s_vq0[72], s_vq1[72];                             // [n]: .x = float(w_j * (1.f / n)) for j = 0, 1; .y = bits of 2^24 / n resp. 2^32 / n (0 for n < 2)
     __shared__ float s_inv[72];
     __shared__ uint32_t s_q32[72];                                      // 2^32 / n
-    __shared__ unsigned long long s_fx[6 * 64];                         // CTA totals [level][taxon - 1], 2^-32 units
-    __shared__ uint32_t s_un[6 * 64];
-    __shared__ uint32_t s_hist[64 * 8];                                 // [taxon - 1][h]: k-mers where the taxon is alone at its levels 2 .. h-1
+    __shared__ unsigned long long s_fx[ML * 64];                        // CTA totals [level][taxon - 1], 2^-32 units
+    __shared__ uint32_t s_un[ML * 64];
+    __shared__ uint32_t s_hist[64 * 32];                                // [taxon - 1][h]: k-mers where the taxon is alone at its levels 2 .. h-1
+    __shared__ float s_wl[32];                                          // level weights (Compare.hpp:392)
     const int tid = threadIdx.x, T = lp.n_taxa, NK = lp.num_k;
     const uint32_t lane = tid & 31u;
     const int w = tid >> 5;
-    DenseWarpMem &M = s_w[w];
+    DenseWarpMem<ML> &M = s_w[w];
     float wj[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) { const int k = lp.k_low + j; wj[j] = (float)(k * k) / 625.f; }      // Compare.hpp:392
-    for (int i = tid; i < 6 * 64; i += blockDim.x) { s_fx[i] = 0; s_un[i] = 0; }
-    for (int i = tid; i < 64 * 8; i += blockDim.x) s_hist[i] = 0;
+    for (int i = tid; i < ML * 64; i += blockDim.x) { s_fx[i] = 0; s_un[i] = 0; }
+    for (int i = tid; i < 64 * 32; i += blockDim.x) s_hist[i] = 0;
+    if (tid < 32) { const int kk = lp.k_low + tid; s_wl[tid] = (float)(kk * kk) / 625.f; }
     if (tid < 72) {
         const float inv = tid ? __fdiv_rn(1.f, (float)tid) : 0.f;       // Compare.hpp:924: 1.f / numOfEntries
         const float q = __uint_as_float(tid >= 2 ? (uint32_t)(((1u << 24) + (tid >> 1)) / tid) : 0u);
@@ -1692,25 +1697,21 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                 const uint32_t e0 = (uint32_t)w3 & kPairMask;
                 if (e0 && (w3 >> kPairBits) == 0) {
                     upd |= e0;                                                                // the usual case: one taxon, alone at its levels 2 ..
-                    atomicAdd(&s_hist[((e0 & 0xffffu) - 1u) * 8 + ((e0 >> 16) & 7u)], 1u);
+                    atomicAdd(&s_hist[((e0 & 0xffffu) - 1u) * 32 + ((e0 >> 16) & 31u)], 1u);
                 } else if (e0) {
                     // several taxa at three or more levels: level sizes (nibbles), level values, counts
                     const uint32_t e[3] = {e0, (uint32_t)(w3 >> kPairBits) & kPairMask, (uint32_t)(w3 >> (2 * kPairBits)) & kPairMask};
-                    uint32_t njp = 0;                                                         // nibble j - 1 = number of pairs reaching level j
+                    uint64_t nlo = 0, nhi = 0;                                                // nibble j = number of pairs reaching level j (<= 3)
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) { const uint32_t h = e[k] >> 16; njp += h ? ((1u << (4 * (h - 1u))) - 1u) & 0x11111u : 0u; }
-                    float vj[6];
-#pragma unroll
-                    for (int j = 2; j < 6; ++j) vj[j] = __fmul_rn(wj[j], s_inv[(njp >> (4 * (j - 1))) & 15u]);
-                    M.val[lane] = make_float4(vj[2], vj[3], vj[4], vj[5]);
+                    for (int k = 0; k < 3; ++k) { uint64_t x, y; nib_below(e[k] >> 16, x, y); nlo += x; nhi += y; }
+                    const uint32_t hm = max(e[0] >> 16, max(e[1] >> 16, e[2] >> 16));
+                    for (uint32_t j = 2; j < hm && j < (uint32_t)ML; ++j) M.val[lane][j - 2] = __fmul_rn(s_wl[j], s_inv[nib_get(nlo, nhi, j)]);
                     M.pairs[lane] = make_uint4((uint32_t)w3, (uint32_t)(w3 >> 32), 0u, 0u);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         const uint32_t h = e[k] >> 16, c = (e[k] & 0xffffu) - 1u;
-#pragma unroll
-                        for (int j = 2; j < 6; ++j) {
-                            if ((uint32_t)j >= h) break;
-                            const uint32_t nn = (njp >> (4 * (j - 1))) & 15u;
+                        for (uint32_t j = 2; j < h && j < (uint32_t)ML; ++j) {
+                            const uint32_t nn = nib_get(nlo, nhi, j);
                             if (nn == 1u) atomicAdd(&s_un[j * 64 + c], 1u);
                             else atomicAdd(&s_fx[j * 64 + c], (unsigned long long)s_q32[nn]);
                         }
@@ -1746,19 +1747,21 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                     const uint64_t l2 = ((uint64_t)pw.y << 32) | pw.x, l3 = ((uint64_t)pw.w << 32) | pw.z;
                     const uint32_t np = rec_count(l0);
                     const uint32_t *list = rec_overflow(l0) ? peers.base[rec_owner(l0)] + l1 : nullptr;
-                    uint32_t nj[6] = {0, 0, 0, 0, 0, 0}, ha = 0, hb = 0;
+                    uint32_t nj[ML], ha = 0, hb = 0;
+#pragma unroll
+                    for (int j = 0; j < ML; ++j) nj[j] = 0;
                     for (uint32_t k = 0; k < np; ++k) {
                         const uint32_t e = list ? __ldg(list + k) : (uint32_t)((k < 3u ? l1 : k < 6u ? l2 : l3) >> (kPairBits * (k % 3u))) & kPairMask;
                         const uint32_t c = (e & 0xffffu) - 1u, h = e >> 16;
 #pragma unroll
-                        for (int j = 1; j < 6; ++j) nj[j] += (uint32_t)j < h ? 1u : 0u;
+                        for (int j = 1; j < ML; ++j) nj[j] += (uint32_t)j < h ? 1u : 0u;
                         if (c == lane) ha = h;
                         if (c == lane + 32u) hb = h;
                     }
 #pragma unroll
-                    for (int j = 1; j < 6; ++j) {
+                    for (int j = 1; j < ML; ++j) {
                         const uint32_t nn = nj[j] < 72u ? nj[j] : 0u;
-                        const float vj = __fmul_rn(wj[j], s_inv[nn]);
+                        const float vj = __fmul_rn(s_wl[j], s_inv[nn]);
                         if ((uint32_t)j < ha) {
                             sa = __fadd_rn(sa, vj);
                             if (nn == 1u) atomicAdd(&s_un[j * 64 + lane], 1u); else atomicAdd(&s_fx[j * 64 + lane], (unsigned long long)s_q32[nn]);
@@ -1782,14 +1785,17 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                     const uint32_t c = (ud & 0xffffu) - 1u, h = ud >> 16;                      // h >= 3
                     const bool mine = (c & 31u) == lane;
                     float x = (TWO && c >= 32u) ? sb : sa;
-                    x = __fadd_rn(x, wj[2]);                                                   // alone there: w * (1.f / 1) == w
-                    if (h > 3u) x = __fadd_rn(x, wj[3]);
-                    if (h > 4u) x = __fadd_rn(x, wj[4]);
-                    if (h > 5u) x = __fadd_rn(x, wj[5]);
+                    if (ML <= 6) {
+                        x = __fadd_rn(x, wj[2]);                                               // alone there: w * (1.f / 1) == w
+                        if (h > 3u) x = __fadd_rn(x, wj[3]);
+                        if (h > 4u) x = __fadd_rn(x, wj[4]);
+                        if (h > 5u) x = __fadd_rn(x, wj[5]);
+                    } else {
+                        for (uint32_t j = 2; j < h; ++j) x = __fadd_rn(x, s_wl[j]);            // (h is the same in every lane)
+                    }
                     if (mine) { if (TWO && c >= 32u) sb = x; else sa = x; }
                 } else {
                     const uint4 pw = M.pairs[i];
-                    const float4 v = M.val[i];
                     const uint64_t p3 = ((uint64_t)pw.y << 32) | pw.x;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
@@ -1798,10 +1804,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                         const uint32_t c = (e & 0xffffu) - 1u, h = e >> 16;
                         const bool mine = (c & 31u) == lane;
                         float x = (TWO && c >= 32u) ? sb : sa;
-                        x = __fadd_rn(x, v.x);
-                        if (h > 3u) x = __fadd_rn(x, v.y);
-                        if (h > 4u) x = __fadd_rn(x, v.z);
-                        if (h > 5u) x = __fadd_rn(x, v.w);
+                        for (uint32_t j = 2; j < h && j < (uint32_t)ML; ++j) x = __fadd_rn(x, M.val[i][j - 2]);
                         if (mine) { if (TWO && c >= 32u) sb = x; else sa = x; }
                     }
                 }
@@ -1831,7 +1834,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
         const int j = i / 64, c = i % 64;
         if (c >= T - 1) continue;
         unsigned long long u = s_un[i];
-        if (j >= 2) for (int h = j + 1; h < 8; ++h) u += s_hist[c * 8 + h];     // alone at the levels 2 .. h-1
+        if (j >= 2) for (int h = j + 1; h < 32; ++h) u += s_hist[c * 32 + h];   // alone at the levels 2 .. h-1
         if (u) atomicAdd(cnt_unique + (size_t)j * T + c + 1, u);
         if (s_fx[i]) atomicAdd(cnt_fx + (size_t)j * T + c + 1, s_fx[i]);
     }
@@ -1931,7 +1934,8 @@ void launch_score_sorted(cudaStream_t s, const uint64_t *rec, const uint64_t *re
                          float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, int lanes_hint, uint32_t *err_flag, uint64_t *launches)
 {
     if (!n_reads) return;
-    KASA_REQUIRE(ops_mask_stream(lp), -6, "the presorted scoring kernel needs <= 64 taxa and <= 6 levels");
+    KASA_REQUIRE(lp.n_taxa <= kMaskTaxa, -6, "the presorted scoring kernels need <= 64 taxa");
+    if (lp.num_k > 6) lanes_hint = 0;                  // only the dense organisation takes more than six levels
     auto go = [&](auto kern, int lanes) {
         int per_sm = 1;
         KASA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSortedBlock, 0));
@@ -1960,15 +1964,18 @@ void launch_score_sorted(cudaStream_t s, const uint64_t *rec, const uint64_t *re
     }
     if (lanes_hint == 0 || lanes_hint == 64) {
         // warp per read, lane per taxon, uniform control flow over two-mask records (score_dense_kernel): the default
-        auto god = [&](auto kern) {
+        auto god = [&](auto kern, size_t sm) {
+            KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             int per_sm = 1;
-            KASA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlkWarps * 32, 0));
+            KASA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlkWarps * 32, sm));
             unsigned grid = (unsigned)div_up<uint64_t>(n_reads, kBlkWarps);
             const unsigned resident = (unsigned)(kSMs * (per_sm > 0 ? per_sm : 1));
             if (grid > resident) grid = resident;
-            kern<<<grid, kBlkWarps * 32, 0, s>>>(rec, read_koff, n_reads, lp, peers, scores, cnt_fx, cnt_unique, err_flag);
+            kern<<<grid, kBlkWarps * 32, sm, s>>>(rec, read_koff, n_reads, lp, peers, scores, cnt_fx, cnt_unique, err_flag);
         };
-        if (taxa > 32) god(score_dense_kernel<true>); else god(score_dense_kernel<false>);
+        constexpr size_t sm6 = sizeof(DenseWarpMem<6>) * kBlkWarps, sm26 = sizeof(DenseWarpMem<26>) * kBlkWarps;
+        if (lp.num_k <= 6) { if (taxa > 32) god(score_dense_kernel<true, 6>, sm6); else god(score_dense_kernel<false, 6>, sm6); }
+        else { if (taxa > 32) god(score_dense_kernel<true, 26>, sm26); else god(score_dense_kernel<false, 26>, sm26); }
         ++*launches;
         KASA_CUDA_TRY(cudaGetLastError());
         return;

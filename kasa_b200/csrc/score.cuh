@@ -80,7 +80,7 @@ void launch_accumulate(cudaStream_t s, OpsWorkspace ws, uint32_t r0, uint32_t r1
 void launch_score_sorted(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp, OverflowPeers peers,
                          float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, int lanes_hint, uint32_t *err_flag, uint64_t *launches);
 // which record format that kernel reads: the dense organisation (lanes_hint 0 / 64) wants two-mask records (lookup.cuh), the others mask records
-inline bool score_sorted_two_masks(int lanes_hint) { return lanes_hint == 0 || lanes_hint == 64; }
+inline bool score_sorted_two_masks(int lanes_hint, const LevelParams &lp) { return lanes_hint == 0 || lanes_hint == 64 || lp.num_k > 6; }
 
 // largest number of instances of any read -> *out (device u32)
 void launch_max_instances(cudaStream_t s, const uint64_t *read_koff, uint32_t n_reads, uint32_t *out, uint64_t *launches);

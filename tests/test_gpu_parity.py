@@ -270,6 +270,27 @@ def test_build_brick_overflow_compacts_and_continues():
     ctx.close()
 
 
+@pytest.mark.parametrize("case,K", [("k12", 12), ("k25", 25)])
+def test_build_larger_than_one_brick_spills_and_merges(case, K):
+    """Build.hpp:305-477 (bricks spilled to temporaries, merged at the end): with a brick far smaller than the index the pushes
+    fill, compact and spill several bricks to host memory; kasa_build_finish merges them by prefix range.  Files, frequencies
+    and the index loaded from the merged result equal the single-brick build = the reference's files."""
+    strings = O.fasta_build_strings(G.gz(case, "ref.fa.gz"), G.acc2tax(case), K, False)
+    _, taxids, _ = G.content(case)
+    want = G.index(case)
+    ctx = _ctx(highest_k=K, k_high=K, k_low=7, max_batch_kmers=len(want) // 3)        # at least three bricks
+    for i in range(0, len(strings), 2):
+        part = strings[i:i + 2]
+        ctx.build_push([s for s, _ in part], [t for _, t in part])
+    rec, trie = ctx.build_finish()
+    assert rec.tobytes() == want.tobytes()
+    assert trie.tobytes() == G.trie(case).tobytes()
+    assert np.array_equal(ctx.build_frequency(taxids), G.frequency(case))
+    ctx.index_from_build(taxids)
+    assert ctx.index_size == len(want)
+    ctx.close()
+
+
 def test_build_then_identify_round_trip_large():
     """Property test at a size the oracle cannot reach in seconds: reads cut from the reference without errors
     must hit their own taxon uniquely at k=12 wherever the 12-mer is unique; totals must be consistent."""
