@@ -820,7 +820,7 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
 // that kernel reads.
 static bool scores_straight_from_records(const kasa_ctx *c, uint32_t max_inst, bool want_hits)
 {
-    return c->p.score_mode != KASA_SCORE_EXACT && !want_hits && c->n_taxa <= (uint32_t)kMaskTaxa && max_inst <= (uint32_t)kPresortMax && c->score_sorted &&
+    return c->p.score_mode != KASA_SCORE_EXACT && !want_hits && c->n_taxa <= (uint32_t)kMaskTaxa && max_inst <= (uint32_t)presort_limit(c->wide) && c->score_sorted &&
            !c->sh.on;
 }
 

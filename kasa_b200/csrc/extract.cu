@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(Pa
     const uint64_t out0 = koff[s_begin];
     const uint32_t n_read = (uint32_t)min((uint64_t)0xffffffffu, koff[s_end] - out0);
     if (n_read == 0) return;
+    if (n_read > (uint32_t)kPresortMax && n_read <= (uint32_t)presort_limit(WIDE)) return;   // ordered by a whole CTA: extract_long_kernel
     const bool presort = n_read <= (uint32_t)kPresortMax && n_read <= cap;      // cap >= min(largest read, kPresortMax): see the launcher
     const int K = p.K;
     const uint64_t mask_lo = WIDE ? ~0ull : ((1ull << (5 * K)) - 1);
@@ -292,6 +293,151 @@ __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(Pa
     }
 }
 
+// ---- reads of more than kPresortMax and at most presort_limit() k-mers: ONE CTA PER READ.  The warps extract the read's segments
+// side by side into one shared-memory array; the CTA then orders it like the warp kernel does, with 4096 buckets on the leading
+// twelve key bits and the read's own output region in global memory (L2-resident: <= 192 KB) as the bucket-grouped second copy:
+//   count -> scan -> group into global -> rank inside the bucket (comparing against the grouped copy) into shared memory -> store.
+constexpr int kLongWarps = 8;
+constexpr int kLongBucketBits = 12;
+constexpr int kLongBuckets = 1 << kLongBucketBits;
+
+template <bool WIDE, bool ASCII>
+__global__ void __launch_bounds__(kLongWarps * 32) extract_long_kernel(PackedSeqs seqs, const char *__restrict__ ascii,
+                                                                       const uint64_t *__restrict__ astart, KmerParams p,
+                                                                       const uint64_t *__restrict__ koff, uint64_t *key_lo, uint64_t *key_hi,
+                                                                       uint32_t *__restrict__ inst, const uint8_t *__restrict__ codon,
+                                                                       const uint32_t *__restrict__ read_first, uint32_t n_reads)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(16) uint8_t s_tab[512];
+    __shared__ uint32_t s_scan[kLongWarps];
+    const uint32_t r = blockIdx.x;
+    const uint32_t s_begin = read_first ? read_first[r] : r, s_end = read_first ? read_first[r + 1] : r + 1;
+    const uint64_t out0 = koff[s_begin];
+    const uint64_t n64 = koff[s_end] - out0;
+    constexpr uint32_t cap = (uint32_t)presort_limit(WIDE);
+    if (n64 <= (uint64_t)kPresortMax || n64 > (uint64_t)cap) return;          // the warp kernel's reads
+    const uint32_t m = (uint32_t)n64;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    uint64_t *klo = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *khi = klo + (WIDE ? cap : 0);
+    uint32_t *bcnt = reinterpret_cast<uint32_t *>(khi + cap);                  // [kLongBuckets + 4]
+    uint8_t *code = reinterpret_cast<uint8_t *>(bcnt + kLongBuckets + 4) + (size_t)w * 2 * (kSegR + kAaPad + 8);
+    uint8_t *aa = code + (kSegR + kAaPad + 8);
+    if (tid < 32) reinterpret_cast<uint4 *>(s_tab)[tid] = reinterpret_cast<const uint4 *>(codon)[tid];
+    for (int i = tid; i < kLongBuckets + 4; i += blockDim.x) bcnt[i] = 0;
+    __syncthreads();
+    // ---- the read's k-mers into shared memory, segment g by warp g % kLongWarps (same steps as extract_identify_kernel)
+    const int K = p.K;
+    const uint64_t mask_lo = WIDE ? ~0ull : ((1ull << (5 * K)) - 1);
+    const uint64_t mask_hi = WIDE ? ((1ull << (5 * K - 64)) - 1) : 0ull;
+    const int j0 = (lane / 3) * (3 * kRoll) + (lane % 3);
+    uint32_t roff = 0, g = 0;
+    for (uint32_t s = s_begin; s < s_end; ++s) {
+        const uint32_t L = seqs.seq_len[s];
+        const uint64_t start = ASCII ? astart[s] : seqs.seq_start[s];
+        const uint32_t n = (uint32_t)kmer_count((uint64_t)L + 3u * (K - p.k_low), K);
+        for (int strand = 0; strand < p.strands && n; ++strand) {
+            for (uint32_t p0 = 0; p0 < n; p0 += kSegR, ++g) {
+                const uint32_t cnt = min((uint32_t)kSegR, n - p0);
+                if ((int)(g % kLongWarps) == w) {
+                    const uint32_t naa = cnt + 3 * (K - 1);
+                    for (uint32_t j = lane; j < naa + 2; j += 32) {
+                        const uint32_t pos = p0 + j;
+                        uint32_t c;
+                        if (!ASCII) c = code_at(seqs.bases2, seqs.nmask, start, L, strand, pos);
+                        else if (pos >= L) c = 4u;
+                        else {
+                            const char ch = ascii[start + (strand ? (L - 1 - pos) : pos)];
+                            const bool ok = (ch == 'A') | (ch == 'C') | (ch == 'G') | (ch == 'T') | (ch == 'a') | (ch == 'c') | (ch == 'g') | (ch == 't');
+                            const uint32_t two = (uint32_t)(ch & 14) >> 1;
+                            c = ok ? (strand ? (two ^ 2u) : two) : 5u;
+                        }
+                        code[j] = (uint8_t)c;
+                    }
+                    __syncwarp();
+                    for (uint32_t j = lane; j < naa; j += 32) aa[j] = s_tab[(uint32_t)code[j] << 6 | (uint32_t)code[j + 1] << 3 | code[j + 2]];
+                    __syncwarp();
+                    if (lane < 30 && (uint32_t)j0 < cnt) {
+                        uint64_t lo = 0, hi = 0;
+                        for (int i = 0; i < K; ++i) {
+                            if (WIDE) hi = (hi << 5) | (lo >> 59);
+                            lo = (lo << 5) | aa[j0 + 3 * i];
+                        }
+                        klo[roff + j0] = lo;
+                        if (WIDE) khi[roff + j0] = hi;
+#pragma unroll
+                        for (int t = 1; t < kRoll; ++t) {
+                            const int j = j0 + 3 * t;
+                            if ((uint32_t)j >= cnt) break;
+                            if (WIDE) hi = ((hi << 5) | (lo >> 59)) & mask_hi;
+                            lo = ((lo << 5) | aa[j + 3 * (K - 1)]) & mask_lo;
+                            klo[roff + j] = lo;
+                            if (WIDE) khi[roff + j] = hi;
+                        }
+                    }
+                    __syncwarp();
+                }
+                roff += cnt;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- order: count, scan, group (into the read's output region), rank, store
+    const int bsh = WIDE ? 5 * K - 64 - kLongBucketBits : 5 * K - kLongBucketBits;
+    auto bucket_of = [&](uint64_t lo, uint64_t hi) -> uint32_t { return (uint32_t)((WIDE ? hi : lo) >> bsh) & (kLongBuckets - 1); };
+    for (uint32_t x = tid; x < m; x += blockDim.x) atomicAdd(&bcnt[bucket_of(klo[x], WIDE ? khi[x] : 0ull)], 1u);
+    __syncthreads();
+    {   // exclusive scan of the bucket counts: every thread owns kLongBuckets / 256 consecutive counters
+        constexpr uint32_t per = kLongBuckets / (kLongWarps * 32);
+        uint32_t c[per], sum = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < per; ++i) { c[i] = bcnt[tid * per + i]; sum += c[i]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (lane == 31) s_scan[w] = incl;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int i = 0; i < w; ++i) base += s_scan[i];
+        uint32_t run = base + incl - sum;
+#pragma unroll
+        for (uint32_t i = 0; i < per; ++i) { bcnt[tid * per + i] = run; run += c[i]; }
+    }
+    __syncthreads();
+    // group: bcnt[b] walks from the start of bucket b to its end (= the start of bucket b + 1)
+    for (uint32_t x = tid; x < m; x += blockDim.x) {
+        const uint64_t lo = klo[x], hi = WIDE ? khi[x] : 0ull;
+        const uint32_t pos = atomicAdd(&bcnt[bucket_of(lo, hi)], 1u);
+        key_lo[out0 + pos] = lo;
+        if (WIDE) key_hi[out0 + pos] = hi;
+    }
+    __syncthreads();                                                            // (also makes the CTA's global writes visible to the CTA)
+    for (uint32_t gpos = tid; gpos < m; gpos += blockDim.x) {
+        const uint64_t xl = __ldcg(key_lo + out0 + gpos), xh = WIDE ? __ldcg(key_hi + out0 + gpos) : 0ull;
+        const uint32_t bk = bucket_of(xl, xh);
+        const uint32_t b0 = bk ? bcnt[bk - 1] : 0u, b1 = bcnt[bk];
+        uint32_t less = 0;
+        for (uint32_t y = b0; y < b1; ++y) {
+            const uint64_t ol = __ldcg(key_lo + out0 + y), oh = WIDE ? __ldcg(key_hi + out0 + y) : 0ull;
+            const bool lt = WIDE && oh != xh ? oh < xh : (ol != xl ? ol < xl : y < gpos);       // equal k-mers: any fixed order
+            less += lt ? 1u : 0u;
+        }
+        klo[b0 + less] = xl;
+        if (WIDE) khi[b0 + less] = xh;
+    }
+    __syncthreads();
+    for (uint32_t j = tid; j < m; j += blockDim.x) {
+        const uint64_t o = out0 + j;
+        key_lo[o] = klo[j];
+        if (WIDE) key_hi[o] = khi[j];
+        inst[o] = (uint32_t)o;
+    }
+}
+
 __global__ void build_counts_kernel(const uint32_t *__restrict__ seq_len, uint32_t n, int K, uint64_t *__restrict__ out)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,6 +520,17 @@ static void launch_extract_kernel(Kern kern, cudaStream_t s, bool wide, PackedSe
     kern<<<div_up(n_reads, warps), warps * 32, sm, s>>>(seqs, ascii, astart, p, koff, key_lo, key_hi, inst, codon, read_first, n_reads, cap, (uint32_t)wbytes);
 }
 
+// reads between kPresortMax and presort_limit() k-mers: one CTA each (launched only when the batch has such reads; CTAs of other reads leave at once)
+template <class Kern>
+static void launch_long_kernel(Kern kern, cudaStream_t s, bool wide, PackedSeqs seqs, const char *ascii, const uint64_t *astart, KmerParams p,
+                               const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo, uint64_t *key_hi, uint32_t *inst,
+                               const uint32_t *read_first, uint32_t n_reads)
+{
+    const size_t sm = (size_t)presort_limit(wide) * (wide ? 16 : 8) + (size_t)4 * (kLongBuckets + 4) + (size_t)kLongWarps * 2 * (kSegR + kAaPad + 8);
+    KASA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<n_reads, kLongWarps * 32, sm, s>>>(seqs, ascii, astart, p, koff, key_lo, key_hi, inst, codon, read_first, n_reads);
+}
+
 void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo,
                              uint64_t *key_hi, uint32_t *inst, const uint32_t *read_first, uint32_t n_reads, uint32_t max_inst, uint64_t *launches)
 {
@@ -381,6 +538,11 @@ void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, cons
     if (p.K > 12) launch_extract_kernel(extract_identify_kernel<true, false>, s, true, seqs, nullptr, nullptr, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads, max_inst);
     else launch_extract_kernel(extract_identify_kernel<false, false>, s, false, seqs, nullptr, nullptr, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads, max_inst);
     ++*launches;
+    if (max_inst > (uint32_t)kPresortMax) {
+        if (p.K > 12) launch_long_kernel(extract_long_kernel<true, false>, s, true, seqs, nullptr, nullptr, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads);
+        else launch_long_kernel(extract_long_kernel<false, false>, s, false, seqs, nullptr, nullptr, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads);
+        ++*launches;
+    }
 }
 
 void launch_extract_identify_ascii(cudaStream_t s, const char *ascii, const uint64_t *ascii_start, const uint32_t *seq_len,
@@ -393,6 +555,11 @@ void launch_extract_identify_ascii(cudaStream_t s, const char *ascii, const uint
     if (p.K > 12) launch_extract_kernel(extract_identify_kernel<true, true>, s, true, seqs, ascii, ascii_start, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads, max_inst);
     else launch_extract_kernel(extract_identify_kernel<false, true>, s, false, seqs, ascii, ascii_start, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads, max_inst);
     ++*launches;
+    if (max_inst > (uint32_t)kPresortMax) {
+        if (p.K > 12) launch_long_kernel(extract_long_kernel<true, true>, s, true, seqs, ascii, ascii_start, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads);
+        else launch_long_kernel(extract_long_kernel<false, true>, s, false, seqs, ascii, ascii_start, p, codon, koff, key_lo, key_hi, inst, read_first, n_reads);
+        ++*launches;
+    }
 }
 
 void launch_build_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, int K, uint64_t *woff, uint64_t *launches)

@@ -38,7 +38,10 @@ void launch_kmer_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs
 // them: extract.cu "presorted emission"); longer reads in the reference's emission order (forward strand, then reverse strand, per
 // sequence).  A read = the sequences [read_first[r], read_first[r+1]) (read_first == nullptr: one sequence per read);
 // max_inst = most k-mers of any read of the batch (sizes the shared memory).  key_hi may be nullptr for K <= 12; inst[i] = i.
-constexpr int kPresortMax = 1024;
+constexpr int kPresortMax = 1024;                 // reads ordered by one warp in its shared memory
+// longer reads are ordered by a whole CTA: as many k-mers as 192 KB of shared memory hold (12 kbp reads with --six; 6 kbp for K = 25);
+// still longer ones keep the reference's emission order and are ordered by rank in the scoring stage
+__host__ __device__ constexpr int presort_limit(bool wide) { return wide ? 12288 : 24576; }
 void launch_extract_identify(cudaStream_t s, PackedSeqs seqs, KmerParams p, const uint8_t *codon, const uint64_t *koff, uint64_t *key_lo,
                              uint64_t *key_hi, uint32_t *inst, const uint32_t *read_first, uint32_t n_reads, uint32_t max_inst, uint64_t *launches);
 

@@ -344,10 +344,12 @@ def identify_kmers_ordered(kmers: np.ndarray, read_id: np.ndarray, n_reads: int,
     return IdentifyResult(len(read_id), ca, cu, sc)
 
 
-PRESORT_MAX = 1024     # kasa_b200/csrc/extract.cuh kPresortMax
+def presort_limit(K: int) -> int:
+    """kasa_b200/csrc/extract.cuh presort_limit(): most k-mers of a read that the extraction still emits in ascending order."""
+    return 12288 if K > 12 else 24576
 
 
-def presorted_emission(kmers: np.ndarray, read_id: np.ndarray, presort_max: int = PRESORT_MAX):
+def presorted_emission(kmers: np.ndarray, read_id: np.ndarray, presort_max: int = 24576):
     """The CUDA library's emission order (extract.cu "presorted emission"): the k-mers of a read of at most `presort_max` k-mers in
     ascending order (equal k-mers keep the reference's emission order), longer reads untouched.  read_id is non-decreasing."""
     n = len(read_id)
@@ -364,9 +366,9 @@ def presorted_emission(kmers: np.ndarray, read_id: np.ndarray, presort_max: int 
 def identify_reads_ordered(reads: list[list[bytes]], index: np.ndarray, K: int, k_high: int, k_low: int, six: bool,
                            taxid_of_idx: np.ndarray, table: np.ndarray | None = None, sort_bits: int = 32) -> IdentifyResult:
     """KASA_SCORE_ORDERED: the library emits the k-mers of ordinary reads presorted and sorts the batch stably on the leading
-    `sort_bits` key bits, so a read's scores are summed in ascending k-mer order (reads longer than PRESORT_MAX k-mers: ascending
+    `sort_bits` key bits, so a read's scores are summed in ascending k-mer order (reads of more than presort_limit(K) k-mers: ascending
     on the leading sort_bits, then emission order)."""
-    k, ids = presorted_emission(*read_kmers(reads, K, k_low, six, table))
+    k, ids = presorted_emission(*read_kmers(reads, K, k_low, six, table), presort_limit(K))
     return identify_kmers_ordered(k, ids, len(reads), index, K, k_high, k_low, taxid_of_idx, sort_bits)
 
 

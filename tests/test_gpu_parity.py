@@ -45,8 +45,10 @@ def _k12_reads():
 @pytest.mark.parametrize("frames,k_low", [(6, 7), (3, 7), (6, 12), (3, 1)])
 def test_extract_matches_oracle_k12(frames, k_low):
     rng = np.random.default_rng(11)
-    long_read = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=2500))      # > 1024 k-mers: not presorted
-    reads = _k12_reads() + [b"", b"ACG", b"acgtnACGTN" * 30, b"N" * 40 + b"ACGT" * 20, b"A" * 250, long_read, b"ACGTTGCA" * 60, long_read[:530]]
+    long_read = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=2500))      # > 1024 k-mers: presorted by a whole CTA
+    huge_read = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=15000))     # > 24576 k-mers with --six: not presorted
+    reads = _k12_reads() + [b"", b"ACG", b"acgtnACGTN" * 30, b"N" * 40 + b"ACGT" * 20, b"A" * 250, long_read, b"ACGTTGCA" * 60, long_read[:530],
+                            huge_read, b"ACG" * 900]
     ctx = _ctx(frames=frames, k_low=k_low, k_high=12)
     lo, hi, rid = ctx.dbg_extract(reads)
     want_k, want_id = O.presorted_emission(*O.read_kmers([[r] for r in reads], 12, k_low, frames == 6))
