@@ -226,7 +226,8 @@ typedef struct {
 typedef struct {
     uint64_t n_kmers;              /* k-mers of the origin's batch                                              */
     int32_t  cur;                  /* which half of the ping-pong holds the sorted run                          */
-    int32_t  reserved;
+    int32_t  reserved;             /* set by kasa_shard_sort, read by the owners in kasa_shard_lookup: bit 0 = the origin scores this batch
+                                      straight from two-mask match records; pass the struct on unchanged                        */
     uint64_t begin[KASA_MAX_SHARDS + 1];   /* sorted positions: [begin[r], begin[r+1]) belongs to shard r       */
 } kasa_shard_runs;
 

@@ -820,8 +820,10 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
 // that kernel reads.
 static bool scores_straight_from_records(const kasa_ctx *c, uint32_t max_inst, bool want_hits)
 {
+    // (prefix-sharded: the owners of the index ranges write the records, so the choice may only depend on what every rank knows when the
+    // batch is sorted — sparse results, chosen per batch, then keep the op-stream path)
     return c->p.score_mode != KASA_SCORE_EXACT && !want_hits && c->n_taxa <= (uint32_t)kMaskTaxa && max_inst <= (uint32_t)presort_limit(c->wide) && c->score_sorted &&
-           !c->sh.on;
+           (!c->sh.on || c->p.max_batch_hits == 0);
 }
 
 // Scoring stage (score.cuh) after the match records of the batch are in c->d_rec: op streams in the reference's summation
@@ -1357,6 +1359,8 @@ int kasa_shard_sort(kasa_ctx *c, const kasa_read_batch *in, kasa_shard_runs *min
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[2], c->stream));
     std::memset(mine, 0, sizeof(*mine));
     mine->n_kmers = n;
+    // what the owners of the index ranges need to know about this batch: bit 0 = its scores come straight from two-mask records
+    mine->reserved = scores_straight_from_records(c, max_inst, false) && score_sorted_two_masks(c->score_lanes, level_params(c)) ? 1 : 0;
     if (n) {
         const int cur = radix_sort(c->stream, c->sb, 0, n, plan, c->sort_ws, c->d_err, &c->launches, sl.sev[3]);
         mine->cur = cur;
@@ -1413,7 +1417,7 @@ int kasa_shard_lookup(kasa_ctx *c, const kasa_shard_runs *all)
         const uint32_t tq = lookup_tile_queries(m, c->idx_n);
         launch_partition(c->stream, q_lo, q_hi, m, idx, lp, c->d_part, tq, sorted_from, &c->launches);
         // the rank of a k-mer is its position in the ORIGIN's sorted run; overflow lists stay in this shard's array (owner = me)
-        launch_lookup(c->stream, q_lo, q_hi, inst, m, b0, idx, lp, c->d_part, rec, tq, c->ovf, (uint32_t)me, c->d_err, &c->launches);
+        launch_lookup(c->stream, q_lo, q_hi, inst, m, b0, idx, lp, c->d_part, rec, tq, c->ovf, (uint32_t)me, c->d_err, &c->launches, (r.reserved & 1) != 0);
     }
     KASA_CUDA_TRY(cudaEventRecord(sl.sev[5], c->stream));
     KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));        // every record this shard owes is in its origin's HBM

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(Pa
 // side by side into one shared-memory array; the CTA then orders it like the warp kernel does, with 4096 buckets on the leading
 // twelve key bits and the read's own output region in global memory (L2-resident: <= 192 KB) as the bucket-grouped second copy:
 //   count -> scan -> group into global -> rank inside the bucket (comparing against the grouped copy) into shared memory -> store.
-constexpr int kLongWarps = 8;
+constexpr int kLongWarps = 16;                 // one CTA per SM (192 KB of keys): as many warps as the rest of shared memory allows
 constexpr int kLongBucketBits = 12;
 constexpr int kLongBuckets = 1 << kLongBucketBits;
 
