@@ -725,7 +725,7 @@ void launch_lookup(cudaStream_t s, const uint64_t *q_lo, const uint64_t *q_hi, c
         kern<<<tiles, kLookupBlock, sm, s>>>(q_lo, q_hi, inst, n, rank_base, idx, lp, part, rec, tq, ovf, owner, err_flag, pf_dist);
     };
     const bool mask = lp.n_taxa <= kMaskTaxa;
-    KASA_REQUIRE(!mask || idx.gmask, -4, "the index of a small content file has no group masks (launch_group_masks)");
+    KASA_REQUIRE(!mask || idx.gmask || idx.n == 0, -4, "the index of a small content file has no group masks (launch_group_masks)");
     KASA_REQUIRE(!two_masks || mask, -6, "two-mask records need a content file of <= 64 taxa");
     if (idx.key_hi) {
         if (mask && two_masks) go(lookup_kernel<true, true, true>, sizeof(SpanStage<true, true>));
