@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <chrono>
 #include <iostream>
 
@@ -304,8 +305,7 @@ int run_identify(const Args &a)
         kasa_ctx *ctx = nullptr;
     };
     std::vector<HostBatch> hb(2 * (size_t)G);
-    std::string o;
-    std::vector<Hit> hits(T);
+    const size_t fmt_threads = std::max(1u, std::thread::hardware_concurrency());      // the reference formats on its worker threads too (Compare.hpp:3391)
     auto submit = [&](HostBatch &h, size_t b, kasa_ctx *ctx) {
         h.ctx = ctx;
         const size_t e = std::min(reads.size(), b + per_batch);
@@ -334,8 +334,8 @@ int run_identify(const Args &a)
         const Pinned<float> &scores = h.scores;
         n_kmers_total += h.res.n_kmers;
         if (a.rtt.empty()) { read_no += e - b; return; }
-        // ---- per-read output (Compare.hpp:1485-1890)
-        for (size_t r = b; r < e; ++r, ++read_no) {
+        // ---- per-read output (Compare.hpp:1485-1890): formatted by all host threads, chunk by chunk, written in input order
+        auto format_read = [&](size_t r, uint64_t rn, std::string &o, std::vector<Hit> &hits) {
             std::string name = reads[r].name + " ";
             uint32_t length = (uint32_t)reads[r].seq.size() + reads[r].lines;
             if (paired) { name += mates[r].name + " "; length += (uint32_t)mates[r].seq.size() + mates[r].lines; }
@@ -347,23 +347,21 @@ int run_identify(const Args &a)
                     const double rel = row[t] / (1.0 + std::log2((double)freq_high[t] * double(length - K * 3 + 1)));
                     if (rel >= a.threshold) hits[nh++] = Hit{t, row[t], rel};
                 }
-            o.clear();
             if (nh == 0) {
-                if (a.format == "tsv") { o += std::to_string(read_no) + "\t" + name + "\t-\t-\t-\t-\n"; }
+                if (a.format == "tsv") { o += std::to_string(rn) + "\t" + name + "\t-\t-\t-\t-\n"; }
                 else if (a.format == "json") {
-                    o += read_no == 0 ? "{\n" : ",\n{\n";
-                    o += "\t\"Read number\": " + std::to_string(read_no) + ",\n\t\"Specifier from input file\": \"" + name + "\",\n\t\"Length\": " +
+                    o += rn == 0 ? "{\n" : ",\n{\n";
+                    o += "\t\"Read number\": " + std::to_string(rn) + ",\n\t\"Specifier from input file\": \"" + name + "\",\n\t\"Length\": " +
                          std::to_string(length) + ",\n\t\"Top hits\": [\n\t],\n\t\"Further hits\": [\n\t]\n}";
                 } else if (a.format == "jsonl") {
-                    o += "{ \"Read number\": " + std::to_string(read_no) + ", \"Specifier from input file\": \"" + name + "\", \"Length\": " +
+                    o += "{ \"Read number\": " + std::to_string(rn) + ", \"Specifier from input file\": \"" + name + "\", \"Length\": " +
                          std::to_string(length) + ", \"Top hits\": [], \"Further hits\": [] }\n";
                 } else {
                     o += "U\t" + name + "\t0\t";
                     o += (char)length;                        // the reference appends the length as a raw char here (Compare.hpp:1568)
                     o += "\tA:00\n";
                 }
-                out << o;
-                continue;
+                return;
             }
             std::stable_sort(hits.begin(), hits.begin() + nh, [](const Hit &x, const Hit &y) { return x.rel > y.rel; });
             float maxv = 0.f;
@@ -391,22 +389,22 @@ int run_identify(const Args &a)
                 }
             };
             if (a.format == "jsonl") {
-                o += "{ \"Read number\": " + std::to_string(read_no) + ", \"Specifier from input file\": \"" + name + "\", \"Length\": " +
+                o += "{ \"Read number\": " + std::to_string(rn) + ", \"Specifier from input file\": \"" + name + "\", \"Length\": " +
                      std::to_string(length) + ", \"Top hits\": [";
                 for (size_t i = 0; i < top; ++i) { if (i) o += ","; o += hit_json(hits[i], true); }
                 o += "], \"Further hits\": [";
                 further([&](const Hit &h, bool firstOne) { if (!firstOne) o += ", "; o += hit_json(h, true); });
                 o += "] }\n";
             } else if (a.format == "json") {
-                o += read_no == 0 ? "{\n" : ",\n{\n";
-                o += "\t\"Read number\": " + std::to_string(read_no) + ",\n\t\"Specifier from input file\": \"" + name + "\",\n\t\"Length\": " +
+                o += rn == 0 ? "{\n" : ",\n{\n";
+                o += "\t\"Read number\": " + std::to_string(rn) + ",\n\t\"Specifier from input file\": \"" + name + "\",\n\t\"Length\": " +
                      std::to_string(length) + ",\n\t\"Top hits\": [\n";
                 for (size_t i = 0; i < top; ++i) { if (i) o += ",\n"; o += hit_json(hits[i], false); }
                 o += "\n\t],\n\t\"Further hits\": [\n";
                 further([&](const Hit &h, bool firstOne) { if (!firstOne) o += ",\n"; o += hit_json(h, false); });
                 o += "\n\t]\n}";
             } else if (a.format == "tsv") {
-                std::string s1 = std::to_string(read_no) + "\t" + name + "\t", s2, s3, s4;
+                std::string s1 = std::to_string(rn) + "\t" + name + "\t", s2, s3, s4;
                 float before = 0;
                 for (size_t j = 0, i = 0; i < nh && (int64_t)j < a.beasts; ++i) {
                     s1 += std::to_string(content.taxids[hits[i].idx]) + ";";
@@ -423,8 +421,24 @@ int run_identify(const Args &a)
                 further([&](const Hit &h, bool) { o += std::to_string(content.taxids[h.idx]) + ":"; append_double((double)h.score, o); o += " "; });
                 o += "\n";
             }
-            out << o;
+        };
+        const size_t n_batch = e - b;
+        const size_t n_thr = std::max<size_t>(1, std::min<size_t>(fmt_threads, n_batch / 256 + 1));
+        std::vector<std::string> pieces(n_thr);
+        auto work = [&](size_t t) {
+            std::vector<Hit> hits(T);
+            const size_t r0 = b + n_batch * t / n_thr, r1 = b + n_batch * (t + 1) / n_thr;
+            pieces[t].reserve((r1 - r0) * 256);
+            for (size_t r = r0; r < r1; ++r) format_read(r, read_no + (r - b), pieces[t], hits);
+        };
+        if (n_thr == 1) work(0);
+        else {
+            std::vector<std::thread> pool;
+            for (size_t t = 0; t < n_thr; ++t) pool.emplace_back(work, t);
+            for (auto &th : pool) th.join();
         }
+        for (const std::string &piece : pieces) out << piece;
+        read_no += n_batch;
     };
     // ring of 2 G host batches: batch nb runs on GPU nb % G; before its slot is reused, the batch that held it (2 G batches
     // ago, the oldest in flight) is emitted
