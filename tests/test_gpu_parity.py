@@ -88,6 +88,21 @@ def test_custom_codon_table_is_a_parameter():
     plain.close()
 
 
+def test_host_helpers_page_locked_buffers_and_builtin_codon_table():
+    """kasa_host_alloc / kasa_host_free (page-locked batch buffers for kasa_identify_submit) and kasa_builtin_codon_table (the table
+    a host patches for `-a`): the built-in table equals the oracle's restatement of kASA.hpp:621-667."""
+    import ctypes as C
+    lib = capi.load_library()
+    p = C.c_void_p()
+    assert lib.kasa_host_alloc(C.byref(p), C.c_uint64(1 << 20)) == 0 and p.value
+    C.memset(p, 0x5a, 1 << 20)
+    assert lib.kasa_host_free(p) == 0
+    assert lib.kasa_host_alloc(C.byref(p), C.c_uint64(0)) == 0 and not p.value
+    t = (C.c_uint8 * 512)()
+    assert lib.kasa_builtin_codon_table(t) == 0
+    assert np.array_equal(np.frombuffer(t, dtype=np.uint8), O.default_codon_table())
+
+
 # ----------------------------------------------------------------------------------------- radix sort
 @pytest.mark.parametrize("n", [0, 1, 31, 4095, 4096, 4097, 100_003, 1_500_000])
 def test_radix_sort_pairs_matches_stable_sort(n):
