@@ -77,7 +77,8 @@ class CShardRuns(C.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libkasa_b200.so")
+    # KASA_B200_LIB: another build of the same library (kernel variants compared by the tools; never a fallback)
+    return os.environ.get("KASA_B200_LIB") or os.path.join(_HERE, "libkasa_b200.so")
 
 
 _LIB = None

@@ -19,7 +19,7 @@ void upload_codon_table(const uint8_t table512[512], uint8_t *d_table, cudaStrea
 
 namespace {
 
-constexpr int kExtractWarps = 4;      // shared memory per warp (presort buffers) sets the occupancy: small CTAs waste less of it
+constexpr int kExtractWarps = 4;      // shared memory per warp (presort buffers) sets the occupancy: small CTAs waste less of it (8 warps: 23.9 vs 21.2 ms)
 constexpr int kSeg = 256;              // output positions per shared-memory segment
 constexpr int kAaPad = 3 * 24 + 8;     // 3*(K-1) extra letters for K <= 25
 

@@ -1614,6 +1614,8 @@ struct DenseWarpMem {
 };
 
 // ML = 6: the default k = 12..7 (six levels, chains unrolled); ML = 26: up to 26 levels (k = 25..7 and every other range kASA allows)
+// (measured: 64 registers / 4 CTAs per SM 93 ms, 85 registers / 2 CTAs 93 ms, the compiler's own 74 registers / 3 CTAs 77 ms;
+//  4 instead of 8 warps per CTA 97 ms)
 template <bool TWO, int ML>
 __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint64_t *__restrict__ rec, const uint64_t *__restrict__ read_koff, uint32_t n_reads,
                                                                       LevelParams lp, OverflowPeers peers, float *__restrict__ scores,
@@ -1732,7 +1734,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
             __syncwarp();
             // ---- main, lane = taxon: the block's k-mers in order (Compare.hpp:530 for level k_low, then the levels above)
             const uint32_t nblk = min(32u, ni - b0);
-#pragma unroll 1
+#pragma unroll 1                                           // (unrolled by 4 the loop thrashed the instruction cache: stall no_instruction 2.6; by 2: no gain)
             for (uint32_t i = 0; i < nblk; ++i) {
                 const uint4 a = M.a[i];
                 const float v0 = __uint_as_float(a.z);
