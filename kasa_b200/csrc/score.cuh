@@ -3,7 +3,11 @@
 //   vCount_all += hits / |taxa_k|, vCount_unique += hits when |taxa_k| == 1; flush order Compare.hpp:917-955, 1032-1041.
 //
 // The reference's per-read score is a float32 running sum, so its value depends on the order of the additions
-// (SURVEY.md §3.1 "Floating-point order").  Two stages reproduce it:
+// (SURVEY.md §3.1 "Floating-point order").
+// PRESORTED BATCHES (the common case: extract.cu emits every read of up to presort_limit() k-mers in ascending k-mer order, so its
+// match records already lie in summation order) of content files with <= 64 taxa are scored by ONE kernel straight from the
+// records: launch_score_sorted -> score_dense_kernel (warp per read, lane per taxon, uniform control flow; two-mask records).
+// Everything else — longer reads, more than 64 taxa, sparse results, KASA_SCORE_EXACT — goes through two stages:
 //   A  order_ops_kernel   warp per read: the read's match records are ordered by their rank in the batch's sorted k-mer
 //                         order (KASA_SCORE_ORDERED: k-mer ascending, k ascending — the reference's order whenever its
 //                         level-by-level flushes follow the k-mer order) or by the reference's flush positions
@@ -74,9 +78,11 @@ inline bool scores_counted_by_order_ops(const LevelParams &lp, bool sparse_hits)
 void launch_accumulate(cudaStream_t s, OpsWorkspace ws, uint32_t r0, uint32_t r1, LevelParams lp, bool exact_stream, float *scores, HitsOut hits,
                        unsigned long long *cnt_fx, unsigned long long *cnt_unique, uint32_t *err_flag, uint64_t *launches);
 
-// Presorted batches (every read has <= kPresortMax k-mers, extract.cuh) of a content file with <= 64 taxa and <= 6 levels
-// (ops_mask_stream): scores (dense [reads][n_taxa] or nullptr = profile only) and counts straight from the match records, which
-// lie in summation order already; replaces launch_order_ops + launch_accumulate.  lanes_hint: 0 = default threads per read.
+// Presorted batches (every read has <= presort_limit() k-mers, extract.cuh) of a content file with <= 64 taxa: scores (dense
+// [reads][n_taxa] or nullptr = profile only) and counts straight from the match records, which lie in summation order already;
+// replaces launch_order_ops + launch_accumulate.  lanes_hint (KASA_TUNE_SCORE_LANES): 0 / 64 = score_dense_kernel (the default; any
+// number of levels), 32 = score_blocks_kernel, 100 = score_items_kernel, 1 / 2 / 4 = score_sorted_kernel (these three: <= 6 levels,
+// mask records; kept as the measured alternatives of DESIGN.md §4).  err_flag |= 512: a record is not in the format the kernel reads.
 void launch_score_sorted(cudaStream_t s, const uint64_t *rec, const uint64_t *read_koff, uint32_t n_reads, LevelParams lp, OverflowPeers peers,
                          float *scores, unsigned long long *cnt_fx, unsigned long long *cnt_unique, int lanes_hint, uint32_t *err_flag, uint64_t *launches);
 // which record format that kernel reads: the dense organisation (lanes_hint 0 / 64) wants two-mask records (lookup.cuh), the others mask records
