@@ -368,7 +368,7 @@ uint64_t host_total_bases(const uint64_t *seq_start, const uint32_t *seq_len, ui
 
 // sum of kMerCount over host-resident sequences (Read.hpp:36-57 with the marker of Read.hpp:1068-1078): what
 // kmer_counts_kernel + scan produce on the device, so that a host batch needs no device round trip before its launches
-uint64_t host_total_kmers(const uint32_t *seq_len, uint32_t n, int K, int k_low, int strands, const uint32_t *read_first_seq,
+uint64_t host_total_kmers(const uint32_t *seq_len, uint32_t n, int K, int k_low, int strands, int one, const uint32_t *read_first_seq,
                            uint32_t n_reads, uint32_t *max_per_read)
 {
     uint64_t total = 0, best = 0, cur = 0;
@@ -376,7 +376,7 @@ uint64_t host_total_kmers(const uint32_t *seq_len, uint32_t n, int K, int k_low,
     for (uint32_t i = 0; i < n; ++i) {
         if (read_first_seq) { while (r < n_reads && read_first_seq[r + 1] <= i) { ++r; cur = 0; } } else cur = 0;
         const uint64_t len = (uint64_t)seq_len[i] + 3u * (K - k_low);
-        const uint64_t k = (len > (uint64_t)(3 * K + 1) ? len - 3 * K + 1 : 0) * strands;
+        const uint64_t k = kmer_count(len, K, one) * strands;
         total += k;
         cur += k;
         best = std::max(best, cur);
@@ -553,7 +553,7 @@ int kasa_ctx_create(const kasa_params *p, kasa_ctx **out)
         KASA_REQUIRE(p->highest_k == 12 || p->highest_k == 25, KASA_ERR_ARG, "highest_k must be 12 or 25");
         KASA_REQUIRE(p->k_low >= 1 && p->k_low <= p->k_high && p->k_high <= p->highest_k, KASA_ERR_ARG,
                      "need 1 <= k_low <= k_high <= highest_k");
-        KASA_REQUIRE(p->frames == 3 || p->frames == 6, KASA_ERR_ARG, "frames must be 3 or 6 (--one is not supported)");
+        KASA_REQUIRE(p->frames == 1 || p->frames == 3 || p->frames == 6, KASA_ERR_ARG, "frames must be 1 (--one), 3 or 6 (--six)");
         KASA_REQUIRE(p->score_mode >= KASA_SCORE_NONE && p->score_mode <= KASA_SCORE_EXACT, KASA_ERR_ARG, "unknown score_mode");
         KASA_REQUIRE(p->max_batch_kmers > 0 && p->max_batch_kmers < (1ull << 32) - 2 * kSortTile, KASA_ERR_ARG,
                      "max_batch_kmers must be in (0, 2^32)");
@@ -789,14 +789,14 @@ static uint64_t extract_batch(kasa_ctx *c, const kasa_read_batch *in, kasa_ctx::
         }
         ps.seq_start = seq_start;
     }
-    KmerParams kp{c->K, c->p.k_low, c->p.frames == 6 ? 2 : 1};
+    KmerParams kp{c->K, c->p.k_low, c->p.frames == 6 ? 2 : 1, c->p.frames == 1 ? 1 : 0};
     launch_kmer_counts(c->stream, seq_len, ns, kp, c->d_koff, &c->launches);
     exclusive_scan_u64(c->stream, c->d_koff, ns, c->d_scan_tmp, &c->launches);
     // host batches: the total is known without asking the device, so submit returns without a stream synchronisation
     uint64_t n = 0;
     uint32_t mi = 0;
     if (in->location == KASA_MEM_HOST) {
-        n = host_total_kmers(in->seq_len, ns, kp.K, kp.k_low, kp.strands, in->read_first_seq, in->n_reads, &mi);
+        n = host_total_kmers(in->seq_len, ns, kp.K, kp.k_low, kp.strands, kp.one, in->read_first_seq, in->n_reads, &mi);
     } else {
         launch_read_offsets(c->stream, c->d_koff, *read_first, in->n_reads, c->d_read_koff, &c->launches);
         launch_max_instances(c->stream, c->d_read_koff, in->n_reads, c->d_max_inst, &c->launches);

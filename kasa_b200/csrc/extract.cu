@@ -63,15 +63,11 @@ __global__ void __launch_bounds__(256) pack_ascii_kernel(const char *__restrict_
     }
 }
 
-__host__ __device__ __forceinline__ uint64_t kmer_count(uint64_t len, int K)
-{
-    return len > (uint64_t)(3 * K + 1) ? len - 3 * K + 1 : 0;   // Read.hpp:50-52
-}
 
 __global__ void kmer_counts_kernel(const uint32_t *__restrict__ seq_len, uint32_t n, KmerParams p, uint64_t *__restrict__ out)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (uint64_t)p.strands * kmer_count((uint64_t)seq_len[i] + 3u * (p.K - p.k_low), p.K);
+    if (i < n) out[i] = (uint64_t)p.strands * kmer_count((uint64_t)seq_len[i] + 3u * (p.K - p.k_low), p.K, p.one);
 }
 
 // 3-bit base code of the prepared string (forward: read + marker; reverse: revcomp(read) + marker)
@@ -157,11 +153,13 @@ __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(Pa
     for (uint32_t s = s_begin; s < s_end; ++s) {
         const uint32_t L = seqs.seq_len[s];
         const uint64_t start = ASCII ? astart[s] : seqs.seq_start[s];
-        const uint32_t n = (uint32_t)kmer_count((uint64_t)L + 3u * (K - p.k_low), K);
+        const uint32_t n = (uint32_t)kmer_count((uint64_t)L + 3u * (K - p.k_low), K, p.one);
         if (n == 0) continue;
+        const uint32_t npos = p.one ? 3u * n : n;                 // base offsets walked: --one keeps every third of them (frame 0)
         for (int strand = 0; strand < p.strands; ++strand) {
-            for (uint32_t p0 = 0; p0 < n; p0 += kSegR) {
-                const uint32_t cnt = min((uint32_t)kSegR, n - p0);
+            for (uint32_t p0 = 0; p0 < npos; p0 += kSegR) {
+                const uint32_t cnt = min((uint32_t)kSegR, npos - p0);
+                const uint32_t ocnt = p.one ? cnt / 3u : cnt;      // k-mers of this segment (kSegR and npos are multiples of three)
                 const uint32_t naa = cnt + 3 * (K - 1);
                 for (uint32_t j = lane; j < naa + 2; j += 32) {
                     const uint32_t pos = p0 + j;
@@ -182,28 +180,30 @@ __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(Pa
                 __syncwarp();
                 // presorted reads collect all their k-mers; the others pass segment by segment through the first kSegR slots
                 uint64_t *dlo = presort ? klo + roff : klo, *dhi = presort ? khi + roff : khi;
-                if (lane < 30 && (uint32_t)j0 < cnt) {
+                if (lane < 30 && (uint32_t)j0 < cnt && (!p.one || lane % 3 == 0)) {
                     uint64_t lo = 0, hi = 0;
                     for (int i = 0; i < K; ++i) {
                         if (WIDE) hi = (hi << 5) | (lo >> 59);
                         lo = (lo << 5) | aa[j0 + 3 * i];
                     }
-                    dlo[j0] = lo;
-                    if (WIDE) dhi[j0] = hi;
+                    const int d0 = p.one ? j0 / 3 : j0;
+                    dlo[d0] = lo;
+                    if (WIDE) dhi[d0] = hi;
 #pragma unroll
                     for (int t = 1; t < kRoll; ++t) {
                         const int j = j0 + 3 * t;
                         if ((uint32_t)j >= cnt) break;
                         if (WIDE) hi = ((hi << 5) | (lo >> 59)) & mask_hi;
                         lo = ((lo << 5) | aa[j + 3 * (K - 1)]) & mask_lo;
-                        dlo[j] = lo;
-                        if (WIDE) dhi[j] = hi;
+                        const int d = p.one ? j / 3 : j;
+                        dlo[d] = lo;
+                        if (WIDE) dhi[d] = hi;
                     }
                 }
                 __syncwarp();
                 if (!presort) {
                     const uint64_t obase = out0 + roff;
-                    for (uint32_t j = lane; j < cnt; j += 32) {
+                    for (uint32_t j = lane; j < ocnt; j += 32) {
                         const uint64_t o = obase + j;
                         key_lo[o] = klo[j];
                         if (WIDE) key_hi[o] = khi[j];
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kExtractWarps * 32) extract_identify_kernel(Pa
                     }
                     __syncwarp();
                 }
-                roff += cnt;
+                roff += ocnt;
             }
         }
     }
@@ -336,10 +336,12 @@ __global__ void __launch_bounds__(kLongWarps * 32) extract_long_kernel(PackedSeq
     for (uint32_t s = s_begin; s < s_end; ++s) {
         const uint32_t L = seqs.seq_len[s];
         const uint64_t start = ASCII ? astart[s] : seqs.seq_start[s];
-        const uint32_t n = (uint32_t)kmer_count((uint64_t)L + 3u * (K - p.k_low), K);
+        const uint32_t n = (uint32_t)kmer_count((uint64_t)L + 3u * (K - p.k_low), K, p.one);
+        const uint32_t npos = p.one ? 3u * n : n;
         for (int strand = 0; strand < p.strands && n; ++strand) {
-            for (uint32_t p0 = 0; p0 < n; p0 += kSegR, ++g) {
-                const uint32_t cnt = min((uint32_t)kSegR, n - p0);
+            for (uint32_t p0 = 0; p0 < npos; p0 += kSegR, ++g) {
+                const uint32_t cnt = min((uint32_t)kSegR, npos - p0);
+                const uint32_t ocnt = p.one ? cnt / 3u : cnt;
                 if ((int)(g % kLongWarps) == w) {
                     const uint32_t naa = cnt + 3 * (K - 1);
                     for (uint32_t j = lane; j < naa + 2; j += 32) {
@@ -358,27 +360,29 @@ __global__ void __launch_bounds__(kLongWarps * 32) extract_long_kernel(PackedSeq
                     __syncwarp();
                     for (uint32_t j = lane; j < naa; j += 32) aa[j] = s_tab[(uint32_t)code[j] << 6 | (uint32_t)code[j + 1] << 3 | code[j + 2]];
                     __syncwarp();
-                    if (lane < 30 && (uint32_t)j0 < cnt) {
+                    if (lane < 30 && (uint32_t)j0 < cnt && (!p.one || lane % 3 == 0)) {
                         uint64_t lo = 0, hi = 0;
                         for (int i = 0; i < K; ++i) {
                             if (WIDE) hi = (hi << 5) | (lo >> 59);
                             lo = (lo << 5) | aa[j0 + 3 * i];
                         }
-                        klo[roff + j0] = lo;
-                        if (WIDE) khi[roff + j0] = hi;
+                        const int d0 = p.one ? j0 / 3 : j0;
+                        klo[roff + d0] = lo;
+                        if (WIDE) khi[roff + d0] = hi;
 #pragma unroll
                         for (int t = 1; t < kRoll; ++t) {
                             const int j = j0 + 3 * t;
                             if ((uint32_t)j >= cnt) break;
                             if (WIDE) hi = ((hi << 5) | (lo >> 59)) & mask_hi;
                             lo = ((lo << 5) | aa[j + 3 * (K - 1)]) & mask_lo;
-                            klo[roff + j] = lo;
-                            if (WIDE) khi[roff + j] = hi;
+                            const int d = p.one ? j / 3 : j;
+                            klo[roff + d] = lo;
+                            if (WIDE) khi[roff + d] = hi;
                         }
                     }
                     __syncwarp();
                 }
-                roff += cnt;
+                roff += ocnt;
             }
         }
     }

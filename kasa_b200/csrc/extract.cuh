@@ -20,8 +20,16 @@ struct PackedSeqs {
 struct KmerParams {
     int K;          // highest_k: 12 or 25
     int k_low;      // marker = 3*(K - k_low) 'X' (Read.hpp:1068-1078)
-    int strands;    // 1 (three forward frames) or 2 (--six)
+    int strands;    // 1 (forward frames) or 2 (--six)
+    int one;        // 1: --one, only the first reading frame (Read.hpp:223-260): k-mers at every third base of the forward strand
 };
+
+// k-mers of one strand of a prepared string of `len` letters (read + marker): Read.hpp:36-57 calculatekMerCount
+__host__ __device__ __forceinline__ uint64_t kmer_count(uint64_t len, int K, int one)
+{
+    if (one) { const uint64_t t = len / 3; return t > (uint64_t)(K + 1) ? t - K + 1 : 0; }
+    return len > (uint64_t)(3 * K + 1) ? len - 3 * K + 1 : 0;
+}
 
 // 5-bit letter codes of a 512-entry codon table -> d_table (512 bytes of device memory owned by the context)
 void upload_codon_table(const uint8_t table512[512], uint8_t *d_table, cudaStream_t s);

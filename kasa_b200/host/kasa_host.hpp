@@ -293,7 +293,8 @@ inline float best_score(uint32_t length, int k_high, int k_low, int frames)
     float best = 0.f;
     for (int k = k_low; k <= k_high; ++k) {
         const float w = (float)(k * k) / 625.f;
-        if (frames == 6) best += 2 * ((size_t)length - k * 3 + 1) * w;
+        if (frames == 1) best += ((size_t)length / 3 - k + 1) * w;          // --one (Compare.hpp:1456-1460)
+        else if (frames == 6) best += 2 * ((size_t)length - k * 3 + 1) * w;
         else best += ((size_t)length - k * 3 + 1) * w;
     }
     return best;

@@ -49,7 +49,7 @@ struct Pinned {
 struct Args {
     std::string mode, content, index, input, in1, in2, profile, rtt, tmp, alphabet_file, alphabet_id;
     int k_high = 12, k_low = 7, highest_k = 12, beasts = 3, device = 0, gpus = 1;
-    bool six = false, verbose = false, exact = false;
+    bool six = false, one = false, verbose = false, exact = false;
     float threshold = 0.f;
     std::string format = "json";
     uint32_t batch_reads = 1u << 20;
@@ -58,7 +58,7 @@ struct Args {
 [[noreturn]] void usage()
 {
     std::cout << "kasa_b200 <build|identify> -c <content> -d <index> [-i <input> | -1 <fq> -2 <fq>] [-p <profile.csv>] [-q <per-read out>]\n"
-                 "          [-k <high> <low>] [--kH <12|25>] [--six] [--json|--jsonl|--tsv|--kraken] [-b <n>] [--threshold <f>] [-v]\n"
+                 "          [-k <high> <low>] [--kH <12|25>] [--six | --one] [--json|--jsonl|--tsv|--kraken] [-b <n>] [--threshold <f>] [-v]\n"
                  "          [-a <gc.prt> <id>]\n"
                  "          [--exact-scores] [--device <n>] [--gpus <n>] [--batch-reads <n>]   (-m -n -t -r -x are accepted and ignored)\n";
     std::exit(0);
@@ -88,6 +88,7 @@ Args parse(int argc, char **argv)
         else if (p == "--threshold") a.threshold = std::stof(next());
         else if (p == "--six") a.six = true;
         else if (p == "--three") a.six = false;
+        else if (p == "--one") a.one = true;
         else if (p == "--json") a.format = "json";
         else if (p == "--jsonl") a.format = "jsonl";
         else if (p == "--tsv") a.format = "tsv";
@@ -247,7 +248,8 @@ int run_identify(const Args &a)
     if (paired && mates.size() != reads.size()) throw std::runtime_error("paired-end files differ in their number of reads");
 
     kasa_params p{};
-    p.device = a.device; p.highest_k = K; p.k_high = k_high; p.k_low = k_low; p.frames = a.six ? 6 : 3;
+    if (a.one && a.six) throw std::runtime_error("--one and --six exclude each other");     // main.cpp:618
+    p.device = a.device; p.highest_k = K; p.k_high = k_high; p.k_low = k_low; p.frames = a.one ? 1 : (a.six ? 6 : 3);
     p.score_mode = a.rtt.empty() ? KASA_SCORE_NONE : (a.exact ? KASA_SCORE_EXACT : KASA_SCORE_ORDERED);
     uint8_t codon[512];
     if (!a.alphabet_file.empty() && load_codon_table(a.alphabet_file, a.alphabet_id, codon)) p.codon_table = codon;
@@ -290,7 +292,7 @@ int run_identify(const Args &a)
         if (a.format == "tsv") out << "#Read number\tSpecifier from input file\tMatched taxa\tNames\tScores{relative,k-mer}\tError\n";
         else if (a.format == "json") out << "[\n";
     }
-    const int frames = a.six ? 6 : 3;
+    const int frames = a.one ? 1 : (a.six ? 6 : 3);
     uint64_t n_kmers_total = 0, read_no = 0;
     // two host batches in flight per GPU (kasa_identify_submit / _wait): while the devices work on the later batches, the
     // oldest one's per-read output is formatted and written here, in input order

@@ -100,19 +100,31 @@ def revcomp(seq: bytes) -> bytes:
     return _RC_TAB[np.frombuffer(seq, dtype=np.uint8)][::-1].tobytes()
 
 
-def prepare_read(seq: bytes, K: int, k_low: int, six: bool) -> list[bytes]:
-    """Read.hpp:699-760 processInput + :612-654: clean, pad with 'X' until len+marker >= 3K,
+def prepare_read(seq: bytes, K: int, k_low: int, six: bool, one: bool = False) -> list[bytes]:
+    """Read.hpp:699-760 processInput + :612-654: clean, pad with 'X' until len+marker >= 3K (--one: until (len+marker)/3 >= K),
     append the marker 'X'*3*(K-kLow) (Read.hpp:1068-1078).  Returns [forward] or [forward, rc]
     in the reference's emission order per read (forward first: Read.hpp:278-281)."""
     marker = b"X" * (3 * (K - k_low))
     s = clean(seq)
     if len(s) > 0:
-        while len(s) + len(marker) < 3 * K:
-            s += b"X"
+        if one:
+            while (len(s) + len(marker)) // 3 < K:
+                s += b"X"
+        else:
+            while len(s) + len(marker) < 3 * K:
+                s += b"X"
     out = [s + marker]
-    if six:
+    if six and not one:
         out.append(revcomp(s) + marker)
     return out
+
+
+def extract_one_frame(seq_prepared: bytes, K: int, table: np.ndarray | None = None) -> np.ndarray:
+    """--one (Read.hpp:223-260 convert_dnaTokMerOneFrame, count Read.hpp:43-48): the k-mers of the first reading frame only, i.e.
+    every third k-mer of the all-frames walk, len/3 - K + 1 of them when len/3 > K + 1."""
+    t = len(seq_prepared) // 3
+    n = t - K + 1 if t > K + 1 else 0
+    return np.ascontiguousarray(extract(seq_prepared, K, table)[0::3][:n])
 
 
 def extract(seq_prepared: bytes, K: int, table: np.ndarray | None = None, build: bool = False) -> np.ndarray:
@@ -364,23 +376,23 @@ def presorted_emission(kmers: np.ndarray, read_id: np.ndarray, presort_max: int 
 
 
 def identify_reads_ordered(reads: list[list[bytes]], index: np.ndarray, K: int, k_high: int, k_low: int, six: bool,
-                           taxid_of_idx: np.ndarray, table: np.ndarray | None = None, sort_bits: int = 32) -> IdentifyResult:
+                           taxid_of_idx: np.ndarray, table: np.ndarray | None = None, sort_bits: int = 32, one: bool = False) -> IdentifyResult:
     """KASA_SCORE_ORDERED: the library emits the k-mers of ordinary reads presorted and sorts the batch stably on the leading
     `sort_bits` key bits, so a read's scores are summed in ascending k-mer order (reads of more than presort_limit(K) k-mers: ascending
     on the leading sort_bits, then emission order)."""
-    k, ids = presorted_emission(*read_kmers(reads, K, k_low, six, table), presort_limit(K))
+    k, ids = presorted_emission(*read_kmers(reads, K, k_low, six, table, one), presort_limit(K))
     return identify_kmers_ordered(k, ids, len(reads), index, K, k_high, k_low, taxid_of_idx, sort_bits)
 
 
-def read_kmers(reads: list[list[bytes]], K: int, k_low: int, six: bool, table: np.ndarray | None = None):
+def read_kmers(reads: list[list[bytes]], K: int, k_low: int, six: bool, table: np.ndarray | None = None, one: bool = False):
     """reads[i] = list of mate sequences sharing read id i (paired-end mates pool their k-mers,
     Read.hpp:963-970).  Returns (kmers [n,2] u64, read_id [n] u32) in the reference's emission order."""
     table = default_codon_table() if table is None else table
     ks, ids = [], []
     for rid, mates in enumerate(reads):
         for m in mates:
-            for st in prepare_read(m, K, k_low, six):
-                k = extract(st, K, table)
+            for st in prepare_read(m, K, k_low, six, one):
+                k = extract_one_frame(st, K, table) if one else extract(st, K, table)
                 ks.append(k)
                 ids.append(np.full(len(k), rid, dtype=np.uint32))
     if not ks:
@@ -389,8 +401,8 @@ def read_kmers(reads: list[list[bytes]], K: int, k_low: int, six: bool, table: n
 
 
 def identify_reads(reads: list[list[bytes]], index: np.ndarray, K: int, k_high: int, k_low: int, six: bool,
-                   taxid_of_idx: np.ndarray, table: np.ndarray | None = None) -> IdentifyResult:
-    k, ids = read_kmers(reads, K, k_low, six, table)
+                   taxid_of_idx: np.ndarray, table: np.ndarray | None = None, one: bool = False) -> IdentifyResult:
+    k, ids = read_kmers(reads, K, k_low, six, table, one)
     return identify_kmers(k, ids, len(reads), index, K, k_high, k_low, taxid_of_idx)
 
 

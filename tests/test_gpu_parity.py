@@ -133,7 +133,7 @@ def test_radix_sort_partial_bits_and_skewed_digits():
 
 
 # ----------------------------------------------------------------------------------------- identify
-def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, rtol=ORDERED_RTOL, exact=False):
+def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, rtol=ORDERED_RTOL, exact=False, one=False):
     _, taxids, _ = G.content(case)
     idx = G.index(case)
     if paired:
@@ -141,7 +141,7 @@ def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, r
         reads = [[x[1], y[1]] for x, y in zip(a, b)]
     else:
         reads = [[x[1]] for x in G.fastq(case)]
-    ctx = _ctx(highest_k=K, k_high=k_high, k_low=k_low, frames=6 if six else 3,
+    ctx = _ctx(highest_k=K, k_high=k_high, k_low=k_low, frames=1 if one else (6 if six else 3),
                score_mode=capi.SCORE_EXACT if exact else capi.SCORE_ORDERED)
     ctx.load_index(idx, taxids)
     pieces = [reads] if split is None else [reads[:split], reads[split:]]
@@ -157,7 +157,7 @@ def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, r
     scores = np.concatenate(scores)
     ca, cu, total = ctx.identify_finish()
     ctx.close()
-    ora = O.identify_reads(reads, idx, K, k_high, k_low, six, taxids)
+    ora = O.identify_reads(reads, idx, K, k_high, k_low, six, taxids, one=one)
     assert n_kmers == total == ora.n_kmers == G.n_kmers(case, tag)
     assert np.array_equal(cu, ora.count_unique)                               # exact integers
     np.testing.assert_allclose(ca, ora.count_all, rtol=COUNT_RTOL, atol=1e-9)
@@ -166,7 +166,7 @@ def _identify_case(case, tag, K, k_high, k_low, six, paired=False, split=None, r
         assert np.array_equal(scores, ora.scores)      # fp32 in the reference's flush order: bit-exact
         rtol = 0.0
     else:
-        mine = O.identify_reads_ordered(reads, idx, K, k_high, k_low, six, taxids)
+        mine = O.identify_reads_ordered(reads, idx, K, k_high, k_low, six, taxids, one=one)
         assert np.array_equal(scores, mine.scores)     # the library's own order, restated on the CPU: bit-exact
         np.testing.assert_allclose(scores, ora.scores, rtol=rtol, atol=0)
         nz = ora.scores != 0
@@ -201,6 +201,21 @@ def test_identify_k12_three_frames_k11_8():
 
 def test_identify_k12_single_level():
     _identify_case("k12", "six_12_12", 12, 12, 12, True)
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_identify_k12_one_frame(exact):
+    """--one (frames = 1, Read.hpp:223-260): k-mers of the first reading frame only, against `kASA identify --one`."""
+    _identify_case("k12", "one_12_7", 12, 12, 7, False, one=True, exact=exact)
+
+
+def test_extract_one_frame_matches_oracle():
+    reads = _k12_reads() + [b"", b"ACG", b"ACGTTGCA" * 6, b"A" * 37, b"A" * 38, b"A" * 39, b"acgtnACGTN" * 30, b"ACGTTGCATTGA" * 400]
+    ctx = _ctx(frames=1, k_low=7, k_high=12)
+    lo, hi, rid = ctx.dbg_extract(reads)
+    want_k, want_id = O.presorted_emission(*O.read_kmers([[r] for r in reads], 12, 7, False, one=True))
+    assert len(lo) == len(want_k) and np.array_equal(lo, want_k[:, 0]) and np.array_equal(rid, want_id)
+    ctx.close()
 
 
 def test_identify_k25_paired():

@@ -128,6 +128,7 @@ def _check_profile(path, case, tag):
     ("k12", "three_11_8", ["-k", "11", "8"]),
     ("k12", "six_12_12", ["--six", "-k", "12", "12"]),
     ("k25", "six_25_7", ["--six", "-k", "25", "7"]),
+    ("k12", "one_12_7", ["--one"]),
 ])
 def test_cli_identify_matches_reference_outputs(case, tag, flags, tmp_path):
     idx = _write_index(case, tmp_path)

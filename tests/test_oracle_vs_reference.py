@@ -35,11 +35,11 @@ def _reads(case, paired):
     return [[x[1]] for x in a], [x[0] + b" " for x in a]
 
 
-def _check_identify(case, tag, K, k_high, k_low, six, paired=False):
+def _check_identify(case, tag, K, k_high, k_low, six, paired=False, one=False):
     _, taxids, _ = G.content(case)
     idx = G.index(case)
     reads, names = _reads(case, paired)
-    res = O.identify_reads(reads, idx, K, k_high, k_low, six, taxids)
+    res = O.identify_reads(reads, idx, K, k_high, k_low, six, taxids, one=one)
     assert res.n_kmers == G.n_kmers(case, tag)
     head, rows = G.profile(case, tag)
     numK = k_high - k_low + 1
@@ -57,7 +57,7 @@ def _check_identify(case, tag, K, k_high, k_low, six, paired=False):
     assert len(pr) == len(reads)
     freq = G.frequency(case)
     tax2idx = {int(t): i for i, t in enumerate(taxids)}
-    frames = 6 if six else 3
+    frames = 1 if one else (6 if six else 3)
     n_cells = 0
     for r, rec in enumerate(pr):
         assert rec["name"].encode() == names[r]
@@ -84,6 +84,10 @@ def test_identify_k12_three_frames_k11_8():
 
 def test_identify_k12_single_level():
     _check_identify("k12", "six_12_12", 12, 12, 12, True)
+
+
+def test_identify_k12_one_frame():
+    _check_identify("k12", "one_12_7", 12, 12, 7, False, one=True)      # --one (Read.hpp:223-260)
 
 
 def test_identify_k25_paired_six():
