@@ -65,8 +65,8 @@ typedef struct {
     int32_t device;           /* CUDA device ordinal                                                   */
     int32_t highest_k;        /* index width: 12 (64-bit k-mers) or 25 (128-bit); kASA _iHighestK      */
     int32_t k_high, k_low;    /* -k <high> <low> (main.cpp:372-385); k_low >= 1, k_high <= highest_k   */
-    int32_t frames;           /* 3 = forward frames (default), 6 = --six, 1 = --one (first frame only,
-                                 Read.hpp:223-260; identify only)                                        */
+    int32_t frames;           /* 3 = forward frames (default), 6 = --six, 1 = --one: first frame only — identify
+                                 Read.hpp:223-260; build: every third window of a pushed string, Read.hpp:2143-2200 */
     int32_t score_mode;       /* KASA_SCORE_*                                                          */
     uint64_t max_batch_kmers; /* workspace sizing: largest sum of kMerCount per batch                  */
     uint32_t max_batch_seqs;  /* largest number of sequences (reads/mates or build pieces) per batch   */

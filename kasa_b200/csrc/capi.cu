@@ -1511,7 +1511,8 @@ int kasa_build_push(kasa_ctx *c, const kasa_seq_batch *in)
     const uint64_t *seq_start = stage_array(c, in->seq_start, ns, c->d_seq_start, in->location);
     const uint32_t *seq_len = stage_array(c, in->seq_len, ns, c->d_seq_len, in->location);
     const uint32_t *taxid = stage_array(c, in->taxid, ns, c->d_taxid, in->location);
-    launch_build_counts(c->stream, seq_len, ns, c->K, c->d_koff, &c->launches);
+    const int one = c->p.frames == 1 ? 1 : 0;                       // build --one: every third window of a string
+    launch_build_counts(c->stream, seq_len, ns, c->K, one, c->d_koff, &c->launches);
     exclusive_scan_u64(c->stream, c->d_koff, ns, c->d_scan_tmp, &c->launches);
     const uint64_t nw = read_u64(c, c->d_koff + ns);
     KASA_REQUIRE(nw <= c->p.max_batch_kmers, KASA_ERR_NOMEM, "one push yields more k-mer windows than max_batch_kmers: push fewer sequences at a time");
@@ -1525,7 +1526,7 @@ int kasa_build_push(kasa_ctx *c, const kasa_seq_batch *in)
     }
     const int b = c->build_buf;
     const uint64_t o = c->build_fill;
-    launch_extract_build(c->stream, ascii, seq_start, seq_len, taxid, ns, c->K, c->d_codon, c->d_koff, nw, c->sb.w0[b] + o,
+    launch_extract_build(c->stream, ascii, seq_start, seq_len, taxid, ns, c->K, one, c->d_codon, c->d_koff, nw, c->sb.w0[b] + o,
                          c->wide ? c->sb.w1[b] + o : nullptr, c->sb.v[b] + o, &c->launches);
     KASA_CUDA_TRY(cudaGetLastError());
     KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));    // staging buffers are reused by the next push

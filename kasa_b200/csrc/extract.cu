@@ -442,15 +442,17 @@ __global__ void __launch_bounds__(kLongWarps * 32) extract_long_kernel(PackedSeq
     }
 }
 
-__global__ void build_counts_kernel(const uint32_t *__restrict__ seq_len, uint32_t n, int K, uint64_t *__restrict__ out)
+__global__ void build_counts_kernel(const uint32_t *__restrict__ seq_len, uint32_t n, int K, int one, uint64_t *__restrict__ out)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = seq_len[i] >= (uint32_t)(3 * K) ? (uint64_t)seq_len[i] - 3 * K + 1 : 0;   // Read.hpp:1995
+    if (i >= n) return;
+    const uint64_t range = seq_len[i] >= (uint32_t)(3 * K) ? (uint64_t)seq_len[i] - 3 * K + 1 : 0;   // Read.hpp:1995
+    out[i] = one ? (range + 2) / 3 : range;             // --one: the offsets 0, 3, 6, ... < range (Read.hpp:2143-2200)
 }
 
 template <bool WIDE>
 __global__ void __launch_bounds__(256) extract_build_kernel(const char *__restrict__ ascii, const uint64_t *__restrict__ seq_start,
-                                                            const uint32_t *__restrict__ taxid, uint32_t n_seqs, int K,
+                                                            const uint32_t *__restrict__ taxid, uint32_t n_seqs, int K, int one,
                                                             const uint64_t *__restrict__ woff, uint64_t n_windows,
                                                             uint64_t *__restrict__ key_lo, uint64_t *__restrict__ key_hi,
                                                             uint32_t *__restrict__ val, const uint8_t *__restrict__ codon)
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(256) extract_build_kernel(const char *__restri
             uint32_t mid = (lo_s + hi_s) >> 1;
             if (__ldg(woff + mid) <= f) lo_s = mid; else hi_s = mid;
         }
-        const char *ptr = ascii + seq_start[lo_s] + (f - __ldg(woff + lo_s));
+        const char *ptr = ascii + seq_start[lo_s] + (f - __ldg(woff + lo_s)) * (one ? 3u : 1u);
         uint64_t lo = 0, hi = 0;
         bool bad = false;
         for (int i = 0; i < K; ++i) {
@@ -566,15 +568,15 @@ void launch_extract_identify_ascii(cudaStream_t s, const char *ascii, const uint
     }
 }
 
-void launch_build_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, int K, uint64_t *woff, uint64_t *launches)
+void launch_build_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, int K, int one, uint64_t *woff, uint64_t *launches)
 {
     if (!n_seqs) return;
-    build_counts_kernel<<<div_up(n_seqs, 256u), 256, 0, s>>>(seq_len, n_seqs, K, woff);
+    build_counts_kernel<<<div_up(n_seqs, 256u), 256, 0, s>>>(seq_len, n_seqs, K, one, woff);
     ++*launches;
 }
 
 void launch_extract_build(cudaStream_t s, const char *ascii, const uint64_t *seq_start, const uint32_t *seq_len,
-                          const uint32_t *taxid, uint32_t n_seqs, int K, const uint8_t *codon, const uint64_t *woff, uint64_t n_windows,
+                          const uint32_t *taxid, uint32_t n_seqs, int K, int one, const uint8_t *codon, const uint64_t *woff, uint64_t n_windows,
                           uint64_t *key_lo, uint64_t *key_hi, uint32_t *val, uint64_t *launches)
 {
     (void)seq_len;
@@ -582,9 +584,9 @@ void launch_extract_build(cudaStream_t s, const char *ascii, const uint64_t *seq
     uint64_t want = div_up<uint64_t>(n_windows, 256);
     unsigned grid = (unsigned)(want < (uint64_t)kSMs * 32 ? want : (uint64_t)kSMs * 32);
     if (K > 12)
-        extract_build_kernel<true><<<grid, 256, 0, s>>>(ascii, seq_start, taxid, n_seqs, K, woff, n_windows, key_lo, key_hi, val, codon);
+        extract_build_kernel<true><<<grid, 256, 0, s>>>(ascii, seq_start, taxid, n_seqs, K, one, woff, n_windows, key_lo, key_hi, val, codon);
     else
-        extract_build_kernel<false><<<grid, 256, 0, s>>>(ascii, seq_start, taxid, n_seqs, K, woff, n_windows, key_lo, key_hi, val, codon);
+        extract_build_kernel<false><<<grid, 256, 0, s>>>(ascii, seq_start, taxid, n_seqs, K, one, woff, n_windows, key_lo, key_hi, val, codon);
     ++*launches;
 }
 

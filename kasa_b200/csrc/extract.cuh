@@ -61,9 +61,10 @@ void launch_extract_identify_ascii(cudaStream_t s, const char *ascii, const uint
 
 // build: one slot per window of each prepared ASCII string; windows holding '_' (31) or giving k-mer 0
 // get the sentinel key ~0 (dropped after the sort): Read.hpp:2016-2024, 2048-2059, 2097, 2122
-void launch_build_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, int K, uint64_t *woff, uint64_t *launches);
+// one = 1: `build --one` (Read.hpp:2143-2200): only the windows at every third base of a string
+void launch_build_counts(cudaStream_t s, const uint32_t *seq_len, uint32_t n_seqs, int K, int one, uint64_t *woff, uint64_t *launches);
 void launch_extract_build(cudaStream_t s, const char *ascii, const uint64_t *seq_start, const uint32_t *seq_len,
-                          const uint32_t *taxid, uint32_t n_seqs, int K, const uint8_t *codon, const uint64_t *woff, uint64_t n_windows,
+                          const uint32_t *taxid, uint32_t n_seqs, int K, int one, const uint8_t *codon, const uint64_t *woff, uint64_t n_windows,
                           uint64_t *key_lo, uint64_t *key_hi, uint32_t *val, uint64_t *launches);
 
 }  // namespace kasa

@@ -138,7 +138,8 @@ int run_build(const Args &a)
     Content content = load_content(a.content);
     const std::string fasta = slurp(a.input);
     kasa_params p{};
-    p.device = a.device; p.highest_k = K; p.k_high = K; p.k_low = std::min(7, K); p.frames = a.six ? 6 : 3;
+    if (a.one && a.six) throw std::runtime_error("--one and --six exclude each other");     // main.cpp:618
+    p.device = a.device; p.highest_k = K; p.k_high = K; p.k_low = std::min(7, K); p.frames = a.one ? 1 : (a.six ? 6 : 3);
     p.score_mode = KASA_SCORE_NONE;
     uint8_t codon[512];
     if (!a.alphabet_file.empty() && load_codon_table(a.alphabet_file, a.alphabet_id, codon)) p.codon_table = codon;

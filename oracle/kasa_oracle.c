@@ -119,11 +119,18 @@ uint64_t ko_extract(const uint8_t *table, const char *s, uint64_t len, int K, ui
  * letter 31 ('_') are dropped (:2016-2024, :2048-2059) and so are k-mers == 0
  * (:2097, :2122).  Build strings have iMaxRange = len - 3K + 1 >= 1 (no +1 rule).
  * Returns number of k-mers written ({low,high} pairs).                        */
+uint64_t ko_extract_build_step(const uint8_t *table, const char *s, uint64_t len, int K, int step, uint64_t *out);
 uint64_t ko_extract_build(const uint8_t *table, const char *s, uint64_t len, int K, uint64_t *out)
+{
+    return ko_extract_build_step(table, s, len, K, 1, out);
+}
+
+/* step = 3: `build --one` (Read.hpp:2143-2200 dnaTokMers_oneFrame): windows at the offsets 0, 3, 6, ... < len - 3K + 1 only. */
+uint64_t ko_extract_build_step(const uint8_t *table, const char *s, uint64_t len, int K, int step, uint64_t *out)
 {
     if (len < (uint64_t)(3 * K)) return 0;
     uint64_t n = len - 3 * K + 1, w = 0;
-    for (uint64_t p = 0; p < n; ++p) {
+    for (uint64_t p = 0; p < n; p += (uint64_t)step) {
         kmer_t v = 0;
         int bad = 0;
         for (int i = 0; i < K; ++i) {

@@ -45,6 +45,8 @@ def lib():
         L.ko_extract.argtypes = [u8p, C.c_char_p, C.c_uint64, C.c_int, u64p]
         L.ko_extract_build.restype = C.c_uint64
         L.ko_extract_build.argtypes = [u8p, C.c_char_p, C.c_uint64, C.c_int, u64p]
+        L.ko_extract_build_step.restype = C.c_uint64
+        L.ko_extract_build_step.argtypes = [u8p, C.c_char_p, C.c_uint64, C.c_int, C.c_int, u64p]
         L.ko_sort_dedup.restype = C.c_uint64
         L.ko_sort_dedup.argtypes = [u64p, u32p, C.c_uint64, C.c_int, u8p]
         L.ko_trie.restype = C.c_uint64
@@ -127,13 +129,15 @@ def extract_one_frame(seq_prepared: bytes, K: int, table: np.ndarray | None = No
     return np.ascontiguousarray(extract(seq_prepared, K, table)[0::3][:n])
 
 
-def extract(seq_prepared: bytes, K: int, table: np.ndarray | None = None, build: bool = False) -> np.ndarray:
-    """[n,2] u64 {low, high} k-mers of one prepared string (identify or build rules)."""
+def extract(seq_prepared: bytes, K: int, table: np.ndarray | None = None, build: bool = False, one: bool = False) -> np.ndarray:
+    """[n,2] u64 {low, high} k-mers of one prepared string (identify or build rules; build with one = True: `build --one`)."""
     table = default_codon_table() if table is None else table
     n = max(0, len(seq_prepared) - 3 * K + 1)
     out = np.zeros((max(n, 1), 2), dtype=np.uint64)
-    fn = lib().ko_extract_build if build else lib().ko_extract
-    w = fn(_p(table, u8p), seq_prepared, len(seq_prepared), K, _p(out, u64p))
+    if build:
+        w = lib().ko_extract_build_step(_p(table, u8p), seq_prepared, len(seq_prepared), K, 3 if one else 1, _p(out, u64p))
+    else:
+        w = lib().ko_extract(_p(table, u8p), seq_prepared, len(seq_prepared), K, _p(out, u64p))
     return out[:w]
 
 
@@ -272,13 +276,13 @@ def fasta_build_strings(data: bytes, acc2tax: dict, K: int, six: bool) -> list[t
     return out
 
 
-def build_index_from_strings(strings: list[tuple[bytes, int]], K: int, table: np.ndarray | None = None):
+def build_index_from_strings(strings: list[tuple[bytes, int]], K: int, table: np.ndarray | None = None, one: bool = False):
     """(string, taxid) pairs -> (index records, trie records): Read.hpp:1991-2139 + Build.hpp:305-477 + Trie.hpp:366-394."""
     bits = 128 if K > 12 else 64
     table = default_codon_table() if table is None else table
     ks, ts = [], []
     for st, tax in strings:
-        k = extract(st, K, table, build=True)
+        k = extract(st, K, table, build=True, one=one)
         ks.append(k)
         ts.append(np.full(len(k), tax, dtype=np.uint32))
     kk = np.ascontiguousarray(np.concatenate(ks)) if ks else np.zeros((0, 2), np.uint64)
@@ -291,9 +295,9 @@ def build_index_from_strings(strings: list[tuple[bytes, int]], K: int, table: np
     return index, tr[:nt].copy()
 
 
-def build_index(fasta: bytes, acc2tax: dict, K: int, six: bool = False, table: np.ndarray | None = None):
+def build_index(fasta: bytes, acc2tax: dict, K: int, six: bool = False, table: np.ndarray | None = None, one: bool = False):
     """Whole `kASA build` restated: FASTA bytes + accession->taxid -> (index, trie)."""
-    return build_index_from_strings(fasta_build_strings(fasta, acc2tax, K, six), K, table)
+    return build_index_from_strings(fasta_build_strings(fasta, acc2tax, K, six and not one), K, table, one)
 
 
 def frequency(index: np.ndarray, K: int, taxid_of_idx: np.ndarray) -> np.ndarray:

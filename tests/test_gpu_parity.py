@@ -292,6 +292,22 @@ def test_build_matches_reference_files(case, K, six):
     ctx.close()
 
 
+def test_build_one_frame_matches_reference_files():
+    """`build --one` (frames = 1; Read.hpp:2143-2200): only the windows at every third base of each FASTA piece; index and prefix table
+    hash to the files `kASA build --one` wrote (tests/golden/k12/one_build_sha256.txt), and equal the oracle's restatement."""
+    import hashlib
+    strings = O.fasta_build_strings(G.gz("k12", "ref.fa.gz"), G.acc2tax("k12"), 12, False)
+    ctx = _ctx(frames=1, max_batch_kmers=1 << 20)
+    ctx.build_push([s for s, _ in strings], [t for _, t in strings])
+    rec, trie = ctx.build_finish()
+    ctx.close()
+    n, sha, nt, tsha = G.text("k12", "one_build_sha256.txt").split()
+    assert len(rec) == int(n) and hashlib.sha256(rec.tobytes()).hexdigest() == sha
+    assert len(trie) == int(nt) and hashlib.sha256(trie.tobytes()).hexdigest() == tsha
+    want, want_trie = O.build_index(G.gz("k12", "ref.fa.gz"), G.acc2tax("k12"), 12, one=True)
+    assert rec.tobytes() == want.tobytes() and trie.tobytes() == want_trie.tobytes()
+
+
 def test_build_brick_overflow_compacts_and_continues():
     strings = O.fasta_build_strings(G.gz("k12", "ref.fa.gz"), G.acc2tax("k12"), 12, False)
     ctx = _ctx(max_batch_kmers=100_000)     # 48k windows per push: the third push overflows the brick

@@ -101,6 +101,18 @@ def test_cli_build_with_another_codon_table(tmp_path):
     assert data != G.gz("k12", "idx.gz")          # and it differs from the standard-code index
 
 
+@pytest.mark.gpu
+def test_cli_build_one_frame(tmp_path):
+    """`build --one`: the index file equals the one `kASA build --one` wrote (tests/golden/k12/one_build_sha256.txt)."""
+    import hashlib
+    idx = str(tmp_path / "idx")
+    rc, out, err = _cli("build", "-c", _g("k12", "content.txt"), "-d", idx, "-i", _g("k12", "ref.fa.gz"), "--one")
+    assert rc == 0, err
+    n_want, sha_want = G.text("k12", "one_build_sha256.txt").split()[:2]
+    n = int(open(idx + "_info.txt").read().split()[0])
+    assert n == int(n_want) and hashlib.sha256(open(idx, "rb").read()[:n * 12]).hexdigest() == sha_want
+
+
 def _write_index(case, tmp_path):
     """golden index files laid out the way `identify -d` expects them."""
     idx = str(tmp_path / "idx")

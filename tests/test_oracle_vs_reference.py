@@ -86,6 +86,14 @@ def test_identify_k12_single_level():
     _check_identify("k12", "six_12_12", 12, 12, 12, True)
 
 
+def test_build_one_frame_matches_reference():
+    import hashlib
+    idx, trie = O.build_index(G.gz("k12", "ref.fa.gz"), G.acc2tax("k12"), 12, one=True)       # build --one (Read.hpp:2143-2200)
+    n, sha, nt, tsha = G.text("k12", "one_build_sha256.txt").split()
+    assert len(idx) == int(n) and hashlib.sha256(idx.tobytes()).hexdigest() == sha
+    assert len(trie) == int(nt) and hashlib.sha256(trie.tobytes()).hexdigest() == tsha
+
+
 def test_identify_k12_one_frame():
     _check_identify("k12", "one_12_7", 12, 12, 7, False, one=True)      # --one (Read.hpp:223-260)
 
