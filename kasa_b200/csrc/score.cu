@@ -1695,8 +1695,8 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                 m1 = w2;
                 const uint32_t n1 = (uint32_t)__popcll(m1);
                 if (n1 == 1u) atomicAdd(&s_un[64 + __ffsll((long long)m1) - 1], 1u);           // alone at k_low + 1
-                upd = 0x80000000u;
-                const uint32_t e0 = (uint32_t)w3 & kPairMask;
+                upd = m1 ? 0x80000000u : 0u;
+                const uint32_t e0 = m1 ? (uint32_t)w3 & kPairMask : 0u;
                 if (e0 && (w3 >> kPairBits) == 0) {
                     upd |= e0;                                                                // the usual case: one taxon, alone at its levels 2 ..
                     atomicAdd(&s_hist[((e0 & 0xffffu) - 1u) * 32 + ((e0 >> 16) & 31u)], 1u);
