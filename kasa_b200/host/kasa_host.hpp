@@ -154,6 +154,78 @@ inline std::vector<ReadRec> parse_reads(const std::string &data)
     return out;
 }
 
+// The same records one at a time from a (possibly gzip-compressed) file: identify streams its input batch by batch instead of holding
+// the whole file (the reference reads it through FileReader::getChunk, Utilities.hpp:448-550, in two passes).
+class ReadStream {
+public:
+    explicit ReadStream(const std::string &path) : f_(gzopen(path.c_str(), "rb")), buf_(1 << 22)
+    {
+        if (!f_) throw std::runtime_error("File couldn't be opened: " + path);
+        gzbuffer(f_, 1 << 20);
+        have_ = next_line(line_);
+    }
+    ReadStream(const ReadStream &) = delete;
+    ReadStream &operator=(const ReadStream &) = delete;
+    ~ReadStream() { if (f_) gzclose(f_); }
+
+    // next record into r; false at the end of the file
+    bool next(ReadRec &r)
+    {
+        while (have_ && line_.empty()) have_ = next_line(line_);
+        if (!have_) return false;
+        r.name.clear(); r.seq.clear(); r.lines = 0;
+        if (line_[0] == '>') {
+            r.name = line_.substr(1);
+            while ((have_ = next_line(line_)) && (line_.empty() || line_[0] != '>')) {
+                if (line_.empty()) continue;
+                r.seq += line_; ++r.lines;
+            }
+        } else if (line_[0] == '@') {
+            r.name = line_.substr(1);
+            while ((have_ = next_line(line_)) && (line_.empty() || line_[0] != '+')) {
+                if (line_.empty()) continue;
+                r.seq += line_; ++r.lines;
+            }
+            size_t q = 0;                    // quality: as many characters as bases
+            while (q < r.seq.size() && (have_ = next_line(line_))) q += line_.size();
+            have_ = next_line(line_);
+        } else {
+            throw std::runtime_error("Input is neither FASTA nor FASTQ.");
+        }
+        return true;
+    }
+
+private:
+    bool fill()
+    {
+        const int n = gzread(f_, buf_.data(), (unsigned)buf_.size());
+        if (n < 0) throw std::runtime_error("Error while reading the input");
+        pos_ = 0; end_ = (size_t)n;
+        return n > 0;
+    }
+    bool next_line(std::string &line)
+    {
+        line.clear();
+        bool any = false;
+        for (;;) {
+            if (pos_ == end_ && !fill()) break;
+            any = true;
+            const char *b = buf_.data() + pos_;
+            const char *nl = static_cast<const char *>(std::memchr(b, '\n', end_ - pos_));
+            if (nl) { line.append(b, (size_t)(nl - b)); pos_ += (size_t)(nl - b) + 1; break; }
+            line.append(b, end_ - pos_);
+            pos_ = end_;
+        }
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        return any;
+    }
+    gzFile f_;
+    std::vector<char> buf_;
+    size_t pos_ = 0, end_ = 0;
+    std::string line_;
+    bool have_ = false;
+};
+
 // ------------------------------------------------------------------------------------------------ build: FASTA pieces
 // The reference reads the FASTA through a 2048-byte buffer; a chunk ends at a newline or at the buffer end
 // (Utilities::FileReader::getChunk, Utilities.hpp:448-550).  Piece boundaries, and with --six the places where the

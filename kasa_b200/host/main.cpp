@@ -7,6 +7,7 @@
 #include <thread>
 #include <chrono>
 #include <iostream>
+#include <memory>
 
 #include "../../include/kasa_b200.h"
 #include "kasa_host.hpp"
@@ -53,6 +54,7 @@ struct Args {
     float threshold = 0.f;
     std::string format = "json";
     uint32_t batch_reads = 1u << 20;
+    uint64_t batch_bases = 0;
 };
 
 [[noreturn]] void usage()
@@ -60,7 +62,7 @@ struct Args {
     std::cout << "kasa_b200 <build|identify> -c <content> -d <index> [-i <input> | -1 <fq> -2 <fq>] [-p <profile.csv>] [-q <per-read out>]\n"
                  "          [-k <high> <low>] [--kH <12|25>] [--six | --one] [--json|--jsonl|--tsv|--kraken] [-b <n>] [--threshold <f>] [-v]\n"
                  "          [-a <gc.prt> <id>]\n"
-                 "          [--exact-scores] [--device <n>] [--gpus <n>] [--batch-reads <n>]   (-m -n -t -r -x are accepted and ignored)\n";
+                 "          [--exact-scores] [--device <n>] [--gpus <n>] [--batch-reads <n>] [--batch-bases <n>]   (-m -n -t -r -x are accepted and ignored)\n";
     std::exit(0);
 }
 
@@ -98,6 +100,7 @@ Args parse(int argc, char **argv)
         else if (p == "--device") a.device = std::stoi(next());
         else if (p == "--gpus") a.gpus = std::max(1, std::stoi(next()));
         else if (p == "--batch-reads") a.batch_reads = (uint32_t)std::stoul(next());
+        else if (p == "--batch-bases") a.batch_bases = std::stoull(next());
         else if (p == "-m" || p == "-n" || p == "-x") (void)next();
         else if (p == "-r" || p == "--ram") {}
         else if (p == "-h" || p == "--help") usage();
@@ -241,12 +244,12 @@ int run_identify(const Args &a)
             freq_high[i++] = std::stoull(v[1 + nk - k_high]);
         }
     }
-    std::string rd1 = slurp(a.in1.empty() ? a.input : a.in1), rd2;
-    std::vector<ReadRec> reads = parse_reads(rd1), mates;
-    rd1.clear(); rd1.shrink_to_fit();
+    // The input is streamed: a batch of reads is parsed while the devices work on the earlier ones (the reference reads its input
+    // through a 2048-byte window in two passes, Utilities.hpp:448-550; nothing here holds more than the batches in flight).
+    ReadStream in1(a.in1.empty() ? a.input : a.in1);
     const bool paired = !a.in2.empty();
-    if (paired) { rd2 = slurp(a.in2); mates = parse_reads(rd2); rd2.clear(); }
-    if (paired && mates.size() != reads.size()) throw std::runtime_error("paired-end files differ in their number of reads");
+    std::unique_ptr<ReadStream> in2;
+    if (paired) in2.reset(new ReadStream(a.in2));
 
     kasa_params p{};
     if (a.one && a.six) throw std::runtime_error("--one and --six exclude each other");     // main.cpp:618
@@ -254,38 +257,10 @@ int run_identify(const Args &a)
     p.score_mode = a.rtt.empty() ? KASA_SCORE_NONE : (a.exact ? KASA_SCORE_EXACT : KASA_SCORE_ORDERED);
     uint8_t codon[512];
     if (!a.alphabet_file.empty() && load_codon_table(a.alphabet_file, a.alphabet_id, codon)) p.codon_table = codon;
-    const uint32_t per_batch = std::max<uint32_t>(1, std::min<uint32_t>(a.batch_reads, (uint32_t)reads.size()));
-    uint64_t max_bases = 0, max_kmers = 0;
+    const uint32_t per_batch = std::max<uint32_t>(1, a.batch_reads);
     const uint32_t marker = 3 * (K - k_low);
-    for (size_t b = 0; b < reads.size(); b += per_batch) {
-        uint64_t bases = 0, kmers = 0;
-        for (size_t r = b; r < std::min(reads.size(), b + per_batch); ++r)
-            for (int m = 0; m < (paired ? 2 : 1); ++m) {
-                const size_t L = (m ? mates[r] : reads[r]).seq.size();
-                bases += L;
-                if (L + marker > (size_t)(3 * K + 1)) kmers += (L + marker - 3 * K + 1) * (a.six ? 2 : 1);
-            }
-        max_bases = std::max(max_bases, bases); max_kmers = std::max(max_kmers, kmers);
-    }
-    p.max_batch_kmers = max_kmers + 4096; p.max_batch_seqs = per_batch * (paired ? 2 : 1) + 1; p.max_batch_bases = max_bases + 4096;
-    // --gpus N: the index is replicated on devices device .. device + N - 1, batches are dealt round-robin (reads are
-    // independent; the reference's worker threads, Compare.hpp:3221-3310, become GPUs).  One host thread drives all of them:
-    // kasa_identify_submit does not wait for the device.
-    const int G = a.gpus;
-    std::vector<kasa_ctx *> ctxs(G, nullptr);
-    {
-        std::ifstream f(a.index, std::ios::binary);
-        if (!f) throw std::runtime_error("Index file not found: " + a.index);
-        std::vector<char> bytes(n_idx * (bits == 128 ? 20 : 12));
-        f.read(bytes.data(), (std::streamsize)bytes.size());
-        const bool same_device = getenv("KASA_CLI_SAME_DEVICE") != nullptr;   // test hook: N contexts on one GPU
-        for (int g = 0; g < G; ++g) {
-            p.device = same_device ? a.device : a.device + g;
-            check(kasa_ctx_create(&p, &ctxs[g]), nullptr);
-            check(kasa_index_load(ctxs[g], bytes.data(), n_idx, bits, content.taxids.data(), (uint32_t)T), ctxs[g]);
-        }
-    }
-
+    // a batch closes at --batch-reads reads or --batch-bases bases, whichever comes first (long reads: fewer per batch)
+    const uint64_t budget_bases = a.batch_bases ? a.batch_bases : std::max<uint64_t>((uint64_t)per_batch * 320, 1ull << 24);
     std::ofstream out;
     if (!a.rtt.empty()) {
         out.open(a.rtt);
@@ -303,47 +278,98 @@ int run_identify(const Args &a)
         Pinned<uint64_t> starts;
         Pinned<uint32_t> lens, first;
         Pinned<float> scores;
+        std::vector<std::string> names;       // per read: "<name> " (paired: both mates' names)
+        std::vector<uint32_t> lengths;        // per read: the reference's "Length" (letters + one per sequence line, Utilities.hpp:521)
+        uint64_t kmers_bound = 0;             // upper bound of the batch's k-mers
         kasa_batch_result res{};
-        size_t b = 0, e = 0;
+        size_t n = 0;
         kasa_ctx *ctx = nullptr;
     };
+    const int G = a.gpus;
     std::vector<HostBatch> hb(2 * (size_t)G);
     const size_t fmt_threads = std::max(1u, std::thread::hardware_concurrency());      // the reference formats on its worker threads too (Compare.hpp:3391)
-    auto submit = [&](HostBatch &h, size_t b, kasa_ctx *ctx) {
-        h.ctx = ctx;
-        const size_t e = std::min(reads.size(), b + per_batch);
-        h.b = b; h.e = e;
-        h.chars.clear(); h.starts.clear(); h.lens.clear(); h.first.clear();
-        for (size_t r = b; r < e; ++r) {
-            h.first.push_back((uint32_t)h.starts.size());
-            for (int m = 0; m < (paired ? 2 : 1); ++m) {
-                const std::string &s = (m ? mates[r] : reads[r]).seq;
-                h.starts.push_back(h.chars.size()); h.lens.push_back((uint32_t)s.size()); h.chars.append(s.data(), s.size());
+    ReadRec pend1, pend2;
+    bool have_pending = false, eof = false;
+    // parses the next batch into h; false when the input is exhausted and the batch is empty
+    auto fill = [&](HostBatch &h) -> bool {
+        h.chars.clear(); h.starts.clear(); h.lens.clear(); h.first.clear(); h.names.clear(); h.lengths.clear();
+        h.n = 0; h.kmers_bound = 0;
+        uint64_t bases = 0;
+        while (h.n < per_batch) {
+            if (!have_pending) {
+                if (!in1.next(pend1)) { eof = true; if (paired && in2->next(pend2)) throw std::runtime_error("paired-end files differ in their number of reads"); break; }
+                if (paired && !in2->next(pend2)) throw std::runtime_error("paired-end files differ in their number of reads");
+                have_pending = true;
             }
+            const uint64_t L = pend1.seq.size() + (paired ? pend2.seq.size() : 0);
+            if (h.n && bases + L > budget_bases) break;                     // the pending read opens the next batch
+            if (L > budget_bases) throw std::runtime_error("a read is longer than --batch-bases (" + std::to_string(budget_bases) + "): raise it");
+            have_pending = false;
+            h.first.push_back((uint32_t)h.starts.size());
+            std::string name = pend1.name + " ";
+            uint32_t length = (uint32_t)pend1.seq.size() + pend1.lines;
+            for (int m = 0; m < (paired ? 2 : 1); ++m) {
+                const std::string &q = (m ? pend2 : pend1).seq;
+                h.starts.push_back(h.chars.size()); h.lens.push_back((uint32_t)q.size()); h.chars.append(q.data(), q.size());
+                if (q.size() + marker > (size_t)(3 * K + 1)) h.kmers_bound += (q.size() + marker - 3 * K + 1) * (a.six ? 2 : 1);
+            }
+            if (paired) { name += pend2.name + " "; length += (uint32_t)pend2.seq.size() + pend2.lines; }
+            h.names.push_back(std::move(name)); h.lengths.push_back(length);
+            bases += L;
+            ++h.n;
         }
         h.first.push_back((uint32_t)h.starts.size());
+        return h.n > 0;
+    };
+    // The first batch is parsed before the contexts exist: an input that ends inside it (the usual small run) sizes the
+    // workspaces exactly, a longer one by the batch limits.
+    const bool any_reads = fill(hb[0]);
+    if (eof && !have_pending) {
+        p.max_batch_kmers = hb[0].kmers_bound + 4096; p.max_batch_seqs = (uint32_t)hb[0].starts.size() + 1; p.max_batch_bases = hb[0].chars.size() + 4096;
+    } else {
+        const uint64_t seqs = (uint64_t)per_batch * (paired ? 2 : 1);
+        p.max_batch_kmers = std::min<uint64_t>((a.six ? 2 : 1) * (budget_bases + seqs * marker) + 4096, (1ull << 32) - (1u << 20));
+        p.max_batch_seqs = (uint32_t)seqs + 1; p.max_batch_bases = budget_bases + 4096;
+    }
+    // --gpus N: the index is replicated on devices device .. device + N - 1, batches are dealt round-robin (reads are
+    // independent; the reference's worker threads, Compare.hpp:3221-3310, become GPUs).  One host thread drives all of them:
+    // kasa_identify_submit does not wait for the device.
+    std::vector<kasa_ctx *> ctxs(G, nullptr);
+    {
+        std::ifstream f(a.index, std::ios::binary);
+        if (!f) throw std::runtime_error("Index file not found: " + a.index);
+        std::vector<char> bytes(n_idx * (bits == 128 ? 20 : 12));
+        f.read(bytes.data(), (std::streamsize)bytes.size());
+        const bool same_device = getenv("KASA_CLI_SAME_DEVICE") != nullptr;   // test hook: N contexts on one GPU
+        for (int g = 0; g < G; ++g) {
+            p.device = same_device ? a.device : a.device + g;
+            check(kasa_ctx_create(&p, &ctxs[g]), nullptr);
+            check(kasa_index_load(ctxs[g], bytes.data(), n_idx, bits, content.taxids.data(), (uint32_t)T), ctxs[g]);
+        }
+    }
+
+    auto submit = [&](HostBatch &h, kasa_ctx *ctx) {
+        h.ctx = ctx;
         kasa_read_batch in{};
-        in.n_reads = (uint32_t)(e - b); in.n_seqs = (uint32_t)h.starts.size(); in.format = KASA_SEQ_ASCII; in.location = KASA_MEM_HOST;
+        in.n_reads = (uint32_t)h.n; in.n_seqs = (uint32_t)h.starts.size(); in.format = KASA_SEQ_ASCII; in.location = KASA_MEM_HOST;
         in.bases = h.chars.data(); in.seq_start = h.starts.data(); in.seq_len = h.lens.data(); in.read_first_seq = h.first.data();
         h.res = kasa_batch_result{};
-        h.scores.assign(a.rtt.empty() ? 0 : (e - b) * T, 0.f);
+        h.scores.assign(a.rtt.empty() ? 0 : h.n * T, 0.f);
         h.res.scores = h.scores.empty() ? nullptr : h.scores.data(); h.res.scores_location = KASA_MEM_HOST;
         check(kasa_identify_submit(ctx, &in, &h.res), ctx);
     };
     auto emit = [&](HostBatch &h) {
         kasa_ctx *ctx = h.ctx;
         check(kasa_identify_wait(ctx), ctx);                  // the oldest batch of that GPU = the oldest batch overall
-        const size_t b = h.b, e = h.e;
         const Pinned<float> &scores = h.scores;
         n_kmers_total += h.res.n_kmers;
-        if (a.rtt.empty()) { read_no += e - b; return; }
+        if (a.rtt.empty()) { read_no += h.n; return; }
         // ---- per-read output (Compare.hpp:1485-1890): formatted by all host threads, chunk by chunk, written in input order
         auto format_read = [&](size_t r, uint64_t rn, std::string &o, std::vector<Hit> &hits) {
-            std::string name = reads[r].name + " ";
-            uint32_t length = (uint32_t)reads[r].seq.size() + reads[r].lines;
-            if (paired) { name += mates[r].name + " "; length += (uint32_t)mates[r].seq.size() + mates[r].lines; }
+            const std::string &name = h.names[r];
+            const uint32_t length = h.lengths[r];
             const float best = best_score(length, k_high, k_low, frames);
-            const float *row = scores.data() + (r - b) * T;
+            const float *row = scores.data() + r * T;
             size_t nh = 0;
             for (size_t t = 1; t < T; ++t)
                 if (row[t] > 0.f) {
@@ -425,14 +451,14 @@ int run_identify(const Args &a)
                 o += "\n";
             }
         };
-        const size_t n_batch = e - b;
+        const size_t n_batch = h.n;
         const size_t n_thr = std::max<size_t>(1, std::min<size_t>(fmt_threads, n_batch / 256 + 1));
         std::vector<std::string> pieces(n_thr);
         auto work = [&](size_t t) {
             std::vector<Hit> hits(T);
-            const size_t r0 = b + n_batch * t / n_thr, r1 = b + n_batch * (t + 1) / n_thr;
+            const size_t r0 = n_batch * t / n_thr, r1 = n_batch * (t + 1) / n_thr;
             pieces[t].reserve((r1 - r0) * 256);
-            for (size_t r = r0; r < r1; ++r) format_read(r, read_no + (r - b), pieces[t], hits);
+            for (size_t r = r0; r < r1; ++r) format_read(r, read_no + r, pieces[t], hits);
         };
         if (n_thr == 1) work(0);
         else {
@@ -447,9 +473,10 @@ int run_identify(const Args &a)
     // ago, the oldest in flight) is emitted
     const size_t ring = hb.size();
     size_t nb = 0, emitted = 0;
-    for (size_t b = 0; b < reads.size(); b += per_batch, ++nb) {
-        if (nb - emitted == ring) emit(hb[emitted++ % ring]);
-        submit(hb[nb % ring], b, ctxs[nb % (size_t)G]);
+    for (bool more = any_reads; more; ++nb) {
+        submit(hb[nb % ring], ctxs[nb % (size_t)G]);
+        if (nb + 1 - emitted == ring) emit(hb[emitted++ % ring]);       // frees the slot the next batch is parsed into
+        more = fill(hb[(nb + 1) % ring]);
     }
     while (emitted < nb) emit(hb[emitted++ % ring]);
     if (!a.rtt.empty() && a.format == "json") out << "\n]";

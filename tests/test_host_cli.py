@@ -160,17 +160,18 @@ def test_cli_identify_matches_reference_outputs(case, tag, flags, tmp_path):
 
 @pytest.mark.gpu
 def test_cli_batching_does_not_change_output(tmp_path):
-    """default scores (exact integer accumulation) are independent of how the reads are cut into batches."""
+    """default scores (float32 sums in ascending k-mer order per read) are independent of how the reads are cut into batches."""
     case = "k25"
     idx = _write_index(case, tmp_path)
     base = ["identify", "-c", _g(case, "content.txt"), "-d", idx, "-1", _g(case, "reads_1.fq.gz"), "-2", _g(case, "reads_2.fq.gz"),
             "--six", "-k", "25", "7", "--jsonl", "-b", "100000"]
     outs = []
-    for i, br in enumerate(["7", "64", "100000"]):
-        rc, _, err = _cli(*base, "-p", str(tmp_path / ("p%d" % i)), "-q", str(tmp_path / ("q%d" % i)), "--batch-reads", br)
+    # the input is streamed: a batch closes at --batch-reads reads or --batch-bases bases (2000 bases = 6 pairs of 2 x 150 bp)
+    for i, extra in enumerate([["--batch-reads", "7"], ["--batch-reads", "64"], ["--batch-reads", "100000"], ["--batch-bases", "2000"]]):
+        rc, _, err = _cli(*base, "-p", str(tmp_path / ("p%d" % i)), "-q", str(tmp_path / ("q%d" % i)), *extra)
         assert rc == 0, err
         outs.append((open(tmp_path / ("p%d" % i)).read(), open(tmp_path / ("q%d" % i)).read()))
-    assert outs[0] == outs[1] == outs[2]
+    assert outs[0] == outs[1] == outs[2] == outs[3]
     _check_profile(str(tmp_path / "p0"), case, "six_25_7")
 
 
