@@ -293,6 +293,13 @@ typedef struct {
  * One push may not yield more than max_batch_kmers windows.                                                              */
 int kasa_build_push(kasa_ctx *ctx, const kasa_seq_batch *in);
 
+/* Replaces: the reading of an existing index in `update` and `merge` (Build.hpp:153-300 `updateIndex`, Update.hpp,
+ * Read.hpp:3180-3243): the records of an index file (as for kasa_index_load) join the build like pushed sequences do, so
+ *   update = kasa_build_push_index(old index) + kasa_build_push(new sequences) + kasa_build_finish,
+ *   merge  = kasa_build_push_index(first) + kasa_build_push_index(second) + kasa_build_finish
+ * (the sort + dedup of kasa_build_finish is the merge; bricks spill to host memory as for any build).                 */
+int kasa_build_push_index(kasa_ctx *ctx, const void *entries, uint64_t n, int bits);
+
 /* Replaces: Build::IntToExtPart + mergeTemporaries (Build.hpp:305-477), Trie::SaveToStxxlVec
  * (Trie.hpp:366-394).  Sorts by (kmer, taxid), removes duplicates, run-length encodes the 6-letter
  * prefixes.  Outputs the counts; fetch the data with kasa_build_fetch.  When bricks were spilled they are merged here, one

@@ -30,7 +30,7 @@ EXPORTS = [
     "kasa_ctx_synchronize", "kasa_ctx_launch_count", "kasa_ctx_stage_times", "kasa_index_load", "kasa_index_from_build", "kasa_index_size",
     "kasa_identify_batch", "kasa_identify_submit", "kasa_identify_wait", "kasa_identify_finish", "kasa_build_push", "kasa_build_finish", "kasa_build_fetch",
     "kasa_shard_plan", "kasa_index_from_build_shard", "kasa_shard_init", "kasa_shard_connect", "kasa_shard_sort", "kasa_shard_lookup",
-    "kasa_shard_score", "kasa_build_shard_local", "kasa_shard_plan_hist", "kasa_build_shard_runs", "kasa_build_shard_pull", "kasa_build_frequency", "kasa_dbg_extract", "kasa_dbg_sort_pairs", "kasa_synth_build_reference", "kasa_synth_build_reference_range", "kasa_synth_reads", "kasa_host_alloc", "kasa_host_free", "kasa_builtin_codon_table",
+    "kasa_shard_score", "kasa_build_shard_local", "kasa_shard_plan_hist", "kasa_build_shard_runs", "kasa_build_shard_pull", "kasa_build_frequency", "kasa_dbg_extract", "kasa_dbg_sort_pairs", "kasa_synth_build_reference", "kasa_synth_build_reference_range", "kasa_synth_reads", "kasa_host_alloc", "kasa_host_free", "kasa_builtin_codon_table", "kasa_build_push_index",
 ]
 
 
@@ -411,6 +411,11 @@ class Context:
         sb = CSeqBatch(len(lens), MEM_HOST, data.ctypes.data if len(data) else None, starts.ctypes.data, lens.ctypes.data,
                        tax.ctypes.data)
         self._check(self.lib.kasa_build_push(self.h, C.byref(sb)))
+
+    def build_push_index(self, records: np.ndarray):
+        """records of an existing index (file layout) join the build: update / merge (kasa_build_push_index)."""
+        rec = np.ascontiguousarray(records)
+        self._check(self.lib.kasa_build_push_index(self.h, _ptr(rec) if len(rec) else None, C.c_uint64(len(rec)), 128 if self.wide else 64))
 
     def build_finish(self, fetch: bool = True):
         n, nt = C.c_uint64(0), C.c_uint64(0)

@@ -1534,6 +1534,39 @@ int kasa_build_push(kasa_ctx *c, const kasa_seq_batch *in)
     KASA_API_END(c)
 }
 
+int kasa_build_push_index(kasa_ctx *c, const void *entries, uint64_t n, int bits)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && (entries || n == 0), KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(bits == (c->wide ? 128 : 64), KASA_ERR_ARG, "index width does not match highest_k of the context");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    ensure_workspace(c);
+    if (c->build_done) { c->build_done = false; c->build_fill = 0; c->build_buf = 0; c->host_result = false; c->host_n = 0; c->host_words.clear(); c->host_trie.clear(); }
+    const size_t wpr = c->wide ? 5 : 3;
+    const uint64_t cap = c->p.max_batch_kmers;
+    // the records join the brick in pieces of at most half a brick (staged as file words in the free half of the ping-pong)
+    const uint64_t piece = std::max<uint64_t>(1, std::min<uint64_t>(cap / 2, cap * 8 / (wpr * 4)));
+    for (uint64_t o = 0; o < n; o += piece) {
+        const uint64_t m = std::min(piece, n - o);
+        if (c->build_fill + m > cap) {
+            build_compact(c);
+            if (c->build_fill + m > cap || c->build_fill > cap / 2) {
+                KASA_REQUIRE(!c->sh.on, KASA_ERR_NOMEM, "the brick of a prefix-sharded build is full: use more shards or a larger max_batch_kmers");
+                spill_brick(c);
+            }
+        }
+        const int b = c->build_buf;
+        uint32_t *stage = reinterpret_cast<uint32_t *>(c->sb.w0[b ^ 1]);
+        KASA_CUDA_TRY(cudaMemcpyAsync(stage, static_cast<const char *>(entries) + o * wpr * 4, m * wpr * 4, cudaMemcpyHostToDevice, c->stream));
+        launch_unpack_records(c->stream, stage, m, c->wide, c->sb.w0[b] + c->build_fill, c->wide ? c->sb.w1[b] + c->build_fill : nullptr,
+                              c->sb.v[b] + c->build_fill, &c->launches);
+        KASA_CUDA_TRY(cudaGetLastError());
+        KASA_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->build_fill += m;
+    }
+    KASA_API_END(c)
+}
+
 int kasa_build_finish(kasa_ctx *c, uint64_t *n_entries, uint64_t *n_trie)
 {
     KASA_API_BEGIN

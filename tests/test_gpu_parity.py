@@ -308,6 +308,37 @@ def test_build_one_frame_matches_reference_files():
     assert rec.tobytes() == want.tobytes() and trie.tobytes() == want_trie.tobytes()
 
 
+@pytest.mark.parametrize("cap", [1 << 20, 12_000])
+def test_update_and_merge_of_indexes_equal_one_build(cap):
+    """`update` / `merge` (Build.hpp:153-300, Update.hpp, Read.hpp:3180-3243) through kasa_build_push_index: an index of half the taxa
+    updated with the other half's sequences, and the merge of the two halves' indexes, both equal the index built from everything at
+    once = the reference's file (cap = 12 000 records per brick: the bricks spill and are merged by prefix range)."""
+    strings = O.fasta_build_strings(G.gz("k12", "ref.fa.gz"), G.acc2tax("k12"), 12, False)
+    taxa = sorted({t for _, t in strings})
+    first = set(taxa[: len(taxa) // 2])
+    part_a = [(s, t) for s, t in strings if t in first]
+    part_b = [(s, t) for s, t in strings if t not in first]
+
+    def build(parts, records=()):
+        ctx = _ctx(max_batch_kmers=cap, max_batch_seqs=1 << 12)
+        for rec in records:
+            ctx.build_push_index(rec)
+        for i in range(0, len(parts), 2):
+            ctx.build_push([s for s, _ in parts[i:i + 2]], [t for _, t in parts[i:i + 2]])
+        rec, trie = ctx.build_finish()
+        ctx.close()
+        return rec, trie
+
+    idx_a, _ = build(part_a)
+    idx_b, _ = build(part_b)
+    assert 0 < len(idx_a) < len(G.index("k12")) and 0 < len(idx_b) < len(G.index("k12"))
+    upd, upd_trie = build(part_b, records=[idx_a])                         # update: old index + new sequences
+    mrg, mrg_trie = build([], records=[idx_a, idx_b])                      # merge: two indexes
+    for rec, trie in ((upd, upd_trie), (mrg, mrg_trie)):
+        assert rec.tobytes() == G.index("k12").tobytes()
+        assert trie.tobytes() == G.trie("k12").tobytes()
+
+
 def test_build_brick_overflow_compacts_and_continues():
     strings = O.fasta_build_strings(G.gz("k12", "ref.fa.gz"), G.acc2tax("k12"), 12, False)
     ctx = _ctx(max_batch_kmers=100_000)     # 48k windows per push: the third push overflows the brick
