@@ -1602,6 +1602,27 @@ __global__ void __launch_bounds__(kItemBlock) score_items_kernel(const uint64_t 
 //          warp-uniform, nothing is indexed dynamically, nothing depends on how many taxa a k-mer names.
 // The sparse organisations above execute fewer useful lanes' worth of work but pay full price for every rare path a single lane takes;
 // against a saturated index (C2: 0.6 up pairs per k-mer, 10 % of the records with several) this one issues the fewest instructions.
+// one lane's share of a k-mer at one level: if its taxon's bit is set, the value joins the score and 1 / n the count — as two
+// predicated instructions (the compiler's own choice was a select and an unconditional add for the count)
+__device__ __forceinline__ void dense_add(float &score, uint32_t &share, float v, uint32_t q, uint32_t mask, uint32_t bit)
+{
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %4, %5;\n\tsetp.ne.u32 p, t, 0;\n\t@p add.rn.f32 %0, %0, %2;\n\t@p add.u32 %1, %1, %3;\n\t}"
+        : "+f"(score), "+r"(share) : "f"(v), "r"(q), "r"(mask), "r"(bit));
+}
+// shared-memory loads that stay where they are written (the compiler would sink them to their first use behind a branch)
+__device__ __forceinline__ uint4 lds_v4(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u32(const uint32_t *p)
+{
+    uint32_t r;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(r) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return r;
+}
+
 template <int ML>
 struct DenseWarpMem {
     uint4 a[32];              // per k-mer: taxa mask of level k_low (lo, hi), bits of float(w_0 * (1.f / n0)), 2^24 / n0 (0 for n0 < 2)
@@ -1734,15 +1755,15 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
             __syncwarp();
             // ---- main, lane = taxon: the block's k-mers in order (Compare.hpp:530 for level k_low, then the levels above)
             const uint32_t nblk = min(32u, ni - b0);
-#pragma unroll 1                                           // (unrolled by 4 the loop thrashed the instruction cache: stall no_instruction 2.6; by 2: no gain)
-            for (uint32_t i = 0; i < nblk; ++i) {
-                const uint4 a = M.a[i];
+            // One k-mer (lane = taxon).  The loop is a chain of dependent instructions per warp — what it waits for is latency, not issue
+            // slots — so the k-mer's second level and the NEXT k-mer's words are loaded before this k-mer's adds (two register sets,
+            // alternating: no moves); reading one element past a[] / b[] / up[] stays inside DenseWarpMem.
+            auto kmer = [&](const uint32_t i, const uint4 a, const uint32_t uc, const uint4 b) {
                 const float v0 = __uint_as_float(a.z);
-                if (a.x & lbit) { sa = __fadd_rn(sa, v0); fa += a.w; }
-                if (TWO && (a.y & lbit)) { sb = __fadd_rn(sb, v0); fb += a.w; }
-                const uint32_t u = M.up[i];
-                if (u == 0u) continue;
-                if (u == kList) {
+                dense_add(sa, fa, v0, a.w, a.x, lbit);
+                if (TWO) dense_add(sb, fb, v0, a.w, a.y, lbit);
+                if (uc == 0u) return;
+                if (uc == kList) {
                     // list record: level sizes by counting its pairs (every lane, the same values), this lane's taxa looked up on the way
                     const uint4 hd = M.head[i], pw = M.pairs[i];
                     const uint64_t l0 = ((uint64_t)hd.y << 32) | hd.x, l1 = ((uint64_t)hd.w << 32) | hd.z;
@@ -1773,16 +1794,15 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                             if (nn == 1u) atomicAdd(&s_un[j * 64 + lane + 32], 1u); else atomicAdd(&s_fx[j * 64 + lane + 32], (unsigned long long)s_q32[nn]);
                         }
                     }
-                    continue;
+                    return;
                 }
                 {   // level k_low + 1: a second mask
-                    const uint4 b = M.b[i];
                     const float v1 = __uint_as_float(b.z);
-                    if (b.x & lbit) { sa = __fadd_rn(sa, v1); ga += b.w; }
-                    if (TWO && (b.y & lbit)) { sb = __fadd_rn(sb, v1); gb += b.w; }
+                    dense_add(sa, ga, v1, b.w, b.x, lbit);
+                    if (TWO) dense_add(sb, gb, v1, b.w, b.y, lbit);
                 }
-                const uint32_t ud = u & kSeveral;
-                if (ud == 0u) continue;
+                const uint32_t ud = uc & kSeveral;
+                if (ud == 0u) return;
                 if (ud != kSeveral) {
                     const uint32_t c = (ud & 0xffffu) - 1u, h = ud >> 16;                      // h >= 3
                     const bool mine = (c & 31u) == lane;
@@ -1810,6 +1830,20 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                         if (mine) { if (TWO && c >= 32u) sb = x; else sa = x; }
                     }
                 }
+            };
+            uint4 a0 = lds_v4(&M.a[0]), a1;
+            uint32_t u0 = lds_u32(&M.up[0]), u1;
+#pragma unroll 1
+            for (uint32_t i = 0; i < nblk; i += 2) {
+                uint4 b = lds_v4(&M.b[i]);
+                a1 = lds_v4(&M.a[i + 1]);
+                u1 = lds_u32(&M.up[i + 1]);
+                kmer(i, a0, u0, b);
+                if (i + 1 >= nblk) break;
+                b = lds_v4(&M.b[i + 1]);
+                a0 = lds_v4(&M.a[i + 2]);
+                u0 = lds_u32(&M.up[i + 2]);
+                kmer(i + 1, a1, u1, b);
             }
             // a k-mer adds at most 2^23 units to a sum: widen before 32 bits could overflow
             if ((b0 & 255u) == 224u) { fa64 += fa; fb64 += fb; ga64 += ga; gb64 += gb; fa = fb = ga = gb = 0; }
