@@ -1609,6 +1609,22 @@ __device__ __forceinline__ void dense_add(float &score, uint32_t &share, float v
     asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %4, %5;\n\tsetp.ne.u32 p, t, 0;\n\t@p add.rn.f32 %0, %0, %2;\n\t@p add.u32 %1, %1, %3;\n\t}"
         : "+f"(score), "+r"(share) : "f"(v), "r"(q), "r"(mask), "r"(bit));
 }
+// a taxon alone at its levels 2 .. h - 1 (six-level instance; ud = h << 8 | taxon - 1, the same in every lane): the lane that owns the
+// taxon adds the level weights in order; all six levels — a k-mer of the read's own genome — is the straight path
+__device__ __forceinline__ void dense_alone(float &s, uint32_t ud, uint32_t lane, float w2, float w3, float w4, float w5)
+{
+    if (ud >= (6u << 8)) {
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %5, 31;\n\tsetp.eq.u32 p, t, %6;\n\t@p add.rn.f32 %0, %0, %1;\n\t@p add.rn.f32 %0, %0, %2;\n\t"
+            "@p add.rn.f32 %0, %0, %3;\n\t@p add.rn.f32 %0, %0, %4;\n\t}"
+            : "+f"(s) : "f"(w2), "f"(w3), "f"(w4), "f"(w5), "r"(ud), "r"(lane));
+    } else {
+        float x = __fadd_rn(s, w2);
+        if (ud >= (4u << 8)) x = __fadd_rn(x, w3);
+        if (ud >= (5u << 8)) x = __fadd_rn(x, w4);
+        if ((ud & 31u) == lane) s = x;
+    }
+}
+
 // shared-memory loads that stay where they are written (the compiler would sink them to their first use behind a branch)
 __device__ __forceinline__ uint4 lds_v4(const uint4 *p)
 {
@@ -1628,7 +1644,7 @@ struct DenseWarpMem {
     uint4 a[32];              // per k-mer: taxa mask of level k_low (lo, hi), bits of float(w_0 * (1.f / n0)), 2^24 / n0 (0 for n0 < 2)
     uint4 b[32];              // the same for level k_low + 1 (two-mask records, lookup.cuh)
     uint32_t up[32];          // bit 31: b[] is not empty; bits 0..30: 0 = no taxon at three or more levels, 0x7fffffff = several (pairs[],
-                              // val[]), else the only such pair (taxon | levels << 16); 0xfffffffe = list record (head[], pairs[])
+                              // val[]), else the only such pair (taxon - 1 | levels << 8); 0xfffffffe = list record (head[], pairs[])
     uint4 pairs[32];          // .xy = the record's pair word w3 when it holds several pairs; list records: the words w2, w3
     uint4 head[32];           // list records: the words w0, w1
     float val[32][ML <= 6 ? 4 : 24];   // float(w_j * (1.f / n_j)) for the levels j = 2 .. ML - 1 of a record with several pairs
@@ -1673,27 +1689,43 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
     __syncthreads();
     // sums of 1 / n of this lane's taxa (lane + 1, lane + 33) at k_low and k_low + 1, 2^-24 units (shared-memory atomics per k-mer
     // for the second level were measured: + 8 ms per step)
-    unsigned long long fa64 = 0, fb64 = 0, ga64 = 0, gb64 = 0;
+    // (64-bit, widened from the per-read 32-bit registers; in shared memory, one private word per warp, sum and lane: registers are
+    // what keeps three CTAs on an SM)
+    __shared__ unsigned long long s_acc[kBlkWarps][4][32];
+    for (int i = tid; i < kBlkWarps * 4 * 32; i += blockDim.x) (&s_acc[0][0][0])[i] = 0;
     const uint32_t lbit = 1u << lane;
     constexpr uint32_t kList = 0xfffffffeu, kSeveral = 0x7fffffffu;
 
     const uint32_t warps_total = gridDim.x * kBlkWarps;
+    // The records of a read arrive one block of 32 ahead of their use, and the first block of the warp's NEXT read is fetched during
+    // the last block of the current one (its offsets at the start of the current one): no load latency lies bare between reads.
+    uint32_t r = blockIdx.x * kBlkWarps + w;
+    uint64_t s0 = 0;
+    uint32_t ni = 0;
+    if (r < n_reads) { s0 = read_koff[r]; ni = (uint32_t)(read_koff[r + 1] - s0); }
+    uint64_t nx[4] = {0, 0, 0, 0};
+    if (lane < ni) asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(rec + (s0 + lane) * kRecWords));
 #pragma unroll 1
-    for (uint32_t r = blockIdx.x * kBlkWarps + w; r < n_reads; r += warps_total) {
-        const uint64_t s0 = read_koff[r];
-        const uint32_t ni = (uint32_t)(read_koff[r + 1] - s0);
+    for (; r < n_reads; r += warps_total) {
+        const uint32_t rn = r + warps_total;
+        uint64_t s0n = 0;
+        uint32_t nin = 0;
+        if (rn < n_reads) { s0n = __ldg(read_koff + rn); nin = (uint32_t)(__ldg(read_koff + rn + 1) - s0n); }
         const uint64_t *p = rec + s0 * kRecWords;
         float sa = 0.f, sb = 0.f;
         uint32_t fa = 0, fb = 0, ga = 0, gb = 0;
-        uint64_t nx[4] = {0, 0, 0, 0};
-        if (lane < ni) asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(p + (uint64_t)lane * kRecWords));
+        if (ni == 0 && lane < nin) asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(rec + (s0n + lane) * kRecWords));
 #pragma unroll 1
         for (uint32_t b0 = 0; b0 < ni; b0 += 32) {
             // ---- setup, lane = k-mer b0 + lane
             const uint64_t w0 = nx[0], w1 = nx[1], w2 = nx[2], w3 = nx[3];
             nx[0] = nx[1] = nx[2] = nx[3] = 0;
-            if (b0 + 32 + lane < ni)
-                asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(p + (uint64_t)(b0 + 32 + lane) * kRecWords));
+            {
+                const bool last = b0 + 32 >= ni;
+                const uint64_t *q = last ? rec + (s0n + lane) * kRecWords : p + (uint64_t)(b0 + 32 + lane) * kRecWords;
+                if (last ? lane < nin : b0 + 32 + lane < ni)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(nx[0]), "=l"(nx[1]), "=l"(nx[2]), "=l"(nx[3]) : "l"(q));
+            }
             const uint32_t n0 = rec_count(w0), hmax = rec_hmax(w0);
             uint64_t mk = n0 ? w1 : 0ull, m1 = 0;
             uint32_t upd = 0;
@@ -1719,7 +1751,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                 upd = m1 ? 0x80000000u : 0u;
                 const uint32_t e0 = m1 ? (uint32_t)w3 & kPairMask : 0u;
                 if (e0 && (w3 >> kPairBits) == 0) {
-                    upd |= e0;                                                                // the usual case: one taxon, alone at its levels 2 ..
+                    upd |= ((e0 >> 16) << 8) | ((e0 & 0xffffu) - 1u);                         // the usual case: one taxon, alone at its levels 2 ..
                     atomicAdd(&s_hist[((e0 & 0xffffu) - 1u) * 32 + ((e0 >> 16) & 31u)], 1u);
                 } else if (e0) {
                     // several taxa at three or more levels: level sizes (nibbles), level values, counts
@@ -1804,18 +1836,18 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                 const uint32_t ud = uc & kSeveral;
                 if (ud == 0u) return;
                 if (ud != kSeveral) {
-                    const uint32_t c = (ud & 0xffffu) - 1u, h = ud >> 16;                      // h >= 3
-                    const bool mine = (c & 31u) == lane;
-                    float x = (TWO && c >= 32u) ? sb : sa;
+                    // the usual case (a read's own taxon): one taxon, alone at its levels 2 .. h - 1; ud = h << 8 | (taxon - 1), h >= 3:
+                    // w * (1.f / 1) == w joins the sum of the lane (ud & 31), in sa or (bit 5) sb
                     if (ML <= 6) {
-                        x = __fadd_rn(x, wj[2]);                                               // alone there: w * (1.f / 1) == w
-                        if (h > 3u) x = __fadd_rn(x, wj[3]);
-                        if (h > 4u) x = __fadd_rn(x, wj[4]);
-                        if (h > 5u) x = __fadd_rn(x, wj[5]);
+                        if (TWO && (ud & 32u)) dense_alone(sb, ud, lane, wj[2], wj[3], wj[4], wj[5]);
+                        else dense_alone(sa, ud, lane, wj[2], wj[3], wj[4], wj[5]);
                     } else {
-                        for (uint32_t j = 2; j < h; ++j) x = __fadd_rn(x, s_wl[j]);            // (h is the same in every lane)
+                        const bool mine = (ud & 31u) == lane;
+                        const uint32_t h = ud >> 8;                                            // (the same in every lane)
+                        float x = (TWO && (ud & 32u)) ? sb : sa;
+                        for (uint32_t j = 2; j < h; ++j) x = __fadd_rn(x, s_wl[j]);
+                        if (mine) { if (TWO && (ud & 32u)) sb = x; else sa = x; }
                     }
-                    if (mine) { if (TWO && c >= 32u) sb = x; else sa = x; }
                 } else {
                     const uint4 pw = M.pairs[i];
                     const uint64_t p3 = ((uint64_t)pw.y << 32) | pw.x;
@@ -1846,24 +1878,28 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                 kmer(i + 1, a1, u1, b);
             }
             // a k-mer adds at most 2^23 units to a sum: widen before 32 bits could overflow
-            if ((b0 & 255u) == 224u) { fa64 += fa; fb64 += fb; ga64 += ga; gb64 += gb; fa = fb = ga = gb = 0; }
+            if ((b0 & 255u) == 224u) { s_acc[w][0][lane] += fa; s_acc[w][1][lane] += fb; s_acc[w][2][lane] += ga; s_acc[w][3][lane] += gb; fa = fb = ga = gb = 0; }
             __syncwarp();
         }
-        fa64 += fa; fb64 += fb; ga64 += ga; gb64 += gb;
+        s_acc[w][0][lane] += fa; s_acc[w][1][lane] += fb; s_acc[w][2][lane] += ga; s_acc[w][3][lane] += gb;
         if (scores) {
             float *row = scores + (uint64_t)r * T;
             if (lane == 0) row[0] = 0.f;
             if ((int)lane + 1 < T) row[lane + 1] = sa;
             if (TWO && (int)lane + 33 < T) row[lane + 33] = sb;
         }
+        s0 = s0n; ni = nin;
     }
-    if ((int)lane + 1 < T) {
-        if (fa64) atomicAdd(&s_fx[lane], fa64 << kFxShift);
-        if (ga64) atomicAdd(&s_fx[64 + lane], ga64 << kFxShift);
-    }
-    if (TWO && (int)lane + 33 < T) {
-        if (fb64) atomicAdd(&s_fx[lane + 32], fb64 << kFxShift);
-        if (gb64) atomicAdd(&s_fx[64 + lane + 32], gb64 << kFxShift);
+    {
+        const unsigned long long fa64 = s_acc[w][0][lane], fb64 = s_acc[w][1][lane], ga64 = s_acc[w][2][lane], gb64 = s_acc[w][3][lane];
+        if ((int)lane + 1 < T) {
+            if (fa64) atomicAdd(&s_fx[lane], fa64 << kFxShift);
+            if (ga64) atomicAdd(&s_fx[64 + lane], ga64 << kFxShift);
+        }
+        if (TWO && (int)lane + 33 < T) {
+            if (fb64) atomicAdd(&s_fx[lane + 32], fb64 << kFxShift);
+            if (gb64) atomicAdd(&s_fx[64 + lane + 32], gb64 << kFxShift);
+        }
     }
     __syncthreads();
     for (int i = tid; i < NK * 64; i += blockDim.x) {
