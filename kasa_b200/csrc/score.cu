@@ -1609,20 +1609,13 @@ __device__ __forceinline__ void dense_add(float &score, uint32_t &share, float v
     asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %4, %5;\n\tsetp.ne.u32 p, t, 0;\n\t@p add.rn.f32 %0, %0, %2;\n\t@p add.u32 %1, %1, %3;\n\t}"
         : "+f"(score), "+r"(share) : "f"(v), "r"(q), "r"(mask), "r"(bit));
 }
-// a taxon alone at its levels 2 .. h - 1 (six-level instance; ud = h << 8 | taxon - 1, the same in every lane): the lane that owns the
-// taxon adds the level weights in order; all six levels — a k-mer of the read's own genome — is the straight path
-__device__ __forceinline__ void dense_alone(float &s, uint32_t ud, uint32_t lane, float w2, float w3, float w4, float w5)
+// a taxon alone at the levels 2 .. 5 of the six-level instance (uc & 31 = the lane that holds its sum; the same uc in every lane): the
+// level weights join that sum in order
+__device__ __forceinline__ void dense_all(float &s, uint32_t uc, uint32_t lane, float w2, float w3, float w4, float w5)
 {
-    if (ud >= (6u << 8)) {
-        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %5, 31;\n\tsetp.eq.u32 p, t, %6;\n\t@p add.rn.f32 %0, %0, %1;\n\t@p add.rn.f32 %0, %0, %2;\n\t"
-            "@p add.rn.f32 %0, %0, %3;\n\t@p add.rn.f32 %0, %0, %4;\n\t}"
-            : "+f"(s) : "f"(w2), "f"(w3), "f"(w4), "f"(w5), "r"(ud), "r"(lane));
-    } else {
-        float x = __fadd_rn(s, w2);
-        if (ud >= (4u << 8)) x = __fadd_rn(x, w3);
-        if (ud >= (5u << 8)) x = __fadd_rn(x, w4);
-        if ((ud & 31u) == lane) s = x;
-    }
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %5, 31;\n\tsetp.eq.u32 p, t, %6;\n\t@p add.rn.f32 %0, %0, %1;\n\t@p add.rn.f32 %0, %0, %2;\n\t"
+        "@p add.rn.f32 %0, %0, %3;\n\t@p add.rn.f32 %0, %0, %4;\n\t}"
+        : "+f"(s) : "f"(w2), "f"(w3), "f"(w4), "f"(w5), "r"(uc), "r"(lane));
 }
 
 // shared-memory loads that stay where they are written (the compiler would sink them to their first use behind a branch)
@@ -1639,12 +1632,18 @@ __device__ __forceinline__ uint32_t lds_u32(const uint32_t *p)
     return r;
 }
 
+struct DenseKmer {            // 48 bytes: one address register reaches a, b and up of the k-mers i, i + 1, i + 2
+    uint4 a;                  // taxa mask of level k_low (lo, hi), bits of float(w_0 * (1.f / n0)), 2^24 / n0 (0 for n0 < 2)
+    uint4 b;                  // the same for level k_low + 1 (two-mask records, lookup.cuh)
+    uint32_t up;              // what the k-mer adds above level k_low (kUp*): 0 = nothing; kUpMask = b only; with b: kUpAllA | lane / kUpAllB | lane = one taxon alone
+                              // at the levels 2 .. 5 of the six-level instance, held by this lane in sa / sb (a read's own taxon); kUpOne |
+                              // levels << 8 | taxon - 1 = one taxon alone at its levels 2 .. h - 1; kUpSeveral (pairs[], val[]); kUpList
+                              // (list record: head[], pairs[], every level above k_low)
+    uint32_t pad[3];
+};
 template <int ML>
 struct DenseWarpMem {
-    uint4 a[32];              // per k-mer: taxa mask of level k_low (lo, hi), bits of float(w_0 * (1.f / n0)), 2^24 / n0 (0 for n0 < 2)
-    uint4 b[32];              // the same for level k_low + 1 (two-mask records, lookup.cuh)
-    uint32_t up[32];          // bit 31: b[] is not empty; bits 0..30: 0 = no taxon at three or more levels, 0x7fffffff = several (pairs[],
-                              // val[]), else the only such pair (taxon - 1 | levels << 8); 0xfffffffe = list record (head[], pairs[])
+    DenseKmer k[33];          // (k[32]: the loop loads one k-mer ahead)
     uint4 pairs[32];          // .xy = the record's pair word w3 when it holds several pairs; list records: the words w2, w3
     uint4 head[32];           // list records: the words w0, w1
     float val[32][ML <= 6 ? 4 : 24];   // float(w_j * (1.f / n_j)) for the levels j = 2 .. ML - 1 of a record with several pairs
@@ -1694,7 +1693,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
     __shared__ unsigned long long s_acc[kBlkWarps][4][32];
     for (int i = tid; i < kBlkWarps * 4 * 32; i += blockDim.x) (&s_acc[0][0][0])[i] = 0;
     const uint32_t lbit = 1u << lane;
-    constexpr uint32_t kList = 0xfffffffeu, kSeveral = 0x7fffffffu;
+    constexpr uint32_t kUpAllA = 0xE0000000u, kUpAllB = 0xC0000000u, kUpOne = 0x40000000u, kUpSeveral = 0x20000000u, kUpList = 0x10000000u, kUpMask = 0x08000000u;
 
     const uint32_t warps_total = gridDim.x * kBlkWarps;
     // The records of a read arrive one block of 32 ahead of their use, and the first block of the warp's NEXT read is fetched during
@@ -1739,7 +1738,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                     mk |= 1ull << ((e & 0xffffu) - 1u);
                 }
                 if (hmax > 1u) {
-                    upd = kList;
+                    upd = kUpList;
                     M.head[lane] = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
                     M.pairs[lane] = make_uint4((uint32_t)w2, (uint32_t)(w2 >> 32), (uint32_t)w3, (uint32_t)(w3 >> 32));
                 }
@@ -1748,10 +1747,12 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                 m1 = w2;
                 const uint32_t n1 = (uint32_t)__popcll(m1);
                 if (n1 == 1u) atomicAdd(&s_un[64 + __ffsll((long long)m1) - 1], 1u);           // alone at k_low + 1
-                upd = m1 ? 0x80000000u : 0u;
+                upd = m1 ? kUpMask : 0u;
                 const uint32_t e0 = m1 ? (uint32_t)w3 & kPairMask : 0u;
                 if (e0 && (w3 >> kPairBits) == 0) {
-                    upd |= ((e0 >> 16) << 8) | ((e0 & 0xffffu) - 1u);                         // the usual case: one taxon, alone at its levels 2 ..
+                    // the usual case: one taxon, alone at its levels 2 ..
+                    const uint32_t c0 = (e0 & 0xffffu) - 1u, h0 = e0 >> 16;
+                    upd = (ML <= 6 && h0 == 6u) ? ((c0 & 32u) ? kUpAllB : kUpAllA) | (c0 & 31u) : kUpOne | (h0 << 8) | c0;
                     atomicAdd(&s_hist[((e0 & 0xffffu) - 1u) * 32 + ((e0 >> 16) & 31u)], 1u);
                 } else if (e0) {
                     // several taxa at three or more levels: level sizes (nibbles), level values, counts
@@ -1771,31 +1772,52 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                             else atomicAdd(&s_fx[j * 64 + c], (unsigned long long)s_q32[nn]);
                         }
                     }
-                    upd |= kSeveral;
+                    upd = kUpSeveral;
                 }
             }
             if (n0 == 1u && mk) atomicAdd(&s_un[__ffsll((long long)mk) - 1], 1u);             // alone at k_low: a unique hit
             {
                 const float2 vq = s_vq0[n0 < 72u ? n0 : 0u];
-                M.a[lane] = make_uint4((uint32_t)mk, (uint32_t)(mk >> 32), __float_as_uint(vq.x), __float_as_uint(vq.y));
-                if (m1) {
-                    const float2 v1 = s_vq1[__popcll(m1)];
-                    M.b[lane] = make_uint4((uint32_t)m1, (uint32_t)(m1 >> 32), __float_as_uint(v1.x), __float_as_uint(v1.y));
+                M.k[lane].a = make_uint4((uint32_t)mk, (uint32_t)(mk >> 32), __float_as_uint(vq.x), __float_as_uint(vq.y));
+                {
+                    const float2 v1 = s_vq1[__popcll(m1)];                                    // (an empty mask adds nothing)
+                    M.k[lane].b = make_uint4((uint32_t)m1, (uint32_t)(m1 >> 32), __float_as_uint(v1.x), __float_as_uint(v1.y));
                 }
-                M.up[lane] = upd;
+                M.k[lane].up = upd;
             }
             __syncwarp();
             // ---- main, lane = taxon: the block's k-mers in order (Compare.hpp:530 for level k_low, then the levels above)
             const uint32_t nblk = min(32u, ni - b0);
             // One k-mer (lane = taxon).  The loop is a chain of dependent instructions per warp — what it waits for is latency, not issue
             // slots — so the k-mer's second level and the NEXT k-mer's words are loaded before this k-mer's adds (two register sets,
-            // alternating: no moves); reading one element past a[] / b[] / up[] stays inside DenseWarpMem.
+            // alternating: no moves).
             auto kmer = [&](const uint32_t i, const uint4 a, const uint32_t uc, const uint4 b) {
                 const float v0 = __uint_as_float(a.z);
                 dense_add(sa, fa, v0, a.w, a.x, lbit);
                 if (TWO) dense_add(sb, fb, v0, a.w, a.y, lbit);
-                if (uc == 0u) return;
-                if (uc == kList) {
+                if (uc == 0u) return;                                   // more than half of C2's k-mers: no taxon above k_low
+                {   // level k_low + 1: a second mask (empty in a list record)
+                    const float v1 = __uint_as_float(b.z);
+                    dense_add(sa, ga, v1, b.w, b.x, lbit);
+                    if (TWO) dense_add(sb, gb, v1, b.w, b.y, lbit);
+                }
+                if (ML <= 6 && uc >= kUpAllB) {
+                    // a read's own taxon, alone at the levels 2 .. 5: w * (1.f / 1) == w joins the sum of the lane (uc & 31), in sa or sb
+                    if (!TWO || uc >= kUpAllA) dense_all(sa, uc, lane, wj[2], wj[3], wj[4], wj[5]);
+                    else dense_all(sb, uc, lane, wj[2], wj[3], wj[4], wj[5]);
+                    return;
+                }
+                if (uc == kUpMask) return;
+                if (uc & kUpOne) {
+                    // one taxon alone at its levels 2 .. h - 1 (h >= 3, the same in every lane)
+                    const bool mine = (uc & 31u) == lane;
+                    const uint32_t h = (uc >> 8) & 31u;
+                    float x = (TWO && (uc & 32u)) ? sb : sa;
+                    for (uint32_t j = 2; j < h; ++j) x = __fadd_rn(x, s_wl[j]);
+                    if (mine) { if (TWO && (uc & 32u)) sb = x; else sa = x; }
+                    return;
+                }
+                if (uc == kUpList) {
                     // list record: level sizes by counting its pairs (every lane, the same values), this lane's taxa looked up on the way
                     const uint4 hd = M.head[i], pw = M.pairs[i];
                     const uint64_t l0 = ((uint64_t)hd.y << 32) | hd.x, l1 = ((uint64_t)hd.w << 32) | hd.z;
@@ -1828,27 +1850,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                     }
                     return;
                 }
-                {   // level k_low + 1: a second mask
-                    const float v1 = __uint_as_float(b.z);
-                    dense_add(sa, ga, v1, b.w, b.x, lbit);
-                    if (TWO) dense_add(sb, gb, v1, b.w, b.y, lbit);
-                }
-                const uint32_t ud = uc & kSeveral;
-                if (ud == 0u) return;
-                if (ud != kSeveral) {
-                    // the usual case (a read's own taxon): one taxon, alone at its levels 2 .. h - 1; ud = h << 8 | (taxon - 1), h >= 3:
-                    // w * (1.f / 1) == w joins the sum of the lane (ud & 31), in sa or (bit 5) sb
-                    if (ML <= 6) {
-                        if (TWO && (ud & 32u)) dense_alone(sb, ud, lane, wj[2], wj[3], wj[4], wj[5]);
-                        else dense_alone(sa, ud, lane, wj[2], wj[3], wj[4], wj[5]);
-                    } else {
-                        const bool mine = (ud & 31u) == lane;
-                        const uint32_t h = ud >> 8;                                            // (the same in every lane)
-                        float x = (TWO && (ud & 32u)) ? sb : sa;
-                        for (uint32_t j = 2; j < h; ++j) x = __fadd_rn(x, s_wl[j]);
-                        if (mine) { if (TWO && (ud & 32u)) sb = x; else sa = x; }
-                    }
-                } else {
+                {   // several taxa at three or more levels
                     const uint4 pw = M.pairs[i];
                     const uint64_t p3 = ((uint64_t)pw.y << 32) | pw.x;
 #pragma unroll
@@ -1863,18 +1865,18 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                     }
                 }
             };
-            uint4 a0 = lds_v4(&M.a[0]), a1;
-            uint32_t u0 = lds_u32(&M.up[0]), u1;
+            uint4 a0 = lds_v4(&M.k[0].a), a1;
+            uint32_t u0 = lds_u32(&M.k[0].up), u1;
 #pragma unroll 1
             for (uint32_t i = 0; i < nblk; i += 2) {
-                uint4 b = lds_v4(&M.b[i]);
-                a1 = lds_v4(&M.a[i + 1]);
-                u1 = lds_u32(&M.up[i + 1]);
+                uint4 b = lds_v4(&M.k[i].b);
+                a1 = lds_v4(&M.k[i + 1].a);
+                u1 = lds_u32(&M.k[i + 1].up);
                 kmer(i, a0, u0, b);
                 if (i + 1 >= nblk) break;
-                b = lds_v4(&M.b[i + 1]);
-                a0 = lds_v4(&M.a[i + 2]);
-                u0 = lds_u32(&M.up[i + 2]);
+                b = lds_v4(&M.k[i + 1].b);
+                a0 = lds_v4(&M.k[i + 2].a);
+                u0 = lds_u32(&M.k[i + 2].up);
                 kmer(i + 1, a1, u1, b);
             }
             // a k-mer adds at most 2^23 units to a sum: widen before 32 bits could overflow
