@@ -1618,6 +1618,18 @@ __device__ __forceinline__ void dense_all(float &s, uint32_t uc, uint32_t lane, 
         : "+f"(s) : "f"(w2), "f"(w3), "f"(w4), "f"(w5), "r"(uc), "r"(lane));
 }
 
+// the same for a taxon alone at the levels 2 .. h - 1, 3 <= h <= 6 (uc bits 8..12 = h)
+__device__ __forceinline__ void dense_some(float &s, uint32_t uc, uint32_t lane, float w2, float w3, float w4, float w5)
+{
+    const uint32_t h = uc & 0x1f00u;
+    if ((uc & 31u) == lane) {
+        s = __fadd_rn(s, w2);
+        if (h > (3u << 8)) s = __fadd_rn(s, w3);
+        if (h > (4u << 8)) s = __fadd_rn(s, w4);
+        if (h > (5u << 8)) s = __fadd_rn(s, w5);
+    }
+}
+
 // shared-memory loads that stay where they are written (the compiler would sink them to their first use behind a branch)
 __device__ __forceinline__ uint4 lds_v4(const uint4 *p)
 {
@@ -1809,12 +1821,17 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                 }
                 if (uc == kUpMask) return;
                 if (uc & kUpOne) {
-                    // one taxon alone at its levels 2 .. h - 1 (h >= 3, the same in every lane)
-                    const bool mine = (uc & 31u) == lane;
-                    const uint32_t h = (uc >> 8) & 31u;
-                    float x = (TWO && (uc & 32u)) ? sb : sa;
-                    for (uint32_t j = 2; j < h; ++j) x = __fadd_rn(x, s_wl[j]);
-                    if (mine) { if (TWO && (uc & 32u)) sb = x; else sa = x; }
+                    // one taxon alone at its levels 2 .. h - 1 (h >= 3, the same in every lane; uc = kUpOne | h << 8 | taxon - 1)
+                    if (ML <= 6) {
+                        if (TWO && (uc & 32u)) dense_some(sb, uc, lane, wj[2], wj[3], wj[4], wj[5]);
+                        else dense_some(sa, uc, lane, wj[2], wj[3], wj[4], wj[5]);
+                    } else {
+                        const bool mine = (uc & 31u) == lane;
+                        const uint32_t h = (uc >> 8) & 31u;
+                        float x = (TWO && (uc & 32u)) ? sb : sa;
+                        for (uint32_t j = 2; j < h; ++j) x = __fadd_rn(x, s_wl[j]);
+                        if (mine) { if (TWO && (uc & 32u)) sb = x; else sa = x; }
+                    }
                     return;
                 }
                 if (uc == kUpList) {
