@@ -1630,6 +1630,17 @@ __device__ __forceinline__ void dense_some(float &s, uint32_t uc, uint32_t lane,
     }
 }
 
+// a taxon among several at three or more levels (six-level instance): the lane that holds its sum adds the level values in order
+__device__ __forceinline__ void dense_vals(float &s, uint32_t c, uint32_t h, uint32_t lane, float4 v)
+{
+    if ((c & 31u) == lane) {
+        s = __fadd_rn(s, v.x);                                                                 // h >= 3
+        if (h > 3u) s = __fadd_rn(s, v.y);
+        if (h > 4u) s = __fadd_rn(s, v.z);
+        if (h > 5u) s = __fadd_rn(s, v.w);
+    }
+}
+
 // shared-memory loads that stay where they are written (the compiler would sink them to their first use behind a branch)
 __device__ __forceinline__ uint4 lds_v4(const uint4 *p)
 {
@@ -1870,15 +1881,20 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
                 {   // several taxa at three or more levels
                     const uint4 pw = M.pairs[i];
                     const uint64_t p3 = ((uint64_t)pw.y << 32) | pw.x;
+                    const float4 vv = *reinterpret_cast<const float4 *>(&M.val[i][0]);          // (six-level instance: the values of the levels 2 .. 5)
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         const uint32_t e = (uint32_t)(p3 >> (kPairBits * k)) & kPairMask;
                         if (!e) break;                                                         // uniform: pairs fill from slot 0
                         const uint32_t c = (e & 0xffffu) - 1u, h = e >> 16;
-                        const bool mine = (c & 31u) == lane;
-                        float x = (TWO && c >= 32u) ? sb : sa;
-                        for (uint32_t j = 2; j < h && j < (uint32_t)ML; ++j) x = __fadd_rn(x, M.val[i][j - 2]);
-                        if (mine) { if (TWO && c >= 32u) sb = x; else sa = x; }
+                        if (ML <= 6) {
+                            if (TWO && c >= 32u) dense_vals(sb, c, h, lane, vv); else dense_vals(sa, c, h, lane, vv);
+                        } else {
+                            const bool mine = (c & 31u) == lane;
+                            float x = (TWO && c >= 32u) ? sb : sa;
+                            for (uint32_t j = 2; j < h && j < (uint32_t)ML; ++j) x = __fadd_rn(x, M.val[i][j - 2]);
+                            if (mine) { if (TWO && c >= 32u) sb = x; else sa = x; }
+                        }
                     }
                 }
             };
