@@ -229,7 +229,7 @@ def workload_config(args, reads_per_step):
 # DRAM bytes per k-mer (dram__bytes_read.sum + dram__bytes_write.sum of one launch / k-mers of the launch) from the committed ncu
 # captures at this workload's full size (profiles/r02_ncu_*.txt; the radix pass from profiles/r01_ncu_onesweep_kernel.txt)
 NCU_DRAM_BYTES = {"extract": (1.142314e9 + 20.847225e9) / 1.742e9, "sort_pass": (3.195906e9 + 3.357949e9) / 2.6e8,
-                  "lookup": (51.864335e9 + 76.196481e9) / 1.742e9, "score": (55.979076e9 + 1.442398e9) / 1.742e9}
+                  "lookup": (51.864335e9 + 76.196481e9) / 1.742e9, "score": (55.928244e9 + 1.429569e9) / 1.742e9}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
