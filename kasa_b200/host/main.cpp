@@ -8,6 +8,7 @@
 #include <chrono>
 #include <iostream>
 #include <memory>
+#include <unordered_set>
 
 #include "../../include/kasa_b200.h"
 #include "kasa_host.hpp"
@@ -48,7 +49,7 @@ struct Pinned {
 };
 
 struct Args {
-    std::string mode, content, index, input, in1, in2, profile, rtt, tmp, alphabet_file, alphabet_id;
+    std::string mode, content, index, input, in1, in2, profile, rtt, tmp, alphabet_file, alphabet_id, out, first_index, second_index, deleted, content_out;
     int k_high = 12, k_low = 7, highest_k = 12, beasts = 3, device = 0, gpus = 1;
     bool six = false, one = false, verbose = false, exact = false;
     float threshold = 0.f;
@@ -60,6 +61,8 @@ struct Args {
 [[noreturn]] void usage()
 {
     std::cout << "kasa_b200 <build|identify> -c <content> -d <index> [-i <input> | -1 <fq> -2 <fq>] [-p <profile.csv>] [-q <per-read out>]\n"
+                 "kasa_b200 trie -d <index> | getFrequency -c <content> -d <index> | delete -c <content> -d <index> -o <out> -l <delnodes.dmp>\n"
+                 "          | merge -c <content> --firstIndex <a> --secondIndex <b> -o <out>     (indexes sharing one content file)\n"
                  "          [-k <high> <low>] [--kH <12|25>] [--six | --one] [--json|--jsonl|--tsv|--kraken] [-b <n>] [--threshold <f>] [-v]\n"
                  "          [-a <gc.prt> <id>]\n"
                  "          [--exact-scores] [--device <n>] [--gpus <n>] [--batch-reads <n>] [--batch-bases <n>]   (-m -n -t -r -x are accepted and ignored)\n";
@@ -77,6 +80,12 @@ Args parse(int argc, char **argv)
         if (p == "-c" || p == "--content") a.content = next();
         else if (p == "-d" || p == "--database") a.index = next();
         else if (p == "-i" || p == "--input") a.input = next();
+        else if (p == "-o" || p == "--outgoing") a.out = next();
+        else if (p == "--firstIndex") a.first_index = next();
+        else if (p == "--secondIndex") a.second_index = next();
+        else if (p == "-l" || p == "--deleted") a.deleted = next();
+        else if (p == "-co") a.content_out = next();
+        else if (p == "-c1" || p == "-c2") { const std::string c = next(); if (a.content.empty()) a.content = c; }
         else if (p == "-1") a.in1 = next();
         else if (p == "-2") a.in2 = next();
         else if (p == "-p" || p == "--profile") a.profile = next();
@@ -134,6 +143,135 @@ bool load_codon_table(const std::string &file, const std::string &id, uint8_t ta
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------ index files
+enum { kWriteIndex = 1, kWriteTrie = 2, kWriteFrequency = 4, kWriteAll = 7 };
+
+// kasa_build_finish + the files of an index: <out>, <out>_info.txt (Build.hpp:466-470), <out>_trie, <out>_trie.txt (Trie.hpp:387-388),
+// <out>_f.txt (kASA.hpp:549-570)
+void finish_and_write(kasa_ctx *ctx, const std::string &out, int K, const Content &content, const std::string &content_path, int what)
+{
+    uint64_t n = 0, nt = 0;
+    check(kasa_build_finish(ctx, &n, &nt), ctx);
+    const size_t rec = K > 12 ? 20 : 12, block = K > 12 ? 2048000 : 2101248;
+    if (what & (kWriteIndex | kWriteTrie)) {
+        std::vector<char> entries(n * rec), trie(nt * 12);
+        check(kasa_build_fetch(ctx, entries.data(), trie.data()), ctx);
+        if (what & kWriteIndex) {
+            write_padded(out, entries.data(), entries.size(), block);
+            std::ofstream f(out + "_info.txt");
+            f << n;
+            if (K > 12) f << std::endl << 128;
+        }
+        if (what & kWriteTrie) {
+            write_padded(out + "_trie", trie.data(), trie.size(), 2101248);
+            std::ofstream f(out + "_trie.txt");
+            f << nt;
+        }
+    }
+    if (what & kWriteFrequency) {
+        std::vector<uint64_t> freq(content.taxids.size() * (size_t)K);
+        check(kasa_build_frequency(ctx, content.taxids.data(), (uint32_t)content.taxids.size(), freq.data()), ctx);
+        std::ofstream f(out + "_f.txt");
+        std::ifstream cf(content_path);
+        f << "non_unique";
+        for (int k = 0; k < K; ++k) f << "\t" << freq[k];
+        f << std::endl;
+        std::string line;
+        for (size_t j = 1; j < content.taxids.size() && std::getline(cf, line);) {
+            if (line.empty()) continue;
+            f << split(line, '\t')[0] << "\t" << freq[j * K];
+            for (int k = 1; k < K; ++k) f << "\t" << freq[j * K + k];
+            f << std::endl;
+            ++j;
+        }
+    }
+}
+
+// the records of an index file: <idx>_info.txt = count [\n 128 | 3] (main.cpp:982-991)
+std::vector<char> read_index_records(const std::string &path, int *bits)
+{
+    std::ifstream info(path + "_info.txt");
+    if (!info) throw std::runtime_error("Info file for this index can not be found!");
+    uint64_t n = 0;
+    std::string tok;
+    info >> n;
+    *bits = 64;
+    if (info >> tok) {
+        if (tok == "128") *bits = 128;
+        else if (tok == "3") throw std::runtime_error("Halved indices cannot be modified in this way. Sorry...");      // main.cpp:787
+    }
+    std::vector<char> rec(n * (*bits == 128 ? 20 : 12));
+    std::ifstream f(path, std::ios::binary);
+    if (!f || !f.read(rec.data(), (std::streamsize)rec.size())) throw std::runtime_error("Library file does not exist or is shorter than its info file says: " + path);
+    return rec;
+}
+
+// trie / getFrequency / delete / merge (main.cpp:1422-1458, 1336-1362, 770-805, 877-977): an index file's records join a build on the
+// device (kasa_build_push_index), whose finish is the merge, the prefix table and the frequencies.
+//   trie          rewrites <index>_trie, <index>_trie.txt
+//   getFrequency  rewrites <index>_f.txt
+//   delete        <out> = <index> without the records of the taxids listed in the first column of -l (Update.hpp:28-94)
+//   merge         <out> = --firstIndex + --secondIndex, both built with the content file -c (Read.hpp:3180-3243; the reference writes no
+//                 <out>_info.txt and, for want of it, a frequency file of zeros: here both are written properly)
+int run_index_mode(const Args &a)
+{
+    const bool merge = a.mode == "merge", del = a.mode == "delete";
+    const std::string first = merge ? a.first_index : a.index;
+    if (first.empty()) throw std::runtime_error("No index given!");
+    if ((merge || del) && a.out.empty()) throw std::runtime_error("No output file given!");
+    if (merge && a.first_index == a.second_index) throw std::runtime_error("-d and -i must point to different indices!");
+    if (merge && (a.out == a.first_index || a.out == a.second_index)) throw std::runtime_error("You can't overwrite indices (yet)!");
+    int bits = 64, bits2 = 64;
+    std::vector<char> rec = read_index_records(first, &bits), rec2;
+    if (merge) {
+        rec2 = read_index_records(a.second_index, &bits2);
+        if (bits != bits2) throw std::runtime_error("Indices are not of the same format!");
+    }
+    const int K = bits == 128 ? 25 : 12;
+    const size_t rb = bits == 128 ? 20 : 12;
+    Content content;
+    const std::string content_path = !a.content.empty() ? a.content : first + "_content.txt";
+    if (a.mode != "trie") content = load_content(content_path);
+    if (del) {
+        std::ifstream f(a.deleted);
+        if (!f) throw std::runtime_error("delnodes.dmp not found");
+        std::unordered_set<uint32_t> gone;
+        std::string line;
+        while (std::getline(f, line))
+            if (!line.empty()) gone.insert((uint32_t)std::stoul(split(line, '\t')[0]));
+        size_t w = 0;                                      // the taxid is the last four bytes of a record (packedPairs.hpp:100-166)
+        for (size_t r = 0; r + rb <= rec.size(); r += rb) {
+            uint32_t t;
+            std::memcpy(&t, rec.data() + r + rb - 4, 4);
+            if (gone.count(t)) continue;
+            if (w != r) std::memmove(rec.data() + w, rec.data() + r, rb);
+            w += rb;
+        }
+        rec.resize(w);
+    }
+    kasa_params p{};
+    p.device = a.device; p.highest_k = K; p.k_high = K; p.k_low = std::min(7, K); p.frames = 3;
+    p.score_mode = KASA_SCORE_NONE;
+    const uint64_t total = (rec.size() + rec2.size()) / rb;
+    p.max_batch_kmers = std::min<uint64_t>(std::max<uint64_t>(total + (1u << 20), 1u << 22), (1ull << 32) - (1u << 20));
+    p.max_batch_seqs = 1u << 10;
+    p.max_batch_bases = 1u << 20;
+    kasa_ctx *ctx = nullptr;
+    check(kasa_ctx_create(&p, &ctx), nullptr);
+    check(kasa_build_push_index(ctx, rec.data(), rec.size() / rb, bits), ctx);
+    if (merge) check(kasa_build_push_index(ctx, rec2.data(), rec2.size() / rb, bits), ctx);
+    const std::string out = (merge || del) ? a.out : a.index;
+    const int what = a.mode == "trie" ? kWriteTrie : a.mode == "getFrequency" ? kWriteFrequency : kWriteAll;
+    finish_and_write(ctx, out, K, content, content_path, what);
+    if (merge && !a.content_out.empty() && a.content_out != content_path) {        // -co: the merged content file = the shared one
+        std::ifstream src(content_path, std::ios::binary);
+        std::ofstream dst(a.content_out, std::ios::binary);
+        dst << src.rdbuf();
+    }
+    kasa_ctx_destroy(ctx);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ build
 int run_build(const Args &a)
 {
@@ -170,36 +308,7 @@ int run_build(const Args &a)
         chars += s;
     });
     flush();
-    uint64_t n = 0, nt = 0;
-    check(kasa_build_finish(ctx, &n, &nt), ctx);
-    const size_t rec = K > 12 ? 20 : 12, block = K > 12 ? 2048000 : 2101248;
-    std::vector<char> entries(n * rec), trie(nt * 12);
-    check(kasa_build_fetch(ctx, entries.data(), trie.data()), ctx);
-    write_padded(a.index, entries.data(), entries.size(), block);
-    {
-        std::ofstream f(a.index + "_info.txt");           // Build.hpp:466-470
-        f << n;
-        if (K > 12) f << std::endl << 128;
-    }
-    write_padded(a.index + "_trie", trie.data(), trie.size(), 2101248);
-    { std::ofstream f(a.index + "_trie.txt"); f << nt; }  // Trie.hpp:387-388
-    std::vector<uint64_t> freq(content.taxids.size() * (size_t)K);
-    check(kasa_build_frequency(ctx, content.taxids.data(), (uint32_t)content.taxids.size(), freq.data()), ctx);
-    {
-        std::ofstream f(a.index + "_f.txt");              // kASA.hpp:549-570
-        std::ifstream cf(a.content);
-        f << "non_unique";
-        for (int k = 0; k < K; ++k) f << "\t" << freq[k];
-        f << std::endl;
-        std::string line;
-        for (size_t j = 1; j < content.taxids.size() && std::getline(cf, line);) {
-            if (line.empty()) continue;
-            f << split(line, '\t')[0] << "\t" << freq[j * K];
-            for (int k = 1; k < K; ++k) f << "\t" << freq[j * K + k];
-            f << std::endl;
-            ++j;
-        }
-    }
+    finish_and_write(ctx, a.index, K, content, a.content, kWriteAll);
     kasa_ctx_destroy(ctx);
     return 0;
 }
@@ -565,6 +674,7 @@ int main(int argc, char **argv)
         }
         if (a.mode == "build") rc = run_build(a);
         else if (a.mode == "identify") rc = run_identify(a);
+        else if (a.mode == "trie" || a.mode == "getFrequency" || a.mode == "delete" || a.mode == "merge") rc = run_index_mode(a);
         else if (a.mode == "-h" || a.mode == "--help") usage();
         else throw std::runtime_error("mode not supported by kasa_b200: " + a.mode + " (build, identify)");
         std::cout << "OUT: Time: " << std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count() << " s" << std::endl;

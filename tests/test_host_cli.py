@@ -242,3 +242,87 @@ def test_cli_other_formats_consistent_with_jsonl(fmt, tmp_path):
             if hits:
                 assert r[2] == hits[0]["tax ID"] and int(r[3]) == j["Length"]
                 assert [x.split(":")[0] for x in r[4].split()] == [h["tax ID"] for h in hits]
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# index-maintenance modes: trie / getFrequency / delete / merge against the reference binary's files
+# (tests/golden/k12/modes_sha256.txt and modes/, written by oracle/make_golden_modes.py from kASA_scalar)
+def _modes():
+    want = {}
+    for line in G.text("k12", "modes_sha256.txt").splitlines():
+        if line and not line.startswith("#"):
+            name, nbytes, sha = line.split()
+            want[name] = (int(nbytes), sha)
+    return want
+
+
+def _records_sha(path, rec=12):
+    import hashlib
+    n = int(open(path + "_info.txt").read().split()[0])
+    return n * rec, hashlib.sha256(open(path, "rb").read()[:n * rec]).hexdigest()
+
+
+def _trie_sha(path):
+    import hashlib
+    n = int(open(path + "_trie.txt").read().split()[0])
+    return n * 12, hashlib.sha256(open(path + "_trie", "rb").read()[:n * 12]).hexdigest()
+
+
+@pytest.mark.gpu
+def test_cli_trie_and_frequency_modes_rewrite_the_reference_files(tmp_path):
+    """`trie -d idx` and `getFrequency -c content -d idx` from the index file alone (main.cpp:1422-1458, 1336-1362)."""
+    import hashlib
+    want = _modes()
+    idx = str(tmp_path / "idx")
+    open(idx, "wb").write(G.gz("k12", "idx.gz"))
+    open(idx + "_info.txt", "w").write(G.text("k12", "idx_info.txt"))
+    rc, out, err = _cli("trie", "-d", idx)
+    assert rc == 0, err
+    assert _trie_sha(idx) == want["trie/t_trie"]
+    rc, out, err = _cli("getFrequency", "-c", _g("k12", "content.txt"), "-d", idx)
+    assert rc == 0, err
+    data = open(idx + "_f.txt", "rb").read()
+    assert (len(data), hashlib.sha256(data).hexdigest()) == want["getFrequency/f_f.txt"]
+    assert data.decode() == G.text("k12", "idx_f.txt")
+
+
+@pytest.mark.gpu
+def test_cli_delete_mode_matches_the_reference(tmp_path):
+    """`delete -l delnodes.dmp`: index, prefix table and frequency file equal the ones `kASA delete` wrote (Update.hpp:28-94)."""
+    want = _modes()
+    idx = _write_index("k12", tmp_path)
+    out_idx = str(tmp_path / "del")
+    rc, out, err = _cli("delete", "-c", _g("k12", "content.txt"), "-d", idx, "-o", out_idx, "-l", _g("k12", os.path.join("modes", "del.dmp")))
+    assert rc == 0, err
+    assert _records_sha(out_idx) == want["delete/del"]
+    assert _trie_sha(out_idx) == want["delete/del_trie"]
+    assert open(out_idx + "_f.txt").read() == G.text("k12", os.path.join("modes", "del_f.txt"))
+
+
+@pytest.mark.gpu
+def test_cli_merge_mode_matches_the_reference(tmp_path):
+    """Two indexes built from the halves of ref.fa, merged: the halves and the merged index + prefix table equal the reference's
+    (`kASA merge`, Read.hpp:3180-3243), which equal the one-shot build.  The reference's merge writes no _info.txt and therefore a
+    frequency file of zeros (modes/m_f.txt); ours writes both, the frequencies being those of the one-shot build."""
+    import gzip
+    want = _modes()
+    text = gzip.open(_g("k12", "ref.fa.gz"), "rt").read()
+    recs = [">" + r for r in text.split(">") if r]
+    h = len(recs) // 2
+    content = _g("k12", "content.txt")
+    for name, part in (("a", recs[:h]), ("b", recs[h:])):
+        open(tmp_path / (name + ".fa"), "w").write("".join(part))
+        rc, out, err = _cli("build", "-c", content, "-d", str(tmp_path / name), "-i", str(tmp_path / (name + ".fa")))
+        assert rc == 0, err
+        assert _records_sha(str(tmp_path / name)) == want["merge/" + name]
+    m = str(tmp_path / "m")
+    rc, out, err = _cli("merge", "-c1", content, "-c2", content, "-co", m + "_content.txt", "--firstIndex", str(tmp_path / "a"),
+                        "--secondIndex", str(tmp_path / "b"), "-o", m)
+    assert rc == 0, err
+    assert _records_sha(m) == want["merge/m"]
+    assert _trie_sha(m) == want["merge/m_trie"]
+    assert open(m + "_content.txt").read() == open(content).read()
+    assert open(m + "_f.txt").read() == G.text("k12", "idx_f.txt")
+    assert all(f == "0" for l in G.text("k12", os.path.join("modes", "m_f.txt")).splitlines() for f in l.split("\t")[1:])     # the reference's file
+    rc, out, err = _cli("merge", "-c", content, "--firstIndex", m, "--secondIndex", m, "-o", str(tmp_path / "mm"))
+    assert rc != 0 and b"different" in err
