@@ -61,6 +61,7 @@ struct Args {
 [[noreturn]] void usage()
 {
     std::cout << "kasa_b200 <build|identify> -c <content> -d <index> [-i <input> | -1 <fq> -2 <fq>] [-p <profile.csv>] [-q <per-read out>]\n"
+                 "kasa_b200 update -c <content> -d <index> -i <new sequences> [-o <out>] (the content file names the new accessions)\n"
                  "kasa_b200 trie -d <index> | getFrequency -c <content> -d <index> | delete -c <content> -d <index> -o <out> -l <delnodes.dmp>\n"
                  "          | merge -c <content> --firstIndex <a> --secondIndex <b> -o <out>     (indexes sharing one content file)\n"
                  "          [-k <high> <low>] [--kH <12|25>] [--six | --one] [--json|--jsonl|--tsv|--kraken] [-b <n>] [--threshold <f>] [-v]\n"
@@ -273,10 +274,19 @@ int run_index_mode(const Args &a)
 }
 
 // ------------------------------------------------------------------------------------------------ build
+// `update` (main.cpp:699-768 with the content file given, Update.hpp:99-: UpdateFromFasta) is a build whose brick starts with the
+// records of the old index: <out> (default: the index itself) = <index> + the sequences of -i.
 int run_build(const Args &a)
 {
-    const int K = a.highest_k;
-    Content content = load_content(a.content);
+    const bool update = a.mode == "update";
+    int K = a.highest_k, old_bits = 64;
+    std::vector<char> old_records;
+    if (update) {
+        old_records = read_index_records(a.index, &old_bits);
+        K = old_bits == 128 ? 25 : 12;
+    }
+    const std::string out_path = update && !a.out.empty() ? a.out : a.index;
+    Content content = load_content(a.content.empty() && update ? a.index + "_content.txt" : a.content);
     const std::string fasta = slurp(a.input);
     kasa_params p{};
     if (a.one && a.six) throw std::runtime_error("--one and --six exclude each other");     // main.cpp:618
@@ -284,12 +294,16 @@ int run_build(const Args &a)
     p.score_mode = KASA_SCORE_NONE;
     uint8_t codon[512];
     if (!a.alphabet_file.empty() && load_codon_table(a.alphabet_file, a.alphabet_id, codon)) p.codon_table = codon;
-    const uint64_t windows = (uint64_t)fasta.size() * (a.six ? 2 : 1) + (1u << 20);
+    const uint64_t windows = (uint64_t)fasta.size() * (a.six ? 2 : 1) + (1u << 20) + old_records.size() / (old_bits == 128 ? 20 : 12);
     p.max_batch_kmers = std::min<uint64_t>(std::max<uint64_t>(windows * 2, 1u << 22), (1ull << 32) - (1u << 20));
     p.max_batch_seqs = 1u << 20;
     p.max_batch_bases = 256ull << 20;
     kasa_ctx *ctx = nullptr;
     check(kasa_ctx_create(&p, &ctx), nullptr);
+    if (update) {
+        check(kasa_build_push_index(ctx, old_records.data(), old_records.size() / (old_bits == 128 ? 20 : 12), old_bits), ctx);
+        std::vector<char>().swap(old_records);
+    }
     std::string chars;
     std::vector<uint64_t> starts;
     std::vector<uint32_t> lens, tax;
@@ -308,7 +322,7 @@ int run_build(const Args &a)
         chars += s;
     });
     flush();
-    finish_and_write(ctx, a.index, K, content, a.content, kWriteAll);
+    finish_and_write(ctx, out_path, K, content, a.content.empty() && update ? a.index + "_content.txt" : a.content, kWriteAll);
     kasa_ctx_destroy(ctx);
     return 0;
 }
@@ -672,7 +686,7 @@ int main(int argc, char **argv)
             for (const ReadRec &r : parse_reads(slurp(a.input))) std::cout << r.name << "\t" << r.lines << "\t" << r.seq << "\n";
             return 0;
         }
-        if (a.mode == "build") rc = run_build(a);
+        if (a.mode == "build" || a.mode == "update") rc = run_build(a);
         else if (a.mode == "identify") rc = run_identify(a);
         else if (a.mode == "trie" || a.mode == "getFrequency" || a.mode == "delete" || a.mode == "merge") rc = run_index_mode(a);
         else if (a.mode == "-h" || a.mode == "--help") usage();

@@ -12,6 +12,7 @@ The reference binary (`kASA_scalar`) runs on the committed k12 g
     merge         -c1 content.txt -c2 content.txt -co m_content.txt --firstIndex a --secondIndex b -o m
                                                            -> m, m_info.txt, m_trie, m_trie.txt, m_f.txt, m_content.txt
                                                                                               (Read.hpp:3180-3243)
+    update        -c content.txt -d a -i b.fa -o u         -> u, u_info.txt, u_trie, u_trie.txt, u_f.txt (Update.hpp:99-)
 Stored: one line per produced file, `<case>/<file> <bytes that count> <sha256>` (index and trie files are hashed over their
 records, without the STXXL block padding), the deleted taxids and how ref.fa was cut.  tests/test_host_cli.py runs
 kasa_b200_cli with the same commands and compares the same hashes.
@@ -109,6 +110,11 @@ def main():
     out.append(("merge/m",) + record_hash(work, "m", 12))
     out.append(("merge/m_trie",) + trie_hash(work, "m"))
     out.append(("merge/m_f.txt",) + text_hash(work, "m_f.txt"))
+    # ---- update: the first half's index + the second half's sequences, content file given
+    run([REF, "update", "-c", "content.txt", "-d", "a", "-i", "b.fa", "-o", "u", "-m", "4", "-n", "1", "-t", "tmp/"], work)
+    out.append(("update/u",) + record_hash(work, "u", 12))
+    out.append(("update/u_trie",) + trie_hash(work, "u"))
+    out.append(("update/u_f.txt",) + text_hash(work, "u_f.txt"))
     os.makedirs(os.path.join(GOLD, "modes"), exist_ok=True)
     for name in ("del_f.txt", "m_f.txt", "del.dmp"):          # the small text files are kept as they are
         shutil.copy(os.path.join(work, name), os.path.join(GOLD, "modes", name))

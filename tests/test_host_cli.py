@@ -326,3 +326,29 @@ def test_cli_merge_mode_matches_the_reference(tmp_path):
     assert all(f == "0" for l in G.text("k12", os.path.join("modes", "m_f.txt")).splitlines() for f in l.split("\t")[1:])     # the reference's file
     rc, out, err = _cli("merge", "-c", content, "--firstIndex", m, "--secondIndex", m, "-o", str(tmp_path / "mm"))
     assert rc != 0 and b"different" in err
+
+
+@pytest.mark.gpu
+def test_cli_update_mode_matches_the_reference(tmp_path):
+    """`update -c content -d a -i b.fa -o u`: the first half's index plus the second half's sequences = the files `kASA update`
+    wrote (Update.hpp:99-), which equal the one-shot build."""
+    import gzip
+    want = _modes()
+    text = gzip.open(_g("k12", "ref.fa.gz"), "rt").read()
+    recs = [">" + r for r in text.split(">") if r]
+    h = len(recs) // 2
+    content = _g("k12", "content.txt")
+    open(tmp_path / "a.fa", "w").write("".join(recs[:h]))
+    open(tmp_path / "b.fa", "w").write("".join(recs[h:]))
+    a, u = str(tmp_path / "a"), str(tmp_path / "u")
+    rc, out, err = _cli("build", "-c", content, "-d", a, "-i", str(tmp_path / "a.fa"))
+    assert rc == 0, err
+    rc, out, err = _cli("update", "-c", content, "-d", a, "-i", str(tmp_path / "b.fa"), "-o", u)
+    assert rc == 0, err
+    assert _records_sha(u) == want["update/u"]
+    assert _trie_sha(u) == want["update/u_trie"]
+    assert open(u + "_f.txt").read() == G.text("k12", "idx_f.txt")
+    # without -o the index is updated in place
+    rc, out, err = _cli("update", "-c", content, "-d", a, "-i", str(tmp_path / "b.fa"))
+    assert rc == 0, err
+    assert _records_sha(a) == want["update/u"]
