@@ -1,6 +1,8 @@
 // kasa_b200 host CLI — `build` and `identify` with kASA's flags, files and outputs (main.cpp:303-586 of the
 // reference for the flag names; formats per SURVEY.md §3.4 / Compare.hpp:1485-1890, 3466-3665).  FASTA/FASTQ(.gz)
 // parsing, content file, scoring and writers stay on the host; all k-mer work goes through libkasa_b200.so.
+#include <dirent.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -48,6 +50,22 @@ struct Pinned {
     const T *data() const { return p; }
 };
 
+// regular entries of a directory, sorted by name
+std::vector<std::string> list_directory(const std::string &path)
+{
+    std::vector<std::string> out;
+    DIR *d = opendir(path.c_str());
+    if (!d) throw std::runtime_error("Input folder not found: " + path);
+    while (dirent *e = readdir(d)) {
+        const std::string n = e->d_name;
+        if (n == "." || n == ".." || e->d_type == DT_DIR) continue;
+        out.push_back(n);
+    }
+    closedir(d);
+    std::sort(out.begin(), out.end());
+    return out;
+}
+
 struct Args {
     std::string mode, content, index, input, in1, in2, profile, rtt, tmp, alphabet_file, alphabet_id, out, first_index, second_index, deleted, content_out;
     int k_high = 12, k_low = 7, highest_k = 12, beasts = 3, device = 0, gpus = 1;
@@ -61,6 +79,7 @@ struct Args {
 [[noreturn]] void usage()
 {
     std::cout << "kasa_b200 <build|identify> -c <content> -d <index> [-i <input> | -1 <fq> -2 <fq>] [-p <profile.csv>] [-q <per-read out>]\n"
+                 "kasa_b200 identify_multiple -c <content> -d <index> -i <folder> [-p <profile prefix>] [-q <per-read prefix>] (identify's flags)\n"
                  "kasa_b200 update -c <content> -d <index> -i <new sequences> [-o <out>] (the content file names the new accessions)\n"
                  "kasa_b200 trie -d <index> | getFrequency -c <content> -d <index> | delete -c <content> -d <index> -o <out> -l <delnodes.dmp>\n"
                  "          | merge -c <content> --firstIndex <a> --secondIndex <b> -o <out>     (indexes sharing one content file)\n"
@@ -334,7 +353,8 @@ struct Hit {
     double rel;
 };
 
-int run_identify(const Args &a)
+// `shared` (identify_multiple): the contexts with the index loaded outlive the call — created by the first input, used by the next ones
+int run_identify(const Args &a, std::vector<kasa_ctx *> *shared = nullptr)
 {
     Content content = load_content(a.content);
     const size_t T = content.taxids.size();
@@ -447,7 +467,7 @@ int run_identify(const Args &a)
     // The first batch is parsed before the contexts exist: an input that ends inside it (the usual small run) sizes the
     // workspaces exactly, a longer one by the batch limits.
     const bool any_reads = fill(hb[0]);
-    if (eof && !have_pending) {
+    if (eof && !have_pending && !shared) {
         p.max_batch_kmers = hb[0].kmers_bound + 4096; p.max_batch_seqs = (uint32_t)hb[0].starts.size() + 1; p.max_batch_bases = hb[0].chars.size() + 4096;
     } else {
         const uint64_t seqs = (uint64_t)per_batch * (paired ? 2 : 1);
@@ -458,7 +478,8 @@ int run_identify(const Args &a)
     // independent; the reference's worker threads, Compare.hpp:3221-3310, become GPUs).  One host thread drives all of them:
     // kasa_identify_submit does not wait for the device.
     std::vector<kasa_ctx *> ctxs(G, nullptr);
-    {
+    if (shared && !shared->empty()) ctxs = *shared;
+    else {
         std::ifstream f(a.index, std::ios::binary);
         if (!f) throw std::runtime_error("Index file not found: " + a.index);
         std::vector<char> bytes(n_idx * (bits == 128 ? 20 : 12));
@@ -469,6 +490,7 @@ int run_identify(const Args &a)
             check(kasa_ctx_create(&p, &ctxs[g]), nullptr);
             check(kasa_index_load(ctxs[g], bytes.data(), n_idx, bits, content.taxids.data(), (uint32_t)T), ctxs[g]);
         }
+        if (shared) *shared = ctxs;
     }
 
     auto submit = [&](HostBatch &h, kasa_ctx *ctx) {
@@ -664,8 +686,34 @@ int run_identify(const Args &a)
         for (int ik = 0; ik < numK; ++ik) std::cout << " " << sum_u[ik];
         std::cout << std::endl;
     }
-    for (kasa_ctx *c : ctxs) kasa_ctx_destroy(c);
+    if (!shared) for (kasa_ctx *c : ctxs) kasa_ctx_destroy(c);
     return 0;
+}
+
+// identify_multiple (main.cpp:1118-1334): every file of the folder -i is identified against the index, which is loaded once; the
+// outputs are <-q prefix><file name without its last extension><.json|.jsonl|.tsv|.ktsv> and <-p prefix><name>.csv.  The reference
+// runs the files on its worker threads; here they pass through the same device contexts one after the other, each pipelined
+// batch by batch like a single identify.
+int run_identify_multiple(const Args &a)
+{
+    if (!a.in1.empty() || !a.in2.empty()) throw std::runtime_error("No paired-end allowed in this mode!");      // main.cpp:1129
+    std::vector<std::string> files = list_directory(a.input);
+    if (files.empty()) throw std::runtime_error("No files found in " + a.input);
+    const std::string ending = a.format == "json" ? ".json" : a.format == "jsonl" ? ".jsonl" : a.format == "tsv" ? ".tsv" : ".ktsv";
+    std::vector<kasa_ctx *> ctxs;
+    int rc = 0;
+    for (const std::string &name : files) {
+        Args b = a;
+        b.mode = "identify";
+        b.input = a.input + (a.input.empty() || a.input.back() == '/' ? "" : "/") + name;
+        const size_t dot = name.rfind('.');
+        const std::string stem = dot == std::string::npos ? name : name.substr(0, dot);
+        b.rtt = a.rtt.empty() ? "" : a.rtt + stem + ending;
+        b.profile = a.profile.empty() ? "" : a.profile + stem + ".csv";
+        rc |= run_identify(b, &ctxs);
+    }
+    for (kasa_ctx *c : ctxs) kasa_ctx_destroy(c);
+    return rc;
 }
 
 }  // namespace
@@ -688,6 +736,7 @@ int main(int argc, char **argv)
         }
         if (a.mode == "build" || a.mode == "update") rc = run_build(a);
         else if (a.mode == "identify") rc = run_identify(a);
+        else if (a.mode == "identify_multiple") rc = run_identify_multiple(a);
         else if (a.mode == "trie" || a.mode == "getFrequency" || a.mode == "delete" || a.mode == "merge") rc = run_index_mode(a);
         else if (a.mode == "-h" || a.mode == "--help") usage();
         else throw std::runtime_error("mode not supported by kasa_b200: " + a.mode + " (build, identify)");

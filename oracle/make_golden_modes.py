@@ -115,6 +115,25 @@ def main():
     out.append(("update/u",) + record_hash(work, "u", 12))
     out.append(("update/u_trie",) + trie_hash(work, "u"))
     out.append(("update/u_f.txt",) + text_hash(work, "u_f.txt"))
+    # ---- identify_multiple: the two halves of reads.fq in one folder; the names of the output files are what is recorded (their
+    # contents equal those of `identify` per file, which tests/golden/k12/six_12_7.* pin)
+    fq = gzip.open(os.path.join(GOLD, "reads.fq.gz"), "rt").read().splitlines(keepends=True)
+    half = (len(fq) // 8) * 4
+    os.makedirs(os.path.join(work, "in"))
+    open(os.path.join(work, "in", "first.part.fq"), "w").write("".join(fq[:half]))
+    open(os.path.join(work, "in", "second.fq"), "w").write("".join(fq[half:]))
+    os.makedirs(os.path.join(work, "res"))
+    run([REF, "identify_multiple", "-c", "content.txt", "-d", "idx", "-i", "in/", "-q", "res/q_", "-p", "res/p_", "--jsonl", "-r", "-m", "8", "-n", "2",
+         "-t", "tmp/", "--six"], work)
+    names = sorted(os.listdir(os.path.join(work, "res")))
+    for nme in names:
+        out.append(("identify_multiple/" + nme,) + text_hash(work, os.path.join("res", nme)))
+    for part in ("first.part.fq", "second.fq"):
+        stem = part.rsplit(".", 1)[0]
+        run([REF, "identify", "-c", "content.txt", "-d", "idx", "-i", "in/" + part, "-q", "res/single_" + stem + ".jsonl", "--jsonl", "-r", "-m", "8",
+             "-n", "1", "-t", "tmp/", "--six"], work)
+        same = open(os.path.join(work, "res", "single_" + stem + ".jsonl")).read() == open(os.path.join(work, "res", "q_" + stem + ".jsonl")).read()
+        print("identify_multiple == identify for", part, ":", same)
     os.makedirs(os.path.join(GOLD, "modes"), exist_ok=True)
     for name in ("del_f.txt", "m_f.txt", "del.dmp"):          # the small text files are kept as they are
         shutil.copy(os.path.join(work, name), os.path.join(GOLD, "modes", name))

@@ -352,3 +352,29 @@ def test_cli_update_mode_matches_the_reference(tmp_path):
     rc, out, err = _cli("update", "-c", content, "-d", a, "-i", str(tmp_path / "b.fa"))
     assert rc == 0, err
     assert _records_sha(a) == want["update/u"]
+
+
+@pytest.mark.gpu
+def test_cli_identify_multiple_names_and_equals_identify(tmp_path):
+    """identify_multiple (main.cpp:1118-1334): every file of a folder against the index loaded once.  The output names are the ones the
+    reference binary produced (modes_sha256.txt: <prefix><file name without its last extension><ending>), the contents those of
+    `identify` on the same file — which the six_12_7 goldens pin against the reference."""
+    import gzip
+    names = sorted(k.split("/", 1)[1] for k in _modes() if k.startswith("identify_multiple/"))
+    assert names == ["p_first.part.csv", "p_second.csv", "q_first.part.jsonl", "q_second.jsonl"]
+    idx = _write_index("k12", tmp_path)
+    fq = gzip.open(_g("k12", "reads.fq.gz"), "rt").read().splitlines(keepends=True)
+    half = (len(fq) // 8) * 4
+    os.makedirs(tmp_path / "in")
+    os.makedirs(tmp_path / "res")
+    open(tmp_path / "in" / "first.part.fq", "w").write("".join(fq[:half]))
+    open(tmp_path / "in" / "second.fq", "w").write("".join(fq[half:]))
+    common = ["-c", _g("k12", "content.txt"), "-d", idx, "--jsonl", "--six", "--batch-reads", "64"]
+    rc, out, err = _cli("identify_multiple", *common, "-i", str(tmp_path / "in") + "/", "-q", str(tmp_path / "res" / "q_"), "-p", str(tmp_path / "res" / "p_"))
+    assert rc == 0, err
+    assert sorted(os.listdir(tmp_path / "res")) == names
+    for part, stem in (("first.part.fq", "first.part"), ("second.fq", "second")):
+        rc, out, err = _cli("identify", *common, "-i", str(tmp_path / "in" / part), "-q", str(tmp_path / "single.jsonl"), "-p", str(tmp_path / "single.csv"))
+        assert rc == 0, err
+        assert open(tmp_path / "single.jsonl").read() == open(tmp_path / "res" / ("q_" + stem + ".jsonl")).read()
+        assert open(tmp_path / "single.csv").read() == open(tmp_path / "res" / ("p_" + stem + ".csv")).read()
