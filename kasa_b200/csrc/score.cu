@@ -1714,7 +1714,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) score_dense_kernel(const uint6
     // (64-bit, widened from the per-read 32-bit registers; in shared memory, one private word per warp, sum and lane: registers are
     // what keeps three CTAs on an SM)
     __shared__ unsigned long long s_acc[kBlkWarps][4][32];
-    for (int i = tid; i < kBlkWarps * 4 * 32; i += blockDim.x) (&s_acc[0][0][0])[i] = 0;
+    for (int j = 0; j < 4; ++j) s_acc[w][j][lane] = 0;              // (every thread its own words: no barrier needed)
     const uint32_t lbit = 1u << lane;
     constexpr uint32_t kUpAllA = 0xE0000000u, kUpAllB = 0xC0000000u, kUpOne = 0x40000000u, kUpSeveral = 0x20000000u, kUpList = 0x10000000u, kUpMask = 0x08000000u;
 
