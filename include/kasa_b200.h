@@ -126,6 +126,13 @@ int kasa_ctx_stage_times(kasa_ctx *ctx, double *ms, uint64_t *batches, uint64_t 
 int kasa_index_load(kasa_ctx *ctx, const void *entries, uint64_t n, int bits,
                     const uint32_t *taxid_of_idx, uint32_t n_taxa);
 
+/* Replaces: the loading of a halved index (`kASA half` / shrink strategy TrieHalf, Shrink::putHalfInTrie Shrink.hpp:78-143; read by
+ * identify through index_t_p, Compare.hpp:185-222).  entries = n records {u32 lower six letters, u16 index into the content table}
+ * (6 bytes each), trie = the n_trie records {u64 count, u32 upper six letters} of <index>_trie.  The keys are put together again on
+ * the device (prefix << 30 | lower letters) and the index then serves identify like a full one: the reference's own results with
+ * the halved and the full index are the same bytes (tests/golden/k12/modes_sha256.txt).  highest_k must be 12.                     */
+int kasa_index_load_half(kasa_ctx *ctx, const void *entries, uint64_t n, const void *trie, uint64_t n_trie, uint32_t n_taxa);
+
 /* Adopt the index just built on this context by kasa_build_finish (stays in HBM, no host round trip).  */
 int kasa_index_from_build(kasa_ctx *ctx, const uint32_t *taxid_of_idx, uint32_t n_taxa);
 

@@ -30,7 +30,7 @@ EXPORTS = [
     "kasa_ctx_synchronize", "kasa_ctx_launch_count", "kasa_ctx_stage_times", "kasa_index_load", "kasa_index_from_build", "kasa_index_size",
     "kasa_identify_batch", "kasa_identify_submit", "kasa_identify_wait", "kasa_identify_finish", "kasa_build_push", "kasa_build_finish", "kasa_build_fetch",
     "kasa_shard_plan", "kasa_index_from_build_shard", "kasa_shard_init", "kasa_shard_connect", "kasa_shard_sort", "kasa_shard_lookup",
-    "kasa_shard_score", "kasa_build_shard_local", "kasa_shard_plan_hist", "kasa_build_shard_runs", "kasa_build_shard_pull", "kasa_build_frequency", "kasa_dbg_extract", "kasa_dbg_sort_pairs", "kasa_synth_build_reference", "kasa_synth_build_reference_range", "kasa_synth_reads", "kasa_host_alloc", "kasa_host_free", "kasa_builtin_codon_table", "kasa_build_push_index",
+    "kasa_shard_score", "kasa_build_shard_local", "kasa_shard_plan_hist", "kasa_build_shard_runs", "kasa_build_shard_pull", "kasa_build_frequency", "kasa_dbg_extract", "kasa_dbg_sort_pairs", "kasa_synth_build_reference", "kasa_synth_build_reference_range", "kasa_synth_reads", "kasa_host_alloc", "kasa_host_free", "kasa_builtin_codon_table", "kasa_build_push_index", "kasa_index_load_half",
 ]
 
 
@@ -252,6 +252,14 @@ class Context:
         tax = np.ascontiguousarray(taxid_of_idx, dtype=np.uint32)
         self._check(self.lib.kasa_index_load(self.h, _ptr(records), len(records), bits, _ptr(tax), len(tax)))
         self.n_taxa = len(tax)
+
+    def load_index_half(self, records6: np.ndarray, trie: np.ndarray, n_taxa: int):
+        """halved index (`kASA half`): 6-byte records {u32 lower letters, u16 content index} + the records of <index>_trie (kasa_index_load_half)."""
+        records6 = np.ascontiguousarray(records6)
+        trie = np.ascontiguousarray(trie)
+        assert records6.dtype.itemsize == 6 and trie.dtype.itemsize == 12
+        self._check(self.lib.kasa_index_load_half(self.h, _ptr(records6), C.c_uint64(len(records6)), _ptr(trie), C.c_uint64(len(trie)), C.c_uint32(n_taxa)))
+        self.n_taxa = n_taxa
 
     def index_from_build(self, taxid_of_idx: np.ndarray):
         tax = np.ascontiguousarray(taxid_of_idx, dtype=np.uint32)

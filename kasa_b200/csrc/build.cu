@@ -72,6 +72,40 @@ __global__ void __launch_bounds__(256) trie_records_kernel(const uint64_t *__res
     }
 }
 
+// ---- halved index (Shrink::putHalfInTrie, Shrink.hpp:78-143): records {u32 lower six letters, u16 taxon index}, the upper six letters
+// in the prefix table {u64 count, u32 prefix}
+__global__ void __launch_bounds__(256) half_trie_split_kernel(const uint32_t *__restrict__ trie_words, uint64_t n_trie, uint64_t *__restrict__ starts,
+                                                              uint32_t *__restrict__ prefix)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_trie; j += stride) {
+        starts[j] = (uint64_t)trie_words[3 * j] | ((uint64_t)trie_words[3 * j + 1] << 32);
+        prefix[j] = trie_words[3 * j + 2];
+    }
+}
+
+// after the exclusive scan of starts: record i belongs to the last prefix whose start is <= i (records behind the table's total — the
+// reference counts the last run one short, Shrink.hpp:131-136 — belong to the last prefix)
+__global__ void __launch_bounds__(256) half_expand_kernel(const uint16_t *__restrict__ rec, uint64_t n, const uint64_t *__restrict__ starts,
+                                                          const uint32_t *__restrict__ prefix, uint64_t n_trie, uint32_t n_taxa,
+                                                          uint64_t *__restrict__ key_lo, uint16_t *__restrict__ tax, uint32_t *err_flag)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t a = 0, b = n_trie;                        // first run whose start is > i
+        while (a < b) {
+            const uint64_t m = (a + b) >> 1;
+            if (starts[m] <= i) a = m + 1; else b = m;
+        }
+        const uint64_t j = a ? a - 1 : 0;
+        const uint32_t lo = (uint32_t)rec[3 * i] | ((uint32_t)rec[3 * i + 1] << 16);
+        const uint16_t t = rec[3 * i + 2];
+        if (t >= n_taxa || (lo >> 30)) atomicExch(err_flag, 2u);      // the taxon index is not one of the content table
+        key_lo[i] = ((uint64_t)prefix[j] << 30) | lo;
+        tax[i] = t;
+    }
+}
+
 __global__ void __launch_bounds__(256) map_taxids_kernel(const uint32_t *__restrict__ taxid, uint64_t n,
                                                          const uint32_t *__restrict__ sorted_taxid,
                                                          const uint16_t *__restrict__ sorted_idx, uint32_t m,
@@ -165,7 +199,7 @@ __global__ void __launch_bounds__(256) check_sorted_kernel(const uint64_t *__res
         bool bad;
         if (hi && hi[i] != hi[i - 1]) bad = hi[i] < hi[i - 1];
         else if (lo[i] != lo[i - 1]) bad = lo[i] < lo[i - 1];
-        else bad = val[i] < val[i - 1];
+        else bad = val && val[i] < val[i - 1];
         if (bad) atomicExch(err_flag, 3u);
     }
 }
@@ -252,6 +286,21 @@ void launch_check_sorted(cudaStream_t s, const uint64_t *key_lo, const uint64_t 
 {
     if (n < 2) return;
     check_sorted_kernel<<<grid_for(n), 256, 0, s>>>(key_lo, key_hi, val, n, err_flag);
+    ++*launches;
+}
+
+void launch_half_trie_split(cudaStream_t s, const uint32_t *trie_words, uint64_t n_trie, uint64_t *starts, uint32_t *prefix, uint64_t *launches)
+{
+    if (!n_trie) return;
+    half_trie_split_kernel<<<grid_for(n_trie), 256, 0, s>>>(trie_words, n_trie, starts, prefix);
+    ++*launches;
+}
+
+void launch_half_expand(cudaStream_t s, const uint16_t *rec, uint64_t n, const uint64_t *starts, const uint32_t *prefix, uint64_t n_trie,
+                        uint32_t n_taxa, uint64_t *key_lo, uint16_t *tax, uint32_t *err_flag, uint64_t *launches)
+{
+    if (!n) return;
+    half_expand_kernel<<<grid_for(n), 256, 0, s>>>(rec, n, starts, prefix, n_trie, n_taxa, key_lo, tax, err_flag);
     ++*launches;
 }
 

@@ -39,4 +39,10 @@ void launch_unpack_records(cudaStream_t s, const uint32_t *words, uint64_t n, bo
 void launch_check_sorted(cudaStream_t s, const uint64_t *key_lo, const uint64_t *key_hi, const uint32_t *val, uint64_t n,
                          uint32_t *err_flag, uint64_t *launches);
 
+// halved index (6-byte records + prefix table, Shrink.hpp:78-143) -> full keys: counts and prefixes out of the table's records, then
+// (after the exclusive scan of starts[0..n_trie]) key = prefix << 30 | lower six letters; err_flag 2: taxon index or letters out of range
+void launch_half_trie_split(cudaStream_t s, const uint32_t *trie_words, uint64_t n_trie, uint64_t *starts, uint32_t *prefix, uint64_t *launches);
+void launch_half_expand(cudaStream_t s, const uint16_t *rec, uint64_t n, const uint64_t *starts, const uint32_t *prefix, uint64_t n_trie,
+                        uint32_t n_taxa, uint64_t *key_lo, uint16_t *tax, uint32_t *err_flag, uint64_t *launches);
+
 }  // namespace kasa

@@ -704,6 +704,37 @@ int kasa_index_load(kasa_ctx *c, const void *entries, uint64_t n, int bits, cons
     KASA_API_END(c)
 }
 
+int kasa_index_load_half(kasa_ctx *c, const void *entries, uint64_t n, const void *trie, uint64_t n_trie, uint32_t n_taxa)
+{
+    KASA_API_BEGIN
+    KASA_REQUIRE(c && entries && trie && n && n_trie, KASA_ERR_ARG, "null argument");
+    KASA_REQUIRE(!c->wide, KASA_ERR_ARG, "halved indices are 64-bit indices (highest_k 12)");
+    KASA_CUDA_TRY(cudaSetDevice(c->p.device));
+    ensure_workspace(c);
+    drop_index(c);
+    set_taxa(c, n_taxa);
+    uint16_t *d_rec = dev_alloc<uint16_t>(c, n * 3 + 2);
+    uint32_t *d_trie = dev_alloc<uint32_t>(c, n_trie * 3 + 1);
+    uint64_t *d_starts = dev_alloc<uint64_t>(c, n_trie + 2);
+    uint32_t *d_prefix = dev_alloc<uint32_t>(c, n_trie + 1);
+    uint64_t *d_tmp = dev_alloc<uint64_t>(c, scan_tmp_elems(n_trie + 1) + 1);
+    c->idx_lo = dev_alloc<uint64_t>(c, n + 16);
+    c->idx_hi = nullptr;
+    c->idx_tax = dev_alloc<uint16_t>(c, n + 16);
+    KASA_CUDA_TRY(cudaMemcpyAsync(d_rec, entries, n * 6, cudaMemcpyHostToDevice, c->stream));
+    KASA_CUDA_TRY(cudaMemcpyAsync(d_trie, trie, n_trie * 12, cudaMemcpyHostToDevice, c->stream));
+    launch_half_trie_split(c->stream, d_trie, n_trie, d_starts, d_prefix, &c->launches);
+    exclusive_scan_u64(c->stream, d_starts, n_trie, d_tmp, &c->launches);
+    launch_half_expand(c->stream, d_rec, n, d_starts, d_prefix, n_trie, n_taxa, c->idx_lo, c->idx_tax, c->d_err, &c->launches);
+    launch_check_sorted(c->stream, c->idx_lo, nullptr, nullptr, n, c->d_err, &c->launches);
+    finalize_index(c, n);
+    KASA_CUDA_TRY(cudaGetLastError());
+    check_device_flags(c);
+    dev_free(c, d_rec); dev_free(c, d_trie); dev_free(c, d_starts); dev_free(c, d_prefix); dev_free(c, d_tmp);
+    c->idx_n = n;
+    KASA_API_END(c)
+}
+
 int kasa_index_from_build(kasa_ctx *c, const uint32_t *taxid_of_idx, uint32_t n_taxa)
 {
     KASA_API_BEGIN

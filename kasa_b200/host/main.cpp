@@ -361,6 +361,7 @@ int run_identify(const Args &a, std::vector<kasa_ctx *> *shared = nullptr)
     // index: <idx>_info.txt = count [\n 128 | 3] (main.cpp:982-991)
     uint64_t n_idx = 0;
     int bits = 64;
+    bool half = false;
     {
         std::ifstream f(a.index + "_info.txt");
         if (!f) throw std::runtime_error("Index info file not found: " + a.index + "_info.txt");
@@ -368,7 +369,7 @@ int run_identify(const Args &a, std::vector<kasa_ctx *> *shared = nullptr)
         f >> n_idx;
         if (f >> tok) {
             if (tok == "128") bits = 128;
-            else if (tok == "3") throw std::runtime_error("halved (6-byte) indices are not supported by kasa_b200");
+            else if (tok == "3") half = true;               // `kASA half`: 6-byte records, the upper six letters in <index>_trie
         }
     }
     const int K = bits == 128 ? 25 : 12;
@@ -482,13 +483,22 @@ int run_identify(const Args &a, std::vector<kasa_ctx *> *shared = nullptr)
     else {
         std::ifstream f(a.index, std::ios::binary);
         if (!f) throw std::runtime_error("Index file not found: " + a.index);
-        std::vector<char> bytes(n_idx * (bits == 128 ? 20 : 12));
+        std::vector<char> bytes(n_idx * (half ? 6 : bits == 128 ? 20 : 12)), trie;
         f.read(bytes.data(), (std::streamsize)bytes.size());
+        uint64_t n_trie = 0;
+        if (half) {
+            std::ifstream ti(a.index + "_trie.txt"), tf(a.index + "_trie", std::ios::binary);
+            if (!ti || !tf) throw std::runtime_error("Trie file not found");                      // main.cpp:362-366
+            ti >> n_trie;
+            trie.resize(n_trie * 12);
+            tf.read(trie.data(), (std::streamsize)trie.size());
+        }
         const bool same_device = getenv("KASA_CLI_SAME_DEVICE") != nullptr;   // test hook: N contexts on one GPU
         for (int g = 0; g < G; ++g) {
             p.device = same_device ? a.device : a.device + g;
             check(kasa_ctx_create(&p, &ctxs[g]), nullptr);
-            check(kasa_index_load(ctxs[g], bytes.data(), n_idx, bits, content.taxids.data(), (uint32_t)T), ctxs[g]);
+            if (half) check(kasa_index_load_half(ctxs[g], bytes.data(), n_idx, trie.data(), n_trie, (uint32_t)T), ctxs[g]);
+            else check(kasa_index_load(ctxs[g], bytes.data(), n_idx, bits, content.taxids.data(), (uint32_t)T), ctxs[g]);
         }
         if (shared) *shared = ctxs;
     }

@@ -13,6 +13,8 @@ The reference binary (`kASA_scalar`) runs on the committed k12 g
                                                            -> m, m_info.txt, m_trie, m_trie.txt, m_f.txt, m_content.txt
                                                                                               (Read.hpp:3180-3243)
     update        -c content.txt -d a -i b.fa -o u         -> u, u_info.txt, u_trie, u_trie.txt, u_f.txt (Update.hpp:99-)
+    half          -c content.txt -d idx -o idxh            -> idxh (6-byte records), idxh_info.txt, idxh_trie, idxh_trie.txt
+                                                                                              (Shrink.hpp:78-143)
 Stored: one line per produced file, `<case>/<file> <bytes that count> <sha256>` (index and trie files are hashed over their
 records, without the STXXL block padding), the deleted taxids and how ref.fa was cut.  tests/test_host_cli.py runs
 kasa_b200_cli with the same commands and compares the same hashes.
@@ -134,6 +136,19 @@ def main():
              "-n", "1", "-t", "tmp/", "--six"], work)
         same = open(os.path.join(work, "res", "single_" + stem + ".jsonl")).read() == open(os.path.join(work, "res", "q_" + stem + ".jsonl")).read()
         print("identify_multiple == identify for", part, ":", same)
+    # ---- half: the 6-byte index + its prefix table; identify with it prints what identify with the full index prints
+    run([REF, "half", "-c", "content.txt", "-d", "idx", "-o", "idxh", "-m", "4", "-t", "tmp/"], work)
+    out.append(("half/idxh",) + record_hash(work, "idxh", 6))
+    out.append(("half/idxh_trie",) + trie_hash(work, "idxh"))
+    open(os.path.join(work, "reads.fq"), "w").write("".join(fq))
+    res = {}
+    for name in ("idx", "idxh"):
+        run([REF, "identify", "-c", "content.txt", "-d", name, "-i", "reads.fq", "-q", name + ".jsonl", "-p", name + ".csv", "--jsonl", "-r", "-m", "4",
+             "-n", "1", "-t", "tmp/", "--six"], work)
+        res[name] = (open(os.path.join(work, name + ".jsonl")).read(), open(os.path.join(work, name + ".csv")).read())
+    print("identify with the halved index == identify with the full index:", res["idx"] == res["idxh"])
+    assert res["idx"] == res["idxh"]
+    out.append(("half/identify_equals_full_index", 1, hashlib.sha256(res["idxh"][0].encode()).hexdigest()))
     os.makedirs(os.path.join(GOLD, "modes"), exist_ok=True)
     for name in ("del_f.txt", "m_f.txt", "del.dmp"):          # the small text files are kept as they are
         shutil.copy(os.path.join(work, name), os.path.join(GOLD, "modes", name))

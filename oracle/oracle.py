@@ -418,6 +418,32 @@ def relative_score(kmer_score, freq_highest: int, read_len: int, K: int) -> floa
     return lib().ko_relative_score(float(kmer_score), int(freq_highest), read_len, K)
 
 
+HALF_DTYPE = np.dtype([("lo", "<u4"), ("idx", "<u2")])
+
+
+def half_index(index: np.ndarray, taxid_of_idx: np.ndarray):
+    """`kASA half` (Shrink::putHalfInTrie, Shrink.hpp:78-143) of a 64-bit index: the records keep their lower six letters and the
+    position of their taxid in the content table; records whose lower six letters are all '^' (30) are dropped; the prefix table
+    counts the kept records per upper six letters.  The reference closes the last run with `count - 1` unless the count is 1
+    (Shrink.hpp:131-136) — restated as it is.  Returns (records, prefix table)."""
+    lo30 = index["lo"] & np.uint64((1 << 30) - 1)
+    keep = lo30 != np.uint64(1039104990)                       # "^^^^^^"
+    pos = {int(t): i for i, t in enumerate(taxid_of_idx)}
+    rec = np.zeros(int(keep.sum()), dtype=HALF_DTYPE)
+    rec["lo"] = lo30[keep].astype(np.uint32)
+    rec["idx"] = np.array([pos[int(t)] for t in index["tax"][keep]], dtype=np.uint16)
+    prefix = (index["lo"][keep] >> np.uint64(30)).astype(np.uint32)
+    # the reference starts from the first record's prefix whether that record is kept or not (Shrink.hpp:93); runs by change of prefix
+    starts = np.flatnonzero(np.concatenate(([True], prefix[1:] != prefix[:-1])))
+    counts = np.diff(np.concatenate((starts, [len(prefix)]))).astype(np.uint64)
+    if len(counts) and counts[-1] != 1:
+        counts[-1] -= np.uint64(1)
+    trie = np.zeros(len(starts), dtype=TRIE_DTYPE)
+    trie["count"] = counts
+    trie["prefix"] = prefix[starts]
+    return rec, trie
+
+
 # --------------------------------------------------------------------------- file helpers (formats of SURVEY.md §3.4)
 def load_index_file(path: str):
     info = open(path + "_info.txt").read().split()

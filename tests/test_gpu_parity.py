@@ -603,3 +603,42 @@ def test_device_resident_batches_match_host_batches():
     assert int(res.n_kmers) == n_host
     assert np.array_equal(d_scores.cpu().numpy().reshape(len(reads), len(taxids)), scores_host)
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", [capi.SCORE_ORDERED, capi.SCORE_EXACT])
+def test_halved_index_serves_identify_like_the_full_one(mode):
+    """`kASA half` (Shrink.hpp:78-143): 6-byte records + the prefix table, put together again on the device (kasa_index_load_half).
+    The reference prints the same bytes with the halved and the full index (tests/golden/k12/modes_sha256.txt); here scores and counts
+    of the two are compared bit for bit, and the EXACT scores with the oracle's (= the reference's)."""
+    _, taxids, _ = G.content("k12")
+    idx = G.index("k12")
+    rec6, trie = O.half_index(idx, taxids)             # pinned on the reference's files by tests/test_oracle_vs_reference.py
+    reads = _k12_reads()
+    res = []
+    for half in (False, True):
+        ctx = _ctx(highest_k=12, k_high=12, k_low=7, frames=6, score_mode=mode)
+        if half:
+            ctx.load_index_half(rec6, trie, len(taxids))
+        else:
+            ctx.load_index(idx, taxids)
+        n, sc, _ = ctx.identify_batch(reads)
+        ca, cu, total = ctx.identify_finish()
+        ctx.close()
+        res.append((n, sc, ca, cu, total))
+    assert res[0][0] == res[1][0] and res[0][4] == res[1][4]
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2]) and np.array_equal(res[0][3], res[1][3])
+    if mode == capi.SCORE_EXACT:
+        ora = O.identify_reads([[r] for r in reads], idx, 12, 12, 7, True, taxids)
+        assert np.array_equal(res[1][1], ora.scores)
+
+
+def test_halved_index_with_a_taxon_outside_the_content_table_is_rejected():
+    _, taxids, _ = G.content("k12")
+    rec6, trie = O.half_index(G.index("k12"), taxids)
+    bad = rec6.copy()
+    bad["idx"][len(bad) // 2] = len(taxids)
+    ctx = _ctx(highest_k=12, k_high=12, k_low=7, frames=6)
+    with pytest.raises(KasaError):
+        ctx.load_index_half(bad, trie, len(taxids))
+    ctx.load_index_half(rec6, trie, len(taxids))       # the context stays usable
+    ctx.close()

@@ -378,3 +378,25 @@ def test_cli_identify_multiple_names_and_equals_identify(tmp_path):
         assert rc == 0, err
         assert open(tmp_path / "single.jsonl").read() == open(tmp_path / "res" / ("q_" + stem + ".jsonl")).read()
         assert open(tmp_path / "single.csv").read() == open(tmp_path / "res" / ("p_" + stem + ".csv")).read()
+
+
+@pytest.mark.gpu
+def test_cli_identify_with_a_halved_index(tmp_path):
+    """An index halved by `kASA half` (info file "<n>\\n3", 6-byte records, the upper letters in _trie) gives the output of the full index —
+    as it does with the reference binary (modes_sha256.txt: half/identify_equals_full_index)."""
+    _, taxids, _ = G.content("k12")
+    rec6, trie = O.half_index(G.index("k12"), taxids)
+    full = _write_index("k12", tmp_path)
+    h = str(tmp_path / "idxh")
+    rec6.tofile(h)
+    trie.tofile(h + "_trie")
+    open(h + "_info.txt", "w").write("%d\n3" % len(rec6))
+    open(h + "_trie.txt", "w").write(str(len(trie)))
+    open(h + "_f.txt", "w").write(G.text("k12", "idx_f.txt"))
+    outs = []
+    for idx, tag in ((full, "full"), (h, "half")):
+        rc, out, err = _cli("identify", "-c", _g("k12", "content.txt"), "-d", idx, "-i", _g("k12", "reads.fq.gz"), "--jsonl", "--six",
+                            "-q", str(tmp_path / (tag + ".jsonl")), "-p", str(tmp_path / (tag + ".csv")))
+        assert rc == 0, err
+        outs.append((open(tmp_path / (tag + ".jsonl")).read(), open(tmp_path / (tag + ".csv")).read()))
+    assert outs[0] == outs[1]

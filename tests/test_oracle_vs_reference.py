@@ -118,3 +118,19 @@ def test_kmer_count_edge_cases():
     assert L.ko_kmer_count(38, 12) == 3
     assert L.ko_kmer_count(165, 12) == 130
     assert L.ko_kmer_count(0, 12) == 0
+
+
+def test_half_index_restatement_equals_the_reference_files():
+    """oracle.half_index (Shrink::putHalfInTrie, Shrink.hpp:78-143) against the files `kASA half` wrote from the k12 golden index
+    (tests/golden/k12/modes_sha256.txt, oracle/make_golden_modes.py): 6-byte records and prefix table byte for byte."""
+    import hashlib
+    want = {}
+    for line in G.text("k12", "modes_sha256.txt").splitlines():
+        if line.startswith("half/"):
+            name, nbytes, sha = line.split()
+            want[name] = (int(nbytes), sha)
+    _, taxids, _ = G.content("k12")
+    rec, trie = O.half_index(G.index("k12"), taxids)
+    assert (rec.nbytes, hashlib.sha256(rec.tobytes()).hexdigest()) == want["half/idxh"]
+    assert (trie.nbytes, hashlib.sha256(trie.tobytes()).hexdigest()) == want["half/idxh_trie"]
+    assert want["half/identify_equals_full_index"][0] == 1      # the reference printed the same JSONL with either index
