@@ -81,6 +81,7 @@ struct Args {
     std::cout << "kasa_b200 <build|identify> -c <content> -d <index> [-i <input> | -1 <fq> -2 <fq>] [-p <profile.csv>] [-q <per-read out>]\n"
                  "kasa_b200 identify_multiple -c <content> -d <index> -i <folder> [-p <profile prefix>] [-q <per-read prefix>] (identify's flags)\n"
                  "kasa_b200 update -c <content> -d <index> -i <new sequences> [-o <out>] (the content file names the new accessions)\n"
+                 "kasa_b200 half -c <content> -d <index> -o <out>     (6-byte records, the upper six letters in <out>_trie)\n"
                  "kasa_b200 trie -d <index> | getFrequency -c <content> -d <index> | delete -c <content> -d <index> -o <out> -l <delnodes.dmp>\n"
                  "          | merge -c <content> --firstIndex <a> --secondIndex <b> -o <out>     (indexes sharing one content file)\n"
                  "          [-k <high> <low>] [--kH <12|25>] [--six | --one] [--json|--jsonl|--tsv|--kraken] [-b <n>] [--threshold <f>] [-v]\n"
@@ -224,6 +225,58 @@ std::vector<char> read_index_records(const std::string &path, int *bits)
     std::ifstream f(path, std::ios::binary);
     if (!f || !f.read(rec.data(), (std::streamsize)rec.size())) throw std::runtime_error("Library file does not exist or is shorter than its info file says: " + path);
     return rec;
+}
+
+// `half` (main.cpp:1465-1474, Shrink::putHalfInTrie Shrink.hpp:78-143): one streaming pass over the index file on the host — nothing to
+// compute.  <out> = 6-byte records {u32 lower six letters, u16 position of the taxid in the content file}, without the records whose lower
+// six letters are all '^'; <out>_trie counts the kept records per upper six letters (the last run one short unless it is 1, as the
+// reference writes it); <out>_info.txt = "<n>\n3"; <out>_f.txt is the old frequency file (Shrink.hpp:441-452).
+int run_half(const Args &a)
+{
+    if (a.out.empty() || a.out == a.index) throw std::runtime_error("Paths and names of input and output are the same!");      // main.cpp:1466
+    int bits = 64;
+    const std::vector<char> rec = read_index_records(a.index, &bits);
+    if (bits != 64) throw std::runtime_error("Only 64-bit indices can be halved");
+    Content content = load_content(a.content.empty() ? a.index + "_content.txt" : a.content);
+    if (content.taxids.size() > 65535) throw std::runtime_error("Too many taxa for a halved index (2^16 - 1 at most)");
+    std::unordered_map<uint32_t, uint16_t> pos;
+    for (size_t i = 0; i < content.taxids.size(); ++i) pos[content.taxids[i]] = (uint16_t)i;
+    const uint64_t n = rec.size() / 12, low_mask = (1ull << 30) - 1;
+    std::vector<char> out6, trie;
+    out6.reserve(n * 6);
+    uint64_t count = 0, current = 0;
+    bool first = true;
+    auto put_run = [&](uint64_t prefix, uint64_t c) {
+        const uint32_t p32 = (uint32_t)prefix;
+        trie.insert(trie.end(), reinterpret_cast<const char *>(&c), reinterpret_cast<const char *>(&c) + 8);
+        trie.insert(trie.end(), reinterpret_cast<const char *>(&p32), reinterpret_cast<const char *>(&p32) + 4);
+    };
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t k;
+        uint32_t t;
+        std::memcpy(&k, rec.data() + i * 12, 8);
+        std::memcpy(&t, rec.data() + i * 12 + 8, 4);
+        if (first) { current = k >> 30; first = false; }
+        if ((k & low_mask) == 1039104990ull) continue;                     // "^^^^^^"
+        auto it = pos.find(t);
+        if (it == pos.end()) throw std::runtime_error("a taxid of the index is missing from the content file: " + std::to_string(t));
+        const uint32_t lo = (uint32_t)(k & low_mask);
+        out6.insert(out6.end(), reinterpret_cast<const char *>(&lo), reinterpret_cast<const char *>(&lo) + 4);
+        out6.insert(out6.end(), reinterpret_cast<const char *>(&it->second), reinterpret_cast<const char *>(&it->second) + 2);
+        ++count;
+        if ((k >> 30) != current) { put_run(current, count - 1); current = k >> 30; count = 1; }
+    }
+    put_run(current, count != 1 ? count - 1 : 1);
+    write_padded(a.out, out6.data(), out6.size(), 2101248);
+    { std::ofstream f(a.out + "_info.txt"); f << out6.size() / 6 << std::endl << 3; }
+    write_padded(a.out + "_trie", trie.data(), trie.size(), 2101248);
+    { std::ofstream f(a.out + "_trie.txt"); f << trie.size() / 12; }
+    {
+        std::ifstream src(a.index + "_f.txt", std::ios::binary);
+        std::ofstream dst(a.out + "_f.txt", std::ios::binary);
+        dst << src.rdbuf();
+    }
+    return 0;
 }
 
 // trie / getFrequency / delete / merge (main.cpp:1422-1458, 1336-1362, 770-805, 877-977): an index file's records join a build on the
@@ -747,6 +800,7 @@ int main(int argc, char **argv)
         if (a.mode == "build" || a.mode == "update") rc = run_build(a);
         else if (a.mode == "identify") rc = run_identify(a);
         else if (a.mode == "identify_multiple") rc = run_identify_multiple(a);
+        else if (a.mode == "half") rc = run_half(a);
         else if (a.mode == "trie" || a.mode == "getFrequency" || a.mode == "delete" || a.mode == "merge") rc = run_index_mode(a);
         else if (a.mode == "-h" || a.mode == "--help") usage();
         else throw std::runtime_error("mode not supported by kasa_b200: " + a.mode + " (build, identify)");

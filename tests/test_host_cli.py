@@ -400,3 +400,20 @@ def test_cli_identify_with_a_halved_index(tmp_path):
         assert rc == 0, err
         outs.append((open(tmp_path / (tag + ".jsonl")).read(), open(tmp_path / (tag + ".csv")).read()))
     assert outs[0] == outs[1]
+
+
+def test_cli_half_mode_matches_the_reference(tmp_path):
+    """`half` (main.cpp:1465-1474): a streaming pass on the host, no device needed.  Records, prefix table and info file equal the ones
+    `kASA half` wrote (modes_sha256.txt); the frequency file is the old one."""
+    want = _modes()
+    idx = _write_index("k12", tmp_path)
+    h = str(tmp_path / "idxh")
+    rc, out, err = _cli("half", "-c", _g("k12", "content.txt"), "-d", idx, "-o", h)
+    assert rc == 0, err
+    info = open(h + "_info.txt").read().split()
+    assert info[1] == "3"
+    assert _records_sha(h, rec=6) == want["half/idxh"]
+    assert _trie_sha(h) == want["half/idxh_trie"]
+    assert open(h + "_f.txt").read() == G.text("k12", "idx_f.txt")
+    rc, out, err = _cli("half", "-c", _g("k12", "content.txt"), "-d", idx, "-o", idx)
+    assert rc != 0 and b"same" in err
