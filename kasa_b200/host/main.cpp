@@ -69,7 +69,7 @@ std::vector<std::string> list_directory(const std::string &path)
 struct Args {
     std::string mode, content, index, input, in1, in2, profile, rtt, tmp, alphabet_file, alphabet_id, out, first_index, second_index, deleted, content_out;
     int k_high = 12, k_low = 7, highest_k = 12, beasts = 3, device = 0, gpus = 1;
-    bool six = false, one = false, verbose = false, exact = false;
+    bool six = false, one = false, verbose = false, exact = false, show = false;
     float threshold = 0.f;
     std::string format = "json";
     uint32_t batch_reads = 1u << 20;
@@ -81,6 +81,7 @@ struct Args {
     std::cout << "kasa_b200 <build|identify> -c <content> -d <index> [-i <input> | -1 <fq> -2 <fq>] [-p <profile.csv>] [-q <per-read out>]\n"
                  "kasa_b200 identify_multiple -c <content> -d <index> -i <folder> [-p <profile prefix>] [-q <per-read prefix>] (identify's flags)\n"
                  "kasa_b200 update -c <content> -d <index> -i <new sequences> [-o <out>] (the content file names the new accessions)\n"
+                 "kasa_b200 --parameters <parameters.yaml>     (kASA's parameter file instead of flags)\n"
                  "kasa_b200 half -c <content> -d <index> -o <out>     (6-byte records, the upper six letters in <out>_trie)\n"
                  "kasa_b200 trie -d <index> | getFrequency -c <content> -d <index> | delete -c <content> -d <index> -o <out> -l <delnodes.dmp>\n"
                  "          | merge -c <content> --firstIndex <a> --secondIndex <b> -o <out>     (indexes sharing one content file)\n"
@@ -90,10 +91,79 @@ struct Args {
     std::exit(0);
 }
 
+// `--parameters <file>` (main.cpp:264, Utilities::readParametersFromYaml Utilities.hpp:1114-): the flat "Key: value" lines of kASA's
+// parameters.yaml; section headers and comments are skipped, quotes dropped.  Keys of features this front end does not have are
+// accepted when they are off and refused when they are on.
+Args parse_yaml(const std::string &path)
+{
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("Config file not found!");
+    Args a;
+    std::string line;
+    auto truth = [](const std::string &v) { return v == "true" || v == "True" || v == "1"; };
+    bool one = false, three = false, six = false;
+    while (std::getline(f, line)) {
+        const size_t b = line.find_first_not_of(" \t");
+        if (b == std::string::npos || line[b] == '#') continue;
+        const size_t colon = line.find(':', b);
+        if (colon == std::string::npos) continue;
+        std::string key = line.substr(b, colon - b), val = line.substr(colon + 1);
+        key.erase(std::remove(key.begin(), key.end(), '"'), key.end());
+        val.erase(std::remove(val.begin(), val.end(), '"'), val.end());
+        val.erase(0, std::min(val.find_first_not_of(" \t"), val.size()));
+        while (!val.empty() && (val.back() == '\r' || val.back() == ' ' || val.back() == '\t')) val.pop_back();
+        if (key == "Mode") a.mode = val;
+        else if (key == "Index") a.index = val;
+        else if (key == "ContentFile") a.content = val;
+        else if (key == "kHigh") { if (!val.empty()) a.k_high = std::stoi(val); }
+        else if (key == "kLow") { if (!val.empty()) a.k_low = std::stoi(val); }
+        else if (key == "FilePathForTemporaryFiles") a.tmp = val;
+        else if (key == "Verbose") a.verbose = truth(val);
+        else if (key == "AlphabetFile") a.alphabet_file = val;
+        else if (key == "AlphabetIndex") a.alphabet_id = val;
+        else if (key == "InputFileOrFolder") a.input = val;
+        else if (key == "PairedEnd-First") a.in1 = val;
+        else if (key == "PairedEnd-Second") a.in2 = val;
+        else if (key == "One") one = truth(val);
+        else if (key == "Three") three = truth(val);
+        else if (key == "Six") six = truth(val);
+        else if (key == "ProfileOutputfile") a.profile = val;
+        else if (key == "ReadIDtoTaxIDOutputfile") a.rtt = val;
+        else if (key == "ReadIDtoTaxIDOutputFormat") { if (!val.empty()) a.format = val; }
+        else if (key == "NumberOfTaxaPerRead") { if (!val.empty()) { a.beasts = std::stoi(val); if (a.beasts == 0) a.beasts = 1; } }
+        else if (key == "ThresholdForScore") { if (!val.empty()) a.threshold = std::stof(val); }
+        else if (key == "FileWithDeletedTaxa") a.deleted = val;
+        else if (key == "ContentFile-First" || key == "ContentFile-Second") { if (a.content.empty()) a.content = val; }
+        else if (key == "ContentFile-Out") a.content_out = val;
+        else if (key == "FirstOldIndex") a.first_index = val;
+        else if (key == "SecondOldIndex") a.second_index = val;
+        else if (key == "NewIndex") a.out = val;
+        else if (key == "AlreadyTranslated" || key == "UniqueKmersOnly" || key == "PrintCoverage" || key == "Coherence" || key == "Spaced" || key == "Visualize" ||
+                 key == "Debug" || key == "TaxIDsAreStrings") {
+            if (truth(val)) throw std::runtime_error("parameter " + key + " is not supported by kasa_b200");
+        }
+        else if (key == "Filter") { if (!val.empty() && val != "_ _") throw std::runtime_error("parameter Filter is not supported by kasa_b200"); }
+        // NumberOfThreads, AvailableRAMinGB, CallIndex, UseRAMOnly, TaxonomicLevel, AccessionToTaxIDFileOrFolder, TaxonomyFolder, IGotSpace,
+        // ErrorThreshold, CoherenceThreshold, Gzip, ShrinkingStrategy, ShrinkPercentage, SpacedMaskIdx: nothing to set here
+    }
+    if (one + three + six > 1) throw std::runtime_error("Only one of the frames One / Three / Six can be true");
+    a.one = one; a.six = six;
+    if (a.alphabet_id.empty() || a.alphabet_file.empty()) { a.alphabet_file.clear(); a.alphabet_id.clear(); }
+    if (a.k_high > 12) a.highest_k = 25;
+    if (a.mode.empty()) throw std::runtime_error("the parameter file names no Mode");
+    return a;
+}
+
 Args parse(int argc, char **argv)
 {
     Args a;
     if (argc < 2) usage();
+    if (std::string(argv[1]) == "--parameters") {
+        if (argc < 3) throw std::runtime_error("missing value after --parameters");
+        a = parse_yaml(argv[2]);
+        if (argc > 3 && std::string(argv[3]) == "--show") a.show = true;          // prints what was read (tests)
+        return a;
+    }
     a.mode = argv[1];
     for (int i = 2; i < argc; ++i) {
         const std::string p = argv[i];
@@ -787,6 +857,14 @@ int main(int argc, char **argv)
         const auto t0 = std::chrono::steady_clock::now();
         Args a = parse(argc, argv);
         int rc;
+        if (a.show) {                                       // host-only: the parameters as read from --parameters
+            std::cout << "mode=" << a.mode << "\nindex=" << a.index << "\ncontent=" << a.content << "\ninput=" << a.input << "\nin1=" << a.in1 << "\nin2=" << a.in2
+                      << "\nprofile=" << a.profile << "\nrtt=" << a.rtt << "\nformat=" << a.format << "\nk=" << a.k_high << " " << a.k_low << "\nhighest_k=" << a.highest_k
+                      << "\nframes=" << (a.one ? 1 : a.six ? 6 : 3) << "\nbeasts=" << a.beasts << "\nthreshold=" << a.threshold << "\nalphabet=" << a.alphabet_file << " "
+                      << a.alphabet_id << "\nout=" << a.out << "\nfirst=" << a.first_index << "\nsecond=" << a.second_index << "\ndeleted=" << a.deleted
+                      << "\nverbose=" << a.verbose << std::endl;
+            return 0;
+        }
         if (a.mode == "host-build-strings") {              // host-only (no device): the strings `build` would push
             Content c = load_content(a.content);
             fasta_build_strings(slurp(a.input), c.acc2tax, a.highest_k, a.six,

@@ -417,3 +417,51 @@ def test_cli_half_mode_matches_the_reference(tmp_path):
     assert open(h + "_f.txt").read() == G.text("k12", "idx_f.txt")
     rc, out, err = _cli("half", "-c", _g("k12", "content.txt"), "-d", idx, "-o", idx)
     assert rc != 0 and b"same" in err
+
+
+def _yaml(path, **kv):
+    """kASA's parameters.yaml (reference repo root): sections with flat `Key: value` lines, strings quoted."""
+    base = {"Mode": '"build"', "Index": '""', "ContentFile": '""', "kHigh": 12, "kLow": 7, "NumberOfThreads": 2, "AvailableRAMinGB": 5,
+            "FilePathForTemporaryFiles": '""', "CallIndex": 0, "Verbose": "false", "AlphabetFile": '""', "AlphabetIndex": 0,
+            "InputFileOrFolder": '""', "PairedEnd-First": '""', "PairedEnd-Second": '""', "AlreadyTranslated": "false",
+            "One": "false", "Three": "true", "Six": "false", "ProfileOutputfile": '""', "ReadIDtoTaxIDOutputfile": '""',
+            "ReadIDtoTaxIDOutputFormat": '"json"', "UseRAMOnly": "false", "NumberOfTaxaPerRead": 3, "UniqueKmersOnly": "false",
+            "ThresholdForScore": 0.0, "PrintCoverage": "false", "Filter": '"_ _"', "FileWithDeletedTaxa": '""', "ShrinkingStrategy": 2,
+            "FirstOldIndex": '""', "SecondOldIndex": '""', "NewIndex": '""'}
+    base.update(kv)
+    with open(path, "w") as f:
+        f.write("# config file for kASA\n\nGeneral: \n # modes available: build, identify, ...\n")
+        for k, v in base.items():
+            f.write(" %s: %s\n" % (k, v))
+    return str(path)
+
+
+def test_cli_parameters_file_is_read_like_the_flags(tmp_path):
+    """`--parameters <yaml>` (main.cpp:264, Utilities.hpp:1114-): the keys of kASA's parameters.yaml land where the flags land."""
+    y = _yaml(tmp_path / "p.yaml", Mode='"identify"', Index='"/data/idx"', ContentFile='"/data/content.txt"', kHigh=11, kLow=8, Verbose="true",
+              InputFileOrFolder='"/data/reads.fq"', Three="false", Six="true", ProfileOutputfile='"/out/p.csv"', ReadIDtoTaxIDOutputfile='"/out/q.jsonl"',
+              ReadIDtoTaxIDOutputFormat='"jsonl"', NumberOfTaxaPerRead=5, ThresholdForScore=0.25)
+    rc, out, err = _cli("--parameters", y, "--show")
+    assert rc == 0, err
+    got = dict(l.split("=", 1) for l in out.decode().splitlines() if "=" in l)
+    assert got["mode"] == "identify" and got["index"] == "/data/idx" and got["content"] == "/data/content.txt" and got["input"] == "/data/reads.fq"
+    assert got["k"] == "11 8" and got["frames"] == "6" and got["format"] == "jsonl" and got["beasts"] == "5" and got["threshold"] == "0.25"
+    assert got["profile"] == "/out/p.csv" and got["rtt"] == "/out/q.jsonl" and got["verbose"] == "1" and got["highest_k"] == "12"
+    # features this front end does not have are refused when switched on; two frames at once as well
+    rc, out, err = _cli("--parameters", _yaml(tmp_path / "q.yaml", PrintCoverage="true"), "--show")
+    assert rc != 0 and b"PrintCoverage" in err
+    rc, out, err = _cli("--parameters", _yaml(tmp_path / "r.yaml", Six="true"), "--show")
+    assert rc != 0 and b"frames" in err
+    rc, out, err = _cli("--parameters", _yaml(tmp_path / "s.yaml", kHigh=25, Mode='"build"'), "--show")
+    assert rc == 0 and b"highest_k=25" in out
+
+
+def test_cli_parameters_file_drives_a_mode(tmp_path):
+    """the `half` mode run from a parameter file (host only): the same files as with flags."""
+    want = _modes()
+    idx = _write_index("k12", tmp_path)
+    h = str(tmp_path / "idxh")
+    y = _yaml(tmp_path / "p.yaml", Mode='"half"', Index='"%s"' % idx, ContentFile='"%s"' % _g("k12", "content.txt"), NewIndex='"%s"' % h)
+    rc, out, err = _cli("--parameters", y)
+    assert rc == 0, err
+    assert _records_sha(h, rec=6) == want["half/idxh"] and _trie_sha(h) == want["half/idxh_trie"]
