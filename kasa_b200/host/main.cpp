@@ -83,6 +83,7 @@ struct Args {
                  "kasa_b200 update -c <content> -d <index> -i <new sequences> [-o <out>] (the content file names the new accessions)\n"
                  "kasa_b200 --parameters <parameters.yaml>     (kASA's parameter file instead of flags)\n"
                  "kasa_b200 half -c <content> -d <index> -o <out>     (6-byte records, the upper six letters in <out>_trie)\n"
+                 "kasa_b200 redundancy -c <content> -d <index> [-v]\n"
                  "kasa_b200 trie -d <index> | getFrequency -c <content> -d <index> | delete -c <content> -d <index> -o <out> -l <delnodes.dmp>\n"
                  "          | merge -c <content> --firstIndex <a> --secondIndex <b> -o <out>     (indexes sharing one content file)\n"
                  "          [-k <high> <low>] [--kH <12|25>] [--six | --one] [--json|--jsonl|--tsv|--kraken] [-b <n>] [--threshold <f>] [-v]\n"
@@ -346,6 +347,38 @@ int run_half(const Args &a)
         std::ofstream dst(a.out + "_f.txt", std::ios::binary);
         dst << src.rdbuf();
     }
+    return 0;
+}
+
+// `redundancy` (main.cpp:1364-1420, Shrink::histogram Shrink.hpp:33-70): how many taxa the k-mers of an index have — one streaming pass
+// on the host.  hist[c] = k-mers listed with c taxa; the cutoff is the smallest c up to which 99 % of the index's records lie.
+int run_redundancy(const Args &a)
+{
+    int bits = 64;
+    const std::vector<char> rec = read_index_records(a.index, &bits);         // (refuses halved indices)
+    const size_t rb = bits == 128 ? 20 : 12, kb = rb - 4;
+    const uint64_t n = rec.size() / rb;
+    Content content = load_content(a.content.empty() ? a.index + "_content.txt" : a.content);
+    const uint32_t n_tax = (uint32_t)content.taxids.size();                      // content lines + 1, as the reference counts them
+    std::vector<uint64_t> hist(n_tax + 2, 0);
+    uint64_t unique = 0;
+    uint32_t counter = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (i == 0 || std::memcmp(rec.data() + i * rb, rec.data() + (i - 1) * rb, kb) == 0) ++counter;
+        else { hist[std::min<uint32_t>(counter, n_tax + 1)]++; counter = 1; ++unique; }
+    }
+    hist[std::min<uint32_t>(counter, n_tax + 1)]++;
+    if (a.verbose) std::cout << "Number of unique k-mers: " << unique << std::endl << "Histogram\nFrequency Counts Percentage" << std::endl;
+    double percentage = 0.0;
+    uint32_t cutoff = 0;
+    for (uint32_t i = 1; i < n_tax + 1; ++i) {
+        if (a.verbose && hist[i]) std::cout << i << " " << hist[i] << " " << 100.0 * (double)hist[i] * i / (double)n << std::endl;
+        percentage += (double)hist[i] * i / (double)n;
+        if (percentage >= 0.99 && cutoff == 0) cutoff = i;
+    }
+    if (cutoff == 1) std::cout << "OUT: 99% of the k-mers in your index have only one taxon. Using unique frequencies makes sense." << std::endl;
+    else if (cutoff < 4) std::cout << "OUT: 99% of the k-mers in your index have " << cutoff << " or less taxa. Using unique frequencies could make sense." << std::endl;
+    else std::cout << "OUT: 99% of the k-mers in your index have " << cutoff << " or less taxa. You should consider looking at the non-unique frequencies as well." << std::endl;
     return 0;
 }
 
@@ -879,6 +912,7 @@ int main(int argc, char **argv)
         else if (a.mode == "identify") rc = run_identify(a);
         else if (a.mode == "identify_multiple") rc = run_identify_multiple(a);
         else if (a.mode == "half") rc = run_half(a);
+        else if (a.mode == "redundancy") rc = run_redundancy(a);
         else if (a.mode == "trie" || a.mode == "getFrequency" || a.mode == "delete" || a.mode == "merge") rc = run_index_mode(a);
         else if (a.mode == "-h" || a.mode == "--help") usage();
         else throw std::runtime_error("mode not supported by kasa_b200: " + a.mode + " (build, identify)");

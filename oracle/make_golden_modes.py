@@ -15,6 +15,7 @@ The reference binary (`kASA_scalar`) runs on the committed k12 g
     update        -c content.txt -d a -i b.fa -o u         -> u, u_info.txt, u_trie, u_trie.txt, u_f.txt (Update.hpp:99-)
     half          -c content.txt -d idx -o idxh            -> idxh (6-byte records), idxh_info.txt, idxh_trie, idxh_trie.txt
                                                                                               (Shrink.hpp:78-143)
+    redundancy    -c content.txt -d idx -v                 -> stdout: histogram of taxa per k-mer (Shrink.hpp:33-70)
 Stored: one line per produced file, `<case>/<file> <bytes that count> <sha256>` (index and trie files are hashed over their
 records, without the STXXL block padding), the deleted taxids and how ref.fa was cut.  tests/test_host_cli.py runs
 kasa_b200_cli with the same commands and compares the same hashes.
@@ -149,8 +150,12 @@ def main():
     print("identify with the halved index == identify with the full index:", res["idx"] == res["idxh"])
     assert res["idx"] == res["idxh"]
     out.append(("half/identify_equals_full_index", 1, hashlib.sha256(res["idxh"][0].encode()).hexdigest()))
+    # ---- redundancy: the histogram of taxa per k-mer and the advice the binary prints
+    red = run([REF, "redundancy", "-c", "content.txt", "-d", "idx", "-m", "4", "-t", "tmp/", "-v"], work)
+    keep = [l for l in red.splitlines() if not l.startswith("OUT: kASA version") and "STXXL" not in l and "redundancy -c" not in l and not l.startswith("OUT: Time")]
+    open(os.path.join(work, "redundancy.txt"), "w").write("\n".join(keep) + "\n")
     os.makedirs(os.path.join(GOLD, "modes"), exist_ok=True)
-    for name in ("del_f.txt", "m_f.txt", "del.dmp"):          # the small text files are kept as they are
+    for name in ("del_f.txt", "m_f.txt", "del.dmp", "redundancy.txt"):          # the small text files are kept as they are
         shutil.copy(os.path.join(work, name), os.path.join(GOLD, "modes", name))
     with open(os.path.join(GOLD, "modes_sha256.txt"), "w") as f:
         f.write("# written by oracle/make_golden_modes.py from kASA_scalar; deleted taxids: %s; ref.fa cut after half of its records\n"

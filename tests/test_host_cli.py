@@ -465,3 +465,12 @@ def test_cli_parameters_file_drives_a_mode(tmp_path):
     rc, out, err = _cli("--parameters", y)
     assert rc == 0, err
     assert _records_sha(h, rec=6) == want["half/idxh"] and _trie_sha(h) == want["half/idxh_trie"]
+
+
+def test_cli_redundancy_mode_prints_what_the_reference_prints(tmp_path):
+    """`redundancy -v` (main.cpp:1364-1420, Shrink::histogram): histogram of taxa per k-mer and the advice line, host only."""
+    idx = _write_index("k12", tmp_path)
+    rc, out, err = _cli("redundancy", "-c", _g("k12", "content.txt"), "-d", idx, "-v")
+    assert rc == 0, err
+    got = [l for l in out.decode().splitlines() if not l.startswith("OUT: Time")]
+    assert got == G.text("k12", os.path.join("modes", "redundancy.txt")).splitlines()
