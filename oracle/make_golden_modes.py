@@ -141,6 +141,14 @@ def main():
     run([REF, "half", "-c", "content.txt", "-d", "idx", "-o", "idxh", "-m", "4", "-t", "tmp/"], work)
     out.append(("half/idxh",) + record_hash(work, "idxh", 6))
     out.append(("half/idxh_trie",) + trie_hash(work, "idxh"))
+    # the same on the index cut after a prefix run of four records: the reference closes the last run one short (Shrink.hpp:131-136)
+    CUT = 45491
+    open(os.path.join(work, "cut"), "wb").write(open(os.path.join(work, "idx"), "rb").read()[:CUT * 12])
+    open(os.path.join(work, "cut_info.txt"), "w").write(str(CUT))
+    shutil.copy(os.path.join(work, "idx_f.txt"), os.path.join(work, "cut_f.txt"))
+    run([REF, "half", "-c", "content.txt", "-d", "cut", "-o", "cuth", "-m", "4", "-t", "tmp/"], work)
+    out.append(("half/cuth_of_the_first_%d_records" % CUT,) + record_hash(work, "cuth", 6))
+    out.append(("half/cuth_trie",) + trie_hash(work, "cuth"))
     open(os.path.join(work, "reads.fq"), "w").write("".join(fq))
     res = {}
     for name in ("idx", "idxh"):

@@ -417,6 +417,15 @@ def test_cli_half_mode_matches_the_reference(tmp_path):
     assert open(h + "_f.txt").read() == G.text("k12", "idx_f.txt")
     rc, out, err = _cli("half", "-c", _g("k12", "content.txt"), "-d", idx, "-o", idx)
     assert rc != 0 and b"same" in err
+    # the index cut after a prefix run of four records (the last run is written one short, as the reference writes it)
+    cut = [int(k.split("_")[-2]) for k in want if k.startswith("half/cuth_of_the_first_")][0]
+    c = str(tmp_path / "cut")
+    open(c, "wb").write(G.gz("k12", "idx.gz")[:cut * 12])
+    open(c + "_info.txt", "w").write(str(cut))
+    open(c + "_f.txt", "w").write(G.text("k12", "idx_f.txt"))
+    rc, out, err = _cli("half", "-c", _g("k12", "content.txt"), "-d", c, "-o", c + "h")
+    assert rc == 0, err
+    assert _records_sha(c + "h", rec=6) == want["half/cuth_of_the_first_%d_records" % cut] and _trie_sha(c + "h") == want["half/cuth_trie"]
 
 
 def _yaml(path, **kv):
